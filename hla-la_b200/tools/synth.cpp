@@ -1,0 +1,571 @@
+// hlala-synth: synthetic PRG directories and seed batches for tests and bench.py.
+//
+// There is no PRG_MHC_GRCh38_withIMGT package, bwa or BAM in the build image (SURVEY.md finding 5), so the
+// inputs of the hot path are synthesised here in the reference's own on-disk formats:
+//   prg   -> PRG/graph.txt (CODE:/NODES:/EDGES:, Graph.cpp:2225-2327), PRG/segments.txt + segment tables
+//            (HLATyper.cpp:105-216), sequences.txt (processBAM.cpp:1216-1320), translation/<id>.txt
+//            (processBAM.cpp:4395-4416), mapping_PRGonly/referenceGenome.fa, extendedReferenceGenome/*.fa
+//   reads -> a flat seed batch (arrayfile.h) holding what `bwa mem -a -M` + BamTools would hand to
+//            processBAM::alignOneReadPair: per read the primary record's SEQ/QUAL, per chain
+//            (contig, pos, flag, AS, BAM-packed CIGAR).
+// The graph model follows Graph/graphSimulator/simpleGraphSimulator.cpp:142-271 in spirit (scaffold + mutated
+// haplotypes + a large-gap haplotype) with gene blocks carrying allele tables added. Not a port of it.
+#include "../host/arrayfile.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <unordered_map>
+#include <vector>
+
+using namespace hlala;
+
+namespace {
+
+struct Rng {
+    std::mt19937_64 g;
+    explicit Rng(uint64_t s) : g(s) {}
+    double u() { return std::generate_canonical<double, 53>(g); }
+    uint64_t below(uint64_t n) { return (uint64_t)(u() * (double)n) % (n ? n : 1); }
+    bool bern(double p) { return u() < p; }
+    int poisson(double m) { std::poisson_distribution<int> d(m); return d(g); }
+    double normal(double m, double s) { std::normal_distribution<double> d(m, s); return d(g); }
+    char base() { return "ACGT"[below(4)]; }
+    char other(char c) { char b; do { b = base(); } while (b == c); return b; }
+};
+
+void mkdirs(const std::string& p) { std::string cmd = "mkdir -p '" + p + "'"; if (system(cmd.c_str()) != 0) throw std::runtime_error("mkdir failed: " + p); }
+
+std::map<std::string, std::string> parse_args(int argc, char** argv, int first) {
+    std::map<std::string, std::string> a;
+    for (int i = first; i + 1 < argc; i += 2) {
+        std::string k = argv[i];
+        if (k.rfind("--", 0) != 0) throw std::runtime_error("bad argument " + k);
+        a[k.substr(2)] = argv[i + 1];
+    }
+    return a;
+}
+template <class T> T arg(const std::map<std::string, std::string>& a, const std::string& k, T def) {
+    auto it = a.find(k); if (it == a.end()) return def; std::istringstream is(it->second); T v; is >> v; return v;
+}
+std::string sarg(const std::map<std::string, std::string>& a, const std::string& k, const std::string& def) { auto it = a.find(k); return it == a.end() ? def : it->second; }
+
+const char* LOCI[] = {"A", "B", "C", "DQA1", "DQB1", "DRB1", "DPA1", "DPB1", "DRA", "DRB3", "DRB4", "E", "F", "G", "H", "K", "V"};
+
+struct GeneSeg { std::string kind; int num; int64_t s, e; };   // [s,e) in levels
+struct Gene {
+    std::string locus; int64_t s, e; std::vector<GeneSeg> segs;
+    std::vector<std::string> allele_names; std::vector<std::string> alleles;   // symbols over [s,e)
+};
+
+// ------------------------------------------------------------------------------------------------- prg
+int cmd_prg(const std::map<std::string, std::string>& a) {
+    const std::string out = sarg(a, "out", "");
+    if (out.empty()) throw std::runtime_error("--out required");
+    const int64_t N = arg<int64_t>(a, "levels", 25000);
+    const int H = arg<int>(a, "haps", 4);
+    const int K = arg<int>(a, "ctx", 2);
+    const double snp = arg<double>(a, "snp", 0.02);
+    const double delfrac = arg<double>(a, "delfrac", 0.3);
+    const int n_genes = arg<int>(a, "genes", 2);
+    const int n_alleles = arg<int>(a, "alleles", 64);
+    const int allele_contigs = arg<int>(a, "allele-contigs", 4);
+    const double gapstart = arg<double>(a, "gapstart", 0.002);
+    const double insrun = arg<double>(a, "insrun", 0.001);
+    const uint64_t seed = arg<uint64_t>(a, "seed", 0xB200);
+    Rng R(seed);
+
+    // --- haplotype symbol matrix
+    std::vector<std::string> hap(H, std::string((size_t)N, 'A'));
+    for (int64_t l = 0; l < N; l++) hap[0][l] = R.base();
+    for (int h = 1; h < H; h++) {
+        for (int64_t l = 0; l < N; l++) {
+            char c = hap[0][l];
+            if (R.bern(snp)) c = R.bern(delfrac) ? '_' : R.other(c);
+            hap[h][l] = c;
+        }
+    }
+    if (H >= 3) {   // the large-gap haplotype (simpleGraphSimulator.cpp: Poisson(10)-length gaps)
+        std::string& g = hap[H - 1];
+        for (int64_t l = 1; l < N - 1; l++) {
+            if (R.bern(gapstart)) {
+                int len = 1 + R.poisson(10);
+                if (R.bern(0.1)) len += 40 + (int)R.below(160);
+                for (int i = 0; i < len && l + i < N - 1; i++) g[l + i] = '_';
+                l += len;
+            }
+        }
+    }
+    // insertion runs: levels where the scaffold itself carries '_' and only some haplotypes have a base
+    for (int64_t l = 50; l < N - 50; l++) {
+        if (R.bern(insrun)) {
+            int len = 1 + (int)R.below(6);
+            uint32_t mask = 0;
+            for (int h = 1; h < H; h++) if (R.bern(0.4)) mask |= 1u << h;
+            for (int i = 0; i < len; i++) {
+                for (int h = 0; h < H; h++) hap[h][l + i] = ((mask >> h) & 1) ? R.base() : '_';
+            }
+            l += len + 5;
+        }
+    }
+    // keep both ends clean so every path has bases there
+    for (int h = 0; h < H; h++) for (int64_t l = 0; l < 20 && l < N; l++) { hap[h][l] = hap[0][l] == '_' ? 'A' : hap[0][l]; hap[h][N - 1 - l] = hap[0][N - 1 - l] == '_' ? 'C' : hap[0][N - 1 - l]; }
+    for (int64_t l = 0; l < 20 && l < N; l++) { if (hap[0][l] == '_') hap[0][l] = 'A'; if (hap[0][N - 1 - l] == '_') hap[0][N - 1 - l] = 'C'; }
+
+    // --- gene blocks
+    std::vector<Gene> genes;
+    const int seglen[5] = {100, 270, 150, 276, 100};
+    const char* segkind[5] = {"intron", "exon", "intron", "exon", "intron"};
+    const int segnum[5] = {1, 2, 2, 3, 3};
+    int64_t glen = 0; for (int i = 0; i < 5; i++) glen += seglen[i];
+    if (n_genes > 0 && (int64_t)n_genes * (glen + 400) + 400 > N) throw std::runtime_error("too many genes for this number of levels");
+    for (int gi = 0; gi < n_genes; gi++) {
+        Gene G; G.locus = LOCI[gi % 17];
+        int64_t stride = N / (n_genes + 1);
+        G.s = stride * (gi + 1) - glen / 2; G.e = G.s + glen;
+        int64_t p = G.s;
+        for (int i = 0; i < 5; i++) { G.segs.push_back({segkind[i], segnum[i], p, p + seglen[i]}); p += seglen[i]; }
+        // allele 0 = scaffold without gaps in the block; further alleles copy an earlier one and mutate exon columns
+        std::string base0((size_t)glen, 'A');
+        for (int64_t i = 0; i < glen; i++) { char c = hap[0][G.s + i]; base0[i] = (c == '_') ? R.base() : c; }
+        G.alleles.push_back(base0);
+        for (int ai = 1; ai < n_alleles; ai++) {
+            std::string s = G.alleles[R.below(G.alleles.size())];
+            int nmut = 1 + (int)R.below(6);
+            for (int m = 0; m < nmut; m++) {
+                const GeneSeg& sg = G.segs[R.bern(0.8) ? (R.bern(0.5) ? 1 : 3) : (int)R.below(5)];
+                int64_t pos = sg.s - G.s + (int64_t)R.below(sg.e - sg.s);
+                if (R.bern(0.03) && pos > 5 && pos < glen - 5) s[pos] = '_';
+                else s[pos] = R.other(s[pos] == '_' ? 'A' : s[pos]);
+            }
+            G.alleles.push_back(s);
+        }
+        // unique sequences only would be nicer but identical alleles exercise the typer's clustering (HLATyper.cpp:1317-1372)
+        for (int ai = 0; ai < n_alleles; ai++) {
+            char nm[64]; snprintf(nm, sizeof nm, "%s*%02d:%02d", G.locus.c_str(), 1 + ai / 50, 1 + ai % 50);
+            G.allele_names.push_back(nm);
+        }
+        // haplotypes carry one allele each over the block
+        for (int h = 0; h < H; h++) {
+            const std::string& al = G.alleles[h == 0 ? 0 : R.below(G.alleles.size())];
+            for (int64_t i = 0; i < glen; i++) hap[h][G.s + i] = al[i];
+        }
+        genes.push_back(std::move(G));
+    }
+
+    // --- level names / segments
+    std::vector<std::string> level_name((size_t)N);
+    struct SegFile { std::string file; int64_t s, e; int gene; int seg; };
+    std::vector<SegFile> segfiles;
+    {
+        int segno = 0; int64_t l = 0; size_t gi = 0;
+        const int64_t chunk = 50000;
+        while (l < N) {
+            int64_t next_gene_s = gi < genes.size() ? genes[gi].s : N;
+            if (l < next_gene_s) {
+                int64_t e = std::min(next_gene_s, l + chunk);
+                char fn[128]; snprintf(fn, sizeof fn, "%d_intergenic_r%d_1_segment_1.txt", segno, segno);
+                segfiles.push_back({fn, l, e, -1, -1});
+                for (int64_t i = l; i < e; i++) { char nm[96]; snprintf(nm, sizeof nm, "%d_ig_r%d_%lld", segno, segno, (long long)(i - l)); level_name[i] = nm; }
+                l = e; segno++;
+            } else {
+                const Gene& G = genes[gi];
+                for (size_t si = 0; si < G.segs.size(); si++) {
+                    const GeneSeg& sg = G.segs[si];
+                    char fn[128]; snprintf(fn, sizeof fn, "%d_gene_%s_%d_%s_%d.txt", segno, G.locus.c_str(), (int)si + 1, sg.kind.c_str(), sg.num);
+                    segfiles.push_back({fn, sg.s, sg.e, (int)gi, (int)si});
+                    for (int64_t i = sg.s; i < sg.e; i++) { char nm[96]; snprintf(nm, sizeof nm, "%d_gene_%s_%s%d_%lld", segno, G.locus.c_str(), sg.kind.c_str(), sg.num, (long long)(i - sg.s)); level_name[i] = nm; }
+                    segno++;
+                }
+                l = G.e; gi++;
+            }
+        }
+    }
+
+    mkdirs(out + "/PRG"); mkdirs(out + "/translation"); mkdirs(out + "/mapping_PRGonly"); mkdirs(out + "/extendedReferenceGenome");
+
+    {
+        std::ofstream sf(out + "/PRG/segments.txt");
+        for (const SegFile& s : segfiles) {
+            sf << s.file << "\n";
+            std::ofstream f(out + "/PRG/" + s.file);
+            f << "IndividualID";
+            for (int64_t i = s.s; i < s.e; i++) f << " " << level_name[i];
+            f << "\n";
+            if (s.gene >= 0) {
+                const Gene& G = genes[s.gene];
+                for (size_t ai = 0; ai < G.alleles.size(); ai++) {
+                    f << G.allele_names[ai];
+                    for (int64_t i = s.s; i < s.e; i++) f << " " << G.alleles[ai][i - G.s];
+                    f << "\n";
+                }
+            } else {
+                for (int h = 0; h < H; h++) { f << "hap" << h; for (int64_t i = s.s; i < s.e; i++) f << " " << hap[h][i]; f << "\n"; }
+            }
+        }
+    }
+
+    // --- graph: nodes keyed by (level, K-symbol left context); paths = haplotypes + alleles inside their blocks
+    {
+        FILE* gf = fopen((out + "/PRG/graph.txt").c_str(), "w");
+        if (!gf) throw std::runtime_error("cannot write graph.txt");
+        std::vector<char> big(1 << 22); setvbuf(gf, big.data(), _IOFBF, big.size());
+        std::string code_lines, node_lines, edge_lines;
+        // stream three sections through temp strings would need O(N) memory; write CODE first in a pre-pass
+        // (codes depend only on the per-level emission sets, recomputed below in the same order).
+        auto sym_of = [&](int path, int64_t l) -> char {
+            if (path < H) return hap[path][l];
+            return 0;
+        };
+        (void)sym_of;
+        // Pre-compute per-level list of (path symbol) lazily: iterate levels once, buffering node/edge text in files.
+        std::string tmpN = out + "/PRG/.nodes.tmp", tmpE = out + "/PRG/.edges.tmp";
+        FILE* nf = fopen(tmpN.c_str(), "w"); FILE* ef = fopen(tmpE.c_str(), "w");
+        std::vector<char> bigN(1 << 22), bigE(1 << 22); setvbuf(nf, bigN.data(), _IOFBF, bigN.size()); setvbuf(ef, bigE.data(), _IOFBF, bigE.size());
+        fprintf(gf, "CODE:\n");
+        int64_t node_id = 0, edge_id = 0;
+        // current nodes per context at this level
+        std::map<std::string, int64_t> cur, nxt;
+        cur[""] = ++node_id; fprintf(nf, "%lld|||0|||0\n", (long long)node_id);
+        size_t gene_i = 0;
+        auto path_sym = [&](int gene, int ai, int64_t l) -> char {   // allele path: allele inside block, scaffold outside
+            const Gene& G = genes[gene];
+            if (l >= G.s && l < G.e) return G.alleles[ai][l - G.s];
+            return hap[0][l];
+        };
+        for (int64_t l = 0; l < N; l++) {
+            while (gene_i < genes.size() && l >= genes[gene_i].e + K) gene_i++;
+            int active_gene = -1;
+            if (gene_i < genes.size() && l >= genes[gene_i].s && l < std::min<int64_t>(N, genes[gene_i].e + K)) active_gene = (int)gene_i;
+            nxt.clear();
+            std::map<std::tuple<int64_t, int64_t, char>, int> seen_edges;
+            std::map<char, int> codes;
+            auto ctx_at = [&](auto&& symf, int64_t lev) { std::string c; for (int64_t j = std::max<int64_t>(0, lev - K); j < lev; j++) c.push_back(symf(j)); return c; };
+            auto add_path = [&](auto&& symf) {
+                std::string cfrom = ctx_at(symf, l), cto = ctx_at(symf, l + 1);
+                auto itf = cur.find(cfrom);
+                if (itf == cur.end()) throw std::runtime_error("internal: path lost its node");
+                auto itt = nxt.find(cto);
+                if (itt == nxt.end()) { itt = nxt.emplace(cto, ++node_id).first; fprintf(nf, "%lld|||%lld|||%d\n", (long long)node_id, (long long)(l + 1), (l + 1 == N) ? 1 : 0); }
+                char em = symf(l);
+                auto key = std::make_tuple(itf->second, itt->second, em);
+                if (!seen_edges.count(key)) {
+                    seen_edges[key] = 1;
+                    if (!codes.count(em)) { int c = '0' + (int)codes.size() + 1; codes[em] = c; fprintf(gf, "%s|||%c|||%d\n", level_name[l].c_str(), em, c); }
+                    fprintf(ef, "%lld|||%s|||1|||%c|||%lld|||%lld||||||0\n", (long long)++edge_id, level_name[l].c_str(), (char)codes[em], (long long)itf->second, (long long)itt->second);
+                }
+            };
+            for (int h = 0; h < H; h++) add_path([&](int64_t j) { return hap[h][j]; });
+            if (active_gene >= 0) {
+                const Gene& G = genes[active_gene];
+                for (size_t ai = 0; ai < G.alleles.size(); ai++) add_path([&](int64_t j) { return path_sym(active_gene, (int)ai, j); });
+            }
+            cur.swap(nxt);
+        }
+        fclose(nf); fclose(ef);
+        auto cat = [&](const std::string& p) { FILE* f = fopen(p.c_str(), "r"); std::vector<char> buf(1 << 22); size_t n; while ((n = fread(buf.data(), 1, buf.size(), f)) > 0) fwrite(buf.data(), 1, n, gf); fclose(f); remove(p.c_str()); };
+        fprintf(gf, "NODES:\n"); cat(tmpN);
+        fprintf(gf, "EDGES:\n"); cat(tmpE);
+        fclose(gf);
+        fprintf(stderr, "hlala-synth: graph with %lld levels, %lld nodes, %lld edges\n", (long long)N, (long long)node_id, (long long)edge_id);
+    }
+
+    // --- contigs
+    {
+        std::ofstream seqs(out + "/sequences.txt");
+        seqs << "SequenceID\tName\tFASTAID\tChr\tStart_1based\tStop_1based\n";
+        std::ofstream fa1(out + "/mapping_PRGonly/referenceGenome.fa"), fa2(out + "/extendedReferenceGenome/extendedReferenceGenome.fa");
+        int id = 10;
+        auto emit = [&](const std::string& name, const std::string& seq, const std::vector<int64_t>& lv) {
+            seqs << id << "\t" << name << "\tPRG_" << id << "\t\t1\t" << seq.size() << "\n";
+            for (std::ofstream* f : {&fa1, &fa2}) { (*f) << ">PRG_" << id << "\n"; for (size_t i = 0; i < seq.size(); i += 80) (*f) << seq.substr(i, 80) << "\n"; }
+            FILE* tf = fopen((out + "/translation/" + std::to_string(id) + ".txt").c_str(), "w");
+            std::vector<char> big(1 << 20); setvbuf(tf, big.data(), _IOFBF, big.size());
+            for (size_t i = 0; i < lv.size(); i++) fprintf(tf, "%lld\n", (long long)lv[i]);   // trailing newline => the reference's parser appends a bogus 0 (Utilities.cpp:644-650)
+            fclose(tf);
+            id++;
+        };
+        for (int h = 0; h < H; h++) {
+            std::string seq; std::vector<int64_t> lv; seq.reserve(N); lv.reserve(N);
+            for (int64_t l = 0; l < N; l++) if (hap[h][l] != '_') { seq.push_back(hap[h][l]); lv.push_back(l); }
+            emit("hap" + std::to_string(h), seq, lv);
+        }
+        for (const Gene& G : genes) {
+            for (int ai = 0; ai < allele_contigs && ai < (int)G.alleles.size(); ai++) {
+                size_t pick = (size_t)ai * G.alleles.size() / std::max(1, allele_contigs);
+                std::string seq; std::vector<int64_t> lv;
+                for (int64_t i = 0; i < G.e - G.s; i++) if (G.alleles[pick][i] != '_') { seq.push_back(G.alleles[pick][i]); lv.push_back(G.s + i); }
+                emit("allele_" + G.allele_names[pick], seq, lv);
+            }
+        }
+    }
+    // The Perl driver only checks that serializedGRAPH exists (HLA-LA.pl:254); our cache lives elsewhere.
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- reads
+struct Contig { int id; std::string name; std::string seq; std::vector<int32_t> lv; bool is_hap; };
+
+std::vector<Contig> load_contigs(const std::string& dir) {
+    std::vector<Contig> cs;
+    std::ifstream s(dir + "/sequences.txt");
+    if (!s.is_open()) throw std::runtime_error("cannot open sequences.txt in " + dir);
+    std::string line; std::getline(s, line);
+    while (std::getline(s, line)) {
+        if (line.empty()) continue;
+        std::vector<std::string> f; std::string cur; for (char c : line) { if (c == '\t') { f.push_back(cur); cur.clear(); } else cur.push_back(c); } f.push_back(cur);
+        Contig c; c.id = atoi(f[0].c_str()); c.name = f[1]; c.is_hap = c.name.rfind("hap", 0) == 0; cs.push_back(c);
+    }
+    std::map<std::string, std::string> fa;
+    { std::ifstream f(dir + "/mapping_PRGonly/referenceGenome.fa"); std::string id; while (std::getline(f, line)) { if (line.empty()) continue; if (line[0] == '>') { id = line.substr(1); fa[id].clear(); } else fa[id] += line; } }
+    for (Contig& c : cs) {
+        c.seq = fa.at("PRG_" + std::to_string(c.id));
+        FILE* tf = fopen((dir + "/translation/" + std::to_string(c.id) + ".txt").c_str(), "r");
+        if (!tf) throw std::runtime_error("missing translation file");
+        long long v; while (fscanf(tf, "%lld", &v) == 1) c.lv.push_back((int32_t)v);
+        fclose(tf);
+        if (c.lv.size() != c.seq.size()) throw std::runtime_error("translation/sequence length mismatch for contig " + c.name);
+    }
+    return cs;
+}
+
+struct ReadItem { char b; char q; int32_t lv; };   // lv == -1: inserted base
+
+struct Chain { int contig = 0; int32_t pos = 0; uint16_t flag = 0; int32_t as = 0; std::vector<uint32_t> cigar; };
+
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_S = 4, OP_H = 5 };
+
+// CIGAR of a read (items with truth levels) against one contig, by level correspondence.
+bool align_to_contig(const std::vector<ReadItem>& rd, const Contig& c, int clipL, int clipR, bool hard, Chain& out) {
+    int first = -1, last = -1;
+    for (int i = 0; i < (int)rd.size(); i++) if (rd[i].lv >= 0) { if (first < 0) first = i; last = i; }
+    if (first < 0) return false;
+    int32_t L0 = rd[first].lv, L1 = rd[last].lv;
+    size_t j = std::lower_bound(c.lv.begin(), c.lv.end(), L0) - c.lv.begin();
+    size_t jend = std::upper_bound(c.lv.begin(), c.lv.end(), L1) - c.lv.begin();
+    if (j >= jend) return false;
+    // per-op expansion: op, and for M whether it matches
+    std::vector<uint8_t> ops; std::vector<uint8_t> mm; ops.reserve(rd.size() + 32);
+    for (int i = 0; i < first; i++) { ops.push_back(OP_S); mm.push_back(0); }
+    int i = first; int32_t pos0 = -1; size_t jj = j;
+    while (i <= last || jj < jend) {
+        if (i <= last && rd[i].lv < 0) { ops.push_back(OP_I); mm.push_back(0); i++; continue; }
+        if (i > last) { ops.push_back(OP_D); mm.push_back(0); jj++; continue; }
+        int32_t rl = rd[i].lv;
+        if (jj < jend && c.lv[jj] < rl) { ops.push_back(OP_D); mm.push_back(0); jj++; }
+        else if (jj < jend && c.lv[jj] == rl) { ops.push_back(OP_M); mm.push_back(rd[i].b != c.seq[jj]); i++; jj++; }
+        else { ops.push_back(OP_I); mm.push_back(0); i++; }
+    }
+    for (int k = last + 1; k < (int)rd.size(); k++) { ops.push_back(OP_S); mm.push_back(0); }
+    // requested clipping: turn the first clipL / last clipR read bases into S, dropping D ops on the way
+    auto clip_side = [&](bool left, int n) {
+        int consumed = 0;
+        if (left) {
+            size_t k = 0; std::vector<uint8_t> o2, m2;
+            for (; k < ops.size() && consumed < n; k++) { if (ops[k] == OP_D) continue; o2.push_back(OP_S); m2.push_back(0); consumed++; }
+            for (; k < ops.size(); k++) { o2.push_back(ops[k]); m2.push_back(mm[k]); }
+            ops.swap(o2); mm.swap(m2);
+        } else {
+            std::vector<uint8_t> o2, m2; size_t k = ops.size();
+            while (k > 0 && consumed < n) { k--; if (ops[k] == OP_D) continue; o2.push_back(OP_S); m2.push_back(0); consumed++; }
+            std::vector<uint8_t> head(ops.begin(), ops.begin() + k), headm(mm.begin(), mm.begin() + k);
+            std::reverse(o2.begin(), o2.end()); std::reverse(m2.begin(), m2.end());
+            head.insert(head.end(), o2.begin(), o2.end()); headm.insert(headm.end(), m2.begin(), m2.end());
+            ops.swap(head); mm.swap(headm);
+        }
+    };
+    if (clipL > 0) clip_side(true, clipL);
+    if (clipR > 0) clip_side(false, clipR);
+    // an alignment must start and end with M: leading/trailing I -> S, leading/trailing D dropped
+    {
+        size_t a = 0; while (a < ops.size() && ops[a] == OP_S) a++;
+        while (a < ops.size() && ops[a] != OP_M) { if (ops[a] == OP_I) ops[a] = OP_S; else { ops.erase(ops.begin() + a); mm.erase(mm.begin() + a); continue; } a++; }
+        // S ops created in the middle of leading D's are still contiguous at the front because D's were erased
+        size_t b = ops.size(); while (b > 0 && ops[b - 1] == OP_S) b--;
+        while (b > 0 && ops[b - 1] != OP_M) { if (ops[b - 1] == OP_I) { ops[b - 1] = OP_S; b--; } else { ops.erase(ops.begin() + (b - 1)); mm.erase(mm.begin() + (b - 1)); b--; } }
+    }
+    // position: contig index of the first M = j + number of ref-consuming ops skipped before it. Recompute by replay.
+    {
+        size_t jj2 = j; int ii = first; bool found = false;
+        // replay the ORIGINAL correspondence to find the contig index of the read base that is the first M
+        int first_m_read = 0; for (size_t k = 0; k < ops.size(); k++) { if (ops[k] == OP_M) break; if (ops[k] == OP_S || ops[k] == OP_I) first_m_read++; }
+        // first_m_read = index into rd of the first M base
+        while (ii <= last || jj2 < jend) {
+            if (ii <= last && rd[ii].lv < 0) { ii++; continue; }
+            if (ii > last) { jj2++; continue; }
+            int32_t rl = rd[ii].lv;
+            if (jj2 < jend && c.lv[jj2] < rl) jj2++;
+            else if (jj2 < jend && c.lv[jj2] == rl) { if (ii == first_m_read) { pos0 = (int32_t)jj2; found = true; break; } ii++; jj2++; }
+            else ii++;
+        }
+        if (!found) return false;
+    }
+    int nM = 0, as = 0; uint8_t prev = 255;
+    for (size_t k = 0; k < ops.size(); k++) {
+        if (ops[k] == OP_M) { nM++; as += mm[k] ? -4 : 1; }
+        else if (ops[k] == OP_I || ops[k] == OP_D) { as -= (prev == ops[k]) ? 1 : 7; }
+        prev = ops[k];
+    }
+    if (!ops.empty() && ops.front() == OP_S) as -= 5;
+    if (!ops.empty() && ops.back() == OP_S) as -= 5;
+    if (nM < 20 || as < 30) return false;
+    out.contig = -1; out.pos = pos0; out.as = as; out.cigar.clear();
+    for (size_t k = 0; k < ops.size();) {
+        size_t e = k; while (e < ops.size() && ops[e] == ops[k]) e++;
+        uint8_t op = ops[k]; if (op == OP_S && hard) op = OP_H;
+        out.cigar.push_back((uint32_t)((e - k) << 4) | op);
+        k = e;
+    }
+    return true;
+}
+
+int cmd_reads(const std::map<std::string, std::string>& a) {
+    const std::string prg = sarg(a, "prg", ""), out = sarg(a, "out", "");
+    if (prg.empty() || out.empty()) throw std::runtime_error("--prg and --out required");
+    const int64_t n_pairs = arg<int64_t>(a, "pairs", 1000);
+    const int L = arg<int>(a, "len", 100);
+    const double gap_mean = arg<double>(a, "gap-mean", 100), gap_sd = arg<double>(a, "gap-sd", 10);
+    const double clip_frac = arg<double>(a, "clip-frac", 0.15);
+    const double indel_rate = arg<double>(a, "indel-rate", 0.0005);
+    const double gene_frac = arg<double>(a, "gene-frac", 0.0);   // fraction of pairs forced to start inside a gene block
+    const int max_chains = arg<int>(a, "max-chains", 12);
+    const double decoy_frac = arg<double>(a, "decoy-frac", 0.02);
+    const uint64_t seed = arg<uint64_t>(a, "seed", 0xB200);
+    Rng R(seed ^ 0x9E3779B97F4A7C15ull);
+    std::vector<Contig> cs = load_contigs(prg);
+    std::vector<int> haps; for (size_t i = 0; i < cs.size(); i++) if (cs[i].is_hap) haps.push_back((int)i);
+    if (haps.empty()) throw std::runtime_error("no haplotype contigs");
+    // gene blocks = level ranges of the non-hap contigs
+    std::vector<std::pair<int32_t, int32_t>> gene_ranges;
+    for (const Contig& c : cs) if (!c.is_hap && !c.lv.empty()) gene_ranges.push_back({c.lv.front(), c.lv.back()});
+
+    std::vector<int64_t> read_off{0}; std::vector<uint8_t> bases, quals;
+    std::vector<int32_t> chain_off{0}, chain_contig, chain_pos, chain_as, cigar_off{0}; std::vector<uint16_t> chain_flag; std::vector<uint32_t> cigar;
+    std::vector<int32_t> truth_first, truth_last, truth_src;
+
+    auto comp = [](char c) { switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; } return 'N'; };
+    (void)comp;
+    auto sample_q = [&]() -> char { double u = R.u(); int q; if (u < 0.75) q = 34 + (int)R.below(8); else if (u < 0.93) q = 22 + (int)R.below(12); else if (u < 0.99) q = 8 + (int)R.below(14); else q = 2; return (char)(q + 33); };
+
+    for (int64_t p = 0; p < n_pairs; p++) {
+        const Contig* src; int64_t start; int gap;
+        for (;;) {
+            src = &cs[haps[R.below(haps.size())]];
+            gap = (int)std::lround(R.normal(gap_mean, gap_sd));
+            int64_t frag = 2 * (int64_t)L + gap + 16;
+            if ((int64_t)src->seq.size() < frag + 64 || gap < -L / 2) continue;
+            if (!gene_ranges.empty() && R.bern(gene_frac)) {
+                auto gr = gene_ranges[R.below(gene_ranges.size())];
+                int64_t c0 = std::lower_bound(src->lv.begin(), src->lv.end(), gr.first) - src->lv.begin();
+                int64_t c1 = std::lower_bound(src->lv.begin(), src->lv.end(), gr.second) - src->lv.begin();
+                start = c0 - frag + 1 + (int64_t)R.below((uint64_t)std::max<int64_t>(1, c1 - c0 + frag));
+            } else start = 32 + (int64_t)R.below(src->seq.size() - frag - 64);
+            if (start < 32 || start + frag + 32 > (int64_t)src->seq.size()) continue;
+            break;
+        }
+        bool first_is_fwd = R.bern(0.5);
+        for (int mate = 0; mate < 2; mate++) {
+            bool upstream = (mate == 0) == first_is_fwd;   // the forward-strand mate is the upstream one
+            int64_t s0 = upstream ? start : start + L + gap;
+            // build the read with sequencing errors, all in reference orientation (BAM SEQ convention)
+            std::vector<ReadItem> rd; int64_t ci = s0;
+            while ((int)rd.size() < L) {
+                if (R.bern(indel_rate)) { ci++; continue; }                                   // deletion
+                if (R.bern(indel_rate)) { rd.push_back({R.base(), sample_q(), -1}); continue; }   // insertion
+                char q = sample_q(); char b = src->seq[ci];
+                double perr = std::pow(10.0, -((int)q - 33) / 10.0);
+                if (R.bern(perr)) b = R.other(b);
+                rd.push_back({b, q, src->lv[ci]}); ci++;
+            }
+            // an inserted first/last base would make truth ambiguous; force them onto levels
+            if (rd.front().lv < 0) { rd.front().lv = src->lv[s0 > 0 ? s0 - 1 : 0]; rd.front().b = src->seq[s0 > 0 ? s0 - 1 : 0]; }
+            int clipL = 0, clipR = 0;
+            if (R.bern(clip_frac)) { int c = 5 + (int)R.below(36); if (R.bern(0.5)) clipL = c; else clipR = c; }
+            std::vector<Chain> chains;
+            for (size_t c = 0; c < cs.size(); c++) {
+                Chain ch;
+                bool is_src = (&cs[c] == src);
+                if (!is_src && (int)chains.size() >= max_chains) continue;
+                if (!align_to_contig(rd, cs[c], clipL, clipR, /*hard=*/false, ch)) continue;
+                ch.contig = (int)c;
+                chains.push_back(ch);
+            }
+            if (chains.empty()) { mate--; continue; }   // cannot happen for the source contig in practice; redo this mate
+            // primary = best AS, ties -> source contig, then lowest contig index
+            size_t prim = 0;
+            for (size_t k = 1; k < chains.size(); k++) {
+                bool better = chains[k].as > chains[prim].as || (chains[k].as == chains[prim].as && &cs[chains[k].contig] == src && &cs[chains[prim].contig] != src);
+                if (better) prim = k;
+            }
+            bool rev = !upstream;
+            uint16_t base_flag = 0x1 | (mate == 0 ? 0x40 : 0x80) | (rev ? 0x10 : 0x20);
+            if (R.bern(decoy_frac)) { Chain d = chains[R.below(chains.size())]; d.as = std::max(30, d.as - 7); d.flag = 0xFFFF; chains.push_back(d); }
+            for (size_t k = 0; k < chains.size(); k++) {
+                bool decoy = chains[k].flag == 0xFFFF;
+                uint16_t fl = base_flag;
+                if (decoy) fl ^= 0x10;
+                if (k != prim) {
+                    fl |= 0x100;
+                    for (uint32_t& op : chains[k].cigar) if ((op & 15) == OP_S && R.bern(0.5)) op = (op & ~15u) | OP_H;   // secondaries: bwa prints H or S
+                    // keep clip kinds consistent per record (all H or all S)
+                    bool anyH = false; for (uint32_t op : chains[k].cigar) anyH |= (op & 15) == OP_H;
+                    if (anyH) for (uint32_t& op : chains[k].cigar) if ((op & 15) == OP_S) op = (op & ~15u) | OP_H;
+                }
+                chains[k].flag = fl;
+            }
+            // BAM order: by contig, then position
+            std::vector<size_t> ord(chains.size()); for (size_t k = 0; k < ord.size(); k++) ord[k] = k;
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { if (chains[x].contig != chains[y].contig) return chains[x].contig < chains[y].contig; return chains[x].pos < chains[y].pos; });
+            for (size_t k : ord) {
+                const Chain& ch = chains[k];
+                chain_contig.push_back(ch.contig); chain_pos.push_back(ch.pos); chain_flag.push_back(ch.flag); chain_as.push_back(ch.as);
+                cigar.insert(cigar.end(), ch.cigar.begin(), ch.cigar.end()); cigar_off.push_back((int32_t)cigar.size());
+            }
+            chain_off.push_back((int32_t)chain_contig.size());
+            for (const ReadItem& it : rd) { bases.push_back((uint8_t)it.b); quals.push_back((uint8_t)it.q); }
+            read_off.push_back((int64_t)bases.size());
+            int32_t tf = -1, tl = -1; for (const ReadItem& it : rd) if (it.lv >= 0) { if (tf < 0) tf = it.lv; tl = it.lv; }
+            truth_first.push_back(tf); truth_last.push_back(tl); truth_src.push_back((int32_t)(src - cs.data()));
+        }
+    }
+    ArrayFile f;
+    std::vector<int32_t> contig_ids; for (const Contig& c : cs) contig_ids.push_back(c.id);
+    std::vector<int64_t> meta{n_pairs, L};
+    f.put("meta", DT_I64, meta);
+    f.put("contig_ids", DT_I32, contig_ids);
+    f.put("read_off", DT_I64, read_off); f.put("bases", DT_U8, bases); f.put("quals", DT_U8, quals);
+    f.put("chain_off", DT_I32, chain_off); f.put("chain_contig", DT_I32, chain_contig); f.put("chain_pos", DT_I32, chain_pos);
+    f.put("chain_flag", DT_U16, chain_flag); f.put("chain_as", DT_I32, chain_as);
+    f.put("cigar_off", DT_I32, cigar_off); f.put("cigar", DT_U32, cigar);
+    f.put("truth_first", DT_I32, truth_first); f.put("truth_last", DT_I32, truth_last); f.put("truth_src", DT_I32, truth_src);
+    f.write(out);
+    fprintf(stderr, "hlala-synth: %lld pairs, %zu chains (%.2f per read)\n", (long long)n_pairs, chain_contig.size(), (double)chain_contig.size() / (2.0 * n_pairs));
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    try {
+        if (argc < 2) { fprintf(stderr, "usage: hlala-synth prg|reads --key value ...\n"); return 2; }
+        std::string cmd = argv[1];
+        auto a = parse_args(argc, argv, 2);
+        if (cmd == "prg") return cmd_prg(a);
+        if (cmd == "reads") return cmd_reads(a);
+        fprintf(stderr, "unknown command %s\n", cmd.c_str());
+        return 2;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "hlala-synth: error: %s\n", e.what());
+        return 1;
+    }
+}

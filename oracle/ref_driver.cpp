@@ -1,1 +1,273 @@
-extern "C" int hlala_ref_dummy() { return 0; }
+// TEST INFRASTRUCTURE — not part of the product. Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load oracle/_ref/libhlala_ref.so.
+//
+// Drives the UNMODIFIED reference translation units (compiled in place from /root/reference by
+// oracle/Makefile.ref against the stand-in headers in oracle/shim/) from the same flat seed batches the
+// CUDA path consumes, and exports results as flat arrays:
+//   graph load            Graph::readFromFile                      Graph/Graph.cpp:2329
+//   gap paths             Graph::computeGapEdgePaths               Graph/Graph.cpp:347
+//   gap stretches         processBAM ctor                          mapper/processBAM.cpp:91-149
+//   per chain             alignment2Chain + extendSeedChain + scoreOneAlignment
+//                                                                   mapper/processBAM.cpp:3019, extensionAligner.cpp:186,52
+//   per pair              processBAM::alignOneReadPair             mapper/processBAM.cpp:3129
+//
+// Two things are pinned so that "bit-exact" is defined at all (SURVEY.md §0 finding 3, §7 hard parts):
+//  * std::set<Node*>/std::set<Edge*> iterate in pointer order. While the graph is being built every
+//    allocation in this library comes from a bump arena, so pointer order == creation order == order of
+//    appearance in graph.txt (libstdc++ is linked statically and -Bsymbolic so that every new/delete inside
+//    the library goes through the operators below).
+//  * the one real random draw (extensionAligner.cpp:1459, rand_r-based) is pinned to "first of the tied
+//    candidates" by binding rand_r/time/rand inside this library to the constant versions below.
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+#include <new>
+#include <string>
+#include <vector>
+#include <map>
+#include <unordered_map>
+#include <chrono>
+
+#include "mapper/processBAM.h"
+#include "Graph/Graph.h"
+#include "Utilities.h"
+
+// ---- allocation: bump arena while loading, malloc otherwise
+static char* g_arena = nullptr; static size_t g_arena_cap = 0, g_arena_used = 0; static bool g_arena_on = false;
+void* operator new(size_t n) {
+    if (g_arena_on) {
+        size_t m = (n + 15) & ~size_t(15);
+        if (g_arena_used + m <= g_arena_cap) { void* p = g_arena + g_arena_used; g_arena_used += m; return p; }
+        fprintf(stderr, "hlala_ref: arena exhausted\n"); abort();
+    }
+    void* p = malloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p;
+}
+void operator delete(void* p) noexcept { if (p >= (void*)g_arena && p < (void*)(g_arena + g_arena_cap)) return; free(p); }
+void operator delete(void* p, size_t) noexcept { operator delete(p); }
+void* operator new[](size_t n) { return operator new(n); }
+void operator delete[](void* p) noexcept { operator delete(p); }
+void operator delete[](void* p, size_t) noexcept { operator delete(p); }
+
+// ---- determinism of the reference's RNG use (bound locally through -Bsymbolic)
+extern "C" int rand_r(unsigned int*) { return 0; }
+
+namespace {
+
+class Driver : public mapper::processBAM {
+public:
+    explicit Driver(const std::string& dir) : mapper::processBAM(dir, 1) {}
+    std::vector<Node*> nodes; std::vector<Edge*> edges;
+    std::unordered_map<const Edge*, int> edge_ord;
+    std::vector<std::string> contig_names;   // batch contig index -> BAM reference name
+
+    void finish_open(const std::string& dir) {
+        // contigs in sequences.txt order = RefID order of the synthetic "BAM"
+        std::ifstream s(dir + "/sequences.txt"); std::string line; std::getline(s, line);
+        BamTools::BamReader::shim_refs().clear();
+        std::vector<int> ids;
+        while (std::getline(s, line)) {
+            Utilities::eraseNL(line); if (line.empty()) continue;
+            std::vector<std::string> f = Utilities::split(line, "\t");
+            std::string name = (f.at(3) != "") ? f.at(3) : ("PRG_" + f.at(0));
+            contig_names.push_back(name); ids.push_back(Utilities::StrtoI(f.at(0)));
+            BamTools::BamReader::shim_refs().push_back(BamTools::RefData(name, (int)PRGonlyReferenceGenomeSequences.at(name).length()));
+        }
+        initBAM(dir + "/sequences.txt", false, false);
+        for (int id : ids) _loadMapping(id);   // all contigs up-front (lazy loading is order-dependent state)
+        nodes.assign(g->Nodes.begin(), g->Nodes.end());
+        edges.assign(g->Edges.begin(), g->Edges.end());
+        for (size_t i = 0; i < edges.size(); i++) edge_ord[edges[i]] = (int)i;
+        eA->init_for_threads(1);
+    }
+    Graph* graph() { return g; }
+    const std::vector<bool>& gapStretch() const { return inGraphGapStretch; }
+
+    struct Batch {
+        int64_t n_reads; const int64_t* read_off; const uint8_t* bases; const uint8_t* quals;
+        const int32_t* chain_off; const int32_t* chain_contig; const int32_t* chain_pos; const uint16_t* chain_flag; const int32_t* chain_as;
+        const int32_t* cigar_off; const uint32_t* cigar;
+    };
+    typedef std::tuple<std::string, int, BamTools::BamAlignment, int> Al;
+
+    // one read's alignments in the reference's containers, sorted as sortChainsInSeeds does; order[] = batch chain indices
+    void build_read(const Batch& b, int64_t r, const std::string& name, std::vector<Al>& als, std::vector<int32_t>& order) const {
+        std::string seq((const char*)b.bases + b.read_off[r], (size_t)(b.read_off[r + 1] - b.read_off[r]));
+        std::string qual((const char*)b.quals + b.read_off[r], seq.size());
+        std::vector<std::pair<Al, int32_t>> tmp;
+        for (int32_t c = b.chain_off[r]; c < b.chain_off[r + 1]; c++) {
+            BamTools::BamAlignment a;
+            a.Name = name; a.QueryBases = seq; a.Qualities = qual; a.Length = (int)seq.size();
+            a.RefID = b.chain_contig[c]; a.Position = b.chain_pos[c]; a.AlignmentFlag = b.chain_flag[c];
+            a.shim_int_tags["AS"] = b.chain_as[c];
+            for (int32_t k = b.cigar_off[c]; k < b.cigar_off[c + 1]; k++) a.CigarData.push_back(BamTools::CigarOp("MIDNSHP=X"[b.cigar[k] & 15], b.cigar[k] >> 4));
+            tmp.push_back(std::make_pair(std::make_tuple(contig_names.at(a.RefID), 0, a, 0), c));
+        }
+        // identical algorithm and comparator outcomes as processBAM::sortChainsInSeeds (processBAM.cpp:1945): std::sort ascending by AS, then reverse
+        std::sort(tmp.begin(), tmp.end(), [](const std::pair<Al, int32_t>& x, const std::pair<Al, int32_t>& y) {
+            int sx = 0, sy = 0; std::get<2>(x.first).GetTag("AS", sx); std::get<2>(y.first).GetTag("AS", sy); return sx < sy; });
+        std::reverse(tmp.begin(), tmp.end());
+        als.clear(); order.clear();
+        for (auto& t : tmp) { als.push_back(t.first); order.push_back(t.second); }
+    }
+
+    void export_chain(const mapper::reads::verboseSeedChain& ch, int cap, int32_t* n_cols, int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq) const {
+        int n = (int)ch.graph_aligned_levels.size();
+        *n_cols = n;
+        for (int i = 0; i < n && i < cap; i++) {
+            level[i] = ch.graph_aligned_levels[i];
+            Edge* e = ch.graph_aligned_edges[i];
+            edge[i] = e ? edge_ord.at(e) : -1;
+            gchar[i] = (uint8_t)ch.graph_aligned[i]; schar[i] = (uint8_t)ch.sequence_aligned[i];
+            if (from_seed) from_seed[i] = ch.is_from_BWAseed.size() > (size_t)i ? (uint8_t)ch.is_from_BWAseed[i] : 0;
+            if (mapq) mapq[i] = ch.mapQ_perPosition.size() > (size_t)i ? (uint8_t)ch.mapQ_perPosition[i] : 0;
+        }
+    }
+
+    int run_chains(const Batch& b, int cap, int32_t* chain_order, int32_t* status, int32_t* n_cols, int32_t* seed_begin, int32_t* seed_end, double* ll,
+                   int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed) const {
+        for (int64_t r = 0; r < b.n_reads; r++) {
+            std::vector<Al> als; std::vector<int32_t> order;
+            build_read(b, r, "r" + std::to_string(r / 2), als, order);
+            if (als.empty()) continue;
+            size_t prim = als.size();
+            for (size_t i = 0; i < als.size(); i++) if (std::get<2>(als[i]).IsPrimaryAlignment()) { prim = i; break; }
+            if (prim == als.size()) return -2;
+            const BamTools::BamAlignment& P = std::get<2>(als[prim]);
+            mapper::reads::oneRead rd(P.Name, P.QueryBases, P.Qualities);
+            if (P.IsReverseStrand()) rd.invert();
+            for (size_t i = 0; i < als.size(); i++) {
+                int32_t slot = b.chain_off[r] + (int32_t)i;
+                chain_order[slot] = order[i];
+                if (std::get<2>(als[i]).IsReverseStrand() != P.IsReverseStrand()) { status[slot] = 1; n_cols[slot] = 0; ll[slot] = 0; continue; }
+                mapper::reads::verboseSeedChain seed = alignment2Chain(als[i], P.QueryBases, P.Qualities);
+                seed_begin[slot] = seed.sequence_begin; seed_end[slot] = seed.sequence_end;
+                mapper::reads::verboseSeedChain ext = eA->extendSeedChain(P.QueryBases, seed);
+                ll[slot] = eA->scoreOneAlignment(ext, rd);
+                status[slot] = 0;
+                size_t o = (size_t)slot * cap;
+                export_chain(ext, cap, n_cols + slot, level + o, edge + o, gchar + o, schar + o, from_seed + o, nullptr);
+            }
+        }
+        return 0;
+    }
+
+    int run_pairs(const Batch& b, double is_mean, double is_sd, int cap, double* pair_mapq, double* read_mapq, uint8_t* read_reverse, int32_t* n_cols,
+                  int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) const {
+        boost::math::normal nd(is_mean, is_sd);
+        double pen = log(boost::math::pdf(nd, is_mean + 8 * is_sd));   // processBAM.cpp:2342-2346
+        auto t0 = std::chrono::steady_clock::now();
+        for (int64_t p = 0; p < b.n_reads / 2; p++) {
+            mapper::reads::protoSeeds ps; std::vector<int32_t> o1, o2;
+            std::string name = "r" + std::to_string(p);
+            build_read(b, 2 * p, name, ps.read1_alignments, o1);
+            build_read(b, 2 * p + 1, name, ps.read2_alignments, o2);
+            mapper::reads::verboseSeedChainPair res = alignOneReadPair(ps, nd, pen, nullptr, nullptr);
+            pair_mapq[p] = res.mapQ;
+            read_mapq[2 * p] = res.chains.first.mapQ; read_mapq[2 * p + 1] = res.chains.second.mapQ;
+            read_reverse[2 * p] = res.chains.first.reverse; read_reverse[2 * p + 1] = res.chains.second.reverse;
+            size_t oa = (size_t)(2 * p) * cap, ob = (size_t)(2 * p + 1) * cap;
+            export_chain(res.chains.first, cap, n_cols + 2 * p, level + oa, edge + oa, gchar + oa, schar + oa, from_seed + oa, mapq + oa);
+            export_chain(res.chains.second, cap, n_cols + 2 * p + 1, level + ob, edge + ob, gchar + ob, schar + ob, from_seed + ob, mapq + ob);
+        }
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return 0;
+    }
+};
+
+std::string g_err;
+template <class F> int guarded(F&& f) {
+    try { return f(); } catch (const std::exception& e) { g_err = e.what(); return -1; } catch (...) { g_err = "unknown exception"; return -1; }
+}
+
+} // namespace
+
+extern "C" {
+
+const char* hlala_ref_last_error() { return g_err.c_str(); }
+
+void* hlala_ref_open(const char* prg_dir, long long arena_bytes) {
+    Driver* d = nullptr;
+    int rc = guarded([&]() {
+        if (g_arena) { g_err = "hlala_ref_open: one graph per process (arena is not recycled)"; return -1; }
+        g_arena_cap = arena_bytes > 0 ? (size_t)arena_bytes : (size_t)1 << 30;
+        g_arena = (char*)malloc(g_arena_cap); if (!g_arena) { g_err = "arena malloc failed"; return -1; }
+        g_arena_on = true;
+        d = new Driver(prg_dir);   // graph, gap-stretch scan, extensionAligner (=> computeGapEdgePaths)
+        g_arena_on = false;
+        d->finish_open(prg_dir);
+        return 0;
+    });
+    g_arena_on = false;
+    return rc == 0 ? d : nullptr;
+}
+
+long long hlala_ref_n_levels(void* h) { return (long long)((Driver*)h)->graph()->NodesPerLevel.size(); }
+long long hlala_ref_n_nodes(void* h) { return (long long)((Driver*)h)->nodes.size(); }
+long long hlala_ref_n_edges(void* h) { return (long long)((Driver*)h)->edges.size(); }
+
+// nodes and edges in std::set (pointer == creation) order
+int hlala_ref_graph_export(void* h, int32_t* node_level, int32_t* edge_from, int32_t* edge_to, uint8_t* edge_emis) {
+    Driver* d = (Driver*)h;
+    return guarded([&]() {
+        std::unordered_map<const Node*, int> nord;
+        for (size_t i = 0; i < d->nodes.size(); i++) { nord[d->nodes[i]] = (int)i; node_level[i] = (int32_t)d->nodes[i]->level; }
+        for (size_t i = 0; i < d->edges.size(); i++) { edge_from[i] = nord.at(d->edges[i]->From); edge_to[i] = nord.at(d->edges[i]->To); edge_emis[i] = (uint8_t)d->edges[i]->emission; }
+        return 0;
+    });
+}
+
+long long hlala_ref_gap_paths_total(void* h, long long* n_paths) {
+    Driver* d = (Driver*)h; long long tot = 0;
+    *n_paths = (long long)d->graph()->completedGapEdgePaths.size();
+    for (auto& p : d->graph()->completedGapEdgePaths) tot += (long long)p.size();
+    return tot;
+}
+int hlala_ref_gap_paths_export(void* h, int64_t* path_off, int32_t* path_edges) {
+    Driver* d = (Driver*)h;
+    return guarded([&]() {
+        int64_t o = 0; size_t i = 0;
+        for (auto& p : d->graph()->completedGapEdgePaths) { path_off[i++] = o; for (Edge* e : p) path_edges[o++] = d->edge_ord.at(e); }
+        path_off[i] = o; return 0;
+    });
+}
+// jump lists in the reference's iteration order (std::map<Node*,Edge*> keyed by target): per node ordinal, targets and path ids
+long long hlala_ref_jumps_export(void* h, int forward, int32_t* from_node, int32_t* to_node, int32_t* path_id, long long cap) {
+    Driver* d = (Driver*)h; long long n = 0;
+    int rc = guarded([&]() {
+        std::unordered_map<const Node*, int> nord; for (size_t i = 0; i < d->nodes.size(); i++) nord[d->nodes[i]] = (int)i;
+        auto& M = forward ? d->graph()->gapEdgePaths_connectedNodes_forwards : d->graph()->gapEdgePaths_connectedNodes_backwards;
+        for (Node* nd : d->nodes) {
+            auto it = M.find(nd); if (it == M.end()) continue;
+            for (auto& kv : it->second) { if (n < cap) { from_node[n] = nord.at(nd); to_node[n] = nord.at(kv.first); path_id[n] = (int32_t)d->graph()->pseudoEdges_correspondingToGapEdgePaths.at(kv.second); } n++; }
+        }
+        return 0;
+    });
+    return rc == 0 ? n : -1;
+}
+int hlala_ref_gap_stretch(void* h, uint8_t* out) {
+    Driver* d = (Driver*)h; const std::vector<bool>& v = d->gapStretch();
+    for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+int hlala_ref_chains(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
+                     const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
+                     const int32_t* cigar_off, const uint32_t* cigar, int cap,
+                     int32_t* chain_order, int32_t* status, int32_t* n_cols, int32_t* seed_begin, int32_t* seed_end, double* ll,
+                     int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed) {
+    Driver* d = (Driver*)h;
+    Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() { return d->run_chains(b, cap, chain_order, status, n_cols, seed_begin, seed_end, ll, level, edge, gchar, schar, from_seed); });
+}
+
+int hlala_ref_pairs(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
+                    const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
+                    const int32_t* cigar_off, const uint32_t* cigar, double is_mean, double is_sd, int cap,
+                    double* pair_mapq, double* read_mapq, uint8_t* read_reverse, int32_t* n_cols,
+                    int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) {
+    Driver* d = (Driver*)h;
+    Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() { return d->run_pairs(b, is_mean, is_sd, cap, pair_mapq, read_mapq, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
+}
+
+} // extern "C"

@@ -1,0 +1,120 @@
+"""Shared test/bench harness: array-file reader, ctypes bindings for the product C-ABI library,
+the oracle restatement and the compiled reference (oracle/_ref). Test infrastructure only."""
+import ctypes as C
+import os
+import struct
+import subprocess
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "hla-la_b200")
+SYNTH = os.path.join(PKG, "build", "hlala-synth")
+LIB_PRODUCT = os.path.join(PKG, "build", "libhlala_b200.so")
+LIB_ORACLE = os.path.join(REPO, "oracle", "build", "libhlala_oracle.so")
+LIB_REF = os.path.join(REPO, "oracle", "_ref", "libhlala_ref.so")
+
+_DT = {1: np.uint8, 2: np.uint16, 3: np.int32, 4: np.uint32, 5: np.int64, 6: np.float64}
+
+
+def read_arrayfile(path):
+    """hla-la_b200/host/arrayfile.h container -> dict of numpy arrays."""
+    out = {}
+    with open(path, "rb") as f:
+        buf = f.read()
+    magic, n = struct.unpack_from("<II", buf, 0)
+    assert magic == 0x42414C48, "bad array file"
+    off = 8
+    for _ in range(n):
+        name = buf[off:off + 24].split(b"\0")[0].decode()
+        dt, _pad, cnt = struct.unpack_from("<IIQ", buf, off + 24)
+        off += 40
+        nbytes = cnt * np.dtype(_DT[dt]).itemsize
+        out[name] = np.frombuffer(buf, dtype=_DT[dt], count=cnt, offset=off).copy()
+        off += nbytes + (-nbytes) % 8
+    return out
+
+
+def synth_prg(out_dir, **kw):
+    args = [SYNTH, "prg", "--out", out_dir]
+    for k, v in kw.items():
+        args += ["--" + k.replace("_", "-"), str(v)]
+    subprocess.run(args, check=True, stderr=subprocess.DEVNULL)
+
+
+def synth_reads(prg_dir, out_file, **kw):
+    args = [SYNTH, "reads", "--prg", prg_dir, "--out", out_file]
+    for k, v in kw.items():
+        args += ["--" + k.replace("_", "-"), str(v)]
+    subprocess.run(args, check=True, stderr=subprocess.DEVNULL)
+    return read_arrayfile(out_file)
+
+
+def p(a, ty=None):
+    """numpy array -> ctypes pointer (keeps dtype)."""
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+BATCH_KEYS = ["read_off", "bases", "quals", "chain_off", "chain_contig", "chain_pos", "chain_flag", "chain_as", "cigar_off", "cigar"]
+
+
+def batch_args(b):
+    return [C.c_longlong(len(b["read_off"]) - 1)] + [p(b[k]) for k in BATCH_KEYS]
+
+
+class Ref:
+    """oracle/_ref/libhlala_ref.so: the unmodified reference TUs behind ref_driver.cpp."""
+
+    def __init__(self, prg_dir, arena_bytes=1 << 30):
+        self.lib = C.CDLL(LIB_REF)
+        self.lib.hlala_ref_open.restype = C.c_void_p
+        self.lib.hlala_ref_last_error.restype = C.c_char_p
+        for fn in ("hlala_ref_n_levels", "hlala_ref_n_nodes", "hlala_ref_n_edges", "hlala_ref_gap_paths_total", "hlala_ref_jumps_export"):
+            getattr(self.lib, fn).restype = C.c_longlong
+        self.h = C.c_void_p(self.lib.hlala_ref_open(prg_dir.encode(), C.c_longlong(arena_bytes)))
+        if not self.h:
+            raise RuntimeError(self.lib.hlala_ref_last_error().decode())
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("reference driver failed: %s" % self.lib.hlala_ref_last_error().decode())
+
+    def graph(self):
+        nl = self.lib.hlala_ref_n_levels(self.h); nn = self.lib.hlala_ref_n_nodes(self.h); ne = self.lib.hlala_ref_n_edges(self.h)
+        node_level = np.zeros(nn, np.int32); ef = np.zeros(ne, np.int32); et = np.zeros(ne, np.int32); em = np.zeros(ne, np.uint8)
+        self._chk(self.lib.hlala_ref_graph_export(self.h, p(node_level), p(ef), p(et), p(em)))
+        npaths = C.c_longlong(0)
+        tot = self.lib.hlala_ref_gap_paths_total(self.h, C.byref(npaths))
+        path_off = np.zeros(npaths.value + 1, np.int64); path_edges = np.zeros(max(tot, 1), np.int32)
+        self._chk(self.lib.hlala_ref_gap_paths_export(self.h, p(path_off), p(path_edges)))
+        gs = np.zeros(nl, np.uint8)
+        ngs = self.lib.hlala_ref_gap_stretch(self.h, p(gs))
+        jumps = {}
+        for fwd in (1, 0):
+            cap = max(npaths.value, 1)
+            a = np.zeros(cap, np.int32); b = np.zeros(cap, np.int32); c = np.zeros(cap, np.int32)
+            n = self.lib.hlala_ref_jumps_export(self.h, fwd, p(a), p(b), p(c), C.c_longlong(cap))
+            assert 0 <= n <= cap
+            jumps[fwd] = (a[:n], b[:n], c[:n])
+        return dict(n_levels=nl, node_level=node_level, edge_from=ef, edge_to=et, edge_emis=em, path_off=path_off, path_edges=path_edges[:tot],
+                    gap_stretch=gs[:ngs], jumps_fwd=jumps[1], jumps_bwd=jumps[0])
+
+    def chains(self, b, cap=1024):
+        nc = len(b["chain_contig"])
+        o = dict(chain_order=np.zeros(nc, np.int32), status=np.full(nc, -1, np.int32), n_cols=np.zeros(nc, np.int32), seed_begin=np.zeros(nc, np.int32),
+                 seed_end=np.zeros(nc, np.int32), ll=np.zeros(nc, np.float64), level=np.zeros((nc, cap), np.int32), edge=np.zeros((nc, cap), np.int32),
+                 gchar=np.zeros((nc, cap), np.uint8), schar=np.zeros((nc, cap), np.uint8), from_seed=np.zeros((nc, cap), np.uint8))
+        self._chk(self.lib.hlala_ref_chains(self.h, *batch_args(b), C.c_int(cap), *[p(o[k]) for k in
+                  ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll", "level", "edge", "gchar", "schar", "from_seed")]))
+        return o
+
+    def pairs(self, b, is_mean, is_sd, cap=1024):
+        nr = len(b["read_off"]) - 1
+        o = dict(pair_mapq=np.zeros(nr // 2, np.float64), read_mapq=np.zeros(nr, np.float64), read_reverse=np.zeros(nr, np.uint8), n_cols=np.zeros(nr, np.int32),
+                 level=np.zeros((nr, cap), np.int32), edge=np.zeros((nr, cap), np.int32), gchar=np.zeros((nr, cap), np.uint8), schar=np.zeros((nr, cap), np.uint8),
+                 from_seed=np.zeros((nr, cap), np.uint8), mapq=np.zeros((nr, cap), np.uint8))
+        sec = C.c_double(0)
+        self._chk(self.lib.hlala_ref_pairs(self.h, *batch_args(b), C.c_double(is_mean), C.c_double(is_sd), C.c_int(cap), *[p(o[k]) for k in
+                  ("pair_mapq", "read_mapq", "read_reverse", "n_cols", "level", "edge", "gchar", "schar", "from_seed", "mapq")], C.byref(sec)))
+        o["seconds"] = sec.value
+        return o
