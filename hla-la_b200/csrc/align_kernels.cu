@@ -1,0 +1,168 @@
+// CUDA kernels of the alignment path + their launchers. Compiled for sm_100a only.
+#include "chain_kernel.cuh"
+#include "align_kernels.h"
+
+#include <cstdio>
+
+namespace hlala {
+
+// ---------------------------------------------------------------------------------------------------------------
+// finalize: [left padding][left extension][seed][right extension][right padding] -> global chain record + LL
+//   verboseSeedChain::extendWithOtherSeedChain / extendToFullSequenceLength (verboseSeedChain.cpp:23-144)
+//   extensionAligner::scoreOneAlignment (extensionAligner.cpp:52-182); the sum runs left to right in one lane so that
+//   every rounding step is the reference's.
+struct ExtView { const int32_t* edge; const uint8_t* s; int n; int n_lvl; };   // n_lvl = columns that carry a level
+
+__device__ void finalize_chain(const ChainParams& P, const WarpSlab& S, int slot, int64_t rd0, int rdlen,
+                               const int32_t* seed_edge, const uint8_t* seed_g, const uint8_t* seed_s, int n_seed,
+                               int seq_begin, int seq_end, int l_first, int l_last, ExtView L, ExtView R, int lane) {
+    const DevGraph& G = P.g; const DevBatch& B = P.b;
+    // after extension: sequence_begin / sequence_end of the chain (extendWithOtherSeedChain)
+    int ext_l_bases = 0, ext_r_bases = 0;
+    for (int i = lane; i < L.n; i += 32) ext_l_bases += (L.s[i] != '_');
+    for (int i = lane; i < R.n; i += 32) ext_r_bases += (R.s[i] != '_');
+    for (int d = 16; d; d >>= 1) { ext_l_bases += __shfl_xor_sync(0xffffffffu, ext_l_bases, d); ext_r_bases += __shfl_xor_sync(0xffffffffu, ext_r_bases, d); }
+    const int padL = seq_begin - ext_l_bases;
+    const int padR = rdlen - 1 - (seq_end + ext_r_bases);
+    const int n_total = padL + L.n + n_seed + R.n + padR;
+    if (padL < 0 || padR < 0 || n_total > P.maxcol) {
+        if (lane == 0) { P.status[slot] = (n_total > P.maxcol) ? HLALA_E_CAPACITY_DEV : HLALA_E_INVARIANT_DEV; P.n_cols[slot] = 0; atomicAdd(P.error_count, 1); }
+        return;
+    }
+    int32_t* oe = P.c_edge + (size_t)slot * P.maxcol; uint8_t* os = P.c_schar + (size_t)slot * P.maxcol; uint8_t* of = P.c_fromseed + (size_t)slot * P.maxcol;
+    uint8_t* kind = S.gA; uint8_t* qv = S.sA;      // per-column scoring class and quality, consumed by lane 0 below
+    // one pass over output columns; idx of the read base under a column = number of non-gap read characters before it
+    int carry = 0;
+    for (int base = 0; base < n_total; base += 32) {
+        int k = base + lane; bool in = k < n_total;
+        int32_t e = -1; uint8_t sc = '_', gc = '_', fs = 0;
+        if (in) {
+            int j = k;
+            if (j < padL) { sc = B.bases[rd0 + j]; }
+            else if ((j -= padL) < L.n) { e = L.edge[j]; sc = L.s[j]; gc = e >= 0 ? (uint8_t)(G.edge_pack[e] >> 16) : (uint8_t)'_'; }
+            else if ((j -= L.n) < n_seed) { e = seed_edge[j]; sc = seed_s[j]; gc = seed_g[j]; fs = 1; }
+            else if ((j -= n_seed) < R.n) { e = R.edge[j]; sc = R.s[j]; gc = e >= 0 ? (uint8_t)(G.edge_pack[e] >> 16) : (uint8_t)'_'; }
+            else { j -= R.n; sc = B.bases[rd0 + (rdlen - padR) + j]; }
+            oe[k] = e; os[k] = sc; of[k] = fs;
+        }
+        bool hasb = in && sc != '_';
+        unsigned m = __ballot_sync(0xffffffffu, hasb);
+        if (in) {
+            uint8_t kd = 0, q = 0;
+            if (hasb) {
+                int idx = carry + __popc(m & ((1u << lane) - 1));
+                q = B.quals[rd0 + idx];
+                kd = (gc == '_') ? 1 : (sc == gc ? 3 : 4);
+            } else kd = (gc == '_') ? 0 : 2;
+            kind[k] = kd; qv[k] = q;
+        }
+        carry += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double ll = 0;
+        for (int k = 0; k < n_total; k++) {
+            switch (kind[k]) {
+            case 1: ll += c_tables.ins_term; break;                                                     // insertion (extensionAligner.cpp:119)
+            case 2: ll += c_tables.rate_deletion; break;                                                // deletion  (:163)
+            case 3: ll += c_tables.rate_match_mismatch; ll += c_tables.log_match[qv[k]]; break;         // (:125,139)
+            case 4: ll += c_tables.rate_match_mismatch; ll += c_tables.log_mismatch[qv[k]]; break;      // (:125,146)
+            default: break;                                                                             // gap against gap
+            }
+        }
+        P.ll[slot] = ll; P.n_cols[slot] = n_total; P.status[slot] = CH_OK;
+        P.first_level[slot] = l_first - L.n_lvl; P.last_level[slot] = l_last + R.n_lvl;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t slab = k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap);
+    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.maxcol, P.pool_cap, P.win_cap);
+    const DevBatch& B = P.b;
+    const int nw = gridDim.x * K1_WARPS;
+    for (int slot = blockIdx.x * K1_WARPS + warp; slot < B.n_chains; slot += nw) {
+        const int r = B.slot_read[slot];
+        const int prim = B.read_primary[r];
+        const int c = B.chain_order[slot];
+        int rc = 0;
+        if (prim < 0) rc = HLALA_E_INVARIANT_DEV;                   // protoSeeds::read1_getPrimaryAlignmentI asserts
+        else if ((B.chain_flag[c] ^ B.chain_flag[B.chain_order[prim]]) & 0x10) {
+            if (lane == 0) { P.status[slot] = CH_SKIPPED_STRAND; P.n_cols[slot] = 0; P.ll[slot] = 0; }
+            continue;                                                // processBAM.cpp:3216,3305
+        }
+        const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
+        ColBuf A{S.lvlA, S.gA, S.sA}, Bc{S.lvlB, S.gB, S.sB};
+        int start_raw = -1, stop_raw = -1, n = 0;
+        if (rc == 0) { n = expand_cigar(P, c, rd0, rdlen, A, lane, start_raw, stop_raw); if (n < 0) rc = n; }
+        if (rc == 0 && !(start_raw < stop_raw)) rc = HLALA_E_INVARIANT_DEV;     // processBAM.cpp:5245
+        if (rc == 0) { n = trim_and_fill(P, A, n, Bc, lane, start_raw, stop_raw); if (n < 0) rc = n; }
+        if (rc == 0) n = clean_columns(Bc, n, A, lane);
+        if (rc == 0) n = restrict_columns(P, Bc, n, A, lane, start_raw, stop_raw);
+        if (rc == 0) rc = viterbi_backtrace(P, Bc, n, S, S.lvlA, lane);
+        if (rc != 0) {
+            if (lane == 0) { P.status[slot] = rc; P.n_cols[slot] = 0; P.ll[slot] = 0; atomicAdd(P.error_count, 1); }
+            __syncwarp();
+            continue;
+        }
+        if (lane == 0) { P.seed_begin[slot] = start_raw; P.seed_end[slot] = stop_raw; }
+        const int l_first = Bc.lvl[0], l_last = Bc.lvl[n - 1];
+        ExtView none{nullptr, nullptr, 0, 0};
+        finalize_chain(P, S, slot, rd0, rdlen, S.lvlA, Bc.g, Bc.s, n, start_raw, stop_raw, l_first, l_last, none, none, lane);
+    }
+}
+
+// edge ids -> canonical ordinals / levels / graph characters for the host-facing chain records
+__global__ void k_export_chain_columns(DevGraph G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
+                                       const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_chains) return;
+    const int n = n_cols[warp]; const size_t o = (size_t)warp * maxcol;
+    int carry = 0; const int l0 = first_level[warp];
+    for (int base = 0; base < n; base += 32) {
+        int k = base + lane; bool in = k < n;
+        int32_t e = in ? c_edge[o + k] : -1;
+        unsigned m = __ballot_sync(0xffffffffu, in && e >= 0);
+        if (in) {
+            if (e >= 0) { out_level[o + k] = l0 + carry + __popc(m & ((1u << lane) - 1)); out_edge_ord[o + k] = G.edge_ord[e]; out_gchar[o + k] = (uint8_t)(G.edge_pack[e] >> 16); }
+            else { out_level[o + k] = -1; out_edge_ord[o + k] = -1; out_gchar[o + k] = '_'; }
+        }
+        carry += __popc(m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+cudaError_t upload_score_tables(const ScoreTables& t) { return cudaMemcpyToSymbol(c_tables, &t, sizeof(ScoreTables)); }
+
+cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream) {
+    size_t slab = k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap);
+    size_t smem = slab * K1_WARPS;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_seed, K1_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)P.b.n_chains + K1_WARPS - 1) / K1_WARPS;
+    int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm);   // persistent: a multiple of the SM count
+    if (grid < 1) grid = 1;
+    k_chain_seed<<<grid, K1_WARPS * 32, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_chain_columns(const DevGraph& G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
+                                        const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar, cudaStream_t stream) {
+    if (n_chains <= 0) return cudaSuccess;
+    int threads = 128; long long blocks = ((long long)n_chains * 32 + threads - 1) / threads;
+    k_export_chain_columns<<<(unsigned)blocks, threads, 0, stream>>>(G, n_chains, maxcol, n_cols, first_level, c_edge, out_level, out_edge_ord, out_gchar);
+    return cudaGetLastError();
+}
+
+} // namespace hlala

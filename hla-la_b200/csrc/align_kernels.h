@@ -1,0 +1,14 @@
+// Launchers implemented in align_kernels.cu (kept free of kernel syntax so that host-only TUs can include it).
+#pragma once
+#include "device_types.h"
+#include <cuda_runtime.h>
+
+namespace hlala {
+
+struct ChainParams;
+cudaError_t upload_score_tables(const ScoreTables& t);
+cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream);
+cudaError_t launch_export_chain_columns(const DevGraph& G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
+                                        const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar, cudaStream_t stream);
+
+} // namespace hlala

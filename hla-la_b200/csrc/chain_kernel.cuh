@@ -1,0 +1,297 @@
+// Kernel 1: one warp per chain. BAM record -> graph-space columns -> column Viterbi over the level DAG ->
+// backtrace -> (extension) -> padding -> alignment log-likelihood.
+//
+// Restates, per chain, the reference sequence
+//   processBAM::transformBAMreadToInternalAlignment   mapper/processBAM.cpp:4794-5337   (expand_cigar)
+//   processBAM::PRGContigAlignment2Seed                mapper/processBAM.cpp:2491-3017   (trim, fill, viterbi, backtrace)
+//   processBAM::cleanInitialAlignment                  mapper/processBAM.cpp:4621-4792   (clean_columns)
+//   processBAM::restrictInitialAlignmentToNoGapAreas   mapper/processBAM.cpp:4461-4619   (restrict_columns)
+//   extensionAligner::extendSeedChain                  mapper/aligner/extensionAligner.cpp:186-333 (extension hook + padding)
+//   verboseSeedChain::extendToFullSequenceLength       mapper/reads/verboseSeedChain.cpp:82-144
+//   extensionAligner::scoreOneAlignment                mapper/aligner/extensionAligner.cpp:52-182
+// as a B200 design: columns live in shared memory (one slab per warp), the edges of the chain's level window are
+// staged once from HBM into shared memory with coalesced loads, the per-column Viterbi step is a shared-memory
+// atomicMax over packed (score, canonical edge rank) keys so that "keep all arg-max incoming edges, take the first in
+// set<Edge*> order" becomes a single integer max, and the backtrace never leaves shared memory.
+#pragma once
+#include "chain_params.h"
+#include <cuda_runtime.h>
+
+namespace hlala {
+
+__constant__ ScoreTables c_tables;
+
+struct WarpSlab {
+    int32_t* lvlA; int32_t* lvlB; uint8_t* gA; uint8_t* sA; uint8_t* gB; uint8_t* sB;
+    uint32_t* bt; uint32_t* win; int32_t* weoff; uint16_t* coloff; uint32_t* cur; uint32_t* nxt;
+};
+
+__device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_cap, int win_cap) {
+    WarpSlab s; unsigned char* p = base;
+    s.lvlA = (int32_t*)p; p += (size_t)maxcol * 4;
+    s.lvlB = (int32_t*)p; p += (size_t)maxcol * 4;
+    s.bt = (uint32_t*)p; p += (size_t)pool_cap * 4;
+    s.win = (uint32_t*)p; p += (size_t)win_cap * 4;
+    s.weoff = (int32_t*)p; p += (size_t)(maxcol + 2) * 4;
+    s.cur = (uint32_t*)p; p += (size_t)K1_WCAP * 4;
+    s.nxt = (uint32_t*)p; p += (size_t)K1_WCAP * 4;
+    s.coloff = (uint16_t*)p; p += (size_t)((maxcol + 1) / 2 * 2) * 2;
+    s.gA = p; p += maxcol; s.sA = p; p += maxcol; s.gB = p; p += maxcol; s.sB = p; p += maxcol;
+    return s;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_maxscan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+    return v;
+}
+
+struct ColBuf { int32_t* lvl; uint8_t* g; uint8_t* s; };
+
+// --- transformBAMreadToInternalAlignment: CIGAR -> (level, graph char, read char) columns. Returns column count or <0.
+__device__ int expand_cigar(const ChainParams& P, int c, int64_t rd0, int rdlen, ColBuf o, int lane, int& start_raw, int& stop_raw) {
+    const DevGraph& G = P.g; const DevBatch& B = P.b;
+    int contig = B.chain_contig[c]; int gpos = B.chain_pos[c];
+    int cg0 = B.cigar_off[c], ncg = B.cigar_off[c + 1] - cg0;
+    if (contig < 0 || contig >= G.n_contigs || ncg < 1) return HLALA_E_ARG_DEV;
+    int64_t cbase = G.contig_off[contig]; int clen = (int)(G.contig_off[contig + 1] - cbase);
+    int ridx = 0, ncol = 0; start_raw = -1; stop_raw = -1;
+    for (int k = 0; k < ncg; k++) {
+        uint32_t cg = B.cigar[cg0 + k]; int op = cg & 15; int len = (int)(cg >> 4);
+        if (op == 0 || op == 7 || op == 8 || op == 2) {            // M = X consume both; D consumes the reference only
+            bool isD = (op == 2);
+            if (gpos < 0 || gpos + len > clen) return HLALA_E_INVARIANT_DEV;
+            if (!isD && ridx + len > rdlen) return HLALA_E_INVARIANT_DEV;
+            if (ncol + len > P.maxcol) return HLALA_E_CAPACITY_DEV;
+            for (int i = lane; i < len; i += 32) {
+                o.lvl[ncol + i] = G.contig_level[cbase + gpos + i];
+                o.g[ncol + i] = G.contig_seq[cbase + gpos + i];
+                o.s[ncol + i] = isD ? (uint8_t)'_' : B.bases[rd0 + ridx + i];
+            }
+            if (start_raw < 0) start_raw = ridx;
+            ncol += len; gpos += len; if (!isD) ridx += len;
+            stop_raw = ridx - 1;
+        } else if (op == 1) {                                       // I: read bases against a graph gap, level -1
+            if (ridx + len > rdlen) return HLALA_E_INVARIANT_DEV;
+            if (ncol + len > P.maxcol) return HLALA_E_CAPACITY_DEV;
+            for (int i = lane; i < len; i += 32) { o.lvl[ncol + i] = -1; o.g[ncol + i] = '_'; o.s[ncol + i] = B.bases[rd0 + ridx + i]; }
+            if (start_raw < 0) start_raw = ridx;
+            ncol += len; ridx += len; stop_raw = ridx - 1;
+        } else if (op == 4) { ridx += len; }                        // S
+        else if (op == 5) { if (k == 0) ridx += len; }              // H: a leading hard clip offsets into the primary's SEQ (processBAM.cpp:4868-4874)
+        else if (op == 6) { }                                        // P: dropped before the column walk (processBAM.cpp:4817)
+        else return HLALA_E_INVARIANT_DEV;                          // N: the reference throws (processBAM.cpp:5167)
+    }
+    __syncwarp();
+    return ncol;
+}
+
+// --- PRGContigAlignment2Seed part 1: drop leading/trailing insertion columns, insert '_'/'_' columns for skipped levels.
+__device__ int trim_and_fill(const ChainParams& P, ColBuf in, int n, ColBuf out, int lane, int& start_raw, int& stop_raw) {
+    // first / last column with a level
+    int first = n, last = -1;
+    for (int i = lane; i < n; i += 32) if (in.lvl[i] != -1) { first = min(first, i); last = max(last, i); }
+    for (int d = 16; d; d >>= 1) { first = min(first, __shfl_xor_sync(0xffffffffu, first, d)); last = max(last, __shfl_xor_sync(0xffffffffu, last, d)); }
+    if (!(first < last)) return HLALA_E_INVARIANT_DEV;              // assert(firstColumn < lastColumn), processBAM.cpp:2532
+    start_raw += first; stop_raw -= (n - 1 - last);
+    int carry_prev = -1;      // last level seen so far
+    int carry_out = 0;        // output columns emitted so far
+    for (int base = first; base <= last; base += 32) {
+        int i = base + lane; bool in_range = i <= last;
+        int lv = in_range ? in.lvl[i] : -1;
+        int seen = warp_incl_maxscan(lv, lane);                     // levels increase along the alignment
+        int prev_incl = max(seen, carry_prev);
+        int prev_excl = __shfl_up_sync(0xffffffffu, prev_incl, 1); if (lane == 0) prev_excl = carry_prev;
+        int fill = 0;
+        if (in_range && lv != -1 && prev_excl != -1) { fill = lv - prev_excl - 1; if (fill < 0) fill = -1000000; }
+        int bad = __any_sync(0xffffffffu, fill < 0);
+        if (bad) return HLALA_E_INVARIANT_DEV;                      // assert((last+1) < level), processBAM.cpp:2563
+        int width = in_range ? 1 + fill : 0;
+        int incl = warp_incl_scan(width, lane);
+        int dst_end = carry_out + incl;                             // one past this column's own slot
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (carry_out + total > P.maxcol) return HLALA_E_CAPACITY_DEV;
+        if (in_range) {
+            int own = dst_end - 1;
+            for (int k = 0; k < fill; k++) { int d = own - fill + k; out.lvl[d] = prev_excl + 1 + k; out.g[d] = '_'; out.s[d] = '_'; }
+            out.lvl[own] = lv; out.g[own] = in.g[i]; out.s[own] = in.s[i];
+        }
+        carry_out += total;
+        carry_prev = __shfl_sync(0xffffffffu, prev_incl, 31);
+    }
+    __syncwarp();
+    return carry_out;
+}
+
+// --- cleanInitialAlignment (processBAM.cpp:4621-4792). Works in place on `c`; `tmp` is scratch. Returns new column count.
+__device__ int clean_columns(ColBuf c, int n, ColBuf tmp, int lane) {
+    int any_ins = 0;
+    for (int i = lane; i < n; i += 32) any_ins |= (c.lvl[i] == -1);
+    if (!__any_sync(0xffffffffu, any_ins)) return n;               // no insertion column: no stretch can balance
+    int cleaning = 0;
+    if (lane == 0) {
+        bool inS = false; int sStart = -1, balance = 0;
+        for (int p = 0; p < n; p++) {
+            bool ins = (c.lvl[p] == -1); bool dgap = (c.g[p] == '_' && c.s[p] == '_');
+            if (ins || dgap) {
+                if (!inS) { sStart = p; inS = true; }
+                if (ins) balance++;
+                if (dgap) balance--;
+            } else if (inS) {
+                int sStop = p - 1;
+                if (balance == 0) {
+                    int L = sStop - sStart + 1, ni = 0, ng = 0;
+                    for (int q = sStart; q <= sStop; q++) { if (c.lvl[q] == -1) tmp.s[sStart + ni++] = c.s[q]; else tmp.lvl[sStart + ng++] = c.lvl[q]; }
+                    for (int q = sStart; q <= sStop; q++) {
+                        int k = q - sStart;
+                        if (k < L / 2) { c.lvl[q] = tmp.lvl[sStart + k]; c.g[q] = '_'; c.s[q] = tmp.s[sStart + k]; }
+                        else { c.lvl[q] = -1; c.g[q] = '_'; c.s[q] = '_'; }
+                    }
+                    cleaning = 1;
+                }
+                inS = false; sStart = -1; balance = 0;
+            }
+        }
+    }
+    cleaning = __shfl_sync(0xffffffffu, cleaning, 0);
+    __syncwarp();
+    if (!cleaning) return n;
+    // delete columns that are (level -1, '_', '_'): stable compaction through tmp
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane; bool keep = i < n && !(c.lvl[i] == -1 && c.g[i] == '_' && c.s[i] == '_');
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) { int d = carry + __popc(m & ((1u << lane) - 1)); tmp.lvl[d] = c.lvl[i]; tmp.g[d] = c.g[i]; tmp.s[d] = c.s[i]; }
+        carry += __popc(m);
+    }
+    __syncwarp();
+    for (int i = lane; i < carry; i += 32) { c.lvl[i] = tmp.lvl[i]; c.g[i] = tmp.g[i]; c.s[i] = tmp.s[i]; }
+    __syncwarp();
+    return carry;
+}
+
+// --- restrictInitialAlignmentToNoGapAreas (processBAM.cpp:4461-4619). In place; returns new column count.
+__device__ int restrict_columns(const ChainParams& P, ColBuf c, int n, ColBuf tmp, int lane, int& start_raw, int& stop_raw) {
+    int any = 0;
+    for (int i = lane; i < n; i += 32) { int lv = c.lvl[i]; any |= (lv != -1 && P.g.gap_stretch[lv]); }
+    if (!__any_sync(0xffffffffu, any)) return n;                   // one uninterrupted run from column 0: no candidate (processBAM.cpp:4492-4502)
+    int selA = -1, selB = -1;
+    if (lane == 0) {
+        int run = -1; int bestLen = 0;
+        auto consider = [&](int a, int b) {
+            // trim insertion columns at both ends (processBAM.cpp:4511-4527)
+            while (c.lvl[a] == -1) { a++; if (a > b || a > n - 1) break; }
+            if (a <= b) { while (c.lvl[b] == -1) { b--; if (b < a || b < 0) break; } }
+            if (b >= a) {
+                int len = b - a + 1;
+                // ascending std::sort by length, then .back(): a longest stretch; among equals the later one
+                // (libstdc++ sorts <= 16 elements by insertion sort, which is stable)
+                if (len >= bestLen) { bestLen = len; selA = a; selB = b; }
+            }
+        };
+        for (int i = 0; i < n; i++) {
+            int lv = c.lvl[i];
+            if (lv != -1 && P.g.gap_stretch[lv]) { if (run != -1) { consider(run, i - 1); run = -1; } }
+            else if (run == -1) run = i;
+        }
+        if (run != -1 && run != 0) consider(run, n - 1);
+    }
+    selA = __shfl_sync(0xffffffffu, selA, 0); selB = __shfl_sync(0xffffffffu, selB, 0);
+    if (selA < 0) return n;
+    int tot = 0, inside = 0, before = 0, after = 0;
+    for (int i = lane; i < n; i += 32) { if (c.s[i] != '_') { tot++; if (i < selA) before++; else if (i > selB) after++; else inside++; } }
+    for (int d = 16; d; d >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, d); inside += __shfl_xor_sync(0xffffffffu, inside, d); before += __shfl_xor_sync(0xffffffffu, before, d); after += __shfl_xor_sync(0xffffffffu, after, d); }
+    if (!(((double)inside / (double)tot) > 0.3)) return n;          // keep the alignment unchanged (processBAM.cpp:4606-4617)
+    int m = selB - selA + 1;
+    for (int i = lane; i < m; i += 32) { tmp.lvl[i] = c.lvl[selA + i]; tmp.g[i] = c.g[selA + i]; tmp.s[i] = c.s[selA + i]; }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) { c.lvl[i] = tmp.lvl[i]; c.g[i] = tmp.g[i]; c.s[i] = tmp.s[i]; }
+    __syncwarp();
+    start_raw += before; stop_raw -= after;
+    return m;
+}
+
+// --- column Viterbi ("sequence" pass, processBAM.cpp:2789-2832) + backtrace (2838-2932).
+// On return edge_out[col] holds the flat edge id (or -1 for insertion columns) and c.g[col] the chosen edge's emission.
+__device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const WarpSlab& S, int32_t* edge_out, int lane) {
+    const DevGraph& G = P.g;
+    if (c.lvl[0] == -1 || c.lvl[n - 1] == -1) return HLALA_E_INVARIANT_DEV;
+    const int l_first = c.lvl[0], l_last = c.lvl[n - 1];
+    const int nlev = l_last - l_first + 1;
+    if (l_last + 1 >= G.n_levels) return HLALA_E_INVARIANT_DEV;
+    // stage the window: edge offsets of levels [l_first, l_last+1] and the packed edges in between
+    for (int i = lane; i <= nlev; i += 32) S.weoff[i] = G.level_edge_off[l_first + i];
+    __syncwarp();
+    const int e_base = S.weoff[0]; const int n_win = S.weoff[nlev] - e_base;
+    const bool staged = n_win <= P.win_cap;
+    if (staged) for (int i = lane; i < n_win; i += 32) S.win[i] = G.edge_pack[e_base + i];
+    __syncwarp();
+    // init: every node of the first level, score 0 (processBAM.cpp:2696-2701)
+    const int w0 = G.level_node_off[l_first + 1] - G.level_node_off[l_first];
+    if (w0 > K1_WCAP) return HLALA_E_CAPACITY_DEV;
+    uint32_t* cur = S.cur; uint32_t* nxt = S.nxt;
+    for (int z = lane; z < w0; z += 32) cur[z] = (1u << 20) | KEY_RANK_MASK;
+    __syncwarp();
+    int pool = 0; int lev = l_first; int status = 0;
+    for (int col = 0; col < n; col++) {
+        if (c.lvl[col] == -1) continue;
+        if (c.lvl[col] != lev) { status = HLALA_E_INVARIANT_DEV; break; }     // level contiguity (processBAM.cpp:2649-2665)
+        const int e0 = S.weoff[lev - l_first] - e_base, e1 = S.weoff[lev - l_first + 1] - e_base;
+        const int wn = G.level_node_off[lev + 2] - G.level_node_off[lev + 1];
+        if (wn > K1_WCAP || (e1 - e0) > (int)KEY_RANK_MASK) { status = HLALA_E_CAPACITY_DEV; break; }
+        if (pool + wn > P.pool_cap || pool > 65535) { status = HLALA_E_CAPACITY_DEV; break; }
+        for (int z = lane; z < wn; z += 32) nxt[z] = 0;
+        __syncwarp();
+        const uint8_t sc = c.s[col], gc = c.g[col]; const bool isMatch = (sc == gc);
+        for (int e = e0 + lane; e < e1; e += 32) {
+            uint32_t pk = staged ? S.win[e] : G.edge_pack[e_base + e];
+            uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);
+            if (kf != 0 && !(isMatch && em != sc)) {
+                uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
+                atomicMax(&nxt[(pk >> 8) & 255u], key);
+            }
+        }
+        __syncwarp();
+        for (int e = e0 + lane; e < e1; e += 32) {
+            uint32_t pk = staged ? S.win[e] : G.edge_pack[e_base + e];
+            uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);
+            if (kf != 0 && !(isMatch && em != sc)) {
+                uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
+                uint32_t tz = (pk >> 8) & 255u;
+                if (nxt[tz] == key) S.bt[pool + tz] = (uint32_t)(e - e0) | ((pk & 255u) << 20);   // rank (20 bits) | from_z
+            }
+        }
+        if (lane == 0) S.coloff[col] = (uint16_t)pool;
+        pool += wn; lev++;
+        uint32_t* t = cur; cur = nxt; nxt = t;
+        __syncwarp();
+    }
+    if (status) return status;
+    // end nodes with maximal score; the first of them in canonical node order (processBAM.cpp:2856-2867)
+    const int wl = G.level_node_off[l_last + 2] - G.level_node_off[l_last + 1];
+    uint32_t best = 0;
+    for (int z = lane; z < wl; z += 32) { uint32_t k = cur[z]; if (k) { uint32_t v = ((k >> 20) << 12) | (uint32_t)(4095 - min(z, 4095)); best = max(best, v); } }
+    for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (best == 0) return HLALA_E_INVARIANT_DEV;                    // the reference asserts a non-empty column map
+    if (lane == 0) {
+        int z = 4095 - (int)(best & 4095u); int l = l_last;
+        for (int col = n - 1; col >= 0; col--) {
+            if (c.lvl[col] == -1) { edge_out[col] = -1; c.g[col] = '_'; continue; }
+            uint32_t ent = S.bt[S.coloff[col] + z];
+            int rank = (int)(ent & KEY_RANK_MASK); int fz = (int)(ent >> 20);
+            int erel = S.weoff[l - l_first] - e_base + rank;
+            uint32_t pk = staged ? S.win[erel] : G.edge_pack[e_base + erel];
+            edge_out[col] = e_base + erel; c.g[col] = (uint8_t)(pk >> 16);
+            z = fz; l--;
+        }
+    }
+    __syncwarp();
+    return 0;
+}
+
+} // namespace hlala

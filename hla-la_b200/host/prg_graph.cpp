@@ -1,0 +1,326 @@
+#include "prg_graph.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace hlala {
+
+namespace {
+
+const char* SEP = "|||";
+
+std::string read_file(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Cannot open graph file: " + path);
+    std::string s; fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    s.resize((size_t)n);
+    if (n > 0 && fread(&s[0], 1, (size_t)n, f) != (size_t)n) { fclose(f); throw std::runtime_error("short read: " + path); }
+    fclose(f);
+    return s;
+}
+
+// fields of one line split on "|||" (Graph.cpp:26, boost::iter_split + first_finder)
+void split_fields(const char* b, const char* e, std::vector<std::pair<const char*, const char*>>& out) {
+    out.clear();
+    const char* p = b;
+    while (true) {
+        const char* hit = nullptr;
+        for (const char* q = p; q + 3 <= e; q++) if (q[0] == '|' && q[1] == '|' && q[2] == '|') { hit = q; break; }
+        if (!hit) { out.emplace_back(p, e); break; }
+        out.emplace_back(p, hit); p = hit + 3;
+    }
+}
+long long to_ll(const std::pair<const char*, const char*>& f) {
+    std::string s(f.first, f.second); char* end = nullptr; long long v = strtoll(s.c_str(), &end, 10);
+    if (end == s.c_str() || *end != 0) throw std::runtime_error("graph.txt: cannot parse integer field '" + s + "'");
+    return v;
+}
+uint64_t fnv(const char* b, const char* e) { uint64_t h = 1469598103934665603ull; for (const char* p = b; p < e; p++) { h ^= (unsigned char)*p; h *= 1099511628211ull; } return h; }
+
+} // namespace
+
+int32_t FlatGraph::z_of(int32_t node) const { return node - level_node_off[node_level[node]]; }
+
+static void compute_gap_paths(FlatGraph& g);
+static void compute_gap_stretches(FlatGraph& g);
+static void load_contigs(const std::string& dir, FlatGraph& g);
+
+void load_prg_dir(const std::string& dir, FlatGraph& g) {
+    const std::string graph_path = dir + "/PRG/graph.txt";
+    std::string txt = read_file(graph_path);
+
+    // ---- section scan (Graph::readFromFile, Graph.cpp:2329-2559)
+    struct Line { const char* b; const char* e; };
+    std::vector<Line> code, nodes, edges;
+    std::vector<std::string> patched;   // lines rewritten for the "|||||||" -> "|||SLASH|||" escape (Graph.cpp:2338-2365)
+    patched.reserve(16);
+    int mode = -1;
+    const char* p = txt.data(); const char* end = p + txt.size();
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        const char* lb = p; p = nl ? nl + 1 : end;
+        while (le > lb && (le[-1] == '\r' || le[-1] == '\n')) le--;
+        if (le == lb) continue;
+        size_t len = (size_t)(le - lb);
+        if (len == 5 && !memcmp(lb, "CODE:", 5)) { mode = 1; continue; }
+        if (len == 6 && !memcmp(lb, "NODES:", 6)) { mode = 2; continue; }
+        if (len == 6 && !memcmp(lb, "EDGES:", 6)) { mode = 3; continue; }
+        if (mode < 0) throw std::runtime_error("graph.txt: content before the first section header");
+        Line L{lb, le};
+        // the 7-bar escape
+        for (const char* q = lb; q + 7 <= le; q++) {
+            if (!memcmp(q, "|||||||", 7)) {
+                std::string s(lb, le); s.replace((size_t)(q - lb), 7, "|||SLASH|||");
+                if (patched.size() == patched.capacity()) throw std::runtime_error("graph.txt: too many '|' emission codes for this loader");
+                patched.push_back(s); L.b = patched.back().data(); L.e = L.b + patched.back().size();
+                break;
+            }
+        }
+        (mode == 1 ? code : mode == 2 ? nodes : edges).push_back(L);
+    }
+
+    // ---- CODE: (locus, code) -> allele (LocusCodeAllocation::readFromVector, LocusCodeAllocation.cpp:287)
+    struct CodeEnt { char sym[8]; uint8_t code[8]; int n = 0; };
+    std::unordered_map<uint64_t, CodeEnt> codes; codes.reserve(code.size());
+    std::vector<std::pair<const char*, const char*>> f;
+    for (const Line& L : code) {
+        split_fields(L.b, L.e, f);
+        if (f.size() != 3) throw std::runtime_error("Cannot read CODE from line, expect 3 fields! Line: " + std::string(L.b, L.e));
+        long long c = to_ll(f[2]);
+        if (c < 0 || c > 250) throw std::runtime_error("Weird codedChar value: cannot convert back! " + std::string(f[2].first, f[2].second));
+        if (f[1].second - f[1].first != 1) throw std::runtime_error("graph.txt: only single-character alleles are supported on the alignment path (Graph.cpp:2517-2519)");
+        CodeEnt& ce = codes[fnv(f[0].first, f[0].second)];
+        if (ce.n >= 8) throw std::runtime_error("graph.txt: more than 8 alleles at one locus");
+        ce.sym[ce.n] = *f[1].first; ce.code[ce.n] = (uint8_t)c; ce.n++;
+    }
+
+    // ---- NODES (ordinal = order of appearance)
+    const int32_t nn = (int32_t)nodes.size();
+    std::vector<int32_t> ord_level(nn);
+    std::unordered_map<long long, int32_t> idx2ord; idx2ord.reserve((size_t)nn * 2);
+    int32_t max_level = -1;
+    for (int32_t i = 0; i < nn; i++) {
+        split_fields(nodes[i].b, nodes[i].e, f);
+        if (f.size() != 3) throw std::runtime_error("Cannot node-parse this line (expext 6 fields): " + std::string(nodes[i].b, nodes[i].e));
+        long long idx = to_ll(f[0]), lev = to_ll(f[1]);
+        if (lev < 0) throw std::runtime_error("graph.txt: negative node level");
+        ord_level[i] = (int32_t)lev; idx2ord[idx] = i; max_level = std::max(max_level, (int32_t)lev);
+    }
+    g.n_levels = max_level + 1; g.n_nodes = nn;
+    // flat node order = (level, ordinal): counting sort keeps ordinal order inside a level
+    g.level_node_off.assign((size_t)g.n_levels + 1, 0);
+    for (int32_t i = 0; i < nn; i++) g.level_node_off[(size_t)ord_level[i] + 1]++;
+    for (int32_t l = 0; l < g.n_levels; l++) g.level_node_off[l + 1] += g.level_node_off[l];
+    std::vector<int32_t> ord2flat(nn); g.node_ord.resize(nn); g.node_level.resize(nn);
+    {
+        std::vector<int32_t> cur(g.level_node_off.begin(), g.level_node_off.end() - 1);
+        for (int32_t i = 0; i < nn; i++) { int32_t fl = cur[ord_level[i]]++; ord2flat[i] = fl; g.node_ord[fl] = i; g.node_level[fl] = ord_level[i]; }
+    }
+    for (int32_t l = 0; l < g.n_levels; l++) {
+        int32_t w = g.level_node_off[l + 1] - g.level_node_off[l];
+        if (w == 0) throw std::runtime_error("graph.txt: a level without nodes");
+        g.max_nodes_per_level = std::max(g.max_nodes_per_level, w);
+    }
+
+    // ---- EDGES
+    const int32_t ne = (int32_t)edges.size();
+    g.n_edges = ne;
+    std::vector<int32_t> o_from(ne), o_to(ne); std::vector<uint8_t> o_em(ne); std::vector<uint64_t> o_loc(ne);
+    std::vector<std::pair<const char*, const char*>> o_locname(ne);
+    for (int32_t i = 0; i < ne; i++) {
+        split_fields(edges[i].b, edges[i].e, f);
+        if (f.size() != 6 && f.size() != 8) throw std::runtime_error("Cannot edge-parse this line (expext 6/8 fields): " + std::string(edges[i].b, edges[i].e));
+        std::pair<const char*, const char*> cf = f[3];
+        uint8_t codeChar;
+        if (cf.second - cf.first == 5 && !memcmp(cf.first, "SLASH", 5)) codeChar = (uint8_t)'|';
+        else if (cf.second - cf.first == 1) codeChar = (uint8_t)*cf.first;
+        else throw std::runtime_error("Cannot cast to unsigned char: " + std::string(cf.first, cf.second));
+        auto itf = idx2ord.find(to_ll(f[4])), itt = idx2ord.find(to_ll(f[5]));
+        if (itf == idx2ord.end() || itt == idx2ord.end()) throw std::runtime_error("graph.txt: edge refers to an unknown node: " + std::string(edges[i].b, edges[i].e));
+        o_from[i] = itf->second; o_to[i] = itt->second;
+        uint64_t lh = fnv(f[1].first, f[1].second); o_loc[i] = lh; o_locname[i] = f[1];
+        auto ci = codes.find(lh);
+        if (ci == codes.end()) throw std::runtime_error("graph.txt: no CODE entry for locus " + std::string(f[1].first, f[1].second));
+        int hit = -1; for (int k = 0; k < ci->second.n; k++) if (ci->second.code[k] == codeChar) hit = k;
+        if (hit < 0) throw std::runtime_error("graph.txt: cannot decode emission of edge line " + std::string(edges[i].b, edges[i].e));
+        o_em[i] = (uint8_t)ci->second.sym[hit];
+        if (ord_level[o_to[i]] != ord_level[o_from[i]] + 1) throw std::runtime_error("graph.txt: edge does not join level l to l+1");
+    }
+    g.level_edge_off.assign((size_t)g.n_levels + 1, 0);
+    for (int32_t i = 0; i < ne; i++) g.level_edge_off[(size_t)ord_level[o_from[i]] + 1]++;
+    for (int32_t l = 0; l < g.n_levels; l++) g.level_edge_off[l + 1] += g.level_edge_off[l];
+    g.edge_from.resize(ne); g.edge_to.resize(ne); g.edge_emis.resize(ne); g.edge_ord.resize(ne); g.ord_to_edge.resize(ne);
+    g.level_names.assign((size_t)std::max(0, g.n_levels - 1), std::string());
+    {
+        std::vector<int32_t> cur(g.level_edge_off.begin(), g.level_edge_off.end() - 1);
+        for (int32_t i = 0; i < ne; i++) {
+            int32_t l = ord_level[o_from[i]]; int32_t fe = cur[l]++;
+            g.edge_from[fe] = ord2flat[o_from[i]]; g.edge_to[fe] = ord2flat[o_to[i]]; g.edge_emis[fe] = o_em[i]; g.edge_ord[fe] = i; g.ord_to_edge[i] = fe;
+        }
+    }
+    for (int32_t l = 0; l + 1 < g.n_levels; l++) g.max_edges_per_level = std::max(g.max_edges_per_level, g.level_edge_off[l + 1] - g.level_edge_off[l]);
+    // adjacency (flat edge order inside a level is ordinal order, so pushing in flat order keeps set<Edge*> order)
+    g.node_out_off.assign((size_t)nn + 1, 0); g.node_in_off.assign((size_t)nn + 1, 0);
+    for (int32_t e = 0; e < ne; e++) { g.node_out_off[(size_t)g.edge_from[e] + 1]++; g.node_in_off[(size_t)g.edge_to[e] + 1]++; }
+    for (int32_t i = 0; i < nn; i++) { g.node_out_off[i + 1] += g.node_out_off[i]; g.node_in_off[i + 1] += g.node_in_off[i]; }
+    g.node_out.resize(ne); g.node_in.resize(ne);
+    {
+        std::vector<int32_t> co(g.node_out_off.begin(), g.node_out_off.end() - 1), ci(g.node_in_off.begin(), g.node_in_off.end() - 1);
+        for (int32_t e = 0; e < ne; e++) { g.node_out[co[g.edge_from[e]]++] = e; g.node_in[ci[g.edge_to[e]]++] = e; }
+    }
+    // Graph::getOneLocusIDforLevel (Graph.cpp:1253): locus of the first outgoing edge of the first node of the level
+    for (int32_t l = 0; l + 1 < g.n_levels; l++) {
+        int32_t n0 = g.level_node_off[l];
+        if (g.node_out_off[n0 + 1] == g.node_out_off[n0]) throw std::runtime_error("graph.txt: node without outgoing edges before the last level");
+        int32_t e0 = g.node_out[g.node_out_off[n0]];
+        const auto& nm = o_locname[g.edge_ord[e0]];
+        g.level_names[l].assign(nm.first, nm.second);
+    }
+
+    compute_gap_paths(g);
+    compute_gap_stretches(g);
+    load_contigs(dir, g);
+}
+
+// Graph::computeGapEdgePaths (Graph.cpp:347-476), containers keyed by canonical ordinals instead of pointers.
+static void compute_gap_paths(FlatGraph& g) {
+    typedef std::map<int32_t, std::vector<int32_t>> ByFrom;     // from-node ordinal -> edge path (flat edges)
+    std::map<int32_t, ByFrom> running;                          // current-node ordinal -> paths ending there
+    std::vector<int32_t> flat_of_ord(g.n_nodes);
+    for (int32_t i = 0; i < g.n_nodes; i++) flat_of_ord[g.node_ord[i]] = i;
+    g.path_off.assign(1, 0);
+    for (int32_t l = 0; l < g.n_levels; l++) {
+        std::map<int32_t, ByFrom> next;
+        std::set<int32_t> seen_gap_edge;
+        for (auto& cur : running) {
+            int32_t node = flat_of_ord[cur.first];
+            int non_gap = 0;
+            for (int32_t k = g.node_out_off[node]; k < g.node_out_off[node + 1]; k++) {
+                int32_t e = g.node_out[k];
+                if (g.edge_emis[e] == '_') {
+                    seen_gap_edge.insert(e);
+                    int32_t tgt = g.node_ord[g.edge_to[e]];
+                    for (auto& fp : cur.second) {
+                        auto it = next.find(tgt);
+                        if (it == next.end() || it->second.count(fp.first) == 0) { std::vector<int32_t> path = fp.second; path.push_back(e); next[tgt][fp.first] = std::move(path); }
+                    }
+                } else non_gap++;
+            }
+            if (non_gap != 0 || l == g.n_levels - 1) {
+                for (auto& fp : cur.second) {
+                    g.path_edges.insert(g.path_edges.end(), fp.second.begin(), fp.second.end());
+                    g.path_off.push_back((int32_t)g.path_edges.size());
+                    g.path_from.push_back(flat_of_ord[fp.first]); g.path_to.push_back(node);
+                }
+            }
+        }
+        if (l + 1 < g.n_levels) {
+            for (int32_t e = g.level_edge_off[l]; e < g.level_edge_off[l + 1]; e++) {   // getEdgesEmanatingFromLevel: set<Edge*> order
+                if (g.edge_emis[e] != '_' || seen_gap_edge.count(e)) continue;
+                int32_t from = g.node_ord[g.edge_from[e]], tgt = g.node_ord[g.edge_to[e]];
+                auto it = next.find(tgt);
+                if (it == next.end() || it->second.count(from) == 0) next[tgt][from] = std::vector<int32_t>(1, e);
+            }
+        }
+        running.swap(next);
+    }
+    g.n_paths = (int32_t)g.path_from.size();
+    // jump lists: gapEdgePaths_connectedNodes_forwards[first][last] / _backwards[last][first]; inner maps iterate by target pointer
+    auto build = [&](const std::vector<int32_t>& key, const std::vector<int32_t>& tgt, std::vector<int32_t>& off, std::vector<int32_t>& lst) {
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> per((size_t)g.n_nodes);
+        for (int32_t pI = 0; pI < g.n_paths; pI++) per[key[pI]].push_back({g.node_ord[tgt[pI]], pI});
+        off.assign((size_t)g.n_nodes + 1, 0); lst.clear();
+        for (int32_t n = 0; n < g.n_nodes; n++) {
+            std::sort(per[n].begin(), per[n].end());
+            for (size_t k = 1; k < per[n].size(); k++) if (per[n][k].first == per[n][k - 1].first) throw std::runtime_error("gap paths: two paths between the same pair of nodes (Graph.cpp:461-462 asserts)");
+            for (auto& x : per[n]) lst.push_back(x.second);
+            off[n + 1] = (int32_t)lst.size();
+        }
+    };
+    build(g.path_from, g.path_to, g.jump_fwd_off, g.jump_fwd_path);
+    build(g.path_to, g.path_from, g.jump_bwd_off, g.jump_bwd_path);
+}
+
+// processBAM ctor, processBAM.cpp:91-149: runs of >= 3 consecutive levels that each have at least one '_' edge
+static void compute_gap_stretches(FlatGraph& g) {
+    int32_t L = g.n_levels - 1;
+    g.gap_stretch.assign((size_t)std::max(0, L), 0);
+    int32_t start = -1;
+    auto add = [&](int32_t a, int32_t b) { if (b - a + 1 >= 3) for (int32_t i = a; i <= b; i++) g.gap_stretch[i] = 1; };
+    for (int32_t l = 0; l < L; l++) {
+        bool have = false;
+        for (int32_t e = g.level_edge_off[l]; e < g.level_edge_off[l + 1]; e++) if (g.edge_emis[e] == '_') { have = true; break; }
+        if (have) { if (start == -1) start = l; }
+        else if (start != -1) { add(start, l - 1); start = -1; }
+    }
+    if (start != -1) add(start, g.n_levels - 2);
+}
+
+static void load_contigs(const std::string& dir, FlatGraph& g) {
+    std::ifstream s(dir + "/sequences.txt");
+    if (!s.is_open()) throw std::runtime_error("Cannot open " + dir + "/sequences.txt");
+    std::string line; std::getline(s, line);
+    std::vector<std::string> header; { std::string cur; for (char c : line) { if (c == '\r' || c == '\n') continue; if (c == '\t') { header.push_back(cur); cur.clear(); } else cur.push_back(c); } header.push_back(cur); }
+    int c_id = -1, c_chr = -1;
+    for (size_t i = 0; i < header.size(); i++) { if (header[i] == "SequenceID") c_id = (int)i; if (header[i] == "Chr") c_chr = (int)i; }
+    if (c_id < 0 || c_chr < 0) throw std::runtime_error("sequences.txt: missing SequenceID/Chr columns");
+    // FASTA: id = text up to the first space (Utilities.cpp:757-808)
+    std::map<std::string, std::string> fa;
+    {
+        std::ifstream f(dir + "/mapping_PRGonly/referenceGenome.fa");
+        if (!f.is_open()) throw std::runtime_error("Cannot open " + dir + "/mapping_PRGonly/referenceGenome.fa");
+        std::string id, l2;
+        while (std::getline(f, l2)) {
+            while (!l2.empty() && (l2.back() == '\r' || l2.back() == '\n')) l2.pop_back();
+            if (l2.empty()) continue;
+            if (l2[0] == '>') { id = l2.substr(1); size_t sp = id.find(' '); if (sp != std::string::npos) id = id.substr(0, sp); fa[id].clear(); }
+            else fa[id] += l2;
+        }
+    }
+    g.contig_off.assign(1, 0);
+    std::vector<std::map<int32_t, int32_t>> anchors((size_t)g.n_levels);
+    while (std::getline(s, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+        if (line.empty()) continue;
+        std::vector<std::string> f; { std::string cur; for (char c : line) { if (c == '\t') { f.push_back(cur); cur.clear(); } else cur.push_back(c); } f.push_back(cur); }
+        if (f.size() != header.size()) throw std::runtime_error("sequences.txt: field count mismatch");
+        int32_t id = atoi(f[c_id].c_str());
+        std::string bam = f[c_chr].empty() ? ("PRG_" + f[c_id]) : f[c_chr];
+        auto it = fa.find(bam);
+        if (it == fa.end()) throw std::runtime_error(bam + " cannot be found in the PRG-only reference genome " + dir + "/mapping_PRGonly/referenceGenome.fa");
+        const std::string& seq = (bam == "PRG_5") ? std::string("N") : it->second;   // processBAM.cpp:87-88
+        // translation file, with the reference's getline semantics (processBAM.cpp:4409-4414): a trailing newline yields one extra 0
+        std::string tp = dir + "/translation/" + f[c_id] + ".txt";
+        std::ifstream ts(tp);
+        if (!ts.is_open()) throw std::runtime_error("Expected coordinate translation file not found: " + tp);
+        std::vector<int32_t> tr; std::string tl;
+        while (ts.good()) { std::getline(ts, tl); while (!tl.empty() && (tl.back() == '\r' || tl.back() == '\n')) tl.pop_back(); tr.push_back(tl.empty() ? 0 : atoi(tl.c_str())); }
+        g.contig_prg_id.push_back(id); g.contig_bam_name.push_back(bam);
+        g.contig_seq.insert(g.contig_seq.end(), seq.begin(), seq.end());
+        size_t n = seq.size();
+        if (tr.size() < n) throw std::runtime_error("translation shorter than contig " + bam);
+        g.contig_level.insert(g.contig_level.end(), tr.begin(), tr.begin() + (long)n);
+        g.contig_tr_len.push_back((int32_t)tr.size());
+        g.contig_off.push_back((int64_t)g.contig_seq.size());
+        for (size_t pos = 0; pos < tr.size(); pos++) {
+            if (tr[pos] < 0 || tr[pos] >= g.n_levels) throw std::runtime_error("translation level out of range for contig " + bam);
+            anchors[tr[pos]][id] = (int32_t)pos;   // processBAM.cpp:4441-4456 (later positions overwrite earlier ones)
+        }
+    }
+    g.n_contigs = (int32_t)g.contig_prg_id.size();
+    g.anchor_off.assign((size_t)g.n_levels + 1, 0);
+    for (int32_t l = 0; l < g.n_levels; l++) {
+        for (auto& kv : anchors[l]) { g.anchor_prg_id.push_back(kv.first); g.anchor_pos.push_back(kv.second); }
+        g.anchor_off[l + 1] = (int32_t)g.anchor_prg_id.size();
+    }
+}
+
+} // namespace hlala

@@ -1,0 +1,141 @@
+/*
+ * hlala_b200.h — C ABI of the B200-native read-to-PRG alignment path.
+ *
+ * The reference (DiltheyLab/HLA-LA) has no plugin/FFI interface; its hot path is ordinary C++ member calls
+ * (SURVEY.md §8b). This header is the seam a maintainer would cut there. Every entry point names the reference
+ * interface it stands in for (paths relative to the reference tree):
+ *
+ *   hlala_graph_load      Graph::readFromFile               Graph/Graph.cpp:2329
+ *                         Graph::computeGapEdgePaths        Graph/Graph.cpp:347
+ *                         processBAM::processBAM (gap-stretch scan, FASTA) mapper/processBAM.cpp:30-158
+ *                         processBAM::initBAM / _loadMapping  mapper/processBAM.cpp:1183, 4389
+ *   hlala_graph_to_gpu    (no counterpart: uploads the flat graph once per device)
+ *   hlala_align_pairs     processBAM::alignReads_postSeedExtraction_andStoreInto  mapper/processBAM.cpp:2340
+ *                         = sortChainsInSeeds (:1945) + per pair processBAM::alignOneReadPair (:3129)
+ *                           [alignment2Chain :3019, transformBAMreadToInternalAlignment :4794,
+ *                            PRGContigAlignment2Seed :2491, extensionAligner::extendSeedChain extensionAligner.cpp:186,
+ *                            extensionAligner::scoreOneAlignment extensionAligner.cpp:52,
+ *                            assignMappingQualities :4062] + bases_per_level counting (:2411-2426)
+ *   hlala_align_chains    the per-chain half of the above (alignment2Chain + extendSeedChain + scoreOneAlignment),
+ *                         exposed for parity tests of the kernels (reference seams B2/B3 of SURVEY.md §8b)
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types. All functions return 0 on success and a negative
+ * HLALA_E_* code on failure; hlala_last_error() returns a message for the calling thread. Nothing throws across
+ * the boundary. Inputs are caller-owned host buffers unless a name ends in _dev. There is NO CPU fallback: if no
+ * CUDA device is usable the compute entry points fail with HLALA_E_CUDA.
+ */
+#ifndef HLALA_B200_H
+#define HLALA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLALA_OK 0
+#define HLALA_E_ARG (-1)       /* bad argument */
+#define HLALA_E_IO (-2)        /* PRG directory unreadable / malformed (message carries the reference's wording) */
+#define HLALA_E_CUDA (-3)      /* CUDA runtime error or no device */
+#define HLALA_E_CAPACITY (-4)  /* a chain exceeded max_columns / graph wider than the kernels' limits */
+#define HLALA_E_INVARIANT (-5) /* an input violated one of the reference's assert()s (it would have aborted) */
+
+typedef struct hlala_graph hlala_graph_t;
+
+/* Seed batch: what `bwa mem -a -M` + BamTools hand to processBAM for a set of read pairs.
+ * Reads 2p and 2p+1 are the mates of pair p. bases/quals are the PRIMARY record's SEQ/QUAL (BAM orientation),
+ * exactly what alignOneReadPair uses for every chain of the read (processBAM.cpp:3142-3145). */
+typedef struct {
+    int64_t n_reads;               /* even */
+    const int64_t* read_off;       /* [n_reads+1] into bases/quals */
+    const uint8_t* bases;          /* ASCII */
+    const uint8_t* quals;          /* phred+33 */
+    const int32_t* chain_off;      /* [n_reads+1] into the chain arrays (BAM order; sorting by AS is done inside) */
+    const int32_t* chain_contig;   /* index into the graph's contig list (sequences.txt order == BAM RefID) */
+    const int32_t* chain_pos;      /* 0-based leftmost reference position */
+    const uint16_t* chain_flag;    /* SAM flag: 0x10 reverse, 0x100 secondary */
+    const int32_t* chain_as;       /* AS tag */
+    const int32_t* cigar_off;      /* [n_chains+1] */
+    const uint32_t* cigar;         /* BAM packed ops: len<<4 | op, op in MIDNSHP=X */
+} hlala_seed_batch_t;
+
+/* Per-chain results, one slot per input chain, in the reference's processing order (AS-sorted within a read).
+ * Column arrays are [n_chains * max_columns], row-major. All buffers caller-allocated (host). */
+typedef struct {
+    int32_t max_columns;
+    int32_t* chain_order;   /* slot -> index of the input chain */
+    int32_t* status;        /* 0 aligned, 1 skipped (other strand than the primary), <0 HLALA_E_* for this chain */
+    int32_t* n_cols;
+    int32_t* seed_begin;    /* verboseSeedChain::sequence_begin/_end of the seed before extension */
+    int32_t* seed_end;
+    double* ll;             /* extensionAligner::scoreOneAlignment */
+    int32_t* level;         /* graph_aligned_levels */
+    int32_t* edge;          /* graph_aligned_edges as canonical edge ordinals (order of appearance in graph.txt), -1 = none */
+    uint8_t* gchar;         /* graph_aligned */
+    uint8_t* schar;         /* sequence_aligned */
+    uint8_t* from_seed;     /* is_from_BWAseed */
+} hlala_chain_out_t;
+
+/* Per-pair results (verboseSeedChainPair). Column arrays are [n_reads * max_columns]. */
+typedef struct {
+    int32_t max_columns;
+    double* pair_mapq;      /* [n_pairs] */
+    double* read_mapq;      /* [n_reads] chains.first/second.mapQ */
+    uint8_t* read_reverse;  /* [n_reads] */
+    int32_t* chosen_slot;   /* [n_reads] slot (see hlala_chain_out_t) of the selected chain */
+    double* pair_ll;        /* [n_pairs] log-likelihood of the selected combination */
+    int32_t* n_cols;        /* [n_reads] */
+    int32_t* level;
+    int32_t* edge;
+    uint8_t* gchar;
+    uint8_t* schar;
+    uint8_t* from_seed;
+    uint8_t* mapq;          /* mapQ_perPosition (phred+33 as unsigned char) */
+} hlala_pair_out_t;
+
+const char* hlala_last_error(void);
+
+/* graph.txt + sequences.txt + translation/ + mapping_PRGonly/referenceGenome.fa -> flat arrays (host). */
+int hlala_graph_load(const char* prg_graph_dir, hlala_graph_t** out);
+void hlala_graph_free(hlala_graph_t* g);
+/* Upload to `device` (cudaSetDevice). Idempotent per handle. */
+int hlala_graph_to_gpu(hlala_graph_t* g, int device);
+
+/* Introspection used by the tests and the CLI. Arrays are owned by the handle. */
+int64_t hlala_graph_n_levels(const hlala_graph_t* g);
+int64_t hlala_graph_n_nodes(const hlala_graph_t* g);
+int64_t hlala_graph_n_edges(const hlala_graph_t* g);
+int64_t hlala_graph_n_paths(const hlala_graph_t* g);
+int64_t hlala_graph_n_contigs(const hlala_graph_t* g);
+/* name in: level_node_off node_ord node_level level_edge_off edge_from edge_to edge_ord path_off path_edges path_from
+ * path_to jump_fwd_off jump_fwd_path jump_bwd_off jump_bwd_path contig_level anchor_off anchor_prg_id anchor_pos (int32),
+ * edge_emis gap_stretch contig_seq (uint8), contig_off (int64). Returns element count or <0. */
+int64_t hlala_graph_array(const hlala_graph_t* g, const char* name, const void** data);
+const char* hlala_graph_level_name(const hlala_graph_t* g, int64_t level);
+
+/* Host-buffer entry points: sort chains, copy H2D, run the kernels, copy results D2H. */
+int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_chain_out_t* out);
+int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double is_mean, double is_sd,
+                      hlala_pair_out_t* out, int32_t* bases_per_level /* [n_levels-1], += ; may be NULL */);
+
+/* Device-resident variant used by bench.py: upload once, run many times, read back small results.
+ * The session owns device copies of the batch and all scratch. */
+typedef struct hlala_session hlala_session_t;
+int hlala_session_create(hlala_graph_t* g, const hlala_seed_batch_t* batch, int32_t max_columns, hlala_session_t** out);
+void hlala_session_free(hlala_session_t* s);
+/* Kernels only (inputs already in HBM). bases_per_level_dev: device int32[n_levels-1] accumulated into, may be 0. */
+int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t bases_per_level_dev, void* cuda_stream);
+/* Number of kernel launches one hlala_session_run performs. */
+int hlala_session_launches(const hlala_session_t* s);
+/* Algorithmic HBM bytes of one run (SURVEY.md §8d formula evaluated on this batch). */
+int64_t hlala_session_algorithmic_bytes(const hlala_session_t* s);
+/* Copy per-pair results of the last run to host buffers (any pointer may be NULL). */
+int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out);
+/* Small digest of the last run for checks at sizes where fetching everything is pointless:
+ * out[0]=sum n_cols, out[1]=sum of edge ordinals (+1) over all columns, out[2]=number of pairs with mapQ<1, out[3]=error count */
+int hlala_session_digest(hlala_session_t* s, int64_t out[4], double* sum_pair_ll);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,52 @@
+"""Ad-hoc GPU probe (development aid): product chains vs the compiled reference on a fresh synthetic PRG."""
+import os, sys, time, tempfile
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np
+import harness as H
+
+
+def quiet(fn, *a, **k):
+    devnull = os.open(os.devnull, os.O_WRONLY); so, se = os.dup(1), os.dup(2)
+    sys.stdout.flush(); sys.stderr.flush(); os.dup2(devnull, 1); os.dup2(devnull, 2)
+    try:
+        return fn(*a, **k)
+    finally:
+        os.dup2(so, 1); os.dup2(se, 2); os.close(devnull)
+
+
+def main():
+    d = tempfile.mkdtemp(prefix="prg")
+    H.synth_prg(d, levels=25000, haps=4, genes=2, alleles=64)
+    b = H.synth_reads(d, d + "/seeds.bin", pairs=2000, len=100, clip_frac=0.15)
+    R = quiet(H.Ref, d)
+    t = time.time(); rc = quiet(R.chains, b); t_ref = time.time() - t
+    P = H.Product(d); P.to_gpu(0)
+    t = time.time(); pc = P.chains(b); t_gpu = time.time() - t
+    print("chains", len(rc["status"]), "ref s", round(t_ref, 2), "gpu s", round(t_gpu, 3))
+    print("status ref", np.unique(rc["status"], return_counts=True), "gpu", np.unique(pc["status"], return_counts=True))
+    assert (rc["chain_order"] == pc["chain_order"]).all()
+    ok = (rc["status"] == 0) & (pc["status"] == 0)
+    L = b["read_off"][1] - b["read_off"][0]
+    noext = ok & (rc["seed_begin"] == 0) & (rc["seed_end"] == L - 1)
+    print("ok", ok.sum(), "no-extension", noext.sum())
+    sb = (rc["seed_begin"] == pc["seed_begin"]) & (rc["seed_end"] == pc["seed_end"])
+    print("seed begin/end mismatch among ok:", (~sb & ok).sum())
+    bad = 0; badll = 0
+    for i in np.nonzero(noext)[0]:
+        n = rc["n_cols"][i]
+        same = n == pc["n_cols"][i] and all((rc[k][i, :n] == pc[k][i, :n]).all() for k in ("level", "edge", "gchar", "schar", "from_seed"))
+        if not same:
+            bad += 1
+            if bad <= 3:
+                print("MISMATCH slot", i, "n", n, pc["n_cols"][i])
+                for k in ("level", "edge", "gchar", "schar"):
+                    print(k, rc[k][i, :n][:60], pc[k][i, :pc["n_cols"][i]][:60])
+        if rc["ll"][i] != pc["ll"][i]:
+            badll += 1
+            if badll <= 3:
+                print("LL differs", i, repr(rc["ll"][i]), repr(pc["ll"][i]))
+    print("column mismatches", bad, "LL not bit-equal", badll, "of", noext.sum())
+
+
+if __name__ == "__main__":
+    main()

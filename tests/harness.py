@@ -118,3 +118,83 @@ class Ref:
                   ("pair_mapq", "read_mapq", "read_reverse", "n_cols", "level", "edge", "gchar", "schar", "from_seed", "mapq")], C.byref(sec)))
         o["seconds"] = sec.value
         return o
+
+
+class SeedBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int64)] + [(k, C.c_void_p) for k in BATCH_KEYS]
+
+
+class ChainOut(C.Structure):
+    _fields_ = [("max_columns", C.c_int32)] + [(k, C.c_void_p) for k in
+                ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll", "level", "edge", "gchar", "schar", "from_seed")]
+
+
+class PairOut(C.Structure):
+    _fields_ = [("max_columns", C.c_int32)] + [(k, C.c_void_p) for k in
+                ("pair_mapq", "read_mapq", "read_reverse", "chosen_slot", "pair_ll", "n_cols", "level", "edge", "gchar", "schar", "from_seed", "mapq")]
+
+
+def make_batch_struct(b):
+    sb = SeedBatch()
+    sb.n_reads = len(b["read_off"]) - 1
+    for k in BATCH_KEYS:
+        setattr(sb, k, b[k].ctypes.data)
+    return sb
+
+
+class Product:
+    """hla-la_b200/build/libhlala_b200.so through its C ABI (include/hlala_b200.h)."""
+
+    INT32 = ("level_node_off node_ord node_level level_edge_off edge_from edge_to edge_ord path_off path_edges path_from path_to "
+             "jump_fwd_off jump_fwd_path jump_bwd_off jump_bwd_path contig_level contig_prg_id anchor_off anchor_prg_id anchor_pos").split()
+    UINT8 = "edge_emis gap_stretch contig_seq".split()
+
+    def __init__(self, prg_dir):
+        self.lib = C.CDLL(LIB_PRODUCT)
+        L = self.lib
+        L.hlala_last_error.restype = C.c_char_p
+        for fn in ("hlala_graph_n_levels", "hlala_graph_n_nodes", "hlala_graph_n_edges", "hlala_graph_n_paths", "hlala_graph_n_contigs", "hlala_graph_array"):
+            getattr(L, fn).restype = C.c_int64
+        L.hlala_graph_level_name.restype = C.c_char_p
+        self.g = C.c_void_p()
+        self._chk(L.hlala_graph_load(prg_dir.encode(), C.byref(self.g)))
+        self.on_gpu = False
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("hlala error %d: %s" % (rc, self.lib.hlala_last_error().decode()))
+
+    def close(self):
+        if self.g:
+            self.lib.hlala_graph_free(self.g)
+            self.g = C.c_void_p()
+
+    def array(self, name):
+        ptr = C.c_void_p()
+        n = self.lib.hlala_graph_array(self.g, name.encode(), C.byref(ptr))
+        assert n >= 0, name
+        dt = np.int32 if name in self.INT32 else np.uint8 if name in self.UINT8 else np.int64
+        if n == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+
+    def dims(self):
+        L = self.lib
+        return dict(n_levels=L.hlala_graph_n_levels(self.g), n_nodes=L.hlala_graph_n_nodes(self.g), n_edges=L.hlala_graph_n_edges(self.g),
+                    n_paths=L.hlala_graph_n_paths(self.g), n_contigs=L.hlala_graph_n_contigs(self.g))
+
+    def to_gpu(self, device=0):
+        self._chk(self.lib.hlala_graph_to_gpu(self.g, C.c_int(device)))
+        self.on_gpu = True
+
+    def chains(self, b, cap=1024):
+        nc = len(b["chain_contig"])
+        o = dict(chain_order=np.zeros(nc, np.int32), status=np.full(nc, -99, np.int32), n_cols=np.zeros(nc, np.int32), seed_begin=np.zeros(nc, np.int32),
+                 seed_end=np.zeros(nc, np.int32), ll=np.zeros(nc, np.float64), level=np.zeros((nc, cap), np.int32), edge=np.zeros((nc, cap), np.int32),
+                 gchar=np.zeros((nc, cap), np.uint8), schar=np.zeros((nc, cap), np.uint8), from_seed=np.zeros((nc, cap), np.uint8))
+        co = ChainOut(); co.max_columns = cap
+        for k in o:
+            setattr(co, k, o[k].ctypes.data)
+        sb = make_batch_struct(b)
+        self._chk(self.lib.hlala_align_chains(self.g, C.byref(sb), C.byref(co)))
+        return o
