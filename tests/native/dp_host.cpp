@@ -1,0 +1,45 @@
+// Test-only: runs hla-la_b200/csrc/extend_dp.h (the very code the GPU executes) on the host, so the CPU test-suite
+// can compare the extension DP with the compiled reference without a GPU.
+#include "../../hla-la_b200/host/prg_graph.h"
+#include "../../hla-la_b200/csrc/extend_dp.h"
+#include <memory>
+#include <string>
+#include <vector>
+#include <cstring>
+
+using namespace hlala;
+
+struct DpHost { FlatGraph g; std::vector<uint32_t> pack; DpGraph view; std::vector<unsigned char> scratch; };
+
+extern "C" {
+void* dp_host_open(const char* dir) {
+    try {
+        std::unique_ptr<DpHost> h(new DpHost()); load_prg_dir(dir, h->g);
+        const FlatGraph& g = h->g; h->pack.resize(g.n_edges);
+        for (int e = 0; e < g.n_edges; e++) { int f = g.edge_from[e], t = g.edge_to[e];
+            h->pack[e] = (uint32_t)(f - g.level_node_off[g.node_level[f]]) | ((uint32_t)(t - g.level_node_off[g.node_level[t]]) << 8) | ((uint32_t)g.edge_emis[e] << 16); }
+        DpGraph& v = h->view; v.n_levels = g.n_levels; v.level_node_off = g.level_node_off.data(); v.edge_pack = h->pack.data();
+        v.node_out_off = g.node_out_off.data(); v.node_out = g.node_out.data(); v.node_in_off = g.node_in_off.data(); v.node_in = g.node_in.data();
+        v.path_off = g.path_off.data(); v.path_edges = g.path_edges.data(); v.path_from = g.path_from.data(); v.path_to = g.path_to.data();
+        v.jump_fwd_off = g.jump_fwd_off.data(); v.jump_fwd_path = g.jump_fwd_path.data(); v.jump_bwd_off = g.jump_bwd_off.data(); v.jump_bwd_path = g.jump_bwd_path.data();
+        h->scratch.resize(dp_scratch_bytes());
+        return h.release();
+    } catch (...) { return nullptr; }
+}
+// seed_edge_ord: canonical ordinal of the seed's first (left, pos=0) or last (right, pos=1) edge.
+int dp_host_extend(void* hv, const uint8_t* seq, int seq_len, int start_seq, int seed_edge_ord, int pos, int32_t* out_edge_ord, uint8_t* out_s, int32_t* n_cols, int32_t* far_y, int32_t* applicable) {
+    DpHost* h = (DpHost*)hv; const FlatGraph& g = h->g;
+    int e = g.ord_to_edge[seed_edge_ord];
+    int node = pos ? g.edge_to[e] : g.edge_from[e]; int level = g.node_level[node]; int z = node - g.level_node_off[level];
+    *applicable = pos ? (level < g.n_levels - 1) : (level > 0);   // extensionAligner.cpp:224,275
+    *n_cols = 0; *far_y = start_seq;
+    if (!*applicable) return 0;
+    DpScratch S = dp_carve(h->scratch.data());
+    std::vector<int32_t> oe(DP_EXT_CAP); DpResult r;
+    int rc = dp_extend(h->view, seq, seq_len, start_seq, level, z, pos != 0, S, oe.data(), out_s, r);
+    if (rc) return rc;
+    for (int i = 0; i < r.n_cols; i++) out_edge_ord[i] = oe[i] >= 0 ? g.edge_ord[oe[i]] : -1;
+    *n_cols = r.n_cols; *far_y = r.far_y;
+    return 0;
+}
+}
