@@ -1,5 +1,7 @@
 // CUDA kernels of the alignment path + their launchers. Compiled for sm_100a only.
 #include "chain_kernel.cuh"
+#include "extend_dp.h"
+#include "pair_kernel.cuh"
 #include "align_kernels.h"
 
 #include <cstdio>
@@ -96,8 +98,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
         }
         const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
         ColBuf A{S.lvlA, S.gA, S.sA}, Bc{S.lvlB, S.gB, S.sB};
-        int start_raw = -1, stop_raw = -1, n = 0;
-        if (rc == 0) { n = expand_cigar(P, c, rd0, rdlen, A, lane, start_raw, stop_raw); if (n < 0) rc = n; }
+        int start_raw = -1, stop_raw = -1, n = 0, idf = -1, idl = -1;
+        if (rc == 0) { n = expand_cigar(P, c, rd0, rdlen, A, lane, start_raw, stop_raw, idf, idl); if (n < 0) rc = n; }
+        if (rc == 0 && lane == 0) { P.id_first[slot] = idf; P.id_last[slot] = idl; }
         if (rc == 0 && !(start_raw < stop_raw)) rc = HLALA_E_INVARIANT_DEV;     // processBAM.cpp:5245
         if (rc == 0) { n = trim_and_fill(P, A, n, Bc, lane, start_raw, stop_raw); if (n < 0) rc = n; }
         if (rc == 0) n = clean_columns(Bc, n, A, lane);
@@ -110,8 +113,80 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
         }
         if (lane == 0) { P.seed_begin[slot] = start_raw; P.seed_end[slot] = stop_raw; }
         const int l_first = Bc.lvl[0], l_last = Bc.lvl[n - 1];
+        // extensionAligner::extendSeedChain (extensionAligner.cpp:220-225, 271-276): DP only where the seed leaves read bases uncovered
+        const bool need_left = (start_raw != 0) && (l_first > 0);
+        const bool need_right = (stop_raw != rdlen - 1) && (l_last + 1 < P.g.n_levels - 1);
+        if (P.do_extension && (need_left || need_right)) {
+            int32_t* oe = P.c_edge + (size_t)slot * P.maxcol; uint8_t* os = P.c_schar + (size_t)slot * P.maxcol;
+            for (int i = lane; i < n; i += 32) { oe[i] = S.lvlA[i]; os[i] = Bc.s[i]; }
+            if (lane == 0) {
+                P.n_cols[slot] = n; P.first_level[slot] = l_first; P.last_level[slot] = l_last; P.status[slot] = CH_PENDING_EXT;
+                int idx = atomicAdd(P.pending_count, 1); P.pending_slots[idx] = slot;
+            }
+            __syncwarp();
+            continue;
+        }
         ExtView none{nullptr, nullptr, 0, 0};
         finalize_chain(P, S, slot, rd0, rdlen, S.lvlA, Bc.g, Bc.s, n, start_raw, stop_raw, l_first, l_last, none, none, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 2: extension DP, one thread per (pending chain, side). extend_dp.h documents the algorithm.
+__global__ void __launch_bounds__(64) k_extend(ExtParams E) {
+    const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= E.n_dp_threads) return;
+    DpScratch S = dp_carve(E.dp_scratch + (size_t)tid * dp_scratch_bytes());
+    DpGraph dg; dg.n_levels = G.n_levels; dg.level_node_off = G.level_node_off; dg.edge_pack = G.edge_pack;
+    dg.node_out_off = G.node_out_off; dg.node_out = G.node_out; dg.node_in_off = G.node_in_off; dg.node_in = G.node_in;
+    dg.path_off = G.path_off; dg.path_edges = G.path_edges; dg.path_from = G.path_from; dg.path_to = G.path_to;
+    dg.jump_fwd_off = G.jump_fwd_off; dg.jump_fwd_path = G.jump_fwd_path; dg.jump_bwd_off = G.jump_bwd_off; dg.jump_bwd_path = G.jump_bwd_path;
+    for (int t = tid; t < 2 * E.n_pending; t += E.n_dp_threads) {
+        const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
+        const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
+        const int n = P.n_cols[slot]; const int sb = P.seed_begin[slot], se = P.seed_end[slot];
+        const int l_first = P.first_level[slot], l_last = P.last_level[slot];
+        const int32_t* se_edge = P.c_edge + (size_t)slot * P.maxcol;
+        E.ext_n[t] = 0; E.ext_nlvl[t] = 0; E.ext_rc[t] = 0;
+        DpResult res; int rc = 0;
+        if (side == 0) {
+            if (!(sb != 0 && l_first > 0)) continue;
+            int z = (int)(G.edge_pack[se_edge[0]] & 255u);                       // From node of the first seed edge
+            rc = dp_extend(dg, B.bases + rd0, rdlen, sb, l_first, z, false, S, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res);
+        } else {
+            if (!(se != rdlen - 1 && l_last + 1 < G.n_levels - 1)) continue;
+            int z = (int)((G.edge_pack[se_edge[n - 1]] >> 8) & 255u);            // To node of the last seed edge
+            rc = dp_extend(dg, B.bases + rd0, rdlen, se + 1, l_last + 1, z, true, S, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res);
+        }
+        E.ext_rc[t] = rc;
+        if (rc == 0) { E.ext_n[t] = res.n_cols; E.ext_nlvl[t] = res.n_lvl; }
+    }
+}
+
+// Kernel 1b: splice extensions into the pending chains, pad, score (one warp per pending chain).
+__global__ void __launch_bounds__(K1_WARPS * 32) k_chain_finish(ExtParams E) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t slab = k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap);
+    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.maxcol, P.pool_cap, P.win_cap);
+    const int nw = gridDim.x * K1_WARPS;
+    for (int pi = blockIdx.x * K1_WARPS + warp; pi < E.n_pending; pi += nw) {
+        const int slot = P.pending_slots[pi];
+        const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
+        const int n = P.n_cols[slot];
+        const int32_t* ge = P.c_edge + (size_t)slot * P.maxcol; const uint8_t* gs = P.c_schar + (size_t)slot * P.maxcol;
+        for (int i = lane; i < n; i += 32) { int32_t e = ge[i]; S.lvlA[i] = e; S.sB[i] = gs[i]; S.gB[i] = e >= 0 ? (uint8_t)(G.edge_pack[e] >> 16) : (uint8_t)'_'; }
+        __syncwarp();
+        int rcL = E.ext_rc[2 * pi], rcR = E.ext_rc[2 * pi + 1];
+        if (rcL < 0 || rcR < 0) {
+            if (lane == 0) { P.status[slot] = rcL < 0 ? rcL : rcR; P.n_cols[slot] = 0; P.ll[slot] = 0; atomicAdd(P.error_count, 1); }
+            __syncwarp(); continue;
+        }
+        ExtView L{E.ext_edge + (size_t)(2 * pi) * DP_EXT_CAP, E.ext_s + (size_t)(2 * pi) * DP_EXT_CAP, E.ext_n[2 * pi], E.ext_nlvl[2 * pi]};
+        ExtView R{E.ext_edge + (size_t)(2 * pi + 1) * DP_EXT_CAP, E.ext_s + (size_t)(2 * pi + 1) * DP_EXT_CAP, E.ext_n[2 * pi + 1], E.ext_nlvl[2 * pi + 1]};
+        finalize_chain(P, S, slot, rd0, rdlen, S.lvlA, S.gB, S.sB, n, P.seed_begin[slot], P.seed_end[slot], P.first_level[slot], P.last_level[slot], L, R, lane);
     }
 }
 
@@ -156,6 +231,43 @@ cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t strea
     k_chain_seed<<<grid, K1_WARPS * 32, smem, stream>>>(P);
     return cudaGetLastError();
 }
+
+cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream) {
+    if (E.n_pending <= 0) return cudaSuccess;
+    int threads = 64; int blocks = (E.n_dp_threads + threads - 1) / threads;
+    k_extend<<<blocks, threads, 0, stream>>>(E);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {
+    if (E.n_pending <= 0) return cudaSuccess;
+    size_t smem = k1_slab_bytes(E.C.maxcol, E.C.pool_cap, E.C.win_cap) * K1_WARPS;
+    static size_t configured = 0;
+    if (smem > configured) { cudaError_t e = cudaFuncSetAttribute(k_chain_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; configured = smem; }
+    int per_sm = 1; cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_finish, K1_WARPS * 32, smem);
+    if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)E.n_pending + K1_WARPS - 1) / K1_WARPS;
+    int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm); if (grid < 1) grid = 1;
+    k_chain_finish<<<grid, K1_WARPS * 32, smem, stream>>>(E);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream) {
+    long long n_pairs = P.b.n_reads / 2;
+    if (n_pairs <= 0) return cudaSuccess;
+    size_t smem = k3_slab_bytes(P.maxcol) * K3_WARPS;
+    static size_t configured = 0;
+    if (smem > configured) { cudaError_t e = cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; configured = smem; }
+    int per_sm = 1; cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair, K3_WARPS * 32, smem);
+    if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
+    long long want = (n_pairs + K3_WARPS - 1) / K3_WARPS;
+    int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm); if (grid < 1) grid = 1;
+    k_pair<<<grid, K3_WARPS * 32, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+size_t dp_thread_scratch_bytes() { return dp_scratch_bytes(); }
+int dp_ext_cap() { return DP_EXT_CAP; }
 
 cudaError_t launch_export_chain_columns(const DevGraph& G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
                                         const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar, cudaStream_t stream) {

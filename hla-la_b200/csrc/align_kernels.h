@@ -5,9 +5,14 @@
 
 namespace hlala {
 
-struct ChainParams;
+struct ChainParams; struct ExtParams; struct PairParams;
 cudaError_t upload_score_tables(const ScoreTables& t);
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream);
+cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream);
+cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream);
+cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream);
+size_t dp_thread_scratch_bytes();
+int dp_ext_cap();
 cudaError_t launch_export_chain_columns(const DevGraph& G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
                                         const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar, cudaStream_t stream);
 

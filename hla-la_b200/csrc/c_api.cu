@@ -117,20 +117,147 @@ int check_batch(const hlala_seed_batch_t* b) {
 }
 
 struct ChainScratch {
-    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count;
+    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count;
     void alloc(int32_t n_chains, int32_t maxcol) {
         size_t nc = (size_t)std::max(n_chains, 1);
         status.alloc(nc * 4); n_cols.alloc(nc * 4); seed_begin.alloc(nc * 4); seed_end.alloc(nc * 4); ll.alloc(nc * 8); first_level.alloc(nc * 4); last_level.alloc(nc * 4);
         c_edge.alloc(nc * maxcol * 4); c_schar.alloc(nc * maxcol); c_fromseed.alloc(nc * maxcol); error_count.alloc(4);
+        id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4);
     }
     void fill(ChainParams& P) {
         P.status = status.as<int32_t>(); P.n_cols = n_cols.as<int32_t>(); P.seed_begin = seed_begin.as<int32_t>(); P.seed_end = seed_end.as<int32_t>(); P.ll = ll.as<double>();
         P.first_level = first_level.as<int32_t>(); P.last_level = last_level.as<int32_t>(); P.c_edge = c_edge.as<int32_t>(); P.c_schar = c_schar.as<uint8_t>(); P.c_fromseed = c_fromseed.as<uint8_t>();
-        P.error_count = error_count.as<int32_t>();
+        P.error_count = error_count.as<int32_t>(); P.id_first = id_first.as<int32_t>(); P.id_last = id_last.as<int32_t>();
+        P.pending_slots = pending_slots.as<int32_t>(); P.pending_count = pending_count.as<int32_t>();
     }
 };
 
 void chain_caps(int32_t maxcol, ChainParams& P) { P.maxcol = maxcol; P.pool_cap = 4 * maxcol; P.win_cap = 4 * maxcol; }
+
+// boost::math::pdf(normal) as Boost.Math computes it (processBAM.cpp:2342-2346, 3446-3472)
+double normal_pdf(double mean, double sd, double x) {
+    double exponent = x - mean; exponent *= -exponent; exponent /= 2 * sd * sd;
+    double result = exp(exponent); result /= sd * sqrt(2 * 3.14159265358979323846264338327950288);
+    return result;
+}
+// Utilities::PCorrectToPhred (Utilities.cpp:178-203)
+int pcorrect_to_phred(double PCorrect) {
+    double pWrong = 1 - PCorrect; if (pWrong == 0) pWrong = 1e-100;
+    double phred1 = -10.0 * log10(pWrong);
+    if ((phred1 + 33) > 255) phred1 = 255 - 33;
+    return (int)round(phred1 + 33);
+}
+// thr[k] = smallest double q in [0,1] with PCorrectToPhred(q) >= 33 + k (the function is monotone in q)
+std::vector<double> phred_thresholds() {
+    std::vector<double> thr(223, 0.0);
+    for (int k = 1; k <= 222; k++) {
+        uint64_t lo = 0, hi; double one = 1.0; memcpy(&hi, &one, 8);     // bit patterns of non-negative doubles are ordered
+        if (pcorrect_to_phred(1.0) < 33 + k) { thr[k] = 2.0; continue; }
+        while (lo < hi) { uint64_t mid = lo + (hi - lo) / 2; double q; memcpy(&q, &mid, 8); if (pcorrect_to_phred(q) >= 33 + k) hi = mid; else lo = mid + 1; }
+        memcpy(&thr[k], &lo, 8);
+    }
+    return thr;
+}
+
+struct Pipeline {
+    hlala_graph* g = nullptr; int32_t maxcol = 0;
+    PreparedBatch pb; DeviceBatch db; ChainScratch cs;
+    DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch; int32_t ext_cap = 0; int32_t n_dp_threads = 0;
+    DevBuf is_table, phred_thr; double is_mean = -1, is_sd = -1, is_pen = 0; int32_t is_dmin = 0, is_n = 0;
+    DevBuf pair_mapq, read_mapq, read_reverse, chosen_slot, pair_ll, pair_status, digest;
+    DevBuf o_n_cols, o_level, o_edge, o_gchar, o_schar, o_fromseed, o_mapq; bool have_columns = false;
+    int launches = 0; int64_t algo_bytes = 0; int32_t n_pending = 0; int32_t n_errors = 0;
+
+    void prepare(hlala_graph* graph, const hlala_seed_batch_t& b, int32_t mc, cudaStream_t st) {
+        g = graph; maxcol = mc;
+        pb.build(b); db.upload(b, pb, st); cs.alloc(pb.n_chains, mc);
+        size_t nr = (size_t)std::max<int64_t>(b.n_reads, 2), np = nr / 2;
+        pair_mapq.alloc(np * 8); read_mapq.alloc(nr * 8); read_reverse.alloc(nr); chosen_slot.alloc(nr * 4); pair_ll.alloc(np * 8); pair_status.alloc(np * 4); digest.alloc(32);
+        phred_thr.upload(phred_thresholds(), st);
+        n_dp_threads = g->n_sm * 2 * 64;
+        dp_scratch.alloc((size_t)n_dp_threads * dp_thread_scratch_bytes());
+        CUDA_OK(cudaMemsetAsync(dp_scratch.p, 0, dp_scratch.bytes, st));
+        // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
+        // chosen alignment columns written once, per-pair scalars, coverage RMW
+        int64_t nb = b.read_off[b.n_reads]; int64_t ncg = b.cigar_off[pb.n_chains];
+        int64_t cols = 0; for (int32_t c = 0; c < pb.n_chains; c++) for (int32_t k = b.cigar_off[c]; k < b.cigar_off[c + 1]; k++) { int op = b.cigar[k] & 15; if (op == 0 || op == 1 || op == 2 || op == 7 || op == 8) cols += b.cigar[k] >> 4; }
+        algo_bytes = 2 * nb + 24ll * pb.n_chains + 4 * ncg + cols * (4 + 7) + 2 * nb * 12 / 2 + 40ll * (b.n_reads / 2) + 4 * nb;
+    }
+    void ensure_columns() {
+        if (have_columns) return;
+        size_t n = (size_t)std::max<int64_t>(pb.n_reads, 2) * maxcol;
+        o_n_cols.alloc((size_t)std::max<int64_t>(pb.n_reads, 2) * 4); o_level.alloc(n * 4); o_edge.alloc(n * 4); o_gchar.alloc(n); o_schar.alloc(n); o_fromseed.alloc(n); o_mapq.alloc(n);
+        have_columns = true;
+    }
+    ChainParams chain_params() { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, P); P.do_extension = 1; cs.fill(P); return P; }
+
+    void run_chains(cudaStream_t st) {
+        launches = 0;
+        const int32_t nc = pb.n_chains;
+        CUDA_OK(cudaMemsetAsync(cs.error_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st));
+        CUDA_OK(cudaMemsetAsync(cs.status.p, 0xFF, (size_t)std::max(nc, 1) * 4, st));
+        ChainParams P = chain_params();
+        if (nc > 0) { CUDA_OK(launch_chain_seed(P, g->n_sm, st)); launches++; }
+        CUDA_OK(cudaMemcpyAsync(&n_pending, cs.pending_count.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (n_pending > 0) {
+            if (n_pending > ext_cap) {
+                ext_cap = n_pending + n_pending / 4 + 64; size_t nt = (size_t)ext_cap * 2;
+                ext_edge.alloc(nt * dp_ext_cap() * 4); ext_s.alloc(nt * dp_ext_cap()); ext_n.alloc(nt * 4); ext_nlvl.alloc(nt * 4); ext_rc.alloc(nt * 4);
+            }
+            ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = ext_edge.as<int32_t>(); E.ext_s = ext_s.as<uint8_t>(); E.ext_n = ext_n.as<int32_t>();
+            E.ext_nlvl = ext_nlvl.as<int32_t>(); E.ext_rc = ext_rc.as<int32_t>(); E.dp_scratch = dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
+            CUDA_OK(launch_extend(E, st)); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); launches += 2;
+        }
+    }
+    void set_insert_size(double mean, double sd, cudaStream_t st) {
+        if (mean == is_mean && sd == is_sd) return;
+        if (!(sd > 0)) throw std::runtime_error("insert size sd must be positive");
+        double pen = normal_pdf(mean, sd, mean + 8 * sd);
+        if (!(pen > 0 && pen <= 1)) throw std::runtime_error("insert size penalty out of range (the reference asserts 0 < pdf <= 1)");
+        is_pen = log(pen);
+        long long lo = (long long)floor(mean - 40 * sd) - 2, hi = (long long)ceil(mean + 40 * sd) + 2;
+        if (hi - lo + 1 > 4000000) throw std::runtime_error("insert size table too large");
+        std::vector<double> t((size_t)(hi - lo + 1));
+        for (long long d = lo; d <= hi; d++) { double p = normal_pdf(mean, sd, (double)d); t[(size_t)(d - lo)] = (p <= 0) ? is_pen : log(p); }
+        if (normal_pdf(mean, sd, (double)(lo - 1)) > 0 || normal_pdf(mean, sd, (double)(hi + 1)) > 0) throw std::runtime_error("insert size table does not cover the support of the density");
+        is_table.upload(t, st); is_dmin = (int32_t)lo; is_n = (int32_t)t.size(); is_mean = mean; is_sd = sd;
+    }
+    void run_pairs(double mean, double sd, int32_t* bases_per_level_dev, bool want_columns, cudaStream_t st) {
+        set_insert_size(mean, sd, st);
+        if (want_columns) ensure_columns();
+        CUDA_OK(cudaMemsetAsync(digest.p, 0, 32, st));
+        PairParams Q{}; Q.g = g->d; Q.b = db.view; Q.maxcol = maxcol;
+        Q.status = cs.status.as<int32_t>(); Q.n_cols = cs.n_cols.as<int32_t>(); Q.ll = cs.ll.as<double>(); Q.first_level = cs.first_level.as<int32_t>(); Q.last_level = cs.last_level.as<int32_t>();
+        Q.id_first = cs.id_first.as<int32_t>(); Q.id_last = cs.id_last.as<int32_t>(); Q.c_edge = cs.c_edge.as<int32_t>(); Q.c_schar = cs.c_schar.as<uint8_t>(); Q.c_fromseed = cs.c_fromseed.as<uint8_t>();
+        Q.is_table = is_table.as<double>(); Q.is_dmin = is_dmin; Q.is_n = is_n; Q.is_penalty = is_pen; Q.phred_thr = phred_thr.as<double>();
+        Q.pair_mapq = pair_mapq.as<double>(); Q.read_mapq = read_mapq.as<double>(); Q.read_reverse = read_reverse.as<uint8_t>(); Q.chosen_slot = chosen_slot.as<int32_t>();
+        Q.pair_ll = pair_ll.as<double>(); Q.pair_status = pair_status.as<int32_t>();
+        if (want_columns) { Q.out_n_cols = o_n_cols.as<int32_t>(); Q.out_level = o_level.as<int32_t>(); Q.out_edge = o_edge.as<int32_t>(); Q.out_gchar = o_gchar.as<uint8_t>(); Q.out_schar = o_schar.as<uint8_t>(); Q.out_fromseed = o_fromseed.as<uint8_t>(); Q.out_mapq = o_mapq.as<uint8_t>(); }
+        Q.bases_per_level = bases_per_level_dev; Q.error_count = cs.error_count.as<int32_t>(); Q.digest = digest.as<unsigned long long>();
+        if (pb.n_reads >= 2) { CUDA_OK(launch_pair(Q, g->n_sm, st)); launches++; }
+    }
+    void fetch(hlala_pair_out_t* out, cudaStream_t st) {
+        size_t nr = (size_t)pb.n_reads, np = nr / 2;
+        if (out->pair_mapq) pair_mapq.download(out->pair_mapq, np, st);
+        if (out->read_mapq) read_mapq.download(out->read_mapq, nr, st);
+        if (out->read_reverse) read_reverse.download(out->read_reverse, nr, st);
+        if (out->chosen_slot) chosen_slot.download(out->chosen_slot, nr, st);
+        if (out->pair_ll) pair_ll.download(out->pair_ll, np, st);
+        if (have_columns) {
+            size_t n = nr * maxcol;
+            if (out->n_cols) o_n_cols.download(out->n_cols, nr, st);
+            if (out->level) o_level.download(out->level, n, st);
+            if (out->edge) o_edge.download(out->edge, n, st);
+            if (out->gchar) o_gchar.download(out->gchar, n, st);
+            if (out->schar) o_schar.download(out->schar, n, st);
+            if (out->from_seed) o_fromseed.download(out->from_seed, n, st);
+            if (out->mapq) o_mapq.download(out->mapq, n, st);
+        }
+        CUDA_OK(cudaMemcpyAsync(&n_errors, cs.error_count.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+};
 
 template <class F> int guarded(F&& f) {
     try { return f(); }
@@ -214,18 +341,13 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(g->device));
         cudaStream_t st = 0;
-        PreparedBatch pb; pb.build(*batch);
-        DeviceBatch db; db.upload(*batch, pb, st);
-        const int32_t nc = pb.n_chains, mc = out->max_columns;
-        ChainScratch cs; cs.alloc(nc, mc);
-        CUDA_OK(cudaMemsetAsync(cs.error_count.p, 0, 4, st));
-        CUDA_OK(cudaMemsetAsync(cs.status.p, 0xFF, (size_t)std::max(nc, 1) * 4, st));
-        ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(mc, P); P.do_extension = 1; cs.fill(P);
-        CUDA_OK(launch_chain_seed(P, g->n_sm, st));
+        Pipeline pl; pl.prepare(g, *batch, out->max_columns, st);
+        pl.run_chains(st);
+        const int32_t nc = pl.pb.n_chains, mc = out->max_columns; ChainScratch& cs = pl.cs;
         DevBuf o_level, o_edge, o_g; size_t ncol = (size_t)std::max(nc, 1) * mc;
         o_level.alloc(ncol * 4); o_edge.alloc(ncol * 4); o_g.alloc(ncol);
-        CUDA_OK(launch_export_chain_columns(g->d, nc, mc, P.n_cols, P.first_level, P.c_edge, o_level.as<int32_t>(), o_edge.as<int32_t>(), o_g.as<uint8_t>(), st));
-        if (out->chain_order) memcpy(out->chain_order, pb.chain_order.data(), (size_t)nc * 4);
+        CUDA_OK(launch_export_chain_columns(g->d, nc, mc, cs.n_cols.as<int32_t>(), cs.first_level.as<int32_t>(), cs.c_edge.as<int32_t>(), o_level.as<int32_t>(), o_edge.as<int32_t>(), o_g.as<uint8_t>(), st));
+        if (out->chain_order) memcpy(out->chain_order, pl.pb.chain_order.data(), (size_t)nc * 4);
         if (out->status) cs.status.download(out->status, nc, st);
         if (out->n_cols) cs.n_cols.download(out->n_cols, nc, st);
         if (out->seed_begin) cs.seed_begin.download(out->seed_begin, nc, st);
@@ -237,6 +359,79 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
         if (out->schar) cs.c_schar.download(out->schar, (size_t)nc * mc, st);
         if (out->from_seed) cs.c_fromseed.download(out->from_seed, (size_t)nc * mc, st);
         CUDA_OK(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double is_mean, double is_sd, hlala_pair_out_t* out, int32_t* bases_per_level) {
+    if (!g || !out) return fail(HLALA_E_ARG, "hlala_align_pairs: null argument");
+    if (int rc = check_batch(batch)) return rc;
+    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
+    if (out->max_columns < 32 || out->max_columns > 2040) return fail(HLALA_E_ARG, "max_columns must be in [32, 2040]");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(g->device));
+        cudaStream_t st = 0;
+        Pipeline pl; pl.prepare(g, *batch, out->max_columns, st);
+        DevBuf bpl; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
+        if (bases_per_level) { bpl.alloc(nl * 4); CUDA_OK(cudaMemsetAsync(bpl.p, 0, nl * 4, st)); }
+        pl.run_chains(st);
+        pl.run_pairs(is_mean, is_sd, bases_per_level ? bpl.as<int32_t>() : nullptr, true, st);
+        pl.fetch(out, st);
+        if (bases_per_level) {
+            std::vector<int32_t> h(nl); bpl.download(h.data(), nl, st); CUDA_OK(cudaStreamSynchronize(st));
+            for (size_t i = 0; i + 1 < (size_t)g->h.n_levels; i++) bases_per_level[i] += h[i];
+        }
+        if (pl.n_errors > 0) return fail(HLALA_E_INVARIANT, std::to_string(pl.n_errors) + " chains/pairs violated a reference invariant or a kernel capacity; see per-chain status via hlala_align_chains");
+        return 0;
+    });
+}
+
+struct hlala_session { Pipeline pl; };
+
+int hlala_session_create(hlala_graph_t* g, const hlala_seed_batch_t* batch, int32_t max_columns, hlala_session_t** out) {
+    if (!g || !out) return fail(HLALA_E_ARG, "hlala_session_create: null argument");
+    *out = nullptr;
+    if (int rc = check_batch(batch)) return rc;
+    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
+    if (max_columns < 32 || max_columns > 2040) return fail(HLALA_E_ARG, "max_columns must be in [32, 2040]");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(g->device));
+        std::unique_ptr<hlala_session> s(new hlala_session());
+        s->pl.prepare(g, *batch, max_columns, 0);
+        CUDA_OK(cudaStreamSynchronize(0));
+        *out = s.release();
+        return 0;
+    });
+}
+void hlala_session_free(hlala_session_t* s) { delete s; }
+
+int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t bases_per_level_dev, void* cuda_stream) {
+    if (!s) return fail(HLALA_E_ARG, "hlala_session_run: null session");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(s->pl.g->device));
+        cudaStream_t st = (cudaStream_t)cuda_stream;
+        s->pl.run_chains(st);
+        s->pl.run_pairs(is_mean, is_sd, (int32_t*)(uintptr_t)bases_per_level_dev, false, st);
+        return 0;
+    });
+}
+int hlala_session_launches(const hlala_session_t* s) { return s ? s->pl.launches : -1; }
+int64_t hlala_session_algorithmic_bytes(const hlala_session_t* s) { return s ? s->pl.algo_bytes : -1; }
+int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out) {
+    if (!s || !out) return fail(HLALA_E_ARG, "hlala_session_fetch: null argument");
+    return guarded([&]() { CUDA_OK(cudaSetDevice(s->pl.g->device)); s->pl.fetch(out, 0); return 0; });
+}
+int hlala_session_digest(hlala_session_t* s, int64_t out[4], double* sum_pair_ll) {
+    if (!s || !out) return fail(HLALA_E_ARG, "hlala_session_digest: null argument");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(s->pl.g->device));
+        unsigned long long d[4]; CUDA_OK(cudaMemcpy(d, s->pl.digest.p, 32, cudaMemcpyDeviceToHost));
+        int32_t ne = 0; CUDA_OK(cudaMemcpy(&ne, s->pl.cs.error_count.p, 4, cudaMemcpyDeviceToHost));
+        out[0] = (int64_t)d[0]; out[1] = (int64_t)d[1]; out[2] = (int64_t)d[2]; out[3] = ne;
+        if (sum_pair_ll) {
+            size_t np = (size_t)s->pl.pb.n_reads / 2; std::vector<double> v(np); s->pl.pair_ll.download(v.data(), np, 0); CUDA_OK(cudaStreamSynchronize(0));
+            double acc = 0; for (double x : v) acc += x; *sum_pair_ll = acc;
+        }
         return 0;
     });
 }

@@ -54,13 +54,14 @@ __device__ __forceinline__ int warp_incl_maxscan(int v, int lane) {
 struct ColBuf { int32_t* lvl; uint8_t* g; uint8_t* s; };
 
 // --- transformBAMreadToInternalAlignment: CIGAR -> (level, graph char, read char) columns. Returns column count or <0.
-__device__ int expand_cigar(const ChainParams& P, int c, int64_t rd0, int rdlen, ColBuf o, int lane, int& start_raw, int& stop_raw) {
+__device__ int expand_cigar(const ChainParams& P, int c, int64_t rd0, int rdlen, ColBuf o, int lane, int& start_raw, int& stop_raw, int& id_first, int& id_last) {
     const DevGraph& G = P.g; const DevBatch& B = P.b;
     int contig = B.chain_contig[c]; int gpos = B.chain_pos[c];
     int cg0 = B.cigar_off[c], ncg = B.cigar_off[c + 1] - cg0;
     if (contig < 0 || contig >= G.n_contigs || ncg < 1) return HLALA_E_ARG_DEV;
     int64_t cbase = G.contig_off[contig]; int clen = (int)(G.contig_off[contig + 1] - cbase);
     int ridx = 0, ncol = 0; start_raw = -1; stop_raw = -1;
+    const int pos0 = gpos;
     for (int k = 0; k < ncg; k++) {
         uint32_t cg = B.cigar[cg0 + k]; int op = cg & 15; int len = (int)(cg >> 4);
         if (op == 0 || op == 7 || op == 8 || op == 2) {            // M = X consume both; D consumes the reference only
@@ -87,6 +88,9 @@ __device__ int expand_cigar(const ChainParams& P, int c, int64_t rd0, int rdlen,
         else if (op == 6) { }                                        // P: dropped before the column walk (processBAM.cpp:4817)
         else return HLALA_E_INVARIANT_DEV;                          // N: the reference throws (processBAM.cpp:5167)
     }
+    // alignment_get_startstop_PRGcoordinates (processBAM.cpp:3840): levels of Position and GetEndPosition(false, true)
+    if (pos0 < 0 || gpos - 1 >= clen || gpos - 1 < pos0) return HLALA_E_INVARIANT_DEV;
+    id_first = G.contig_level[cbase + pos0]; id_last = G.contig_level[cbase + gpos - 1];
     __syncwarp();
     return ncol;
 }

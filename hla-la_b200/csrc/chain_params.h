@@ -27,7 +27,50 @@ struct ChainParams {
     uint8_t* c_schar;      // [n_chains * maxcol]
     uint8_t* c_fromseed;   // [n_chains * maxcol]
     int32_t* error_count;  // global counter of chains that ended with status < 0
+    int32_t* id_first; int32_t* id_last;   // PRG levels of the BAM record's first/last reference base (processBAM.cpp:3840): de-dup key
+    int32_t* pending_slots; int32_t* pending_count;   // chains whose seed needs the extension DP
 };
+
+constexpr int32_t CH_PENDING_EXT = 2;
+
+// extension stage (one thread per (pending chain, side))
+struct ExtParams {
+    ChainParams C;
+    int32_t n_pending;
+    int32_t* ext_edge; uint8_t* ext_s;      // [2 * n_pending * DP_EXT_CAP]
+    int32_t* ext_n; int32_t* ext_nlvl; int32_t* ext_rc;   // [2 * n_pending]
+    unsigned char* dp_scratch; int32_t n_dp_threads;
+};
+
+constexpr int K3_WARPS = 4;
+constexpr int K3_KCAP = 32;        // kept chains per read
+constexpr int K3_COMBO_CAP = 512;  // chain combinations per pair
+
+struct PairParams {
+    DevGraph g; DevBatch b; int32_t maxcol;
+    // chain records (outputs of the chain stage)
+    const int32_t* status; const int32_t* n_cols; const double* ll; const int32_t* first_level; const int32_t* last_level;
+    const int32_t* id_first; const int32_t* id_last; const int32_t* c_edge; const uint8_t* c_schar; const uint8_t* c_fromseed;
+    // insert-size model: log N(d; mean, sd) for integer d in [is_dmin, is_dmin + is_n), is_penalty elsewhere (processBAM.cpp:3446-3472)
+    const double* is_table; int32_t is_dmin; int32_t is_n; double is_penalty;
+    const double* phred_thr;       // [223]: smallest Q mapped to phred char 33+k (Utilities::PCorrectToPhred, Utilities.cpp:178-203)
+    // per pair / per read outputs
+    double* pair_mapq; double* read_mapq; uint8_t* read_reverse; int32_t* chosen_slot; double* pair_ll; int32_t* pair_status;
+    int32_t* out_n_cols; int32_t* out_level; int32_t* out_edge; uint8_t* out_gchar; uint8_t* out_schar; uint8_t* out_fromseed; uint8_t* out_mapq;   // [n_reads * maxcol], may be null
+    int32_t* bases_per_level;      // [n_levels-1] += , may be null
+    int32_t* error_count;
+    unsigned long long* digest;    // [4]: sum n_cols, sum (edge ordinal + 1), pairs with mapQ < 1, -
+};
+
+__host__ __device__ inline size_t k3_slab_bytes(int maxcol) {
+    size_t b = 0;
+    b += (size_t)K3_COMBO_CAP * 8;      // LL / PP
+    b += (size_t)maxcol * 8;            // Q
+    b += (size_t)maxcol * 4 * 2;        // member masks, base->level table
+    b += (size_t)maxcol * 2;            // base->gchar, level info
+    b += (size_t)K3_KCAP * 4 * 2;       // kept slots
+    return (b + 15) & ~size_t(15);
+}
 
 __host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int win_cap) {
     size_t b = 0;

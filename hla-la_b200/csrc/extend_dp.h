@@ -37,26 +37,29 @@ constexpr int DP_LIST_CAP = 512;        // wavefront lists / touched cells per d
 constexpr int DP_TDHASH_CAP = 1024;     // power of two
 constexpr int DP_ACH_CAP = 256;
 constexpr int DP_EXT_CAP = 512;         // output columns per extension
+static_assert(DP_CELL_CAP <= 4096 && DP_LIST_CAP <= 1024, "hash entry layouts");
 
 struct DpBT { int32_t src; int32_t edge; int32_t mat; };      // edge: flat id, -1 none, <= -2: gap path (-2 - id)
 struct DpCell { int32_t x, y, z; int32_t D, GG, SG; DpBT bD, bGG, bSG; };
 struct DpTouch { int32_t x, y, z; int32_t hasD, hasGG, hasSG; int32_t vD, vGG, vSG; DpBT bD, bGG, bSG; };
 
 struct DpScratch {
-    DpCell* cells; int32_t* hash; DpTouch* td; int32_t* tdhash; int32_t* m1; int32_t* m2; int32_t* mt; int32_t* order; int32_t* ach; int32_t* maxima;
+    DpCell* cells; uint32_t* hash; DpTouch* td; uint32_t* tdhash; int32_t* m1; int32_t* m2; int32_t* mt; int32_t* order; int32_t* ach; int32_t* maxima;
+    uint32_t* gens;   // [0] generation of the cell hash, [1] generation of the per-diagonal hash (entries of older generations read as empty)
 };
 __host__ __device__ inline size_t dp_scratch_bytes() {
-    return sizeof(DpCell) * DP_CELL_CAP + 4 * DP_HASH_CAP + sizeof(DpTouch) * DP_LIST_CAP + 4 * DP_TDHASH_CAP + 4 * DP_LIST_CAP * 4 + 4 * DP_ACH_CAP * 2 + 4 * DP_LIST_CAP;
+    return sizeof(DpCell) * DP_CELL_CAP + 4 * DP_HASH_CAP + sizeof(DpTouch) * DP_LIST_CAP + 4 * DP_TDHASH_CAP + 4 * DP_LIST_CAP * 4 + 4 * DP_ACH_CAP * 2 + 4 * DP_LIST_CAP + 16;
 }
 __host__ __device__ inline DpScratch dp_carve(unsigned char* p) {
     DpScratch s;
     s.cells = (DpCell*)p; p += sizeof(DpCell) * DP_CELL_CAP;
     s.td = (DpTouch*)p; p += sizeof(DpTouch) * DP_LIST_CAP;
-    s.hash = (int32_t*)p; p += 4 * DP_HASH_CAP;
-    s.tdhash = (int32_t*)p; p += 4 * DP_TDHASH_CAP;
+    s.hash = (uint32_t*)p; p += 4 * DP_HASH_CAP;
+    s.tdhash = (uint32_t*)p; p += 4 * DP_TDHASH_CAP;
     s.m1 = (int32_t*)p; p += 4 * DP_LIST_CAP; s.m2 = (int32_t*)p; p += 4 * DP_LIST_CAP; s.mt = (int32_t*)p; p += 4 * DP_LIST_CAP; s.order = (int32_t*)p; p += 4 * DP_LIST_CAP;
     s.ach = (int32_t*)p; p += 4 * DP_ACH_CAP * 2;
     s.maxima = (int32_t*)p; p += 4 * DP_LIST_CAP;
+    s.gens = (uint32_t*)p; p += 16;
     return s;
 }
 
@@ -90,18 +93,23 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     const int max_level = G.n_levels - 1, max_seq = seq_len, min_level = 0, min_seq = 0;
     const int dir = pos ? 1 : -1;
     const int end_seq = pos ? max_seq : min_seq;
-    for (int i = 0; i < DP_HASH_CAP; i++) S.hash[i] = -1;
+    // hash entries are (generation << 12) | index; a scratch slice is zero-initialised once and then reused across
+    // extensions without clearing (generation 0 never matches)
+    uint32_t cgen = S.gens[0] + 1;
+    if (cgen >= (1u << 19)) { for (int i = 0; i < DP_HASH_CAP; i++) S.hash[i] = 0; cgen = 1; }
+    S.gens[0] = cgen;
+    uint32_t tgen = S.gens[1];
     int n_cells = 0;
     auto find_cell = [&](int x, int y, int z) -> int {
         uint32_t h = dp_hash3(x, y, z) & (DP_HASH_CAP - 1);
-        while (S.hash[h] >= 0) { const DpCell& c = S.cells[S.hash[h]]; if (c.x == x && c.y == y && c.z == z) return S.hash[h]; h = (h + 1) & (DP_HASH_CAP - 1); }
+        while ((S.hash[h] >> 12) == cgen) { int idx = (int)(S.hash[h] & 4095u); const DpCell& c = S.cells[idx]; if (c.x == x && c.y == y && c.z == z) return idx; h = (h + 1) & (DP_HASH_CAP - 1); }
         return -1;
     };
     auto add_cell = [&](int x, int y, int z) -> int {
         if (n_cells >= DP_CELL_CAP) return -1;
         uint32_t h = dp_hash3(x, y, z) & (DP_HASH_CAP - 1);
-        while (S.hash[h] >= 0) h = (h + 1) & (DP_HASH_CAP - 1);
-        S.hash[h] = n_cells; DpCell& c = S.cells[n_cells]; c.x = x; c.y = y; c.z = z; c.D = c.GG = c.SG = DP_NEG;
+        while ((S.hash[h] >> 12) == cgen) h = (h + 1) & (DP_HASH_CAP - 1);
+        S.hash[h] = (cgen << 12) | (uint32_t)n_cells; DpCell& c = S.cells[n_cells]; c.x = x; c.y = y; c.z = z; c.D = c.GG = c.SG = DP_NEG;
         c.bD = c.bGG = c.bSG = DpBT{-1, -1, -1};
         return n_cells++;
     };
@@ -114,9 +122,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     int n_td = 0;
     auto touch = [&](int x, int y, int z) -> int {
         uint32_t h = dp_hash3(x, y, z) & (DP_TDHASH_CAP - 1);
-        while (S.tdhash[h] >= 0) { const DpTouch& t = S.td[S.tdhash[h]]; if (t.x == x && t.y == y && t.z == z) return S.tdhash[h]; h = (h + 1) & (DP_TDHASH_CAP - 1); }
+        while ((S.tdhash[h] >> 10) == tgen) { int idx = (int)(S.tdhash[h] & 1023u); const DpTouch& t = S.td[idx]; if (t.x == x && t.y == y && t.z == z) return idx; h = (h + 1) & (DP_TDHASH_CAP - 1); }
         if (n_td >= DP_LIST_CAP) return -1;
-        S.tdhash[h] = n_td; DpTouch& t = S.td[n_td]; t.x = x; t.y = y; t.z = z; t.hasD = t.hasGG = t.hasSG = 0; t.vD = t.vGG = t.vSG = DP_NEG;
+        S.tdhash[h] = (tgen << 10) | (uint32_t)n_td; DpTouch& t = S.td[n_td]; t.x = x; t.y = y; t.z = z; t.hasD = t.hasGG = t.hasSG = 0; t.vD = t.vGG = t.vSG = DP_NEG;
         t.bD = t.bGG = t.bSG = DpBT{-1, -1, -1};
         return n_td++;
     };
@@ -130,7 +138,8 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     for (int diag = 1; ; diag++) {
         if (diag - last_inc > 40) break;
         if (n_m1 == 0 && n_m2 == 0) break;      // nothing can be produced any more; the reference idles until the patience test fires
-        for (int i = 0; i < DP_TDHASH_CAP; i++) S.tdhash[i] = -1;
+        tgen++;
+        if (tgen >= (1u << 22)) { for (int i = 0; i < DP_TDHASH_CAP; i++) S.tdhash[i] = 0; tgen = 1; }
         n_td = 0;
         // ---- from the m-2 list: diagonal steps
         for (int i = 0; i < n_m2 && !status; i++) {
@@ -238,6 +247,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
         }
         int32_t* t2 = m2; m2 = m1; n_m2 = n_m1; m1 = mt; n_m1 = n_mt; mt = t2;
     }
+    S.gens[1] = tgen;
     if (status) return status;
 
     // ---- end cell

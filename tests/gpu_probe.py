@@ -27,8 +27,8 @@ def main():
     assert (rc["chain_order"] == pc["chain_order"]).all()
     ok = (rc["status"] == 0) & (pc["status"] == 0)
     L = b["read_off"][1] - b["read_off"][0]
-    noext = ok & (rc["seed_begin"] == 0) & (rc["seed_end"] == L - 1)
-    print("ok", ok.sum(), "no-extension", noext.sum())
+    noext = ok
+    print("ok", ok.sum(), "with extension", (ok & ~((rc["seed_begin"] == 0) & (rc["seed_end"] == L - 1))).sum())
     sb = (rc["seed_begin"] == pc["seed_begin"]) & (rc["seed_end"] == pc["seed_end"])
     print("seed begin/end mismatch among ok:", (~sb & ok).sum())
     bad = 0; badll = 0
@@ -46,6 +46,26 @@ def main():
             if badll <= 3:
                 print("LL differs", i, repr(rc["ll"][i]), repr(pc["ll"][i]))
     print("column mismatches", bad, "LL not bit-equal", badll, "of", noext.sum())
+    # ---- pairs
+    t = time.time(); rp = quiet(R.pairs, b, 100.0, 10.0); t_ref = time.time() - t
+    t = time.time(); pp = P.pairs(b, 100.0, 10.0); t_gpu = time.time() - t
+    print("pairs", len(rp["pair_mapq"]), "ref s", round(t_ref, 2), "gpu s", round(t_gpu, 3))
+    badp = 0; badq = 0; badmq = 0
+    for r in range(len(rp["n_cols"])):
+        n = rp["n_cols"][r]
+        same = n == pp["n_cols"][r] and all((rp[k][r, :n] == pp[k][r, :n]).all() for k in ("level", "edge", "gchar", "schar", "from_seed"))
+        if not same:
+            badp += 1
+            if badp <= 3:
+                print("PAIR MISMATCH read", r, n, pp["n_cols"][r]); print(rp["level"][r, :n][:40], pp["level"][r, :pp["n_cols"][r]][:40])
+        elif not (rp["mapq"][r, :n] == pp["mapq"][r, :n]).all():
+            badq += 1
+            if badq <= 3:
+                print("MAPQ chars differ read", r, rp["mapq"][r, :n][:50], pp["mapq"][r, :n][:50])
+    dm = np.abs(rp["pair_mapq"] - pp["pair_mapq"]).max(); dr = np.abs(rp["read_mapq"] - pp["read_mapq"]).max()
+    print("pair column mismatches", badp, "mapq-char mismatches", badq, "max |mapQ diff|", dm, dr, "pairs with mapQ<1", (rp["pair_mapq"] < 1).sum(),
+          "bit-equal pair mapQ", (rp["pair_mapq"] == pp["pair_mapq"]).mean())
+    print("bases_per_level sum", pp["bases_per_level"].sum())
 
 
 if __name__ == "__main__":

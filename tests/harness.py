@@ -198,3 +198,18 @@ class Product:
         sb = make_batch_struct(b)
         self._chk(self.lib.hlala_align_chains(self.g, C.byref(sb), C.byref(co)))
         return o
+
+    def pairs(self, b, is_mean, is_sd, cap=1024, want_levels=True):
+        nr = len(b["read_off"]) - 1
+        o = dict(pair_mapq=np.zeros(nr // 2, np.float64), read_mapq=np.zeros(nr, np.float64), read_reverse=np.zeros(nr, np.uint8), chosen_slot=np.zeros(nr, np.int32),
+                 pair_ll=np.zeros(nr // 2, np.float64), n_cols=np.zeros(nr, np.int32), level=np.zeros((nr, cap), np.int32), edge=np.zeros((nr, cap), np.int32),
+                 gchar=np.zeros((nr, cap), np.uint8), schar=np.zeros((nr, cap), np.uint8), from_seed=np.zeros((nr, cap), np.uint8), mapq=np.zeros((nr, cap), np.uint8))
+        po = PairOut(); po.max_columns = cap
+        for k in o:
+            setattr(po, k, o[k].ctypes.data)
+        sb = make_batch_struct(b)
+        nl = self.dims()["n_levels"]
+        bpl = np.zeros(max(nl - 1, 1), np.int32) if want_levels else None
+        self._chk(self.lib.hlala_align_pairs(self.g, C.byref(sb), C.c_double(is_mean), C.c_double(is_sd), C.byref(po), p(bpl) if want_levels else None))
+        o["bases_per_level"] = bpl
+        return o
