@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — paired reads/sec of the read-to-PRG alignment path (BASELINE.json metric) on N B200s of one node.
+
+One "step" = one pass of the whole hot path (chain kernel -> extension DP -> chain finish -> pair kernel) over one batch of
+synthetic read pairs with their bwa-style seed chains, against a synthetic PRG in the reference's on-disk format.
+  value        pairs/s with the batch already resident in HBM (kernels only, CUDA-event timed, max over ranks)
+  e2e          pairs/s through the host-buffer C-ABI call hlala_align_pairs: chain sorting on the host, H2D of the batch from
+               pinned memory, all kernels, D2H of the per-pair results and the per-level coverage
+  roofline     algorithmic bytes of the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the unmodified reference C++ (oracle/_ref) timed on this box's host cores on a bounded sample
+`--impl reference` times the reference's own CPU implementation of the path on the same workload definition.
+Weak scaling: every rank aligns its own batch of --pairs pairs (reads shard by pair); the only exchange is the all-reduce of the
+per-level coverage histogram and of the pair counters at the end of a step (NCCL).
+"""
+import argparse
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def rank_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def ensure_built():
+    import harness as H
+    need = [H.LIB_PRODUCT, H.SYNTH]
+    if not all(os.path.exists(p) for p in need):
+        sys.path.insert(0, REPO)
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def workload_dirs(args):
+    key = hashlib.sha1(("prg-v3|%d|%d|%d|%d" % (args.levels, args.haps, args.genes, args.alleles)).encode()).hexdigest()[:12]
+    root = os.environ.get("HLALA_BENCH_CACHE", "/tmp/hlala_bench_cache")
+    return os.path.join(root, "prg_" + key), root
+
+
+def make_prg(args, prg_dir):
+    import harness as H
+    done = os.path.join(prg_dir, ".complete")
+    if not os.path.exists(done):
+        os.makedirs(prg_dir, exist_ok=True)
+        H.synth_prg(prg_dir, levels=args.levels, haps=args.haps, genes=args.genes, alleles=args.alleles, allele_contigs=4, seed=0xB200)
+        open(done, "w").write("ok\n")
+
+
+def make_reads(args, prg_dir, rank, n_pairs, tag="bench"):
+    import harness as H
+    path = os.path.join(prg_dir, "seeds_%s_r%d_p%d_l%d.bin" % (tag, rank, n_pairs, args.read_len))
+    if os.path.exists(path + ".ok"):
+        return H.read_arrayfile(path)
+    b = H.synth_reads(prg_dir, path, pairs=n_pairs, len=args.read_len, seed=0xB200 + 7919 * rank, clip_frac=0.15)
+    open(path + ".ok", "w").write("ok\n")
+    return b
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index; self.rows = []; self.stop_flag = False; self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = []; mx = 0; reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for i, n in enumerate(names):
+                    if r[2 + i].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+_REF = {}
+
+
+def cpu_reference_run(args, prg_dir_small, n_pairs, threads):
+    """The unmodified reference C++ (oracle/_ref) over a bounded sample; returns pairs/s."""
+    import harness as H
+    from gpu_probe import quiet
+    b = make_reads(args, prg_dir_small, 0, n_pairs, tag="cpu")
+    if prg_dir_small not in _REF:
+        _REF[prg_dir_small] = quiet(H.Ref, prg_dir_small)   # one reference graph per process (its arena is not recycled)
+    R = _REF[prg_dir_small]
+    out = quiet(R.pairs, b, args.is_mean, args.is_sd, 1024, threads, False)
+    return n_pairs / out["seconds"], out["seconds"]
+
+
+def small_prg(args, root):
+    import harness as H
+    d = os.path.join(root, "prg_cpu_sample_l%d" % args.cpu_levels)
+    if not os.path.exists(os.path.join(d, ".complete")):
+        os.makedirs(d, exist_ok=True)
+        H.synth_prg(d, levels=args.cpu_levels, haps=args.haps, genes=min(args.genes, 4), alleles=min(args.alleles, 200), allele_contigs=4, seed=0xB200)
+        open(os.path.join(d, ".complete"), "w").write("ok\n")
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1000000, help="read pairs per GPU per step (BASELINE.json configs[1]: 1M pairs 2x150)")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--levels", type=int, default=5000000)
+    ap.add_argument("--haps", type=int, default=8)
+    ap.add_argument("--genes", type=int, default=17)
+    ap.add_argument("--alleles", type=int, default=1000)
+    ap.add_argument("--is-mean", type=float, default=100.0)
+    ap.add_argument("--is-sd", type=float, default=10.0)
+    ap.add_argument("--max-columns", type=int, default=640)
+    ap.add_argument("--cpu-pairs", type=int, default=6000)
+    ap.add_argument("--cpu-levels", type=int, default=250000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank, local_rank, world = rank_info()
+    n_gpus = max(world, 1)
+
+    ensure_built()
+    import harness as H
+    prg_dir, root = workload_dirs(args)
+    os.makedirs(root, exist_ok=True)
+    config = {"workload": "%d synthetic 2x%dbp pairs per GPU, bwa-style seed chains (15%% soft-clipped), synthetic PRG of %d levels / %d haplotypes / %d gene blocks x %d alleles; "
+                          "full seed projection + graph-DP extension + pair likelihood/mapQ + per-level coverage" % (args.pairs, args.read_len, args.levels, args.haps, args.genes, args.alleles),
+              "pairs_per_gpu": args.pairs, "read_len": args.read_len, "levels": args.levels, "sharding": "pairs sharded across ranks (weak scaling)",
+              "cache": "batch (>1 GB) and per-wave scratch exceed the 126 MB L2, so every step streams its inputs from HBM"}
+
+    # ------------------------------------------------------------------ reference arm: the reference's own CPU implementation
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        if not os.path.exists(H.LIB_REF):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhlala_ref.so not built on this box"}))
+            return 0
+        d = small_prg(args, root)
+        threads = os.cpu_count() or 1
+        vals = []
+        n = args.cpu_pairs
+        for i in range(args.warmup + args.steps):
+            v, sec = cpu_reference_run(args, d, n, threads)
+            if i >= args.warmup:
+                vals.append((v, sec))
+        tot_pairs = n * len(vals); tot_sec = sum(s for _, s in vals)
+        value = tot_pairs / tot_sec
+        sample = "%d pairs 2x%d per step on a %d-level PRG built with the same generator parameters; reference TUs unmodified, outer OpenMP loop over pairs (%d threads)" % (n, args.read_len, args.cpu_levels, threads)
+        line = {"metric": "paired reads/sec aligned to the PRG (seed projection + extension + pair scoring)", "value": value, "unit": "pairs/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * tot_sec / max(len(vals), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+                "config": config, "impl": "reference", "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": sample},
+                "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        make_prg(args, prg_dir)
+    if dist:
+        dist.barrier()
+    b = make_reads(args, prg_dir, rank, args.pairs)
+    P = H.Product(prg_dir)
+    P.to_gpu(local_rank)
+    L = P.lib
+    L.hlala_session_chain_kernel_bytes.restype = C.c_int64
+    L.hlala_session_algorithmic_bytes.restype = C.c_int64
+    n_levels = P.dims()["n_levels"]
+    sb = H.make_batch_struct(b)
+    sess = C.c_void_p()
+    P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(sess)))
+    cov = torch.zeros(n_levels - 1, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        P._chk(L.hlala_session_run(sess, C.c_double(args.is_mean), C.c_double(args.is_sd), C.c_uint64(cov.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        if dist:
+            dist.all_reduce(cov)   # the path's one exchange: per-level coverage (reads_per_level.txt is written from the sum)
+
+    for _ in range(args.warmup):
+        cov.zero_(); step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    L.hlala_session_set_timing(sess, 1)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        cov.zero_(); step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.finish()
+    kms = (C.c_double * 4)(); kl = (C.c_int * 4)()
+    P._chk(L.hlala_session_timing(sess, kms, kl))
+    L.hlala_session_set_timing(sess, 0)
+    launches = L.hlala_session_launches(sess)
+    dig = (C.c_int64 * 4)(); sll = C.c_double(0)
+    P._chk(L.hlala_session_digest(sess, dig, C.byref(sll)))
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = n_gpus * args.pairs * args.steps / (ms_total / 1000.0)
+    if rank == 0:
+        sys.stderr.write("[bench] resident: %.1f ms/step, %.0f pairs/s; kernel ms/step: seed %.1f extend %.1f finish %.1f pair %.1f; launches %d; errors %d\n" % (
+            ms_total / args.steps, value, kms[0] / args.steps, kms[1] / args.steps, kms[2] / args.steps, kms[3] / args.steps, launches, dig[3]))
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host inputs, H2D + kernels + D2H inside the timed region)
+    pinned = {k: torch.from_numpy(b[k]).pin_memory() for k in H.BATCH_KEYS}
+    sbp = H.SeedBatch(); sbp.n_reads = len(b["read_off"]) - 1
+    for k in H.BATCH_KEYS:
+        setattr(sbp, k, pinned[k].data_ptr())
+    nr = len(b["read_off"]) - 1
+    res = {"pair_mapq": torch.empty(nr // 2, dtype=torch.float64).pin_memory(), "read_mapq": torch.empty(nr, dtype=torch.float64).pin_memory(),
+           "chosen_slot": torch.empty(nr, dtype=torch.int32).pin_memory(), "pair_ll": torch.empty(nr // 2, dtype=torch.float64).pin_memory()}
+    po = H.PairOut(); po.max_columns = args.max_columns
+    for k, v in res.items():
+        setattr(po, k, v.data_ptr())
+    cov_host = np.zeros(n_levels - 1, np.int32)
+    h2d = int(sum(b[k].nbytes for k in H.BATCH_KEYS)) + 3 * 4 * len(b["chain_contig"])
+    d2h = int(sum(v.numel() * v.element_size() for v in res.values())) + cov_host.nbytes
+    L.hlala_session_free(sess)   # e2e allocates its own device buffers per call, like a user's call would
+    torch.cuda.synchronize()
+    e2e_times = []
+    for i in range(1 + args.e2e_steps):
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        cov_host[:] = 0
+        P._chk(L.hlala_align_pairs(P.g, C.byref(sbp), C.c_double(args.is_mean), C.c_double(args.is_sd), C.byref(po), cov_host.ctypes.data_as(C.c_void_p)))
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_times.append(dt)
+    te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * args.pairs * len(e2e_times) / float(te.item())
+    if rank == 0:
+        sys.stderr.write("[bench] e2e: %.0f pairs/s (%s s per call)\n" % (e2e_value, [round(x, 3) for x in e2e_times]))
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = measured_peak()
+    chain_bytes = L.hlala_session_chain_kernel_bytes(sess) if False else None
+    # chain kernel roofline: algorithmic bytes per launch / average launch duration
+    sess2 = C.c_void_p()
+    P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(sess2)))
+    chain_bytes = int(L.hlala_session_chain_kernel_bytes(sess2)); total_bytes = int(L.hlala_session_algorithmic_bytes(sess2))
+    L.hlala_session_free(sess2)
+    names = ["k_chain_seed", "k_extend", "k_chain_finish", "k_pair"]
+    per_kernel = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kl[i] / args.steps} for i in range(4)}
+    dom = max(range(4), key=lambda i: kms[i])
+    ach = None; frac = None
+    if kms[0] > 0:
+        ach = chain_bytes * args.steps / (kms[0] / 1000.0) / 1e9
+        frac = ach / peak
+    roofline = {"bound": "hbm", "kernel": "k_chain_seed", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": frac, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": chain_bytes, "whole_path_algorithmic_bytes_per_step": total_bytes,
+                "whole_path_achieved": total_bytes * args.steps / (ms_total / 1000.0) / 1e9, "dominant_kernel_by_time": names[dom], "per_kernel": per_kernel}
+    cpu = None
+    if os.path.exists(H.LIB_REF) and n_gpus == 1:
+        d = small_prg(args, root)
+        v1, s1 = cpu_reference_run(args, d, max(500, args.cpu_pairs // 4), 1)
+        threads = os.cpu_count() or 1
+        vN, sN = cpu_reference_run(args, d, args.cpu_pairs, threads)
+        cpu = {"value": vN, "unit": "pairs/s", "cores": threads, "kind": "reference",
+               "single_thread_value": v1,
+               "sample": "%d pairs 2x%d on a %d-level PRG built with the same generator parameters; unmodified reference TUs; the reference itself runs this loop on 1 thread (%.0f pairs/s), "
+                         "the value is the courtesy all-cores OpenMP loop over pairs" % (args.cpu_pairs, args.read_len, args.cpu_levels, v1)}
+    line = {"metric": "paired reads/sec aligned to the PRG (seed projection + extension + pair scoring)", "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

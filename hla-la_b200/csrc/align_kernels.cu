@@ -31,7 +31,8 @@ __device__ void finalize_chain(const ChainParams& P, const WarpSlab& S, int slot
         if (lane == 0) { P.status[slot] = (n_total > P.maxcol) ? HLALA_E_CAPACITY_DEV : HLALA_E_INVARIANT_DEV; P.n_cols[slot] = 0; atomicAdd(P.error_count, 1); }
         return;
     }
-    int32_t* oe = P.c_edge + (size_t)slot * P.maxcol; uint8_t* os = P.c_schar + (size_t)slot * P.maxcol; uint8_t* of = P.c_fromseed + (size_t)slot * P.maxcol;
+    const size_t cbase = (size_t)(slot - P.slot_base) * P.maxcol;
+    int32_t* oe = P.c_edge + cbase; uint8_t* os = P.c_schar + cbase; uint8_t* of = P.c_fromseed + cbase;
     uint8_t* kind = S.gA; uint8_t* qv = S.sA;      // per-column scoring class and quality, consumed by lane 0 below
     // one pass over output columns; idx of the read base under a column = number of non-gap read characters before it
     int carry = 0;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
     WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.maxcol, P.pool_cap, P.win_cap);
     const DevBatch& B = P.b;
     const int nw = gridDim.x * K1_WARPS;
-    for (int slot = blockIdx.x * K1_WARPS + warp; slot < B.n_chains; slot += nw) {
+    for (int slot = P.slot_base + blockIdx.x * K1_WARPS + warp; slot < P.slot_end; slot += nw) {
         const int r = B.slot_read[slot];
         const int prim = B.read_primary[r];
         const int c = B.chain_order[slot];
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
         const bool need_left = (start_raw != 0) && (l_first > 0);
         const bool need_right = (stop_raw != rdlen - 1) && (l_last + 1 < P.g.n_levels - 1);
         if (P.do_extension && (need_left || need_right)) {
-            int32_t* oe = P.c_edge + (size_t)slot * P.maxcol; uint8_t* os = P.c_schar + (size_t)slot * P.maxcol;
+            int32_t* oe = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol; uint8_t* os = P.c_schar + (size_t)(slot - P.slot_base) * P.maxcol;
             for (int i = lane; i < n; i += 32) { oe[i] = S.lvlA[i]; os[i] = Bc.s[i]; }
             if (lane == 0) {
                 P.n_cols[slot] = n; P.first_level[slot] = l_first; P.last_level[slot] = l_last; P.status[slot] = CH_PENDING_EXT;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(64) k_extend(ExtParams E) {
         const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
         const int n = P.n_cols[slot]; const int sb = P.seed_begin[slot], se = P.seed_end[slot];
         const int l_first = P.first_level[slot], l_last = P.last_level[slot];
-        const int32_t* se_edge = P.c_edge + (size_t)slot * P.maxcol;
+        const int32_t* se_edge = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol;
         E.ext_n[t] = 0; E.ext_nlvl[t] = 0; E.ext_rc[t] = 0;
         DpResult res; int rc = 0;
         if (side == 0) {
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_finish(ExtParams E) {
         const int slot = P.pending_slots[pi];
         const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
         const int n = P.n_cols[slot];
-        const int32_t* ge = P.c_edge + (size_t)slot * P.maxcol; const uint8_t* gs = P.c_schar + (size_t)slot * P.maxcol;
+        const int32_t* ge = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol; const uint8_t* gs = P.c_schar + (size_t)(slot - P.slot_base) * P.maxcol;
         for (int i = lane; i < n; i += 32) { int32_t e = ge[i]; S.lvlA[i] = e; S.sB[i] = gs[i]; S.gB[i] = e >= 0 ? (uint8_t)(G.edge_pack[e] >> 16) : (uint8_t)'_'; }
         __syncwarp();
         int rcL = E.ext_rc[2 * pi], rcR = E.ext_rc[2 * pi + 1];
@@ -225,7 +226,7 @@ cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t strea
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_seed, K1_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    long long want = ((long long)P.b.n_chains + K1_WARPS - 1) / K1_WARPS;
+    long long want = ((long long)(P.slot_end - P.slot_base) + K1_WARPS - 1) / K1_WARPS;
     int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm);   // persistent: a multiple of the SM count
     if (grid < 1) grid = 1;
     k_chain_seed<<<grid, K1_WARPS * 32, smem, stream>>>(P);
@@ -253,7 +254,7 @@ cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t strea
 }
 
 cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream) {
-    long long n_pairs = P.b.n_reads / 2;
+    long long n_pairs = P.pair_end - P.pair_begin;
     if (n_pairs <= 0) return cudaSuccess;
     size_t smem = k3_slab_bytes(P.maxcol) * K3_WARPS;
     static size_t configured = 0;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -118,10 +119,10 @@ int check_batch(const hlala_seed_batch_t* b) {
 
 struct ChainScratch {
     DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count;
-    void alloc(int32_t n_chains, int32_t maxcol) {
-        size_t nc = (size_t)std::max(n_chains, 1);
+    void alloc(int32_t n_chains, int32_t wave_chains, int32_t maxcol) {
+        size_t nc = (size_t)std::max(n_chains, 1); size_t wc = (size_t)std::max(wave_chains, 1);
         status.alloc(nc * 4); n_cols.alloc(nc * 4); seed_begin.alloc(nc * 4); seed_end.alloc(nc * 4); ll.alloc(nc * 8); first_level.alloc(nc * 4); last_level.alloc(nc * 4);
-        c_edge.alloc(nc * maxcol * 4); c_schar.alloc(nc * maxcol); c_fromseed.alloc(nc * maxcol); error_count.alloc(4);
+        c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol); error_count.alloc(4);
         id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4);
     }
     void fill(ChainParams& P) {
@@ -132,7 +133,14 @@ struct ChainScratch {
     }
 };
 
-void chain_caps(int32_t maxcol, ChainParams& P) { P.maxcol = maxcol; P.pool_cap = 4 * maxcol; P.win_cap = 4 * maxcol; }
+// Shared-memory budget of one warp slab: 4 slabs per CTA must fit the 227 KB a CTA may use. Whatever the fixed arrays leave is split
+// 2:1 between the backtrack pool (sum over columns of the level width) and the staged edge window (falls back to L2 reads if short).
+void chain_caps(int32_t maxcol, ChainParams& P) {
+    P.maxcol = maxcol;
+    const long long budget = 56000 - ((long long)maxcol * (8 + 4 + 4 + 2) + 2 * 4 * 256 + 64);
+    long long pool = std::min<long long>(8LL * maxcol, budget * 2 / 3 / 4), win = std::min<long long>(4LL * maxcol, budget / 3 / 4);
+    P.pool_cap = (int32_t)std::max<long long>(pool, 512); P.win_cap = (int32_t)std::max<long long>(win, 256);
+}
 
 // boost::math::pdf(normal) as Boost.Math computes it (processBAM.cpp:2342-2346, 3446-3472)
 double normal_pdf(double mean, double sd, double x) {
@@ -167,14 +175,39 @@ struct Pipeline {
     DevBuf pair_mapq, read_mapq, read_reverse, chosen_slot, pair_ll, pair_status, digest;
     DevBuf o_n_cols, o_level, o_edge, o_gchar, o_schar, o_fromseed, o_mapq; bool have_columns = false;
     int launches = 0; int64_t algo_bytes = 0; int32_t n_pending = 0; int32_t n_errors = 0;
+    bool timing = false; std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;   // (kernel class, start/stop)
+    int64_t chain_kernel_bytes = 0;
+    void tic(int cls, cudaStream_t st) { if (!timing) return; cudaEvent_t a, b; CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b)); CUDA_OK(cudaEventRecord(a, st)); timed.push_back({cls, {a, b}}); }
+    void toc(cudaStream_t st) { if (!timing) return; CUDA_OK(cudaEventRecord(timed.back().second.second, st)); }
+    void collect_timing(double ms[4], int launches_per_class[4]) {
+        for (int i = 0; i < 4; i++) { ms[i] = 0; launches_per_class[i] = 0; }
+        for (auto& t : timed) { float f = 0; CUDA_OK(cudaEventSynchronize(t.second.second)); CUDA_OK(cudaEventElapsedTime(&f, t.second.first, t.second.second)); ms[t.first] += f; launches_per_class[t.first]++; cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
+        timed.clear();
+    }
+    std::vector<int64_t> wave_pair;    // wave w covers pairs [wave_pair[w], wave_pair[w+1])
+    size_t scratch_budget = (size_t)6 << 30;   // bytes of per-chain column scratch per wave
+    bool allow_env_budget = true;
 
     void prepare(hlala_graph* graph, const hlala_seed_batch_t& b, int32_t mc, cudaStream_t st) {
         g = graph; maxcol = mc;
-        pb.build(b); db.upload(b, pb, st); cs.alloc(pb.n_chains, mc);
+        if (const char* e = allow_env_budget ? getenv("HLALA_WAVE_BYTES") : nullptr) scratch_budget = (size_t)strtoull(e, nullptr, 10);   // test hook: force several waves
+        pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1);
+        // waves: consecutive pairs whose chains fit the column-scratch budget
+        wave_pair.assign(1, 0); int32_t max_wave_chains = 0;
+        { const int64_t np = b.n_reads / 2; const int64_t cap = std::max<int64_t>(1024, (int64_t)(scratch_budget / ((size_t)mc * 6)));
+          int64_t p0 = 0;
+          while (p0 < np) {
+              int64_t p1 = p0; int32_t c0 = b.chain_off[2 * p0];
+              while (p1 < np && (int64_t)(b.chain_off[2 * (p1 + 1)] - c0) <= cap) p1++;
+              if (p1 == p0) p1 = p0 + 1;
+              max_wave_chains = std::max(max_wave_chains, b.chain_off[2 * p1] - c0);
+              wave_pair.push_back(p1); p0 = p1;
+          } }
+        cs.alloc(pb.n_chains, max_wave_chains, mc);
         size_t nr = (size_t)std::max<int64_t>(b.n_reads, 2), np = nr / 2;
         pair_mapq.alloc(np * 8); read_mapq.alloc(nr * 8); read_reverse.alloc(nr); chosen_slot.alloc(nr * 4); pair_ll.alloc(np * 8); pair_status.alloc(np * 4); digest.alloc(32);
         phred_thr.upload(phred_thresholds(), st);
-        n_dp_threads = g->n_sm * 2 * 64;
+        n_dp_threads = g->n_sm * 64;
         dp_scratch.alloc((size_t)n_dp_threads * dp_thread_scratch_bytes());
         CUDA_OK(cudaMemsetAsync(dp_scratch.p, 0, dp_scratch.bytes, st));
         // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
@@ -182,6 +215,10 @@ struct Pipeline {
         int64_t nb = b.read_off[b.n_reads]; int64_t ncg = b.cigar_off[pb.n_chains];
         int64_t cols = 0; for (int32_t c = 0; c < pb.n_chains; c++) for (int32_t k = b.cigar_off[c]; k < b.cigar_off[c + 1]; k++) { int op = b.cigar[k] & 15; if (op == 0 || op == 1 || op == 2 || op == 7 || op == 8) cols += b.cigar[k] >> 4; }
         algo_bytes = 2 * nb + 24ll * pb.n_chains + 4 * ncg + cols * (4 + 7) + 2 * nb * 12 / 2 + 40ll * (b.n_reads / 2) + 4 * nb;
+        // chain kernel alone ("Kernel 1"): per chain record+CIGAR 24+4*ops, read bases+quals once per chain (2L), per column
+        // translation 4 + contig base 1 + graph window (edge_pack 4*1.5 + level offsets 8 + gap flag 1) + output (edge 4 + read char 1 + seed flag 1), 44 B scalars
+        { int64_t rb = 0; for (int64_t r = 0; r < b.n_reads; r++) rb += (b.read_off[r + 1] - b.read_off[r]) * (int64_t)(b.chain_off[r + 1] - b.chain_off[r]);
+          chain_kernel_bytes = 24ll * pb.n_chains + 4 * ncg + 2 * rb + cols * (4 + 1 + 6 + 8 + 1 + 6) + 44ll * pb.n_chains; }
     }
     void ensure_columns() {
         if (have_columns) return;
@@ -191,13 +228,18 @@ struct Pipeline {
     }
     ChainParams chain_params() { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, P); P.do_extension = 1; cs.fill(P); return P; }
 
-    void run_chains(cudaStream_t st) {
+    void begin_run(cudaStream_t st) {
         launches = 0;
-        const int32_t nc = pb.n_chains;
-        CUDA_OK(cudaMemsetAsync(cs.error_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st));
-        CUDA_OK(cudaMemsetAsync(cs.status.p, 0xFF, (size_t)std::max(nc, 1) * 4, st));
+        CUDA_OK(cudaMemsetAsync(cs.error_count.p, 0, 4, st));
+        CUDA_OK(cudaMemsetAsync(cs.status.p, 0xFF, (size_t)std::max(pb.n_chains, 1) * 4, st));
+        CUDA_OK(cudaMemsetAsync(digest.p, 0, 32, st));
+    }
+    // chain stage for the slots of one wave
+    ChainParams run_chains_wave(size_t w, cudaStream_t st) {
         ChainParams P = chain_params();
-        if (nc > 0) { CUDA_OK(launch_chain_seed(P, g->n_sm, st)); launches++; }
+        P.slot_base = db_chain_off(2 * wave_pair[w]); P.slot_end = db_chain_off(2 * wave_pair[w + 1]);
+        CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st));
+        if (P.slot_end > P.slot_base) { tic(0, st); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches++; }
         CUDA_OK(cudaMemcpyAsync(&n_pending, cs.pending_count.p, 4, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         if (n_pending > 0) {
@@ -207,9 +249,12 @@ struct Pipeline {
             }
             ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = ext_edge.as<int32_t>(); E.ext_s = ext_s.as<uint8_t>(); E.ext_n = ext_n.as<int32_t>();
             E.ext_nlvl = ext_nlvl.as<int32_t>(); E.ext_rc = ext_rc.as<int32_t>(); E.dp_scratch = dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
-            CUDA_OK(launch_extend(E, st)); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); launches += 2;
+            tic(1, st); CUDA_OK(launch_extend(E, st)); toc(st); tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 2;
         }
+        return P;
     }
+    std::vector<int32_t> host_chain_off;
+    int32_t db_chain_off(int64_t r) const { return host_chain_off[(size_t)r]; }
     void set_insert_size(double mean, double sd, cudaStream_t st) {
         if (mean == is_mean && sd == is_sd) return;
         if (!(sd > 0)) throw std::runtime_error("insert size sd must be positive");
@@ -223,11 +268,9 @@ struct Pipeline {
         if (normal_pdf(mean, sd, (double)(lo - 1)) > 0 || normal_pdf(mean, sd, (double)(hi + 1)) > 0) throw std::runtime_error("insert size table does not cover the support of the density");
         is_table.upload(t, st); is_dmin = (int32_t)lo; is_n = (int32_t)t.size(); is_mean = mean; is_sd = sd;
     }
-    void run_pairs(double mean, double sd, int32_t* bases_per_level_dev, bool want_columns, cudaStream_t st) {
-        set_insert_size(mean, sd, st);
-        if (want_columns) ensure_columns();
-        CUDA_OK(cudaMemsetAsync(digest.p, 0, 32, st));
+    void run_pairs_wave(size_t w, const ChainParams& C, int32_t* bases_per_level_dev, bool want_columns, cudaStream_t st) {
         PairParams Q{}; Q.g = g->d; Q.b = db.view; Q.maxcol = maxcol;
+        Q.slot_base = C.slot_base; Q.pair_begin = wave_pair[w]; Q.pair_end = wave_pair[w + 1];
         Q.status = cs.status.as<int32_t>(); Q.n_cols = cs.n_cols.as<int32_t>(); Q.ll = cs.ll.as<double>(); Q.first_level = cs.first_level.as<int32_t>(); Q.last_level = cs.last_level.as<int32_t>();
         Q.id_first = cs.id_first.as<int32_t>(); Q.id_last = cs.id_last.as<int32_t>(); Q.c_edge = cs.c_edge.as<int32_t>(); Q.c_schar = cs.c_schar.as<uint8_t>(); Q.c_fromseed = cs.c_fromseed.as<uint8_t>();
         Q.is_table = is_table.as<double>(); Q.is_dmin = is_dmin; Q.is_n = is_n; Q.is_penalty = is_pen; Q.phred_thr = phred_thr.as<double>();
@@ -235,7 +278,14 @@ struct Pipeline {
         Q.pair_ll = pair_ll.as<double>(); Q.pair_status = pair_status.as<int32_t>();
         if (want_columns) { Q.out_n_cols = o_n_cols.as<int32_t>(); Q.out_level = o_level.as<int32_t>(); Q.out_edge = o_edge.as<int32_t>(); Q.out_gchar = o_gchar.as<uint8_t>(); Q.out_schar = o_schar.as<uint8_t>(); Q.out_fromseed = o_fromseed.as<uint8_t>(); Q.out_mapq = o_mapq.as<uint8_t>(); }
         Q.bases_per_level = bases_per_level_dev; Q.error_count = cs.error_count.as<int32_t>(); Q.digest = digest.as<unsigned long long>();
-        if (pb.n_reads >= 2) { CUDA_OK(launch_pair(Q, g->n_sm, st)); launches++; }
+        if (Q.pair_end > Q.pair_begin) { tic(3, st); CUDA_OK(launch_pair(Q, g->n_sm, st)); toc(st); launches++; }
+    }
+    // the whole path: per wave chain stage (+ extension) then pair stage
+    void run(double mean, double sd, int32_t* bases_per_level_dev, bool want_columns, cudaStream_t st) {
+        set_insert_size(mean, sd, st);
+        if (want_columns) ensure_columns();
+        begin_run(st);
+        for (size_t w = 0; w + 1 < wave_pair.size(); w++) { ChainParams C = run_chains_wave(w, st); run_pairs_wave(w, C, bases_per_level_dev, want_columns, st); }
     }
     void fetch(hlala_pair_out_t* out, cudaStream_t st) {
         size_t nr = (size_t)pb.n_reads, np = nr / 2;
@@ -256,6 +306,12 @@ struct Pipeline {
         }
         CUDA_OK(cudaMemcpyAsync(&n_errors, cs.error_count.p, 4, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
+    }
+    std::string error_breakdown() {
+        std::vector<int32_t> st((size_t)pb.n_chains); cs.status.download(st.data(), st.size(), 0); CUDA_OK(cudaStreamSynchronize(0));
+        std::map<int, long long> cnt; for (int32_t v : st) if (v < 0) cnt[v]++;
+        std::string r; for (auto& kv : cnt) r += " chains with status " + std::to_string(kv.first) + ": " + std::to_string(kv.second) + ";";
+        return r;
     }
 };
 
@@ -341,8 +397,9 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(g->device));
         cudaStream_t st = 0;
-        Pipeline pl; pl.prepare(g, *batch, out->max_columns, st);
-        pl.run_chains(st);
+        Pipeline pl; pl.scratch_budget = (size_t)1 << 62; pl.allow_env_budget = false; pl.prepare(g, *batch, out->max_columns, st);   // one wave: the chain records are exported whole
+        pl.begin_run(st);
+        if (pl.wave_pair.size() > 1) pl.run_chains_wave(0, st);
         const int32_t nc = pl.pb.n_chains, mc = out->max_columns; ChainScratch& cs = pl.cs;
         DevBuf o_level, o_edge, o_g; size_t ncol = (size_t)std::max(nc, 1) * mc;
         o_level.alloc(ncol * 4); o_edge.alloc(ncol * 4); o_g.alloc(ncol);
@@ -374,14 +431,14 @@ int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double 
         Pipeline pl; pl.prepare(g, *batch, out->max_columns, st);
         DevBuf bpl; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
         if (bases_per_level) { bpl.alloc(nl * 4); CUDA_OK(cudaMemsetAsync(bpl.p, 0, nl * 4, st)); }
-        pl.run_chains(st);
-        pl.run_pairs(is_mean, is_sd, bases_per_level ? bpl.as<int32_t>() : nullptr, true, st);
+        const bool want_cols = out->level || out->edge || out->gchar || out->schar || out->from_seed || out->mapq || out->n_cols;
+        pl.run(is_mean, is_sd, bases_per_level ? bpl.as<int32_t>() : nullptr, want_cols, st);
         pl.fetch(out, st);
         if (bases_per_level) {
             std::vector<int32_t> h(nl); bpl.download(h.data(), nl, st); CUDA_OK(cudaStreamSynchronize(st));
             for (size_t i = 0; i + 1 < (size_t)g->h.n_levels; i++) bases_per_level[i] += h[i];
         }
-        if (pl.n_errors > 0) return fail(HLALA_E_INVARIANT, std::to_string(pl.n_errors) + " chains/pairs violated a reference invariant or a kernel capacity; see per-chain status via hlala_align_chains");
+        if (pl.n_errors > 0) return fail(HLALA_E_INVARIANT, std::to_string(pl.n_errors) + " chains/pairs violated a reference invariant (-5) or a kernel capacity (-4):" + pl.error_breakdown());
         return 0;
     });
 }
@@ -410,12 +467,17 @@ int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(s->pl.g->device));
         cudaStream_t st = (cudaStream_t)cuda_stream;
-        s->pl.run_chains(st);
-        s->pl.run_pairs(is_mean, is_sd, (int32_t*)(uintptr_t)bases_per_level_dev, false, st);
+        s->pl.run(is_mean, is_sd, (int32_t*)(uintptr_t)bases_per_level_dev, false, st);
         return 0;
     });
 }
 int hlala_session_launches(const hlala_session_t* s) { return s ? s->pl.launches : -1; }
+int hlala_session_set_timing(hlala_session_t* s, int on) { if (!s) return fail(HLALA_E_ARG, "null session"); s->pl.timing = on != 0; return 0; }
+int hlala_session_timing(hlala_session_t* s, double ms[4], int launches[4]) {
+    if (!s) return fail(HLALA_E_ARG, "null session");
+    return guarded([&]() { s->pl.collect_timing(ms, launches); return 0; });
+}
+int64_t hlala_session_chain_kernel_bytes(const hlala_session_t* s) { return s ? s->pl.chain_kernel_bytes : -1; }
 int64_t hlala_session_algorithmic_bytes(const hlala_session_t* s) { return s ? s->pl.algo_bytes : -1; }
 int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out) {
     if (!s || !out) return fail(HLALA_E_ARG, "hlala_session_fetch: null argument");

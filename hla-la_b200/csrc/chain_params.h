@@ -20,6 +20,7 @@ struct ChainParams {
     int32_t pool_cap;      // backtrack pool entries per warp
     int32_t win_cap;       // staged edge window entries per warp
     int32_t do_extension;  // 1: run the soft-clip extension DP
+    int32_t slot_base, slot_end;   // this launch handles slots [slot_base, slot_end); column scratch is indexed by slot - slot_base
     // per-slot outputs
     int32_t* status; int32_t* n_cols; int32_t* seed_begin; int32_t* seed_end; double* ll;
     int32_t* first_level; int32_t* last_level;
@@ -48,6 +49,7 @@ constexpr int K3_COMBO_CAP = 512;  // chain combinations per pair
 
 struct PairParams {
     DevGraph g; DevBatch b; int32_t maxcol;
+    int32_t slot_base; long long pair_begin, pair_end;   // wave: pairs [pair_begin, pair_end), column scratch indexed by slot - slot_base
     // chain records (outputs of the chain stage)
     const int32_t* status; const int32_t* n_cols; const double* ll; const int32_t* first_level; const int32_t* last_level;
     const int32_t* id_first; const int32_t* id_last; const int32_t* c_edge; const uint8_t* c_schar; const uint8_t* c_fromseed;

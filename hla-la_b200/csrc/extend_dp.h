@@ -31,17 +31,20 @@
 namespace hlala {
 
 constexpr int DP_NEG = -30000;
-constexpr int DP_CELL_CAP = 4096;
-constexpr int DP_HASH_CAP = 8192;       // power of two
-constexpr int DP_LIST_CAP = 512;        // wavefront lists / touched cells per diagonal
-constexpr int DP_TDHASH_CAP = 1024;     // power of two
-constexpr int DP_ACH_CAP = 256;
+// Capacities. Inside gene blocks the graph is ~14 nodes wide and every node of the band stays alive, so one extension can
+// visit > 10^4 cells; outside it is a few hundred.
+constexpr int DP_CELL_CAP = 32768;
+constexpr int DP_HASH_CAP = 65536;      // power of two
+constexpr int DP_LIST_CAP = 2048;       // wavefront lists / touched cells per diagonal
+constexpr int DP_TDHASH_CAP = 4096;     // power of two
+constexpr int DP_ACH_CAP = 1024;
 constexpr int DP_EXT_CAP = 512;         // output columns per extension
-static_assert(DP_CELL_CAP <= 4096 && DP_LIST_CAP <= 1024, "hash entry layouts");
+static_assert(DP_CELL_CAP <= 65536 && DP_LIST_CAP <= 4096, "hash entry layouts");
 
-struct DpBT { int32_t src; int32_t edge; int32_t mat; };      // edge: flat id, -1 none, <= -2: gap path (-2 - id)
-struct DpCell { int32_t x, y, z; int32_t D, GG, SG; DpBT bD, bGG, bSG; };
+struct DpBT { int32_t edge; int16_t mat; uint16_t srcu; int32_t src; };      // edge: flat id, -1 none, <= -2: gap path (-2 - id); src: cell index, -1 none, -3 self
+struct DpCell { int32_t x; int16_t y; int16_t z; int16_t D, GG, SG; int16_t pad; DpBT bD, bGG, bSG; };
 struct DpTouch { int32_t x, y, z; int32_t hasD, hasGG, hasSG; int32_t vD, vGG, vSG; DpBT bD, bGG, bSG; };
+__host__ __device__ inline DpBT dp_bt(int src, int edge, int mat) { DpBT b; b.edge = edge; b.mat = (int16_t)mat; b.srcu = 0; b.src = src; return b; }
 
 struct DpScratch {
     DpCell* cells; uint32_t* hash; DpTouch* td; uint32_t* tdhash; int32_t* m1; int32_t* m2; int32_t* mt; int32_t* order; int32_t* ach; int32_t* maxima;
@@ -93,24 +96,24 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     const int max_level = G.n_levels - 1, max_seq = seq_len, min_level = 0, min_seq = 0;
     const int dir = pos ? 1 : -1;
     const int end_seq = pos ? max_seq : min_seq;
-    // hash entries are (generation << 12) | index; a scratch slice is zero-initialised once and then reused across
+    // hash entries are (generation << 16) | index; a scratch slice is zero-initialised once and then reused across
     // extensions without clearing (generation 0 never matches)
     uint32_t cgen = S.gens[0] + 1;
-    if (cgen >= (1u << 19)) { for (int i = 0; i < DP_HASH_CAP; i++) S.hash[i] = 0; cgen = 1; }
+    if (cgen >= (1u << 15)) { for (int i = 0; i < DP_HASH_CAP; i++) S.hash[i] = 0; cgen = 1; }
     S.gens[0] = cgen;
     uint32_t tgen = S.gens[1];
     int n_cells = 0;
     auto find_cell = [&](int x, int y, int z) -> int {
         uint32_t h = dp_hash3(x, y, z) & (DP_HASH_CAP - 1);
-        while ((S.hash[h] >> 12) == cgen) { int idx = (int)(S.hash[h] & 4095u); const DpCell& c = S.cells[idx]; if (c.x == x && c.y == y && c.z == z) return idx; h = (h + 1) & (DP_HASH_CAP - 1); }
+        while ((S.hash[h] >> 16) == cgen) { int idx = (int)(S.hash[h] & 65535u); const DpCell& c = S.cells[idx]; if (c.x == x && c.y == y && c.z == z) return idx; h = (h + 1) & (DP_HASH_CAP - 1); }
         return -1;
     };
     auto add_cell = [&](int x, int y, int z) -> int {
         if (n_cells >= DP_CELL_CAP) return -1;
         uint32_t h = dp_hash3(x, y, z) & (DP_HASH_CAP - 1);
-        while ((S.hash[h] >> 12) == cgen) h = (h + 1) & (DP_HASH_CAP - 1);
-        S.hash[h] = (cgen << 12) | (uint32_t)n_cells; DpCell& c = S.cells[n_cells]; c.x = x; c.y = y; c.z = z; c.D = c.GG = c.SG = DP_NEG;
-        c.bD = c.bGG = c.bSG = DpBT{-1, -1, -1};
+        while ((S.hash[h] >> 16) == cgen) h = (h + 1) & (DP_HASH_CAP - 1);
+        S.hash[h] = (cgen << 16) | (uint32_t)n_cells; DpCell& c = S.cells[n_cells]; c.x = x; c.y = (int16_t)y; c.z = (int16_t)z; c.D = c.GG = c.SG = (int16_t)DP_NEG;
+        c.bD = c.bGG = c.bSG = dp_bt(-1, -1, -1);
         return n_cells++;
     };
     const int start_cell = add_cell(start_level, start_seq, start_z);
@@ -122,10 +125,10 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     int n_td = 0;
     auto touch = [&](int x, int y, int z) -> int {
         uint32_t h = dp_hash3(x, y, z) & (DP_TDHASH_CAP - 1);
-        while ((S.tdhash[h] >> 10) == tgen) { int idx = (int)(S.tdhash[h] & 1023u); const DpTouch& t = S.td[idx]; if (t.x == x && t.y == y && t.z == z) return idx; h = (h + 1) & (DP_TDHASH_CAP - 1); }
+        while ((S.tdhash[h] >> 12) == tgen) { int idx = (int)(S.tdhash[h] & 4095u); const DpTouch& t = S.td[idx]; if (t.x == x && t.y == y && t.z == z) return idx; h = (h + 1) & (DP_TDHASH_CAP - 1); }
         if (n_td >= DP_LIST_CAP) return -1;
-        S.tdhash[h] = (tgen << 10) | (uint32_t)n_td; DpTouch& t = S.td[n_td]; t.x = x; t.y = y; t.z = z; t.hasD = t.hasGG = t.hasSG = 0; t.vD = t.vGG = t.vSG = DP_NEG;
-        t.bD = t.bGG = t.bSG = DpBT{-1, -1, -1};
+        S.tdhash[h] = (tgen << 12) | (uint32_t)n_td; DpTouch& t = S.td[n_td]; t.x = x; t.y = y; t.z = z; t.hasD = t.hasGG = t.hasSG = 0; t.vD = t.vGG = t.vSG = DP_NEG;
+        t.bD = t.bGG = t.bSG = dp_bt(-1, -1, -1);
         return n_td++;
     };
     // "push_back then first maximum" == keep the first candidate, replace only on strictly greater
@@ -139,7 +142,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
         if (diag - last_inc > 40) break;
         if (n_m1 == 0 && n_m2 == 0) break;      // nothing can be produced any more; the reference idles until the patience test fires
         tgen++;
-        if (tgen >= (1u << 22)) { for (int i = 0; i < DP_TDHASH_CAP; i++) S.tdhash[i] = 0; tgen = 1; }
+        if (tgen >= (1u << 19)) { for (int i = 0; i < DP_TDHASH_CAP; i++) S.tdhash[i] = 0; tgen = 1; }
         n_td = 0;
         // ---- from the m-2 list: diagonal steps
         for (int i = 0; i < n_m2 && !status; i++) {
@@ -153,7 +156,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
                 int e = pos ? G.node_out[k] : G.node_in[k]; uint32_t pk = G.edge_pack[e];
                 int nz = pos ? (int)((pk >> 8) & 255u) : (int)(pk & 255u); uint8_t em = (uint8_t)(pk >> 16);
                 int ti = touch(nx, ny, nz); if (ti < 0) { status = -4; break; }
-                candD(ti, pc.D + (em == sc ? 2 : -5), DpBT{m2[i], e, 0});
+                candD(ti, pc.D + (em == sc ? 2 : -5), dp_bt(m2[i], e, 0));
             }
         }
         // ---- from the m-1 list
@@ -163,7 +166,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
             { int gx = pc.x, gy = pc.y + dir;
               bool ok = pos ? (gx <= max_level && gy <= max_seq) : (gx >= min_level && gy >= min_seq);
               if (ok) { int ti = touch(gx, gy, pc.z); if (ti < 0) { status = -4; break; }
-                        candGG(ti, pc.D - 4 - 2, DpBT{m1[i], -1, 0}); candGG(ti, addneg(pc.GG, -2), DpBT{m1[i], -1, 1}); } }
+                        candGG(ti, pc.D - 4 - 2, dp_bt(m1[i], -1, 0)); candGG(ti, addneg(pc.GG, -2), dp_bt(m1[i], -1, 1)); } }
             // gap in sequence: follow an edge without consuming a read base
             { int sx = pc.x + dir, sy = pc.y;
               bool ok = pos ? (sx <= max_level && sy <= max_seq) : (sx >= min_level && sy >= min_seq);
@@ -174,9 +177,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
                       int e = pos ? G.node_out[k] : G.node_in[k]; uint32_t pk = G.edge_pack[e];
                       int nz = pos ? (int)((pk >> 8) & 255u) : (int)(pk & 255u); bool gapEdge = ((uint8_t)(pk >> 16) == '_');
                       int ti = touch(sx, sy, nz); if (ti < 0) { status = -4; break; }
-                      candSG(ti, gapEdge ? DP_NEG : pc.D - 4 - 2, DpBT{m1[i], e, 0});
-                      candSG(ti, gapEdge ? addneg(pc.SG, 0) : addneg(pc.SG, -2), DpBT{m1[i], e, 2});
-                      if (gapEdge) candD(ti, pc.D + 0, DpBT{m1[i], e, 0});
+                      candSG(ti, gapEdge ? DP_NEG : pc.D - 4 - 2, dp_bt(m1[i], e, 0));
+                      candSG(ti, gapEdge ? addneg(pc.SG, 0) : addneg(pc.SG, -2), dp_bt(m1[i], e, 2));
+                      if (gapEdge) candD(ti, pc.D + 0, dp_bt(m1[i], e, 0));
                   }
                   if (status) break;
               } }
@@ -192,7 +195,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
                   int tgt = pos ? G.path_to[p] : G.path_from[p];
                   int jz = tgt - G.level_node_off[jx];
                   int ti = touch(jx, jy, jz); if (ti < 0) { status = -4; break; }
-                  candD(ti, pc.D + 0, DpBT{m1[i], -2 - p, 0});
+                  candD(ti, pc.D + 0, dp_bt(m1[i], -2 - p, 0));
               } }
         }
         if (status) break;
@@ -211,17 +214,17 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
             int ci = find_cell(t.x, t.y, t.z);
             // the two candidates entering D from the gap matrices of this very cell (source = the cell itself)
             // (the cell index is only known once it exists; -3 marks "self")
-            { if (!t.hasD || selGG > t.vD) { t.vD = selGG; t.bD = DpBT{-3, -1, 1}; } t.hasD = 1;
-              if (selSG > t.vD) { t.vD = selSG; t.bD = DpBT{-3, -1, 2}; } }
+            { if (!t.hasD || selGG > t.vD) { t.vD = selGG; t.bD = dp_bt(-3, -1, 1); } t.hasD = 1;
+              if (selSG > t.vD) { t.vD = selSG; t.bD = dp_bt(-3, -1, 2); } }
             int selD = t.vD;
             if (selD < -16) continue;
             bool isNew = (ci < 0);
             if (isNew) { ci = add_cell(t.x, t.y, t.z); if (ci < 0) { status = -4; break; } }
             DpCell& c = S.cells[ci];
             bool overwritten = false;
-            if (isNew || c.D < selD) { overwritten = !isNew; c.D = selD; c.bD = t.bD; if (c.bD.src == -3) c.bD.src = ci; }
-            if (isNew || c.GG < selGG) { overwritten = !isNew; c.GG = selGG; c.bGG = t.bGG; }
-            if (isNew || c.SG < selSG) { overwritten = !isNew; c.SG = selSG; c.bSG = t.bSG; }
+            if (isNew || c.D < selD) { overwritten = !isNew; c.D = (int16_t)selD; c.bD = t.bD; if (c.bD.src == -3) c.bD.src = ci; }
+            if (isNew || c.GG < selGG) { overwritten = !isNew; c.GG = (int16_t)selGG; c.bGG = t.bGG; }
+            if (isNew || c.SG < selSG) { overwritten = !isNew; c.SG = (int16_t)selSG; c.bSG = t.bSG; }
             if (t.y == end_seq) {
                 bool have = false; for (int a = 0; a < n_ach; a++) if (S.ach[2 * a] == t.x && S.ach[2 * a + 1] == t.z) { have = true; break; }
                 if (!have) { if (n_ach >= DP_ACH_CAP) { status = -4; break; } S.ach[2 * n_ach] = t.x; S.ach[2 * n_ach + 1] = t.z; n_ach++; }
@@ -269,7 +272,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     int cur = end_cell, mat = 0; int guard = 0;
     res.far_y = S.cells[end_cell].y;
     while (!(S.cells[cur].x == start_level && S.cells[cur].y == start_seq)) {
-        if (++guard > 4 * DP_CELL_CAP) return -5;
+        if (++guard > 8 * DP_CELL_CAP) return -5;
         const DpCell& c = S.cells[cur];
         DpBT step = mat == 0 ? c.bD : (mat == 1 ? c.bGG : c.bSG);
         if (step.src < 0) return -5;

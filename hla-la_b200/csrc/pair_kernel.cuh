@@ -84,7 +84,7 @@ __device__ int gather_kept(const PairParams& P, int r, int32_t* kept, int& err) 
 __device__ void mark_members(const PairParams& P, const PairSlab& S, int cs, int as, int bit, int lane) {
     const int mc = P.maxcol;
     const int na = P.n_cols[as], fa = P.first_level[as], nlev_a = P.last_level[as] - fa + 1;
-    const int32_t* ae = P.c_edge + (size_t)as * mc; const uint8_t* asq = P.c_schar + (size_t)as * mc;
+    const int32_t* ae = P.c_edge + (size_t)(as - P.slot_base) * mc; const uint8_t* asq = P.c_schar + (size_t)(as - P.slot_base) * mc;
     for (int i = lane; i < nlev_a && i < mc; i += 32) S.linfo[i] = 0;
     __syncwarp();
     int cl = 0, cb = 0;
@@ -102,7 +102,7 @@ __device__ void mark_members(const PairParams& P, const PairSlab& S, int cs, int
     }
     __syncwarp();
     const int nc = P.n_cols[cs], fc = P.first_level[cs];
-    const int32_t* ce = P.c_edge + (size_t)cs * mc; const uint8_t* csq = P.c_schar + (size_t)cs * mc;
+    const int32_t* ce = P.c_edge + (size_t)(cs - P.slot_base) * mc; const uint8_t* csq = P.c_schar + (size_t)(cs - P.slot_base) * mc;
     cl = 0; cb = 0;
     for (int base = 0; base < nc; base += 32) {
         int k = base + lane; bool in = k < nc;
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     PairSlab S = carve_pair_slab(smem + (size_t)warp * k3_slab_bytes(P.maxcol), P.maxcol);
     const DevBatch& B = P.b; const int mc = P.maxcol;
-    const long long n_pairs = B.n_reads / 2; const int nw = gridDim.x * K3_WARPS;
-    for (long long p = (long long)blockIdx.x * K3_WARPS + warp; p < n_pairs; p += nw) {
+    const int nw = gridDim.x * K3_WARPS;
+    for (long long p = P.pair_begin + (long long)blockIdx.x * K3_WARPS + warp; p < P.pair_end; p += nw) {
         const int r1 = (int)(2 * p), r2 = r1 + 1;
         int n1 = 0, n2 = 0, err = 0;
         if (lane == 0) { n1 = gather_kept(P, r1, S.kept1, err); if (!err) n2 = gather_kept(P, r2, S.kept2, err); if (!err && (n1 == 0 || n2 == 0)) err = HLALA_E_INVARIANT_DEV; if (!err && n1 * n2 > K3_COMBO_CAP) err = HLALA_E_CAPACITY_DEV; }
@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
                 }
                 __syncwarp();
             }
-            const int32_t* ce = P.c_edge + (size_t)cs * mc; const uint8_t* csq = P.c_schar + (size_t)cs * mc; const uint8_t* cfs = P.c_fromseed + (size_t)cs * mc;
+            const size_t cb0 = (size_t)(cs - P.slot_base) * mc;
+            const int32_t* ce = P.c_edge + cb0; const uint8_t* csq = P.c_schar + cb0; const uint8_t* cfs = P.c_fromseed + cb0;
             const size_t oo = (size_t)r * mc;
             int cl = 0; unsigned long long dsum = 0;
             for (int base = 0; base < ncol; base += 32) {

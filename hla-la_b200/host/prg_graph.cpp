@@ -1,4 +1,6 @@
 #include "prg_graph.h"
+#include "arrayfile.h"
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -14,7 +16,6 @@ namespace hlala {
 
 namespace {
 
-const char* SEP = "|||";
 
 std::string read_file(const std::string& path) {
     FILE* f = fopen(path.c_str(), "rb");
@@ -32,15 +33,22 @@ void split_fields(const char* b, const char* e, std::vector<std::pair<const char
     const char* p = b;
     while (true) {
         const char* hit = nullptr;
-        for (const char* q = p; q + 3 <= e; q++) if (q[0] == '|' && q[1] == '|' && q[2] == '|') { hit = q; break; }
+        for (const char* q = p; q + 3 <= e;) {
+            q = (const char*)memchr(q, '|', (size_t)(e - q));
+            if (!q || q + 3 > e) break;
+            if (q[1] == '|' && q[2] == '|') { hit = q; break; }
+            q++;
+        }
         if (!hit) { out.emplace_back(p, e); break; }
         out.emplace_back(p, hit); p = hit + 3;
     }
 }
 long long to_ll(const std::pair<const char*, const char*>& f) {
-    std::string s(f.first, f.second); char* end = nullptr; long long v = strtoll(s.c_str(), &end, 10);
-    if (end == s.c_str() || *end != 0) throw std::runtime_error("graph.txt: cannot parse integer field '" + s + "'");
-    return v;
+    const char* p = f.first; bool neg = false; long long v = 0;
+    if (p < f.second && (*p == '-' || *p == '+')) { neg = (*p == '-'); p++; }
+    if (p == f.second) throw std::runtime_error("graph.txt: cannot parse integer field '" + std::string(f.first, f.second) + "'");
+    for (; p < f.second; p++) { if (*p < '0' || *p > '9') throw std::runtime_error("graph.txt: cannot parse integer field '" + std::string(f.first, f.second) + "'"); v = v * 10 + (*p - '0'); }
+    return neg ? -v : v;
 }
 uint64_t fnv(const char* b, const char* e) { uint64_t h = 1469598103934665603ull; for (const char* p = b; p < e; p++) { h ^= (unsigned char)*p; h *= 1099511628211ull; } return h; }
 
@@ -52,8 +60,64 @@ static void compute_gap_paths(FlatGraph& g);
 static void compute_gap_stretches(FlatGraph& g);
 static void load_contigs(const std::string& dir, FlatGraph& g);
 
+// Binary cache of the flat arrays next to graph.txt, reused when newer than its inputs — the role serializedGRAPH plays for the
+// reference (processBAM.cpp:37-53); its Boost text archive cannot be read without Boost and holds nothing graph.txt lacks.
+static const int64_t CACHE_VERSION = 3;
+static time_t mtime_of(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 ? st.st_mtime : 0; }
+
+#define FG_I32(X) X(level_node_off) X(node_ord) X(node_level) X(level_edge_off) X(edge_from) X(edge_to) X(edge_ord) X(ord_to_edge) X(node_out_off) X(node_out) \
+    X(node_in_off) X(node_in) X(path_off) X(path_edges) X(path_from) X(path_to) X(jump_fwd_off) X(jump_fwd_path) X(jump_bwd_off) X(jump_bwd_path) \
+    X(contig_prg_id) X(contig_level) X(contig_tr_len) X(anchor_off) X(anchor_prg_id) X(anchor_pos)
+#define FG_U8(X) X(edge_emis) X(gap_stretch) X(contig_seq)
+
+static void save_cache(const std::string& path, const FlatGraph& g) {
+    try {
+        ArrayFile f;
+        std::vector<int64_t> meta{CACHE_VERSION, g.n_levels, g.n_nodes, g.n_edges, g.max_nodes_per_level, g.max_edges_per_level, g.n_paths, g.n_contigs};
+        f.put("meta", DT_I64, meta);
+#define X(n) f.put(#n, DT_I32, g.n);
+        FG_I32(X)
+#undef X
+#define X(n) f.put(#n, DT_U8, g.n);
+        FG_U8(X)
+#undef X
+        f.put("contig_off", DT_I64, g.contig_off);
+        auto blob = [](const std::vector<std::string>& v) { std::vector<uint8_t> b; for (const std::string& s : v) { b.insert(b.end(), s.begin(), s.end()); b.push_back('\n'); } return b; };
+        f.put("level_names", DT_U8, blob(g.level_names)); f.put("contig_bam_name", DT_U8, blob(g.contig_bam_name));
+        f.write(path + ".tmp");
+        rename((path + ".tmp").c_str(), path.c_str());
+    } catch (...) { /* a read-only PRG directory just means no cache */ }
+}
+static bool load_cache(const std::string& path, FlatGraph& g) {
+    try {
+        ArrayFile f; f.read(path);
+        uint64_t n = 0; const int64_t* meta = f.get<int64_t>("meta", &n);
+        if (n != 8 || meta[0] != CACHE_VERSION) return false;
+        g.n_levels = (int32_t)meta[1]; g.n_nodes = (int32_t)meta[2]; g.n_edges = (int32_t)meta[3]; g.max_nodes_per_level = (int32_t)meta[4]; g.max_edges_per_level = (int32_t)meta[5];
+        g.n_paths = (int32_t)meta[6]; g.n_contigs = (int32_t)meta[7];
+#define X(nm) { uint64_t c; const int32_t* p = f.get<int32_t>(#nm, &c); g.nm.assign(p, p + c); }
+        FG_I32(X)
+#undef X
+#define X(nm) { uint64_t c; const uint8_t* p = f.get<uint8_t>(#nm, &c); g.nm.assign(p, p + c); }
+        FG_U8(X)
+#undef X
+        { uint64_t c; const int64_t* p = f.get<int64_t>("contig_off", &c); g.contig_off.assign(p, p + c); }
+        auto unblob = [&](const char* nm, std::vector<std::string>& out) { uint64_t c; const uint8_t* p = f.get<uint8_t>(nm, &c); out.clear(); std::string cur; for (uint64_t i = 0; i < c; i++) { if (p[i] == '\n') { out.push_back(cur); cur.clear(); } else cur.push_back((char)p[i]); } };
+        unblob("level_names", g.level_names); unblob("contig_bam_name", g.contig_bam_name);
+        return true;
+    } catch (...) { return false; }
+}
+
 void load_prg_dir(const std::string& dir, FlatGraph& g) {
     const std::string graph_path = dir + "/PRG/graph.txt";
+    const std::string cache_path = dir + "/PRG/graph.hlala_b200.cache";
+    {
+        time_t tc = mtime_of(cache_path);
+        if (tc && tc > mtime_of(graph_path) && tc > mtime_of(dir + "/sequences.txt") && tc > mtime_of(dir + "/mapping_PRGonly/referenceGenome.fa") && !getenv("HLALA_NO_GRAPH_CACHE")) {
+            if (load_cache(cache_path, g)) return;
+            g = FlatGraph();
+        }
+    }
     std::string txt = read_file(graph_path);
 
     // ---- section scan (Graph::readFromFile, Graph.cpp:2329-2559)
@@ -188,6 +252,7 @@ void load_prg_dir(const std::string& dir, FlatGraph& g) {
     compute_gap_paths(g);
     compute_gap_stretches(g);
     load_contigs(dir, g);
+    if (!getenv("HLALA_NO_GRAPH_CACHE")) save_cache(cache_path, g);
 }
 
 // Graph::computeGapEdgePaths (Graph.cpp:347-476), containers keyed by canonical ordinals instead of pointers.
@@ -275,18 +340,20 @@ static void load_contigs(const std::string& dir, FlatGraph& g) {
     // FASTA: id = text up to the first space (Utilities.cpp:757-808)
     std::map<std::string, std::string> fa;
     {
-        std::ifstream f(dir + "/mapping_PRGonly/referenceGenome.fa");
-        if (!f.is_open()) throw std::runtime_error("Cannot open " + dir + "/mapping_PRGonly/referenceGenome.fa");
-        std::string id, l2;
-        while (std::getline(f, l2)) {
-            while (!l2.empty() && (l2.back() == '\r' || l2.back() == '\n')) l2.pop_back();
-            if (l2.empty()) continue;
-            if (l2[0] == '>') { id = l2.substr(1); size_t sp = id.find(' '); if (sp != std::string::npos) id = id.substr(0, sp); fa[id].clear(); }
-            else fa[id] += l2;
+        std::string txt = read_file(dir + "/mapping_PRGonly/referenceGenome.fa");
+        const char* p = txt.data(); const char* end = p + txt.size(); std::string* cur = nullptr;
+        while (p < end) {
+            const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p)); const char* le = nl ? nl : end;
+            const char* lb = p; p = nl ? nl + 1 : end;
+            while (le > lb && (le[-1] == '\r')) le--;
+            if (le == lb) continue;
+            if (*lb == '>') { std::string id(lb + 1, le); size_t sp = id.find(' '); if (sp != std::string::npos) id = id.substr(0, sp); cur = &fa[id]; cur->clear(); }
+            else if (cur) cur->append(lb, le);
         }
     }
     g.contig_off.assign(1, 0);
-    std::vector<std::map<int32_t, int32_t>> anchors((size_t)g.n_levels);
+    struct Tr { int32_t id; std::vector<int32_t> lv; };
+    std::vector<Tr> trs;
     while (std::getline(s, line)) {
         while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
         if (line.empty()) continue;
@@ -296,30 +363,64 @@ static void load_contigs(const std::string& dir, FlatGraph& g) {
         std::string bam = f[c_chr].empty() ? ("PRG_" + f[c_id]) : f[c_chr];
         auto it = fa.find(bam);
         if (it == fa.end()) throw std::runtime_error(bam + " cannot be found in the PRG-only reference genome " + dir + "/mapping_PRGonly/referenceGenome.fa");
-        const std::string& seq = (bam == "PRG_5") ? std::string("N") : it->second;   // processBAM.cpp:87-88
-        // translation file, with the reference's getline semantics (processBAM.cpp:4409-4414): a trailing newline yields one extra 0
+        const std::string seq = (bam == "PRG_5") ? std::string("N") : it->second;   // processBAM.cpp:87-88
+        // translation file with the reference's getline loop semantics (processBAM.cpp:4409-4414): every line is parsed with
+        // StrtoI, and a file ending in a newline yields one more (empty) line that parses as 0
         std::string tp = dir + "/translation/" + f[c_id] + ".txt";
-        std::ifstream ts(tp);
-        if (!ts.is_open()) throw std::runtime_error("Expected coordinate translation file not found: " + tp);
-        std::vector<int32_t> tr; std::string tl;
-        while (ts.good()) { std::getline(ts, tl); while (!tl.empty() && (tl.back() == '\r' || tl.back() == '\n')) tl.pop_back(); tr.push_back(tl.empty() ? 0 : atoi(tl.c_str())); }
+        std::string tt;
+        try { tt = read_file(tp); } catch (...) { throw std::runtime_error("Expected coordinate translation file not found: " + tp); }
+        Tr tr; tr.id = id; tr.lv.reserve(seq.size() + 1);
+        { const char* p = tt.data(); const char* end = p + tt.size();
+          while (true) {
+              const char* nl = (p < end) ? (const char*)memchr(p, '\n', (size_t)(end - p)) : nullptr; const char* le = nl ? nl : end;
+              long long v = 0; bool neg = false; const char* q = p; if (q < le && *q == '-') { neg = true; q++; }
+              for (; q < le && *q >= '0' && *q <= '9'; q++) v = v * 10 + (*q - '0');
+              tr.lv.push_back((int32_t)(neg ? -v : v));
+              if (!nl) break;
+              p = nl + 1;
+          } }
         g.contig_prg_id.push_back(id); g.contig_bam_name.push_back(bam);
         g.contig_seq.insert(g.contig_seq.end(), seq.begin(), seq.end());
         size_t n = seq.size();
-        if (tr.size() < n) throw std::runtime_error("translation shorter than contig " + bam);
-        g.contig_level.insert(g.contig_level.end(), tr.begin(), tr.begin() + (long)n);
-        g.contig_tr_len.push_back((int32_t)tr.size());
+        if (tr.lv.size() < n) throw std::runtime_error("translation shorter than contig " + bam);
+        g.contig_level.insert(g.contig_level.end(), tr.lv.begin(), tr.lv.begin() + (long)n);
+        g.contig_tr_len.push_back((int32_t)tr.lv.size());
         g.contig_off.push_back((int64_t)g.contig_seq.size());
-        for (size_t pos = 0; pos < tr.size(); pos++) {
-            if (tr[pos] < 0 || tr[pos] >= g.n_levels) throw std::runtime_error("translation level out of range for contig " + bam);
-            anchors[tr[pos]][id] = (int32_t)pos;   // processBAM.cpp:4441-4456 (later positions overwrite earlier ones)
-        }
+        for (int32_t lv : tr.lv) if (lv < 0 || lv >= g.n_levels) throw std::runtime_error("translation level out of range for contig " + bam);
+        trs.push_back(std::move(tr));
     }
     g.n_contigs = (int32_t)g.contig_prg_id.size();
+    // graphLevel_2_underlyingSequencePositions (processBAM.cpp:4441-4456): per level a std::map<PRG id, position>; a later
+    // position of the same contig overwrites an earlier one. Built as a CSR: contigs in ascending id order, counting sort by level.
+    std::sort(trs.begin(), trs.end(), [](const Tr& a, const Tr& b) { return a.id < b.id; });
+    for (size_t i = 1; i < trs.size(); i++) if (trs[i].id == trs[i - 1].id) throw std::runtime_error("sequences.txt: duplicate SequenceID");
     g.anchor_off.assign((size_t)g.n_levels + 1, 0);
-    for (int32_t l = 0; l < g.n_levels; l++) {
-        for (auto& kv : anchors[l]) { g.anchor_prg_id.push_back(kv.first); g.anchor_pos.push_back(kv.second); }
-        g.anchor_off[l + 1] = (int32_t)g.anchor_prg_id.size();
+    std::vector<int32_t> lastpos;   // per contig: dedupe repeated levels (keep the last position)
+    for (const Tr& t : trs) {
+        // a level can repeat inside one contig only through the bogus trailing 0; count distinct levels
+        std::vector<int32_t> seen_level0;   // handled by the overwrite pass below
+        for (size_t pos = 0; pos < t.lv.size(); pos++) {
+            bool repeat = false;
+            if (pos + 1 == t.lv.size() && t.lv[pos] == 0) { for (size_t q = 0; q < pos && !repeat; q++) { if (t.lv[q] == 0) repeat = true; if (t.lv[q] > 0) break; } }
+            if (!repeat) g.anchor_off[(size_t)t.lv[pos] + 1]++;
+        }
+    }
+    for (int32_t l = 0; l < g.n_levels; l++) g.anchor_off[l + 1] += g.anchor_off[l];
+    g.anchor_prg_id.assign((size_t)g.anchor_off[g.n_levels], 0); g.anchor_pos.assign((size_t)g.anchor_off[g.n_levels], 0);
+    {
+        std::vector<int32_t> cur(g.anchor_off.begin(), g.anchor_off.end() - 1);
+        for (const Tr& t : trs) {
+            int32_t slot0 = -1;   // slot of this contig at level 0, if any
+            for (size_t pos = 0; pos < t.lv.size(); pos++) {
+                int32_t lv = t.lv[pos];
+                if (lv == 0 && slot0 >= 0) { g.anchor_pos[slot0] = (int32_t)pos; continue; }     // overwrite (last position wins)
+                int32_t k = cur[lv]++;
+                if (k >= g.anchor_off[lv + 1]) throw std::runtime_error("translation is not strictly increasing for a contig (levels repeat)");
+                g.anchor_prg_id[k] = t.id; g.anchor_pos[k] = (int32_t)pos;
+                if (lv == 0) slot0 = k;
+            }
+        }
+        for (int32_t l = 0; l < g.n_levels; l++) if (cur[l] != g.anchor_off[l + 1]) throw std::runtime_error("translation is not strictly increasing for a contig (levels repeat)");
     }
 }
 

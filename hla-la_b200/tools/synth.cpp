@@ -25,6 +25,8 @@
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
+#include <atomic>
 #include <unordered_map>
 #include <vector>
 
@@ -330,10 +332,13 @@ std::vector<Contig> load_contigs(const std::string& dir) {
     { std::ifstream f(dir + "/mapping_PRGonly/referenceGenome.fa"); std::string id; while (std::getline(f, line)) { if (line.empty()) continue; if (line[0] == '>') { id = line.substr(1); fa[id].clear(); } else fa[id] += line; } }
     for (Contig& c : cs) {
         c.seq = fa.at("PRG_" + std::to_string(c.id));
-        FILE* tf = fopen((dir + "/translation/" + std::to_string(c.id) + ".txt").c_str(), "r");
+        FILE* tf = fopen((dir + "/translation/" + std::to_string(c.id) + ".txt").c_str(), "rb");
         if (!tf) throw std::runtime_error("missing translation file");
-        long long v; while (fscanf(tf, "%lld", &v) == 1) c.lv.push_back((int32_t)v);
+        fseek(tf, 0, SEEK_END); long fn = ftell(tf); fseek(tf, 0, SEEK_SET);
+        std::string buf((size_t)fn, 0); if (fn > 0 && fread(&buf[0], 1, (size_t)fn, tf) != (size_t)fn) throw std::runtime_error("short read");
         fclose(tf);
+        c.lv.reserve(c.seq.size());
+        { long long v = 0; bool have = false; for (char ch : buf) { if (ch >= '0' && ch <= '9') { v = v * 10 + (ch - '0'); have = true; } else { if (have) c.lv.push_back((int32_t)v); v = 0; have = false; } } if (have) c.lv.push_back((int32_t)v); }
         if (c.lv.size() != c.seq.size()) throw std::runtime_error("translation/sequence length mismatch for contig " + c.name);
     }
     return cs;
@@ -441,7 +446,6 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
     const int max_chains = arg<int>(a, "max-chains", 12);
     const double decoy_frac = arg<double>(a, "decoy-frac", 0.02);
     const uint64_t seed = arg<uint64_t>(a, "seed", 0xB200);
-    Rng R(seed ^ 0x9E3779B97F4A7C15ull);
     std::vector<Contig> cs = load_contigs(prg);
     std::vector<int> haps; for (size_t i = 0; i < cs.size(); i++) if (cs[i].is_hap) haps.push_back((int)i);
     if (haps.empty()) throw std::runtime_error("no haplotype contigs");
@@ -449,15 +453,29 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
     std::vector<std::pair<int32_t, int32_t>> gene_ranges;
     for (const Contig& c : cs) if (!c.is_hap && !c.lv.empty()) gene_ranges.push_back({c.lv.front(), c.lv.back()});
 
-    std::vector<int64_t> read_off{0}; std::vector<uint8_t> bases, quals;
-    std::vector<int32_t> chain_off{0}, chain_contig, chain_pos, chain_as, cigar_off{0}; std::vector<uint16_t> chain_flag; std::vector<uint32_t> cigar;
-    std::vector<int32_t> truth_first, truth_last, truth_src;
-
+    struct Out {
+        std::vector<int64_t> read_len; std::vector<uint8_t> bases, quals;
+        std::vector<int32_t> chain_cnt, chain_contig, chain_pos, chain_as, cigar_cnt; std::vector<uint16_t> chain_flag; std::vector<uint32_t> cigar;
+        std::vector<int32_t> truth_first, truth_last, truth_src;
+    };
     auto comp = [](char c) { switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; } return 'N'; };
     (void)comp;
-    auto sample_q = [&]() -> char { double u = R.u(); int q; if (u < 0.75) q = 34 + (int)R.below(8); else if (u < 0.93) q = 22 + (int)R.below(12); else if (u < 0.99) q = 8 + (int)R.below(14); else q = 2; return (char)(q + 33); };
-
-    for (int64_t p = 0; p < n_pairs; p++) {
+    unsigned n_threads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("HLALA_SYNTH_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
+    const int64_t chunk = 4096; const int64_t n_chunks = (n_pairs + chunk - 1) / chunk;
+    std::vector<Out> outs((size_t)n_chunks);
+    std::atomic<int64_t> next_chunk(0);
+    auto worker = [&]() {
+      for (;;) {
+        int64_t ck = next_chunk.fetch_add(1); if (ck >= n_chunks) break;
+        Out& O = outs[(size_t)ck];
+        std::vector<uint8_t>& bases = O.bases; std::vector<uint8_t>& quals = O.quals;
+        std::vector<int32_t>& chain_contig = O.chain_contig; std::vector<int32_t>& chain_pos = O.chain_pos; std::vector<int32_t>& chain_as = O.chain_as;
+        std::vector<uint16_t>& chain_flag = O.chain_flag; std::vector<uint32_t>& cigar = O.cigar;
+        std::vector<int32_t>& truth_first = O.truth_first; std::vector<int32_t>& truth_last = O.truth_last; std::vector<int32_t>& truth_src = O.truth_src;
+        for (int64_t p = ck * chunk; p < std::min(n_pairs, (ck + 1) * chunk); p++) {
+        Rng R((seed ^ 0x9E3779B97F4A7C15ull) + (uint64_t)p * 0xD1B54A32D192ED03ull);
+        auto sample_q = [&]() -> char { double u = R.u(); int q; if (u < 0.75) q = 34 + (int)R.below(8); else if (u < 0.93) q = 22 + (int)R.below(12); else if (u < 0.99) q = 8 + (int)R.below(14); else q = 2; return (char)(q + 33); };
         const Contig* src; int64_t start; int gap;
         for (;;) {
             src = &cs[haps[R.below(haps.size())]];
@@ -529,14 +547,34 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
             for (size_t k : ord) {
                 const Chain& ch = chains[k];
                 chain_contig.push_back(ch.contig); chain_pos.push_back(ch.pos); chain_flag.push_back(ch.flag); chain_as.push_back(ch.as);
-                cigar.insert(cigar.end(), ch.cigar.begin(), ch.cigar.end()); cigar_off.push_back((int32_t)cigar.size());
+                cigar.insert(cigar.end(), ch.cigar.begin(), ch.cigar.end()); O.cigar_cnt.push_back((int32_t)ch.cigar.size());
             }
-            chain_off.push_back((int32_t)chain_contig.size());
+            O.chain_cnt.push_back((int32_t)ord.size());
             for (const ReadItem& it : rd) { bases.push_back((uint8_t)it.b); quals.push_back((uint8_t)it.q); }
-            read_off.push_back((int64_t)bases.size());
+            O.read_len.push_back((int64_t)rd.size());
             int32_t tf = -1, tl = -1; for (const ReadItem& it : rd) if (it.lv >= 0) { if (tf < 0) tf = it.lv; tl = it.lv; }
             truth_first.push_back(tf); truth_last.push_back(tl); truth_src.push_back((int32_t)(src - cs.data()));
         }
+    }
+      }
+    };
+    { std::vector<std::thread> th; for (unsigned t = 0; t < n_threads; t++) th.emplace_back(worker); for (auto& t : th) t.join(); }
+    std::vector<int64_t> read_off{0}; std::vector<uint8_t> bases, quals;
+    std::vector<int32_t> chain_off{0}, chain_contig, chain_pos, chain_as, cigar_off{0}; std::vector<uint16_t> chain_flag; std::vector<uint32_t> cigar;
+    std::vector<int32_t> truth_first, truth_last, truth_src;
+    { size_t nb = 0, nc = 0, ng = 0; for (const Out& O : outs) { nb += O.bases.size(); nc += O.chain_contig.size(); ng += O.cigar.size(); }
+      bases.reserve(nb); quals.reserve(nb); chain_contig.reserve(nc); chain_pos.reserve(nc); chain_as.reserve(nc); chain_flag.reserve(nc); cigar.reserve(ng); cigar_off.reserve(nc + 1);
+      read_off.reserve((size_t)n_pairs * 2 + 1); chain_off.reserve((size_t)n_pairs * 2 + 1); }
+    for (Out& O : outs) {
+        for (int64_t l : O.read_len) read_off.push_back(read_off.back() + l);
+        bases.insert(bases.end(), O.bases.begin(), O.bases.end()); quals.insert(quals.end(), O.quals.begin(), O.quals.end());
+        for (int32_t c : O.chain_cnt) chain_off.push_back(chain_off.back() + c);
+        chain_contig.insert(chain_contig.end(), O.chain_contig.begin(), O.chain_contig.end()); chain_pos.insert(chain_pos.end(), O.chain_pos.begin(), O.chain_pos.end());
+        chain_as.insert(chain_as.end(), O.chain_as.begin(), O.chain_as.end()); chain_flag.insert(chain_flag.end(), O.chain_flag.begin(), O.chain_flag.end());
+        for (int32_t c : O.cigar_cnt) cigar_off.push_back(cigar_off.back() + c);
+        cigar.insert(cigar.end(), O.cigar.begin(), O.cigar.end());
+        truth_first.insert(truth_first.end(), O.truth_first.begin(), O.truth_first.end()); truth_last.insert(truth_last.end(), O.truth_last.begin(), O.truth_last.end()); truth_src.insert(truth_src.end(), O.truth_src.begin(), O.truth_src.end());
+        O = Out();
     }
     ArrayFile f;
     std::vector<int32_t> contig_ids; for (const Contig& c : cs) contig_ids.push_back(c.id);

@@ -27,6 +27,7 @@
 #include <map>
 #include <unordered_map>
 #include <chrono>
+#include <omp.h>
 
 #include "mapper/processBAM.h"
 #include "Graph/Graph.h"
@@ -151,11 +152,16 @@ public:
         return 0;
     }
 
-    int run_pairs(const Batch& b, double is_mean, double is_sd, int cap, double* pair_mapq, double* read_mapq, uint8_t* read_reverse, int32_t* n_cols,
+    int run_pairs(const Batch& b, double is_mean, double is_sd, int cap, int threads, double* pair_mapq, double* read_mapq, uint8_t* read_reverse, int32_t* n_cols,
                   int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) const {
         boost::math::normal nd(is_mean, is_sd);
         double pen = log(boost::math::pdf(nd, is_mean + 8 * is_sd));   // processBAM.cpp:2342-2346
+        // threads == 1 is what the reference does (HLA-LA.cpp:799 passes threads = 1; the omp pragmas at processBAM.cpp:2076,2267,2390
+        // are commented out). threads > 1 is a courtesy upper bound: alignOneReadPair is const, the DP only requires init_for_threads.
+        if (threads < 1) threads = 1;
+        omp_set_num_threads(threads); eA->init_for_threads(threads);
         auto t0 = std::chrono::steady_clock::now();
+        #pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
         for (int64_t p = 0; p < b.n_reads / 2; p++) {
             mapper::reads::protoSeeds ps; std::vector<int32_t> o1, o2;
             std::string name = "r" + std::to_string(p);
@@ -166,9 +172,12 @@ public:
             read_mapq[2 * p] = res.chains.first.mapQ; read_mapq[2 * p + 1] = res.chains.second.mapQ;
             read_reverse[2 * p] = res.chains.first.reverse; read_reverse[2 * p + 1] = res.chains.second.reverse;
             size_t oa = (size_t)(2 * p) * cap, ob = (size_t)(2 * p + 1) * cap;
-            export_chain(res.chains.first, cap, n_cols + 2 * p, level + oa, edge + oa, gchar + oa, schar + oa, from_seed + oa, mapq + oa);
-            export_chain(res.chains.second, cap, n_cols + 2 * p + 1, level + ob, edge + ob, gchar + ob, schar + ob, from_seed + ob, mapq + ob);
+            if (level) {
+                export_chain(res.chains.first, cap, n_cols + 2 * p, level + oa, edge + oa, gchar + oa, schar + oa, from_seed + oa, mapq + oa);
+                export_chain(res.chains.second, cap, n_cols + 2 * p + 1, level + ob, edge + ob, gchar + ob, schar + ob, from_seed + ob, mapq + ob);
+            }
         }
+        omp_set_num_threads(1); eA->init_for_threads(1);
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return 0;
     }
@@ -262,12 +271,12 @@ int hlala_ref_chains(void* h, long long n_reads, const int64_t* read_off, const 
 
 int hlala_ref_pairs(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
                     const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
-                    const int32_t* cigar_off, const uint32_t* cigar, double is_mean, double is_sd, int cap,
+                    const int32_t* cigar_off, const uint32_t* cigar, double is_mean, double is_sd, int cap, int threads,
                     double* pair_mapq, double* read_mapq, uint8_t* read_reverse, int32_t* n_cols,
                     int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) {
     Driver* d = (Driver*)h;
     Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
-    return guarded([&]() { return d->run_pairs(b, is_mean, is_sd, cap, pair_mapq, read_mapq, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
+    return guarded([&]() { return d->run_pairs(b, is_mean, is_sd, cap, threads, pair_mapq, read_mapq, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
 }
 
 } // extern "C"

@@ -14,10 +14,14 @@ def quiet(fn, *a, **k):
         os.dup2(so, 1); os.dup2(se, 2); os.close(devnull)
 
 
-def main():
+def main(which="S"):
     d = tempfile.mkdtemp(prefix="prg")
-    H.synth_prg(d, levels=25000, haps=4, genes=2, alleles=64)
-    b = H.synth_reads(d, d + "/seeds.bin", pairs=2000, len=100, clip_frac=0.15)
+    if which == "S":
+        H.synth_prg(d, levels=25000, haps=4, genes=2, alleles=64)
+        b = H.synth_reads(d, d + "/seeds.bin", pairs=2000, len=100, clip_frac=0.15)
+    else:   # gene blocks: ~14 nodes per level, ~11 chains per read
+        H.synth_prg(d, levels=60000, haps=8, genes=17, alleles=1000)
+        b = H.synth_reads(d, d + "/seeds.bin", pairs=600, len=150, clip_frac=0.15, gene_frac=1.0)
     R = quiet(H.Ref, d)
     t = time.time(); rc = quiet(R.chains, b); t_ref = time.time() - t
     P = H.Product(d); P.to_gpu(0)
@@ -69,4 +73,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "S")

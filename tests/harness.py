@@ -108,13 +108,19 @@ class Ref:
                   ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll", "level", "edge", "gchar", "schar", "from_seed")]))
         return o
 
-    def pairs(self, b, is_mean, is_sd, cap=1024):
+    def pairs(self, b, is_mean, is_sd, cap=1024, threads=1, columns=True):
         nr = len(b["read_off"]) - 1
+        if not columns:
+            o = dict(pair_mapq=np.zeros(nr // 2, np.float64), read_mapq=np.zeros(nr, np.float64), read_reverse=np.zeros(nr, np.uint8), n_cols=np.zeros(nr, np.int32))
+            sec = C.c_double(0)
+            self._chk(self.lib.hlala_ref_pairs(self.h, *batch_args(b), C.c_double(is_mean), C.c_double(is_sd), C.c_int(cap), C.c_int(threads), p(o["pair_mapq"]), p(o["read_mapq"]), p(o["read_reverse"]), p(o["n_cols"]), None, None, None, None, None, None, C.byref(sec)))
+            o["seconds"] = sec.value
+            return o
         o = dict(pair_mapq=np.zeros(nr // 2, np.float64), read_mapq=np.zeros(nr, np.float64), read_reverse=np.zeros(nr, np.uint8), n_cols=np.zeros(nr, np.int32),
                  level=np.zeros((nr, cap), np.int32), edge=np.zeros((nr, cap), np.int32), gchar=np.zeros((nr, cap), np.uint8), schar=np.zeros((nr, cap), np.uint8),
                  from_seed=np.zeros((nr, cap), np.uint8), mapq=np.zeros((nr, cap), np.uint8))
         sec = C.c_double(0)
-        self._chk(self.lib.hlala_ref_pairs(self.h, *batch_args(b), C.c_double(is_mean), C.c_double(is_sd), C.c_int(cap), *[p(o[k]) for k in
+        self._chk(self.lib.hlala_ref_pairs(self.h, *batch_args(b), C.c_double(is_mean), C.c_double(is_sd), C.c_int(cap), C.c_int(threads), *[p(o[k]) for k in
                   ("pair_mapq", "read_mapq", "read_reverse", "n_cols", "level", "edge", "gchar", "schar", "from_seed", "mapq")], C.byref(sec)))
         o["seconds"] = sec.value
         return o
