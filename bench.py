@@ -246,7 +246,7 @@ def main():
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.finish()
-    kms = (C.c_double * 4)(); kl = (C.c_int * 4)()
+    kms = (C.c_double * 6)(); kl = (C.c_int * 6)()
     P._chk(L.hlala_session_timing(sess, kms, kl))
     L.hlala_session_set_timing(sess, 0)
     launches = L.hlala_session_launches(sess)
@@ -259,7 +259,8 @@ def main():
     value = n_gpus * args.pairs * args.steps / (ms_total / 1000.0)
     if rank == 0:
         sys.stderr.write("[bench] resident: %.1f ms/step, %.0f pairs/s; kernel ms/step: seed %.1f extend %.1f finish %.1f pair %.1f; launches %d; errors %d\n" % (
-            ms_total / args.steps, value, kms[0] / args.steps, kms[1] / args.steps, kms[2] / args.steps, kms[3] / args.steps, launches, dig[3]))
+            ms_total / args.steps, value, kms[0] / args.steps, (kms[1] + kms[4] + kms[5]) / args.steps, kms[2] / args.steps, kms[3] / args.steps, launches, dig[3]))
+        sys.stderr.write("[bench] extension ms/step: warp-small %.1f warp-large %.1f scalar %.1f\n" % (kms[1] / args.steps, kms[4] / args.steps, kms[5] / args.steps))
 
     # ---- end to end through the host-buffer C-ABI call (pinned host inputs, H2D + kernels + D2H inside the timed region)
     pinned = {k: torch.from_numpy(b[k]).pin_memory() for k in H.BATCH_KEYS}
@@ -305,9 +306,9 @@ def main():
     P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(sess2)))
     chain_bytes = int(L.hlala_session_chain_kernel_bytes(sess2)); total_bytes = int(L.hlala_session_algorithmic_bytes(sess2))
     L.hlala_session_free(sess2)
-    names = ["k_chain_seed", "k_extend", "k_chain_finish", "k_pair"]
-    per_kernel = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kl[i] / args.steps} for i in range(4)}
-    dom = max(range(4), key=lambda i: kms[i])
+    names = ["k_chain_seed", "k_extend_warp<small>", "k_chain_finish", "k_pair", "k_extend_warp<large>", "k_extend(scalar)"]
+    per_kernel = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kl[i] / args.steps} for i in range(6)}
+    dom = max(range(6), key=lambda i: kms[i])
     ach = None; frac = None
     if kms[0] > 0:
         ach = chain_bytes * args.steps / (kms[0] / 1000.0) / 1e9

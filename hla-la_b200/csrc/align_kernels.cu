@@ -1,6 +1,7 @@
 // CUDA kernels of the alignment path + their launchers. Compiled for sm_100a only.
 #include "chain_kernel.cuh"
 #include "extend_dp.h"
+#include "extend_warp.cuh"
 #include "pair_kernel.cuh"
 #include "align_kernels.h"
 
@@ -80,6 +81,42 @@ __device__ void finalize_chain(const ChainParams& P, const WarpSlab& S, int slot
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Kernel 0: one thread per read. Strand rule (processBAM.cpp:3216), PRG start/stop of every BAM record
+// (alignment_get_startstop_PRGcoordinates, processBAM.cpp:3840) and the identical-coordinates rule (:3234). The reference aligns
+// a chain and only then discards it as a duplicate; the outcome does not depend on the discarded work, so it is skipped here.
+__global__ void k_prepare(ChainParams P) {
+    const DevGraph& G = P.g; const DevBatch& B = P.b;
+    const int r = P.read_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.read_end) return;
+    const int s0 = B.chain_off[r], s1 = B.chain_off[r + 1];
+    const int prim = B.read_primary[r];
+    for (int s = s0; s < s1; s++) {
+        const int c = B.chain_order[s];
+        int st = CH_TODO;
+        if (prim < 0) st = HLALA_E_INVARIANT_DEV;
+        else if ((B.chain_flag[c] ^ B.chain_flag[B.chain_order[prim]]) & 0x10) st = CH_SKIPPED_STRAND;
+        else {
+            const int contig = B.chain_contig[c]; const int pos = B.chain_pos[c];
+            if (contig < 0 || contig >= G.n_contigs) st = HLALA_E_ARG_DEV;
+            else {
+                int reflen = 0;
+                for (int k = B.cigar_off[c]; k < B.cigar_off[c + 1]; k++) { uint32_t cg = B.cigar[k]; int op = cg & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += (int)(cg >> 4); }
+                const int64_t cbase = G.contig_off[contig]; const int clen = (int)(G.contig_off[contig + 1] - cbase);
+                if (pos < 0 || reflen < 1 || pos + reflen > clen) st = HLALA_E_INVARIANT_DEV;
+                else {
+                    const int idf = G.contig_level[cbase + pos], idl = G.contig_level[cbase + pos + reflen - 1];
+                    P.id_first[s] = idf; P.id_last[s] = idl;
+                    if (P.dedup) { for (int t = s0; t < s; t++) if (P.status[t] == CH_TODO && P.id_first[t] == idf && P.id_last[t] == idl) { st = CH_DUPLICATE; break; } }
+                }
+            }
+        }
+        P.status[s] = st;
+        if (st == CH_TODO) { int idx = atomicAdd(P.todo_count, 1); P.todo_slots[idx] = s; }
+        else { P.n_cols[s] = 0; P.ll[s] = 0; if (st < 0) atomicAdd(P.error_count, 1); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,26 +124,21 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
     WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.maxcol, P.pool_cap, P.win_cap);
     const DevBatch& B = P.b;
     const int nw = gridDim.x * K1_WARPS;
-    for (int slot = P.slot_base + blockIdx.x * K1_WARPS + warp; slot < P.slot_end; slot += nw) {
+    const int n_todo = *P.todo_count;
+    for (int ti = blockIdx.x * K1_WARPS + warp; ti < n_todo; ti += nw) {
+        const int slot = P.todo_slots[ti];
         const int r = B.slot_read[slot];
-        const int prim = B.read_primary[r];
         const int c = B.chain_order[slot];
         int rc = 0;
-        if (prim < 0) rc = HLALA_E_INVARIANT_DEV;                   // protoSeeds::read1_getPrimaryAlignmentI asserts
-        else if ((B.chain_flag[c] ^ B.chain_flag[B.chain_order[prim]]) & 0x10) {
-            if (lane == 0) { P.status[slot] = CH_SKIPPED_STRAND; P.n_cols[slot] = 0; P.ll[slot] = 0; }
-            continue;                                                // processBAM.cpp:3216,3305
-        }
         const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
         ColBuf A{S.lvlA, S.gA, S.sA}, Bc{S.lvlB, S.gB, S.sB};
         int start_raw = -1, stop_raw = -1, n = 0, idf = -1, idl = -1;
         if (rc == 0) { n = expand_cigar(P, c, rd0, rdlen, A, lane, start_raw, stop_raw, idf, idl); if (n < 0) rc = n; }
-        if (rc == 0 && lane == 0) { P.id_first[slot] = idf; P.id_last[slot] = idl; }
         if (rc == 0 && !(start_raw < stop_raw)) rc = HLALA_E_INVARIANT_DEV;     // processBAM.cpp:5245
         if (rc == 0) { n = trim_and_fill(P, A, n, Bc, lane, start_raw, stop_raw); if (n < 0) rc = n; }
         if (rc == 0) n = clean_columns(Bc, n, A, lane);
         if (rc == 0) n = restrict_columns(P, Bc, n, A, lane, start_raw, stop_raw);
-        if (rc == 0) rc = viterbi_backtrace(P, Bc, n, S, S.lvlA, lane);
+        if (rc == 0) rc = P.bt16 ? viterbi_backtrace<true>(P, Bc, n, S, S.lvlA, lane) : viterbi_backtrace<false>(P, Bc, n, S, S.lvlA, lane);
         if (rc != 0) {
             if (lane == 0) { P.status[slot] = rc; P.n_cols[slot] = 0; P.ll[slot] = 0; atomicAdd(P.error_count, 1); }
             __syncwarp();
@@ -149,6 +181,7 @@ __global__ void __launch_bounds__(64) k_extend(ExtParams E) {
         const int n = P.n_cols[slot]; const int sb = P.seed_begin[slot], se = P.seed_end[slot];
         const int l_first = P.first_level[slot], l_last = P.last_level[slot];
         const int32_t* se_edge = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol;
+        if (E.only_deferred && E.ext_rc[t] != DP_DEFER) continue;
         E.ext_n[t] = 0; E.ext_nlvl[t] = 0; E.ext_rc[t] = 0;
         DpResult res; int rc = 0;
         if (side == 0) {
@@ -162,6 +195,41 @@ __global__ void __launch_bounds__(64) k_extend(ExtParams E) {
         }
         E.ext_rc[t] = rc;
         if (rc == 0) { E.ext_n[t] = res.n_cols; E.ext_nlvl[t] = res.n_lvl; }
+    }
+}
+
+// Kernel 2 (fast path): extension DP, one warp per (pending chain, side); see extend_warp.cuh.
+__host__ __device__ inline size_t wd_hbm_bytes() { return sizeof(DpCell) * (size_t)DP_CELL_CAP + 4 * (size_t)DP_HASH_CAP + 16; }
+template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend_warp(ExtParams E) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * CFG::WARPS + warp; const int nw = gridDim.x * CFG::WARPS;
+    if (gw >= E.n_wd_warps) return;
+    WdSlab S = wd_carve<CFG>(smem + (size_t)warp * wd_slab_bytes<CFG>());
+    unsigned char* hb = E.wd_scratch + (size_t)gw * wd_hbm_bytes();
+    DpGraph dg; dg.n_levels = G.n_levels; dg.level_node_off = G.level_node_off; dg.edge_pack = G.edge_pack;
+    dg.node_out_off = G.node_out_off; dg.node_out = G.node_out; dg.node_in_off = G.node_in_off; dg.node_in = G.node_in;
+    dg.path_off = G.path_off; dg.path_edges = G.path_edges; dg.path_from = G.path_from; dg.path_to = G.path_to;
+    dg.jump_fwd_off = G.jump_fwd_off; dg.jump_fwd_path = G.jump_fwd_path; dg.jump_bwd_off = G.jump_bwd_off; dg.jump_bwd_path = G.jump_bwd_path;
+    WdCtx C; C.G = &dg; C.cells = (DpCell*)hb; C.hash = (uint32_t*)(hb + sizeof(DpCell) * (size_t)DP_CELL_CAP); C.gens = C.hash + DP_HASH_CAP;
+    for (int t = gw; t < 2 * E.n_pending; t += nw) {
+        const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
+        const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
+        const int n = P.n_cols[slot]; const int sb = P.seed_begin[slot], se = P.seed_end[slot];
+        const int l_first = P.first_level[slot], l_last = P.last_level[slot];
+        const int32_t* se_edge = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol;
+        if (E.only_deferred && E.ext_rc[t] != DP_DEFER) continue;
+        DpResult res; res.n_cols = 0; res.n_lvl = 0; res.far_y = 0; int rc = 0; bool run = false;
+        C.seq = B.bases + rd0; C.seq_len = rdlen;
+        if (side == 0) {
+            if (sb != 0 && l_first > 0) { run = true; C.start_seq = sb; C.start_level = l_first; C.start_z = (int)(G.edge_pack[se_edge[0]] & 255u); C.pos = false; }
+        } else {
+            if (se != rdlen - 1 && l_last + 1 < G.n_levels - 1) { run = true; C.start_seq = se + 1; C.start_level = l_last + 1; C.start_z = (int)((G.edge_pack[se_edge[n - 1]] >> 8) & 255u); C.pos = true; }
+        }
+        if (run) rc = wd_extend<CFG>(C, S, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res, lane);
+        if (lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; }
+        __syncwarp();
     }
 }
 
@@ -233,11 +301,42 @@ cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t strea
     return cudaGetLastError();
 }
 
+cudaError_t launch_prepare(const ChainParams& P, cudaStream_t stream) {
+    int n = P.read_end - P.read_begin; if (n <= 0) return cudaSuccess;
+    k_prepare<<<(n + 127) / 128, 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
     int threads = 64; int blocks = (E.n_dp_threads + threads - 1) / threads;
     k_extend<<<blocks, threads, 0, stream>>>(E);
     return cudaGetLastError();
+}
+
+template <class CFG> static int wd_occupancy(int n_sm) {
+    size_t smem = wd_slab_bytes<CFG>() * CFG::WARPS; int per_sm = 1;
+    if (cudaFuncSetAttribute(k_extend_warp<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_warp<CFG>, CFG::WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return n_sm * per_sm * CFG::WARPS;
+}
+int wd_warps_for(int n_sm) { return std::max(wd_occupancy<WdSmall>(n_sm), wd_occupancy<WdLarge>(n_sm)); }
+size_t wd_warp_scratch_bytes() { return wd_hbm_bytes(); }
+
+template <class CFG> static cudaError_t launch_wd(ExtParams E, int n_sm, cudaStream_t stream) {
+    int warps = std::min(wd_occupancy<CFG>(n_sm), E.n_wd_warps);
+    if (warps < CFG::WARPS) return cudaErrorInvalidConfiguration;
+    E.n_wd_warps = warps;
+    long long want = ((long long)2 * E.n_pending + CFG::WARPS - 1) / CFG::WARPS;
+    int grid = (int)std::min<long long>(want, (long long)(warps / CFG::WARPS)); if (grid < 1) grid = 1;
+    k_extend_warp<CFG><<<grid, CFG::WARPS * 32, wd_slab_bytes<CFG>() * CFG::WARPS, stream>>>(E);
+    return cudaGetLastError();
+}
+// large = 0: every task through the small configuration; large = 1: only the tasks the small one deferred, through the large one
+cudaError_t launch_extend_warp(const ExtParams& E0, int n_sm, int large, cudaStream_t stream) {
+    if (E0.n_pending <= 0) return cudaSuccess;
+    ExtParams E = E0; E.only_deferred = large;
+    return large ? launch_wd<WdLarge>(E, n_sm, stream) : launch_wd<WdSmall>(E, n_sm, stream);
 }
 
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {

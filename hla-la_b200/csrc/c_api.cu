@@ -12,6 +12,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace hlala;
@@ -79,17 +80,24 @@ struct PreparedBatch {
     void build(const hlala_seed_batch_t& b) {
         n_reads = b.n_reads; n_chains = b.chain_off[b.n_reads];
         chain_order.resize(n_chains); read_primary.assign(n_reads, -1); slot_read.resize(n_chains);
-        std::vector<int32_t> idx;
-        for (int64_t r = 0; r < n_reads; r++) {
-            int32_t c0 = b.chain_off[r], c1 = b.chain_off[r + 1];
-            idx.resize(c1 - c0); for (int32_t i = 0; i < c1 - c0; i++) idx[i] = c0 + i;
-            std::sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return b.chain_as[x] < b.chain_as[y]; });
-            std::reverse(idx.begin(), idx.end());
-            for (int32_t i = 0; i < c1 - c0; i++) {
-                chain_order[c0 + i] = idx[i]; slot_read[c0 + i] = (int32_t)r;
-                if (read_primary[r] < 0 && !(b.chain_flag[idx[i]] & 0x100)) read_primary[r] = c0 + i;
+        auto work = [&](int64_t r0, int64_t r1) {
+            std::vector<int32_t> idx;
+            for (int64_t r = r0; r < r1; r++) {
+                int32_t c0 = b.chain_off[r], c1 = b.chain_off[r + 1];
+                idx.resize(c1 - c0); for (int32_t i = 0; i < c1 - c0; i++) idx[i] = c0 + i;
+                std::sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return b.chain_as[x] < b.chain_as[y]; });
+                std::reverse(idx.begin(), idx.end());
+                for (int32_t i = 0; i < c1 - c0; i++) {
+                    chain_order[c0 + i] = idx[i]; slot_read[c0 + i] = (int32_t)r;
+                    if (read_primary[r] < 0 && !(b.chain_flag[idx[i]] & 0x100)) read_primary[r] = c0 + i;
+                }
             }
-        }
+        };
+        unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (n_reads < 20000) nt = 1;
+        std::vector<std::thread> th; int64_t per = (n_reads + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; t++) { int64_t r0 = t * per, r1 = std::min<int64_t>(n_reads, r0 + per); if (r0 < r1) th.emplace_back(work, r0, r1); }
+        for (auto& t : th) t.join();
     }
 };
 
@@ -118,28 +126,32 @@ int check_batch(const hlala_seed_batch_t* b) {
 }
 
 struct ChainScratch {
-    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count;
+    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count, todo_slots, todo_count;
     void alloc(int32_t n_chains, int32_t wave_chains, int32_t maxcol) {
         size_t nc = (size_t)std::max(n_chains, 1); size_t wc = (size_t)std::max(wave_chains, 1);
         status.alloc(nc * 4); n_cols.alloc(nc * 4); seed_begin.alloc(nc * 4); seed_end.alloc(nc * 4); ll.alloc(nc * 8); first_level.alloc(nc * 4); last_level.alloc(nc * 4);
         c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol); error_count.alloc(4);
-        id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4);
+        id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4); todo_slots.alloc(nc * 4); todo_count.alloc(4);
     }
     void fill(ChainParams& P) {
         P.status = status.as<int32_t>(); P.n_cols = n_cols.as<int32_t>(); P.seed_begin = seed_begin.as<int32_t>(); P.seed_end = seed_end.as<int32_t>(); P.ll = ll.as<double>();
         P.first_level = first_level.as<int32_t>(); P.last_level = last_level.as<int32_t>(); P.c_edge = c_edge.as<int32_t>(); P.c_schar = c_schar.as<uint8_t>(); P.c_fromseed = c_fromseed.as<uint8_t>();
         P.error_count = error_count.as<int32_t>(); P.id_first = id_first.as<int32_t>(); P.id_last = id_last.as<int32_t>();
         P.pending_slots = pending_slots.as<int32_t>(); P.pending_count = pending_count.as<int32_t>();
+        P.todo_slots = todo_slots.as<int32_t>(); P.todo_count = todo_count.as<int32_t>();
     }
 };
 
-// Shared-memory budget of one warp slab: 4 slabs per CTA must fit the 227 KB a CTA may use. Whatever the fixed arrays leave is split
-// 2:1 between the backtrack pool (sum over columns of the level width) and the staged edge window (falls back to L2 reads if short).
-void chain_caps(int32_t maxcol, ChainParams& P) {
-    P.maxcol = maxcol;
-    const long long budget = 56000 - ((long long)maxcol * (8 + 4 + 4 + 2) + 2 * 4 * 256 + 64);
-    long long pool = std::min<long long>(8LL * maxcol, budget * 2 / 3 / 4), win = std::min<long long>(4LL * maxcol, budget / 3 / 4);
-    P.pool_cap = (int32_t)std::max<long long>(pool, 512); P.win_cap = (int32_t)std::max<long long>(win, 256);
+// Shared-memory slab of one warp of the chain kernels. The backtrack pool holds one entry per (column, node of the column's level):
+// max(4 x max_columns, 2560) entries cover a 150-column read inside a 14-node-wide gene block; a chain that needs more gets
+// HLALA_E_CAPACITY. The staged edge window falls back to L2 reads when the window is larger than its capacity.
+void chain_caps(int32_t maxcol, bool bt16, ChainParams& P) {
+    P.maxcol = maxcol; P.bt16 = bt16 ? 1 : 0;
+    long long pool_entries = std::max<long long>(4LL * maxcol, 2560);       // entries needed
+    P.pool_cap = (int32_t)(bt16 ? (pool_entries + 1) / 2 : pool_entries);    // in 32-bit words when 16-bit entries are used
+    P.win_cap = (int32_t)std::max<long long>(2LL * maxcol, 512);
+    while (k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap) * K1_WARPS > 220000 && P.win_cap > 256) P.win_cap /= 2;
+    while (k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap) * K1_WARPS > 220000 && P.pool_cap > 512) P.pool_cap /= 2;
 }
 
 // boost::math::pdf(normal) as Boost.Math computes it (processBAM.cpp:2342-2346, 3446-3472)
@@ -170,7 +182,8 @@ std::vector<double> phred_thresholds() {
 struct Pipeline {
     hlala_graph* g = nullptr; int32_t maxcol = 0;
     PreparedBatch pb; DeviceBatch db; ChainScratch cs;
-    DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch; int32_t ext_cap = 0; int32_t n_dp_threads = 0;
+    DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch; int32_t ext_cap = 0; int32_t n_dp_threads = 0; int32_t n_wd_warps = 0;
+    bool scalar_dp_only = false;   // test hook: run every extension through the scalar kernel
     DevBuf is_table, phred_thr; double is_mean = -1, is_sd = -1, is_pen = 0; int32_t is_dmin = 0, is_n = 0;
     DevBuf pair_mapq, read_mapq, read_reverse, chosen_slot, pair_ll, pair_status, digest;
     DevBuf o_n_cols, o_level, o_edge, o_gchar, o_schar, o_fromseed, o_mapq; bool have_columns = false;
@@ -179,14 +192,15 @@ struct Pipeline {
     int64_t chain_kernel_bytes = 0;
     void tic(int cls, cudaStream_t st) { if (!timing) return; cudaEvent_t a, b; CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b)); CUDA_OK(cudaEventRecord(a, st)); timed.push_back({cls, {a, b}}); }
     void toc(cudaStream_t st) { if (!timing) return; CUDA_OK(cudaEventRecord(timed.back().second.second, st)); }
-    void collect_timing(double ms[4], int launches_per_class[4]) {
-        for (int i = 0; i < 4; i++) { ms[i] = 0; launches_per_class[i] = 0; }
+    void collect_timing(double ms[6], int launches_per_class[6]) {
+        for (int i = 0; i < 6; i++) { ms[i] = 0; launches_per_class[i] = 0; }
         for (auto& t : timed) { float f = 0; CUDA_OK(cudaEventSynchronize(t.second.second)); CUDA_OK(cudaEventElapsedTime(&f, t.second.first, t.second.second)); ms[t.first] += f; launches_per_class[t.first]++; cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
         timed.clear();
     }
     std::vector<int64_t> wave_pair;    // wave w covers pairs [wave_pair[w], wave_pair[w+1])
     size_t scratch_budget = (size_t)6 << 30;   // bytes of per-chain column scratch per wave
     bool allow_env_budget = true;
+    bool dedup = true;    // false: align every same-strand chain (parity tests of the chain kernels)
 
     void prepare(hlala_graph* graph, const hlala_seed_batch_t& b, int32_t mc, cudaStream_t st) {
         g = graph; maxcol = mc;
@@ -210,6 +224,10 @@ struct Pipeline {
         n_dp_threads = g->n_sm * 64;
         dp_scratch.alloc((size_t)n_dp_threads * dp_thread_scratch_bytes());
         CUDA_OK(cudaMemsetAsync(dp_scratch.p, 0, dp_scratch.bytes, st));
+        n_wd_warps = wd_warps_for(g->n_sm);
+        wd_scratch.alloc((size_t)n_wd_warps * wd_warp_scratch_bytes());
+        CUDA_OK(cudaMemsetAsync(wd_scratch.p, 0, wd_scratch.bytes, st));
+        if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;
         // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
         // chosen alignment columns written once, per-pair scalars, coverage RMW
         int64_t nb = b.read_off[b.n_reads]; int64_t ncg = b.cigar_off[pb.n_chains];
@@ -226,7 +244,7 @@ struct Pipeline {
         o_n_cols.alloc((size_t)std::max<int64_t>(pb.n_reads, 2) * 4); o_level.alloc(n * 4); o_edge.alloc(n * 4); o_gchar.alloc(n); o_schar.alloc(n); o_fromseed.alloc(n); o_mapq.alloc(n);
         have_columns = true;
     }
-    ChainParams chain_params() { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, P); P.do_extension = 1; cs.fill(P); return P; }
+    ChainParams chain_params() { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, P); P.do_extension = 1; cs.fill(P); return P; }
 
     void begin_run(cudaStream_t st) {
         launches = 0;
@@ -238,8 +256,9 @@ struct Pipeline {
     ChainParams run_chains_wave(size_t w, cudaStream_t st) {
         ChainParams P = chain_params();
         P.slot_base = db_chain_off(2 * wave_pair[w]); P.slot_end = db_chain_off(2 * wave_pair[w + 1]);
-        CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st));
-        if (P.slot_end > P.slot_base) { tic(0, st); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches++; }
+        P.read_begin = (int32_t)(2 * wave_pair[w]); P.read_end = (int32_t)(2 * wave_pair[w + 1]); P.dedup = dedup ? 1 : 0;
+        CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.todo_count.p, 0, 4, st));
+        if (P.slot_end > P.slot_base) { CUDA_OK(launch_prepare(P, st)); tic(0, st); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches += 2; }
         CUDA_OK(cudaMemcpyAsync(&n_pending, cs.pending_count.p, 4, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         if (n_pending > 0) {
@@ -249,7 +268,16 @@ struct Pipeline {
             }
             ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = ext_edge.as<int32_t>(); E.ext_s = ext_s.as<uint8_t>(); E.ext_n = ext_n.as<int32_t>();
             E.ext_nlvl = ext_nlvl.as<int32_t>(); E.ext_rc = ext_rc.as<int32_t>(); E.dp_scratch = dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
-            tic(1, st); CUDA_OK(launch_extend(E, st)); toc(st); tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 2;
+            E.wd_scratch = wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps;
+            tic(1, st);
+            if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
+            else {
+                CUDA_OK(launch_extend_warp(E, g->n_sm, 0, st)); toc(st);
+                tic(4, st); CUDA_OK(launch_extend_warp(E, g->n_sm, 1, st)); toc(st);
+                tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 3;
+            }
+            toc(st);
+            tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 1;
         }
         return P;
     }
@@ -397,7 +425,7 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(g->device));
         cudaStream_t st = 0;
-        Pipeline pl; pl.scratch_budget = (size_t)1 << 62; pl.allow_env_budget = false; pl.prepare(g, *batch, out->max_columns, st);   // one wave: the chain records are exported whole
+        Pipeline pl; pl.scratch_budget = (size_t)1 << 62; pl.allow_env_budget = false; pl.dedup = false; pl.prepare(g, *batch, out->max_columns, st);   // one wave: the chain records are exported whole
         pl.begin_run(st);
         if (pl.wave_pair.size() > 1) pl.run_chains_wave(0, st);
         const int32_t nc = pl.pb.n_chains, mc = out->max_columns; ChainScratch& cs = pl.cs;
@@ -473,7 +501,7 @@ int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t
 }
 int hlala_session_launches(const hlala_session_t* s) { return s ? s->pl.launches : -1; }
 int hlala_session_set_timing(hlala_session_t* s, int on) { if (!s) return fail(HLALA_E_ARG, "null session"); s->pl.timing = on != 0; return 0; }
-int hlala_session_timing(hlala_session_t* s, double ms[4], int launches[4]) {
+int hlala_session_timing(hlala_session_t* s, double ms[6], int launches[6]) {
     if (!s) return fail(HLALA_E_ARG, "null session");
     return guarded([&]() { s->pl.collect_timing(ms, launches); return 0; });
 }

@@ -23,7 +23,7 @@ __constant__ ScoreTables c_tables;
 
 struct WarpSlab {
     int32_t* lvlA; int32_t* lvlB; uint8_t* gA; uint8_t* sA; uint8_t* gB; uint8_t* sB;
-    uint32_t* bt; uint32_t* win; int32_t* weoff; uint16_t* coloff; uint32_t* cur; uint32_t* nxt;
+    uint32_t* bt; uint32_t* win; uint16_t* weoff; uint16_t* wwid; uint16_t* coloff; uint32_t* cur; uint32_t* nxt;
 };
 
 __device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_cap, int win_cap) {
@@ -32,7 +32,7 @@ __device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_
     s.lvlB = (int32_t*)p; p += (size_t)maxcol * 4;
     s.bt = (uint32_t*)p; p += (size_t)pool_cap * 4;
     s.win = (uint32_t*)p; p += (size_t)win_cap * 4;
-    s.weoff = (int32_t*)p; p += (size_t)(maxcol + 2) * 4;
+    s.weoff = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2; s.wwid = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2;
     s.cur = (uint32_t*)p; p += (size_t)K1_WCAP * 4;
     s.nxt = (uint32_t*)p; p += (size_t)K1_WCAP * 4;
     s.coloff = (uint16_t*)p; p += (size_t)((maxcol + 1) / 2 * 2) * 2;
@@ -222,33 +222,41 @@ __device__ int restrict_columns(const ChainParams& P, ColBuf c, int n, ColBuf tm
 
 // --- column Viterbi ("sequence" pass, processBAM.cpp:2789-2832) + backtrace (2838-2932).
 // On return edge_out[col] holds the flat edge id (or -1 for insertion columns) and c.g[col] the chosen edge's emission.
+template <bool BT16>
 __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const WarpSlab& S, int32_t* edge_out, int lane) {
     const DevGraph& G = P.g;
     if (c.lvl[0] == -1 || c.lvl[n - 1] == -1) return HLALA_E_INVARIANT_DEV;
     const int l_first = c.lvl[0], l_last = c.lvl[n - 1];
     const int nlev = l_last - l_first + 1;
-    if (l_last + 1 >= G.n_levels) return HLALA_E_INVARIANT_DEV;
-    // stage the window: edge offsets of levels [l_first, l_last+1] and the packed edges in between
-    for (int i = lane; i <= nlev; i += 32) S.weoff[i] = G.level_edge_off[l_first + i];
+    if (l_last + 1 >= G.n_levels || nlev > P.maxcol) return HLALA_E_INVARIANT_DEV;
+    // stage the window: per level the edge offset (relative) and the node count, then the packed edges in between
+    const int e_base = G.level_edge_off[l_first];
+    int bad = 0;
+    for (int i = lane; i <= nlev + 1; i += 32) {
+        if (i <= nlev) { int rel = G.level_edge_off[l_first + i] - e_base; if (rel > 65535) bad = 1; S.weoff[i] = (uint16_t)rel; }
+        int w = G.level_node_off[l_first + i + 1] - G.level_node_off[l_first + i]; if (w > K1_WCAP) bad = 1; S.wwid[i] = (uint16_t)w;
+    }
+    if (__any_sync(0xffffffffu, bad)) return HLALA_E_CAPACITY_DEV;
     __syncwarp();
-    const int e_base = S.weoff[0]; const int n_win = S.weoff[nlev] - e_base;
+    const int n_win = S.weoff[nlev];
     const bool staged = n_win <= P.win_cap;
     if (staged) for (int i = lane; i < n_win; i += 32) S.win[i] = G.edge_pack[e_base + i];
     __syncwarp();
     // init: every node of the first level, score 0 (processBAM.cpp:2696-2701)
-    const int w0 = G.level_node_off[l_first + 1] - G.level_node_off[l_first];
-    if (w0 > K1_WCAP) return HLALA_E_CAPACITY_DEV;
+    const int w0 = S.wwid[0];
     uint32_t* cur = S.cur; uint32_t* nxt = S.nxt;
+    uint16_t* bt16 = (uint16_t*)S.bt; const int pool_cap = BT16 ? P.pool_cap * 2 : P.pool_cap;
     for (int z = lane; z < w0; z += 32) cur[z] = (1u << 20) | KEY_RANK_MASK;
     __syncwarp();
     int pool = 0; int lev = l_first; int status = 0;
     for (int col = 0; col < n; col++) {
         if (c.lvl[col] == -1) continue;
         if (c.lvl[col] != lev) { status = HLALA_E_INVARIANT_DEV; break; }     // level contiguity (processBAM.cpp:2649-2665)
-        const int e0 = S.weoff[lev - l_first] - e_base, e1 = S.weoff[lev - l_first + 1] - e_base;
-        const int wn = G.level_node_off[lev + 2] - G.level_node_off[lev + 1];
-        if (wn > K1_WCAP || (e1 - e0) > (int)KEY_RANK_MASK) { status = HLALA_E_CAPACITY_DEV; break; }
-        if (pool + wn > P.pool_cap || pool > 65535) { status = HLALA_E_CAPACITY_DEV; break; }
+        const int li = lev - l_first;
+        const int e0 = S.weoff[li], e1 = S.weoff[li + 1];
+        const int wn = S.wwid[li + 1];
+        if (BT16 && (e1 - e0) > 255) { status = HLALA_E_CAPACITY_DEV; break; }
+        if (pool + wn > pool_cap || pool > 65535) { status = HLALA_E_CAPACITY_DEV; break; }
         for (int z = lane; z < wn; z += 32) nxt[z] = 0;
         __syncwarp();
         const uint8_t sc = c.s[col], gc = c.g[col]; const bool isMatch = (sc == gc);
@@ -267,7 +275,10 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
             if (kf != 0 && !(isMatch && em != sc)) {
                 uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
                 uint32_t tz = (pk >> 8) & 255u;
-                if (nxt[tz] == key) S.bt[pool + tz] = (uint32_t)(e - e0) | ((pk & 255u) << 20);   // rank (20 bits) | from_z
+                if (nxt[tz] == key) {                                    // the unique winner records (edge rank, from node)
+                    if (BT16) bt16[pool + tz] = (uint16_t)((e - e0) | ((pk & 255u) << 8));
+                    else S.bt[pool + tz] = (uint32_t)(e - e0) | ((pk & 255u) << 20);
+                }
             }
         }
         if (lane == 0) S.coloff[col] = (uint16_t)pool;
@@ -277,7 +288,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     }
     if (status) return status;
     // end nodes with maximal score; the first of them in canonical node order (processBAM.cpp:2856-2867)
-    const int wl = G.level_node_off[l_last + 2] - G.level_node_off[l_last + 1];
+    const int wl = S.wwid[nlev];
     uint32_t best = 0;
     for (int z = lane; z < wl; z += 32) { uint32_t k = cur[z]; if (k) { uint32_t v = ((k >> 20) << 12) | (uint32_t)(4095 - min(z, 4095)); best = max(best, v); } }
     for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
@@ -286,9 +297,10 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
         int z = 4095 - (int)(best & 4095u); int l = l_last;
         for (int col = n - 1; col >= 0; col--) {
             if (c.lvl[col] == -1) { edge_out[col] = -1; c.g[col] = '_'; continue; }
-            uint32_t ent = S.bt[S.coloff[col] + z];
-            int rank = (int)(ent & KEY_RANK_MASK); int fz = (int)(ent >> 20);
-            int erel = S.weoff[l - l_first] - e_base + rank;
+            int rank, fz;
+            if (BT16) { uint16_t ent = bt16[S.coloff[col] + z]; rank = ent & 255; fz = ent >> 8; }
+            else { uint32_t ent = S.bt[S.coloff[col] + z]; rank = (int)(ent & KEY_RANK_MASK); fz = (int)(ent >> 20); }
+            int erel = S.weoff[l - l_first] + rank;
             uint32_t pk = staged ? S.win[erel] : G.edge_pack[e_base + erel];
             edge_out[col] = e_base + erel; c.g[col] = (uint8_t)(pk >> 16);
             z = fz; l--;

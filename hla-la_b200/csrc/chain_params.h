@@ -19,6 +19,7 @@ struct ChainParams {
     int32_t maxcol;        // capacity of a column slab (and of the output stride)
     int32_t pool_cap;      // backtrack pool entries per warp
     int32_t win_cap;       // staged edge window entries per warp
+    int32_t bt16;          // 1: backtrack entries are 16 bit (graph has <= 255 edges per level and <= 256 nodes per level)
     int32_t do_extension;  // 1: run the soft-clip extension DP
     int32_t slot_base, slot_end;   // this launch handles slots [slot_base, slot_end); column scratch is indexed by slot - slot_base
     // per-slot outputs
@@ -30,7 +31,13 @@ struct ChainParams {
     int32_t* error_count;  // global counter of chains that ended with status < 0
     int32_t* id_first; int32_t* id_last;   // PRG levels of the BAM record's first/last reference base (processBAM.cpp:3840): de-dup key
     int32_t* pending_slots; int32_t* pending_count;   // chains whose seed needs the extension DP
+    int32_t* todo_slots; int32_t* todo_count;         // chains the chain kernel has to align (written by k_prepare)
+    int32_t read_begin, read_end;                     // reads of this wave
+    int32_t dedup;                                    // 1: chains that the pair stage would discard as duplicates are not aligned at all
 };
+
+constexpr int32_t CH_TODO = -100;
+constexpr int32_t CH_DUPLICATE = 3;   // same PRG start/stop as an earlier (better or equal AS) chain of the read (processBAM.cpp:3234)
 
 constexpr int32_t CH_PENDING_EXT = 2;
 
@@ -40,7 +47,9 @@ struct ExtParams {
     int32_t n_pending;
     int32_t* ext_edge; uint8_t* ext_s;      // [2 * n_pending * DP_EXT_CAP]
     int32_t* ext_n; int32_t* ext_nlvl; int32_t* ext_rc;   // [2 * n_pending]
-    unsigned char* dp_scratch; int32_t n_dp_threads;
+    unsigned char* dp_scratch; int32_t n_dp_threads;   // scalar kernel: one slice per thread
+    unsigned char* wd_scratch; int32_t n_wd_warps;     // warp kernel: one slice per warp
+    int32_t only_deferred;                              // scalar kernel: run only the tasks the warp kernel deferred
 };
 
 constexpr int K3_WARPS = 4;
@@ -78,9 +87,9 @@ __host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int wi
     size_t b = 0;
     b += (size_t)maxcol * 4 * 2;          // lvlA, lvlB
     b += (size_t)maxcol * 4;              // gA,sA,gB,sB
-    b += (size_t)pool_cap * 4;            // bt
+    b += (size_t)pool_cap * 4;            // bt (half of it used when entries are 16 bit: pool_cap then counts 16-bit entries * 2)
     b += (size_t)win_cap * 4;             // win
-    b += (size_t)(maxcol + 2) * 4;        // weoff
+    b += (size_t)(maxcol + 4) * 2 * 2;    // weoff, wwid (u16)
     b += (size_t)((maxcol + 1) / 2 * 2) * 2;   // coloff (u16)
     b += (size_t)K1_WCAP * 4 * 2;         // cur, nxt
     return (b + 15) & ~size_t(15);

@@ -69,7 +69,7 @@ __device__ int gather_kept(const PairParams& P, int r, int32_t* kept, int& err) 
     int n = 0;
     for (int s = P.b.chain_off[r]; s < P.b.chain_off[r + 1]; s++) {
         int st = P.status[s];
-        if (st == CH_SKIPPED_STRAND) continue;
+        if (st == CH_SKIPPED_STRAND || st == CH_DUPLICATE) continue;
         if (st != CH_OK) { err = st < 0 ? st : HLALA_E_INVARIANT_DEV; return n; }
         bool dup = false;
         for (int k = 0; k < n; k++) if (P.id_first[kept[k]] == P.id_first[s] && P.id_last[kept[k]] == P.id_last[s]) { dup = true; break; }
