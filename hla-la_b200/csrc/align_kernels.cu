@@ -28,8 +28,12 @@ __device__ void finalize_chain(const ChainParams& P, const WarpSlab& S, int slot
     const int padL = seq_begin - ext_l_bases;
     const int padR = rdlen - 1 - (seq_end + ext_r_bases);
     const int n_total = padL + L.n + n_seed + R.n + padR;
-    if (padL < 0 || padR < 0 || n_total > P.maxcol) {
-        if (lane == 0) { P.status[slot] = (n_total > P.maxcol) ? HLALA_E_CAPACITY_DEV : HLALA_E_INVARIANT_DEV; P.n_cols[slot] = 0; atomicAdd(P.error_count, 1); }
+    if (padL < 0 || padR < 0 || n_total > P.maxcol || n_total > P.slab_cols) {
+        const bool cap = padL >= 0 && padR >= 0;
+        if (lane == 0) {
+            if (cap && P.tier == 0 && n_total <= P.maxcol) { P.status[slot] = CH_DEFERRED; int idx = atomicAdd(P.defer_count, 1); P.defer_slots[idx] = slot; }
+            else { P.status[slot] = cap ? HLALA_E_CAPACITY_DEV : HLALA_E_INVARIANT_DEV; P.n_cols[slot] = 0; atomicAdd(P.error_count, 1); }
+        }
         return;
     }
     const size_t cbase = (size_t)(slot - P.slot_base) * P.maxcol;
@@ -120,13 +124,14 @@ __global__ void k_prepare(ChainParams P) {
 __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t slab = k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap);
-    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.maxcol, P.pool_cap, P.win_cap);
+    const size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
     const DevBatch& B = P.b;
     const int nw = gridDim.x * K1_WARPS;
-    const int n_todo = *P.todo_count;
+    const int n_todo = P.tier == 0 ? *P.todo_count : *P.defer_count;
+    const int32_t* work = P.tier == 0 ? P.todo_slots : P.defer_slots;
     for (int ti = blockIdx.x * K1_WARPS + warp; ti < n_todo; ti += nw) {
-        const int slot = P.todo_slots[ti];
+        const int slot = work[ti];
         const int r = B.slot_read[slot];
         const int c = B.chain_order[slot];
         int rc = 0;
@@ -140,7 +145,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
         if (rc == 0) n = restrict_columns(P, Bc, n, A, lane, start_raw, stop_raw);
         if (rc == 0) rc = P.bt16 ? viterbi_backtrace<true>(P, Bc, n, S, S.lvlA, lane) : viterbi_backtrace<false>(P, Bc, n, S, S.lvlA, lane);
         if (rc != 0) {
-            if (lane == 0) { P.status[slot] = rc; P.n_cols[slot] = 0; P.ll[slot] = 0; atomicAdd(P.error_count, 1); }
+            if (lane == 0) {
+                if (rc == HLALA_E_CAPACITY_DEV && P.tier == 0) { P.status[slot] = CH_DEFERRED; int idx = atomicAdd(P.defer_count, 1); P.defer_slots[idx] = slot; }
+                else { P.status[slot] = rc; P.n_cols[slot] = 0; P.ll[slot] = 0; atomicAdd(P.error_count, 1); }
+            }
             __syncwarp();
             continue;
         }
@@ -212,6 +220,7 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     dg.node_out_off = G.node_out_off; dg.node_out = G.node_out; dg.node_in_off = G.node_in_off; dg.node_in = G.node_in;
     dg.path_off = G.path_off; dg.path_edges = G.path_edges; dg.path_from = G.path_from; dg.path_to = G.path_to;
     dg.jump_fwd_off = G.jump_fwd_off; dg.jump_fwd_path = G.jump_fwd_path; dg.jump_bwd_off = G.jump_bwd_off; dg.jump_bwd_path = G.jump_bwd_path;
+    dg.adj4 = G.adj4; dg.out_adj4 = G.out_adj4; dg.in_adj4 = G.in_adj4; dg.jf4 = G.jf4; dg.jb4 = G.jb4; dg.node_gapflags = G.node_gapflags;
     WdCtx C; C.G = &dg; C.cells = (DpCell*)hb; C.hash = (uint32_t*)(hb + sizeof(DpCell) * (size_t)DP_CELL_CAP); C.gens = C.hash + DP_HASH_CAP;
     for (int t = gw; t < 2 * E.n_pending; t += nw) {
         const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
@@ -223,9 +232,9 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
         DpResult res; res.n_cols = 0; res.n_lvl = 0; res.far_y = 0; int rc = 0; bool run = false;
         C.seq = B.bases + rd0; C.seq_len = rdlen;
         if (side == 0) {
-            if (sb != 0 && l_first > 0) { run = true; C.start_seq = sb; C.start_level = l_first; C.start_z = (int)(G.edge_pack[se_edge[0]] & 255u); C.pos = false; }
+            if (sb != 0 && l_first > 0) { run = true; C.start_seq = sb; C.start_level = l_first; C.start_z = (int)(G.edge_pack[se_edge[0]] & 255u); C.pos = false; C.start_node = G.level_node_off[l_first] + C.start_z; }
         } else {
-            if (se != rdlen - 1 && l_last + 1 < G.n_levels - 1) { run = true; C.start_seq = se + 1; C.start_level = l_last + 1; C.start_z = (int)((G.edge_pack[se_edge[n - 1]] >> 8) & 255u); C.pos = true; }
+            if (se != rdlen - 1 && l_last + 1 < G.n_levels - 1) { run = true; C.start_seq = se + 1; C.start_level = l_last + 1; C.start_z = (int)((G.edge_pack[se_edge[n - 1]] >> 8) & 255u); C.pos = true; C.start_node = G.level_node_off[l_last + 1] + C.start_z; }
         }
         if (run) rc = wd_extend<CFG>(C, S, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res, lane);
         if (lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; }
@@ -238,8 +247,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_finish(ExtParams E) {
     extern __shared__ __align__(16) unsigned char smem[];
     const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t slab = k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap);
-    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.maxcol, P.pool_cap, P.win_cap);
+    const size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
     const int nw = gridDim.x * K1_WARPS;
     for (int pi = blockIdx.x * K1_WARPS + warp; pi < E.n_pending; pi += nw) {
         const int slot = P.pending_slots[pi];
@@ -282,7 +291,7 @@ __global__ void k_export_chain_columns(DevGraph G, int n_chains, int maxcol, con
 cudaError_t upload_score_tables(const ScoreTables& t) { return cudaMemcpyToSymbol(c_tables, &t, sizeof(ScoreTables)); }
 
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream) {
-    size_t slab = k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap);
+    size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
     size_t smem = slab * K1_WARPS;
     static size_t configured = 0;
     if (smem > configured) {
@@ -320,7 +329,7 @@ template <class CFG> static int wd_occupancy(int n_sm) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_warp<CFG>, CFG::WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     return n_sm * per_sm * CFG::WARPS;
 }
-int wd_warps_for(int n_sm) { return std::max(wd_occupancy<WdSmall>(n_sm), wd_occupancy<WdLarge>(n_sm)); }
+int wd_warps_for(int n_sm) { return std::max(wd_occupancy<WdTiny>(n_sm), std::max(wd_occupancy<WdSmall>(n_sm), wd_occupancy<WdLarge>(n_sm))); }
 size_t wd_warp_scratch_bytes() { return wd_hbm_bytes(); }
 
 template <class CFG> static cudaError_t launch_wd(ExtParams E, int n_sm, cudaStream_t stream) {
@@ -332,16 +341,16 @@ template <class CFG> static cudaError_t launch_wd(ExtParams E, int n_sm, cudaStr
     k_extend_warp<CFG><<<grid, CFG::WARPS * 32, wd_slab_bytes<CFG>() * CFG::WARPS, stream>>>(E);
     return cudaGetLastError();
 }
-// large = 0: every task through the small configuration; large = 1: only the tasks the small one deferred, through the large one
-cudaError_t launch_extend_warp(const ExtParams& E0, int n_sm, int large, cudaStream_t stream) {
+// tier 0: every task through the tiny configuration; tier 1 / 2: only the tasks the previous tier deferred, through the small / large one
+cudaError_t launch_extend_warp(const ExtParams& E0, int n_sm, int tier, cudaStream_t stream) {
     if (E0.n_pending <= 0) return cudaSuccess;
-    ExtParams E = E0; E.only_deferred = large;
-    return large ? launch_wd<WdLarge>(E, n_sm, stream) : launch_wd<WdSmall>(E, n_sm, stream);
+    ExtParams E = E0; E.only_deferred = tier > 0;
+    return tier == 0 ? launch_wd<WdTiny>(E, n_sm, stream) : tier == 1 ? launch_wd<WdSmall>(E, n_sm, stream) : launch_wd<WdLarge>(E, n_sm, stream);
 }
 
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
-    size_t smem = k1_slab_bytes(E.C.maxcol, E.C.pool_cap, E.C.win_cap) * K1_WARPS;
+    size_t smem = k1_slab_bytes(E.C.slab_cols, E.C.pool_cap, E.C.win_cap, E.C.wcap) * K1_WARPS;
     static size_t configured = 0;
     if (smem > configured) { cudaError_t e = cudaFuncSetAttribute(k_chain_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; configured = smem; }
     int per_sm = 1; cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_finish, K1_WARPS * 32, smem);

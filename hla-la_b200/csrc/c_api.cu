@@ -126,12 +126,12 @@ int check_batch(const hlala_seed_batch_t* b) {
 }
 
 struct ChainScratch {
-    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count, todo_slots, todo_count;
+    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count;
     void alloc(int32_t n_chains, int32_t wave_chains, int32_t maxcol) {
         size_t nc = (size_t)std::max(n_chains, 1); size_t wc = (size_t)std::max(wave_chains, 1);
         status.alloc(nc * 4); n_cols.alloc(nc * 4); seed_begin.alloc(nc * 4); seed_end.alloc(nc * 4); ll.alloc(nc * 8); first_level.alloc(nc * 4); last_level.alloc(nc * 4);
         c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol); error_count.alloc(4);
-        id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4); todo_slots.alloc(nc * 4); todo_count.alloc(4);
+        id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4); todo_slots.alloc(nc * 4); todo_count.alloc(4); defer_slots.alloc(nc * 4); defer_count.alloc(4);
     }
     void fill(ChainParams& P) {
         P.status = status.as<int32_t>(); P.n_cols = n_cols.as<int32_t>(); P.seed_begin = seed_begin.as<int32_t>(); P.seed_end = seed_end.as<int32_t>(); P.ll = ll.as<double>();
@@ -139,19 +139,26 @@ struct ChainScratch {
         P.error_count = error_count.as<int32_t>(); P.id_first = id_first.as<int32_t>(); P.id_last = id_last.as<int32_t>();
         P.pending_slots = pending_slots.as<int32_t>(); P.pending_count = pending_count.as<int32_t>();
         P.todo_slots = todo_slots.as<int32_t>(); P.todo_count = todo_count.as<int32_t>();
+        P.defer_slots = defer_slots.as<int32_t>(); P.defer_count = defer_count.as<int32_t>();
     }
 };
 
 // Shared-memory slab of one warp of the chain kernels. The backtrack pool holds one entry per (column, node of the column's level):
 // max(4 x max_columns, 2560) entries cover a 150-column read inside a 14-node-wide gene block; a chain that needs more gets
 // HLALA_E_CAPACITY. The staged edge window falls back to L2 reads when the window is larger than its capacity.
-void chain_caps(int32_t maxcol, bool bt16, ChainParams& P) {
-    P.maxcol = maxcol; P.bt16 = bt16 ? 1 : 0;
+void chain_caps(int32_t maxcol, bool bt16, int tier, ChainParams& P) {
+    P.maxcol = maxcol; P.bt16 = bt16 ? 1 : 0; P.tier = tier;
+    if (tier == 0) {   // small slab (~10 KB per warp): covers ~99.9 % of short-read chains at ~20 resident warps per SM
+        P.slab_cols = std::min<int32_t>(maxcol, 256); P.wcap = 64;
+        long long pool_entries = 1024; P.pool_cap = (int32_t)(bt16 ? pool_entries / 2 : pool_entries); P.win_cap = 512;
+        return;
+    }
+    P.slab_cols = maxcol; P.wcap = K1_WCAP;
     long long pool_entries = std::max<long long>(4LL * maxcol, 2560);       // entries needed
     P.pool_cap = (int32_t)(bt16 ? (pool_entries + 1) / 2 : pool_entries);    // in 32-bit words when 16-bit entries are used
     P.win_cap = (int32_t)std::max<long long>(2LL * maxcol, 512);
-    while (k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap) * K1_WARPS > 220000 && P.win_cap > 256) P.win_cap /= 2;
-    while (k1_slab_bytes(P.maxcol, P.pool_cap, P.win_cap) * K1_WARPS > 220000 && P.pool_cap > 512) P.pool_cap /= 2;
+    while (k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap) * K1_WARPS > 220000 && P.win_cap > 256) P.win_cap /= 2;
+    while (k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap) * K1_WARPS > 220000 && P.pool_cap > 512) P.pool_cap /= 2;
 }
 
 // boost::math::pdf(normal) as Boost.Math computes it (processBAM.cpp:2342-2346, 3446-3472)
@@ -244,7 +251,7 @@ struct Pipeline {
         o_n_cols.alloc((size_t)std::max<int64_t>(pb.n_reads, 2) * 4); o_level.alloc(n * 4); o_edge.alloc(n * 4); o_gchar.alloc(n); o_schar.alloc(n); o_fromseed.alloc(n); o_mapq.alloc(n);
         have_columns = true;
     }
-    ChainParams chain_params() { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, P); P.do_extension = 1; cs.fill(P); return P; }
+    ChainParams chain_params(int tier) { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, tier, P); P.do_extension = 1; cs.fill(P); return P; }
 
     void begin_run(cudaStream_t st) {
         launches = 0;
@@ -254,11 +261,16 @@ struct Pipeline {
     }
     // chain stage for the slots of one wave
     ChainParams run_chains_wave(size_t w, cudaStream_t st) {
-        ChainParams P = chain_params();
-        P.slot_base = db_chain_off(2 * wave_pair[w]); P.slot_end = db_chain_off(2 * wave_pair[w + 1]);
-        P.read_begin = (int32_t)(2 * wave_pair[w]); P.read_end = (int32_t)(2 * wave_pair[w + 1]); P.dedup = dedup ? 1 : 0;
-        CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.todo_count.p, 0, 4, st));
-        if (P.slot_end > P.slot_base) { CUDA_OK(launch_prepare(P, st)); tic(0, st); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches += 2; }
+        ChainParams P0 = chain_params(0), P = chain_params(1);
+        for (ChainParams* q : {&P0, &P}) {
+            q->slot_base = db_chain_off(2 * wave_pair[w]); q->slot_end = db_chain_off(2 * wave_pair[w + 1]);
+            q->read_begin = (int32_t)(2 * wave_pair[w]); q->read_end = (int32_t)(2 * wave_pair[w + 1]); q->dedup = dedup ? 1 : 0;
+        }
+        CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.todo_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.defer_count.p, 0, 4, st));
+        if (P.slot_end > P.slot_base) {
+            CUDA_OK(launch_prepare(P0, st));
+            tic(0, st); CUDA_OK(launch_chain_seed(P0, g->n_sm, st)); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches += 3;
+        }
         CUDA_OK(cudaMemcpyAsync(&n_pending, cs.pending_count.p, 4, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         if (n_pending > 0) {
@@ -273,8 +285,8 @@ struct Pipeline {
             if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
             else {
                 CUDA_OK(launch_extend_warp(E, g->n_sm, 0, st)); toc(st);
-                tic(4, st); CUDA_OK(launch_extend_warp(E, g->n_sm, 1, st)); toc(st);
-                tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 3;
+                tic(4, st); CUDA_OK(launch_extend_warp(E, g->n_sm, 1, st)); CUDA_OK(launch_extend_warp(E, g->n_sm, 2, st)); toc(st);
+                tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4;
             }
             toc(st);
             tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 1;
@@ -387,6 +399,19 @@ int hlala_graph_to_gpu(hlala_graph_t* g, int device) {
         d.node_out_off = g->up(h.node_out_off); d.node_out = g->up(h.node_out); d.node_in_off = g->up(h.node_in_off); d.node_in = g->up(h.node_in);
         d.path_off = g->up(h.path_off); d.path_edges = g->up(h.path_edges); d.path_from = g->up(h.path_from); d.path_to = g->up(h.path_to);
         d.jump_fwd_off = g->up(h.jump_fwd_off); d.jump_fwd_path = g->up(h.jump_fwd_path); d.jump_bwd_off = g->up(h.jump_bwd_off); d.jump_bwd_path = g->up(h.jump_bwd_path);
+        {
+            std::vector<I4> adj((size_t)h.n_nodes + 1), oa((size_t)h.n_edges), ia((size_t)h.n_edges), jf((size_t)h.n_paths), jb((size_t)h.n_paths);
+            for (int32_t n = 0; n <= h.n_nodes; n++) adj[n] = I4{h.node_out_off[n], h.node_in_off[n], h.jump_fwd_off[n], h.jump_bwd_off[n]};
+            for (int32_t k = 0; k < h.n_edges; k++) { int32_t e = h.node_out[k]; oa[k] = I4{e, h.edge_to[e], (int32_t)pack[e], 0}; int32_t e2 = h.node_in[k]; ia[k] = I4{e2, h.edge_from[e2], (int32_t)pack[e2], 0}; }
+            for (int32_t k = 0; k < h.n_paths; k++) {
+                int32_t p = h.jump_fwd_path[k], t = h.path_to[p]; jf[k] = I4{p, t, t - h.level_node_off[h.node_level[t]], h.path_off[p + 1] - h.path_off[p]};
+                int32_t q = h.jump_bwd_path[k], f = h.path_from[q]; jb[k] = I4{q, f, f - h.level_node_off[h.node_level[f]], h.path_off[q + 1] - h.path_off[q]};
+            }
+            std::vector<uint8_t> gf((size_t)h.n_nodes, 0);
+            for (int32_t e = 0; e < h.n_edges; e++) if (h.edge_emis[e] == '_') { gf[h.edge_from[e]] |= 1; gf[h.edge_to[e]] |= 2; }
+            d.node_gapflags = g->up(gf);
+            d.adj4 = g->up(adj); d.out_adj4 = g->up(oa); d.in_adj4 = g->up(ia); d.jf4 = g->up(jf); d.jb4 = g->up(jb);
+        }
         d.gap_stretch = g->up(h.gap_stretch); d.contig_off = g->up(h.contig_off); d.contig_seq = g->up(h.contig_seq); d.contig_level = g->up(h.contig_level);
         d.contig_prg_id = g->up(h.contig_prg_id); d.anchor_off = g->up(h.anchor_off); d.anchor_prg_id = g->up(h.anchor_prg_id); d.anchor_pos = g->up(h.anchor_pos);
         ScoreTables t = make_score_tables();

@@ -26,15 +26,15 @@ struct WarpSlab {
     uint32_t* bt; uint32_t* win; uint16_t* weoff; uint16_t* wwid; uint16_t* coloff; uint32_t* cur; uint32_t* nxt;
 };
 
-__device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_cap, int win_cap) {
+__device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_cap, int win_cap, int wcap) {
     WarpSlab s; unsigned char* p = base;
     s.lvlA = (int32_t*)p; p += (size_t)maxcol * 4;
     s.lvlB = (int32_t*)p; p += (size_t)maxcol * 4;
     s.bt = (uint32_t*)p; p += (size_t)pool_cap * 4;
     s.win = (uint32_t*)p; p += (size_t)win_cap * 4;
     s.weoff = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2; s.wwid = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2;
-    s.cur = (uint32_t*)p; p += (size_t)K1_WCAP * 4;
-    s.nxt = (uint32_t*)p; p += (size_t)K1_WCAP * 4;
+    s.cur = (uint32_t*)p; p += (size_t)wcap * 4;
+    s.nxt = (uint32_t*)p; p += (size_t)wcap * 4;
     s.coloff = (uint16_t*)p; p += (size_t)((maxcol + 1) / 2 * 2) * 2;
     s.gA = p; p += maxcol; s.sA = p; p += maxcol; s.gB = p; p += maxcol; s.sB = p; p += maxcol;
     return s;
@@ -68,7 +68,7 @@ __device__ int expand_cigar(const ChainParams& P, int c, int64_t rd0, int rdlen,
             bool isD = (op == 2);
             if (gpos < 0 || gpos + len > clen) return HLALA_E_INVARIANT_DEV;
             if (!isD && ridx + len > rdlen) return HLALA_E_INVARIANT_DEV;
-            if (ncol + len > P.maxcol) return HLALA_E_CAPACITY_DEV;
+            if (ncol + len > P.slab_cols) return HLALA_E_CAPACITY_DEV;
             for (int i = lane; i < len; i += 32) {
                 o.lvl[ncol + i] = G.contig_level[cbase + gpos + i];
                 o.g[ncol + i] = G.contig_seq[cbase + gpos + i];
@@ -79,7 +79,7 @@ __device__ int expand_cigar(const ChainParams& P, int c, int64_t rd0, int rdlen,
             stop_raw = ridx - 1;
         } else if (op == 1) {                                       // I: read bases against a graph gap, level -1
             if (ridx + len > rdlen) return HLALA_E_INVARIANT_DEV;
-            if (ncol + len > P.maxcol) return HLALA_E_CAPACITY_DEV;
+            if (ncol + len > P.slab_cols) return HLALA_E_CAPACITY_DEV;
             for (int i = lane; i < len; i += 32) { o.lvl[ncol + i] = -1; o.g[ncol + i] = '_'; o.s[ncol + i] = B.bases[rd0 + ridx + i]; }
             if (start_raw < 0) start_raw = ridx;
             ncol += len; ridx += len; stop_raw = ridx - 1;
@@ -119,7 +119,7 @@ __device__ int trim_and_fill(const ChainParams& P, ColBuf in, int n, ColBuf out,
         int incl = warp_incl_scan(width, lane);
         int dst_end = carry_out + incl;                             // one past this column's own slot
         int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (carry_out + total > P.maxcol) return HLALA_E_CAPACITY_DEV;
+        if (carry_out + total > P.slab_cols) return HLALA_E_CAPACITY_DEV;
         if (in_range) {
             int own = dst_end - 1;
             for (int k = 0; k < fill; k++) { int d = own - fill + k; out.lvl[d] = prev_excl + 1 + k; out.g[d] = '_'; out.s[d] = '_'; }
@@ -228,13 +228,14 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     if (c.lvl[0] == -1 || c.lvl[n - 1] == -1) return HLALA_E_INVARIANT_DEV;
     const int l_first = c.lvl[0], l_last = c.lvl[n - 1];
     const int nlev = l_last - l_first + 1;
-    if (l_last + 1 >= G.n_levels || nlev > P.maxcol) return HLALA_E_INVARIANT_DEV;
+    if (l_last + 1 >= G.n_levels) return HLALA_E_INVARIANT_DEV;
+    if (nlev > P.slab_cols) return HLALA_E_CAPACITY_DEV;
     // stage the window: per level the edge offset (relative) and the node count, then the packed edges in between
     const int e_base = G.level_edge_off[l_first];
     int bad = 0;
     for (int i = lane; i <= nlev + 1; i += 32) {
         if (i <= nlev) { int rel = G.level_edge_off[l_first + i] - e_base; if (rel > 65535) bad = 1; S.weoff[i] = (uint16_t)rel; }
-        int w = G.level_node_off[l_first + i + 1] - G.level_node_off[l_first + i]; if (w > K1_WCAP) bad = 1; S.wwid[i] = (uint16_t)w;
+        int w = G.level_node_off[l_first + i + 1] - G.level_node_off[l_first + i]; if (w > P.wcap) bad = 1; S.wwid[i] = (uint16_t)w;
     }
     if (__any_sync(0xffffffffu, bad)) return HLALA_E_CAPACITY_DEV;
     __syncwarp();
@@ -257,9 +258,29 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
         const int wn = S.wwid[li + 1];
         if (BT16 && (e1 - e0) > 255) { status = HLALA_E_CAPACITY_DEV; break; }
         if (pool + wn > pool_cap || pool > 65535) { status = HLALA_E_CAPACITY_DEV; break; }
+        const uint8_t sc = c.s[col], gc = c.g[col]; const bool isMatch = (sc == gc);
+        if (wn == 1 && S.wwid[li] == 1 && (e1 - e0) <= 32) {
+            // one node on either side (the common case outside variant sites): the step is a single warp reduction
+            uint32_t key = 0; uint32_t pk = 0; const int e = e0 + lane;
+            if (e < e1) {
+                pk = staged ? S.win[e] : G.edge_pack[e_base + e];
+                const uint32_t kf = cur[0]; const uint8_t em = (uint8_t)(pk >> 16);
+                if (kf != 0 && !(isMatch && em != sc)) key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
+            }
+            const uint32_t best = __reduce_max_sync(0xffffffffu, key);
+            if (lane == 0) {
+                nxt[0] = best;
+                const uint32_t rank = KEY_RANK_MASK - (best & KEY_RANK_MASK);
+                if (BT16) bt16[pool] = (uint16_t)rank; else S.bt[pool] = rank;       // from node is node 0
+                S.coloff[col] = (uint16_t)pool;
+            }
+            pool += 1; lev++;
+            uint32_t* t = cur; cur = nxt; nxt = t;
+            __syncwarp();
+            continue;
+        }
         for (int z = lane; z < wn; z += 32) nxt[z] = 0;
         __syncwarp();
-        const uint8_t sc = c.s[col], gc = c.g[col]; const bool isMatch = (sc == gc);
         for (int e = e0 + lane; e < e1; e += 32) {
             uint32_t pk = staged ? S.win[e] : G.edge_pack[e_base + e];
             uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);

@@ -16,7 +16,10 @@ constexpr uint32_t KEY_RANK_MASK = 0xFFFFFu;   // 20 bits of edge rank inside a 
 
 struct ChainParams {
     DevGraph g; DevBatch b;
-    int32_t maxcol;        // capacity of a column slab (and of the output stride)
+    int32_t maxcol;        // stride of the per-chain column records in HBM (= the caller's max_columns)
+    int32_t slab_cols;     // column capacity of the shared-memory slab of this launch (tier 0: small slab, high occupancy; tier 1: maxcol)
+    int32_t wcap;          // node-per-level capacity of the slab's Viterbi state
+    int32_t tier;          // 0: chains from todo_slots, capacity overflow defers the chain; 1: chains from defer_slots
     int32_t pool_cap;      // backtrack pool entries per warp
     int32_t win_cap;       // staged edge window entries per warp
     int32_t bt16;          // 1: backtrack entries are 16 bit (graph has <= 255 edges per level and <= 256 nodes per level)
@@ -32,11 +35,13 @@ struct ChainParams {
     int32_t* id_first; int32_t* id_last;   // PRG levels of the BAM record's first/last reference base (processBAM.cpp:3840): de-dup key
     int32_t* pending_slots; int32_t* pending_count;   // chains whose seed needs the extension DP
     int32_t* todo_slots; int32_t* todo_count;         // chains the chain kernel has to align (written by k_prepare)
+    int32_t* defer_slots; int32_t* defer_count;       // chains that did not fit the tier-0 slab
     int32_t read_begin, read_end;                     // reads of this wave
     int32_t dedup;                                    // 1: chains that the pair stage would discard as duplicates are not aligned at all
 };
 
 constexpr int32_t CH_TODO = -100;
+constexpr int32_t CH_DEFERRED = -101;   // transient: did not fit the small slab, handled by the tier-1 launch
 constexpr int32_t CH_DUPLICATE = 3;   // same PRG start/stop as an earlier (better or equal AS) chain of the read (processBAM.cpp:3234)
 
 constexpr int32_t CH_PENDING_EXT = 2;
@@ -83,7 +88,7 @@ __host__ __device__ inline size_t k3_slab_bytes(int maxcol) {
     return (b + 15) & ~size_t(15);
 }
 
-__host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int win_cap) {
+__host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int win_cap, int wcap) {
     size_t b = 0;
     b += (size_t)maxcol * 4 * 2;          // lvlA, lvlB
     b += (size_t)maxcol * 4;              // gA,sA,gB,sB
@@ -91,7 +96,7 @@ __host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int wi
     b += (size_t)win_cap * 4;             // win
     b += (size_t)(maxcol + 4) * 2 * 2;    // weoff, wwid (u16)
     b += (size_t)((maxcol + 1) / 2 * 2) * 2;   // coloff (u16)
-    b += (size_t)K1_WCAP * 4 * 2;         // cur, nxt
+    b += (size_t)wcap * 4 * 2;            // cur, nxt
     return (b + 15) & ~size_t(15);
 }
 

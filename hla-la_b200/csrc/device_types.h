@@ -4,6 +4,8 @@
 
 namespace hlala {
 
+struct alignas(16) I4 { int32_t x, y, z, w; };
+
 struct DevGraph {
     int32_t n_levels, n_nodes, n_edges, n_contigs;
     const int32_t* level_node_off;   // [n_levels+1]
@@ -15,6 +17,13 @@ struct DevGraph {
     const int32_t* path_off; const int32_t* path_edges; const int32_t* path_from; const int32_t* path_to;
     const int32_t* jump_fwd_off; const int32_t* jump_fwd_path;
     const int32_t* jump_bwd_off; const int32_t* jump_bwd_path;
+    // adjacency packed for the extension DP: one 16-byte record per node / edge / jump, so that a DP step costs one load each
+    const I4* adj4;        // [n_nodes+1] {node_out_off, node_in_off, jump_fwd_off, jump_bwd_off}
+    const I4* out_adj4;    // [n_edges] in node_out order: {flat edge, target node, edge_pack, 0}
+    const I4* in_adj4;     // [n_edges] in node_in order:  {flat edge, source node, edge_pack, 0}
+    const I4* jf4;         // [n_paths] in jump_fwd_path order: {path, target node, target z, path length}
+    const I4* jb4;         // [n_paths] in jump_bwd_path order: {path, source node, source z, path length}
+    const uint8_t* node_gapflags;   // [n_nodes] bit 0: has an outgoing '_' edge, bit 1: has an incoming '_' edge
     const uint8_t* gap_stretch;      // [n_levels-1]
     const int64_t* contig_off;       // [n_contigs+1]
     const uint8_t* contig_seq;

@@ -72,6 +72,7 @@ struct DpGraph {
     const int32_t* node_out_off; const int32_t* node_out; const int32_t* node_in_off; const int32_t* node_in;
     const int32_t* path_off; const int32_t* path_edges; const int32_t* path_from; const int32_t* path_to;
     const int32_t* jump_fwd_off; const int32_t* jump_fwd_path; const int32_t* jump_bwd_off; const int32_t* jump_bwd_path;
+    const void* adj4; const void* out_adj4; const void* in_adj4; const void* jf4; const void* jb4; const uint8_t* node_gapflags;   // packed adjacency (device only)
 };
 
 struct DpResult { int32_t n_cols; int32_t n_lvl; int32_t far_y; };   // far_y: read coordinate of the end cell

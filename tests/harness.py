@@ -126,6 +126,72 @@ class Ref:
         return o
 
 
+class Oracle(Ref):
+    """oracle/build/libhlala_oracle.so: the plain C++ restatement (oracle/hlala_oracle.cpp). Same interface as Ref."""
+
+    def __init__(self, prg_dir):
+        self.lib = C.CDLL(LIB_ORACLE)
+        L = self.lib
+        # expose the oracle's entry points under the names Ref's methods call
+        for name in ("open", "last_error", "n_levels", "n_nodes", "n_edges", "graph_export", "gap_paths_total", "gap_paths_export", "gap_stretch", "chains", "pairs"):
+            setattr(L, "hlala_ref_" + name, getattr(L, "hlala_oracle_" + name))
+        L.hlala_ref_open.restype = C.c_void_p
+        L.hlala_ref_last_error.restype = C.c_char_p
+        for fn in ("hlala_ref_n_levels", "hlala_ref_n_nodes", "hlala_ref_n_edges", "hlala_ref_gap_paths_total"):
+            getattr(L, fn).restype = C.c_longlong
+        self.h = C.c_void_p(L.hlala_ref_open(prg_dir.encode()))
+        if not self.h:
+            raise RuntimeError(L.hlala_ref_last_error().decode())
+
+    def graph(self):
+        nl = self.lib.hlala_ref_n_levels(self.h); nn = self.lib.hlala_ref_n_nodes(self.h); ne = self.lib.hlala_ref_n_edges(self.h)
+        node_level = np.zeros(nn, np.int32); ef = np.zeros(ne, np.int32); et = np.zeros(ne, np.int32); em = np.zeros(ne, np.uint8)
+        self._chk(self.lib.hlala_ref_graph_export(self.h, p(node_level), p(ef), p(et), p(em)))
+        npaths = C.c_longlong(0)
+        tot = self.lib.hlala_ref_gap_paths_total(self.h, C.byref(npaths))
+        path_off = np.zeros(npaths.value + 1, np.int64); path_edges = np.zeros(max(tot, 1), np.int32)
+        self._chk(self.lib.hlala_ref_gap_paths_export(self.h, p(path_off), p(path_edges)))
+        gs = np.zeros(nl, np.uint8); ngs = self.lib.hlala_ref_gap_stretch(self.h, p(gs))
+        return dict(n_levels=nl, node_level=node_level, edge_from=ef, edge_to=et, edge_emis=em, path_off=path_off, path_edges=path_edges[:tot], gap_stretch=gs[:ngs])
+
+
+_REF_CACHE = {}
+
+
+def have_ref():
+    return os.path.exists(LIB_REF)
+
+
+def checker(prg_dir):
+    """The strongest oracle available on this box: the compiled reference if oracle/_ref was built, else the restatement.
+    (One compiled-reference graph per process: its load-time arena is not recycled.)"""
+    if have_ref():
+        if prg_dir not in _REF_CACHE:
+            if _REF_CACHE:
+                return Oracle(prg_dir), "restatement (oracle/hlala_oracle.cpp)"
+            _REF_CACHE[prg_dir] = quiet(Ref, prg_dir)
+        return _REF_CACHE[prg_dir], "compiled reference (oracle/_ref)"
+    return Oracle(prg_dir), "restatement (oracle/hlala_oracle.cpp)"
+
+
+def oracle_pairs(prg_dir, b, is_mean, is_sd, cap=1024):
+    o, kind = checker(prg_dir)
+    r = quiet(o.pairs, b, is_mean, is_sd, cap)
+    r["oracle"] = kind
+    return r
+
+
+def quiet(fn, *a, **k):
+    """Run fn with stdout/stderr of the process silenced (the reference prints progress lines)."""
+    import sys
+    devnull = os.open(os.devnull, os.O_WRONLY); so, se = os.dup(1), os.dup(2)
+    sys.stdout.flush(); sys.stderr.flush(); os.dup2(devnull, 1); os.dup2(devnull, 2)
+    try:
+        return fn(*a, **k)
+    finally:
+        os.dup2(so, 1); os.dup2(se, 2); os.close(devnull); os.close(so); os.close(se)
+
+
 class SeedBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int64)] + [(k, C.c_void_p) for k in BATCH_KEYS]
 

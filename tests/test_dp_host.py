@@ -1,0 +1,40 @@
+"""The extension DP the GPU executes (hla-la_b200/csrc/extend_dp.h, compiled for the host by tests/native/dp_host.cpp) against the
+oracle's independent restatement, on every chain of the datasets that needs an extension."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+LIB = os.path.join(H.REPO, "tests", "native", "build", "libdp_host.so")
+
+
+@pytest.mark.parametrize("name", ["S", "genes"])
+def test_extension_dp_matches_oracle(dataset, name):
+    d, b, mu, sd = dataset(name)
+    oc = H.Oracle(d).chains(b, 1024)
+    lib = C.CDLL(LIB); lib.dp_host_open.restype = C.c_void_p
+    h = C.c_void_p(lib.dp_host_open(d.encode())); assert h
+    slot_read = np.repeat(np.arange(len(b["chain_off"]) - 1), np.diff(b["chain_off"]))
+    tested = 0
+    for i in np.nonzero(oc["status"] == 0)[0]:
+        r = slot_read[i]; seq = b["bases"][b["read_off"][r]:b["read_off"][r + 1]].copy(); L = len(seq)
+        sb, se = oc["seed_begin"][i], oc["seed_end"][i]
+        if sb == 0 and se == L - 1:
+            continue
+        n = oc["n_cols"][i]; idx = np.nonzero(oc["from_seed"][i, :n])[0]; s0, s1 = idx[0], idx[-1]
+        parts = []
+        for pos, need, start_seq, eord in ((0, sb != 0, sb, oc["edge"][i, s0]), (1, se != L - 1, se + 1, oc["edge"][i, s1])):
+            oe = np.zeros(512, np.int32); os_ = np.zeros(512, np.uint8); nc = C.c_int32(); fy = C.c_int32(); app = C.c_int32()
+            if need:
+                assert lib.dp_host_extend(h, H.p(seq), len(seq), int(start_seq), int(eord), pos, H.p(oe), H.p(os_), C.byref(nc), C.byref(fy), C.byref(app)) == 0
+            parts.append((oe[:nc.value].copy(), os_[:nc.value].copy(), fy.value if need else start_seq))
+        (le, ls, lfar), (re_, rs, rfar) = parts
+        padL = lfar if sb != 0 else 0; padR = (L - rfar) if se != L - 1 else 0
+        edge = np.concatenate([np.full(padL, -1, np.int32), le, oc["edge"][i, s0:s1 + 1], re_, np.full(padR, -1, np.int32)])
+        sch = np.concatenate([seq[:padL], ls, oc["schar"][i, s0:s1 + 1], rs, seq[L - padR:] if padR else np.zeros(0, np.uint8)])
+        assert len(edge) == n and np.array_equal(edge, oc["edge"][i, :n]) and np.array_equal(sch, oc["schar"][i, :n]), "slot %d" % i
+        tested += 1
+    assert tested > 50

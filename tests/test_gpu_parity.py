@@ -1,0 +1,125 @@
+"""Parity tests proper: the CUDA path, through the C ABI, against the oracle (the compiled reference when oracle/_ref is present,
+else the restatement) on seeded inputs; golden fixtures; size-independent properties at larger sizes. Integer/byte/index outputs
+are compared bit-exactly; log-likelihoods are compared bit-exactly too (north_star tolerance: 1e-6); mapping qualities within 1e-12."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+_products = {}
+
+
+def product(d):
+    if d not in _products:
+        P = H.Product(d); P.to_gpu(0); _products[d] = P
+    return _products[d]
+
+
+def assert_pairs_equal(got, want):
+    n = want["n_cols"]
+    assert np.array_equal(got["n_cols"], n)
+    for r in range(len(n)):
+        for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+            assert np.array_equal(got[k][r, :n[r]], want[k][r, :n[r]]), "read %d: %s" % (r, k)
+    assert np.array_equal(got["read_reverse"], want["read_reverse"])
+    assert np.allclose(got["pair_mapq"], want["pair_mapq"], rtol=0, atol=1e-12) and np.allclose(got["read_mapq"], want["read_mapq"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["S", "genes"])
+def test_chains_match_oracle(dataset, name):
+    d, b, mu, sd = dataset(name)
+    o, kind = H.checker(d)
+    want = H.quiet(o.chains, b, 1024); got = product(d).chains(b, 1024)
+    for k in ("chain_order", "status", "n_cols", "seed_begin", "seed_end"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(got["ll"], want["ll"]), "log-likelihoods differ (tolerance 1e-6 allowed by north_star; we require 0)"
+    n = want["n_cols"]
+    for i in range(len(n)):
+        for k in ("level", "edge", "gchar", "schar", "from_seed"):
+            assert np.array_equal(got[k][i, :n[i]], want[k][i, :n[i]]), "slot %d: %s" % (i, k)
+
+
+@pytest.mark.parametrize("name", ["S", "genes"])
+def test_pairs_match_oracle(dataset, name):
+    d, b, mu, sd = dataset(name)
+    want = H.oracle_pairs(d, b, mu, sd, 1024); got = product(d).pairs(b, mu, sd, 1024)
+    assert_pairs_equal(got, want)
+    # per-level coverage (processBAM.cpp:2411-2426) recomputed from the oracle's alignments
+    cov = np.zeros_like(got["bases_per_level"])
+    for r in range(len(want["n_cols"])):
+        n = want["n_cols"][r]; lv = want["level"][r, :n]; g = want["gchar"][r, :n]; m = (lv != -1) & (g != ord("_"))
+        np.add.at(cov, lv[m], 1)
+    assert np.array_equal(cov, got["bases_per_level"])
+
+
+def test_golden_fixture(dataset):
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "alignment_small.npz"))
+    d, b, mu, sd = dataset("small")
+    got = product(d).pairs(b, mu, sd, 512)
+    pack = lambda cols, n: np.concatenate([cols[r, :n[r]] for r in range(len(n))])
+    assert np.array_equal(got["n_cols"], gold["n_cols"])
+    for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+        assert np.array_equal(pack(got[k], got["n_cols"]), gold[k]), k
+    assert np.allclose(got["pair_mapq"], gold["pair_mapq"], rtol=0, atol=1e-12)
+    ch = product(d).chains(b, 512)
+    assert np.array_equal(ch["ll"], gold["chain_ll"]) and np.array_equal(pack(ch["edge"], ch["n_cols"]), gold["chain_edge"])
+
+
+def test_waves_and_scalar_dp_give_identical_results(dataset, monkeypatch):
+    d, b, mu, sd = dataset("S")
+    base = product(d).pairs(b, mu, sd, 1024)
+    monkeypatch.setenv("HLALA_WAVE_BYTES", "2000000")      # many waves
+    waves = product(d).pairs(b, mu, sd, 1024)
+    monkeypatch.delenv("HLALA_WAVE_BYTES")
+    monkeypatch.setenv("HLALA_SCALAR_DP", "1")             # every extension through the scalar DP kernel
+    scalar = product(d).pairs(b, mu, sd, 1024)
+    for other in (waves, scalar):
+        for k in base:
+            if base[k] is not None:
+                assert np.array_equal(base[k], other[k]), k
+
+
+def test_capacity_error_is_reported(dataset):
+    d, b, mu, sd = dataset("small")
+    with pytest.raises(RuntimeError, match="capacity"):
+        product(d).pairs(b, mu, sd, 64)         # 100-base reads cannot fit 64 columns
+
+
+def test_session_digest_idempotence_and_shard_additivity(dataset, tmp_path):
+    """Size-independent properties on a batch too large for the oracle to be worth running."""
+    import sys
+    sys.path.insert(0, H.PKG)
+    import hlala_dist
+    d, _, mu, sd = dataset("S")
+    b = H.synth_reads(d, str(tmp_path / "big.bin"), pairs=20000, len=100, clip_frac=0.15, seed=99)
+    P = product(d)
+    full = P.pairs(b, mu, sd, 512)
+    again = P.pairs(b, mu, sd, 512)
+    for k in full:
+        if full[k] is not None:
+            assert np.array_equal(full[k], again[k]), "run-to-run difference in " + k
+    halves = [P.pairs(hlala_dist.shard_batch(b, r, 2), mu, sd, 512) for r in range(2)]
+    assert np.array_equal(full["bases_per_level"], halves[0]["bases_per_level"] + halves[1]["bases_per_level"])
+    assert np.array_equal(full["pair_mapq"], np.concatenate([h["pair_mapq"] for h in halves]))
+    assert np.array_equal(full["n_cols"], np.concatenate([h["n_cols"] for h in halves]))
+    assert (full["n_cols"] >= 100).all() and ((full["pair_mapq"] >= 0) & (full["pair_mapq"] <= 1)).all()
+    # every read base appears exactly once in its alignment
+    nb = np.array([(full["schar"][r, :full["n_cols"][r]] != ord("_")).sum() for r in range(0, len(full["n_cols"]), 97)])
+    assert (nb == 100).all()
+    # session API digest agrees with the fetched results
+    L = P.lib
+    sb = H.make_batch_struct(b); sess = C.c_void_p()
+    P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(512), C.byref(sess)))
+    P._chk(L.hlala_session_run(sess, C.c_double(mu), C.c_double(sd), C.c_uint64(0), None))
+    dig = (C.c_int64 * 4)(); sll = C.c_double(0)
+    P._chk(L.hlala_session_digest(sess, dig, C.byref(sll)))
+    assert dig[0] == int(full["n_cols"].sum()) and dig[2] == int((full["pair_mapq"] < 1).sum()) and dig[3] == 0
+    edges = sum(int((full["edge"][r, :full["n_cols"][r]].astype(np.int64) + 1).sum()) for r in range(len(full["n_cols"])))
+    assert dig[1] == edges
+    assert abs(sll.value - full["pair_ll"].sum()) < 1e-6 * abs(sll.value)
+    L.hlala_session_free(sess)
