@@ -311,6 +311,26 @@ int cmd_prg(const std::map<std::string, std::string>& a) {
             }
         }
     }
+    // --- G-group nomenclature table in the IMGT hla_nom_g.txt format (parsed at HLATyper.cpp:4150-4198): "locus*;a/b/c;group" or "locus*;a;"
+    {
+        std::ofstream gf(out + "/hla_nom_g.txt");
+        gf << "# synthetic G groups\n";
+        std::set<std::string> done;
+        for (const Gene& G : genes) {
+            if (G.locus == "K" || G.locus == "V") continue;          // loci without G groups exercise can_translateToG_locus() == false
+            if (!done.insert(G.locus).second) continue;
+            for (size_t ai = 0; ai < G.allele_names.size();) {
+                size_t n = 1 + (ai * 7 + 3) % 4; if (ai + n > G.allele_names.size()) n = G.allele_names.size() - ai;
+                std::vector<std::string> f; for (size_t k = 0; k < n; k++) f.push_back(G.allele_names[ai + k].substr(G.locus.size() + 1));
+                if (ai % 11 == 5) { ai += n; continue; }             // some alleles are unknown to the table ("Can't G-translate")
+                gf << G.locus << "*;";
+                for (size_t k = 0; k < n; k++) gf << (k ? "/" : "") << f[k];
+                gf << ";"; if (n > 1) gf << f[0] << "G";
+                gf << "\n";
+                ai += n;
+            }
+        }
+    }
     // The Perl driver only checks that serializedGRAPH exists (HLA-LA.pl:254); our cache lives elsewhere.
     return 0;
 }

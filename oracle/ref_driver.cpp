@@ -10,6 +10,7 @@
 //   per chain             alignment2Chain + extendSeedChain + scoreOneAlignment
 //                                                                   mapper/processBAM.cpp:3019, extensionAligner.cpp:186,52
 //   per pair              processBAM::alignOneReadPair             mapper/processBAM.cpp:3129
+//   typing                gene filter (processBAM.cpp:2427-2481) + HLATyper::HLATypeInference (hla/HLATyper.cpp:933)
 //
 // Two things are pinned so that "bit-exact" is defined at all (SURVEY.md §0 finding 3, §7 hard parts):
 //  * std::set<Node*>/std::set<Edge*> iterate in pointer order. While the graph is being built every
@@ -29,7 +30,10 @@
 #include <chrono>
 #include <omp.h>
 
+#include <unistd.h>
+
 #include "mapper/processBAM.h"
+#include "hla/HLATyper.h"
 #include "Graph/Graph.h"
 #include "Utilities.h"
 
@@ -181,6 +185,49 @@ public:
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return 0;
     }
+
+    // processBAM.cpp:2410-2481 (serial loop, gene filter, raw read construction) followed by the one HLATypeInference call at :1920.
+    // HLATypeInference reads hla_nom_g.txt from the current directory, so the call runs with cwd = g_dir.
+    hla::HLATyper* typer = nullptr;
+    int run_type(const Batch& b, const std::string& prg_dir, double is_mean, double is_sd, const std::string& out_dir, const std::string& g_dir, int threads, long long* n_used, double* seconds) {
+        if (!typer) typer = new hla::HLATyper(g, prg_dir, "");
+        boost::math::normal nd(is_mean, is_sd);
+        double pen = log(boost::math::pdf(nd, is_mean + 8 * is_sd));
+        omp_set_num_threads(1); eA->init_for_threads(1);
+        std::vector<mapper::reads::oneReadPair> raw; std::vector<mapper::reads::verboseSeedChainPair> aligned;
+        for (int64_t p = 0; p < b.n_reads / 2; p++) {
+            mapper::reads::protoSeeds ps; std::vector<int32_t> o1, o2;
+            std::string name = "r" + std::to_string(p);
+            build_read(b, 2 * p, name, ps.read1_alignments, o1);
+            build_read(b, 2 * p + 1, name, ps.read2_alignments, o2);
+            mapper::reads::verboseSeedChainPair alignment = alignOneReadPair(ps, nd, pen, nullptr, nullptr);
+            bool include = false;
+            std::pair<int, int> l1 = std::make_pair(alignment.chains.first.alignment_firstLevel(), alignment.chains.first.alignment_lastLevel());
+            std::pair<int, int> l2 = std::make_pair(alignment.chains.second.alignment_firstLevel(), alignment.chains.second.alignment_lastLevel());
+            if (l1.first != -1) include = include || typer->intervalOverlapsWithGenes(l1.first, l1.second);
+            if (l2.first != -1) include = include || typer->intervalOverlapsWithGenes(l2.first, l2.second);
+            if (!include) continue;
+            size_t p1 = ps.read1_getPrimaryAlignmentI(), p2 = ps.read2_getPrimaryAlignmentI();
+            const BamTools::BamAlignment& A1 = std::get<2>(ps.read1_alignments.at(p1)); const BamTools::BamAlignment& A2 = std::get<2>(ps.read2_alignments.at(p2));
+            mapper::reads::oneRead r1(A1.Name, A1.QueryBases, A1.Qualities), r2(A2.Name, A2.QueryBases, A2.Qualities);
+            if (A1.IsReverseStrand()) r1.invert();
+            if (A2.IsReverseStrand()) r2.invert();
+            raw.push_back(mapper::reads::oneReadPair(r1, r2, 0)); aligned.push_back(alignment);
+        }
+        if (n_used) *n_used = (long long)raw.size();
+        char cwd[4096]; if (!getcwd(cwd, sizeof cwd)) return -3;
+        if (chdir(g_dir.c_str()) != 0) return -4;
+        int rc = 0;
+        auto t0 = std::chrono::steady_clock::now();
+        try {
+            omp_set_num_threads(threads < 1 ? 1 : threads);   // processBAM.cpp:1919 (threads_for_HLAtyping)
+            typer->HLATypeInference(raw, aligned, std::vector<mapper::reads::oneRead>(), std::vector<mapper::reads::verboseSeedChain>(), is_mean, is_sd, out_dir, "");
+        } catch (...) { omp_set_num_threads(1); if (chdir(cwd) != 0) {} throw; }
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        omp_set_num_threads(1);
+        if (chdir(cwd) != 0) rc = -5;
+        return rc;
+    }
 };
 
 std::string g_err;
@@ -277,6 +324,17 @@ int hlala_ref_pairs(void* h, long long n_reads, const int64_t* read_off, const u
     Driver* d = (Driver*)h;
     Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
     return guarded([&]() { return d->run_pairs(b, is_mean, is_sd, cap, threads, pair_mapq, read_mapq, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
+}
+
+// Gene filter + HLATyper::HLATypeInference on the pairs of the batch; writes the reference's files into out_dir.
+// g_dir is a directory holding hla_nom_g.txt (the reference opens it relative to the current directory, HLATyper.cpp:4157).
+int hlala_ref_type(void* h, const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
+                   const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
+                   const int32_t* cigar_off, const uint32_t* cigar, double is_mean, double is_sd, const char* out_dir, const char* g_dir, int threads,
+                   long long* n_used, double* seconds) {
+    Driver* d = (Driver*)h;
+    Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() { return d->run_type(b, prg_dir, is_mean, is_sd, out_dir, g_dir, threads, n_used, seconds); });
 }
 
 } // extern "C"

@@ -126,6 +126,15 @@ class Ref:
         return o
 
 
+    def type(self, prg_dir, b, is_mean, is_sd, out_dir, threads=1):
+        """gene filter + unmodified HLATyper::HLATypeInference; writes the reference's files into out_dir."""
+        os.makedirs(out_dir, exist_ok=True)
+        n_used = C.c_longlong(0); sec = C.c_double(0)
+        self._chk(self.lib.hlala_ref_type(self.h, prg_dir.encode(), *batch_args(b), C.c_double(is_mean), C.c_double(is_sd), out_dir.encode(), prg_dir.encode(),
+                                          C.c_int(threads), C.byref(n_used), C.byref(sec)))
+        return dict(n_used=n_used.value, seconds=sec.value)
+
+
 class Oracle(Ref):
     """oracle/build/libhlala_oracle.so: the plain C++ restatement (oracle/hlala_oracle.cpp). Same interface as Ref."""
 
@@ -153,6 +162,38 @@ class Oracle(Ref):
         self._chk(self.lib.hlala_ref_gap_paths_export(self.h, p(path_off), p(path_edges)))
         gs = np.zeros(nl, np.uint8); ngs = self.lib.hlala_ref_gap_stretch(self.h, p(gs))
         return dict(n_levels=nl, node_level=node_level, edge_from=ef, edge_to=et, edge_emis=em, path_off=path_off, path_edges=path_edges[:tot], gap_stretch=gs[:ngs])
+
+
+class OracleTyping:
+    """oracle/hlala_oracle_typing.cpp: typing restatement on exported alignment arrays (any aligner's `pairs` output with columns)."""
+
+    def __init__(self, prg_dir, b, aln, is_mean, is_sd, out_dir, cap=None):
+        L = self.lib = C.CDLL(LIB_ORACLE)
+        L.hlala_oracle_type.restype = C.c_void_p
+        L.hlala_oracle_type_last_error.restype = C.c_char_p
+        os.makedirs(out_dir, exist_ok=True)
+        cap = aln["level"].shape[1] if cap is None else cap
+        rmq = np.ascontiguousarray(aln["read_mapq"], np.float64)
+        self.h = C.c_void_p(L.hlala_oracle_type(prg_dir.encode(), C.c_longlong(len(b["read_off"]) - 1), p(b["read_off"]), p(b["bases"]), p(b["quals"]), C.c_int(cap),
+                                                p(aln["n_cols"]), p(aln["level"]), p(aln["gchar"]), p(aln["schar"]), p(aln["mapq"]), p(aln["read_reverse"]), p(rmq),
+                                                C.c_double(is_mean), C.c_double(is_sd), out_dir.encode(), prg_dir.encode()))
+        if not self.h:
+            raise RuntimeError("oracle typing failed: %s" % L.hlala_oracle_type_last_error().decode())
+        self.n_loci = L.hlala_oracle_type_n_loci(self.h)
+
+    def locus(self, i):
+        c = C.c_int(0); r = C.c_int(0)
+        self.lib.hlala_oracle_type_dims(self.h, C.c_int(i), C.byref(c), C.byref(r))
+        Cn, R = c.value, r.value
+        LL = np.zeros((Cn, R), np.float64); mm = np.zeros((Cn, R), np.int32); npair = Cn * (Cn + 1) // 2
+        pl = np.zeros(npair, np.float64); pa = np.zeros(npair, np.float64); pm = np.zeros(npair, np.float64)
+        self.lib.hlala_oracle_type_read_ll(self.h, C.c_int(i), p(LL), p(mm))
+        self.lib.hlala_oracle_type_pair_ll(self.h, C.c_int(i), p(pl), p(pa), p(pm))
+        return dict(C=Cn, R=R, LL=LL, mism=mm, pair_ll=pl, pair_mavg=pa, pair_mmin=pm)
+
+    def close(self):
+        if self.h:
+            self.lib.hlala_oracle_type_free(self.h); self.h = None
 
 
 _REF_CACHE = {}
