@@ -27,6 +27,7 @@ DATASETS = {
     # name: (prg kwargs, reads kwargs, insert-size mean, sd)
     "small": (dict(levels=6000, haps=4, genes=1, alleles=16, seed=7), dict(pairs=150, len=100, seed=7), 100.0, 10.0),
     "S": (dict(levels=25000, haps=4, genes=2, alleles=64), dict(pairs=1200, len=100, clip_frac=0.15), 100.0, 10.0),
+    "typing": (dict(levels=40000, haps=4, genes=17, alleles=24, seed=11), dict(pairs=1500, len=100, seed=11, gene_frac=0.8), 100.0, 10.0),
     "genes": (dict(levels=30000, haps=8, genes=8, alleles=300), dict(pairs=250, len=150, clip_frac=0.15, gene_frac=1.0), 100.0, 10.0),
 }
 
