@@ -234,7 +234,8 @@ struct Pipeline {
         n_wd_warps = wd_warps_for(g->n_sm);
         wd_scratch.alloc((size_t)n_wd_warps * wd_warp_scratch_bytes());
         CUDA_OK(cudaMemsetAsync(wd_scratch.p, 0, wd_scratch.bytes, st));
-        if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;
+        if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;            // test hooks (tools/scale_parity.py): the scalar DP only /
+        if (allow_env_budget && getenv("HLALA_ALIGN_DUPLICATES")) dedup = false;   // align the chains k_prepare would skip
         // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
         // chosen alignment columns written once, per-pair scalars, coverage RMW
         int64_t nb = b.read_off[b.n_reads]; int64_t ncg = b.cigar_off[pb.n_chains];

@@ -243,6 +243,10 @@ template <class CFG> __device__ int wd_extend(const WdCtx& C, const WdSlab& S, i
                 if (isNew || c.SG < selSG) { overwritten = !isNew; c.SG = (int16_t)selSG; c.bSG = kSG ? wd_decode(C, m1, m2, kSG, 2) : dp_bt(-1, -1, -1); }
                 if (ty == end_seq) c.pad = 1;                               // sequence-complete cell (extensionAligner.cpp:982-998)
                 stD = c.D; stGG = c.GG; stSG = c.SG;
+                // The reference's wavefront lists hold coordinates and read the score table when they are used. A cell that is revisited
+                // (only possible after a gap-path jump) and improved while it still sits in the m-1 list must therefore show its new
+                // scores when that list is consumed as the m-2 list of the next diagonal: refresh the snapshot.
+                if (overwritten) for (int i = 0; i < n_m1; i++) if (m1[i].cell == ci) { m1[i].D = (int16_t)stD; m1[i].GG = (int16_t)stGG; m1[i].SG = (int16_t)stSG; }
                 if (isNew && hashed) wd_insert_cell(C, cgen, tx, ty, tz, ci);
                 if (selD == running) {
                     // score before the last real step, through the stored backtrace (extensionAligner.cpp:1007-1041)

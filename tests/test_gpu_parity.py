@@ -70,6 +70,25 @@ def test_golden_fixture(dataset):
     assert np.array_equal(ch["ll"], gold["chain_ll"]) and np.array_equal(pack(ch["edge"], ch["n_cols"]), gold["chain_edge"])
 
 
+def test_cascade_regression_fixture(tmp_path):
+    """19 pairs found by tools/scale_parity.py at 1 M pairs where a revisited cell (after a gap-path jump) decided a tie in the
+    extension DP; expected outputs come from the compiled reference (tests/golden/make_cascade_regress.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_cascade_regress import PRG_KW
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cascade_regress_pairs.npz"))
+    d = str(tmp_path / "prg"); H.synth_prg(d, **PRG_KW)
+    b = {k[3:]: gold[k] for k in gold.files if k.startswith("in_")}
+    P = H.Product(d); P.to_gpu(0)
+    got = P.pairs(b, 100.0, 10.0, 640, want_levels=False)
+    pack = lambda cols, n: np.concatenate([cols[r, :n[r]] for r in range(len(n))])
+    assert np.array_equal(got["n_cols"], gold["n_cols"])
+    for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+        assert np.array_equal(pack(got[k], got["n_cols"]), gold[k]), k
+    assert np.allclose(got["pair_mapq"], gold["pair_mapq"], rtol=0, atol=1e-12) and np.allclose(got["read_mapq"], gold["read_mapq"], rtol=0, atol=1e-12)
+    P.close()
+
+
 def test_waves_and_scalar_dp_give_identical_results(dataset, monkeypatch):
     d, b, mu, sd = dataset("S")
     base = product(d).pairs(b, mu, sd, 1024)

@@ -45,3 +45,18 @@ def test_oracle_pairs_match_golden(dataset):
     assert np.array_equal(pr["pair_mapq"], GOLD["pair_mapq"]) and np.array_equal(pr["read_mapq"], GOLD["read_mapq"])
     assert np.array_equal(pr["read_reverse"], GOLD["read_reverse"])
     assert (GOLD["pair_mapq"] < 1).sum() > 0, "the fixture must exercise the multi-combination mapQ path"
+
+
+def test_oracle_matches_cascade_regression_fixture(tmp_path):
+    """The restatement on the 19 tie-after-gap-jump pairs of tests/golden/cascade_regress_pairs.npz (expected = compiled reference)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_cascade_regress import PRG_KW
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cascade_regress_pairs.npz"))
+    d = str(tmp_path / "prg"); H.synth_prg(d, **PRG_KW)
+    b = {k[3:]: gold[k] for k in gold.files if k.startswith("in_")}
+    pr = H.Oracle(d).pairs(b, 100.0, 10.0, 640)
+    assert np.array_equal(pr["n_cols"], gold["n_cols"])
+    for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+        assert np.array_equal(pack(pr[k], pr["n_cols"]), gold[k]), k
+    assert np.array_equal(pr["pair_mapq"], gold["pair_mapq"]) and np.array_equal(pr["read_mapq"], gold["read_mapq"])
