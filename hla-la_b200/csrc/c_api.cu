@@ -3,6 +3,8 @@
 #include "../host/prg_graph.h"
 #include "chain_params.h"
 #include "align_kernels.h"
+#include "typing_kernels.h"
+#include "../host/hla_typing.h"
 
 #include <algorithm>
 #include <cmath>
@@ -212,7 +214,7 @@ struct Pipeline {
     void prepare(hlala_graph* graph, const hlala_seed_batch_t& b, int32_t mc, cudaStream_t st) {
         g = graph; maxcol = mc;
         if (const char* e = allow_env_budget ? getenv("HLALA_WAVE_BYTES") : nullptr) scratch_budget = (size_t)strtoull(e, nullptr, 10);   // test hook: force several waves
-        pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1);
+        pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1); host_read_off.assign(b.read_off, b.read_off + b.n_reads + 1);
         // waves: consecutive pairs whose chains fit the column-scratch budget
         wave_pair.assign(1, 0); int32_t max_wave_chains = 0;
         { const int64_t np = b.n_reads / 2; const int64_t cap = std::max<int64_t>(1024, (int64_t)(scratch_budget / ((size_t)mc * 6)));
@@ -295,6 +297,8 @@ struct Pipeline {
         return P;
     }
     std::vector<int32_t> host_chain_off;
+    std::vector<int64_t> host_read_off;
+    bool keep_columns = false;         // session runs materialise the chosen alignments' columns (typing stage input)
     int32_t db_chain_off(int64_t r) const { return host_chain_off[(size_t)r]; }
     void set_insert_size(double mean, double sd, cudaStream_t st) {
         if (mean == is_mean && sd == is_sd) return;
@@ -497,7 +501,7 @@ int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double 
     });
 }
 
-struct hlala_session { Pipeline pl; };
+struct hlala_session { Pipeline pl; std::vector<uint8_t> typing_blob; };
 
 int hlala_session_create(hlala_graph_t* g, const hlala_seed_batch_t* batch, int32_t max_columns, hlala_session_t** out) {
     if (!g || !out) return fail(HLALA_E_ARG, "hlala_session_create: null argument");
@@ -521,7 +525,7 @@ int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(s->pl.g->device));
         cudaStream_t st = (cudaStream_t)cuda_stream;
-        s->pl.run(is_mean, is_sd, (int32_t*)(uintptr_t)bases_per_level_dev, false, st);
+        s->pl.run(is_mean, is_sd, (int32_t*)(uintptr_t)bases_per_level_dev, s->pl.keep_columns, st);
         return 0;
     });
 }
@@ -550,6 +554,179 @@ int hlala_session_digest(hlala_session_t* s, int64_t out[4], double* sum_pair_ll
         }
         return 0;
     });
+}
+
+} // extern "C"
+
+// ===================================================================================================================
+// HLA typing stage
+namespace {
+
+TypingScoreTables make_typing_tables() {   // HLATyper.cpp:2060-2066, 2189-2216; Utilities.cpp:357-377, 1368-1379
+    TypingScoreTables t;
+    const double insertionP = 0.001, deletionP = 0.001;
+    const double ll_ins = log(insertionP);
+    t.ll_ins_actual = ll_ins + log(1.0 / 4.0); t.ll_del = log(deletionP); t.ll_mm = log(1 - insertionP - deletionP);
+    t.log_half = log(0.5); t.log_two = log(1 + exp(0.0));
+    for (int q = 0; q < 256; q++) {
+        if (q < 33) { t.log_pc[q] = NAN; t.log_pi[q] = NAN; continue; }
+        double pc = 1 - exp(log(10) * ((double)(q - 33) / (double)-10));
+        if (pc > 0.999) pc = 0.999;
+        if (pc == 0) pc = 0.001;
+        t.log_pc[q] = log(pc);
+        double pi = (1 - pc) * (1.0 / 3.0);
+        t.log_pi[q] = log(pi);
+    }
+    return t;
+}
+
+struct GpuTypingDevice : TypingDevice {
+    int rank = 0, world = 1; hlala_allreduce_f64_fn allreduce = nullptr; void* ctx = nullptr; cudaStream_t st = 0;
+    double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0};
+    void run_locus(const LocusDeviceInput& in, bool want_read_ll, LocusDeviceOutput& out) override {
+        const int32_t C = in.C, P = in.P, R = in.R; const int32_t Cpad = (C + 31) / 32 * 32;
+        const size_t npair = (size_t)C * ((size_t)C + 1) / 2;
+        std::vector<uint8_t> ct((size_t)P * Cpad, (uint8_t)'_');
+        for (int32_t c = 0; c < C; c++) { const std::string& s = (*in.cluster_seq)[(size_t)c]; for (int32_t p = 0; p < P; p++) ct[(size_t)p * Cpad + c] = (uint8_t)s[(size_t)p]; }
+        DevBuf d_ct, d_off, d_pos, d_c0, d_q0, d_glen, d_ll, d_mm, d_pair;
+        d_ct.upload(ct, st); d_off.upload(in.rec_off, st);
+        if (!in.rec_pos.empty()) { d_pos.upload(in.rec_pos, st); d_c0.upload(in.rec_c0, st); d_q0.upload(in.rec_q0, st); d_glen.upload(in.rec_glen, st); }
+        d_ll.alloc((size_t)std::max(R, 1) * Cpad * 8); d_mm.alloc((size_t)std::max(R, 1) * Cpad * 4); d_pair.alloc(3 * npair * 8);
+        const int32_t r0 = (int32_t)((int64_t)R * rank / world), r1 = (int32_t)((int64_t)R * (rank + 1) / world);
+        if (want_read_ll) { CUDA_OK(cudaMemsetAsync(d_ll.p, 0, d_ll.bytes, st)); CUDA_OK(cudaMemsetAsync(d_mm.p, 0, d_mm.bytes, st)); }
+        int32_t max_rec = 0; double steps = 0;
+        for (int32_t r = 0; r < R; r++) { max_rec = std::max(max_rec, in.rec_off[r + 1] - in.rec_off[r]); if (r >= r0 && r < r1) steps += (double)(in.rec_off[r + 1] - in.rec_off[r]); }
+        cudaEvent_t e0, e1, e2; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaEventCreate(&e2));
+        CUDA_OK(cudaEventRecord(e0, st));
+        CUDA_OK(launch_read_cluster_ll(d_ct.as<uint8_t>(), C, Cpad, r0, r1, max_rec, d_off.as<int32_t>(), d_pos.as<int16_t>(), d_c0.as<uint8_t>(), d_q0.as<uint8_t>(), d_glen.as<uint16_t>(), d_ll.as<double>(), d_mm.as<int32_t>(), st));
+        CUDA_OK(cudaEventRecord(e1, st));
+        double* pl = d_pair.as<double>();
+        CUDA_OK(launch_allele_pair_ll(d_ll.as<double>(), d_mm.as<int32_t>(), C, Cpad, r0, r1, pl, pl + npair, pl + 2 * npair, st));
+        CUDA_OK(cudaEventRecord(e2, st));
+        if (world > 1) {
+            if (!allreduce) throw std::runtime_error("hlala_typer_infer: world > 1 needs an all-reduce callback");
+            if (allreduce(ctx, (uint64_t)(uintptr_t)d_pair.p, (int64_t)(3 * npair), (void*)st) != 0) throw std::runtime_error("hlala_typer_infer: all-reduce callback failed");
+        }
+        out.pair_ll.resize(npair); out.pair_mavg.resize(npair); out.pair_mmin.resize(npair);
+        CUDA_OK(cudaMemcpyAsync(out.pair_ll.data(), pl, npair * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(out.pair_mavg.data(), pl + npair, npair * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(out.pair_mmin.data(), pl + 2 * npair, npair * 8, cudaMemcpyDeviceToHost, st));
+        std::vector<double> llt; std::vector<int32_t> mmt;
+        if (want_read_ll && R > 0) { llt.resize((size_t)R * Cpad); mmt.resize((size_t)R * Cpad); d_ll.download(llt.data(), llt.size(), st); d_mm.download(mmt.data(), mmt.size(), st); }
+        CUDA_OK(cudaStreamSynchronize(st));
+        float f = 0; CUDA_OK(cudaEventElapsedTime(&f, e0, e1)); ms[0] += f; CUDA_OK(cudaEventElapsedTime(&f, e1, e2)); ms[1] += f; launches[0] += (r1 > r0); launches[1]++;
+        work[0] += steps * C; work[1] += (double)npair * (r1 - r0);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        out.LL.clear(); out.mism.clear();
+        if (want_read_ll) { out.LL.assign((size_t)C * R, 0.0); out.mism.assign((size_t)C * R, 0);
+            for (int32_t r = 0; r < R; r++) for (int32_t c = 0; c < C; c++) { out.LL[(size_t)c * R + r] = llt[(size_t)r * Cpad + c]; out.mism[(size_t)c * R + r] = mmt[(size_t)r * Cpad + c]; } }
+    }
+};
+
+} // namespace
+
+struct hlala_typer { TypingTables T; std::vector<LocusCall> calls; double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0}; bool tables_on_device = false; int device = -1; };
+
+extern "C" {
+
+int hlala_typer_create(const char* dir, hlala_typer_t** out) {
+    if (!dir || !out) return fail(HLALA_E_ARG, "hlala_typer_create: null argument");
+    *out = nullptr;
+    return guarded([&]() { std::unique_ptr<hlala_typer> t(new hlala_typer()); t->T.load(dir); *out = t.release(); return 0; });
+}
+void hlala_typer_free(hlala_typer_t* t) { delete t; }
+int hlala_typer_n_loci(const hlala_typer_t* t) { return t ? (int)t->T.loci.size() : -1; }
+const char* hlala_typer_locus_name(const hlala_typer_t* t, int l) { return (t && l >= 0 && l < (int)t->T.loci.size()) ? t->T.loci[(size_t)l].name.c_str() : nullptr; }
+int hlala_typer_locus_dims(const hlala_typer_t* t, int l, int32_t* C, int32_t* P) {
+    if (!t || l < 0 || l >= (int)t->T.loci.size()) return fail(HLALA_E_ARG, "hlala_typer_locus_dims: bad locus");
+    if (C) *C = t->T.loci[(size_t)l].C(); if (P) *P = t->T.loci[(size_t)l].P(); return 0;
+}
+
+int hlala_session_set_keep_columns(hlala_session_t* s, int on) { if (!s) return fail(HLALA_E_ARG, "null session"); s->pl.keep_columns = on != 0; return 0; }
+
+int hlala_session_typing_extract(hlala_session_t* s, const hlala_typer_t* t, const char* const* pair_names, int64_t pair_index_base,
+                                 const uint8_t** blob, int64_t* blob_bytes, int64_t* n_selected) {
+    if (!s || !t || !blob || !blob_bytes) return fail(HLALA_E_ARG, "hlala_session_typing_extract: null argument");
+    Pipeline& pl = s->pl;
+    if (!pl.have_columns) return fail(HLALA_E_ARG, "hlala_session_typing_extract: run the session with hlala_session_set_keep_columns(s, 1) first");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(pl.g->device)); cudaStream_t st = 0;
+        const int64_t nr = pl.pb.n_reads, np = nr / 2;
+        if (t->T.gene_bounds.size() > (size_t)TY_MAX_GENES) return fail(HLALA_E_CAPACITY, "more than 64 genes in segments.txt");
+        GeneBounds gb; gb.n = (int32_t)t->T.gene_bounds.size(); for (int i = 0; i < gb.n; i++) { gb.first[i] = t->T.gene_bounds[(size_t)i].first; gb.last[i] = t->T.gene_bounds[(size_t)i].second; }
+        DevBuf d_flag; d_flag.alloc((size_t)std::max<int64_t>(np, 1));
+        CUDA_OK(launch_gene_filter(gb, np, pl.maxcol, pl.o_n_cols.as<int32_t>(), pl.o_level.as<int32_t>(), d_flag.as<uint8_t>(), st));
+        std::vector<uint8_t> flag((size_t)np), rev((size_t)nr); std::vector<int32_t> ncols((size_t)nr); std::vector<double> rmq((size_t)nr);
+        d_flag.download(flag.data(), (size_t)np, st); pl.o_n_cols.download(ncols.data(), (size_t)nr, st); pl.read_reverse.download(rev.data(), (size_t)nr, st); pl.read_mapq.download(rmq.data(), (size_t)nr, st);
+        CUDA_OK(cudaStreamSynchronize(st));
+        TypingReads tr; tr.col_off.push_back(0); tr.base_off.push_back(0); std::vector<int64_t> src;
+        for (int64_t p = 0; p < np; p++) if (flag[(size_t)p]) {
+            tr.pair_id.push_back(pair_index_base + p); tr.name.push_back(pair_names ? std::string(pair_names[p]) : "r" + std::to_string(pair_index_base + p));
+            for (int m = 0; m < 2; m++) { const int64_t r = 2 * p + m; src.push_back(r); tr.col_off.push_back(tr.col_off.back() + ncols[(size_t)r]); tr.base_off.push_back(tr.base_off.back() + (pl.host_read_off[(size_t)r + 1] - pl.host_read_off[(size_t)r]));
+                tr.reverse.push_back(rev[(size_t)r]); tr.mapq.push_back(rmq[(size_t)r]); }
+        }
+        const size_t ncol = (size_t)tr.col_off.back(), nb = (size_t)tr.base_off.back();
+        tr.level.resize(ncol); tr.g.resize(ncol); tr.s.resize(ncol); tr.mq.resize(ncol); tr.bases.resize(nb); tr.quals.resize(nb);
+        if (!src.empty()) {
+            DevBuf d_src, d_co, d_bo, o_l, o_g, o_s, o_m, o_b, o_q; d_src.upload(src, st); d_co.upload(tr.col_off, st); d_bo.upload(tr.base_off, st);
+            o_l.alloc(std::max<size_t>(ncol, 1) * 4); o_g.alloc(std::max<size_t>(ncol, 1)); o_s.alloc(std::max<size_t>(ncol, 1)); o_m.alloc(std::max<size_t>(ncol, 1)); o_b.alloc(std::max<size_t>(nb, 1)); o_q.alloc(std::max<size_t>(nb, 1));
+            CUDA_OK(launch_gather_reads((int64_t)src.size(), d_src.as<int64_t>(), d_co.as<int64_t>(), d_bo.as<int64_t>(), pl.maxcol, pl.o_n_cols.as<int32_t>(), pl.o_level.as<int32_t>(), pl.o_gchar.as<uint8_t>(), pl.o_schar.as<uint8_t>(),
+                                        pl.o_mapq.as<uint8_t>(), pl.db.view.read_off, pl.db.view.bases, pl.db.view.quals, o_l.as<int32_t>(), o_g.as<uint8_t>(), o_s.as<uint8_t>(), o_m.as<uint8_t>(), o_b.as<uint8_t>(), o_q.as<uint8_t>(), st));
+            o_l.download(tr.level.data(), ncol, st); o_g.download(tr.g.data(), ncol, st); o_s.download(tr.s.data(), ncol, st); o_m.download(tr.mq.data(), ncol, st); o_b.download(tr.bases.data(), nb, st); o_q.download(tr.quals.data(), nb, st);
+            CUDA_OK(cudaStreamSynchronize(st));
+        }
+        s->typing_blob = tr.serialize();
+        *blob = s->typing_blob.data(); *blob_bytes = (int64_t)s->typing_blob.size(); if (n_selected) *n_selected = (int64_t)tr.n_pairs();
+        return 0;
+    });
+}
+
+int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs, const int64_t* blob_bytes, int n_blobs, double is_mean, double is_sd,
+                      const char* out_dir, const char* g_nom_dir, int rank, int world, hlala_allreduce_f64_fn allreduce, void* allreduce_ctx, int keep_read_ll) {
+    if (!t || !blobs || !blob_bytes || n_blobs < 1 || !g_nom_dir) return fail(HLALA_E_ARG, "hlala_typer_infer: null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(HLALA_E_ARG, "hlala_typer_infer: bad rank/world");
+    try {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(HLALA_E_CUDA, "no CUDA device available: the typing kernels have no CPU fallback");
+        CUDA_OK(cudaSetDevice(device));
+        if (!t->tables_on_device || t->device != device) { CUDA_OK(upload_typing_tables(make_typing_tables())); t->tables_on_device = true; t->device = device; }
+        TypingReads all; for (int i = 0; i < n_blobs; i++) all.deserialize_append(blobs[i], (size_t)blob_bytes[i]);
+        GpuTypingDevice dev; dev.rank = rank; dev.world = world; dev.allreduce = allreduce; dev.ctx = allreduce_ctx;
+        TypingOptions opt; opt.keep_read_ll = keep_read_ll != 0;
+        t->calls.clear();
+        run_typing(t->T, all, is_mean, is_sd, out_dir ? std::string(out_dir) : std::string(), g_nom_dir, dev, opt, t->calls);
+        for (int k = 0; k < 2; k++) { t->ms[k] = dev.ms[k]; t->launches[k] = dev.launches[k]; t->work[k] = dev.work[k]; }
+        return 0;
+    }
+    catch (const CudaError& e) { return fail(HLALA_E_CUDA, e.what()); }
+    catch (const std::runtime_error& e) { const std::string m = e.what(); return fail(m.find("reference assertion would fail") != std::string::npos ? HLALA_E_INVARIANT : HLALA_E_IO, m); }
+    catch (const std::exception& e) { return fail(HLALA_E_IO, e.what()); }
+}
+
+int hlala_typer_result_dims(const hlala_typer_t* t, int l, int32_t* C, int32_t* R) {
+    if (!t || l < 0 || l >= (int)t->calls.size()) return fail(HLALA_E_ARG, "hlala_typer_result_dims: no result for this locus");
+    if (C) *C = t->calls[(size_t)l].C; if (R) *R = t->calls[(size_t)l].R; return 0;
+}
+int hlala_typer_result_read_ll(const hlala_typer_t* t, int l, double* ll, int32_t* mm) {
+    if (!t || l < 0 || l >= (int)t->calls.size()) return fail(HLALA_E_ARG, "hlala_typer_result_read_ll: no result for this locus");
+    const LocusCall& c = t->calls[(size_t)l];
+    if (c.dev.LL.size() != (size_t)c.C * c.R) return fail(HLALA_E_ARG, "hlala_typer_result_read_ll: run hlala_typer_infer with keep_read_ll");
+    if (ll) memcpy(ll, c.dev.LL.data(), c.dev.LL.size() * 8); if (mm) memcpy(mm, c.dev.mism.data(), c.dev.mism.size() * 4); return 0;
+}
+int hlala_typer_result_pair_ll(const hlala_typer_t* t, int l, double* pl, double* ma, double* mn) {
+    if (!t || l < 0 || l >= (int)t->calls.size()) return fail(HLALA_E_ARG, "hlala_typer_result_pair_ll: no result for this locus");
+    const LocusCall& c = t->calls[(size_t)l];
+    if (pl) memcpy(pl, c.dev.pair_ll.data(), c.dev.pair_ll.size() * 8); if (ma) memcpy(ma, c.dev.pair_mavg.data(), c.dev.pair_mavg.size() * 8); if (mn) memcpy(mn, c.dev.pair_mmin.data(), c.dev.pair_mmin.size() * 8); return 0;
+}
+int hlala_typer_result_call(const hlala_typer_t* t, int l, const char** a1, const char** a2, double* q1, double* q2) {
+    if (!t || l < 0 || l >= (int)t->calls.size()) return fail(HLALA_E_ARG, "hlala_typer_result_call: no result for this locus");
+    const LocusCall& c = t->calls[(size_t)l];
+    if (a1) *a1 = c.call1.c_str(); if (a2) *a2 = c.call2.c_str(); if (q1) *q1 = c.q1; if (q2) *q2 = c.q2; return 0;
+}
+int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], double work[2]) {
+    if (!t) return fail(HLALA_E_ARG, "null typer");
+    for (int k = 0; k < 2; k++) { if (ms) ms[k] = t->ms[k]; if (launches) launches[k] = t->launches[k]; if (work) work[k] = t->work[k]; }
+    return 0;
 }
 
 } // extern "C"

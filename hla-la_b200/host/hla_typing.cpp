@@ -93,7 +93,8 @@ void TypingTables::load(const std::string& dir) {
             const int32_t len = last - first + 1; TY_REQUIRE((int32_t)hf.size() - 1 == len, "exon columns are consecutive levels");
             for (int32_t i = 0; i < len; i++) { TY_REQUIRE(level_of.at(hf[1 + i]) == first + i, "exon columns are consecutive levels");
                 L.col_level.push_back(first + i); L.col_exon.push_back(ei); L.col_exonpos.push_back(i);
-                if (L.lmin == -1 || first + i < L.lmin) L.lmin = first + i; if (L.lmax == -1 || first + i > L.lmax) L.lmax = first + i; }
+                if (L.lmin == -1 || first + i < L.lmin) L.lmin = first + i;
+                if (L.lmax == -1 || first + i > L.lmax) L.lmax = first + i; }
             L.exon_len.push_back(len);
             for (size_t li = 1; li < lines.size(); li++) {
                 if (lines[li].empty()) continue;
@@ -235,11 +236,10 @@ void project_read(const Mate& A, const Mate& M, const TypingLocus& L, std::vecto
     }
     // keep exon columns; positions must be consecutive inside one visit of the exon table (:3501-3561)
     int state = 0, last = -1;
-    const int32_t base0 = L.col_level.empty() ? 0 : L.col_level[0];
     for (ExonObs& e : all) {
         int pos = -1;
         if (e.level >= L.lmin && e.level <= L.lmax) {   // exon columns are one or two consecutive level ranges
-            int cum = 0; int32_t lv = base0; (void)lv;
+            int cum = 0;
             for (size_t x = 0, at = 0; x < L.exon_len.size(); at += (size_t)L.exon_len[x], x++) { int32_t f = L.col_level[at]; if (e.level >= f && e.level < f + L.exon_len[x]) { pos = cum + (e.level - f); break; } cum += L.exon_len[x]; }
         }
         if (pos >= 0) { if (state == 2) last = -1; TY_REQUIRE(last == -1 || pos == last + 1, "consecutive exon positions"); e.pos = (uint32_t)pos; last = pos; state = 1; out.push_back(std::move(e)); }
@@ -311,16 +311,18 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         KmerSet::scan(mates[r].bases, (size_t)mates[r].len, [&](uint64_t k) { read_kmers.insert(k); }, []() {});
     }
 
-    mkdir(out_dir.c_str(), 0777);
+    // out_dir empty: compute only (ranks other than 0 of a multi-GPU run); every stream then goes to /dev/null
+    auto target = [&](const std::string& name) { return out_dir.empty() ? std::string("/dev/null") : out_dir + "/" + name; };
+    if (!out_dir.empty()) mkdir(out_dir.c_str(), 0777);
     {   // summaryStatistics.txt (HLATyper.cpp:1026-1125)
         int valid = 0, valid_dist = 0, perfect = 0, one_perfect = 0; std::vector<double> dists; double fsum = 0;
         for (size_t p = 0; p < NP; p++) { const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1];
             if (strands_ok(a, b)) { valid++; double d = level_distance(a, b); dists.push_back(d); if (fabs(d - is_mean) <= 5 * is_sd) valid_dist++; }
-            if (a.fraction_ok == 1) perfect++; if (b.fraction_ok == 1) perfect++; if (a.fraction_ok == 1 || b.fraction_ok == 1) one_perfect++; fsum += a.fraction_ok; fsum += b.fraction_ok; }
+            perfect += (a.fraction_ok == 1) + (b.fraction_ok == 1); one_perfect += (a.fraction_ok == 1 || b.fraction_ok == 1); fsum += a.fraction_ok; fsum += b.fraction_ok; }
         std::sort(dists.begin(), dists.end()); double dsum = 0; for (double d : dists) dsum += d;
         double dmean = 0, dmed = 0; if (!dists.empty()) { dmean = dsum / (double)dists.size(); dmed = dists[dists.size() / 2]; }
         auto pct = [](double a, double b) { return str((a / b) * 100); };
-        std::ofstream s(out_dir + "/summaryStatistics.txt"); if (!s.is_open()) throw std::runtime_error("Cannot open " + out_dir + "/summaryStatistics.txt for writing");
+        std::ofstream s(target("summaryStatistics.txt")); if (!s.is_open()) throw std::runtime_error("Cannot open " + target("summaryStatistics.txt") + " for writing");
         s << "\nRead alignment statistics:\n" << "\t - Total number (paired) alignments:                 " << NP << "\n"
           << "\t\t - Alignment pairs with strands OK:                  " << valid << " (" << pct(valid, NP) << "%)\n"
           << "\t\t - Alignment pairs with strands OK && distance OK:   " << valid_dist << " (" << pct(valid_dist, NP) << "%)\n"
@@ -329,7 +331,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
           << "\t\t - Single alignments, perfect (total):   " << perfect << " (" << NP * 2 << ")\n" << "\t - Total number (unpaired) alignments:                 " << 0 << "\n"
           << "\t\t - Alignment pairs, average fraction alignment OK:   " << 0.0 << "\n" << "\t\t - Single alignments, perfect (total):   " << 0 << " (" << 0 << ")\n" << "\t\t - Alignments with length >= " << 1000 << ":   " << 0 << "\n";
     }
-    std::ofstream best(out_dir + "/R1_bestguess.txt"), bestG(out_dir + "/R1_bestguess_G.txt"), hist(out_dir + "/histogram_matchesPerRead.txt");
+    std::ofstream best(target("R1_bestguess.txt")), bestG(target("R1_bestguess_G.txt")), hist(target("histogram_matchesPerRead.txt"));
     if (!best.is_open() || !bestG.is_open() || !hist.is_open()) throw std::runtime_error("Cannot open output files in " + out_dir);
     const std::string unacc_field = "NColumns_UnaccountedAllele_fGT" + str(unacc_min_frac);
     best << "Locus\tChromosome\tAllele\tQ1\tQ2\tAverageCoverage\tCoverageFirstDecile\tMinimumCoverage\tproportionkMersCovered\tLocusAvgColumnError\t" << unacc_field << "\n";
@@ -391,7 +393,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         std::map<int, std::map<int, std::vector<const ExonObs*>>> pile; std::set<std::string> utilized;
         for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; pile[L.col_exon[e.pos]][L.col_exonpos[e.pos]].push_back(&e); hist << L.name << "\t" << "base" << e.self->weighted_ok << "\n"; }
         {
-            std::ofstream ps(out_dir + "/R1_pileup_" + L.name + ".txt");
+            std::ofstream ps(target("R1_pileup_" + L.name + ".txt"));
             for (auto& ex : pile) { const int exon = ex.first, len = L.exon_len.at((size_t)exon);
                 for (int ep = 0; ep < len; ep++) {
                     auto it = ex.second.find(ep);
@@ -406,7 +408,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
                     ps << exon << "\t" << ep << "\t" << pu.size() << "\t" << join_with(parts, ", ") << "\t" << summary << "\n";
                 } }
         }
-        { std::ofstream rs(out_dir + "/R1_readIDs_" + L.name + ".txt"); for (const std::string& id : utilized) rs << id << "\n"; }
+        { std::ofstream rs(target("R1_readIDs_" + L.name + ".txt")); for (const std::string& id : utilized) rs << id << "\n"; }
 
         // ---- the two GPU stages: per-read x cluster log-likelihoods, allele-pair sums
         LocusDeviceInput di; di.C = C; di.P = P; di.R = (int32_t)R; di.cluster_seq = &L.cluster_seq; di.rec_off.assign(1, 0); long long bases_used = 0;
@@ -428,7 +430,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         std::vector<double> Pn(NPAIR); for (size_t i = 0; i < NPAIR; i++) { if (psum > 0) { Pn[i] = exp(LLs[i] - ll_max) / psum; TY_REQUIRE(Pn[i] >= 0 && Pn[i] <= 1, "P_normalized in [0,1]"); } else Pn[i] = 1.0 / (double)NPAIR; }
         auto members = [&](uint32_t c) { return join_with(L.cluster_members[c], ";"); };
         std::map<int, double> marginal;
-        { std::ofstream ap(out_dir + "/R1_PP_" + L.name + "_pairs.txt"); ap << "ClusterID\tP\tLL\tMismatches_avg\n";
+        { std::ofstream ap(target("R1_PP_" + L.name + "_pairs.txt")); ap << "ClusterID\tP\tLL\tMismatches_avg\n";
           for (size_t k = 0; k < NPAIR; k++) { const size_t i = order[k]; ap << members(ids[i].first) << "/" << members(ids[i].second) << "\t" << Pn[i] << "\t" << LLs[i] << "\t" << Mavg[i] << "\n";
               marginal[(int)ids[i].first] += Pn[i]; if (ids[i].second != ids[i].first) marginal[(int)ids[i].second] += Pn[i]; } }
         auto first_max = [](const std::map<int, double>& m) { double mx = 0; int at = 0; bool first = true; for (auto& kv : m) if (first || kv.second > mx) { mx = kv.second; at = kv.first; first = false; } return std::make_pair(mx, at); };   // Utilities::findIntMapMaxP_nonCritical
@@ -460,7 +462,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             return tot == 0 ? -1.0 : (double)present / (double)tot; };
         const double k1 = kmer_presence(ex1), k2 = kmer_presence(ex2);
         const double avg_err = all_tot > 0 ? (double)all_inc / (double)all_tot : 0;
-        { std::ofstream ce(out_dir + "/R1_columnIncompatibilities_" + L.name + ".txt"); ce << "Column\tCoverage\tExpectedIncompatible\tObservedIncompatible\tp\n";
+        { std::ofstream ce(target("R1_columnIncompatibilities_" + L.name + ".txt")); ce << "Column\tCoverage\tExpectedIncompatible\tObservedIncompatible\tp\n";
           for (int32_t col = 0; col < P; col++) { const int cov = col_tot[col], obs = col_inc[col]; const double expd = avg_err * cov; double pv = 1;
               if (obs > expd) { double o0 = cov - obs, o1 = obs, e0 = cov - expd, e1 = expd; TY_REQUIRE(e0 > 0 && e1 > 0, "expected counts > 0"); double st = 0; st += pow(o0 - e0, 2) / e0; st += pow(o1 - e1, 2) / e1; pv = chi2_1_pvalue(st); TY_REQUIRE(pv >= 0 && pv <= 1, "p in [0,1]"); }
               ce << col << "\t" << cov << "\t" << expd << "\t" << obs << "\t" << pv << "\n"; } }
@@ -483,7 +485,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         if (!opt.keep_read_ll) { call.dev.LL.clear(); call.dev.LL.shrink_to_fit(); call.dev.mism.clear(); call.dev.mism.shrink_to_fit(); }
         calls.push_back(std::move(call));
     }
-    { std::ofstream ps(out_dir + "/R1_parameters.txt"); ps << "Loci = " << join_with(locus_names, ",") << "\n" << "veryConservativeReadLikelihoods = " << true << "\n"; }
+    { std::ofstream ps(target("R1_parameters.txt")); ps << "Loci = " << join_with(locus_names, ",") << "\n" << "veryConservativeReadLikelihoods = " << true << "\n"; }
 }
 
 } // namespace hlala

@@ -142,6 +142,49 @@ int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out);
  * out[0]=sum n_cols, out[1]=sum of edge ordinals (+1) over all columns, out[2]=number of pairs with mapQ<1, out[3]=error count */
 int hlala_session_digest(hlala_session_t* s, int64_t out[4], double* sum_pair_ll);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * HLA typing stage (short-read paired mode). Reference seam B4 of SURVEY.md §8b:
+ *   hlala_typer_create             hla::HLATyper::HLATyper (segments, gene boundaries)  hla/HLATyper.cpp:36-256
+ *                                  + exon tables / allele clustering of HLATypeInference  hla/HLATyper.cpp:1177-1372
+ *   hlala_session_set_keep_columns (no counterpart: keep the chosen alignments' columns in HBM for the typing stage)
+ *   hlala_session_typing_extract   gene filter of alignReads_postSeedExtraction_andStoreInto  mapper/processBAM.cpp:2427-2446,
+ *                                  HLATyper::intervalOverlapsWithGenes hla/HLATyper.cpp:259 (GPU kernel + compaction)
+ *   hlala_typer_infer              hla::HLATyper::HLATypeInference  hla/HLATyper.h:110, hla/HLATyper.cpp:933-2810:
+ *                                  host: exon projection (:3192-3565), read gates/filters (:1405-1931), calls/QC/files (:2366-2810);
+ *                                  GPU:  per-read x cluster log-likelihoods (:2049-2277), allele-pair sums (:2280-2364, the
+ *                                        reference's only OpenMP loop)
+ * Multi-GPU: every rank extracts its own pairs; the blobs are exchanged by the caller (all-gather, rank order == pair order) and
+ * every rank calls hlala_typer_infer with all blobs. Reads are split across ranks for the two kernels and the allele-pair sums
+ * are combined with ONE all-reduce per locus through the callback (NCCL in bench.py / the CLI). Only a rank with a non-NULL
+ * out_dir writes files. */
+typedef struct hlala_typer hlala_typer_t;
+int hlala_typer_create(const char* prg_graph_dir, hlala_typer_t** out);
+void hlala_typer_free(hlala_typer_t* t);
+int hlala_typer_n_loci(const hlala_typer_t* t);
+const char* hlala_typer_locus_name(const hlala_typer_t* t, int locus);
+int hlala_typer_locus_dims(const hlala_typer_t* t, int locus, int32_t* n_clusters, int32_t* n_exon_columns);
+
+int hlala_session_set_keep_columns(hlala_session_t* s, int on);
+/* After hlala_session_run with keep_columns on. pair_names: [n_pairs] BAM QNAMEs or NULL ("r<pair_index_base + pair>").
+ * *blob stays valid until the next call on this session or hlala_session_free. */
+int hlala_session_typing_extract(hlala_session_t* s, const hlala_typer_t* t, const char* const* pair_names, int64_t pair_index_base,
+                                 const uint8_t** blob, int64_t* blob_bytes, int64_t* n_pairs_selected);
+
+/* sum-all-reduce `count` doubles at device address dev_ptr over all ranks, ordered on cuda_stream; return 0 on success */
+typedef int (*hlala_allreduce_f64_fn)(void* ctx, uint64_t dev_ptr, int64_t count, void* cuda_stream);
+int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs, const int64_t* blob_bytes, int n_blobs,
+                      double is_mean, double is_sd, const char* out_dir /* NULL: compute only */, const char* g_nom_dir /* holds hla_nom_g.txt */,
+                      int rank, int world, hlala_allreduce_f64_fn allreduce, void* allreduce_ctx, int keep_read_ll);
+/* Results of the last hlala_typer_infer (arrays caller-allocated). LL / mism: [C*R], index c*R + r (needs keep_read_ll; with
+ * world > 1 only this rank's reads are filled). Pair arrays: [C(C+1)/2] in the reference's c1 <= c2 loop order. */
+int hlala_typer_result_dims(const hlala_typer_t* t, int locus, int32_t* n_clusters, int32_t* n_reads);
+int hlala_typer_result_read_ll(const hlala_typer_t* t, int locus, double* ll, int32_t* mismatches);
+int hlala_typer_result_pair_ll(const hlala_typer_t* t, int locus, double* pair_ll, double* mismatches_avg, double* mismatches_min);
+int hlala_typer_result_call(const hlala_typer_t* t, int locus, const char** allele1, const char** allele2, double* q1, double* q2);
+/* Device time of the last hlala_typer_infer: ms[0] per-read x cluster kernel, ms[1] allele-pair kernel (CUDA events); launches of each;
+ * work[0] = sum over loci of C*R*observations (select+add steps), work[1] = sum over loci of C(C+1)/2 * R (logAvg evaluations). */
+int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], double work[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,8 @@ def pytest_configure(config):
 def built():
     """Build everything once per session if a product of the build is missing (the driver normally calls build() first)."""
     import harness as H
-    need = [H.LIB_PRODUCT, H.LIB_ORACLE, H.SYNTH, os.path.join(H.REPO, "tests", "native", "build", "libdp_host.so")]
+    need = [H.LIB_PRODUCT, H.LIB_ORACLE, H.SYNTH, os.path.join(H.REPO, "tests", "native", "build", "libdp_host.so"),
+            os.path.join(H.REPO, "tests", "native", "build", "libtyping_host.so")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()

@@ -326,3 +326,90 @@ class Product:
         self._chk(self.lib.hlala_align_pairs(self.g, C.byref(sb), C.c_double(is_mean), C.c_double(is_sd), C.byref(po), p(bpl) if want_levels else None))
         o["bases_per_level"] = bpl
         return o
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p)
+
+
+class ProductTyping:
+    """Typing stage of the product through the C ABI: hlala_typer_* + hlala_session_typing_extract (include/hlala_b200.h)."""
+
+    def __init__(self, P, prg_dir):
+        self.P = P; self.lib = L = P.lib
+        L.hlala_typer_locus_name.restype = C.c_char_p
+        self.t = C.c_void_p()
+        P._chk(L.hlala_typer_create(prg_dir.encode(), C.byref(self.t)))
+        self.prg_dir = prg_dir
+        self.n_loci = L.hlala_typer_n_loci(self.t)
+
+    def close(self):
+        if self.t:
+            self.lib.hlala_typer_free(self.t); self.t = C.c_void_p()
+
+    def table_dims(self):
+        out = []
+        for i in range(self.n_loci):
+            c = C.c_int32(0); p_ = C.c_int32(0)
+            self.P._chk(self.lib.hlala_typer_locus_dims(self.t, i, C.byref(c), C.byref(p_)))
+            out.append((self.lib.hlala_typer_locus_name(self.t, i).decode(), c.value, p_.value))
+        return out
+
+    def extract(self, sess, names=None, base=0):
+        """gene filter + compaction on the device-resident results of the session's last run -> bytes"""
+        blob = C.POINTER(C.c_uint8)(); nb = C.c_int64(0); ns = C.c_int64(0)
+        arr = None
+        if names is not None:
+            arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        self.P._chk(self.lib.hlala_session_typing_extract(sess, self.t, arr, C.c_int64(base), C.byref(blob), C.byref(nb), C.byref(ns)))
+        return C.string_at(blob, nb.value), ns.value
+
+    def infer(self, blobs, is_mean, is_sd, out_dir, device=0, rank=0, world=1, allreduce=None, keep_read_ll=True):
+        if out_dir:
+            os.makedirs(out_dir, exist_ok=True)
+        bufs = [C.create_string_buffer(b, len(b)) for b in blobs]
+        ptrs = (C.POINTER(C.c_uint8) * len(bufs))(*[C.cast(x, C.POINTER(C.c_uint8)) for x in bufs])
+        sizes = (C.c_int64 * len(bufs))(*[len(b) for b in blobs])
+        cb = ALLREDUCE_FN(allreduce) if allreduce else C.cast(None, ALLREDUCE_FN)
+        self.P._chk(self.lib.hlala_typer_infer(self.t, C.c_int(device), ptrs, sizes, C.c_int(len(bufs)), C.c_double(is_mean), C.c_double(is_sd),
+                                               out_dir.encode() if out_dir else None, self.prg_dir.encode(), C.c_int(rank), C.c_int(world), cb, None, C.c_int(1 if keep_read_ll else 0)))
+
+    def locus(self, i, read_ll=True):
+        c = C.c_int32(0); r = C.c_int32(0)
+        self.P._chk(self.lib.hlala_typer_result_dims(self.t, i, C.byref(c), C.byref(r)))
+        Cn, R = c.value, r.value; npair = Cn * (Cn + 1) // 2
+        o = dict(C=Cn, R=R, pair_ll=np.zeros(npair, np.float64), pair_mavg=np.zeros(npair, np.float64), pair_mmin=np.zeros(npair, np.float64))
+        self.P._chk(self.lib.hlala_typer_result_pair_ll(self.t, i, p(o["pair_ll"]), p(o["pair_mavg"]), p(o["pair_mmin"])))
+        if read_ll:
+            o["LL"] = np.zeros((Cn, R), np.float64); o["mism"] = np.zeros((Cn, R), np.int32)
+            self.P._chk(self.lib.hlala_typer_result_read_ll(self.t, i, p(o["LL"]), p(o["mism"])))
+        a1 = C.c_char_p(); a2 = C.c_char_p(); q1 = C.c_double(0); q2 = C.c_double(0)
+        self.P._chk(self.lib.hlala_typer_result_call(self.t, i, C.byref(a1), C.byref(a2), C.byref(q1), C.byref(q2)))
+        o.update(call1=a1.value.decode(), call2=a2.value.decode(), q1=q1.value, q2=q2.value)
+        return o
+
+    def timing(self):
+        ms = (C.c_double * 2)(); ln = (C.c_int * 2)(); wk = (C.c_double * 2)()
+        self.P._chk(self.lib.hlala_typer_timing(self.t, ms, ln, wk))
+        return dict(ms=list(ms), launches=list(ln), work=list(wk))
+
+
+def session_align(P, b, is_mean, is_sd, maxcol, keep_columns=True):
+    """device-resident run of the alignment path; returns the session handle (caller frees with P.lib.hlala_session_free)"""
+    L = P.lib
+    sb = make_batch_struct(b); sess = C.c_void_p()
+    P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(maxcol), C.byref(sess)))
+    if keep_columns:
+        P._chk(L.hlala_session_set_keep_columns(sess, 1))
+    P._chk(L.hlala_session_run(sess, C.c_double(is_mean), C.c_double(is_sd), C.c_uint64(0), None))
+    return sess
+
+
+class _DevArray:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def dev_f64_tensor(ptr, count):
+    """torch view (no copy) of `count` doubles at device address `ptr` (what the typing all-reduce callback receives)."""
+    import torch
+    return torch.as_tensor(_DevArray(ptr, count), device="cuda")

@@ -1,0 +1,70 @@
+// Test-only: drives the product's typing HOST logic (hla-la_b200/host/hla_typing.cpp: tables, projection, filters, calls, writers) with a
+// plain-loop stand-in for the two GPU kernels, so that the CPU test-suite can compare every file the host side writes with the oracle /
+// the compiled reference without a GPU. The stand-in lives here, in tests/, and is never linked into libhlala_b200.so.
+#include "../../hla-la_b200/host/hla_typing.h"
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+using namespace hlala;
+
+namespace {
+struct LoopDevice : TypingDevice {   // HLATyper.cpp:2049-2364 restated as loops over the device input layout
+    void run_locus(const LocusDeviceInput& in, bool, LocusDeviceOutput& out) override {
+        const int C = in.C, R = in.R; const double ll_ins_actual = log(0.001) + log(1.0 / 4.0), ll_del = log(0.001), ll_mm = log(1 - 0.001 - 0.001);
+        out.LL.assign((size_t)C * R, 0); out.mism.assign((size_t)C * R, 0);
+        for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) { double ll = 0; int mm = 0; const std::string& cs = (*in.cluster_seq)[c];
+            for (int k = in.rec_off[r]; k < in.rec_off[r + 1]; k++) { char e = cs[in.rec_pos[k]]; char c0 = (char)in.rec_c0[k]; unsigned glen = in.rec_glen[k]; double lp = 0;
+                if (e == '_') { if (c0 != '_') lp += ll_ins_actual * (1 + (glen - 1)); }
+                else { if (c0 == '_') lp += ll_del; else { lp += ll_mm; double pc = 1 - exp(log(10) * ((double)((int)in.rec_q0[k] - 33) / (double)-10)); if (pc > 0.999) pc = 0.999; if (pc == 0) pc = 0.001; if (e == c0) lp += log(pc); else lp += log((1 - pc) * (1.0 / 3.0)); }
+                       lp += ll_ins_actual * (glen - 1); }
+                if (c0 != '_' && !(glen == 1 && c0 == e)) mm++;
+                ll += lp; }
+            out.LL[(size_t)c * R + r] = ll; out.mism[(size_t)c * R + r] = mm; }
+        auto log_avg = [](double a, double b) { return a > b ? log(0.5) + (log(1 + exp(b - a)) + a) : log(0.5) + (log(1 + exp(a - b)) + b); };
+        for (int c1 = 0; c1 < C; c1++) for (int c2 = c1; c2 < C; c2++) { double pl = 0, sa = 0, sm = 0;
+            for (int r = 0; r < R; r++) { int m1 = out.mism[(size_t)c1 * R + r], m2 = out.mism[(size_t)c2 * R + r]; pl += log_avg(out.LL[(size_t)c1 * R + r], out.LL[(size_t)c2 * R + r]); sa += (double)(m1 + m2) / 2.0; sm += m1 < m2 ? m1 : m2; }
+            out.pair_ll.push_back(pl); out.pair_mavg.push_back(sa); out.pair_mmin.push_back(sm); }
+    }
+};
+std::string g_err;
+}
+
+extern "C" {
+const char* typing_host_last_error() { return g_err.c_str(); }
+// alignment arrays as every implementation's `pairs` exports them ([n_reads, cap]); pairs named "r<p>"
+int typing_host_run(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
+                    const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, double is_mean, double is_sd, const char* out_dir, int roundtrip_blob) {
+    try {
+        TypingTables T; T.load(prg_dir);
+        TypingReads tr; tr.col_off.push_back(0); tr.base_off.push_back(0);
+        for (long long p = 0; p + 1 < n_reads; p += 2) {
+            int f[2] = {-1, -1}, l[2] = {-1, -1};
+            for (int m = 0; m < 2; m++) for (int c = 0; c < n_cols[p + m]; c++) { int lv = level[(size_t)(p + m) * cap + c]; if (lv != -1) { if (f[m] == -1) f[m] = lv; l[m] = lv; } }
+            if (!pair_overlaps_genes(T, f[0], l[0], f[1], l[1])) continue;
+            tr.pair_id.push_back(p / 2); tr.name.push_back("r" + std::to_string(p / 2));
+            for (int m = 0; m < 2; m++) { long long r = p + m; size_t o = (size_t)r * cap; int n = n_cols[r];
+                tr.level.insert(tr.level.end(), level + o, level + o + n); tr.g.insert(tr.g.end(), g + o, g + o + n); tr.s.insert(tr.s.end(), s + o, s + o + n); tr.mq.insert(tr.mq.end(), mq + o, mq + o + n);
+                tr.col_off.push_back((int64_t)tr.level.size());
+                tr.bases.insert(tr.bases.end(), bases + read_off[r], bases + read_off[r + 1]); tr.quals.insert(tr.quals.end(), quals + read_off[r], quals + read_off[r + 1]); tr.base_off.push_back((int64_t)tr.bases.size());
+                tr.reverse.push_back(reverse[r]); tr.mapq.push_back(read_mapq[r]); }
+        }
+        TypingReads use;
+        if (roundtrip_blob) {   // through the wire format, split in two blobs like a 2-rank gather
+            TypingReads a, b; a.col_off.push_back(0); a.base_off.push_back(0); b.col_off.push_back(0); b.base_off.push_back(0);
+            size_t half = tr.n_pairs() / 2;
+            for (size_t i = 0; i < tr.n_pairs(); i++) { TypingReads& d = i < half ? a : b; d.pair_id.push_back(tr.pair_id[i]); d.name.push_back(tr.name[i]);
+                for (int m = 0; m < 2; m++) { size_t r = 2 * i + m; d.level.insert(d.level.end(), tr.level.begin() + tr.col_off[r], tr.level.begin() + tr.col_off[r + 1]); d.g.insert(d.g.end(), tr.g.begin() + tr.col_off[r], tr.g.begin() + tr.col_off[r + 1]);
+                    d.s.insert(d.s.end(), tr.s.begin() + tr.col_off[r], tr.s.begin() + tr.col_off[r + 1]); d.mq.insert(d.mq.end(), tr.mq.begin() + tr.col_off[r], tr.mq.begin() + tr.col_off[r + 1]); d.col_off.push_back((int64_t)d.level.size());
+                    d.bases.insert(d.bases.end(), tr.bases.begin() + tr.base_off[r], tr.bases.begin() + tr.base_off[r + 1]); d.quals.insert(d.quals.end(), tr.quals.begin() + tr.base_off[r], tr.quals.begin() + tr.base_off[r + 1]); d.base_off.push_back((int64_t)d.bases.size());
+                    d.reverse.push_back(tr.reverse[r]); d.mapq.push_back(tr.mapq[r]); } }
+            std::vector<uint8_t> ba = a.serialize(), bb = b.serialize();
+            use.deserialize_append(ba.data(), ba.size()); use.deserialize_append(bb.data(), bb.size());
+        } else use = tr;
+        LoopDevice dev; TypingOptions opt; std::vector<LocusCall> calls;
+        run_typing(T, use, is_mean, is_sd, out_dir, prg_dir, dev, opt, calls);
+        return (int)calls.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+}

@@ -1,0 +1,100 @@
+"""Typing stage on the GPU through the C ABI (gene filter + compaction, per-read x cluster log-likelihoods, allele-pair sums, host
+calls/QC/writers) against the typing oracle, which tests/test_typing_oracle.py pins byte-for-byte to the unmodified reference.
+Per-read log-likelihoods and mismatch counts: bit-exact (north_star allows 1e-6). Allele-pair sums: 1e-12 relative (device exp/log
+instead of glibc's; north_star 1e-6). Calls and every output file: identical text."""
+import ctypes as C
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+
+def run_product(d, b, mu, sd, out_dir, world=1):
+    P = H.Product(d); P.to_gpu(0)
+    T = H.ProductTyping(P, d)
+    if world == 1:
+        sess = H.session_align(P, b, mu, sd, 512)
+        blob, nsel = T.extract(sess)
+        P.lib.hlala_session_free(sess)
+        blobs = [blob]
+    else:
+        import sys
+        sys.path.insert(0, H.PKG)
+        import hlala_dist
+        blobs = []; base = 0
+        for r in range(world):
+            sb = hlala_dist.shard_batch(b, r, world)
+            sess = H.session_align(P, sb, mu, sd, 512)
+            blob, nsel = T.extract(sess, base=base); blobs.append(blob)
+            base += (len(sb["read_off"]) - 1) // 2
+            P.lib.hlala_session_free(sess)
+    return P, T, blobs
+
+
+def test_typing_matches_oracle(dataset, tmp_path):
+    d, b, mu, sd = dataset("typing")
+    P, T, blobs = run_product(d, b, mu, sd, None)
+    out = str(tmp_path / "gpu" / "hla")
+    T.infer(blobs, mu, sd, out)
+    aln = P.pairs(b, mu, sd, 512, want_levels=False)       # the product's own alignments (parity-tested elsewhere) feed the oracle
+    or_dir = str(tmp_path / "oracle" / "hla")
+    O = H.OracleTyping(d, b, aln, mu, sd, or_dir)
+    assert T.n_loci == O.n_loci == 17
+    worst = 0.0
+    for i in range(17):
+        g = T.locus(i); o = O.locus(i)
+        assert (g["C"], g["R"]) == (o["C"], o["R"])
+        assert np.array_equal(g["LL"], o["LL"]), "locus %d: per-read log-likelihoods must be bit-identical" % i
+        assert np.array_equal(g["mism"], o["mism"])
+        assert np.array_equal(g["pair_mavg"], o["pair_mavg"]) and np.array_equal(g["pair_mmin"], o["pair_mmin"])
+        rel = np.abs(g["pair_ll"] - o["pair_ll"]) / np.maximum(1.0, np.abs(o["pair_ll"]))
+        worst = max(worst, float(rel.max()))
+        assert rel.max() < 1e-12, "locus %d: allele-pair log-likelihood sums differ by %g (relative)" % (i, rel.max())
+    fo = sorted(os.listdir(or_dir)); assert sorted(os.listdir(out)) == fo and len(fo) == 73
+    exact = ["R1_bestguess.txt", "R1_bestguess_G.txt", "summaryStatistics.txt", "histogram_matchesPerRead.txt", "R1_parameters.txt"]
+    exact += [f for f in fo if f.startswith(("R1_pileup_", "R1_readIDs_", "R1_columnIncompatibilities_"))]
+    bad = [f for f in exact if not filecmp.cmp(os.path.join(or_dir, f), os.path.join(out, f), shallow=False)]
+    assert not bad, bad
+    # the pair tables print 6 significant digits of sums that may differ in the last bits: compare them field by field
+    for f in fo:
+        if not f.startswith("R1_PP_"):
+            continue
+        a = open(os.path.join(or_dir, f)).read().split("\n"); g_ = open(os.path.join(out, f)).read().split("\n")
+        assert len(a) == len(g_)
+        for la, lg in zip(a[1:], g_[1:]):
+            if la == lg:
+                continue
+            fa, fg = la.split("\t"), lg.split("\t")
+            assert fa[0] == fg[0] and np.allclose([float(x) for x in fa[1:]], [float(x) for x in fg[1:]], rtol=1e-5, atol=0), (f, la, lg)
+    O.close(); T.close(); P.close()
+
+
+def test_typing_two_rank_split_gives_same_calls(dataset, tmp_path):
+    """Pairs extracted by two 'ranks' and gathered, reads split across two ranks for the kernels with a host-side sum standing in for
+    the all-reduce: same calls, pair sums within 1e-12 of the single-rank run."""
+    d, b, mu, sd = dataset("typing")
+    P, T, blobs1 = run_product(d, b, mu, sd, None)
+    T.infer(blobs1, mu, sd, None)
+    single = [T.locus(i, read_ll=False) for i in range(17)]
+    P2, T2, blobs2 = run_product(d, b, mu, sd, None, world=2)
+    assert b"".join(blobs1)[64:200] != b"" and sum(len(x) for x in blobs2) > len(blobs1[0]) * 0.9
+    # run rank 0 and rank 1 one after the other; the callback records each rank's partial sums instead of reducing them
+    partial = [[], []]
+    for rank in (0, 1):
+        def cb(ctx, ptr, count, stream, rank=rank):
+            import torch
+            torch.cuda.synchronize()
+            partial[rank].append(H.dev_f64_tensor(ptr, count).cpu().numpy().copy())
+            return 0
+        T2.infer(blobs2, mu, sd, None, rank=rank, world=2, allreduce=cb, keep_read_ll=False)
+    for i in range(17):
+        n = len(single[i]["pair_ll"])
+        tot = partial[0][i] + partial[1][i]
+        assert np.allclose(tot[:n], single[i]["pair_ll"], rtol=1e-12, atol=1e-9)
+        assert np.array_equal(tot[n:2 * n], single[i]["pair_mavg"]) and np.array_equal(tot[2 * n:], single[i]["pair_mmin"])
+    T.close(); P.close(); T2.close(); P2.close()
