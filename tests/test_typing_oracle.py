@@ -1,9 +1,10 @@
 """Pins the typing restatement (oracle/hlala_oracle_typing.cpp) against the UNMODIFIED reference HLATyper::HLATypeInference
 (oracle/_ref): every file the reference writes into outDir/hla must be byte-identical, for all 17 loci."""
-import filecmp
+import json
 import os
+import subprocess
+import sys
 
-import numpy as np
 import pytest
 
 import harness as H
@@ -13,20 +14,11 @@ pytestmark = pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref/libhlala_r
 
 def test_typing_files_byte_identical(dataset, tmp_path):
     d, b, mu, sd = dataset("typing")
-    R = H.quiet(H.Ref, d)
-    aln = H.quiet(R.pairs, b, mu, sd, 512)
-    ref_dir = str(tmp_path / "ref" / "hla"); or_dir = str(tmp_path / "oracle" / "hla")
-    r = H.quiet(R.type, d, b, mu, sd, ref_dir)
-    assert r["n_used"] > 500
-    T = H.OracleTyping(d, b, aln, mu, sd, or_dir)
-    try:
-        fr = sorted(os.listdir(ref_dir)); fo = sorted(os.listdir(or_dir))
-        assert fr == fo and len(fr) == 5 + 4 * 17
-        bad = [f for f in fr if not filecmp.cmp(os.path.join(ref_dir, f), os.path.join(or_dir, f), shallow=False)]
-        assert not bad, "files differ from the reference's: %s" % bad
-        assert T.n_loci == 17
-        dims = [T.locus(i) for i in range(T.n_loci)]
-        assert all(x["C"] >= 8 and x["R"] >= 20 for x in dims)
-        assert all(np.isfinite(x["pair_ll"]).all() for x in dims)
-    finally:
-        T.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "typing_ref_compare.py"), d, os.path.join(d, "seeds.bin"), str(mu), str(sd), str(tmp_path)],
+                       cwd=here, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    v = json.loads(r.stdout.strip().split("\n")[-1])
+    assert v["n_used"] > 500 and v["files_ref"] == v["files_oracle"] == 5 + 4 * 17
+    assert not v["differing"], "files differ from the reference's: %s" % v["differing"]
+    assert v["n_loci"] == 17 and v["min_C"] >= 8 and v["min_R"] >= 20 and v["finite"]
