@@ -2,6 +2,7 @@
 #include "chain_kernel.cuh"
 #include "extend_dp.h"
 #include "extend_warp.cuh"
+#include "extend_group.cuh"
 #include "pair_kernel.cuh"
 #include "align_kernels.h"
 
@@ -242,6 +243,63 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     }
 }
 
+
+// Kernel 2 (first tier): extension DP, one 8-lane group per (pending chain, side); the groups of a warp advance one diagonal each per
+// iteration of a flat loop (see extend_group.cuh). Tasks are dealt round-robin to the groups of the persistent grid.
+template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend_group(ExtParams E) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
+    constexpr int GW = CFG::GW, NG = CFG::NG;
+    const int gcta = threadIdx.x / GW;                               // group inside the CTA
+    const int gg = blockIdx.x * (CFG::WARPS * NG) + gcta; const int ng = gridDim.x * CFG::WARPS * NG;
+    Grp<GW> g; g.lane = threadIdx.x % GW; g.shift = ((threadIdx.x & 31) / GW) * GW; g.mask = (GW == 32) ? 0xffffffffu : (((1u << (GW & 31)) - 1u) << g.shift);
+    GdSlab S = gd_carve<CFG>(smem + (size_t)gcta * gd_slab_bytes<CFG>());
+    unsigned char* hb = E.gd_scratch + (size_t)gg * gd_hbm_bytes<CFG>();
+    DpGraph dg; dg.n_levels = G.n_levels; dg.level_node_off = G.level_node_off; dg.edge_pack = G.edge_pack;
+    dg.node_out_off = G.node_out_off; dg.node_out = G.node_out; dg.node_in_off = G.node_in_off; dg.node_in = G.node_in;
+    dg.path_off = G.path_off; dg.path_edges = G.path_edges; dg.path_from = G.path_from; dg.path_to = G.path_to;
+    dg.jump_fwd_off = G.jump_fwd_off; dg.jump_fwd_path = G.jump_fwd_path; dg.jump_bwd_off = G.jump_bwd_off; dg.jump_bwd_path = G.jump_bwd_path;
+    dg.adj4 = G.adj4; dg.out_adj4 = G.out_adj4; dg.in_adj4 = G.in_adj4; dg.jf4 = G.jf4; dg.jb4 = G.jb4; dg.node_gapflags = G.node_gapflags;
+    WdCtx C; C.G = &dg; C.cells = (DpCell*)hb; C.hash = (uint32_t*)(hb + sizeof(DpCell) * (size_t)CFG::CELLS); C.gens = C.hash + CFG::HASH;
+    C.seq = nullptr; C.seq_len = 0; C.start_seq = C.start_level = C.start_z = C.start_node = 0; C.pos = false;
+    GdState st{}; int phase = (gg < E.n_gd_groups) ? 0 : 2;        // 0: needs a task, 1: running, 2: out of tasks
+    int t = gg - ng; const int n_tasks = 2 * E.n_pending;
+    for (;;) {
+        if (phase == 0) {
+            for (;;) {
+                t += ng;
+                if (t >= n_tasks) { phase = 2; break; }
+                const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
+                const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
+                const int n = P.n_cols[slot]; const int sb = P.seed_begin[slot], se = P.seed_end[slot];
+                const int l_first = P.first_level[slot], l_last = P.last_level[slot];
+                const int32_t* se_edge = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol;
+                bool run = false;
+                C.seq = B.bases + rd0; C.seq_len = rdlen;
+                if (side == 0) {
+                    if (sb != 0 && l_first > 0) { run = true; C.start_seq = sb; C.start_level = l_first; C.start_z = (int)(G.edge_pack[se_edge[0]] & 255u); C.pos = false; C.start_node = G.level_node_off[l_first] + C.start_z; }
+                } else {
+                    if (se != rdlen - 1 && l_last + 1 < G.n_levels - 1) { run = true; C.start_seq = se + 1; C.start_level = l_last + 1; C.start_z = (int)((G.edge_pack[se_edge[n - 1]] >> 8) & 255u); C.pos = true; C.start_node = G.level_node_off[l_last + 1] + C.start_z; }
+                }
+                if (!run) { if (g.lane == 0) { E.ext_rc[t] = 0; E.ext_n[t] = 0; E.ext_nlvl[t] = 0; } continue; }
+                gd_init<CFG>(C, S, st, g);
+                phase = 1; break;
+            }
+        }
+        if (__all_sync(0xffffffffu, phase == 2)) break;
+        if (phase == 1) {
+            int rc = gd_step<CFG>(C, S, st, g);
+            if (rc != 0) {
+                DpResult res; res.n_cols = 0; res.n_lvl = 0; res.far_y = 0;
+                if (rc == 1) rc = gd_finish<CFG>(C, st, g, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res);
+                if (g.lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; }
+                g.sync();
+                phase = 0;
+            }
+        }
+    }
+}
+
 // Kernel 1b: splice extensions into the pending chains, pad, score (one warp per pending chain).
 __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_finish(ExtParams E) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -341,11 +399,33 @@ template <class CFG> static cudaError_t launch_wd(ExtParams E, int n_sm, cudaStr
     k_extend_warp<CFG><<<grid, CFG::WARPS * 32, wd_slab_bytes<CFG>() * CFG::WARPS, stream>>>(E);
     return cudaGetLastError();
 }
-// tier 0: every task through the tiny configuration; tier 1 / 2: only the tasks the previous tier deferred, through the small / large one
-cudaError_t launch_extend_warp(const ExtParams& E0, int n_sm, int tier, cudaStream_t stream) {
+// cfg 0 / 1 / 2: tiny / small / large shared-memory configuration; only_deferred: run only the tasks an earlier tier deferred
+cudaError_t launch_extend_warp(const ExtParams& E0, int n_sm, int cfg, bool only_deferred, cudaStream_t stream) {
     if (E0.n_pending <= 0) return cudaSuccess;
-    ExtParams E = E0; E.only_deferred = tier > 0;
-    return tier == 0 ? launch_wd<WdTiny>(E, n_sm, stream) : tier == 1 ? launch_wd<WdSmall>(E, n_sm, stream) : launch_wd<WdLarge>(E, n_sm, stream);
+    ExtParams E = E0; E.only_deferred = only_deferred ? 1 : 0;
+    return cfg == 0 ? launch_wd<WdTiny>(E, n_sm, stream) : cfg == 1 ? launch_wd<WdSmall>(E, n_sm, stream) : launch_wd<WdLarge>(E, n_sm, stream);
+}
+
+template <class CFG> static int gd_occupancy_groups(int n_sm) {
+    size_t smem = gd_slab_bytes<CFG>() * CFG::WARPS * CFG::NG; int per_sm = 1;
+    if (cudaFuncSetAttribute(k_extend_group<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_group<CFG>, CFG::WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return n_sm * per_sm * CFG::WARPS * CFG::NG;
+}
+int gd_groups_for(int n_sm) { return gd_occupancy_groups<GdOct>(n_sm); }
+size_t gd_group_scratch_bytes() { return gd_hbm_bytes<GdOct>(); }
+cudaError_t launch_extend_group(const ExtParams& E0, int n_sm, cudaStream_t stream) {
+    if (E0.n_pending <= 0) return cudaSuccess;
+    typedef GdOct CFG;
+    ExtParams E = E0;
+    const int per_cta = CFG::WARPS * CFG::NG;
+    int groups = std::min(gd_occupancy_groups<CFG>(n_sm), E.n_gd_groups);
+    if (groups < per_cta) return cudaErrorInvalidConfiguration;
+    long long want = ((long long)2 * E.n_pending + per_cta - 1) / per_cta;
+    int grid = (int)std::min<long long>(want, (long long)(groups / per_cta)); if (grid < 1) grid = 1;
+    E.n_gd_groups = grid * per_cta;
+    k_extend_group<CFG><<<grid, CFG::WARPS * 32, gd_slab_bytes<CFG>() * per_cta, stream>>>(E);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {

@@ -10,7 +10,10 @@ cudaError_t upload_score_tables(const ScoreTables& t);
 cudaError_t launch_prepare(const ChainParams& P, cudaStream_t stream);
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream);
 cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream);
-cudaError_t launch_extend_warp(const ExtParams& E, int n_sm, int large, cudaStream_t stream);
+cudaError_t launch_extend_warp(const ExtParams& E, int n_sm, int cfg, bool only_deferred, cudaStream_t stream);
+cudaError_t launch_extend_group(const ExtParams& E, int n_sm, cudaStream_t stream);
+int gd_groups_for(int n_sm);
+size_t gd_group_scratch_bytes();
 int wd_warps_for(int n_sm);
 size_t wd_warp_scratch_bytes();
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream);

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <map>
@@ -193,6 +194,7 @@ struct Pipeline {
     PreparedBatch pb; DeviceBatch db; ChainScratch cs;
     DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch; int32_t ext_cap = 0; int32_t n_dp_threads = 0; int32_t n_wd_warps = 0;
     bool scalar_dp_only = false;   // test hook: run every extension through the scalar kernel
+    DevBuf gd_scratch; int32_t n_gd_groups = 0; bool group_dp = true; bool dp_trace = false;
     DevBuf is_table, phred_thr; double is_mean = -1, is_sd = -1, is_pen = 0; int32_t is_dmin = 0, is_n = 0;
     DevBuf pair_mapq, read_mapq, read_reverse, chosen_slot, pair_ll, pair_status, digest;
     DevBuf o_n_cols, o_level, o_edge, o_gchar, o_schar, o_fromseed, o_mapq; bool have_columns = false;
@@ -236,6 +238,11 @@ struct Pipeline {
         n_wd_warps = wd_warps_for(g->n_sm);
         wd_scratch.alloc((size_t)n_wd_warps * wd_warp_scratch_bytes());
         CUDA_OK(cudaMemsetAsync(wd_scratch.p, 0, wd_scratch.bytes, st));
+        n_gd_groups = gd_groups_for(g->n_sm);
+        gd_scratch.alloc((size_t)n_gd_groups * gd_group_scratch_bytes());
+        CUDA_OK(cudaMemsetAsync(gd_scratch.p, 0, gd_scratch.bytes, st));
+        if (getenv("HLALA_DP_TRACE")) dp_trace = true;
+        if (getenv("HLALA_NO_GROUP_DP")) group_dp = false;               // test hook: first tier = warp kernel, tiny configuration
         if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;            // test hooks (tools/scale_parity.py): the scalar DP only /
         if (allow_env_budget && getenv("HLALA_ALIGN_DUPLICATES")) dedup = false;   // align the chains k_prepare would skip
         // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
@@ -283,13 +290,24 @@ struct Pipeline {
             }
             ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = ext_edge.as<int32_t>(); E.ext_s = ext_s.as<uint8_t>(); E.ext_n = ext_n.as<int32_t>();
             E.ext_nlvl = ext_nlvl.as<int32_t>(); E.ext_rc = ext_rc.as<int32_t>(); E.dp_scratch = dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
-            E.wd_scratch = wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps;
+            E.wd_scratch = wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps; E.gd_scratch = gd_scratch.as<unsigned char>(); E.n_gd_groups = n_gd_groups;
             tic(1, st);
             if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
             else {
-                CUDA_OK(launch_extend_warp(E, g->n_sm, 0, st)); toc(st);
-                tic(4, st); CUDA_OK(launch_extend_warp(E, g->n_sm, 1, st)); CUDA_OK(launch_extend_warp(E, g->n_sm, 2, st)); toc(st);
-                tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4;
+                // cascade: 8-lane groups (every task) -> warp kernels with growing shared-memory capacities -> scalar kernel; each tier only
+                // re-runs what the previous one deferred for capacity
+                auto trace = [&](const char* what, cudaEvent_t a) {   // HLALA_DP_TRACE=1: time and deferral count of each tier (debug runs only)
+                    cudaEvent_t b; CUDA_OK(cudaEventCreate(&b)); CUDA_OK(cudaEventRecord(b, st)); CUDA_OK(cudaEventSynchronize(b)); float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+                    std::vector<int32_t> rc((size_t)2 * n_pending); ext_rc.download(rc.data(), rc.size(), st); CUDA_OK(cudaStreamSynchronize(st));
+                    long long nd = 0; for (int32_t v : rc) nd += (v == -100);
+                    fprintf(stderr, "[dp-trace] %-12s %8.2f ms, tasks %d, still deferred %lld\n", what, ms, 2 * n_pending, nd); cudaEventDestroy(b); CUDA_OK(cudaEventRecord(a, st)); };
+                cudaEvent_t tr0 = nullptr; if (dp_trace) { CUDA_OK(cudaEventCreate(&tr0)); CUDA_OK(cudaEventRecord(tr0, st)); }
+                if (group_dp) { CUDA_OK(launch_extend_group(E, g->n_sm, st)); launches += 1; if (dp_trace) trace("group8", tr0); }
+                toc(st);
+                tic(4, st); CUDA_OK(launch_extend_warp(E, g->n_sm, 0, group_dp, st)); if (dp_trace) trace("warp tiny", tr0);
+                CUDA_OK(launch_extend_warp(E, g->n_sm, 1, true, st)); if (dp_trace) trace("warp small", tr0);
+                CUDA_OK(launch_extend_warp(E, g->n_sm, 2, true, st)); if (dp_trace) trace("warp large", tr0); toc(st);
+                tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4; if (dp_trace) { trace("scalar", tr0); cudaEventDestroy(tr0); }
             }
             toc(st);
             tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 1;

@@ -54,6 +54,7 @@ struct ExtParams {
     int32_t* ext_n; int32_t* ext_nlvl; int32_t* ext_rc;   // [2 * n_pending]
     unsigned char* dp_scratch; int32_t n_dp_threads;   // scalar kernel: one slice per thread
     unsigned char* wd_scratch; int32_t n_wd_warps;     // warp kernel: one slice per warp
+    unsigned char* gd_scratch; int32_t n_gd_groups;    // group kernel: one slice per 8-lane group
     int32_t only_deferred;                              // scalar kernel: run only the tasks the warp kernel deferred
 };
 

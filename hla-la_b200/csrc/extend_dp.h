@@ -76,6 +76,10 @@ struct DpGraph {
 };
 
 struct DpResult { int32_t n_cols; int32_t n_lvl; int32_t far_y; };   // far_y: read coordinate of the end cell
+#ifdef HLALA_DP_STATS   // host-only instrumentation (tools/dp_stats.py): work per extension
+struct DpStats { long long ext, diags, touched, m1, m2, cells, diags_all_at_end, cand, max_td, max_m1; };
+inline DpStats& dp_stats() { static DpStats s = {}; return s; }
+#endif
 
 __host__ __device__ inline uint32_t dp_hash3(int x, int y, int z) { uint32_t h = (uint32_t)x * 0x9E3779B1u ^ (uint32_t)y * 0x85EBCA77u ^ (uint32_t)z * 0xC2B2AE3Du; h ^= h >> 15; return h; }
 
@@ -142,6 +146,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     for (int diag = 1; ; diag++) {
         if (diag - last_inc > 40) break;
         if (n_m1 == 0 && n_m2 == 0) break;      // nothing can be produced any more; the reference idles until the patience test fires
+#ifdef HLALA_DP_STATS
+        { DpStats& st = dp_stats(); st.diags++; st.m1 += n_m1; st.m2 += n_m2; if (n_m1 > st.max_m1) st.max_m1 = n_m1; bool all_end = true; for (int i = 0; i < n_m1; i++) all_end &= S.cells[m1[i]].y == end_seq; for (int i = 0; i < n_m2; i++) all_end &= S.cells[m2[i]].y == end_seq; st.diags_all_at_end += all_end; }
+#endif
         tgen++;
         if (tgen >= (1u << 19)) { for (int i = 0; i < DP_TDHASH_CAP; i++) S.tdhash[i] = 0; tgen = 1; }
         n_td = 0;
@@ -200,6 +207,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
               } }
         }
         if (status) break;
+#ifdef HLALA_DP_STATS
+        dp_stats().touched += n_td; if (n_td > dp_stats().max_td) dp_stats().max_td = n_td;
+#endif
         // ---- finalise touched cells in (x, y, z) order
         for (int i = 0; i < n_td; i++) {
             int j = i; const DpTouch& t = S.td[i];
@@ -252,6 +262,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
         int32_t* t2 = m2; m2 = m1; n_m2 = n_m1; m1 = mt; n_m1 = n_mt; mt = t2;
     }
     S.gens[1] = tgen;
+#ifdef HLALA_DP_STATS
+    dp_stats().ext++; dp_stats().cells += n_cells;
+#endif
     if (status) return status;
 
     // ---- end cell

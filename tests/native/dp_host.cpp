@@ -43,3 +43,6 @@ int dp_host_extend(void* hv, const uint8_t* seq, int seq_len, int start_seq, int
     return 0;
 }
 }
+#ifdef HLALA_DP_STATS
+extern "C" void dp_host_stats(long long* out) { DpStats& s = dp_stats(); out[0] = s.ext; out[1] = s.diags; out[2] = s.touched; out[3] = s.m1; out[4] = s.m2; out[5] = s.cells; out[6] = s.diags_all_at_end; out[7] = s.max_td; out[8] = s.max_m1; s = DpStats(); }
+#endif
