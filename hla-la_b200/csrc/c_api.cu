@@ -4,6 +4,8 @@
 #include "chain_params.h"
 #include "align_kernels.h"
 #include "typing_kernels.h"
+#include "seed_kernels.h"
+#include "../host/kmer_index.h"
 #include "../host/hla_typing.h"
 
 #include <algorithm>
@@ -71,6 +73,9 @@ struct hlala_graph {
     DevGraph d{};
     std::vector<std::unique_ptr<DevBuf>> bufs;
     template <class T> const T* up(const std::vector<T>& v) { bufs.emplace_back(new DevBuf()); bufs.back()->upload(v); return bufs.back()->as<T>(); }
+    // k-mer index (hlala_kmer_index_build)
+    std::unique_ptr<KmerIndex> kix; DevKmerIndex dkix{}; bool kix_on_gpu = false; std::vector<std::unique_ptr<DevBuf>> kbufs;
+    template <class T> const T* kup(const std::vector<T>& v) { kbufs.emplace_back(new DevBuf()); kbufs.back()->upload(v); return kbufs.back()->as<T>(); }
 };
 
 namespace {
@@ -415,10 +420,10 @@ int hlala_graph_to_gpu(hlala_graph_t* g, int device) {
             pack[e] = (uint32_t)(f - h.level_node_off[h.node_level[f]]) | ((uint32_t)(t - h.level_node_off[h.node_level[t]]) << 8) | ((uint32_t)h.edge_emis[e] << 16);
         }
         std::vector<int32_t> leo(h.level_edge_off); leo.resize((size_t)h.n_levels + 1, h.n_edges);
-        g->bufs.clear();
+        g->bufs.clear(); g->kbufs.clear(); g->kix_on_gpu = false;
         DevGraph& d = g->d;
         d.n_levels = h.n_levels; d.n_nodes = h.n_nodes; d.n_edges = h.n_edges; d.n_contigs = h.n_contigs;
-        d.level_node_off = g->up(h.level_node_off); d.level_edge_off = g->up(leo); d.edge_pack = g->up(pack); d.edge_ord = g->up(h.edge_ord);
+        d.level_node_off = g->up(h.level_node_off); d.level_edge_off = g->up(leo); d.edge_pack = g->up(pack); d.edge_ord = g->up(h.edge_ord); d.edge_from = g->up(h.edge_from); d.edge_to = g->up(h.edge_to);
         d.node_out_off = g->up(h.node_out_off); d.node_out = g->up(h.node_out); d.node_in_off = g->up(h.node_in_off); d.node_in = g->up(h.node_in);
         d.path_off = g->up(h.path_off); d.path_edges = g->up(h.path_edges); d.path_from = g->up(h.path_from); d.path_to = g->up(h.path_to);
         d.jump_fwd_off = g->up(h.jump_fwd_off); d.jump_fwd_path = g->up(h.jump_fwd_path); d.jump_bwd_off = g->up(h.jump_bwd_off); d.jump_bwd_path = g->up(h.jump_bwd_path);
@@ -746,5 +751,147 @@ int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], do
     for (int k = 0; k < 2; k++) { if (ms) ms[k] = t->ms[k]; if (launches) launches[k] = t->launches[k]; if (work) work[k] = t->work[k]; }
     return 0;
 }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k-mer seeding (reference seam B5 of SURVEY.md §8b)
+struct hlala_kmer_chains {
+    int64_t n_reads = 0, n_chains = 0, n_edges = 0, n_failed = 0;
+    DevBuf chain_off, read_status, begin, end, edge_off, edges;
+    double ms[3] = {0, 0, 0};
+};
+
+namespace {
+void upload_kmer_index(hlala_graph* g) {
+    if (g->kix_on_gpu) return;
+    const KmerIndex& x = *g->kix; const FlatGraph& h = g->h;
+    std::vector<int32_t> pf((size_t)x.n_pos), pt((size_t)x.n_pos);
+    for (int64_t p = 0; p < x.n_pos; p++) { pf[(size_t)p] = h.edge_from[x.pos_edges[(size_t)x.pos_edge_off[(size_t)p]]]; pt[(size_t)p] = h.edge_to[x.pos_edges[(size_t)x.pos_edge_off[(size_t)p + 1] - 1]]; }
+    g->kbufs.clear();
+    DevKmerIndex& d = g->dkix; d.k = x.k; d.ht_mask = x.ht_mask; d.n_kmers = x.n_kmers; d.n_pos = x.n_pos;
+    d.ht = g->kup(x.ht); d.kmer_bytes = g->kup(x.kmer_bytes); d.kmer_pos_off = g->kup(x.kmer_pos_off); d.pos_edge_off = g->kup(x.pos_edge_off);
+    d.pos_edges = g->kup(x.pos_edges); d.pos_from = g->kup(pf); d.pos_to = g->kup(pt);
+    CUDA_OK(cudaDeviceSynchronize());
+    g->kix_on_gpu = true;
+}
+} // namespace
+
+extern "C" {
+
+int hlala_kmer_index_build(hlala_graph_t* g, int k) {
+    if (!g) return fail(HLALA_E_ARG, "hlala_kmer_index_build: null graph");
+    return guarded([&]() {
+        std::unique_ptr<KmerIndex> x(new KmerIndex());
+        try { build_kmer_index(g->h, k, *x); } catch (const std::exception& e) { return fail(HLALA_E_ARG, e.what()); }
+        g->kix = std::move(x); g->kix_on_gpu = false; g->kbufs.clear();
+        if (g->on_gpu) { CUDA_OK(cudaSetDevice(g->device)); upload_kmer_index(g); }
+        return 0;
+    });
+}
+int hlala_kmer_index_dims(const hlala_graph_t* g, int32_t* k, int64_t* n_kmers, int64_t* n_pos, int64_t* n_edges) {
+    if (!g || !g->kix) return fail(HLALA_E_ARG, "hlala_kmer_index_dims: no k-mer index (call hlala_kmer_index_build)");
+    if (k) *k = g->kix->k; if (n_kmers) *n_kmers = g->kix->n_kmers; if (n_pos) *n_pos = g->kix->n_pos; if (n_edges) *n_edges = (int64_t)g->kix->pos_edges.size();
+    return 0;
+}
+int hlala_kmer_index_export(const hlala_graph_t* g, uint8_t* kmer_bytes, int64_t* pos_off, int64_t* edge_off, int32_t* edges) {
+    if (!g || !g->kix) return fail(HLALA_E_ARG, "hlala_kmer_index_export: no k-mer index (call hlala_kmer_index_build)");
+    const KmerIndex& x = *g->kix;
+    if (kmer_bytes) memcpy(kmer_bytes, x.kmer_bytes.data(), x.kmer_bytes.size());
+    if (pos_off) memcpy(pos_off, x.kmer_pos_off.data(), x.kmer_pos_off.size() * 8);
+    if (edge_off) memcpy(edge_off, x.pos_edge_off.data(), x.pos_edge_off.size() * 8);
+    if (edges) for (size_t i = 0; i < x.pos_edges.size(); i++) edges[i] = g->h.edge_ord[(size_t)x.pos_edges[i]];
+    return 0;
+}
+
+int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_kmer_chains_t** out) {
+    if (!g || !reads || !out) return fail(HLALA_E_ARG, "hlala_seed_kmers: null argument");
+    *out = nullptr;
+    if (reads->n_reads < 0 || (reads->n_reads > 0 && (!reads->read_off || !reads->bases))) return fail(HLALA_E_ARG, "hlala_seed_kmers: bad read batch");
+    if (!g->kix) return fail(HLALA_E_ARG, "hlala_seed_kmers: no k-mer index (call hlala_kmer_index_build)");
+    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
+    if (reads->n_reads >= ((int64_t)1 << 31) - 1) return fail(HLALA_E_ARG, "hlala_seed_kmers: at most 2^31-2 reads per call");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(g->device));
+        upload_kmer_index(g);
+        cudaStream_t st = 0;
+        std::unique_ptr<hlala_kmer_chains> R(new hlala_kmer_chains());
+        const int64_t nr = reads->n_reads; R->n_reads = nr;
+        const int64_t nb = nr ? reads->read_off[nr] : 0; int64_t maxL = 0;
+        for (int64_t r = 0; r < nr; r++) maxL = std::max<int64_t>(maxL, reads->read_off[r + 1] - reads->read_off[r]);
+        DevBuf d_off, d_bases, n_chains, recs, pool, counts, counters, chain_scratch, scan_scratch, ordered, ord_ne, temp;
+        std::vector<int64_t> off0(1, 0);
+        d_off.upload(nr ? reads->read_off : off0.data(), (size_t)nr + 1, st); d_bases.upload(reads->bases, (size_t)nb, st);
+        n_chains.alloc((size_t)std::max<int64_t>(nr, 1) * 4); R->read_status.alloc((size_t)std::max<int64_t>(nr, 1) * 4);
+        SeedParams P{}; P.g = g->d; P.ix = g->dkix; P.n_reads = nr; P.read_off = d_off.as<int64_t>(); P.bases = d_bases.as<uint8_t>();
+        P.ecap = (int32_t)std::max<int64_t>(512, 3 * maxL);
+        const int warps = (int)std::min<int64_t>(seed_warps_for(g->n_sm), std::max<int64_t>(SEED_WARPS, ((nr + SEED_WARPS - 1) / SEED_WARPS) * SEED_WARPS));
+        chain_scratch.alloc((size_t)warps * SEED_RC * (size_t)P.ecap * 4); scan_scratch.alloc((size_t)warps * seed_scan_scratch_ints() * 4);
+        P.chain_scratch = chain_scratch.as<int32_t>(); P.scan_scratch = scan_scratch.as<int32_t>();
+        P.read_n_chains = n_chains.as<int32_t>(); P.read_status = R->read_status.as<int32_t>();
+        counts.alloc(16); counters.alloc(16);
+        P.rec_count = counts.as<unsigned long long>(); P.edge_count = counts.as<unsigned long long>() + 1; P.counters = counters.as<int32_t>();
+        int64_t rec_cap = nr * 3 + 1024, edge_cap = nb * 3 + 65536;
+        cudaEvent_t e0, e1, e2; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaEventCreate(&e2));
+        unsigned long long cnt[2] = {0, 0}; int32_t ctr[4] = {0, 0, 0, 0};
+        for (int attempt = 0; ; attempt++) {
+            recs.alloc((size_t)rec_cap * sizeof(SeedChainRec)); pool.alloc((size_t)edge_cap * 4);
+            P.recs = recs.as<SeedChainRec>(); P.rec_cap = rec_cap; P.edge_pool = pool.as<int32_t>(); P.edge_cap = edge_cap;
+            CUDA_OK(cudaMemsetAsync(counts.p, 0, 16, st)); CUDA_OK(cudaMemsetAsync(counters.p, 0, 16, st));
+            CUDA_OK(cudaEventRecord(e0, st));
+            CUDA_OK(launch_seed_chains(P, g->n_sm, st));
+            CUDA_OK(cudaEventRecord(e1, st));
+            counts.download(cnt, 2, st); counters.download(ctr, 4, st);
+            CUDA_OK(cudaStreamSynchronize(st));
+            if (!ctr[2]) break;
+            if (attempt >= 8) return fail(HLALA_E_CAPACITY, "hlala_seed_kmers: chain output does not fit after 8 capacity doublings");
+            rec_cap = std::max<int64_t>(rec_cap * 2, (int64_t)cnt[0] + 1024); edge_cap = std::max<int64_t>(edge_cap * 2, (int64_t)cnt[1] + 65536);   // the counters keep counting past the capacity
+        }
+        R->n_failed = ctr[1];
+        // (read, order) order + contiguous edges as canonical ordinals
+        R->chain_off.alloc((size_t)(nr + 1) * 8);
+        size_t need = 0; CUDA_OK(seed_exclusive_scan_i32_to_i64(n_chains.as<int32_t>(), nr, R->chain_off.as<long long>(), nullptr, 0, &need, st));
+        temp.alloc(need + 16);
+        CUDA_OK(seed_exclusive_scan_i32_to_i64(n_chains.as<int32_t>(), nr, R->chain_off.as<long long>(), temp.p, need, &need, st));
+        long long total_chains = 0; CUDA_OK(cudaMemcpyAsync(&total_chains, R->chain_off.as<long long>() + nr, 8, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+        R->n_chains = total_chains;
+        ordered.alloc((size_t)std::max<long long>(total_chains, 1) * sizeof(SeedChainRec)); ord_ne.alloc((size_t)std::max<long long>(total_chains, 1) * 4);
+        CUDA_OK(launch_seed_order(recs.as<SeedChainRec>(), (long long)cnt[0], R->chain_off.as<long long>(), R->read_status.as<int32_t>(), ordered.as<SeedChainRec>(), ord_ne.as<int32_t>(), st));
+        R->edge_off.alloc((size_t)(total_chains + 1) * 8);
+        size_t need2 = 0; CUDA_OK(seed_exclusive_scan_i32_to_i64(ord_ne.as<int32_t>(), total_chains, R->edge_off.as<long long>(), nullptr, 0, &need2, st));
+        if (need2 > need) { temp.alloc(need2 + 16); }
+        CUDA_OK(seed_exclusive_scan_i32_to_i64(ord_ne.as<int32_t>(), total_chains, R->edge_off.as<long long>(), temp.p, std::max(need, need2), &need2, st));
+        long long total_edges = 0; CUDA_OK(cudaMemcpyAsync(&total_edges, R->edge_off.as<long long>() + total_chains, 8, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+        R->n_edges = total_edges;
+        R->begin.alloc((size_t)std::max<long long>(total_chains, 1) * 4); R->end.alloc((size_t)std::max<long long>(total_chains, 1) * 4); R->edges.alloc((size_t)std::max<long long>(total_edges, 1) * 4);
+        CUDA_OK(launch_seed_gather(g->d, ordered.as<SeedChainRec>(), total_chains, R->edge_off.as<long long>(), pool.as<int32_t>(), R->begin.as<int32_t>(), R->end.as<int32_t>(), R->edges.as<int32_t>(), st));
+        CUDA_OK(cudaEventRecord(e2, st)); CUDA_OK(cudaEventSynchronize(e2));
+        float f1 = 0, f2 = 0; CUDA_OK(cudaEventElapsedTime(&f1, e0, e1)); CUDA_OK(cudaEventElapsedTime(&f2, e1, e2));
+        R->ms[0] = f1; R->ms[1] = f2; R->ms[2] = 0;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        *out = R.release();
+        return 0;
+    });
+}
+int hlala_kmer_chains_dims(const hlala_kmer_chains_t* c, int64_t* n_reads, int64_t* n_chains, int64_t* n_edges, int64_t* n_failed_reads) {
+    if (!c) return fail(HLALA_E_ARG, "hlala_kmer_chains_dims: null result");
+    if (n_reads) *n_reads = c->n_reads; if (n_chains) *n_chains = c->n_chains; if (n_edges) *n_edges = c->n_edges; if (n_failed_reads) *n_failed_reads = c->n_failed;
+    return 0;
+}
+int hlala_kmer_chains_fetch(const hlala_kmer_chains_t* c, int64_t* chain_off, int32_t* read_status, int32_t* seq_begin, int32_t* seq_end, int64_t* edge_off, int32_t* edges) {
+    if (!c) return fail(HLALA_E_ARG, "hlala_kmer_chains_fetch: null result");
+    return guarded([&]() {
+        if (chain_off) c->chain_off.download(chain_off, (size_t)c->n_reads + 1); if (read_status) c->read_status.download(read_status, (size_t)c->n_reads);
+        if (seq_begin) c->begin.download(seq_begin, (size_t)c->n_chains); if (seq_end) c->end.download(seq_end, (size_t)c->n_chains);
+        if (edge_off) c->edge_off.download(edge_off, (size_t)c->n_chains + 1); if (edges) c->edges.download(edges, (size_t)c->n_edges);
+        CUDA_OK(cudaStreamSynchronize(0));
+        return 0;
+    });
+}
+int hlala_kmer_chains_timing(const hlala_kmer_chains_t* c, double ms[2]) {
+    if (!c || !ms) return fail(HLALA_E_ARG, "hlala_kmer_chains_timing: null argument");
+    ms[0] = c->ms[0]; ms[1] = c->ms[1]; return 0;
+}
+void hlala_kmer_chains_free(hlala_kmer_chains_t* c) { delete c; }
 
 } // extern "C"

@@ -185,6 +185,35 @@ int hlala_typer_result_call(const hlala_typer_t* t, int locus, const char** alle
  * work[0] = sum over loci of C*R*observations (select+add steps), work[1] = sum over loci of C(C+1)/2 * R (logAvg evaluations). */
 int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], double work[2]);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * k-mer seeding. Reference seam B5 of SURVEY.md §8b (no live caller in the reference: HLA-LA.cpp:230,1439 are commented out):
+ *   hlala_kmer_index_build    GraphAndEdgeIndex::GraphAndEdgeIndex(Graph*, int k) -> Index()   Graph/GraphAndEdgeIndex.cpp:18-26, 428-959
+ *   hlala_kmer_index_export   getIndexedkMers() + queryIndex() over the whole index            Graph/GraphAndEdgeIndex.cpp:28-38, 986-997
+ *   hlala_seed_kmers          std::vector<kMerEdgeChain*> findChains(std::string sequence)     Graph/GraphAndEdgeIndex.cpp:39-356
+ * The index is built on the host from the flat graph and uploaded; hlala_seed_kmers runs on the GPU only. A read whose working set
+ * exceeds the kernel's capacities (128 running chains, chains of 3 x the longest read) gets read_status HLALA_E_CAPACITY and no chains. */
+int hlala_kmer_index_build(hlala_graph_t* g, int k);
+int hlala_kmer_index_dims(const hlala_graph_t* g, int32_t* k, int64_t* n_kmers, int64_t* n_positions, int64_t* n_edges);
+/* k-mers ascending ([n_kmers * k] bytes, std::map<std::string> order), pos_off [n_kmers+1], edge_off [n_positions+1], edges as canonical
+ * ordinals; positions of a k-mer in the order Index() records them. Any pointer may be NULL. */
+int hlala_kmer_index_export(const hlala_graph_t* g, uint8_t* kmer_bytes, int64_t* pos_off, int64_t* edge_off, int32_t* edges);
+
+typedef struct {
+    int64_t n_reads;
+    const int64_t* read_off;   /* [n_reads+1] into bases */
+    const uint8_t* bases;      /* ASCII, the string handed to findChains */
+} hlala_read_batch_t;
+typedef struct hlala_kmer_chains hlala_kmer_chains_t;   /* result, device resident, owned by the library */
+int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_kmer_chains_t** out);
+int hlala_kmer_chains_dims(const hlala_kmer_chains_t* c, int64_t* n_reads, int64_t* n_chains, int64_t* n_edges, int64_t* n_failed_reads);
+/* chains of read r: [chain_off[r], chain_off[r+1]) in the order findChains returns them; per chain sequence_begin / sequence_end and
+ * traversedEdges = edges[edge_off[c] .. edge_off[c+1]) as canonical edge ordinals. Caller-allocated host arrays, any may be NULL. */
+int hlala_kmer_chains_fetch(const hlala_kmer_chains_t* c, int64_t* chain_off, int32_t* read_status, int32_t* seq_begin, int32_t* seq_end,
+                            int64_t* edge_off, int32_t* edges);
+/* device time (CUDA events) of the call that produced c: ms[0] k_seed_chains, ms[1] ordering + edge gather */
+int hlala_kmer_chains_timing(const hlala_kmer_chains_t* c, double ms[2]);
+void hlala_kmer_chains_free(hlala_kmer_chains_t* c);
+
 #ifdef __cplusplus
 }
 #endif

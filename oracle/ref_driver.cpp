@@ -11,6 +11,7 @@
 //                                                                   mapper/processBAM.cpp:3019, extensionAligner.cpp:186,52
 //   per pair              processBAM::alignOneReadPair             mapper/processBAM.cpp:3129
 //   typing                gene filter (processBAM.cpp:2427-2481) + HLATyper::HLATypeInference (hla/HLATyper.cpp:933)
+//   k-mer seeding         GraphAndEdgeIndex::Index / queryIndex / findChains   Graph/GraphAndEdgeIndex.cpp:428,986,39
 //
 // Two things are pinned so that "bit-exact" is defined at all (SURVEY.md §0 finding 3, §7 hard parts):
 //  * std::set<Node*>/std::set<Edge*> iterate in pointer order. While the graph is being built every
@@ -35,6 +36,7 @@
 #include "mapper/processBAM.h"
 #include "hla/HLATyper.h"
 #include "Graph/Graph.h"
+#include "Graph/GraphAndEdgeIndex.h"
 #include "Utilities.h"
 
 // ---- allocation: bump arena while loading, malloc otherwise
@@ -335,6 +337,63 @@ int hlala_ref_type(void* h, const char* prg_dir, long long n_reads, const int64_
     Driver* d = (Driver*)h;
     Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
     return guarded([&]() { return d->run_type(b, prg_dir, is_mean, is_sd, out_dir, g_dir, threads, n_used, seconds); });
+}
+
+// ---- k-mer seeding (GraphAndEdgeIndex; dormant in the reference's own main(), HLA-LA.cpp:230,1439)
+struct KmerRef {
+    GraphAndEdgeIndex* gi = nullptr; int k = 0;
+    std::vector<int64_t> r_chain_off; std::vector<int32_t> r_begin, r_end; std::vector<int64_t> r_edge_off; std::vector<int32_t> r_edges;
+};
+
+void* hlala_ref_kmer_index(void* h, int k) {
+    Driver* d = (Driver*)h; KmerRef* R = nullptr;
+    int rc = guarded([&]() { R = new KmerRef(); R->k = k; R->gi = new GraphAndEdgeIndex(d->graph(), k); return 0; });
+    return rc == 0 ? R : nullptr;
+}
+// the whole index: k-mers in std::map order, positions in the order Index() recorded them, edges as canonical ordinals
+int hlala_ref_kmer_dump_sizes(void* h, void* idx, long long* n_kmers, long long* n_pos, long long* n_edges) {
+    KmerRef* R = (KmerRef*)idx;
+    return guarded([&]() {
+        std::vector<std::string> ks = R->gi->getIndexedkMers(); *n_kmers = (long long)ks.size(); *n_pos = 0; *n_edges = 0;
+        for (auto& s : ks) { std::vector<kMerInGraphSpec> v = R->gi->queryIndex(s); *n_pos += (long long)v.size(); for (auto& p : v) *n_edges += (long long)p.traversedEdges.size(); }
+        return 0; });
+}
+int hlala_ref_kmer_dump(void* h, void* idx, uint8_t* kmer_bytes, int64_t* pos_off, int64_t* edge_off, int32_t* edges) {
+    Driver* d = (Driver*)h; KmerRef* R = (KmerRef*)idx;
+    return guarded([&]() {
+        std::vector<std::string> ks = R->gi->getIndexedkMers(); int64_t np = 0, ne = 0;
+        for (size_t i = 0; i < ks.size(); i++) {
+            memcpy(kmer_bytes + i * (size_t)R->k, ks[i].data(), (size_t)R->k); pos_off[i] = np;
+            std::vector<kMerInGraphSpec> v = R->gi->queryIndex(ks[i]);
+            for (auto& p : v) { edge_off[np++] = ne; for (Edge* e : p.traversedEdges) edges[ne++] = d->edge_ord.at(e); }
+        }
+        pos_off[ks.size()] = np; edge_off[np] = ne; return 0; });
+}
+// findChains over a batch of sequences; results are kept in the handle until fetched
+int hlala_ref_find_chains(void* h, void* idx, long long n_reads, const int64_t* read_off, const uint8_t* bases, long long* n_chains, long long* n_edges, double* seconds) {
+    Driver* d = (Driver*)h; KmerRef* R = (KmerRef*)idx;
+    return guarded([&]() {
+        R->r_chain_off.assign(1, 0); R->r_begin.clear(); R->r_end.clear(); R->r_edge_off.assign(1, 0); R->r_edges.clear();
+        auto t0 = std::chrono::steady_clock::now();
+        for (long long r = 0; r < n_reads; r++) {
+            std::string seq((const char*)bases + read_off[r], (size_t)(read_off[r + 1] - read_off[r]));
+            std::vector<kMerEdgeChain*> ch = R->gi->findChains(seq);
+            for (kMerEdgeChain* c : ch) {
+                R->r_begin.push_back(c->sequence_begin); R->r_end.push_back(c->sequence_end);
+                for (Edge* e : c->traversedEdges) R->r_edges.push_back(d->edge_ord.at(e));
+                R->r_edge_off.push_back((int64_t)R->r_edges.size());
+                delete c;
+            }
+            R->r_chain_off.push_back((int64_t)R->r_begin.size());
+        }
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *n_chains = (long long)R->r_begin.size(); *n_edges = (long long)R->r_edges.size(); return 0; });
+}
+int hlala_ref_find_chains_fetch(void* idx, int64_t* chain_off, int32_t* begin, int32_t* end, int64_t* edge_off, int32_t* edges) {
+    KmerRef* R = (KmerRef*)idx;
+    memcpy(chain_off, R->r_chain_off.data(), R->r_chain_off.size() * 8); memcpy(begin, R->r_begin.data(), R->r_begin.size() * 4); memcpy(end, R->r_end.data(), R->r_end.size() * 4);
+    memcpy(edge_off, R->r_edge_off.data(), R->r_edge_off.size() * 8); memcpy(edges, R->r_edges.data(), R->r_edges.size() * 4);
+    return 0;
 }
 
 } // extern "C"

@@ -135,6 +135,34 @@ class Ref:
         return dict(n_used=n_used.value, seconds=sec.value)
 
 
+
+    # ---- k-mer seeding (GraphAndEdgeIndex)
+    def kmer_index(self, k):
+        L = self.lib; L.hlala_ref_kmer_index.restype = C.c_void_p
+        idx = C.c_void_p(L.hlala_ref_kmer_index(self.h, C.c_int(k)))
+        if not idx:
+            raise RuntimeError("k-mer index failed: %s" % L.hlala_ref_last_error().decode())
+        self.kidx = idx; self.k = k
+        return idx
+
+    def kmer_dump(self):
+        nk = C.c_longlong(); npos = C.c_longlong(); ne = C.c_longlong()
+        self._chk(self.lib.hlala_ref_kmer_dump_sizes(self.h, self.kidx, C.byref(nk), C.byref(npos), C.byref(ne)))
+        o = dict(kmers=np.zeros((nk.value, self.k), np.uint8), pos_off=np.zeros(nk.value + 1, np.int64), edge_off=np.zeros(npos.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32))
+        self._chk(self.lib.hlala_ref_kmer_dump(self.h, self.kidx, p(o["kmers"]), p(o["pos_off"]), p(o["edge_off"]), p(o["edges"])))
+        o["edges"] = o["edges"][:ne.value]
+        return o
+
+    def find_chains(self, read_off, bases):
+        nr = len(read_off) - 1; nc = C.c_longlong(); ne = C.c_longlong(); sec = C.c_double()
+        self._chk(self.lib.hlala_ref_find_chains(self.h, self.kidx, C.c_longlong(nr), p(read_off), p(bases), C.byref(nc), C.byref(ne), C.byref(sec)))
+        o = dict(chain_off=np.zeros(nr + 1, np.int64), begin=np.zeros(max(nc.value, 1), np.int32), end=np.zeros(max(nc.value, 1), np.int32),
+                 edge_off=np.zeros(nc.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32))
+        self._chk(self.lib.hlala_ref_find_chains_fetch(self.kidx, p(o["chain_off"]), p(o["begin"]), p(o["end"]), p(o["edge_off"]), p(o["edges"])))
+        o["begin"] = o["begin"][:nc.value]; o["end"] = o["end"][:nc.value]; o["edges"] = o["edges"][:ne.value]; o["seconds"] = sec.value
+        return o
+
+
 class Oracle(Ref):
     """oracle/build/libhlala_oracle.so: the plain C++ restatement (oracle/hlala_oracle.cpp). Same interface as Ref."""
 
@@ -194,6 +222,80 @@ class OracleTyping:
     def close(self):
         if self.h:
             self.lib.hlala_oracle_type_free(self.h); self.h = None
+
+
+class OracleKmer:
+    """oracle/hlala_oracle_kmer.cpp: restatement of GraphAndEdgeIndex (Index + findChains) on exported graph arrays. Same methods as Ref's k-mer part."""
+
+    def __init__(self, graph, k):
+        L = self.lib = C.CDLL(LIB_ORACLE)
+        L.hlala_oracle_kmer_open.restype = C.c_void_p; L.hlala_oracle_kmer_last_error.restype = C.c_char_p
+        self.k = k
+        nl = np.ascontiguousarray(graph["node_level"], np.int32); ef = np.ascontiguousarray(graph["edge_from"], np.int32)
+        et = np.ascontiguousarray(graph["edge_to"], np.int32); em = np.ascontiguousarray(graph["edge_emis"], np.uint8)
+        self.kidx = C.c_void_p(L.hlala_oracle_kmer_open(C.c_longlong(len(nl)), p(nl), C.c_longlong(len(ef)), p(ef), p(et), p(em), C.c_int(k)))
+        if not self.kidx:
+            raise RuntimeError("oracle k-mer index failed: %s" % L.hlala_oracle_kmer_last_error().decode())
+
+    def close(self):
+        if self.kidx:
+            self.lib.hlala_oracle_kmer_free(self.kidx); self.kidx = None
+
+    def kmer_dump(self):
+        nk = C.c_longlong(); npos = C.c_longlong(); ne = C.c_longlong()
+        self.lib.hlala_oracle_kmer_dump_sizes(self.kidx, C.byref(nk), C.byref(npos), C.byref(ne))
+        o = dict(kmers=np.zeros((nk.value, self.k), np.uint8), pos_off=np.zeros(nk.value + 1, np.int64), edge_off=np.zeros(npos.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32))
+        self.lib.hlala_oracle_kmer_dump(self.kidx, p(o["kmers"]), p(o["pos_off"]), p(o["edge_off"]), p(o["edges"]))
+        o["edges"] = o["edges"][:ne.value]
+        return o
+
+    def find_chains(self, read_off, bases):
+        nr = len(read_off) - 1; nc = C.c_longlong(); ne = C.c_longlong(); sec = C.c_double()
+        if self.lib.hlala_oracle_find_chains(self.kidx, C.c_longlong(nr), p(read_off), p(bases), C.byref(nc), C.byref(ne), C.byref(sec)) != 0:
+            raise RuntimeError("oracle findChains failed: %s" % self.lib.hlala_oracle_kmer_last_error().decode())
+        o = dict(chain_off=np.zeros(nr + 1, np.int64), begin=np.zeros(max(nc.value, 1), np.int32), end=np.zeros(max(nc.value, 1), np.int32),
+                 edge_off=np.zeros(nc.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32))
+        self.lib.hlala_oracle_find_chains_fetch(self.kidx, p(o["chain_off"]), p(o["begin"]), p(o["end"]), p(o["edge_off"]), p(o["edges"]))
+        o["begin"] = o["begin"][:nc.value]; o["end"] = o["end"][:nc.value]; o["edges"] = o["edges"][:ne.value]; o["seconds"] = sec.value
+        return o
+
+
+def walk_reads(graph, n, length, seed, err=0.01, random_frac=0.05, short_frac=0.02):
+    """Sequences for the k-mer seeding tests: random walks through the graph (graph arrays in canonical order) spelling `length` bases,
+    with substitutions at rate err; a few random sequences and a few shorter than any k. Returns (read_off int64, bases uint8)."""
+    rng = np.random.RandomState(seed)
+    ef = graph["edge_from"]; et = graph["edge_to"]; em = graph["edge_emis"]; nn = len(graph["node_level"])
+    order = np.argsort(ef, kind="stable"); starts = np.searchsorted(ef[order], np.arange(nn + 1))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs = []
+    for i in range(n):
+        u = rng.rand()
+        if u < short_frac:
+            seqs.append(acgt[rng.randint(0, 4, rng.randint(0, 6))]); continue
+        if u < short_frac + random_frac:
+            seqs.append(acgt[rng.randint(0, 4, length)]); continue
+        node = rng.randint(0, nn); out = []
+        while len(out) < length:
+            a, b = starts[node], starts[node + 1]
+            if a == b:
+                break
+            e = order[a + rng.randint(0, b - a)]
+            if em[e] != ord("_"):
+                out.append(em[e])
+            node = et[e]
+        s = np.array(out, np.uint8)
+        if len(s):
+            m = rng.rand(len(s)) < err
+            s[m] = acgt[rng.randint(0, 4, int(m.sum()))]
+        seqs.append(s)
+    off = np.zeros(n + 1, np.int64); off[1:] = np.cumsum([len(s) for s in seqs])
+    bases = np.concatenate(seqs).astype(np.uint8) if off[-1] else np.zeros(1, np.uint8)
+    return off, np.ascontiguousarray(bases)
+
+
+def same_chains(a, b):
+    """findChains results equal, order included"""
+    return all(a[k].shape == b[k].shape and (a[k] == b[k]).all() for k in ("chain_off", "begin", "end", "edge_off", "edges"))
 
 
 _REF_CACHE = {}
@@ -326,6 +428,39 @@ class Product:
         self._chk(self.lib.hlala_align_pairs(self.g, C.byref(sb), C.c_double(is_mean), C.c_double(is_sd), C.byref(po), p(bpl) if want_levels else None))
         o["bases_per_level"] = bpl
         return o
+
+
+
+    # ---- k-mer seeding
+    def kmer_index(self, k):
+        self._chk(self.lib.hlala_kmer_index_build(self.g, C.c_int(k)))
+        self.k = k
+
+    def kmer_dump(self):
+        nk = C.c_int64(); npos = C.c_int64(); ne = C.c_int64(); k = C.c_int32()
+        self._chk(self.lib.hlala_kmer_index_dims(self.g, C.byref(k), C.byref(nk), C.byref(npos), C.byref(ne)))
+        o = dict(kmers=np.zeros((nk.value, k.value), np.uint8), pos_off=np.zeros(nk.value + 1, np.int64), edge_off=np.zeros(npos.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32))
+        self._chk(self.lib.hlala_kmer_index_export(self.g, p(o["kmers"]), p(o["pos_off"]), p(o["edge_off"]), p(o["edges"])))
+        o["edges"] = o["edges"][:ne.value]
+        return o
+
+    def find_chains(self, read_off, bases):
+        class RB(C.Structure):
+            _fields_ = [("n_reads", C.c_int64), ("read_off", C.c_void_p), ("bases", C.c_void_p)]
+        rb = RB(); rb.n_reads = len(read_off) - 1; rb.read_off = read_off.ctypes.data; rb.bases = bases.ctypes.data
+        res = C.c_void_p()
+        self._chk(self.lib.hlala_seed_kmers(self.g, C.byref(rb), C.byref(res)))
+        try:
+            nr = C.c_int64(); nc = C.c_int64(); ne = C.c_int64(); nf = C.c_int64()
+            self._chk(self.lib.hlala_kmer_chains_dims(res, C.byref(nr), C.byref(nc), C.byref(ne), C.byref(nf)))
+            o = dict(chain_off=np.zeros(nr.value + 1, np.int64), status=np.zeros(max(nr.value, 1), np.int32), begin=np.zeros(max(nc.value, 1), np.int32), end=np.zeros(max(nc.value, 1), np.int32),
+                     edge_off=np.zeros(nc.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32), n_failed=nf.value)
+            self._chk(self.lib.hlala_kmer_chains_fetch(res, p(o["chain_off"]), p(o["status"]), p(o["begin"]), p(o["end"]), p(o["edge_off"]), p(o["edges"])))
+            ms = (C.c_double * 2)(); self._chk(self.lib.hlala_kmer_chains_timing(res, ms)); o["ms"] = list(ms)
+            o["begin"] = o["begin"][:nc.value]; o["end"] = o["end"][:nc.value]; o["edges"] = o["edges"][:ne.value]; o["status"] = o["status"][:nr.value]
+            return o
+        finally:
+            self.lib.hlala_kmer_chains_free(res)
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p)
