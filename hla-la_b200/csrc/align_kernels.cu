@@ -213,7 +213,7 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     extern __shared__ __align__(16) unsigned char smem[];
     const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * CFG::WARPS + warp; const int nw = gridDim.x * CFG::WARPS;
+    const int gw = blockIdx.x * CFG::WARPS + warp;
     if (gw >= E.n_wd_warps) return;
     WdSlab S = wd_carve<CFG>(smem + (size_t)warp * wd_slab_bytes<CFG>());
     unsigned char* hb = E.wd_scratch + (size_t)gw * wd_hbm_bytes();
@@ -223,13 +223,16 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     dg.jump_fwd_off = G.jump_fwd_off; dg.jump_fwd_path = G.jump_fwd_path; dg.jump_bwd_off = G.jump_bwd_off; dg.jump_bwd_path = G.jump_bwd_path;
     dg.adj4 = G.adj4; dg.out_adj4 = G.out_adj4; dg.in_adj4 = G.in_adj4; dg.jf4 = G.jf4; dg.jb4 = G.jb4; dg.node_gapflags = G.node_gapflags;
     WdCtx C; C.G = &dg; C.cells = (DpCell*)hb; C.hash = (uint32_t*)(hb + sizeof(DpCell) * (size_t)DP_CELL_CAP); C.gens = C.hash + DP_HASH_CAP;
-    for (int t = gw; t < 2 * E.n_pending; t += nw) {
+    const int n_in = E.in_list ? *E.in_count : 2 * E.n_pending;
+    for (;;) {
+        int ti = 0; if (lane == 0) ti = atomicAdd(E.pop, 1); ti = __shfl_sync(0xffffffffu, ti, 0);
+        if (ti >= n_in) break;
+        const int t = E.in_list ? E.in_list[ti] : ti;
         const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
         const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
         const int n = P.n_cols[slot]; const int sb = P.seed_begin[slot], se = P.seed_end[slot];
         const int l_first = P.first_level[slot], l_last = P.last_level[slot];
         const int32_t* se_edge = P.c_edge + (size_t)(slot - P.slot_base) * P.maxcol;
-        if (E.only_deferred && E.ext_rc[t] != DP_DEFER) continue;
         DpResult res; res.n_cols = 0; res.n_lvl = 0; res.far_y = 0; int rc = 0; bool run = false;
         C.seq = B.bases + rd0; C.seq_len = rdlen;
         if (side == 0) {
@@ -238,7 +241,7 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
             if (se != rdlen - 1 && l_last + 1 < G.n_levels - 1) { run = true; C.start_seq = se + 1; C.start_level = l_last + 1; C.start_z = (int)((G.edge_pack[se_edge[n - 1]] >> 8) & 255u); C.pos = true; C.start_node = G.level_node_off[l_last + 1] + C.start_z; }
         }
         if (run) rc = wd_extend<CFG>(C, S, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res, lane);
-        if (lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; }
+        if (lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; if (rc == DP_DEFER) E.out_list[atomicAdd(E.out_count, 1)] = t; }
         __syncwarp();
     }
 }
@@ -251,7 +254,7 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
     constexpr int GW = CFG::GW, NG = CFG::NG;
     const int gcta = threadIdx.x / GW;                               // group inside the CTA
-    const int gg = blockIdx.x * (CFG::WARPS * NG) + gcta; const int ng = gridDim.x * CFG::WARPS * NG;
+    const int gg = blockIdx.x * (CFG::WARPS * NG) + gcta;
     Grp<GW> g; g.lane = threadIdx.x % GW; g.shift = ((threadIdx.x & 31) / GW) * GW; g.mask = (GW == 32) ? 0xffffffffu : (((1u << (GW & 31)) - 1u) << g.shift);
     GdSlab S = gd_carve<CFG>(smem + (size_t)gcta * gd_slab_bytes<CFG>());
     unsigned char* hb = E.gd_scratch + (size_t)gg * gd_hbm_bytes<CFG>();
@@ -263,11 +266,12 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     WdCtx C; C.G = &dg; C.cells = (DpCell*)hb; C.hash = (uint32_t*)(hb + sizeof(DpCell) * (size_t)CFG::CELLS); C.gens = C.hash + CFG::HASH;
     C.seq = nullptr; C.seq_len = 0; C.start_seq = C.start_level = C.start_z = C.start_node = 0; C.pos = false;
     GdState st{}; int phase = (gg < E.n_gd_groups) ? 0 : 2;        // 0: needs a task, 1: running, 2: out of tasks
-    int t = gg - ng; const int n_tasks = 2 * E.n_pending;
+    int t = 0; const int n_tasks = 2 * E.n_pending;
     for (;;) {
         if (phase == 0) {
             for (;;) {
-                t += ng;
+                if (g.lane == 0) t = atomicAdd(E.pop, 1);
+                t = g.shfl(t, 0);
                 if (t >= n_tasks) { phase = 2; break; }
                 const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
                 const int r = B.slot_read[slot]; const int64_t rd0 = B.read_off[r]; const int rdlen = (int)(B.read_off[r + 1] - rd0);
@@ -292,7 +296,7 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
             if (rc != 0) {
                 DpResult res; res.n_cols = 0; res.n_lvl = 0; res.far_y = 0;
                 if (rc == 1) rc = gd_finish<CFG>(C, st, g, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res);
-                if (g.lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; }
+                if (g.lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; if (rc == DP_DEFER) E.out_list[atomicAdd(E.out_count, 1)] = t; }
                 g.sync();
                 phase = 0;
             }

@@ -14,7 +14,9 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <chrono>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -31,11 +33,16 @@ struct CudaError : std::runtime_error { explicit CudaError(const std::string& m)
 #define CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
 
 struct DevBuf {
-    void* p = nullptr; size_t bytes = 0;
+    void* p = nullptr; size_t bytes = 0, cap = 0; bool fresh = false;   // fresh: the last alloc() returned new (uninitialised) memory
     DevBuf() {}
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { if (p) cudaFree(p); }
-    void alloc(size_t n) { if (p) { cudaFree(p); p = nullptr; } bytes = n; if (n) CUDA_OK(cudaMalloc(&p, n)); }
+    // grow-only: a buffer that is large enough is reused, so that a workspace kept across calls does not pay cudaMalloc/cudaFree again
+    void alloc(size_t n) {
+        if (n <= cap && p) { bytes = n; fresh = false; return; }
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        bytes = n; fresh = true; if (n) { CUDA_OK(cudaMalloc(&p, n)); cap = n; }
+    }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
     template <class T> void upload(const T* h, size_t count, cudaStream_t st = 0) { alloc(count * sizeof(T)); if (count) CUDA_OK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st)); }
     template <class T> void upload(const std::vector<T>& v, cudaStream_t st = 0) { upload(v.data(), v.size(), st); }
@@ -73,6 +80,8 @@ struct hlala_graph {
     DevGraph d{};
     std::vector<std::unique_ptr<DevBuf>> bufs;
     template <class T> const T* up(const std::vector<T>& v) { bufs.emplace_back(new DevBuf()); bufs.back()->upload(v); return bufs.back()->as<T>(); }
+    // workspace of hlala_align_pairs kept across calls (device buffers are grow-only), one call at a time per handle
+    std::shared_ptr<void> ws; std::mutex ws_mu;
     // k-mer index (hlala_kmer_index_build)
     std::unique_ptr<KmerIndex> kix; DevKmerIndex dkix{}; bool kix_on_gpu = false; std::vector<std::unique_ptr<DevBuf>> kbufs;
     template <class T> const T* kup(const std::vector<T>& v) { kbufs.emplace_back(new DevBuf()); kbufs.back()->upload(v); return kbufs.back()->as<T>(); }
@@ -133,18 +142,41 @@ int check_batch(const hlala_seed_batch_t* b) {
     return 0;
 }
 
-struct ChainScratch {
-    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, c_edge, c_schar, c_fromseed, error_count, id_first, id_last, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count;
-    void alloc(int32_t n_chains, int32_t wave_chains, int32_t maxcol) {
-        size_t nc = (size_t)std::max(n_chains, 1); size_t wc = (size_t)std::max(wave_chains, 1);
+struct ChainScratch {   // per-chain results of the whole batch
+    DevBuf status, n_cols, seed_begin, seed_end, ll, first_level, last_level, error_count, id_first, id_last;
+    void alloc(int32_t n_chains) {
+        size_t nc = (size_t)std::max(n_chains, 1);
         status.alloc(nc * 4); n_cols.alloc(nc * 4); seed_begin.alloc(nc * 4); seed_end.alloc(nc * 4); ll.alloc(nc * 8); first_level.alloc(nc * 4); last_level.alloc(nc * 4);
-        c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol); error_count.alloc(4);
-        id_first.alloc(nc * 4); id_last.alloc(nc * 4); pending_slots.alloc(nc * 4); pending_count.alloc(4); todo_slots.alloc(nc * 4); todo_count.alloc(4); defer_slots.alloc(nc * 4); defer_count.alloc(4);
+        error_count.alloc(4); id_first.alloc(nc * 4); id_last.alloc(nc * 4);
     }
     void fill(ChainParams& P) {
         P.status = status.as<int32_t>(); P.n_cols = n_cols.as<int32_t>(); P.seed_begin = seed_begin.as<int32_t>(); P.seed_end = seed_end.as<int32_t>(); P.ll = ll.as<double>();
-        P.first_level = first_level.as<int32_t>(); P.last_level = last_level.as<int32_t>(); P.c_edge = c_edge.as<int32_t>(); P.c_schar = c_schar.as<uint8_t>(); P.c_fromseed = c_fromseed.as<uint8_t>();
+        P.first_level = first_level.as<int32_t>(); P.last_level = last_level.as<int32_t>();
         P.error_count = error_count.as<int32_t>(); P.id_first = id_first.as<int32_t>(); P.id_last = id_last.as<int32_t>();
+    }
+};
+
+// One in-flight wave: its column scratch, work lists, extension buffers, DP working memory and stream. Waves alternate between the
+// lanes, so the low-occupancy tail of one wave's extension cascade overlaps the next wave's chain kernel and first DP tier.
+struct Lane {
+    DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count;
+    DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch, gd_scratch; int32_t ext_cap = 0;
+    DevBuf q_ctr, q_a, q_b;   // task queues of the extension cascade (counters, two ping-pong lists of deferred tasks)
+    int32_t* n_pending_host = nullptr; cudaStream_t stream = nullptr; cudaEvent_t front_done = nullptr, done = nullptr;
+    Lane() {}
+    Lane(const Lane&) = delete; Lane& operator=(const Lane&) = delete;
+    ~Lane() { if (n_pending_host) cudaFreeHost(n_pending_host); if (stream) cudaStreamDestroy(stream); if (front_done) cudaEventDestroy(front_done); if (done) cudaEventDestroy(done); }
+    void alloc(int32_t wave_chains, int32_t maxcol, size_t dp_bytes, size_t wd_bytes, size_t gd_bytes) {
+        size_t wc = (size_t)std::max(wave_chains, 1);
+        c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol);
+        pending_slots.alloc(wc * 4); pending_count.alloc(4); todo_slots.alloc(wc * 4); todo_count.alloc(4); defer_slots.alloc(wc * 4); defer_count.alloc(4);
+        dp_scratch.alloc(dp_bytes); wd_scratch.alloc(wd_bytes); gd_scratch.alloc(gd_bytes); q_ctr.alloc(64);
+        if (!n_pending_host) { CUDA_OK(cudaMallocHost((void**)&n_pending_host, 4)); *n_pending_host = 0; }
+        if (!stream) CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (!front_done) { CUDA_OK(cudaEventCreateWithFlags(&front_done, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); }
+    }
+    void fill(ChainParams& P) {
+        P.c_edge = c_edge.as<int32_t>(); P.c_schar = c_schar.as<uint8_t>(); P.c_fromseed = c_fromseed.as<uint8_t>();
         P.pending_slots = pending_slots.as<int32_t>(); P.pending_count = pending_count.as<int32_t>();
         P.todo_slots = todo_slots.as<int32_t>(); P.todo_count = todo_count.as<int32_t>();
         P.defer_slots = defer_slots.as<int32_t>(); P.defer_count = defer_count.as<int32_t>();
@@ -197,13 +229,16 @@ std::vector<double> phred_thresholds() {
 struct Pipeline {
     hlala_graph* g = nullptr; int32_t maxcol = 0;
     PreparedBatch pb; DeviceBatch db; ChainScratch cs;
-    DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch; int32_t ext_cap = 0; int32_t n_dp_threads = 0; int32_t n_wd_warps = 0;
+    std::vector<std::unique_ptr<Lane>> lanes; int n_lanes_max = 3; cudaEvent_t fork_ev = nullptr;
+    int32_t n_dp_threads = 0; int32_t n_wd_warps = 0;
+    ~Pipeline() { if (fork_ev) cudaEventDestroy(fork_ev); }
     bool scalar_dp_only = false;   // test hook: run every extension through the scalar kernel
-    DevBuf gd_scratch; int32_t n_gd_groups = 0; bool group_dp = true; bool dp_trace = false;
+    int32_t n_gd_groups = 0; bool group_dp = true; bool dp_trace = false;
+    DevBuf bpl_ws; std::vector<int32_t> bpl_host;   // per-level coverage of a host-buffer call
     DevBuf is_table, phred_thr; double is_mean = -1, is_sd = -1, is_pen = 0; int32_t is_dmin = 0, is_n = 0;
     DevBuf pair_mapq, read_mapq, read_reverse, chosen_slot, pair_ll, pair_status, digest;
     DevBuf o_n_cols, o_level, o_edge, o_gchar, o_schar, o_fromseed, o_mapq; bool have_columns = false;
-    int launches = 0; int64_t algo_bytes = 0; int32_t n_pending = 0; int32_t n_errors = 0;
+    int launches = 0; int64_t algo_bytes = 0; int32_t n_errors = 0;
     bool timing = false; std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;   // (kernel class, start/stop)
     int64_t chain_kernel_bytes = 0;
     void tic(int cls, cudaStream_t st) { if (!timing) return; cudaEvent_t a, b; CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b)); CUDA_OK(cudaEventRecord(a, st)); timed.push_back({cls, {a, b}}); }
@@ -219,7 +254,7 @@ struct Pipeline {
     bool dedup = true;    // false: align every same-strand chain (parity tests of the chain kernels)
 
     void prepare(hlala_graph* graph, const hlala_seed_batch_t& b, int32_t mc, cudaStream_t st) {
-        g = graph; maxcol = mc;
+        g = graph; maxcol = mc; have_columns = false;
         if (const char* e = allow_env_budget ? getenv("HLALA_WAVE_BYTES") : nullptr) scratch_budget = (size_t)strtoull(e, nullptr, 10);   // test hook: force several waves
         pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1); host_read_off.assign(b.read_off, b.read_off + b.n_reads + 1);
         // waves: consecutive pairs whose chains fit the column-scratch budget
@@ -233,25 +268,35 @@ struct Pipeline {
               max_wave_chains = std::max(max_wave_chains, b.chain_off[2 * p1] - c0);
               wave_pair.push_back(p1); p0 = p1;
           } }
-        cs.alloc(pb.n_chains, max_wave_chains, mc);
+        cs.alloc(pb.n_chains);
         size_t nr = (size_t)std::max<int64_t>(b.n_reads, 2), np = nr / 2;
         pair_mapq.alloc(np * 8); read_mapq.alloc(nr * 8); read_reverse.alloc(nr); chosen_slot.alloc(nr * 4); pair_ll.alloc(np * 8); pair_status.alloc(np * 4); digest.alloc(32);
         phred_thr.upload(phred_thresholds(), st);
-        n_dp_threads = g->n_sm * 64;
-        dp_scratch.alloc((size_t)n_dp_threads * dp_thread_scratch_bytes());
-        CUDA_OK(cudaMemsetAsync(dp_scratch.p, 0, dp_scratch.bytes, st));
+        n_dp_threads = g->n_sm * 8;     // the scalar kernel is the last resort of the cascade (a handful of tasks per wave)
         n_wd_warps = wd_warps_for(g->n_sm);
-        wd_scratch.alloc((size_t)n_wd_warps * wd_warp_scratch_bytes());
-        CUDA_OK(cudaMemsetAsync(wd_scratch.p, 0, wd_scratch.bytes, st));
         n_gd_groups = gd_groups_for(g->n_sm);
-        gd_scratch.alloc((size_t)n_gd_groups * gd_group_scratch_bytes());
-        CUDA_OK(cudaMemsetAsync(gd_scratch.p, 0, gd_scratch.bytes, st));
+        if (const char* e = allow_env_budget ? getenv("HLALA_LANES") : nullptr) n_lanes_max = std::max(1, atoi(e));   // test hook
+        const int n_lanes = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_lanes_max, wave_pair.size() - 1));
+        while ((int)lanes.size() > n_lanes) lanes.pop_back();
+        for (int i = 0; i < n_lanes; i++) {
+            if ((int)lanes.size() <= i) lanes.emplace_back(new Lane());
+            Lane& L = *lanes[(size_t)i];
+            L.alloc(max_wave_chains, mc, (size_t)n_dp_threads * dp_thread_scratch_bytes(), (size_t)n_wd_warps * wd_warp_scratch_bytes(), (size_t)n_gd_groups * gd_group_scratch_bytes());
+            // DP working memory is zeroed once; its hashes are generation-stamped and reused without clearing afterwards
+            if (L.dp_scratch.fresh) CUDA_OK(cudaMemsetAsync(L.dp_scratch.p, 0, L.dp_scratch.bytes, st));
+            if (L.wd_scratch.fresh) CUDA_OK(cudaMemsetAsync(L.wd_scratch.p, 0, L.wd_scratch.bytes, st));
+            if (L.gd_scratch.fresh) CUDA_OK(cudaMemsetAsync(L.gd_scratch.p, 0, L.gd_scratch.bytes, st));
+        }
+        if (!fork_ev) CUDA_OK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+        CUDA_OK(cudaStreamSynchronize(st));   // the lanes' own streams start from initialised scratch
         if (getenv("HLALA_DP_TRACE")) dp_trace = true;
         if (getenv("HLALA_NO_GROUP_DP")) group_dp = false;               // test hook: first tier = warp kernel, tiny configuration
         if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;            // test hooks (tools/scale_parity.py): the scalar DP only /
         if (allow_env_budget && getenv("HLALA_ALIGN_DUPLICATES")) dedup = false;   // align the chains k_prepare would skip
-        // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
-        // chosen alignment columns written once, per-pair scalars, coverage RMW
+    }
+    // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
+    // chosen alignment columns written once, per-pair scalars, coverage RMW. Only the bench asks for them.
+    void compute_algorithmic_bytes(const hlala_seed_batch_t& b) {
         int64_t nb = b.read_off[b.n_reads]; int64_t ncg = b.cigar_off[pb.n_chains];
         int64_t cols = 0; for (int32_t c = 0; c < pb.n_chains; c++) for (int32_t k = b.cigar_off[c]; k < b.cigar_off[c + 1]; k++) { int op = b.cigar[k] & 15; if (op == 0 || op == 1 || op == 2 || op == 7 || op == 8) cols += b.cigar[k] >> 4; }
         algo_bytes = 2 * nb + 24ll * pb.n_chains + 4 * ncg + cols * (4 + 7) + 2 * nb * 12 / 2 + 40ll * (b.n_reads / 2) + 4 * nb;
@@ -260,13 +305,15 @@ struct Pipeline {
         { int64_t rb = 0; for (int64_t r = 0; r < b.n_reads; r++) rb += (b.read_off[r + 1] - b.read_off[r]) * (int64_t)(b.chain_off[r + 1] - b.chain_off[r]);
           chain_kernel_bytes = 24ll * pb.n_chains + 4 * ncg + 2 * rb + cols * (4 + 1 + 6 + 8 + 1 + 6) + 44ll * pb.n_chains; }
     }
+    // defaults of everything the test hooks (environment variables read in prepare) can change; a workspace kept across calls starts from them
+    void reset_config() { scratch_budget = (size_t)6 << 30; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; dp_trace = false; }
     void ensure_columns() {
         if (have_columns) return;
         size_t n = (size_t)std::max<int64_t>(pb.n_reads, 2) * maxcol;
         o_n_cols.alloc((size_t)std::max<int64_t>(pb.n_reads, 2) * 4); o_level.alloc(n * 4); o_edge.alloc(n * 4); o_gchar.alloc(n); o_schar.alloc(n); o_fromseed.alloc(n); o_mapq.alloc(n);
         have_columns = true;
     }
-    ChainParams chain_params(int tier) { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, tier, P); P.do_extension = 1; cs.fill(P); return P; }
+    ChainParams chain_params(int tier, Lane& L) { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, tier, P); P.do_extension = 1; cs.fill(P); L.fill(P); return P; }
 
     void begin_run(cudaStream_t st) {
         launches = 0;
@@ -274,28 +321,38 @@ struct Pipeline {
         CUDA_OK(cudaMemsetAsync(cs.status.p, 0xFF, (size_t)std::max(pb.n_chains, 1) * 4, st));
         CUDA_OK(cudaMemsetAsync(digest.p, 0, 32, st));
     }
-    // chain stage for the slots of one wave
-    ChainParams run_chains_wave(size_t w, cudaStream_t st) {
-        ChainParams P0 = chain_params(0), P = chain_params(1);
+    // chain stage for the slots of one wave, first half: strand/duplicate rules, seed projection; leaves the number of chains that
+    // need an extension in the lane's pinned counter once front_done has fired
+    ChainParams wave_front(size_t w, Lane& L) {
+        cudaStream_t st = L.stream;
+        ChainParams P0 = chain_params(0, L), P = chain_params(1, L);
         for (ChainParams* q : {&P0, &P}) {
             q->slot_base = db_chain_off(2 * wave_pair[w]); q->slot_end = db_chain_off(2 * wave_pair[w + 1]);
             q->read_begin = (int32_t)(2 * wave_pair[w]); q->read_end = (int32_t)(2 * wave_pair[w + 1]); q->dedup = dedup ? 1 : 0;
         }
-        CUDA_OK(cudaMemsetAsync(cs.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.todo_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(cs.defer_count.p, 0, 4, st));
+        CUDA_OK(cudaMemsetAsync(L.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.todo_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.defer_count.p, 0, 4, st));
         if (P.slot_end > P.slot_base) {
             CUDA_OK(launch_prepare(P0, st));
             tic(0, st); CUDA_OK(launch_chain_seed(P0, g->n_sm, st)); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches += 3;
         }
-        CUDA_OK(cudaMemcpyAsync(&n_pending, cs.pending_count.p, 4, cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaMemcpyAsync(L.n_pending_host, L.pending_count.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaEventRecord(L.front_done, st));
+        return P;
+    }
+    // second half: extension cascade + chain finish
+    void wave_back(const ChainParams& P, Lane& L) {
+        cudaStream_t st = L.stream;
+        CUDA_OK(cudaEventSynchronize(L.front_done));
+        const int32_t n_pending = *L.n_pending_host;
         if (n_pending > 0) {
-            if (n_pending > ext_cap) {
-                ext_cap = n_pending + n_pending / 4 + 64; size_t nt = (size_t)ext_cap * 2;
-                ext_edge.alloc(nt * dp_ext_cap() * 4); ext_s.alloc(nt * dp_ext_cap()); ext_n.alloc(nt * 4); ext_nlvl.alloc(nt * 4); ext_rc.alloc(nt * 4);
+            if (n_pending > L.ext_cap) {
+                CUDA_OK(cudaStreamSynchronize(st));   // an earlier wave of this lane may still read the old buffers
+                L.ext_cap = n_pending + n_pending / 4 + 64; size_t nt = (size_t)L.ext_cap * 2;
+                L.ext_edge.alloc(nt * dp_ext_cap() * 4); L.ext_s.alloc(nt * dp_ext_cap()); L.ext_n.alloc(nt * 4); L.ext_nlvl.alloc(nt * 4); L.ext_rc.alloc(nt * 4); L.q_a.alloc(nt * 4); L.q_b.alloc(nt * 4);
             }
-            ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = ext_edge.as<int32_t>(); E.ext_s = ext_s.as<uint8_t>(); E.ext_n = ext_n.as<int32_t>();
-            E.ext_nlvl = ext_nlvl.as<int32_t>(); E.ext_rc = ext_rc.as<int32_t>(); E.dp_scratch = dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
-            E.wd_scratch = wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps; E.gd_scratch = gd_scratch.as<unsigned char>(); E.n_gd_groups = n_gd_groups;
+            ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = L.ext_edge.as<int32_t>(); E.ext_s = L.ext_s.as<uint8_t>(); E.ext_n = L.ext_n.as<int32_t>();
+            E.ext_nlvl = L.ext_nlvl.as<int32_t>(); E.ext_rc = L.ext_rc.as<int32_t>(); E.dp_scratch = L.dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
+            E.wd_scratch = L.wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps; E.gd_scratch = L.gd_scratch.as<unsigned char>(); E.n_gd_groups = n_gd_groups;
             tic(1, st);
             if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
             else {
@@ -303,22 +360,28 @@ struct Pipeline {
                 // re-runs what the previous one deferred for capacity
                 auto trace = [&](const char* what, cudaEvent_t a) {   // HLALA_DP_TRACE=1: time and deferral count of each tier (debug runs only)
                     cudaEvent_t b; CUDA_OK(cudaEventCreate(&b)); CUDA_OK(cudaEventRecord(b, st)); CUDA_OK(cudaEventSynchronize(b)); float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, a, b));
-                    std::vector<int32_t> rc((size_t)2 * n_pending); ext_rc.download(rc.data(), rc.size(), st); CUDA_OK(cudaStreamSynchronize(st));
+                    std::vector<int32_t> rc((size_t)2 * n_pending); L.ext_rc.download(rc.data(), rc.size(), st); CUDA_OK(cudaStreamSynchronize(st));
                     long long nd = 0; for (int32_t v : rc) nd += (v == -100);
                     fprintf(stderr, "[dp-trace] %-12s %8.2f ms, tasks %d, still deferred %lld\n", what, ms, 2 * n_pending, nd); cudaEventDestroy(b); CUDA_OK(cudaEventRecord(a, st)); };
                 cudaEvent_t tr0 = nullptr; if (dp_trace) { CUDA_OK(cudaEventCreate(&tr0)); CUDA_OK(cudaEventRecord(tr0, st)); }
-                if (group_dp) { CUDA_OK(launch_extend_group(E, g->n_sm, st)); launches += 1; if (dp_trace) trace("group8", tr0); }
+                int32_t* ctr = L.q_ctr.as<int32_t>(); int32_t* qa = L.q_a.as<int32_t>(); int32_t* qb = L.q_b.as<int32_t>();
+                CUDA_OK(cudaMemsetAsync(ctr, 0, 64, st));
+                if (group_dp) { E.in_list = nullptr; E.in_count = nullptr; E.pop = ctr + 0; E.out_list = qa; E.out_count = ctr + 1; CUDA_OK(launch_extend_group(E, g->n_sm, st)); launches += 1; if (dp_trace) trace("group8", tr0); }
                 toc(st);
-                tic(4, st); CUDA_OK(launch_extend_warp(E, g->n_sm, 0, group_dp, st)); if (dp_trace) trace("warp tiny", tr0);
+                tic(4, st);
+                E.in_list = group_dp ? qa : nullptr; E.in_count = ctr + 1; E.pop = ctr + 2; E.out_list = qb; E.out_count = ctr + 3;
+                CUDA_OK(launch_extend_warp(E, g->n_sm, 0, group_dp, st)); if (dp_trace) trace("warp tiny", tr0);
+                E.in_list = qb; E.in_count = ctr + 3; E.pop = ctr + 4; E.out_list = qa; E.out_count = ctr + 5;
                 CUDA_OK(launch_extend_warp(E, g->n_sm, 1, true, st)); if (dp_trace) trace("warp small", tr0);
+                E.in_list = qa; E.in_count = ctr + 5; E.pop = ctr + 6; E.out_list = qb; E.out_count = ctr + 7;
                 CUDA_OK(launch_extend_warp(E, g->n_sm, 2, true, st)); if (dp_trace) trace("warp large", tr0); toc(st);
                 tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4; if (dp_trace) { trace("scalar", tr0); cudaEventDestroy(tr0); }
             }
             toc(st);
             tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 1;
         }
-        return P;
     }
+    ChainParams run_chains_wave(size_t w, Lane& L) { ChainParams P = wave_front(w, L); wave_back(P, L); return P; }
     std::vector<int32_t> host_chain_off;
     std::vector<int64_t> host_read_off;
     bool keep_columns = false;         // session runs materialise the chosen alignments' columns (typing stage input)
@@ -336,11 +399,12 @@ struct Pipeline {
         if (normal_pdf(mean, sd, (double)(lo - 1)) > 0 || normal_pdf(mean, sd, (double)(hi + 1)) > 0) throw std::runtime_error("insert size table does not cover the support of the density");
         is_table.upload(t, st); is_dmin = (int32_t)lo; is_n = (int32_t)t.size(); is_mean = mean; is_sd = sd;
     }
-    void run_pairs_wave(size_t w, const ChainParams& C, int32_t* bases_per_level_dev, bool want_columns, cudaStream_t st) {
+    void run_pairs_wave(size_t w, const ChainParams& C, Lane& L, int32_t* bases_per_level_dev, bool want_columns) {
+        cudaStream_t st = L.stream;
         PairParams Q{}; Q.g = g->d; Q.b = db.view; Q.maxcol = maxcol;
         Q.slot_base = C.slot_base; Q.pair_begin = wave_pair[w]; Q.pair_end = wave_pair[w + 1];
         Q.status = cs.status.as<int32_t>(); Q.n_cols = cs.n_cols.as<int32_t>(); Q.ll = cs.ll.as<double>(); Q.first_level = cs.first_level.as<int32_t>(); Q.last_level = cs.last_level.as<int32_t>();
-        Q.id_first = cs.id_first.as<int32_t>(); Q.id_last = cs.id_last.as<int32_t>(); Q.c_edge = cs.c_edge.as<int32_t>(); Q.c_schar = cs.c_schar.as<uint8_t>(); Q.c_fromseed = cs.c_fromseed.as<uint8_t>();
+        Q.id_first = cs.id_first.as<int32_t>(); Q.id_last = cs.id_last.as<int32_t>(); Q.c_edge = L.c_edge.as<int32_t>(); Q.c_schar = L.c_schar.as<uint8_t>(); Q.c_fromseed = L.c_fromseed.as<uint8_t>();
         Q.is_table = is_table.as<double>(); Q.is_dmin = is_dmin; Q.is_n = is_n; Q.is_penalty = is_pen; Q.phred_thr = phred_thr.as<double>();
         Q.pair_mapq = pair_mapq.as<double>(); Q.read_mapq = read_mapq.as<double>(); Q.read_reverse = read_reverse.as<uint8_t>(); Q.chosen_slot = chosen_slot.as<int32_t>();
         Q.pair_ll = pair_ll.as<double>(); Q.pair_status = pair_status.as<int32_t>();
@@ -348,12 +412,17 @@ struct Pipeline {
         Q.bases_per_level = bases_per_level_dev; Q.error_count = cs.error_count.as<int32_t>(); Q.digest = digest.as<unsigned long long>();
         if (Q.pair_end > Q.pair_begin) { tic(3, st); CUDA_OK(launch_pair(Q, g->n_sm, st)); toc(st); launches++; }
     }
-    // the whole path: per wave chain stage (+ extension) then pair stage
+    // lanes start after everything queued on the caller's stream and the caller's stream continues after the lanes
+    void fork_lanes(cudaStream_t st) { CUDA_OK(cudaEventRecord(fork_ev, st)); for (auto& L : lanes) CUDA_OK(cudaStreamWaitEvent(L->stream, fork_ev, 0)); }
+    void join_lanes(cudaStream_t st) { for (auto& L : lanes) { CUDA_OK(cudaEventRecord(L->done, L->stream)); CUDA_OK(cudaStreamWaitEvent(st, L->done, 0)); } }
+    // the whole path: per wave chain stage (+ extension) then pair stage; consecutive waves run on different lanes
     void run(double mean, double sd, int32_t* bases_per_level_dev, bool want_columns, cudaStream_t st) {
         set_insert_size(mean, sd, st);
         if (want_columns) ensure_columns();
         begin_run(st);
-        for (size_t w = 0; w + 1 < wave_pair.size(); w++) { ChainParams C = run_chains_wave(w, st); run_pairs_wave(w, C, bases_per_level_dev, want_columns, st); }
+        fork_lanes(st);
+        for (size_t w = 0; w + 1 < wave_pair.size(); w++) { Lane& L = *lanes[w % lanes.size()]; ChainParams C = run_chains_wave(w, L); run_pairs_wave(w, C, L, bases_per_level_dev, want_columns); }
+        join_lanes(st);
     }
     void fetch(hlala_pair_out_t* out, cudaStream_t st) {
         size_t nr = (size_t)pb.n_reads, np = nr / 2;
@@ -480,11 +549,14 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
         cudaStream_t st = 0;
         Pipeline pl; pl.scratch_budget = (size_t)1 << 62; pl.allow_env_budget = false; pl.dedup = false; pl.prepare(g, *batch, out->max_columns, st);   // one wave: the chain records are exported whole
         pl.begin_run(st);
-        if (pl.wave_pair.size() > 1) pl.run_chains_wave(0, st);
+        Lane& L0 = *pl.lanes[0];
+        pl.fork_lanes(st);
+        if (pl.wave_pair.size() > 1) pl.run_chains_wave(0, L0);
+        pl.join_lanes(st);
         const int32_t nc = pl.pb.n_chains, mc = out->max_columns; ChainScratch& cs = pl.cs;
         DevBuf o_level, o_edge, o_g; size_t ncol = (size_t)std::max(nc, 1) * mc;
         o_level.alloc(ncol * 4); o_edge.alloc(ncol * 4); o_g.alloc(ncol);
-        CUDA_OK(launch_export_chain_columns(g->d, nc, mc, cs.n_cols.as<int32_t>(), cs.first_level.as<int32_t>(), cs.c_edge.as<int32_t>(), o_level.as<int32_t>(), o_edge.as<int32_t>(), o_g.as<uint8_t>(), st));
+        CUDA_OK(launch_export_chain_columns(g->d, nc, mc, cs.n_cols.as<int32_t>(), cs.first_level.as<int32_t>(), L0.c_edge.as<int32_t>(), o_level.as<int32_t>(), o_edge.as<int32_t>(), o_g.as<uint8_t>(), st));
         if (out->chain_order) memcpy(out->chain_order, pl.pb.chain_order.data(), (size_t)nc * 4);
         if (out->status) cs.status.download(out->status, nc, st);
         if (out->n_cols) cs.n_cols.download(out->n_cols, nc, st);
@@ -494,8 +566,8 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
         if (out->level) o_level.download(out->level, (size_t)nc * mc, st);
         if (out->edge) o_edge.download(out->edge, (size_t)nc * mc, st);
         if (out->gchar) o_g.download(out->gchar, (size_t)nc * mc, st);
-        if (out->schar) cs.c_schar.download(out->schar, (size_t)nc * mc, st);
-        if (out->from_seed) cs.c_fromseed.download(out->from_seed, (size_t)nc * mc, st);
+        if (out->schar) L0.c_schar.download(out->schar, (size_t)nc * mc, st);
+        if (out->from_seed) L0.c_fromseed.download(out->from_seed, (size_t)nc * mc, st);
         CUDA_OK(cudaStreamSynchronize(st));
         return 0;
     });
@@ -509,16 +581,25 @@ int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double 
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(g->device));
         cudaStream_t st = 0;
-        Pipeline pl; pl.prepare(g, *batch, out->max_columns, st);
-        DevBuf bpl; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
+        std::lock_guard<std::mutex> lock(g->ws_mu);
+        if (!g->ws) g->ws = std::shared_ptr<void>(std::make_shared<Pipeline>());
+        Pipeline& pl = *static_cast<Pipeline*>(g->ws.get());
+        const bool trace = getenv("HLALA_TRACE_HOST") != nullptr; auto t0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) { if (!trace) return; CUDA_OK(cudaDeviceSynchronize()); auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[host-trace] %-10s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count()); t0 = t1; };
+        pl.reset_config();
+        pl.prepare(g, *batch, out->max_columns, st);
+        lap("prepare");
+        DevBuf& bpl = pl.bpl_ws; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
         if (bases_per_level) { bpl.alloc(nl * 4); CUDA_OK(cudaMemsetAsync(bpl.p, 0, nl * 4, st)); }
         const bool want_cols = out->level || out->edge || out->gchar || out->schar || out->from_seed || out->mapq || out->n_cols;
         pl.run(is_mean, is_sd, bases_per_level ? bpl.as<int32_t>() : nullptr, want_cols, st);
+        lap("run");
         pl.fetch(out, st);
         if (bases_per_level) {
-            std::vector<int32_t> h(nl); bpl.download(h.data(), nl, st); CUDA_OK(cudaStreamSynchronize(st));
+            std::vector<int32_t>& h = pl.bpl_host; h.resize(nl); bpl.download(h.data(), nl, st); CUDA_OK(cudaStreamSynchronize(st));
             for (size_t i = 0; i + 1 < (size_t)g->h.n_levels; i++) bases_per_level[i] += h[i];
         }
+        lap("fetch");
         if (pl.n_errors > 0) return fail(HLALA_E_INVARIANT, std::to_string(pl.n_errors) + " chains/pairs violated a reference invariant (-5) or a kernel capacity (-4):" + pl.error_breakdown());
         return 0;
     });
@@ -536,6 +617,7 @@ int hlala_session_create(hlala_graph_t* g, const hlala_seed_batch_t* batch, int3
         CUDA_OK(cudaSetDevice(g->device));
         std::unique_ptr<hlala_session> s(new hlala_session());
         s->pl.prepare(g, *batch, max_columns, 0);
+        s->pl.compute_algorithmic_bytes(*batch);
         CUDA_OK(cudaStreamSynchronize(0));
         *out = s.release();
         return 0;

@@ -56,6 +56,9 @@ struct ExtParams {
     unsigned char* wd_scratch; int32_t n_wd_warps;     // warp kernel: one slice per warp
     unsigned char* gd_scratch; int32_t n_gd_groups;    // group kernel: one slice per 8-lane group
     int32_t only_deferred;                              // scalar kernel: run only the tasks the warp kernel deferred
+    // dynamic task queues of the cascade: a tier pops task indices from `pop`; its tasks are in_list[0 .. *in_count) (in_list == nullptr: all
+    // 2 * n_pending tasks) and the tasks it defers for capacity are appended to out_list
+    const int32_t* in_list; const int32_t* in_count; int32_t* pop; int32_t* out_list; int32_t* out_count;
 };
 
 constexpr int K3_WARPS = 4;

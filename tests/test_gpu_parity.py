@@ -92,12 +92,14 @@ def test_cascade_regression_fixture(tmp_path):
 def test_waves_and_scalar_dp_give_identical_results(dataset, monkeypatch):
     d, b, mu, sd = dataset("S")
     base = product(d).pairs(b, mu, sd, 1024)
-    monkeypatch.setenv("HLALA_WAVE_BYTES", "2000000")      # many waves
+    monkeypatch.setenv("HLALA_WAVE_BYTES", "2000000")      # many waves, alternating between three lanes (streams)
     waves = product(d).pairs(b, mu, sd, 1024)
-    monkeypatch.delenv("HLALA_WAVE_BYTES")
+    monkeypatch.setenv("HLALA_LANES", "1")                 # many waves, one after the other on one lane
+    one_lane = product(d).pairs(b, mu, sd, 1024)
+    monkeypatch.delenv("HLALA_WAVE_BYTES"); monkeypatch.delenv("HLALA_LANES")
     monkeypatch.setenv("HLALA_SCALAR_DP", "1")             # every extension through the scalar DP kernel
     scalar = product(d).pairs(b, mu, sd, 1024)
-    for other in (waves, scalar):
+    for other in (waves, one_lane, scalar):
         for k in base:
             if base[k] is not None:
                 assert np.array_equal(base[k], other[k]), k
