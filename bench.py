@@ -140,6 +140,92 @@ def small_prg(args, root):
     return d
 
 
+def ncu_traffic_bytes(kernel_file):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summary of the kernel (profiles/), or None"""
+    path = os.path.join(REPO, "profiles", kernel_file)
+    try:
+        tot = 0.0; seen = 0
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+                tot += float(f[2]) * mult; seen += 1
+        return tot if seen == 2 else None
+    except Exception:
+        return None
+
+
+def stage_kmer_seeding(args, root, H):
+    """§8 a29 on this box: index build (host) + hlala_seed_kmers (GPU) on the bases of a synthetic batch; the reference's findChains on a sample.
+    The index enumerates every k-mer path, which explodes inside 1000-allele gene blocks (the reference's Index() likewise), so this stage
+    uses a PRG of the same generator with 8 alleles per gene block."""
+    d = os.path.join(root, "prg_seed_stage")
+    if not os.path.exists(os.path.join(d, ".complete")):
+        os.makedirs(d, exist_ok=True)
+        H.synth_prg(d, levels=1000000, haps=args.haps, genes=args.genes, alleles=8, allele_contigs=4, seed=0xB200)
+        open(os.path.join(d, ".complete"), "w").write("ok\n")
+    b = H.synth_reads(d, os.path.join(d, "seeds_stage.bin"), pairs=250000, len=args.read_len, seed=0xB200, clip_frac=0.15)
+    off = np.ascontiguousarray(b["read_off"], np.int64); bases = np.ascontiguousarray(b["bases"], np.uint8)
+    P = H.Product(d); P.to_gpu(int(os.environ.get("LOCAL_RANK", "0")))
+    t = time.time(); P.kmer_index(25); t_index = time.time() - t
+
+    class RB(C.Structure):
+        _fields_ = [("n_reads", C.c_int64), ("read_off", C.c_void_p), ("bases", C.c_void_p)]
+    rb = RB(); rb.n_reads = len(off) - 1; rb.read_off = off.ctypes.data; rb.bases = bases.ctypes.data
+    best = None
+    for _ in range(3):
+        res = C.c_void_p(); t = time.time()
+        P._chk(P.lib.hlala_seed_kmers(P.g, C.byref(rb), C.byref(res))); dt = time.time() - t
+        ms = (C.c_double * 2)(); P._chk(P.lib.hlala_kmer_chains_timing(res, ms))
+        nr = C.c_int64(); nc = C.c_int64(); ne = C.c_int64(); nf = C.c_int64()
+        P._chk(P.lib.hlala_kmer_chains_dims(res, C.byref(nr), C.byref(nc), C.byref(ne), C.byref(nf)))
+        P.lib.hlala_kmer_chains_free(res)
+        if best is None or ms[0] < best["kernel_ms"]:
+            best = dict(kernel_ms=ms[0], order_gather_ms=ms[1], call_s=dt, chains=nc.value, chain_edges=ne.value, reads_over_capacity=nf.value)
+    n = len(off) - 1
+    out = dict(workload="%d reads x %d bp, k=25, PRG of 1000000 levels / %d haplotypes / %d gene blocks x 8 alleles" % (n, args.read_len, args.haps, args.genes),
+               index_build_host_s=t_index, reads_per_s_kernel=n / (best["kernel_ms"] / 1e3), reads_per_s_call_device_resident_output=n / best["call_s"], **best)
+    if os.path.exists(H.LIB_REF):   # the compiled reference holds one graph per process: its sample runs in a process of its own
+        try:
+            dref = os.path.join(root, "prg_seed_stage_ref")   # the reference's Index() needs minutes and tens of GB at 1M levels: its sample uses 100000 levels of the same generator
+            r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "seed_probe.py"), "--dir", dref, "--levels", "100000", "--alleles", "8", "--genes", str(args.genes), "--pairs", "20000", "--len", str(args.read_len),
+                                "--ref-only", "1", "--ref-reads", "20000"],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            out.update(reference_reads_per_s_1_thread=ref["ref_reads_per_s"], reference_index_build_s=ref["ref_index_build_s"],
+                       reference_sample="%d reads on a 100000-level PRG of the same generator, unmodified GraphAndEdgeIndex::findChains (single-threaded, as the reference is)" % ref["ref_reads"])
+        except Exception as e:
+            out["reference_error"] = str(e)[:200]
+    P.close()
+    return out
+
+
+def stage_typing(args, root, H):
+    """§8 a20-a28 on this box: alignment session with columns kept -> gene filter/extract -> hlala_typer_infer (per-read x cluster kernel,
+    allele-pair kernel) on a PRG with 17 gene blocks x 200 alleles and reads concentrated in the gene blocks."""
+    import tempfile
+    d = os.path.join(root, "prg_typing_stage")
+    if not os.path.exists(os.path.join(d, ".complete")):
+        os.makedirs(d, exist_ok=True)
+        H.synth_prg(d, levels=200000, haps=4, genes=17, alleles=200, seed=11)
+        open(os.path.join(d, ".complete"), "w").write("ok\n")
+    b = H.synth_reads(d, os.path.join(d, "seeds_stage.bin"), pairs=60000, len=args.read_len, seed=11, gene_frac=0.8)
+    P = H.Product(d); P.to_gpu(int(os.environ.get("LOCAL_RANK", "0")))
+    T = H.ProductTyping(P, d)
+    sess = H.session_align(P, b, args.is_mean, args.is_sd, args.max_columns, keep_columns=True)
+    t = time.time(); blob, n_sel = T.extract(sess); t_extract = time.time() - t
+    out_dir = tempfile.mkdtemp(prefix="hlala_typing_stage_")
+    t = time.time(); T.infer([blob], args.is_mean, args.is_sd, out_dir, device=int(os.environ.get("LOCAL_RANK", "0")), keep_read_ll=False); t_infer = time.time() - t
+    tm = T.timing()
+    P.lib.hlala_session_free(sess)
+    res = dict(workload="60000 pairs 2x%d (80%% inside gene blocks), PRG of 200000 levels / 17 gene blocks x 200 alleles" % args.read_len, pairs_selected=n_sel,
+               extract_s=t_extract, infer_call_s=t_infer, read_x_cluster_kernel_ms=tm["ms"][0], allele_pair_kernel_ms=tm["ms"][1], kernel_launches=tm["launches"],
+               read_cluster_observation_steps=tm["work"][0], log_avg_evaluations=tm["work"][1],
+               log_avg_evaluations_per_s=(tm["work"][1] / (tm["ms"][1] / 1e3)) if tm["ms"][1] > 0 else None, files_written=len(os.listdir(os.path.join(out_dir, "hla"))) if os.path.isdir(os.path.join(out_dir, "hla")) else 0)
+    T.close(); P.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,6 +244,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=6000)
     ap.add_argument("--cpu-levels", type=int, default=250000)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--stages", type=int, default=1, help="also time the k-mer seeding and typing stages (rank 0, N=1 only)")
     args = ap.parse_args()
     rank, local_rank, world = rank_info()
     n_gpus = max(world, 1)
@@ -216,6 +303,7 @@ def main():
     L = P.lib
     L.hlala_session_chain_kernel_bytes.restype = C.c_int64
     L.hlala_session_algorithmic_bytes.restype = C.c_int64
+    L.hlala_session_dp_kernel_bytes.restype = C.c_int64
     n_levels = P.dims()["n_levels"]
     sb = H.make_batch_struct(b)
     sess = C.c_void_p()
@@ -248,6 +336,8 @@ def main():
     clocks = sampler.finish()
     kms = (C.c_double * 6)(); kl = (C.c_int * 6)()
     P._chk(L.hlala_session_timing(sess, kms, kl))
+    dp_bytes_total = int(L.hlala_session_dp_kernel_bytes(sess))
+    chain_bytes = int(L.hlala_session_chain_kernel_bytes(sess)); total_bytes = int(L.hlala_session_algorithmic_bytes(sess))
     L.hlala_session_set_timing(sess, 0)
     launches = L.hlala_session_launches(sess)
     dig = (C.c_int64 * 4)(); sll = C.c_double(0)
@@ -276,7 +366,7 @@ def main():
     cov_host = np.zeros(n_levels - 1, np.int32)
     h2d = int(sum(b[k].nbytes for k in H.BATCH_KEYS)) + 3 * 4 * len(b["chain_contig"])
     d2h = int(sum(v.numel() * v.element_size() for v in res.values())) + cov_host.nbytes
-    L.hlala_session_free(sess)   # e2e allocates its own device buffers per call, like a user's call would
+    L.hlala_session_free(sess)   # the e2e call owns its device buffers (a workspace kept in the graph handle across calls)
     torch.cuda.synchronize()
     e2e_times = []
     for i in range(1 + args.e2e_steps):
@@ -300,22 +390,22 @@ def main():
             dist.destroy_process_group()
         return 0
     peak, peak_src = measured_peak()
-    chain_bytes = L.hlala_session_chain_kernel_bytes(sess) if False else None
-    # chain kernel roofline: algorithmic bytes per launch / average launch duration
-    sess2 = C.c_void_p()
-    P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(sess2)))
-    chain_bytes = int(L.hlala_session_chain_kernel_bytes(sess2)); total_bytes = int(L.hlala_session_algorithmic_bytes(sess2))
-    L.hlala_session_free(sess2)
-    names = ["k_chain_seed", "k_extend_warp<small>", "k_chain_finish", "k_pair", "k_extend_warp<large>", "k_extend(scalar)"]
+    names = ["k_chain_seed", "k_extend_group", "k_chain_finish", "k_pair", "k_extend_warp(tiny+small+large)", "k_extend(scalar)"]
     per_kernel = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kl[i] / args.steps} for i in range(6)}
     dom = max(range(6), key=lambda i: kms[i])
-    ach = None; frac = None
-    if kms[0] > 0:
-        ach = chain_bytes * args.steps / (kms[0] / 1000.0) / 1e9
-        frac = ach / peak
-    roofline = {"bound": "hbm", "kernel": "k_chain_seed", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": frac, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_step": chain_bytes, "whole_path_algorithmic_bytes_per_step": total_bytes,
-                "whole_path_achieved": total_bytes * args.steps / (ms_total / 1000.0) / 1e9, "dominant_kernel_by_time": names[dom], "per_kernel": per_kernel}
+    # dominant kernel: the first tier of the extension DP. Algorithmic bytes of all extension tasks (it attempts every task) over the summed
+    # CUDA-event durations of its launches; the launches of different waves overlap on several streams, so this is a per-launch average.
+    dp_ach = dp_bytes_total / (kms[1] / 1000.0) / 1e9 if kms[1] > 0 and dp_bytes_total > 0 else None
+    chain_ach = chain_bytes * args.steps / (kms[0] / 1000.0) / 1e9 if kms[0] > 0 else None
+    traffic = ncu_traffic_bytes("r01_ncu_k_extend_group.txt")
+    roofline = {"bound": "hbm", "kernel": "k_extend_group", "achieved": dp_ach, "peak": peak, "unit": "GB/s", "frac": (dp_ach / peak) if dp_ach else None, "traffic": traffic,
+                "traffic_source": "profiles/r01_ncu_k_extend_group.txt (ncu --set full, one launch = one wave of the same size as here)", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dp_bytes_total / max(kl[1], 1), "launch_ms_avg": kms[1] / max(kl[1], 1),
+                "note": "integer DP over a sparse cell set: bounded by dependent-load latency and issue slots (ncu: 16 % issue-active, long-scoreboard stalls), not by HBM bandwidth; the fraction is reported as measured",
+                "chain_kernel": {"kernel": "k_chain_seed", "achieved": chain_ach, "frac": (chain_ach / peak) if chain_ach else None, "algorithmic_bytes_per_step": chain_bytes},
+                "whole_path_algorithmic_bytes_per_step": total_bytes, "whole_path_achieved": total_bytes * args.steps / (ms_total / 1000.0) / 1e9,
+                "dominant_kernel_by_time": names[dom], "per_kernel": per_kernel,
+                "per_kernel_note": "durations of launches on different streams overlap; their sum exceeds ms_per_step"}
     cpu = None
     if os.path.exists(H.LIB_REF) and n_gpus == 1:
         d = small_prg(args, root)
@@ -326,12 +416,20 @@ def main():
                "single_thread_value": v1,
                "sample": "%d pairs 2x%d on a %d-level PRG built with the same generator parameters; unmodified reference TUs; the reference itself runs this loop on 1 thread (%.0f pairs/s), "
                          "the value is the courtesy all-cores OpenMP loop over pairs" % (args.cpu_pairs, args.read_len, args.cpu_levels, v1)}
+    stages = None
+    if args.stages and n_gpus == 1:
+        stages = {}
+        for nm, fn in (("kmer_seeding", stage_kmer_seeding), ("typing", stage_typing)):
+            try:
+                stages[nm] = fn(args, root, H)
+            except Exception as e:   # a stage measurement must not cost the headline line
+                stages[nm] = {"error": str(e)[:300]}
     line = {"metric": "paired reads/sec aligned to the PRG (seed projection + extension + pair scoring)", "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
-            "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
+            "stages": stages, "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

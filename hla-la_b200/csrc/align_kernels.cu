@@ -432,6 +432,30 @@ cudaError_t launch_extend_group(const ExtParams& E0, int n_sm, cudaStream_t stre
     return cudaGetLastError();
 }
 
+// Algorithmic HBM bytes of the extension tasks of one wave (extension DP): per task that runs, per clipped read base: the base
+// itself (1) + one level of graph window (adj4 record 16 + 1.1 out/in records of 16) + one output column (edge 4 + read char 1), plus 40 B
+// of task scalars. Summed into a 64-bit counter; launched only when the session's timing is on.
+__global__ void k_dp_task_bytes(ExtParams E, unsigned long long* out) {
+    const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long b = 0;
+    if (t < 2 * E.n_pending) {
+        const int slot = P.pending_slots[t >> 1]; const int side = t & 1;
+        const int r = B.slot_read[slot]; const int rdlen = (int)(B.read_off[r + 1] - B.read_off[r]);
+        const int sb = P.seed_begin[slot], se = P.seed_end[slot]; const int l_first = P.first_level[slot], l_last = P.last_level[slot];
+        int len = 0;
+        if (side == 0) { if (sb != 0 && l_first > 0) len = sb; } else { if (se != rdlen - 1 && l_last + 1 < G.n_levels - 1) len = rdlen - 1 - se; }
+        if (len > 0) b = 40ull + (unsigned long long)len * (1 + 16 + 18 + 5);
+    }
+    for (int d = 16; d; d >>= 1) b += __shfl_xor_sync(0xffffffffu, b, d);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, b);
+}
+cudaError_t launch_dp_task_bytes(const ExtParams& E, unsigned long long* out, cudaStream_t stream) {
+    if (E.n_pending <= 0) return cudaSuccess;
+    k_dp_task_bytes<<<(2 * E.n_pending + 255) / 256, 256, 0, stream>>>(E, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
     size_t smem = k1_slab_bytes(E.C.slab_cols, E.C.pool_cap, E.C.win_cap, E.C.wcap) * K1_WARPS;

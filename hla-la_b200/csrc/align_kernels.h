@@ -17,6 +17,7 @@ size_t gd_group_scratch_bytes();
 int wd_warps_for(int n_sm);
 size_t wd_warp_scratch_bytes();
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream);
+cudaError_t launch_dp_task_bytes(const ExtParams& E, unsigned long long* out, cudaStream_t stream);
 cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream);
 size_t dp_thread_scratch_bytes();
 int dp_ext_cap();

@@ -241,6 +241,7 @@ struct Pipeline {
     int launches = 0; int64_t algo_bytes = 0; int32_t n_errors = 0;
     bool timing = false; std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;   // (kernel class, start/stop)
     int64_t chain_kernel_bytes = 0;
+    DevBuf dp_bytes;   // algorithmic bytes of the extension tasks of the timed runs (k_dp_task_bytes)
     void tic(int cls, cudaStream_t st) { if (!timing) return; cudaEvent_t a, b; CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b)); CUDA_OK(cudaEventRecord(a, st)); timed.push_back({cls, {a, b}}); }
     void toc(cudaStream_t st) { if (!timing) return; CUDA_OK(cudaEventRecord(timed.back().second.second, st)); }
     void collect_timing(double ms[6], int launches_per_class[6]) {
@@ -272,7 +273,8 @@ struct Pipeline {
         size_t nr = (size_t)std::max<int64_t>(b.n_reads, 2), np = nr / 2;
         pair_mapq.alloc(np * 8); read_mapq.alloc(nr * 8); read_reverse.alloc(nr); chosen_slot.alloc(nr * 4); pair_ll.alloc(np * 8); pair_status.alloc(np * 4); digest.alloc(32);
         phred_thr.upload(phred_thresholds(), st);
-        n_dp_threads = g->n_sm * 8;     // the scalar kernel is the last resort of the cascade (a handful of tasks per wave)
+        if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;            // test hook (tools/scale_parity.py): the scalar DP only
+        n_dp_threads = g->n_sm * (scalar_dp_only ? 64 : 8);     // otherwise the scalar kernel is the last resort of the cascade (a handful of tasks per wave)
         n_wd_warps = wd_warps_for(g->n_sm);
         n_gd_groups = gd_groups_for(g->n_sm);
         if (const char* e = allow_env_budget ? getenv("HLALA_LANES") : nullptr) n_lanes_max = std::max(1, atoi(e));   // test hook
@@ -291,7 +293,6 @@ struct Pipeline {
         CUDA_OK(cudaStreamSynchronize(st));   // the lanes' own streams start from initialised scratch
         if (getenv("HLALA_DP_TRACE")) dp_trace = true;
         if (getenv("HLALA_NO_GROUP_DP")) group_dp = false;               // test hook: first tier = warp kernel, tiny configuration
-        if (getenv("HLALA_SCALAR_DP")) scalar_dp_only = true;            // test hooks (tools/scale_parity.py): the scalar DP only /
         if (allow_env_budget && getenv("HLALA_ALIGN_DUPLICATES")) dedup = false;   // align the chains k_prepare would skip
     }
     // algorithmic bytes: bases+quals, seed records + CIGARs, translation + graph window per chain column,
@@ -353,6 +354,7 @@ struct Pipeline {
             ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = L.ext_edge.as<int32_t>(); E.ext_s = L.ext_s.as<uint8_t>(); E.ext_n = L.ext_n.as<int32_t>();
             E.ext_nlvl = L.ext_nlvl.as<int32_t>(); E.ext_rc = L.ext_rc.as<int32_t>(); E.dp_scratch = L.dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
             E.wd_scratch = L.wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps; E.gd_scratch = L.gd_scratch.as<unsigned char>(); E.n_gd_groups = n_gd_groups;
+            if (timing) { if (!dp_bytes.p) { dp_bytes.alloc(8); CUDA_OK(cudaMemsetAsync(dp_bytes.p, 0, 8, st)); } CUDA_OK(launch_dp_task_bytes(E, dp_bytes.as<unsigned long long>(), st)); }
             tic(1, st);
             if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
             else {
@@ -635,7 +637,15 @@ int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t
     });
 }
 int hlala_session_launches(const hlala_session_t* s) { return s ? s->pl.launches : -1; }
-int hlala_session_set_timing(hlala_session_t* s, int on) { if (!s) return fail(HLALA_E_ARG, "null session"); s->pl.timing = on != 0; return 0; }
+int hlala_session_set_timing(hlala_session_t* s, int on) {
+    if (!s) return fail(HLALA_E_ARG, "null session");
+    return guarded([&]() { s->pl.timing = on != 0; if (on) { CUDA_OK(cudaSetDevice(s->pl.g->device)); s->pl.dp_bytes.alloc(8); CUDA_OK(cudaMemset(s->pl.dp_bytes.p, 0, 8)); } return 0; });
+}
+int64_t hlala_session_dp_kernel_bytes(hlala_session_t* s) {
+    if (!s || !s->pl.dp_bytes.p) return -1;
+    unsigned long long v = 0; if (cudaSetDevice(s->pl.g->device) != cudaSuccess || cudaMemcpy(&v, s->pl.dp_bytes.p, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
 int hlala_session_timing(hlala_session_t* s, double ms[6], int launches[6]) {
     if (!s) return fail(HLALA_E_ARG, "null session");
     return guarded([&]() { s->pl.collect_timing(ms, launches); return 0; });

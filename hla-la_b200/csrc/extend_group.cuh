@@ -72,7 +72,8 @@ template <class CFG> __device__ __forceinline__ void gd_insert_cell(const WdCtx&
 }
 
 // per-group DP state (uniform across the lanes of a group)
-struct GdState { int n_m1, n_m2, rot, diag, last_inc, cur_max, first_max_cell, n_cells; uint32_t cgen; bool hashed; };
+struct GdState { int n_m1, n_m2, rot, diag, last_inc, cur_max, first_max_cell, n_cells; uint32_t cgen; bool hashed;
+                 int end_c; };   // index of the first sequence-complete cell (-1: none); cells are numbered in creation order
 
 template <class CFG> __device__ __forceinline__ void gd_init(const WdCtx& C, const GdSlab& S, GdState& st, const Grp<CFG::GW>& g) {
     const DpGraph& G = *C.G;
@@ -85,7 +86,7 @@ template <class CFG> __device__ __forceinline__ void gd_init(const WdCtx& C, con
         *S.cnt = 0;
     }
     for (int i = g.lane; i < CFG::TDHASH; i += CFG::GW) { S.tkey[i] = 0; S.kD[i] = 0; S.kGG[i] = 0; S.kSG[i] = 0; }
-    st.n_m1 = 1; st.n_m2 = 0; st.rot = 0; st.diag = 0; st.last_inc = 0; st.cur_max = 0; st.first_max_cell = 0; st.n_cells = 1; st.cgen = 0; st.hashed = false;
+    st.n_m1 = 1; st.n_m2 = 0; st.rot = 0; st.diag = 0; st.last_inc = 0; st.cur_max = 0; st.first_max_cell = 0; st.n_cells = 1; st.cgen = 0; st.hashed = false; st.end_c = -1;
     g.sync();
 }
 
@@ -144,7 +145,7 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
             if (!ok) continue;
             const int ti = gd_touch<CFG>(S, C.start_level, jx, pc.y, jp.z, jp.y); if (ti < 0) { ovf = true; break; }
             atomicMax(&S.kD[ti], wd_key(pc.D, wd_mkseq(1, i, (int)pc.deg + j, 0)));
-            saw_jump = true;
+            if (jp.w > 1) saw_jump = true;   // a jump over one level lands on the same anti-diagonal as the '_' edge itself: still no revisits
         }
     }
     g.sync();
@@ -212,6 +213,7 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
             ne.cell = ci; ne.node = tn; ne.x = tx; ne.y = (int16_t)ty; ne.z = (int16_t)tz; ne.D = (int16_t)stD; ne.GG = (int16_t)stGG; ne.SG = (int16_t)stSG; ne.pad = (uint16_t)((__ldg(G.node_gapflags + tn) >> (C.pos ? 0 : 1)) & 1);
             int deg, jdeg; wd_adj(C, tn, ne.k0, deg, ne.j0, jdeg); ne.deg = (uint16_t)min(deg, 65535); ne.jdeg = (uint16_t)min(jdeg, 65535);
         }
+        { const unsigned em = g.ballot(keep && ty == end_seq); if (em && st.end_c < 0) st.end_c = g.shfl(ci, __ffs(em) - 1); }   // first sequence-complete cell: the end-cell scan starts there
         if (g.any(keep && (selD > running || tie_counts || overwritten))) any_inc = true;
         const int chunk_max = g.shfl(incl, GW - 1);
         if (chunk_max > run_max) {
@@ -258,11 +260,11 @@ template <class CFG> __device__ __forceinline__ int gd_finish(const WdCtx& C, co
     int end_cell = -1;
     {
         int bs = DP_NEG - 1, bx = -1, bz = -1, bc = -1;
-        for (int i = lane; i < st.n_cells; i += GW) {
+        if (st.end_c >= 0) for (int i = st.end_c + lane; i < st.n_cells; i += GW) {
             const DpCell& c = C.cells[i];
             if (c.pad == 1 && c.y == end_seq) { const int s = c.D; if (bc < 0 || s > bs || (s == bs && dp_key_less(c.x, c.z, bx, bz))) { bs = s; bx = c.x; bz = c.z; bc = i; } }
         }
-        for (int d = GW / 2; d; d >>= 1) {
+        if (st.end_c >= 0) for (int d = GW / 2; d; d >>= 1) {
             const int os = g.shfl_xor(bs, d), ox = g.shfl_xor(bx, d), oz = g.shfl_xor(bz, d), oc = g.shfl_xor(bc, d);
             if (oc >= 0 && (bc < 0 || os > bs || (os == bs && dp_key_less(ox, oz, bx, bz)))) { bs = os; bx = ox; bz = oz; bc = oc; }
         }

@@ -177,13 +177,13 @@ template <class CFG> __device__ int wd_extend(const WdCtx& C, const WdSlab& S, i
                 if (!ok) continue;
                 const int ti = wd_touch<CFG>(S, C.start_level, jx, pc.y, jp.z, jp.y); if (ti < 0) { ovf = true; break; }
                 atomicMax(&S.kD[ti], wd_key(pc.D, wd_mkseq(1, i, (int)pc.deg + j, 0)));
-                saw_jump = true;
+                if (jp.w > 1) saw_jump = true;   // see extend_group.cuh: one-level jumps stay on the anti-diagonal of the '_' edge
             }
         }
         __syncwarp();
         if (__any_sync(0xffffffffu, ovf)) { status = DP_DEFER; break; }
         if (!hashed && __any_sync(0xffffffffu, saw_jump)) {
-            // first jump of this extension: from now on cells can be revisited, so build the (x, y, z) -> cell map
+            // first jump over more than one level in this extension: from now on cells can be revisited, so build the (x, y, z) -> cell map
             if (lane == 0) { cgen = C.gens[0] + 1; if (cgen >= (1u << 15)) cgen = 0; C.gens[0] = cgen ? cgen : 1; }
             cgen = __shfl_sync(0xffffffffu, cgen, 0);
             if (cgen == 0) { for (int i = lane; i < DP_HASH_CAP; i += 32) C.hash[i] = 0; cgen = 1; __syncwarp(); }

@@ -10,6 +10,7 @@
 #include <dirent.h>
 #include <fstream>
 #include <sstream>
+#include <type_traits>
 #include <stdexcept>
 #include <sys/stat.h>
 #include <unordered_set>
@@ -30,7 +31,9 @@ std::vector<std::string> split_on(const std::string& s, const std::string& d) {
 }
 std::string join_with(const std::vector<std::string>& v, const char* d) { std::string r; for (size_t i = 0; i < v.size(); i++) { if (i) r += d; r += v[i]; } return r; }
 void chomp(std::string& s) { while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); }
-template <class T> std::string str(T v) { std::ostringstream o; o << v; return o.str(); }   // default ostream formatting == Utilities::ItoStr / DtoStr
+// default ostream formatting == Utilities::ItoStr / DtoStr; spelled with snprintf / to_string because constructing a stream per number dominated
+// the host time of the typing stage ("%g" is what operator<<(double) prints at the default precision of 6)
+template <class T> std::string str(T v) { if constexpr (std::is_floating_point<T>::value) { char b[40]; snprintf(b, sizeof b, "%g", (double)v); return b; } else if constexpr (std::is_integral<T>::value) return std::to_string(v); else { std::ostringstream o; o << v; return o.str(); } }
 
 std::vector<std::string> read_lines(const std::string& path, bool keep_trailing_empty) {
     std::ifstream f(path); if (!f.is_open()) throw std::runtime_error("Cannot open file " + path);

@@ -127,11 +127,14 @@ void hlala_session_free(hlala_session_t* s);
 int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t bases_per_level_dev, void* cuda_stream);
 /* Number of kernel launches one hlala_session_run performs. */
 int hlala_session_launches(const hlala_session_t* s);
-/* Per-kernel device time of the runs since the last call: ms[0] chain kernel (k_chain_seed), [1] extension DP, warp kernel, small
- * configuration, [2] chain finish (k_chain_finish), [3] pair kernel (k_pair), [4] extension DP, warp kernel, large configuration
- * (tasks deferred by [1]), [5] extension DP, scalar kernel (tasks deferred by [4]); CUDA events on the launching stream. */
+/* Per-kernel device time of the runs since the last call: ms[0] chain kernel (k_chain_seed, both capacity tiers), [1] extension DP first
+ * tier (k_extend_group, 8 lanes per task), [2] chain finish (k_chain_finish), [3] pair kernel (k_pair), [4] extension DP warp tiers
+ * (k_extend_warp tiny + small + large: tasks deferred by [1]), [5] extension DP scalar kernel (tasks deferred by [4]); CUDA events on the
+ * launching streams. Waves run on several streams, so these durations overlap: their sum exceeds the wall time of a run. */
 int hlala_session_set_timing(hlala_session_t* s, int on);
 int hlala_session_timing(hlala_session_t* s, double ms[6], int launches[6]);
+/* Algorithmic HBM bytes of the extension tasks of all runs since hlala_session_set_timing(s, 1) (extension DP). */
+int64_t hlala_session_dp_kernel_bytes(hlala_session_t* s);
 /* Algorithmic HBM bytes of the chain kernel alone for this batch (Kernel 1). */
 int64_t hlala_session_chain_kernel_bytes(const hlala_session_t* s);
 /* Algorithmic HBM bytes of one run (SURVEY.md §8d formula evaluated on this batch). */

@@ -9,7 +9,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(REPO, "hla-la_b200")
 SYNTH = os.path.join(PKG, "build", "hlala-synth")
-LIB_PRODUCT = os.path.join(PKG, "build", "libhlala_b200.so")
+LIB_PRODUCT = os.environ.get("HLALA_B200_LIB") or os.path.join(PKG, "build", "libhlala_b200.so")   # the override is for A/B timing of two builds in one GPU call
 LIB_ORACLE = os.path.join(REPO, "oracle", "build", "libhlala_oracle.so")
 LIB_REF = os.path.join(REPO, "oracle", "_ref", "libhlala_ref.so")
 

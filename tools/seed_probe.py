@@ -13,12 +13,19 @@ def main():
     ap.add_argument("--levels", type=int, default=1000000); ap.add_argument("--pairs", type=int, default=250000); ap.add_argument("--k", type=int, default=25)
     ap.add_argument("--alleles", type=int, default=8); ap.add_argument("--genes", type=int, default=17); ap.add_argument("--len", type=int, default=150)
     ap.add_argument("--ref-reads", type=int, default=0); ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--dir", default=""); ap.add_argument("--ref-only", type=int, default=0, help="only time the compiled reference on the sample (no GPU needed)")
     a = ap.parse_args()
-    d = "/tmp/hlala_seed_probe_l%d_g%d_a%d" % (a.levels, a.genes, a.alleles)
+    d = a.dir or "/tmp/hlala_seed_probe_l%d_g%d_a%d" % (a.levels, a.genes, a.alleles)
     if not os.path.exists(d + "/.complete"):
         os.makedirs(d, exist_ok=True); H.synth_prg(d, levels=a.levels, haps=8, genes=a.genes, alleles=a.alleles, allele_contigs=4, seed=0xB200); open(d + "/.complete", "w").write("ok")
     b = H.synth_reads(d, os.path.join(d, "seeds_p%d.bin" % a.pairs), pairs=a.pairs, len=a.len, seed=0xB200, clip_frac=0.15)
     off = np.ascontiguousarray(b["read_off"], np.int64); bases = np.ascontiguousarray(b["bases"], np.uint8)
+    if a.ref_only:
+        R = H.quiet(H.Ref, d); t = time.time(); H.quiet(R.kmer_index, a.k); t_ref_index = time.time() - t
+        n = min(a.ref_reads, len(off) - 1)
+        ref = R.find_chains(off[:n + 1], bases)
+        print(json.dumps(dict(ref_reads=n, ref_seconds=ref["seconds"], ref_reads_per_s=n / ref["seconds"], ref_index_build_s=t_ref_index, ref_chains=len(ref["begin"]))))
+        return
     P = H.Product(d); P.to_gpu(0)
     t = time.time(); P.kmer_index(a.k); t_index = time.time() - t
     nk = len(P.kmer_dump()["kmers"]) if a.levels <= 2000000 else -1
