@@ -6,6 +6,7 @@
 #include "typing_kernels.h"
 #include "seed_kernels.h"
 #include "../host/kmer_index.h"
+#include "../host/bam_reader.h"
 #include "../host/hla_typing.h"
 
 #include <algorithm>
@@ -607,7 +608,7 @@ int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double 
     });
 }
 
-struct hlala_session { Pipeline pl; std::vector<uint8_t> typing_blob; };
+struct hlala_session { Pipeline pl; std::vector<uint8_t> typing_blob; bool own_cov = false; DevBuf cov; };
 
 int hlala_session_create(hlala_graph_t* g, const hlala_seed_batch_t* batch, int32_t max_columns, hlala_session_t** out) {
     if (!g || !out) return fail(HLALA_E_ARG, "hlala_session_create: null argument");
@@ -632,7 +633,9 @@ int hlala_session_run(hlala_session_t* s, double is_mean, double is_sd, uint64_t
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(s->pl.g->device));
         cudaStream_t st = (cudaStream_t)cuda_stream;
-        s->pl.run(is_mean, is_sd, (int32_t*)(uintptr_t)bases_per_level_dev, s->pl.keep_columns, st);
+        int32_t* cov = (int32_t*)(uintptr_t)bases_per_level_dev;
+        if (!cov && s->own_cov) { const size_t nl = (size_t)std::max(s->pl.g->h.n_levels - 1, 1); s->cov.alloc(nl * 4); CUDA_OK(cudaMemsetAsync(s->cov.p, 0, nl * 4, st)); cov = s->cov.as<int32_t>(); }
+        s->pl.run(is_mean, is_sd, cov, s->pl.keep_columns, st);
         return 0;
     });
 }
@@ -985,5 +988,49 @@ int hlala_kmer_chains_timing(const hlala_kmer_chains_t* c, double ms[2]) {
     ms[0] = c->ms[0]; ms[1] = c->ms[1]; return 0;
 }
 void hlala_kmer_chains_free(hlala_kmer_chains_t* c) { delete c; }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BAM ingest and the session's own coverage histogram (what the CLI needs on top of the kernels)
+struct hlala_bam_batch { BamBatch b; std::vector<const char*> names; };
+
+extern "C" {
+
+int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out) {
+    if (!g || !bam_path || !out) return fail(HLALA_E_ARG, "hlala_bam_read: null argument");
+    *out = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<hlala_bam_batch> B(new hlala_bam_batch());
+        std::vector<int64_t> len; for (int32_t c = 0; c < g->h.n_contigs; c++) len.push_back(g->h.contig_off[(size_t)c + 1] - g->h.contig_off[(size_t)c]);
+        read_bam_seeds(bam_path, g->h.contig_bam_name, len, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency()), B->b);
+        for (const std::string& n : B->b.pair_name) B->names.push_back(n.c_str());
+        *out = B.release();
+        return 0;
+    });
+}
+int hlala_bam_batch_view(const hlala_bam_batch_t* B, hlala_seed_batch_t* view, const char* const** pair_names) {
+    if (!B || !view) return fail(HLALA_E_ARG, "hlala_bam_batch_view: null argument");
+    const BamBatch& b = B->b;
+    view->n_reads = (int64_t)b.read_off.size() - 1; view->read_off = b.read_off.data(); view->bases = b.bases.data(); view->quals = b.quals.data();
+    view->chain_off = b.chain_off.data(); view->chain_contig = b.chain_contig.data(); view->chain_pos = b.chain_pos.data(); view->chain_flag = b.chain_flag.data(); view->chain_as = b.chain_as.data();
+    view->cigar_off = b.cigar_off.data(); view->cigar = b.cigar.data();
+    if (pair_names) *pair_names = B->names.data();
+    return 0;
+}
+int hlala_bam_batch_stats(const hlala_bam_batch_t* B, int64_t counts[4], double* is_mean, double* is_sd, int64_t* is_n) {
+    if (!B) return fail(HLALA_E_ARG, "hlala_bam_batch_stats: null argument");
+    if (counts) { counts[0] = B->b.records; counts[1] = B->b.records_used; counts[2] = B->b.names_seen; counts[3] = B->b.pairs_incomplete; }
+    if (is_mean) *is_mean = B->b.tlen_mean; if (is_sd) *is_sd = B->b.tlen_sd; if (is_n) *is_n = B->b.tlen_n;
+    return 0;
+}
+void hlala_bam_batch_free(hlala_bam_batch_t* B) { delete B; }
+
+int hlala_session_set_coverage(hlala_session_t* s, int on) { if (!s) return fail(HLALA_E_ARG, "null session"); s->own_cov = on != 0; return 0; }
+int hlala_session_fetch_coverage(hlala_session_t* s, int32_t* bases_per_level) {
+    if (!s || !bases_per_level) return fail(HLALA_E_ARG, "hlala_session_fetch_coverage: null argument");
+    if (!s->cov.p) return fail(HLALA_E_ARG, "hlala_session_fetch_coverage: run the session with hlala_session_set_coverage(s, 1) first");
+    return guarded([&]() { CUDA_OK(cudaSetDevice(s->pl.g->device)); CUDA_OK(cudaMemcpy(bases_per_level, s->cov.p, (size_t)std::max(s->pl.g->h.n_levels - 1, 1) * 4, cudaMemcpyDeviceToHost)); return 0; });
+}
 
 } // extern "C"

@@ -10,6 +10,7 @@
 //            (contig, pos, flag, AS, BAM-packed CIGAR).
 // The graph model follows Graph/graphSimulator/simpleGraphSimulator.cpp:142-271 in spirit (scaffold + mutated
 // haplotypes + a large-gap haplotype) with gene blocks carrying allele tables added. Not a port of it.
+#include <zlib.h>
 #include "../host/arrayfile.h"
 
 #include <algorithm>
@@ -611,15 +612,73 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- bam
+// Writes a seed batch as the BAM `bwa mem -a -M` would produce for it (test input of the BAM ingest): header with the PRG contigs in
+// sequences.txt order, one record per chain in batch order (unsorted), names r%09d, flags paired / first or last mate / reverse / secondary,
+// SEQ and QUAL on primary records only ('*' on secondary ones, as bwa writes them), AS:i tags. BGZF per SAM specification §4.1.
+struct Bgzf {
+    FILE* f; std::vector<uint8_t> buf;
+    explicit Bgzf(const std::string& path) { f = fopen(path.c_str(), "wb"); if (!f) throw std::runtime_error("cannot write " + path); }
+    void flush_block(const uint8_t* p, size_t n) {
+        uint8_t comp[70000]; z_stream zs; memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2");
+        zs.next_in = const_cast<Bytef*>(p); zs.avail_in = (uInt)n; zs.next_out = comp; zs.avail_out = sizeof comp;
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw std::runtime_error("deflate");
+        const size_t cn = zs.total_out; deflateEnd(&zs);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, (uInt)n); const uint16_t bsize = (uint16_t)(cn + 25);
+        uint8_t h[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (uint8_t)(bsize & 255), (uint8_t)(bsize >> 8)};
+        fwrite(h, 1, 18, f); fwrite(comp, 1, cn, f); uint32_t t[2] = {crc, (uint32_t)n}; fwrite(t, 4, 2, f);
+    }
+    void write(const void* p, size_t n) { const uint8_t* q = (const uint8_t*)p; buf.insert(buf.end(), q, q + n); while (buf.size() >= 60000) { flush_block(buf.data(), 60000); buf.erase(buf.begin(), buf.begin() + 60000); } }
+    template <class T> void put(T v) { write(&v, sizeof v); }
+    void close() { if (!buf.empty()) flush_block(buf.data(), buf.size()); flush_block(nullptr, 0); fclose(f); f = nullptr; }
+};
+
+int cmd_bam(const std::map<std::string, std::string>& a) {
+    const std::string prg = sarg(a, "prg", ""), seeds = sarg(a, "seeds", ""), out = sarg(a, "out", "");
+    if (prg.empty() || seeds.empty() || out.empty()) throw std::runtime_error("--prg, --seeds and --out required");
+    std::vector<Contig> cs = load_contigs(prg);
+    ArrayFile f; f.read(seeds);
+    uint64_t n_off = 0; const int64_t* read_off = f.get<int64_t>("read_off", &n_off); const int64_t n_reads = (int64_t)n_off - 1;
+    const uint8_t* bases = f.get<uint8_t>("bases"); const uint8_t* quals = f.get<uint8_t>("quals");
+    const int32_t* chain_off = f.get<int32_t>("chain_off"); const int32_t* chain_contig = f.get<int32_t>("chain_contig"); const int32_t* chain_pos = f.get<int32_t>("chain_pos");
+    const uint16_t* chain_flag = f.get<uint16_t>("chain_flag"); const int32_t* chain_as = f.get<int32_t>("chain_as"); const int32_t* cigar_off = f.get<int32_t>("cigar_off"); const uint32_t* cigar = f.get<uint32_t>("cigar");
+    Bgzf z(out);
+    std::string text = "@HD\tVN:1.6\tSO:unsorted\n"; for (const Contig& c : cs) text += "@SQ\tSN:PRG_" + std::to_string(c.id) + "\tLN:" + std::to_string(c.seq.size()) + "\n";
+    z.write("BAM\1", 4); z.put<int32_t>((int32_t)text.size()); z.write(text.data(), text.size()); z.put<int32_t>((int32_t)cs.size());
+    for (const Contig& c : cs) { const std::string n = "PRG_" + std::to_string(c.id); z.put<int32_t>((int32_t)n.size() + 1); z.write(n.c_str(), n.size() + 1); z.put<int32_t>((int32_t)c.seq.size()); }
+    auto code = [](uint8_t b) -> uint8_t { const char* t = "=ACMGRSVTWYHKDBN"; const char* q = strchr(t, (char)b); return q ? (uint8_t)(q - t) : 15; };
+    for (int64_t r = 0; r < n_reads; r++) {
+        char name[32]; snprintf(name, sizeof name, "r%09lld", (long long)(r / 2));
+        const int64_t b0 = read_off[r]; const int32_t L = (int32_t)(read_off[r + 1] - b0);
+        for (int32_t c = chain_off[r]; c < chain_off[r + 1]; c++) {
+            const bool secondary = (chain_flag[c] & 0x100) != 0; const int32_t l_seq = secondary ? 0 : L; const int32_t n_cig = cigar_off[c + 1] - cigar_off[c];
+            const uint16_t flag = (uint16_t)((chain_flag[c] & 0x110) | 0x1 | ((r & 1) ? 0x80 : 0x40));
+            std::vector<uint8_t> rec;
+            auto put32 = [&](int32_t v) { const uint8_t* q = (const uint8_t*)&v; rec.insert(rec.end(), q, q + 4); }; auto put16 = [&](uint16_t v) { rec.push_back((uint8_t)(v & 255)); rec.push_back((uint8_t)(v >> 8)); };
+            put32(chain_contig[c]); put32(chain_pos[c]); rec.push_back((uint8_t)(strlen(name) + 1)); rec.push_back(60); put16(4680); put16((uint16_t)n_cig); put16(flag); put32(l_seq); put32(-1); put32(-1); put32(0);
+            rec.insert(rec.end(), name, name + strlen(name) + 1);
+            for (int32_t k = cigar_off[c]; k < cigar_off[c + 1]; k++) put32((int32_t)cigar[k]);
+            for (int32_t i = 0; i < l_seq; i += 2) rec.push_back((uint8_t)((code(bases[b0 + i]) << 4) | (i + 1 < l_seq ? code(bases[b0 + i + 1]) : 0)));
+            for (int32_t i = 0; i < l_seq; i++) rec.push_back((uint8_t)(quals[b0 + i] - 33));
+            rec.push_back('A'); rec.push_back('S'); rec.push_back('i'); put32(chain_as[c]);
+            z.put<int32_t>((int32_t)rec.size()); z.write(rec.data(), rec.size());
+        }
+    }
+    z.close();
+    return 0;
+}
+
 } // namespace
 
 int main(int argc, char** argv) {
     try {
-        if (argc < 2) { fprintf(stderr, "usage: hlala-synth prg|reads --key value ...\n"); return 2; }
+        if (argc < 2) { fprintf(stderr, "usage: hlala-synth prg|reads|bam --key value ...\n"); return 2; }
         std::string cmd = argv[1];
         auto a = parse_args(argc, argv, 2);
         if (cmd == "prg") return cmd_prg(a);
         if (cmd == "reads") return cmd_reads(a);
+        if (cmd == "bam") return cmd_bam(a);
         fprintf(stderr, "unknown command %s\n", cmd.c_str());
         return 2;
     } catch (const std::exception& e) {

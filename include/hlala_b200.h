@@ -217,6 +217,26 @@ int hlala_kmer_chains_fetch(const hlala_kmer_chains_t* c, int64_t* chain_off, in
 int hlala_kmer_chains_timing(const hlala_kmer_chains_t* c, double ms[2]);
 void hlala_kmer_chains_free(hlala_kmer_chains_t* c);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * BAM ingest: the remapped BAM (bwa mem -a -M against the PRG-only reference) -> seed batch, in one streaming pass.
+ *   hlala_bam_read   processBAM::getReadIDs mapper/processBAM.cpp:169 + processBAM::extractSeeds2 :703 + protoSeeds::takeAlignment
+ *                    mapper/reads/protoSeeds.cpp:24 + the isComplete filter and name order of alignReads_postSeedExtraction_andStoreInto :2362-2377
+ * Reads 2p / 2p+1 of the view are the first / other mate of pair p; pairs are in byte order of their names (the reference iterates a
+ * std::map<std::string, protoSeeds>). The view and the names point into the batch object. counts: [0] records in the file, [1] records
+ * kept, [2] read names with a kept record, [3] pairs dropped because a mate has no primary record. is_mean / is_sd / is_n: gap between the
+ * mates of properly oriented primary pairs (the reference estimates the insert size by random sampling, estimateInsertSize :865; ours is
+ * the deterministic full-file statistic and can be overridden by the caller). */
+typedef struct hlala_bam_batch hlala_bam_batch_t;
+int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads /* <=0: all cores */, hlala_bam_batch_t** out);
+int hlala_bam_batch_view(const hlala_bam_batch_t* b, hlala_seed_batch_t* view, const char* const** pair_names);
+int hlala_bam_batch_stats(const hlala_bam_batch_t* b, int64_t counts[4], double* is_mean, double* is_sd, int64_t* is_n);
+void hlala_bam_batch_free(hlala_bam_batch_t* b);
+
+/* Let the session own the per-level coverage histogram (processBAM.cpp:2411-2426): zeroed at every hlala_session_run that is given no
+ * bases_per_level_dev, copied out as int32[n_levels-1]. */
+int hlala_session_set_coverage(hlala_session_t* s, int on);
+int hlala_session_fetch_coverage(hlala_session_t* s, int32_t* bases_per_level);
+
 #ifdef __cplusplus
 }
 #endif

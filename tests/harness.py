@@ -9,6 +9,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(REPO, "hla-la_b200")
 SYNTH = os.path.join(PKG, "build", "hlala-synth")
+CLI = os.path.join(PKG, "build", "hlala-b200")
 LIB_PRODUCT = os.environ.get("HLALA_B200_LIB") or os.path.join(PKG, "build", "libhlala_b200.so")   # the override is for A/B timing of two builds in one GPU call
 LIB_ORACLE = os.path.join(REPO, "oracle", "build", "libhlala_oracle.so")
 LIB_REF = os.path.join(REPO, "oracle", "_ref", "libhlala_ref.so")
@@ -298,6 +299,37 @@ def same_chains(a, b):
     return all(a[k].shape == b[k].shape and (a[k] == b[k]).all() for k in ("chain_off", "begin", "end", "edge_off", "edges"))
 
 
+def synth_bam(prg_dir, seeds_file, out_bam):
+    subprocess.run([SYNTH, "bam", "--prg", prg_dir, "--seeds", seeds_file, "--out", out_bam], check=True, stderr=subprocess.DEVNULL)
+
+
+def write_bam(path, refs, records, block=40000):
+    """Minimal BAM writer for the ingest tests. refs: [(name, length)]; records: dicts with name, flag, ref, pos, cigar [(op char, len)],
+    seq (str, may be ''), qual (bytes of phred values), tags {b'AS': int}. BGZF blocks of `block` uncompressed bytes."""
+    import zlib
+    out = bytearray(b"BAM\1")
+    text = b"@HD\tVN:1.6\tSO:unsorted\n" + b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (n.encode(), ln) for n, ln in refs)
+    out += struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for n, ln in refs:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", ln)
+    code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    for r in records:
+        nm = r["name"].encode() + b"\0"; cig = b"".join(struct.pack("<I", (ln << 4) | "MIDNSHP=X".index(op)) for op, ln in r["cigar"])
+        seq = r.get("seq", ""); packed = bytearray()
+        for i in range(0, len(seq), 2):
+            packed.append((code[seq[i]] << 4) | (code[seq[i + 1]] if i + 1 < len(seq) else 0))
+        aux = b""
+        for tag, val in r.get("tags", {}).items():
+            aux += tag + (b"Z" + val + b"\0" if isinstance(val, bytes) else b"i" + struct.pack("<i", val))
+        body = struct.pack("<iiBBHHHiiii", r["ref"], r["pos"], len(nm), 60, 4680, len(r["cigar"]), r["flag"], len(seq), -1, -1, 0) + nm + cig + bytes(packed) + bytes(r.get("qual", b"")) + aux
+        out += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as f:
+        for o in list(range(0, len(out), block)) + [None]:
+            chunk = bytes(out[o:o + block]) if o is not None else b""
+            co = zlib.compressobj(1, zlib.DEFLATED, -15); comp = co.compress(chunk) + co.flush()
+            f.write(struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(comp) + 25) + comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
 _REF_CACHE = {}
 
 
@@ -430,6 +462,30 @@ class Product:
         return o
 
 
+
+    # ---- BAM ingest
+    def bam_read(self, path, threads=0):
+        L = self.lib; h = C.c_void_p()
+        self._chk(L.hlala_bam_read(self.g, path.encode(), C.c_int(threads), C.byref(h)))
+        try:
+            v = SeedBatch(); names = C.POINTER(C.c_char_p)()
+            self._chk(L.hlala_bam_batch_view(h, C.byref(v), C.byref(names)))
+            nr = v.n_reads; dts = dict(read_off=np.int64, bases=np.uint8, quals=np.uint8, chain_off=np.int32, chain_contig=np.int32, chain_pos=np.int32, chain_flag=np.uint16, chain_as=np.int32, cigar_off=np.int32, cigar=np.uint32)
+
+            def arr(key, n):
+                ptr = getattr(v, key)
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dts[key]))), shape=(n,)).copy() if n and ptr else np.zeros(n, dts[key])
+            b = {"read_off": arr("read_off", nr + 1)}
+            nb = int(b["read_off"][-1]); b["bases"] = arr("bases", nb) if nb else np.zeros(1, np.uint8); b["quals"] = arr("quals", nb) if nb else np.zeros(1, np.uint8)
+            b["chain_off"] = arr("chain_off", nr + 1); nc = int(b["chain_off"][-1])
+            for k in ("chain_contig", "chain_pos", "chain_flag", "chain_as"):
+                b[k] = arr(k, nc)
+            b["cigar_off"] = arr("cigar_off", nc + 1); b["cigar"] = arr("cigar", int(b["cigar_off"][-1]))
+            cnt = (C.c_int64 * 4)(); m = C.c_double(); sd = C.c_double(); n = C.c_int64()
+            self._chk(L.hlala_bam_batch_stats(h, cnt, C.byref(m), C.byref(sd), C.byref(n)))
+            return b, [names[i].decode() for i in range(nr // 2)], dict(records=cnt[0], used=cnt[1], names=cnt[2], incomplete=cnt[3], is_mean=m.value, is_sd=sd.value, is_n=n.value)
+        finally:
+            L.hlala_bam_batch_free(h)
 
     # ---- k-mer seeding
     def kmer_index(self, k):
