@@ -381,9 +381,9 @@ def main():
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_gpus * args.pairs * len(e2e_times) / float(te.item())
+    e2e_value = n_gpus * args.pairs * len(e2e_times) / float(te.item()) if e2e_times else None
     if rank == 0:
-        sys.stderr.write("[bench] e2e: %.0f pairs/s (%s s per call)\n" % (e2e_value, [round(x, 3) for x in e2e_times]))
+        sys.stderr.write("[bench] e2e: %s pairs/s (%s s per call)\n" % (e2e_value, [round(x, 3) for x in e2e_times]))
 
     if rank != 0:
         if dist:

@@ -15,13 +15,17 @@ namespace hlala {
 template <int GW_, int LIST_, int TD_, int TDHASH_, int CELLS_, int HASH_, int WARPS_> struct GdCfg {
     static constexpr int GW = GW_, LIST = LIST_, TD = TD_, TDHASH = TDHASH_, CELLS = CELLS_, HASH = HASH_, WARPS = WARPS_, NG = 32 / GW_;
 };
-typedef GdCfg<8, 16, 24, 64, 2048, 4096, 4> GdOctS;     // 3.1 KB of shared memory per group
-typedef GdCfg<8, 24, 32, 64, 2048, 4096, 4> GdOct;      // 4.0 KB: holds 96 % of the bench workload's extensions (LIST 16 holds 80 %)
+typedef GdCfg<8, 24, 32, 64, 2048, 4096, 4> GdOct;      // 3.4 KB of shared memory per group: holds 96 % of the bench workload's extensions (LIST 16 holds 80 %)
 
-struct GdSlab { WdEntry* l[3]; uint32_t* tkey; int32_t* tnode; uint32_t* kD; uint32_t* kGG; uint32_t* kSG; uint16_t* slots; uint16_t* order; int32_t* cnt; };
-template <class CFG> __host__ __device__ inline size_t gd_slab_bytes() { return (sizeof(WdEntry) * CFG::LIST * 3 + 20 * CFG::TDHASH + 2 * CFG::TD * 2 + 16 + 15) & ~size_t(15); }
+// wavefront entry of the group kernel: WdEntry packed into 28 bytes (cell index 16 bit, level relative to the start level, z / degrees 8 bit), so
+// that a group's slab is 3.4 KB and four CTAs (64 groups) fit an SM's shared memory instead of three
+struct GdEntry { int32_t node; int32_t k0; int32_t j0; uint16_t cell; int16_t xr; int16_t y; int16_t D, GG, SG; uint8_t z, deg, jdeg, pad; };
+static_assert(sizeof(GdEntry) == 28, "GdEntry layout");
+
+struct GdSlab { GdEntry* l[3]; uint32_t* tkey; int32_t* tnode; uint32_t* kD; uint32_t* kGG; uint32_t* kSG; uint16_t* slots; uint16_t* order; int32_t* cnt; };
+template <class CFG> __host__ __device__ inline size_t gd_slab_bytes() { return (sizeof(GdEntry) * CFG::LIST * 3 + 20 * CFG::TDHASH + 2 * CFG::TD * 2 + 16 + 15) & ~size_t(15); }
 template <class CFG> __device__ inline GdSlab gd_carve(unsigned char* p) {
-    GdSlab s; for (int i = 0; i < 3; i++) { s.l[i] = (WdEntry*)p; p += sizeof(WdEntry) * CFG::LIST; }
+    GdSlab s; for (int i = 0; i < 3; i++) { s.l[i] = (GdEntry*)p; p += sizeof(GdEntry) * CFG::LIST; }
     s.tkey = (uint32_t*)p; p += 4 * CFG::TDHASH; s.tnode = (int32_t*)p; p += 4 * CFG::TDHASH; s.kD = (uint32_t*)p; p += 4 * CFG::TDHASH; s.kGG = (uint32_t*)p; p += 4 * CFG::TDHASH; s.kSG = (uint32_t*)p; p += 4 * CFG::TDHASH;
     s.slots = (uint16_t*)p; p += 2 * CFG::TD; s.order = (uint16_t*)p; p += 2 * CFG::TD; s.cnt = (int32_t*)p; return s;
 }
@@ -39,7 +43,7 @@ template <int GW> struct Grp {
     __device__ __forceinline__ unsigned below() const { return (1u << lane) - 1u; }
 };
 
-template <class CFG> __device__ __forceinline__ int gd_touch(const GdSlab& S, int start_level, int x, int y, int z, int node) {
+template <class CFG> __device__ __noinline__ int gd_touch(const GdSlab& S, int start_level, int x, int y, int z, int node) {
     const int xrel = x - start_level + 2048;
     if (xrel < 0 || xrel > 4095) return -1;
     const uint32_t key = wd_pack(xrel, y, z);
@@ -52,7 +56,7 @@ template <class CFG> __device__ __forceinline__ int gd_touch(const GdSlab& S, in
     }
     return -1;
 }
-template <class CFG> __device__ __forceinline__ int gd_find_cell(const WdCtx& C, uint32_t cgen, int x, int y, int z) {
+template <class CFG> __device__ __noinline__ int gd_find_cell(const WdCtx& C, uint32_t cgen, int x, int y, int z) {
     uint32_t h = dp_hash3(x, y, z) & (CFG::HASH - 1);
     for (;;) {
         const uint32_t v = C.hash[h];
@@ -62,13 +66,25 @@ template <class CFG> __device__ __forceinline__ int gd_find_cell(const WdCtx& C,
         h = (h + 1) & (CFG::HASH - 1);
     }
 }
-template <class CFG> __device__ __forceinline__ void gd_insert_cell(const WdCtx& C, uint32_t cgen, int x, int y, int z, int idx) {
+template <class CFG> __device__ __noinline__ void gd_insert_cell(const WdCtx& C, uint32_t cgen, int x, int y, int z, int idx) {
     uint32_t h = dp_hash3(x, y, z) & (CFG::HASH - 1);
     for (;;) {
         const uint32_t v = C.hash[h];
         if ((v >> 16) != cgen) { if (atomicCAS(&C.hash[h], v, (cgen << 16) | (uint32_t)idx) == v) return; continue; }
         h = (h + 1) & (CFG::HASH - 1);
     }
+}
+
+// decode the backtrace step of a winning candidate (wd_decode for the packed entries)
+__device__ __noinline__ DpBT gd_decode(const WdCtx& C, const GdEntry* m1, const GdEntry* m2, uint32_t key, int matrix /*0 D,1 GG,2 SG*/) {
+    const uint32_t seq = wd_seq(key); const int type = seq & 1; const int sub = (seq >> 1) & (WD_SUB - 1); const int li = seq >> 7; const int list = li / 2048, i = li % 2048;
+    const GdEntry& src = list == 0 ? m2[i] : m1[i];
+    if (matrix == 1) return dp_bt(src.cell, -1, type == 0 ? 0 : 1);
+    const void* el = C.pos ? C.G->out_adj4 : C.G->in_adj4;
+    if (matrix == 2) return dp_bt(src.cell, ld4(el, src.k0 + sub).x, type == 0 ? 0 : 2);
+    if (sub < (int)src.deg) return dp_bt(src.cell, ld4(el, src.k0 + sub).x, 0);
+    const void* jl = C.pos ? C.G->jf4 : C.G->jb4;
+    return dp_bt(src.cell, -2 - ld4(jl, src.j0 + (sub - (int)src.deg)).x, 0);
 }
 
 // per-group DP state (uniform across the lanes of a group)
@@ -80,9 +96,9 @@ template <class CFG> __device__ __forceinline__ void gd_init(const WdCtx& C, con
     if (g.lane == 0) {
         DpCell& c = C.cells[0]; c.x = C.start_level; c.y = (int16_t)C.start_seq; c.z = (int16_t)C.start_z; c.D = 0; c.GG = c.SG = (int16_t)DP_NEG; c.pad = 0;
         c.bD = c.bGG = c.bSG = dp_bt(-1, -1, -1);
-        WdEntry& e = S.l[0][0]; e.cell = 0; e.node = C.start_node; e.x = C.start_level; e.y = (int16_t)C.start_seq; e.z = (int16_t)C.start_z; e.D = 0; e.GG = e.SG = (int16_t)DP_NEG;
-        int deg, jdeg; wd_adj(C, C.start_node, e.k0, deg, e.j0, jdeg); e.deg = (uint16_t)deg; e.jdeg = (uint16_t)jdeg;
-        e.pad = (uint16_t)((G.node_gapflags[C.start_node] >> (C.pos ? 0 : 1)) & 1);
+        GdEntry& e = S.l[0][0]; e.cell = 0; e.node = C.start_node; e.xr = 0; e.y = (int16_t)C.start_seq; e.z = (uint8_t)C.start_z; e.D = 0; e.GG = e.SG = (int16_t)DP_NEG;
+        int deg, jdeg; wd_adj(C, C.start_node, e.k0, deg, e.j0, jdeg); e.deg = (uint8_t)min(deg, 255); e.jdeg = (uint8_t)min(jdeg, 255);
+        e.pad = (uint8_t)((G.node_gapflags[C.start_node] >> (C.pos ? 0 : 1)) & 1);
         *S.cnt = 0;
     }
     for (int i = g.lane; i < CFG::TDHASH; i += CFG::GW) { S.tkey[i] = 0; S.kD[i] = 0; S.kGG[i] = 0; S.kSG[i] = 0; }
@@ -97,21 +113,21 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
     const int max_level = G.n_levels - 1, max_seq = C.seq_len;
     const int dir = C.pos ? 1 : -1; const int end_seq = C.pos ? max_seq : 0;
     const void* el = C.pos ? G.out_adj4 : G.in_adj4; const void* jl = C.pos ? G.jf4 : G.jb4;
-    WdEntry* m1 = S.l[st.rot]; WdEntry* m2 = S.l[(st.rot + 2) % 3]; WdEntry* mt = S.l[(st.rot + 1) % 3];
+    GdEntry* m1 = S.l[st.rot]; GdEntry* m2 = S.l[(st.rot + 2) % 3]; GdEntry* mt = S.l[(st.rot + 1) % 3];
     const int lane = g.lane; const int n_m1 = st.n_m1, n_m2 = st.n_m2;
     const int diag = ++st.diag;
     if (diag - st.last_inc > 40) return 1;
     if (n_m1 == 0 && n_m2 == 0) return 1;
     {   // exact early exit (see extend_warp.cuh)
         bool live = false;
-        for (int i = lane; i < n_m1; i += GW) { const WdEntry& e = m1[i]; live |= (e.y != end_seq) || e.pad || e.jdeg; }
+        for (int i = lane; i < n_m1; i += GW) { const GdEntry& e = m1[i]; live |= (e.y != end_seq) || e.pad || e.jdeg; }
         for (int i = lane; i < n_m2; i += GW) live |= (m2[i].y != end_seq);
         if (!g.any(live)) return 1;
     }
     bool ovf = false, saw_jump = false;
     for (int i = lane; i < n_m2; i += GW) {
-        const WdEntry pc = m2[i];
-        const int nx = pc.x + dir, ny = pc.y + dir;
+        const GdEntry pc = m2[i]; const int pcx = C.start_level + pc.xr;
+        const int nx = pcx + dir, ny = pc.y + dir;
         if (nx > max_level || ny > max_seq || nx < 0 || ny < 0) continue;
         const uint8_t sc = C.pos ? C.seq[pc.y] : C.seq[pc.y - 1];
         if (pc.deg > WD_SUB) { ovf = true; continue; }
@@ -123,13 +139,13 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
         }
     }
     for (int i = lane; i < n_m1; i += GW) {
-        const WdEntry pc = m1[i];
-        { const int gy = pc.y + dir; const bool ok = C.pos ? (pc.x <= max_level && gy <= max_seq) : (pc.x >= 0 && gy >= 0);
-          if (ok) { const int ti = gd_touch<CFG>(S, C.start_level, pc.x, gy, pc.z, pc.node); if (ti < 0) ovf = true; else {
+        const GdEntry pc = m1[i]; const int pcx = C.start_level + pc.xr;
+        { const int gy = pc.y + dir; const bool ok = C.pos ? (pcx <= max_level && gy <= max_seq) : (pcx >= 0 && gy >= 0);
+          if (ok) { const int ti = gd_touch<CFG>(S, C.start_level, pcx, gy, pc.z, pc.node); if (ti < 0) ovf = true; else {
               atomicMax(&S.kGG[ti], wd_key(pc.D - 6, wd_mkseq(1, i, 0, 0)));
               atomicMax(&S.kGG[ti], wd_key(pc.GG <= DP_NEG ? DP_NEG : pc.GG - 2, wd_mkseq(1, i, 0, 1))); } } }
         if ((int)pc.deg + (int)pc.jdeg > WD_SUB) { ovf = true; continue; }
-        { const int sx = pc.x + dir; const bool ok = C.pos ? (sx <= max_level && pc.y <= max_seq) : (sx >= 0 && pc.y >= 0);
+        { const int sx = pcx + dir; const bool ok = C.pos ? (sx <= max_level && pc.y <= max_seq) : (sx >= 0 && pc.y >= 0);
           if (ok) for (int k = 0; k < (int)pc.deg; k++) {
               const I4 a = ld4(el, pc.k0 + k); const uint32_t pk = (uint32_t)a.z;
               const int nz = C.pos ? (int)((pk >> 8) & 255u) : (int)(pk & 255u); const bool gapEdge = ((uint8_t)(pk >> 16) == '_');
@@ -140,7 +156,7 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
           } }
         for (int j = 0; j < (int)pc.jdeg; j++) {
             const I4 jp = ld4(jl, pc.j0 + j);
-            const int jx = pc.x + dir * jp.w;
+            const int jx = pcx + dir * jp.w;
             const bool ok = C.pos ? (jx <= max_level && pc.y <= max_seq) : (jx >= 0 && pc.y >= 0);
             if (!ok) continue;
             const int ti = gd_touch<CFG>(S, C.start_level, jx, pc.y, jp.z, jp.y); if (ti < 0) { ovf = true; break; }
@@ -192,13 +208,13 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
         int excl = g.shfl_up(incl, 1); if (lane == 0) excl = -1000000;
         const int running = max(run_max, excl);
         bool overwritten = false; int stD = DP_NEG, stGG = DP_NEG, stSG = DP_NEG; bool tie_counts = false;
-        WdEntry ne;
+        GdEntry ne;
         if (keep) {
             DpCell& c = C.cells[ci];
             if (isNew) { c.x = tx; c.y = (int16_t)ty; c.z = (int16_t)tz; c.pad = 0; c.D = c.GG = c.SG = (int16_t)DP_NEG; c.bD = c.bGG = c.bSG = dp_bt(-1, -1, -1); }
-            if (isNew || c.D < selD) { overwritten = !isNew; c.D = (int16_t)selD; c.bD = selfmat ? dp_bt(ci, -1, selfmat) : wd_decode(C, m1, m2, kD, 0); }
-            if (isNew || c.GG < selGG) { overwritten = !isNew; c.GG = (int16_t)selGG; c.bGG = kGG ? wd_decode(C, m1, m2, kGG, 1) : dp_bt(-1, -1, -1); }
-            if (isNew || c.SG < selSG) { overwritten = !isNew; c.SG = (int16_t)selSG; c.bSG = kSG ? wd_decode(C, m1, m2, kSG, 2) : dp_bt(-1, -1, -1); }
+            if (isNew || c.D < selD) { overwritten = !isNew; c.D = (int16_t)selD; c.bD = selfmat ? dp_bt(ci, -1, selfmat) : gd_decode(C, m1, m2, kD, 0); }
+            if (isNew || c.GG < selGG) { overwritten = !isNew; c.GG = (int16_t)selGG; c.bGG = kGG ? gd_decode(C, m1, m2, kGG, 1) : dp_bt(-1, -1, -1); }
+            if (isNew || c.SG < selSG) { overwritten = !isNew; c.SG = (int16_t)selSG; c.bSG = kSG ? gd_decode(C, m1, m2, kSG, 2) : dp_bt(-1, -1, -1); }
             if (ty == end_seq) c.pad = 1;
             stD = c.D; stGG = c.GG; stSG = c.SG;
             if (overwritten) for (int i = 0; i < n_m1; i++) if (m1[i].cell == ci) { m1[i].D = (int16_t)stD; m1[i].GG = (int16_t)stGG; m1[i].SG = (int16_t)stSG; }   // see extend_warp.cuh
@@ -210,8 +226,8 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
                 if (step.src >= 0) { const DpCell& pc = C.cells[step.src]; prev = step.mat == 0 ? pc.D : (step.mat == 1 ? pc.GG : pc.SG); }
                 tie_counts = (selD - prev) != 0;
             }
-            ne.cell = ci; ne.node = tn; ne.x = tx; ne.y = (int16_t)ty; ne.z = (int16_t)tz; ne.D = (int16_t)stD; ne.GG = (int16_t)stGG; ne.SG = (int16_t)stSG; ne.pad = (uint16_t)((__ldg(G.node_gapflags + tn) >> (C.pos ? 0 : 1)) & 1);
-            int deg, jdeg; wd_adj(C, tn, ne.k0, deg, ne.j0, jdeg); ne.deg = (uint16_t)min(deg, 65535); ne.jdeg = (uint16_t)min(jdeg, 65535);
+            ne.cell = (uint16_t)ci; ne.node = tn; ne.xr = (int16_t)(tx - C.start_level); ne.y = (int16_t)ty; ne.z = (uint8_t)tz; ne.D = (int16_t)stD; ne.GG = (int16_t)stGG; ne.SG = (int16_t)stSG; ne.pad = (uint8_t)((__ldg(G.node_gapflags + tn) >> (C.pos ? 0 : 1)) & 1);
+            int deg, jdeg; wd_adj(C, tn, ne.k0, deg, ne.j0, jdeg); ne.deg = (uint8_t)min(deg, 255); ne.jdeg = (uint8_t)min(jdeg, 255);
         }
         { const unsigned em = g.ballot(keep && ty == end_seq); if (em && st.end_c < 0) st.end_c = g.shfl(ci, __ffs(em) - 1); }   // first sequence-complete cell: the end-cell scan starts there
         if (g.any(keep && (selD > running || tie_counts || overwritten))) any_inc = true;
@@ -238,7 +254,7 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
         for (int d = GW / 2; d; d >>= 1) mx = max(mx, g.shfl_xor(mx, d));
         int w = 0;
         for (int base = 0; base < n_mt; base += GW) {
-            const int i = base + lane; const bool in = i < n_mt; WdEntry e; if (in) e = mt[i];
+            const int i = base + lane; const bool in = i < n_mt; GdEntry e; if (in) e = mt[i];
             const bool k = in && (mx - e.D <= 15);
             const unsigned m = g.ballot(k);
             g.sync();
@@ -253,7 +269,7 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
 }
 
 // end cell + backtrace (lane 0 of the group); returns rc and fills res
-template <class CFG> __device__ __forceinline__ int gd_finish(const WdCtx& C, const GdState& st, const Grp<CFG::GW>& g, int32_t* out_edge, uint8_t* out_s, DpResult& res) {
+template <class CFG> __device__ __noinline__ int gd_finish(const WdCtx& C, const GdState& st, const Grp<CFG::GW>& g, int32_t* out_edge, uint8_t* out_s, DpResult& res) {
     constexpr int GW = CFG::GW;
     const DpGraph& G = *C.G; const int end_seq = C.pos ? C.seq_len : 0; const int lane = g.lane;
     res.n_cols = 0; res.n_lvl = 0; res.far_y = C.start_seq;
