@@ -5,6 +5,11 @@
 #include "hla_typing.h"
 
 #include <algorithm>
+#include <exception>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <dirent.h>
@@ -346,10 +351,19 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     for (size_t p = 0; p < NP; p++) { const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1]; TY_REQUIRE(a.mapQ >= 0 && a.mapQ <= 1, "mapQ in [0,1]");
         gate[p] = strands_ok(a, b) && fabs(level_distance(a, b) - is_mean) <= 5 * is_sd && a.mapQ >= min_mapq && a.weighted_ok >= min_weighted && b.weighted_ok >= min_weighted; }
 
-    std::vector<std::string> locus_names;
-    for (TypingLocus& L : T.loci) {
-        locus_names.push_back(L.name);
-        LocusCall call; call.locus = L.name; const int32_t C = L.C(), P = L.P(); call.C = C;
+    // The loci are independent up to the order of their lines in the shared files and the order of the device stage (with several ranks
+    // the per-locus all-reduce must be issued in the same order everywhere): host work of different loci runs on a thread pool, the device
+    // stage is entered in locus order, and the shared files are assembled in locus order afterwards.
+    struct LocusOut { LocusCall call; std::string hist, best, bestG; std::exception_ptr err; };
+    const size_t NL = T.loci.size(); std::vector<LocusOut> outs(NL);
+    T.load_G(g_dir);
+    std::mutex dev_mu; std::condition_variable dev_cv; size_t dev_turn = 0;
+    auto take_turn = [&](size_t li) { std::unique_lock<std::mutex> lk(dev_mu); dev_cv.wait(lk, [&]() { return dev_turn == li; }); };
+    auto pass_turn = [&](size_t li) { { std::lock_guard<std::mutex> lk(dev_mu); if (dev_turn == li) dev_turn = li + 1; } dev_cv.notify_all(); };
+    auto process = [&](size_t li) {
+        TypingLocus& L = T.loci[li]; LocusCall& call = outs[li].call;
+        std::ostringstream hist, best, bestG;   // this locus' lines of histogram_matchesPerRead.txt / R1_bestguess.txt / R1_bestguess_G.txt
+        call.locus = L.name; const int32_t C = L.C(), P = L.P(); call.C = C;
         // ---- exon observations per read pair
         std::vector<std::vector<ExonObs>> reads;
         for (size_t p = 0; p < NP; p++) {
@@ -421,7 +435,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
                 di.rec_pos.push_back((int16_t)e.pos); di.rec_c0.push_back(gap ? (uint8_t)'_' : (uint8_t)e.genotype[0]); di.rec_q0.push_back(gap ? 0 : (uint8_t)e.qualities[0]); di.rec_glen.push_back((uint16_t)std::min<size_t>(e.genotype.size(), 65535)); bases_used++; }
             di.rec_off.push_back((int32_t)di.rec_pos.size());
         }
-        dev.run_locus(di, opt.keep_read_ll, call.dev);
+        take_turn(li); try { dev.run_locus(di, opt.keep_read_ll, call.dev); } catch (...) { pass_turn(li); throw; } pass_turn(li);
         const std::vector<double>& LLs = call.dev.pair_ll; const std::vector<double>& Mavg = call.dev.pair_mavg; const std::vector<double>& Mmin = call.dev.pair_mmin;
         const size_t NPAIR = (size_t)C * ((size_t)C + 1) / 2; TY_REQUIRE(LLs.size() == NPAIR && Mavg.size() == NPAIR && Mmin.size() == NPAIR, "pair arrays complete");
         std::vector<std::pair<uint32_t, uint32_t>> ids; ids.reserve(NPAIR); for (uint32_t c1 = 0; c1 < (uint32_t)C; c1++) for (uint32_t c2 = c1; c2 < (uint32_t)C; c2++) ids.push_back({c1, c2});
@@ -472,7 +486,6 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         const double first_decile = pos_cov.at((size_t)((double)pos_cov.size() / 10.0)), min_cov = pos_cov.at(0);
         auto row = [&](std::ostream& o, int chrom, const std::string& allele, double qa) { o << L.name << "\t" << chrom << "\t" << allele << "\t" << qa << "\t" << b2.first << "\t" << locus_cov << "\t" << first_decile << "\t" << min_cov << "\t" << (chrom == 1 ? k1 : k2) << "\t" << avg_err << "\t" << n_unacc; };
         row(best, 1, call.call1, b1.first); best << "\n"; row(best, 2, call.call2, p2.first); best << "\n" << std::flush;
-        T.load_G(g_dir);
         if (T.G_loci.count(L.name)) {   // HLATyper.cpp:4095-4148
             auto to_G = [&](const std::vector<std::string>& alleles, bool& perfect) -> std::string {
                 std::map<std::string, int> groups;
@@ -486,8 +499,26 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             row(bestG, 1, g1, b1.first); bestG << "\t" << p1 << "\n"; row(bestG, 2, g2, p2.first); bestG << "\t" << p2g << "\n" << std::flush;
         }
         if (!opt.keep_read_ll) { call.dev.LL.clear(); call.dev.LL.shrink_to_fit(); call.dev.mism.clear(); call.dev.mism.shrink_to_fit(); }
-        calls.push_back(std::move(call));
+        outs[li].hist = hist.str(); outs[li].best = best.str(); outs[li].bestG = bestG.str();
+    };
+    {
+        std::atomic<size_t> next(0);
+        auto worker = [&]() { for (;;) { const size_t li = next.fetch_add(1); if (li >= NL) break;
+            try { process(li); } catch (...) { outs[li].err = std::current_exception(); }
+            { std::unique_lock<std::mutex> lk(dev_mu); dev_cv.wait(lk, [&]() { return dev_turn >= li; }); if (dev_turn == li) dev_turn = li + 1; }   // a locus that failed before its device stage still hands the turn on
+            dev_cv.notify_all(); } };
+        unsigned nt = std::max(1u, std::min<unsigned>((unsigned)NL, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("HLALA_TYPING_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        std::vector<std::thread> th; for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+        worker(); for (auto& t : th) t.join();
     }
+    std::vector<std::string> locus_names;
+    for (size_t li = 0; li < NL; li++) {
+        if (outs[li].err) std::rethrow_exception(outs[li].err);
+        locus_names.push_back(T.loci[li].name); hist << outs[li].hist; best << outs[li].best; bestG << outs[li].bestG;
+        calls.push_back(std::move(outs[li].call));
+    }
+    best << std::flush; bestG << std::flush;
     { std::ofstream ps(target("R1_parameters.txt")); ps << "Loci = " << join_with(locus_names, ",") << "\n" << "veryConservativeReadLikelihoods = " << true << "\n"; }
 }
 
