@@ -699,9 +699,10 @@ TypingScoreTables make_typing_tables() {   // HLATyper.cpp:2060-2066, 2189-2216;
 }
 
 struct GpuTypingDevice : TypingDevice {
-    int rank = 0, world = 1; hlala_allreduce_f64_fn allreduce = nullptr; void* ctx = nullptr; cudaStream_t st = 0;
+    int device = 0, rank = 0, world = 1; hlala_allreduce_f64_fn allreduce = nullptr; void* ctx = nullptr; cudaStream_t st = 0;
     double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0};
     void run_locus(const LocusDeviceInput& in, bool want_read_ll, LocusDeviceOutput& out) override {
+        CUDA_OK(cudaSetDevice(device));   // entered from the host thread pool of run_typing (one locus at a time, in locus order)
         const int32_t C = in.C, P = in.P, R = in.R; const int32_t Cpad = (C + 31) / 32 * 32;
         const size_t npair = (size_t)C * ((size_t)C + 1) / 2;
         std::vector<uint8_t> ct((size_t)P * Cpad, (uint8_t)'_');
@@ -809,8 +810,9 @@ int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs,
         CUDA_OK(cudaSetDevice(device));
         if (!t->tables_on_device || t->device != device) { CUDA_OK(upload_typing_tables(make_typing_tables())); t->tables_on_device = true; t->device = device; }
         TypingReads all; for (int i = 0; i < n_blobs; i++) all.deserialize_append(blobs[i], (size_t)blob_bytes[i]);
-        GpuTypingDevice dev; dev.rank = rank; dev.world = world; dev.allreduce = allreduce; dev.ctx = allreduce_ctx;
+        GpuTypingDevice dev; dev.device = device; dev.rank = rank; dev.world = world; dev.allreduce = allreduce; dev.ctx = allreduce_ctx;
         TypingOptions opt; opt.keep_read_ll = keep_read_ll != 0;
+        if (allreduce) opt.threads = 1;   // the caller's all-reduce callback (NCCL, Python) is only ever entered from the calling thread
         t->calls.clear();
         run_typing(t->T, all, is_mean, is_sd, out_dir ? std::string(out_dir) : std::string(), g_nom_dir, dev, opt, t->calls);
         for (int k = 0; k < 2; k++) { t->ms[k] = dev.ms[k]; t->launches[k] = dev.launches[k]; t->work[k] = dev.work[k]; }

@@ -72,7 +72,7 @@ public:
 
 struct LocusCall { std::string locus; int32_t C = 0, R = 0; std::string call1, call2; double q1 = 0, q2 = 0; LocusDeviceOutput dev; };
 
-struct TypingOptions { bool keep_read_ll = false; };
+struct TypingOptions { bool keep_read_ll = false; int threads = 0; };   // threads: host threads over loci; 0 = one per locus up to the core count, 1 = everything on the calling thread
 
 // Gene filter predicate (processBAM.cpp:2427-2446): either mate's [first,last] level interval overlaps a gene.
 bool pair_overlaps_genes(const TypingTables& T, int32_t f1, int32_t l1, int32_t f2, int32_t l2);
