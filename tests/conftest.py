@@ -30,6 +30,7 @@ DATASETS = {
     "S": (dict(levels=25000, haps=4, genes=2, alleles=64), dict(pairs=1200, len=100, clip_frac=0.15), 100.0, 10.0),
     "typing": (dict(levels=40000, haps=4, genes=17, alleles=24, seed=11), dict(pairs=1500, len=100, seed=11, gene_frac=0.8), 100.0, 10.0),
     "genes": (dict(levels=30000, haps=8, genes=8, alleles=300), dict(pairs=250, len=150, clip_frac=0.15, gene_frac=1.0), 100.0, 10.0),
+    "L250": (dict(levels=20000, haps=6, genes=2, alleles=32, seed=21), dict(pairs=400, len=250, clip_frac=0.3, indel_rate=0.002, seed=21), 250.0, 35.0),
 }
 
 

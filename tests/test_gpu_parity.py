@@ -144,3 +144,31 @@ def test_session_digest_idempotence_and_shard_additivity(dataset, tmp_path):
     assert dig[1] == edges
     assert abs(sll.value - full["pair_ll"].sum()) < 1e-6 * abs(sll.value)
     L.hlala_session_free(sess)
+
+
+def test_pairs_match_oracle_250bp_wide_insert(dataset):
+    """BASELINE.json config sweep: 2x250 bp reads, 30 % soft-clipped, more indels, insert-size model N(250, 35)"""
+    d, b, mu, sd = dataset("L250")
+    want = H.oracle_pairs(d, b, mu, sd, 1024); got = product(d).pairs(b, mu, sd, 1024)
+    assert_pairs_equal(got, want)
+
+
+def test_empty_and_single_pair_batches(dataset):
+    """no pairs at all: nothing is aligned, nothing is counted, no error; a batch of one pair"""
+    d, b, mu, sd = dataset("small")
+    P = product(d)
+    empty = {k: (np.zeros(1, b[k].dtype) if k in ("read_off", "chain_off", "cigar_off") else np.zeros(1, b[k].dtype)[:0].copy()) for k in H.BATCH_KEYS}
+    for k in ("bases", "quals", "chain_contig", "chain_pos", "chain_flag", "chain_as", "cigar"):
+        empty[k] = np.zeros(1, b[k].dtype)          # non-null pointers, zero logical length
+    got = P.pairs(empty, mu, sd, 256)
+    assert len(got["pair_mapq"]) == 0 and int(got["bases_per_level"].sum()) == 0
+    # a single pair on its own gives what it gives inside the batch
+    import sys
+    sys.path.insert(0, H.PKG)
+    import hlala_dist
+    full = P.pairs(b, mu, sd, 512)
+    npairs = (len(b["read_off"]) - 1) // 2
+    one = P.pairs(hlala_dist.shard_batch(b, npairs - 1, npairs), mu, sd, 512)
+    assert np.array_equal(one["n_cols"], full["n_cols"][-2:]) and np.array_equal(one["pair_mapq"], full["pair_mapq"][-1:])
+    for k in ("level", "edge", "schar", "mapq"):
+        assert np.array_equal(one[k], full[k][-2:]), k
