@@ -24,8 +24,8 @@ def test_round_trip_of_a_seed_batch(dataset, tmp_path):
     mate = np.repeat(np.arange(len(b["read_off"]) - 1) & 1, np.diff(b["chain_off"]))
     assert np.array_equal((got["chain_flag"] & 0xC0) == 0x80, mate == 1) and (got["chain_flag"] & 1).all()
     assert st["is_n"] > 100 and 80 < st["is_mean"] < 120     # the generator draws gaps from N(100, 10)
-    one = P.bam_read(bam, threads=1)[0]
-    assert all(np.array_equal(one[k], got[k]) for k in got)
+    one, _names1, st1 = P.bam_read(bam, threads=1)
+    assert all(np.array_equal(one[k], got[k]) for k in got) and st1 == st      # the thread count changes nothing, insert-size estimate included
     P.close()
 
 
