@@ -8,6 +8,7 @@
 // Everything goes through the C ABI (include/hlala_b200.h); there is no CPU fallback.
 #include "../../include/hlala_b200.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,10 @@
 #include <sys/stat.h>
 #include <vector>
 
+static std::chrono::steady_clock::time_point g_t0;
+static void phase(const char* what) {   // wall time of every phase, on stdout
+    const auto t1 = std::chrono::steady_clock::now(); fprintf(stdout, "hlala-b200: [%8.2f s] %s\n", std::chrono::duration<double>(t1 - g_t0).count(), what); g_t0 = t1;
+}
 static int die(const char* what) { fprintf(stderr, "hlala-b200: %s: %s\n", what, hlala_last_error()); return 1; }
 
 int main(int argc, char** argv) {
@@ -28,11 +33,15 @@ int main(int argc, char** argv) {
     }
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"];
     const int device = a.count("device") ? atoi(a["device"].c_str()) : 0; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
+    g_t0 = std::chrono::steady_clock::now();
     hlala_graph_t* g = nullptr;
     if (hlala_graph_load(prg.c_str(), &g)) return die("loading the PRG");
+    phase("PRG loaded (graph.txt, gap paths, contigs, translations)");
     if (hlala_graph_to_gpu(g, device)) return die("uploading the PRG");
+    phase("PRG on the GPU");
     hlala_bam_batch_t* bam = nullptr;
     if (hlala_bam_read(g, a["BAM"].c_str(), a.count("threads") ? atoi(a["threads"].c_str()) : 0, &bam)) return die("reading the BAM");
+    phase("BAM read, records selected and grouped");
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
     if (a.count("insertSizeMean")) is_mean = atof(a["insertSizeMean"].c_str());
@@ -46,6 +55,7 @@ int main(int argc, char** argv) {
     if (hlala_session_create(g, &batch, maxcol, &s)) return die("creating the alignment session");
     hlala_session_set_keep_columns(s, 1); hlala_session_set_coverage(s, 1);
     if (hlala_session_run(s, is_mean, is_sd, 0, nullptr)) return die("aligning");
+    phase("read pairs aligned (batch upload + kernels)");
     int64_t dig[4]; double sll = 0;
     if (hlala_session_digest(s, dig, &sll)) return die("reading the alignment digest");
     if (dig[3] != 0) { fprintf(stderr, "hlala-b200: %lld chains/pairs violated a reference invariant or a kernel capacity\n", (long long)dig[3]); return 1; }
@@ -57,6 +67,7 @@ int main(int argc, char** argv) {
         for (int64_t l = 0; l + 1 < nl; l++) fprintf(f, "%lld\t%s\t%d\n", (long long)l, hlala_graph_level_name(g, l), cov[(size_t)l]);
         fclose(f);
     }
+    phase("reads_per_level.txt written");
     hlala_typer_t* t = nullptr;
     if (hlala_typer_create(prg.c_str(), &t)) return die("loading the typing tables");
     const uint8_t* blob = nullptr; int64_t blob_bytes = 0, n_sel = 0;
@@ -65,6 +76,7 @@ int main(int argc, char** argv) {
     const std::string hla_dir = out_dir + "/hla";
     struct stat sb; const std::string gdir = a.count("hla_nom_g_dir") ? a["hla_nom_g_dir"] : (stat((prg + "/hla_nom_g.txt").c_str(), &sb) == 0 ? prg : std::string("."));   // the reference opens hla_nom_g.txt in the current directory (HLATyper.cpp:4157)
     if (hlala_typer_infer(t, device, &blob, &blob_bytes, 1, is_mean, is_sd, hla_dir.c_str(), gdir.c_str(), 0, 1, nullptr, nullptr, 0)) return die("HLA type inference");
+    phase("HLA types inferred, hla/* written");
     for (int l = 0; l < hlala_typer_n_loci(t); l++) {
         const char* a1 = nullptr; const char* a2 = nullptr; double q1 = 0, q2 = 0;
         if (hlala_typer_result_call(t, l, &a1, &a2, &q1, &q2) == 0) fprintf(stdout, "%s\t%s\t%s\t%g\t%g\n", hlala_typer_locus_name(t, l), a1, a2, q1, q2);
