@@ -256,6 +256,7 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
     const int gcta = threadIdx.x / GW;                               // group inside the CTA
     const int gg = blockIdx.x * (CFG::WARPS * NG) + gcta;
     Grp<GW> g; g.lane = threadIdx.x % GW; g.shift = ((threadIdx.x & 31) / GW) * GW; g.mask = (GW == 32) ? 0xffffffffu : (((1u << (GW & 31)) - 1u) << g.shift);
+    GrpW<GW> gw; gw.lane = g.lane; gw.shift = g.shift;
     GdSlab S = gd_carve<CFG>(smem + (size_t)gcta * gd_slab_bytes<CFG>());
     unsigned char* hb = E.gd_scratch + (size_t)gg * gd_hbm_bytes<CFG>();
     DpGraph dg; dg.n_levels = G.n_levels; dg.level_node_off = G.level_node_off; dg.edge_pack = G.edge_pack;
@@ -291,9 +292,9 @@ template <class CFG> __global__ void __launch_bounds__(CFG::WARPS * 32) k_extend
             }
         }
         if (__all_sync(0xffffffffu, phase == 2)) break;
-        if (phase == 1) {
-            int rc = gd_step<CFG>(C, S, st, g);
-            if (rc != 0) {
+        {   // every lane of the warp takes the step together (groups without a running extension are predicated off inside)
+            int rc = gd_step<CFG>(C, S, st, gw, phase == 1);
+            if (phase == 1 && rc != 0) {
                 DpResult res; res.n_cols = 0; res.n_lvl = 0; res.far_y = 0;
                 if (rc == 1) rc = gd_finish<CFG>(C, st, g, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res);
                 if (g.lane == 0) { E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0; if (rc == DP_DEFER) E.out_list[atomicAdd(E.out_count, 1)] = t; }

@@ -106,26 +106,43 @@ template <class CFG> __device__ __forceinline__ void gd_init(const WdCtx& C, con
     g.sync();
 }
 
-// One diagonal. Returns 0 to continue, 1 when the extension has ended (patience / nothing left / exact early exit), DP_DEFER on overflow.
-template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, const GdSlab& S, GdState& st, const Grp<CFG::GW>& g) {
-    constexpr int GW = CFG::GW;
+// Group collectives issued by the WHOLE warp (full member mask, segments of GW lanes). The four groups of a warp only stay on one
+// instruction stream if every collective inside the step is executed by all 32 lanes: with per-group member masks the hardware issues a
+// vote / shuffle / barrier once per distinct mask, the groups drift apart and each instruction serves one group (ncu: 6.9 active lanes).
+template <int GW> struct GrpW {
+    int shift; int lane;
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(0xffffffffu, p) >> shift) & ((1u << GW) - 1u); }
+    __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0u; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src, GW); }
+    template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(0xffffffffu, v, d, GW); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int d) const { return __shfl_xor_sync(0xffffffffu, v, d, GW); }
+    __device__ __forceinline__ unsigned below() const { return (1u << lane) - 1u; }
+};
+
+// One diagonal for every group of the warp at once. ALL 32 lanes call it; `act` says whether the lane's group has a running extension.
+// Control flow around collectives is warp-uniform (loops run to the warp-wide maximum trip count, early exits become per-group flags);
+// what a group computes is exactly what the one-group-at-a-time version computed.
+// Returns, per group: 0 to continue, 1 when the extension has ended (patience / nothing left / exact early exit), DP_DEFER on overflow.
+template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, const GdSlab& S, GdState& st, const GrpW<CFG::GW>& g, bool act) {
+    constexpr int GW = CFG::GW; constexpr unsigned FULL = 0xffffffffu;
     const DpGraph& G = *C.G;
     const int max_level = G.n_levels - 1, max_seq = C.seq_len;
     const int dir = C.pos ? 1 : -1; const int end_seq = C.pos ? max_seq : 0;
     const void* el = C.pos ? G.out_adj4 : G.in_adj4; const void* jl = C.pos ? G.jf4 : G.jb4;
     GdEntry* m1 = S.l[st.rot]; GdEntry* m2 = S.l[(st.rot + 2) % 3]; GdEntry* mt = S.l[(st.rot + 1) % 3];
-    const int lane = g.lane; const int n_m1 = st.n_m1, n_m2 = st.n_m2;
-    const int diag = ++st.diag;
-    if (diag - st.last_inc > 40) return 1;
-    if (n_m1 == 0 && n_m2 == 0) return 1;
+    const int lane = g.lane; const int n_m1 = act ? st.n_m1 : 0, n_m2 = act ? st.n_m2 : 0;
+    int rc = 0; int diag = st.diag;
+    if (act) { diag = ++st.diag; if (diag - st.last_inc > 40 || (n_m1 == 0 && n_m2 == 0)) { rc = 1; act = false; } }
     {   // exact early exit (see extend_warp.cuh)
         bool live = false;
-        for (int i = lane; i < n_m1; i += GW) { const GdEntry& e = m1[i]; live |= (e.y != end_seq) || e.pad || e.jdeg; }
-        for (int i = lane; i < n_m2; i += GW) live |= (m2[i].y != end_seq);
-        if (!g.any(live)) return 1;
+        if (act) { for (int i = lane; i < n_m1; i += GW) { const GdEntry& e = m1[i]; live |= (e.y != end_seq) || e.pad || e.jdeg; }
+                   for (int i = lane; i < n_m2; i += GW) live |= (m2[i].y != end_seq); }
+        const bool any_live = g.any(live);
+        if (act && !any_live) { rc = 1; act = false; }
     }
     bool ovf = false, saw_jump = false;
-    for (int i = lane; i < n_m2; i += GW) {
+    if (act) for (int i = lane; i < n_m2; i += GW) {
         const GdEntry pc = m2[i]; const int pcx = C.start_level + pc.xr;
         const int nx = pcx + dir, ny = pc.y + dir;
         if (nx > max_level || ny > max_seq || nx < 0 || ny < 0) continue;
@@ -138,7 +155,7 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
             atomicMax(&S.kD[ti], wd_key(pc.D + ((uint8_t)(pk >> 16) == sc ? 2 : -5), wd_mkseq(0, i, k, 0)));
         }
     }
-    for (int i = lane; i < n_m1; i += GW) {
+    if (act) for (int i = lane; i < n_m1; i += GW) {
         const GdEntry pc = m1[i]; const int pcx = C.start_level + pc.xr;
         { const int gy = pc.y + dir; const bool ok = C.pos ? (pcx <= max_level && gy <= max_seq) : (pcx >= 0 && gy >= 0);
           if (ok) { const int ti = gd_touch<CFG>(S, C.start_level, pcx, gy, pc.z, pc.node); if (ti < 0) ovf = true; else {
@@ -165,16 +182,20 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
         }
     }
     g.sync();
-    const int n_td = *S.cnt;
-    if (g.any(ovf) || n_td > CFG::TD) return DP_DEFER;
-    if (!st.hashed && g.any(saw_jump)) {
-        uint32_t cgen = 0;
-        if (lane == 0) { cgen = C.gens[0] + 1; if (cgen >= (1u << 15)) cgen = 0; C.gens[0] = cgen ? cgen : 1; }
-        cgen = g.shfl(cgen, 0);
-        if (cgen == 0) { for (int i = lane; i < CFG::HASH; i += GW) C.hash[i] = 0; cgen = 1; g.sync(); }
-        for (int i = lane; i < st.n_cells; i += GW) { const DpCell& c = C.cells[i]; gd_insert_cell<CFG>(C, cgen, c.x, c.y, c.z, i); }
-        st.cgen = cgen; st.hashed = true;
-        g.sync();
+    int n_td = act ? *S.cnt : 0;
+    { const bool any_ovf = g.any(ovf); if (act && (any_ovf || n_td > CFG::TD)) { rc = DP_DEFER; act = false; n_td = 0; } }
+    {   // first jump over more than one level in this extension: from now on cells can be revisited, so build the (x, y, z) -> cell map
+        const bool any_jump = g.any(saw_jump); const bool need = act && !st.hashed && any_jump;
+        if (__any_sync(FULL, need)) {
+            uint32_t cgen = 0;
+            if (need && lane == 0) { cgen = C.gens[0] + 1; if (cgen >= (1u << 15)) cgen = 0; C.gens[0] = cgen ? cgen : 1; }
+            cgen = g.shfl(cgen, 0);
+            const bool clr = need && cgen == 0;
+            if (__any_sync(FULL, clr)) { if (clr) for (int i = lane; i < CFG::HASH; i += GW) C.hash[i] = 0; __syncwarp(); }
+            if (clr) cgen = 1;
+            if (need) { for (int i = lane; i < st.n_cells; i += GW) { const DpCell& c = C.cells[i]; gd_insert_cell<CFG>(C, cgen, c.x, c.y, c.z, i); } st.cgen = cgen; st.hashed = true; }
+            __syncwarp();
+        }
     }
     // rank the touched slots in (x, y, z) order (the packed key is monotone in it)
     for (int i = lane; i < n_td; i += GW) {
@@ -183,9 +204,10 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
         S.order[rank] = S.slots[i];
     }
     g.sync();
-    int n_mt = 0; int run_max = st.cur_max; int new_first = -1; bool any_inc = false; int status = 0;
-    for (int base = 0; base < n_td; base += GW) {
-        const int oi = base + lane; const bool in = oi < n_td;
+    int n_mt = 0; int run_max = st.cur_max; int new_first = -1; bool any_inc = false;
+    const int n_td_w = __reduce_max_sync(FULL, n_td);
+    for (int base = 0; base < n_td_w; base += GW) {
+        const int oi = base + lane; const bool in = act && oi < n_td;
         int selD = DP_NEG, selGG = DP_NEG, selSG = DP_NEG; uint32_t kD = 0, kGG = 0, kSG = 0; int selfmat = 0; int tx = 0, ty = 0, tz = 0, tn = 0;
         if (in) {
             const int ti = S.order[oi]; const uint32_t tk = S.tkey[ti] - 1u; tx = (int)(tk >> 19) - 2048 + C.start_level; ty = (int)((tk >> 8) & 2047u); tz = (int)(tk & 255u); tn = S.tnode[ti];
@@ -196,13 +218,14 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
             if (!haveD || selGG > selD) { selD = selGG; selfmat = 1; }
             if (selSG > selD) { selD = selSG; selfmat = 2; }
         }
-        const bool keep = in && selD >= -16;
+        bool keep = in && selD >= -16;
         int ci = (keep && st.hashed) ? gd_find_cell<CFG>(C, st.cgen, tx, ty, tz) : -1;
-        const bool isNew = keep && ci < 0;
+        bool isNew = keep && ci < 0;
         const unsigned newmask = g.ballot(isNew);
+        if (act && st.n_cells + __popc(newmask) > CFG::CELLS) { rc = DP_DEFER; act = false; }   // nothing of this group is stored from here on
+        keep = keep && act; isNew = isNew && act;
         if (isNew) ci = st.n_cells + __popc(newmask & g.below());
-        if (st.n_cells + __popc(newmask) > CFG::CELLS) { status = DP_DEFER; break; }
-        st.n_cells += __popc(newmask);
+        if (act) st.n_cells += __popc(newmask);
         int incl = keep ? selD : -1000000;
         for (int d = 1; d < GW; d <<= 1) { const int t2 = g.shfl_up(incl, d); if (lane >= d) incl = max(incl, t2); }
         int excl = g.shfl_up(incl, 1); if (lane == 0) excl = -1000000;
@@ -229,31 +252,30 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
             ne.cell = (uint16_t)ci; ne.node = tn; ne.xr = (int16_t)(tx - C.start_level); ne.y = (int16_t)ty; ne.z = (uint8_t)tz; ne.D = (int16_t)stD; ne.GG = (int16_t)stGG; ne.SG = (int16_t)stSG; ne.pad = (uint8_t)((__ldg(G.node_gapflags + tn) >> (C.pos ? 0 : 1)) & 1);
             int deg, jdeg; wd_adj(C, tn, ne.k0, deg, ne.j0, jdeg); ne.deg = (uint8_t)min(deg, 255); ne.jdeg = (uint8_t)min(jdeg, 255);
         }
-        { const unsigned em = g.ballot(keep && ty == end_seq); if (em && st.end_c < 0) st.end_c = g.shfl(ci, __ffs(em) - 1); }   // first sequence-complete cell: the end-cell scan starts there
+        { const unsigned em = g.ballot(keep && ty == end_seq); const int first_end = g.shfl(ci, em ? __ffs(em) - 1 : 0); if (em && st.end_c < 0) st.end_c = first_end; }   // first sequence-complete cell: the end-cell scan starts there
         if (g.any(keep && (selD > running || tie_counts || overwritten))) any_inc = true;
         const int chunk_max = g.shfl(incl, GW - 1);
-        if (chunk_max > run_max) {
-            const unsigned m = g.ballot(keep && selD == chunk_max);
-            new_first = g.shfl(ci, __ffs(m) - 1);
-            run_max = chunk_max;
-        }
+        { const unsigned m = g.ballot(keep && selD == chunk_max); const int first_at_max = g.shfl(ci, m ? __ffs(m) - 1 : 0);
+          if (act && chunk_max > run_max) { new_first = first_at_max; run_max = chunk_max; } }
         const unsigned km = g.ballot(keep);
-        if (n_mt + __popc(km) > CFG::LIST) { status = DP_DEFER; break; }
-        if (keep) mt[n_mt + __popc(km & g.below())] = ne;
-        n_mt += __popc(km);
+        if (act && n_mt + __popc(km) > CFG::LIST) { rc = DP_DEFER; act = false; }
+        if (keep && act) mt[n_mt + __popc(km & g.below())] = ne;
+        if (act) n_mt += __popc(km);
         g.sync();
     }
-    if (status) return status;
-    for (int i = lane; i < n_td; i += GW) { const int sl = S.slots[i]; S.tkey[sl] = 0; S.kD[sl] = 0; S.kGG[sl] = 0; S.kSG[sl] = 0; }
-    if (lane == 0) *S.cnt = 0;
-    if (run_max > st.cur_max) { st.cur_max = run_max; st.first_max_cell = new_first; }
-    if (any_inc) st.last_inc = diag;
+    if (act) {
+        for (int i = lane; i < n_td; i += GW) { const int sl = S.slots[i]; S.tkey[sl] = 0; S.kD[sl] = 0; S.kGG[sl] = 0; S.kSG[sl] = 0; }
+        if (lane == 0) *S.cnt = 0;
+        if (run_max > st.cur_max) { st.cur_max = run_max; st.first_max_cell = new_first; }
+        if (any_inc) st.last_inc = diag;
+    } else n_mt = 0;
     g.sync();
-    if (n_mt > 0) {   // keep cells within 15 of the best stored D (stable compaction)
+    {   // keep cells within 15 of the best stored D (stable compaction)
         int mx = -1000000; for (int i = lane; i < n_mt; i += GW) mx = max(mx, (int)mt[i].D);
         for (int d = GW / 2; d; d >>= 1) mx = max(mx, g.shfl_xor(mx, d));
+        const int n_mt_w = __reduce_max_sync(FULL, n_mt);
         int w = 0;
-        for (int base = 0; base < n_mt; base += GW) {
+        for (int base = 0; base < n_mt_w; base += GW) {
             const int i = base + lane; const bool in = i < n_mt; GdEntry e; if (in) e = mt[i];
             const bool k = in && (mx - e.D <= 15);
             const unsigned m = g.ballot(k);
@@ -262,10 +284,9 @@ template <class CFG> __device__ __forceinline__ int gd_step(const WdCtx& C, cons
             w += __popc(m);
             g.sync();
         }
-        n_mt = w;
+        if (act) { st.n_m2 = n_m1; st.n_m1 = w; st.rot = (st.rot + 1) % 3; }
     }
-    st.n_m2 = n_m1; st.n_m1 = n_mt; st.rot = (st.rot + 1) % 3;
-    return 0;
+    return rc;
 }
 
 // end cell + backtrace (lane 0 of the group); returns rc and fills res
