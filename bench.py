@@ -367,6 +367,25 @@ def main():
     h2d = int(sum(b[k].nbytes for k in H.BATCH_KEYS)) + 3 * 4 * len(b["chain_contig"])
     d2h = int(sum(v.numel() * v.element_size() for v in res.values())) + cov_host.nbytes
     L.hlala_session_free(sess)   # the e2e call owns its device buffers (a workspace kept in the graph handle across calls)
+    # one extra step on a single lane (no overlap between waves): the per-kernel split that is comparable with a serialised profiler run
+    serial = None
+    if rank == 0:
+        try:
+            os.environ["HLALA_LANES"] = "1"
+            s1 = C.c_void_p()
+            P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(s1)))
+            del os.environ["HLALA_LANES"]
+            P._chk(L.hlala_session_run(s1, C.c_double(args.is_mean), C.c_double(args.is_sd), C.c_uint64(0), C.c_void_p(stream.cuda_stream)))
+            L.hlala_session_set_timing(s1, 1)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+            P._chk(L.hlala_session_run(s1, C.c_double(args.is_mean), C.c_double(args.is_sd), C.c_uint64(0), C.c_void_p(stream.cuda_stream)))
+            e1.record(); torch.cuda.synchronize()
+            k1 = (C.c_double * 6)(); l1 = (C.c_int * 6)(); P._chk(L.hlala_session_timing(s1, k1, l1))
+            serial = {"ms_per_step": e0.elapsed_time(e1), "kernel_ms": [k1[i] for i in range(6)]}
+            L.hlala_session_free(s1)
+        except Exception as e:
+            os.environ.pop("HLALA_LANES", None)
+            serial = {"error": str(e)[:200]}
     torch.cuda.synchronize()
     e2e_times = []
     for i in range(1 + args.e2e_steps):
@@ -405,7 +424,15 @@ def main():
                 "chain_kernel": {"kernel": "k_chain_seed", "achieved": chain_ach, "frac": (chain_ach / peak) if chain_ach else None, "algorithmic_bytes_per_step": chain_bytes},
                 "whole_path_algorithmic_bytes_per_step": total_bytes, "whole_path_achieved": total_bytes * args.steps / (ms_total / 1000.0) / 1e9,
                 "dominant_kernel_by_time": names[dom], "per_kernel": per_kernel,
-                "per_kernel_note": "durations of launches on different streams overlap; their sum exceeds ms_per_step"}
+                "per_kernel_note": "durations of launches on different streams overlap (and slow each other down); their sum exceeds ms_per_step"}
+    if serial and "kernel_ms" in serial:
+        tot1 = sum(serial["kernel_ms"]) or 1.0
+        roofline["single_lane_step"] = {"ms_per_step": serial["ms_per_step"], "per_kernel_ms": {names[i]: serial["kernel_ms"][i] for i in range(6)},
+                                        "per_kernel_share": {names[i]: serial["kernel_ms"][i] / tot1 for i in range(6)},
+                                        "note": "one step with HLALA_LANES=1: waves one after the other, no overlap; these shares are the ones to compare with the ncu launch list"}
+        roofline["dominant_kernel_by_time"] = names[max(range(6), key=lambda i: serial["kernel_ms"][i])]
+    elif serial:
+        roofline["single_lane_step"] = serial
     cpu = None
     if os.path.exists(H.LIB_REF) and n_gpus == 1:
         d = small_prg(args, root)
