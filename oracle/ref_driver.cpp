@@ -12,6 +12,8 @@
 //   per pair              processBAM::alignOneReadPair             mapper/processBAM.cpp:3129
 //   typing                gene filter (processBAM.cpp:2427-2481) + HLATyper::HLATypeInference (hla/HLATyper.cpp:933)
 //   k-mer seeding         GraphAndEdgeIndex::Index / queryIndex / findChains   Graph/GraphAndEdgeIndex.cpp:428,986,39
+//   seed collection       processBAM::extractSeeds2 + protoSeeds (record selection, grouping, completeness; the records come from the
+//                         in-memory stand-in for BamTools::BamReader)                  mapper/processBAM.cpp:703, mapper/reads/protoSeeds.cpp:24,377
 //
 // Two things are pinned so that "bit-exact" is defined at all (SURVEY.md §0 finding 3, §7 hard parts):
 //  * std::set<Node*>/std::set<Edge*> iterate in pointer order. While the graph is being built every
@@ -393,6 +395,47 @@ int hlala_ref_find_chains_fetch(void* idx, int64_t* chain_off, int32_t* begin, i
     KmerRef* R = (KmerRef*)idx;
     memcpy(chain_off, R->r_chain_off.data(), R->r_chain_off.size() * 8); memcpy(begin, R->r_begin.data(), R->r_begin.size() * 4); memcpy(end, R->r_end.data(), R->r_end.size() * 4);
     memcpy(edge_off, R->r_edge_off.data(), R->r_edge_off.size() * 8); memcpy(edges, R->r_edges.data(), R->r_edges.size() * 4);
+    return 0;
+}
+
+// ---- seed collection: the reference's own extractSeeds2 over in-memory records (record i carries the tag XI = i)
+struct SeedsRef { std::vector<std::string> names; std::vector<int32_t> complete, n1, n2, recs; };
+static SeedsRef g_seeds;
+int hlala_ref_extract_seeds(void* h, long long n_rec, const char* names_blob /* n_rec zero-terminated names */, const int32_t* ref, const int32_t* pos, const uint16_t* flag, const int32_t* as,
+                            const int32_t* cigar_off, const uint32_t* cigar, long long* n_seeds, long long* n_out_recs) {
+    Driver* d = (Driver*)h;
+    return guarded([&]() {
+        std::vector<BamTools::BamAlignment>& R = BamTools::BamReader::shim_records(); R.clear();
+        const size_t n_prg_refs = BamTools::BamReader::shim_refs().size(); bool extra_ref = false;
+        for (long long i = 0; i < n_rec; i++) if (ref[i] == (int32_t)n_prg_refs) extra_ref = true;
+        if (extra_ref) BamTools::BamReader::shim_refs().push_back(BamTools::RefData("chrUn", 1000000));   // a reference that is not a PRG contig
+        const char* nm = names_blob;
+        for (long long i = 0; i < n_rec; i++) {
+            BamTools::BamAlignment a; a.Name = nm; nm += a.Name.size() + 1;
+            a.RefID = ref[i]; a.Position = pos[i]; a.AlignmentFlag = flag[i]; a.shim_int_tags["AS"] = as[i]; a.shim_int_tags["XI"] = (int32_t)i;
+            int qlen = 0;
+            for (int32_t k = cigar_off[i]; k < cigar_off[i + 1]; k++) { const char t = "MIDNSHP=X"[cigar[k] & 15]; const int l = (int)(cigar[k] >> 4); a.CigarData.push_back(BamTools::CigarOp(t, l)); if (t == 'M' || t == 'I' || t == 'S' || t == '=' || t == 'X') qlen += l; }
+            a.QueryBases.assign((size_t)qlen, 'A'); a.Qualities.assign((size_t)qlen, 'I'); a.Length = qlen;
+            R.push_back(a);
+        }
+        std::map<std::string, mapper::reads::protoSeeds> seeds = d->extractSeeds2();
+        g_seeds = SeedsRef();
+        for (auto& kv : seeds) {
+            g_seeds.names.push_back(kv.first); g_seeds.complete.push_back(kv.second.isComplete() ? 1 : 0);
+            g_seeds.n1.push_back((int32_t)kv.second.read1_alignments.size()); g_seeds.n2.push_back((int32_t)kv.second.read2_alignments.size());
+            for (auto& al : kv.second.read1_alignments) { int32_t xi = -1; std::get<2>(al).GetTag("XI", xi); g_seeds.recs.push_back(xi); }
+            for (auto& al : kv.second.read2_alignments) { int32_t xi = -1; std::get<2>(al).GetTag("XI", xi); g_seeds.recs.push_back(xi); }
+        }
+        R.clear(); if (extra_ref) BamTools::BamReader::shim_refs().pop_back();
+        *n_seeds = (long long)g_seeds.names.size(); *n_out_recs = (long long)g_seeds.recs.size();
+        return 0; });
+}
+// names: caller buffer of name_bytes, zero-terminated names back to back
+int hlala_ref_extract_seeds_fetch(char* names, long long name_bytes, int32_t* complete, int32_t* n1, int32_t* n2, int32_t* recs) {
+    long long at = 0;
+    for (const std::string& s : g_seeds.names) { if (at + (long long)s.size() + 1 > name_bytes) return -1; memcpy(names + at, s.c_str(), s.size() + 1); at += (long long)s.size() + 1; }
+    memcpy(complete, g_seeds.complete.data(), g_seeds.complete.size() * 4); memcpy(n1, g_seeds.n1.data(), g_seeds.n1.size() * 4); memcpy(n2, g_seeds.n2.data(), g_seeds.n2.size() * 4);
+    memcpy(recs, g_seeds.recs.data(), g_seeds.recs.size() * 4);
     return 0;
 }
 

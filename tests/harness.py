@@ -137,6 +137,15 @@ class Ref:
 
 
 
+    # ---- seed collection (processBAM::extractSeeds2 over in-memory records)
+    def extract_seeds(self, names, ref, pos, flag, as_, cigar_off, cigar):
+        blob = b"".join(n.encode() + b"\0" for n in names); ns = C.c_longlong(); nr = C.c_longlong()
+        self._chk(self.lib.hlala_ref_extract_seeds(self.h, C.c_longlong(len(names)), blob, p(ref), p(pos), p(flag), p(as_), p(cigar_off), p(cigar), C.byref(ns), C.byref(nr)))
+        buf = C.create_string_buffer(len(blob) + 16); comp = np.zeros(max(ns.value, 1), np.int32); n1 = np.zeros(max(ns.value, 1), np.int32); n2 = np.zeros(max(ns.value, 1), np.int32); recs = np.zeros(max(nr.value, 1), np.int32)
+        self._chk(self.lib.hlala_ref_extract_seeds_fetch(buf, C.c_longlong(len(blob) + 16), p(comp), p(n1), p(n2), p(recs)))
+        out_names = buf.raw.split(b"\0")[:ns.value]
+        return [x.decode() for x in out_names], comp[:ns.value], n1[:ns.value], n2[:ns.value], recs[:nr.value]
+
     # ---- k-mer seeding (GraphAndEdgeIndex)
     def kmer_index(self, k):
         L = self.lib; L.hlala_ref_kmer_index.restype = C.c_void_p
