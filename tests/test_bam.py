@@ -1,6 +1,8 @@
 """BAM ingest: hlala_bam_read against the rules of processBAM::extractSeeds2 / protoSeeds (mapper/processBAM.cpp:703-862,
 mapper/reads/protoSeeds.cpp:24,377) and the command-line front end. BamTools is not part of the reference tree, so there is no reference binary to
-pin against: the tests are round trips and the documented record-selection rules."""
+pin BamTools' byte-level record decoding against (round-trip tests). What the reference itself decides on decoded records (which are kept, how they
+are grouped and ordered, which pairs are complete) is pinned against its unmodified extractSeeds2 / protoSeeds, fed the same records through the
+in-memory BamReader stand-in."""
 import os
 import subprocess
 
@@ -72,6 +74,14 @@ def test_record_selection_rules(dataset, tmp_path):
     with pytest.raises(RuntimeError, match="Cannot open"):
         P.bam_read(str(tmp_path / "missing.bam"))
     P.close()
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not built on this box")
+def test_ingest_matches_the_references_extractSeeds2():
+    """selection, grouping, name order and completeness against the unmodified processBAM::extractSeeds2 + protoSeeds (own process)"""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "bam_ref_compare.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
 
 
 def test_cli_usage_and_loud_failure_without_gpu(dataset, tmp_path):
