@@ -224,8 +224,8 @@ void hlala_kmer_chains_free(hlala_kmer_chains_t* c);
  * Reads 2p / 2p+1 of the view are the first / other mate of pair p; pairs are in byte order of their names (the reference iterates a
  * std::map<std::string, protoSeeds>). The view and the names point into the batch object. counts: [0] records in the file, [1] records
  * kept, [2] read names with a kept record, [3] pairs dropped because a mate has no primary record. is_mean / is_sd / is_n: gap between the
- * mates of properly oriented primary pairs (the reference estimates the insert size by random sampling, estimateInsertSize :865; ours is
- * the deterministic full-file statistic and can be overridden by the caller). */
+ * mates of properly oriented primary pairs (the reference aligns the primary records of its first ~4000 seeds and histograms their distances in the underlying sequences,
+ * estimateInsertSize processBAM.cpp:1071-1181; ours is the whole-file statistic on contig coordinates and can be overridden by the caller). */
 typedef struct hlala_bam_batch hlala_bam_batch_t;
 int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads /* <=0: all cores */, hlala_bam_batch_t** out);
 int hlala_bam_batch_view(const hlala_bam_batch_t* b, hlala_seed_batch_t* view, const char* const** pair_names);
