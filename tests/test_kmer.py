@@ -80,6 +80,16 @@ def test_oracle_and_product_match_compiled_reference():
     assert r.returncode == 0, r.stdout[-3000:]
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not built on this box")
+@pytest.mark.parametrize("seed", [1, 7, 19])
+def test_fuzz_random_graphs_against_compiled_reference(seed):
+    """random levelled graphs with gap bubbles and shuffled node / edge order (tests/kmer_fuzz.py, own process per graph)"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "kmer_fuzz.py"), str(seed), "3", "6"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and r.stdout.count(" ok") == 2, r.stdout[-3000:]
+
+
 # ------------------------------------------------------------------------------------------------------------------ GPU
 _gpu = {}
 
