@@ -1,0 +1,76 @@
+"""Alignment-path fuzz on small random graphs (own process per graph). The graph of a synthetic PRG directory is replaced by a random levelled
+graph (tests/kmer_fuzz.py: gap bubbles, gap runs, shuffled node / edge order) and its contigs by random walks through that graph; reads
+with soft clips and indels are drawn from the contigs. Compared, bit for bit: the oracle restatement (oracle/hlala_oracle.cpp) against the
+UNMODIFIED reference (per-chain columns + log-likelihoods, per-pair columns + mapping qualities), and the extension DP the GPU executes
+(hla-la_b200/csrc/extend_dp.h on the host) against both.   usage: align_fuzz.py <seed>"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import harness as H  # noqa: E402
+import kmer_fuzz  # noqa: E402
+from test_dp_host import check_dp_host  # noqa: E402
+
+
+def rewrite_contigs(d, G, rng):
+    """every contig of sequences.txt becomes a random walk from level 0 to the last level"""
+    ef, et, em, nl = G["edge_from"], G["edge_to"], G["edge_emis"], G["node_level"]
+    order = np.argsort(ef, kind="stable"); starts = np.searchsorted(ef[order], np.arange(len(nl) + 1))
+    n_levels = int(nl.max()) + 1
+    lines = open(os.path.join(d, "sequences.txt")).read().split("\n")
+    fa = {}; out_lines = [lines[0]]
+    for ln in lines[1:]:
+        if not ln.strip():
+            continue
+        f = ln.split("\t"); sid = int(f[0])
+        node = int(np.nonzero(nl == 0)[0][0]); seq = []; lv = []
+        while nl[node] < n_levels - 1:
+            a, b = starts[node], starts[node + 1]; e = order[a + rng.randint(0, b - a)]
+            if em[e] != ord("_"):
+                seq.append(chr(em[e])); lv.append(int(nl[node]))
+            node = et[e]
+        fa["PRG_%d" % sid] = "".join(seq)
+        with open(os.path.join(d, "translation", "%d.txt" % sid), "w") as t:
+            t.write("".join("%d\n" % x for x in lv))
+        f[5] = str(len(seq)); out_lines.append("\t".join(f))
+    open(os.path.join(d, "sequences.txt"), "w").write("\n".join(out_lines) + "\n")
+    for p in (os.path.join(d, "mapping_PRGonly", "referenceGenome.fa"), os.path.join(d, "extendedReferenceGenome", "extendedReferenceGenome.fa")):
+        with open(p, "w") as o:
+            for k, s in fa.items():
+                o.write(">%s\n" % k + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
+
+
+def main():
+    seed = int(sys.argv[1])
+    os.environ["HLALA_NO_GRAPH_CACHE"] = "1"
+    rng = np.random.RandomState(seed)
+    d = tempfile.mkdtemp(prefix="align_fuzz_")
+    H.synth_prg(d, levels=int(rng.randint(500, 900)), haps=3, genes=0, alleles=4, seed=seed)
+    kmer_fuzz.write_random_graph(d, rng, max_w=int(rng.randint(2, 4)), p_gap=float(rng.choice([0.02, 0.08, 0.15])), p_extra=0.25)
+    P = H.Product(d)
+    G = dict(node_level=P.array("node_level"), edge_from=P.array("edge_from"), edge_to=P.array("edge_to"), edge_emis=P.array("edge_emis"))
+    rewrite_contigs(d, G, rng); P.close()
+    b = H.synth_reads(d, os.path.join(d, "seeds.bin"), pairs=120, len=60, seed=seed, clip_frac=0.5, indel_rate=0.01, gap_mean=30, gap_sd=6)
+    R = H.quiet(H.Ref, d); O = H.Oracle(d)
+    rc = H.quiet(R.chains, b, 512); oc = O.chains(b, 512)
+    for k in ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll"):
+        assert np.array_equal(rc[k], oc[k]), "seed %d: chains %s: oracle != reference" % (seed, k)
+    n = rc["n_cols"]
+    for i in range(len(n)):
+        for k in ("level", "edge", "gchar", "schar", "from_seed"):
+            assert np.array_equal(rc[k][i, :n[i]], oc[k][i, :n[i]]), "seed %d slot %d %s" % (seed, i, k)
+    rp = H.quiet(R.pairs, b, 30.0, 6.0, 512); op = O.pairs(b, 30.0, 6.0, 512)
+    assert np.array_equal(rp["n_cols"], op["n_cols"]) and np.array_equal(rp["pair_mapq"], op["pair_mapq"]) and np.array_equal(rp["read_mapq"], op["read_mapq"]), "seed %d: pairs" % seed
+    m = rp["n_cols"]
+    for r in range(len(m)):
+        for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+            assert np.array_equal(rp[k][r, :m[r]], op[k][r, :m[r]]), "seed %d read %d %s" % (seed, r, k)
+    tested = check_dp_host(d, b, rc)
+    print("seed %d: %d chains, %d extended by extend_dp.h, %d pairs ok" % (seed, int((rc["status"] == 0).sum()), tested, len(m) // 2))
+
+
+if __name__ == "__main__":
+    main()

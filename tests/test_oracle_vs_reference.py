@@ -38,3 +38,14 @@ def test_pairs_bit_equal(dataset):
     rp = H.quiet(ref_for(d).pairs, b, mu, sd); op = H.Oracle(d).pairs(b, mu, sd)
     for k in ("pair_mapq", "read_mapq", "read_reverse", "n_cols", "level", "edge", "gchar", "schar", "from_seed", "mapq"):
         assert np.array_equal(rp[k], op[k]), k
+
+
+@pytest.mark.parametrize("seed", [2, 11])
+def test_fuzz_random_graphs(seed):
+    """random levelled graphs with dense gap structure, contigs = random walks, soft-clipped reads (tests/align_fuzz.py, own process per graph):
+    oracle restatement and the host build of the GPU's extension DP against the compiled reference, bit for bit"""
+    import os
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "align_fuzz.py"), str(seed)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "pairs ok" in r.stdout, r.stdout[-3000:]
