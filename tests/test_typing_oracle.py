@@ -12,13 +12,14 @@ import harness as H
 pytestmark = pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref/libhlala_ref.so not built (reference tree absent)")
 
 
-def test_typing_files_byte_identical(dataset, tmp_path):
-    d, b, mu, sd = dataset("typing")
+@pytest.mark.parametrize("name", ["typing", "typing250"])
+def test_typing_files_byte_identical(dataset, tmp_path, name):
+    d, b, mu, sd = dataset(name)
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, os.path.join(here, "typing_ref_compare.py"), d, os.path.join(d, "seeds.bin"), str(mu), str(sd), str(tmp_path)],
                        cwd=here, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     v = json.loads(r.stdout.strip().split("\n")[-1])
     assert v["n_used"] > 500 and v["files_ref"] == v["files_oracle"] == 5 + 4 * 17
-    assert not v["differing"], "files differ from the reference's: %s" % v["differing"]
-    assert v["n_loci"] == 17 and v["min_C"] >= 8 and v["min_R"] >= 20 and v["finite"]
+    assert not v["differing"], "files differ from the reference's: %s" % v["differing"]       # the one undefined number of the reference is masked, see typing_ref_compare.py
+    assert v["n_loci"] == 17 and v["min_C"] >= 8 and v["min_R"] >= 15 and v["finite"]
