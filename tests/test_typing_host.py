@@ -34,12 +34,13 @@ def test_typing_without_gpu_fails_loudly(dataset):
     T.close(); P.close()
 
 
-def test_host_typing_logic_writes_the_oracles_files(dataset, tmp_path):
+@pytest.mark.parametrize("name", ["typing", "typing250"])
+def test_host_typing_logic_writes_the_oracles_files(dataset, tmp_path, name):
     """hla_typing.cpp (projection, filters, calls, QC, writers) driven by a test-only loop stand-in for the two kernels
     (tests/native/typing_host.cpp): all 73 files byte-identical to the oracle's (which is pinned to the compiled reference)."""
     import filecmp
     import os
-    d, b, mu, sd = dataset("typing")
+    d, b, mu, sd = dataset(name)
     aln = H.Oracle(d).pairs(b, mu, sd, 512)
     or_dir = str(tmp_path / "oracle" / "hla")
     O = H.OracleTyping(d, b, aln, mu, sd, or_dir); O.close()
