@@ -2,7 +2,8 @@
 graph (tests/kmer_fuzz.py: gap bubbles, gap runs, shuffled node / edge order) and its contigs by random walks through that graph; reads
 with soft clips and indels are drawn from the contigs. Compared, bit for bit: the oracle restatement (oracle/hlala_oracle.cpp) against the
 UNMODIFIED reference (per-chain columns + log-likelihoods, per-pair columns + mapping qualities), and the extension DP the GPU executes
-(hla-la_b200/csrc/extend_dp.h on the host) against both.   usage: align_fuzz.py <seed>"""
+(hla-la_b200/csrc/extend_dp.h on the host) against both. With --gpu (a box with a GPU) the product's kernels are compared as well (not part of
+the suite yet: first GPU run pending).   usage: align_fuzz.py <seed> [--gpu]"""
 import os
 import sys
 import tempfile
@@ -69,6 +70,20 @@ def main():
         for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
             assert np.array_equal(rp[k][r, :m[r]], op[k][r, :m[r]]), "seed %d read %d %s" % (seed, r, k)
     tested = check_dp_host(d, b, rc)
+    if "--gpu" in sys.argv:
+        Pg = H.Product(d); Pg.to_gpu(0)
+        gc = Pg.chains(b, 512)
+        for k in ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll"):
+            assert np.array_equal(gc[k], rc[k]), "seed %d: GPU chains %s" % (seed, k)
+        for i in range(len(n)):
+            for k in ("level", "edge", "gchar", "schar", "from_seed"):
+                assert np.array_equal(gc[k][i, :n[i]], rc[k][i, :n[i]]), "seed %d GPU slot %d %s" % (seed, i, k)
+        gp = Pg.pairs(b, 30.0, 6.0, 512)
+        assert np.array_equal(gp["n_cols"], rp["n_cols"]) and np.allclose(gp["pair_mapq"], rp["pair_mapq"], rtol=0, atol=1e-12)
+        for r in range(len(m)):
+            for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+                assert np.array_equal(gp[k][r, :m[r]], rp[k][r, :m[r]]), "seed %d GPU read %d %s" % (seed, r, k)
+        print("seed %d: GPU kernels ok" % seed)
     print("seed %d: %d chains, %d extended by extend_dp.h, %d pairs ok" % (seed, int((rc["status"] == 0).sum()), tested, len(m) // 2))
 
 
