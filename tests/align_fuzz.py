@@ -44,6 +44,40 @@ def rewrite_contigs(d, G, rng):
                 o.write(">%s\n" % k + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
 
 
+def add_secondary_chains(b, rng, contig_len):
+    """about half of the reads get extra secondary records: the primary's CIGAR at a random place of a random contig (same or other strand,
+    lower score), and sometimes an exact duplicate of the primary's coordinates — the pair stage then has several combinations to rank,
+    chains on the wrong strand to skip and duplicates to drop"""
+    nr = len(b["read_off"]) - 1
+    out = {k: [] for k in ("chain_contig", "chain_pos", "chain_flag", "chain_as")}; cig = []; cig_off = [0]; chain_off = [0]
+    for r in range(nr):
+        c0, c1 = int(b["chain_off"][r]), int(b["chain_off"][r + 1])
+        recs = [(int(b["chain_contig"][c]), int(b["chain_pos"][c]), int(b["chain_flag"][c]), int(b["chain_as"][c]), list(b["cigar"][b["cigar_off"][c]:b["cigar_off"][c + 1]])) for c in range(c0, c1)]
+        if recs and rng.rand() < 0.5:
+            ctg, pos, flag, as_, cg = recs[0]
+            reflen = sum(int(x) >> 4 for x in cg if (int(x) & 15) in (0, 2, 3, 7, 8))
+            for _ in range(int(rng.randint(1, 4))):
+                u = rng.rand()
+                if u < 0.2:
+                    recs.append((ctg, pos, flag | 0x100, as_ - 1, cg))                       # same coordinates: dropped as a duplicate
+                else:
+                    c2 = int(rng.randint(0, len(contig_len)))
+                    if contig_len[c2] > reflen + 2:
+                        p2 = int(rng.randint(0, contig_len[c2] - reflen - 1))
+                        f2 = (flag | 0x100) ^ (0x10 if rng.rand() < 0.3 else 0)
+                        recs.append((c2, p2, f2, as_ - int(rng.randint(0, 30)), cg))
+            order = list(range(len(recs))); rng.shuffle(order); recs = [recs[i] for i in order]
+        for ctg, pos, flag, as_, cg in recs:
+            out["chain_contig"].append(ctg); out["chain_pos"].append(pos); out["chain_flag"].append(flag); out["chain_as"].append(as_)
+            cig += [int(x) for x in cg]; cig_off.append(len(cig))
+        chain_off.append(len(out["chain_contig"]))
+    nb = dict(b)
+    nb["chain_off"] = np.array(chain_off, b["chain_off"].dtype); nb["cigar_off"] = np.array(cig_off, b["cigar_off"].dtype); nb["cigar"] = np.array(cig, b["cigar"].dtype)
+    for k in out:
+        nb[k] = np.array(out[k], b[k].dtype)
+    return nb
+
+
 def main():
     seed = int(sys.argv[1])
     os.environ["HLALA_NO_GRAPH_CACHE"] = "1"
@@ -54,7 +88,9 @@ def main():
     P = H.Product(d)
     G = dict(node_level=P.array("node_level"), edge_from=P.array("edge_from"), edge_to=P.array("edge_to"), edge_emis=P.array("edge_emis"))
     rewrite_contigs(d, G, rng); P.close()
+    Pn = H.Product(d); P_dims = np.diff(Pn.array("contig_off")); Pn.close()
     b = H.synth_reads(d, os.path.join(d, "seeds.bin"), pairs=120, len=60, seed=seed, clip_frac=0.5, indel_rate=0.01, gap_mean=30, gap_sd=6)
+    b = add_secondary_chains(b, rng, P_dims)
     R = H.quiet(H.Ref, d); O = H.Oracle(d)
     rc = H.quiet(R.chains, b, 512); oc = O.chains(b, 512)
     for k in ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll"):
