@@ -1028,6 +1028,8 @@ int hlala_bam_batch_stats(const hlala_bam_batch_t* B, int64_t counts[4], double*
 }
 void hlala_bam_batch_free(hlala_bam_batch_t* B) { delete B; }
 
+void hlala_graph_release_workspace(hlala_graph_t* g) { if (!g) return; std::lock_guard<std::mutex> lock(g->ws_mu); g->ws.reset(); }
+
 int hlala_session_set_coverage(hlala_session_t* s, int on) { if (!s) return fail(HLALA_E_ARG, "null session"); s->own_cov = on != 0; return 0; }
 int hlala_session_fetch_coverage(hlala_session_t* s, int32_t* bases_per_level) {
     if (!s || !bases_per_level) return fail(HLALA_E_ARG, "hlala_session_fetch_coverage: null argument");

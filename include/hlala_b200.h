@@ -118,6 +118,10 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
 int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double is_mean, double is_sd,
                       hlala_pair_out_t* out, int32_t* bases_per_level /* [n_levels-1], += ; may be NULL */);
 
+/* hlala_align_pairs keeps its device workspace (column scratch of up to three waves, DP slabs; grow-only) in the graph handle so that the next
+ * call does not pay cudaMalloc / cudaFree again; calls on one handle are serialised. This frees it early (hlala_graph_free does so too). */
+void hlala_graph_release_workspace(hlala_graph_t* g);
+
 /* Device-resident variant used by bench.py: upload once, run many times, read back small results.
  * The session owns device copies of the batch and all scratch. */
 typedef struct hlala_session hlala_session_t;
