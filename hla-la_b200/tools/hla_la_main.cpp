@@ -26,8 +26,22 @@ static int die(const char* what) { fprintf(stderr, "hlala-b200: %s: %s\n", what,
 int main(int argc, char** argv) {
     std::map<std::string, std::string> a;
     for (int i = 1; i + 1 < argc; i += 2) { if (strncmp(argv[i], "--", 2) != 0) { fprintf(stderr, "hlala-b200: bad argument %s\n", argv[i]); return 2; } a[argv[i] + 2] = argv[i + 1]; }
+    if (a["action"] == "prepareGraph" && a.count("PRG_graph_dir")) {
+        // HLA-LA.cpp:1341-1385 reads graph.txt, computes the gap-edge paths and serialises the pointer graph (hours and ~40 GB for the real
+        // PRG). Here the flat arrays (gap paths included) are built in seconds and cached next to graph.txt (PRG/graph.hlala_b200.cache); the
+        // boost archives serializedGRAPH* are neither read nor written. No GPU is needed for this action.
+        g_t0 = std::chrono::steady_clock::now();
+        hlala_graph_t* g = nullptr;
+        if (hlala_graph_load(a["PRG_graph_dir"].c_str(), &g)) return die("loading the PRG");
+        phase("graph.txt read, gap-edge paths computed, flat arrays cached");
+        fprintf(stdout, "hlala-b200: %lld levels, %lld nodes, %lld edges, %lld gap-edge paths, %lld contigs\n", (long long)hlala_graph_n_levels(g), (long long)hlala_graph_n_nodes(g),
+                (long long)hlala_graph_n_edges(g), (long long)hlala_graph_n_paths(g), (long long)hlala_graph_n_contigs(g));
+        hlala_graph_free(g);
+        return 0;
+    }
     if (a["action"] != "HLA" || !a.count("BAM") || !a.count("outputDirectory") || !a.count("PRG_graph_dir")) {
         fprintf(stderr, "usage: hlala-b200 --action HLA --sampleID <id> --BAM <remapped.bam> --outputDirectory <dir> --PRG_graph_dir <dir>\n"
+                        "       hlala-b200 --action prepareGraph --PRG_graph_dir <dir>\n"
                         "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n>] [--maxColumns <n>] [--threads <n>]\n");
         return 2;
     }

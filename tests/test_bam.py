@@ -84,6 +84,18 @@ def test_ingest_matches_the_references_extractSeeds2():
     assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
 
 
+def test_cli_prepare_graph(dataset):
+    """--action prepareGraph (HLA-LA.cpp:1341): needs no GPU; builds the flat-array cache next to graph.txt"""
+    d, _b, _mu, _sd = dataset("small")
+    cache = os.path.join(d, "PRG", "graph.hlala_b200.cache")
+    if os.path.exists(cache):
+        os.remove(cache)
+    r = subprocess.run([H.CLI, "--action", "prepareGraph", "--PRG_graph_dir", d], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and os.path.exists(cache), r.stderr
+    P = H.Product(d); dm = P.dims(); P.close()
+    assert "%d levels, %d nodes, %d edges, %d gap-edge paths" % (dm["n_levels"], dm["n_nodes"], dm["n_edges"], dm["n_paths"]) in r.stdout
+
+
 def test_cli_usage_and_loud_failure_without_gpu(dataset, tmp_path):
     r = subprocess.run([H.CLI, "--action", "HLA"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 2 and "usage: hlala-b200 --action HLA" in r.stderr
