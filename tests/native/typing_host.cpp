@@ -10,9 +10,11 @@
 using namespace hlala;
 
 namespace {
+typedef int (*host_allreduce_fn)(double* data, long long count);   // sum over ranks, in place (the gloo test passes torch.distributed.all_reduce)
 struct LoopDevice : TypingDevice {   // HLATyper.cpp:2049-2364 restated as loops over the device input layout
+    int rank = 0, world = 1; host_allreduce_fn allreduce = nullptr;   // reads split across ranks like the GPU device does (c_api.cu: r0 = R*rank/world)
     void run_locus(const LocusDeviceInput& in, bool, LocusDeviceOutput& out) override {
-        const int C = in.C, R = in.R; const double ll_ins_actual = log(0.001) + log(1.0 / 4.0), ll_del = log(0.001), ll_mm = log(1 - 0.001 - 0.001);
+        const int C = in.C, R = in.R; const int r0 = (int)((long long)R * rank / world), r1 = (int)((long long)R * (rank + 1) / world); const double ll_ins_actual = log(0.001) + log(1.0 / 4.0), ll_del = log(0.001), ll_mm = log(1 - 0.001 - 0.001);
         out.LL.assign((size_t)C * R, 0); out.mism.assign((size_t)C * R, 0);
         for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) { double ll = 0; int mm = 0; const std::string& cs = (*in.cluster_seq)[c];
             for (int k = in.rec_off[r]; k < in.rec_off[r + 1]; k++) { char e = cs[in.rec_pos[k]]; char c0 = (char)in.rec_c0[k]; unsigned glen = in.rec_glen[k]; double lp = 0;
@@ -24,8 +26,14 @@ struct LoopDevice : TypingDevice {   // HLATyper.cpp:2049-2364 restated as loops
             out.LL[(size_t)c * R + r] = ll; out.mism[(size_t)c * R + r] = mm; }
         auto log_avg = [](double a, double b) { return a > b ? log(0.5) + (log(1 + exp(b - a)) + a) : log(0.5) + (log(1 + exp(a - b)) + b); };
         for (int c1 = 0; c1 < C; c1++) for (int c2 = c1; c2 < C; c2++) { double pl = 0, sa = 0, sm = 0;
-            for (int r = 0; r < R; r++) { int m1 = out.mism[(size_t)c1 * R + r], m2 = out.mism[(size_t)c2 * R + r]; pl += log_avg(out.LL[(size_t)c1 * R + r], out.LL[(size_t)c2 * R + r]); sa += (double)(m1 + m2) / 2.0; sm += m1 < m2 ? m1 : m2; }
+            for (int r = r0; r < r1; r++) { int m1 = out.mism[(size_t)c1 * R + r], m2 = out.mism[(size_t)c2 * R + r]; pl += log_avg(out.LL[(size_t)c1 * R + r], out.LL[(size_t)c2 * R + r]); sa += (double)(m1 + m2) / 2.0; sm += m1 < m2 ? m1 : m2; }
             out.pair_ll.push_back(pl); out.pair_mavg.push_back(sa); out.pair_mmin.push_back(sm); }
+        if (world > 1) {   // ONE all-reduce per locus over [pair_ll | pair_mavg | pair_mmin], as hlala_typer_infer does on the device
+            if (!allreduce) throw std::runtime_error("world > 1 needs an all-reduce callback");
+            std::vector<double> v; v.insert(v.end(), out.pair_ll.begin(), out.pair_ll.end()); v.insert(v.end(), out.pair_mavg.begin(), out.pair_mavg.end()); v.insert(v.end(), out.pair_mmin.begin(), out.pair_mmin.end());
+            if (allreduce(v.data(), (long long)v.size()) != 0) throw std::runtime_error("all-reduce callback failed");
+            const size_t n = out.pair_ll.size(); for (size_t i = 0; i < n; i++) { out.pair_ll[i] = v[i]; out.pair_mavg[i] = v[n + i]; out.pair_mmin[i] = v[2 * n + i]; }
+        }
     }
 };
 std::string g_err;
@@ -34,8 +42,16 @@ std::string g_err;
 extern "C" {
 const char* typing_host_last_error() { return g_err.c_str(); }
 // alignment arrays as every implementation's `pairs` exports them ([n_reads, cap]); pairs named "r<p>"
+int typing_host_run_ranked(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
+                           const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, double is_mean, double is_sd, const char* out_dir, int roundtrip_blob,
+                           int rank, int world, host_allreduce_fn allreduce, double* call_q /* [n_loci * 2] */, double* pair_ll_sum /* [n_loci] */);
 int typing_host_run(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
                     const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, double is_mean, double is_sd, const char* out_dir, int roundtrip_blob) {
+    return typing_host_run_ranked(prg_dir, n_reads, read_off, bases, quals, cap, n_cols, level, g, s, mq, reverse, read_mapq, is_mean, is_sd, out_dir, roundtrip_blob, 0, 1, nullptr, nullptr, nullptr);
+}
+int typing_host_run_ranked(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
+                    const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, double is_mean, double is_sd, const char* out_dir, int roundtrip_blob,
+                           int rank, int world, host_allreduce_fn allreduce, double* call_q, double* pair_ll_sum) {
     try {
         TypingTables T; T.load(prg_dir);
         TypingReads tr; tr.col_off.push_back(0); tr.base_off.push_back(0);
@@ -62,8 +78,9 @@ int typing_host_run(const char* prg_dir, long long n_reads, const int64_t* read_
             std::vector<uint8_t> ba = a.serialize(), bb = b.serialize();
             use.deserialize_append(ba.data(), ba.size()); use.deserialize_append(bb.data(), bb.size());
         } else use = tr;
-        LoopDevice dev; TypingOptions opt; std::vector<LocusCall> calls;
+        LoopDevice dev; dev.rank = rank; dev.world = world; dev.allreduce = allreduce; TypingOptions opt; if (allreduce) opt.threads = 1; std::vector<LocusCall> calls;
         run_typing(T, use, is_mean, is_sd, out_dir, prg_dir, dev, opt, calls);
+        for (size_t l = 0; l < calls.size(); l++) { if (call_q) { call_q[2 * l] = calls[l].q1; call_q[2 * l + 1] = calls[l].q2; } if (pair_ll_sum) { double t = 0; for (double v : calls[l].dev.pair_ll) t += v; pair_ll_sum[l] = t; } }
         return (int)calls.size();
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }

@@ -59,3 +59,55 @@ def test_shard_bounds_cover_everything():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------- typing exchange
+def _typing_worker(rank, world, d, port, out_root):
+    """each rank runs the product's typing HOST logic (hla_typing.cpp) with the test-only loop stand-in for the kernels on its slice of the reads;
+    the allele-pair vectors are combined with ONE gloo all-reduce per locus through the callback, as hlala_typer_infer does with NCCL"""
+    import ctypes as C
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = H.read_arrayfile(os.path.join(d, "seeds.bin"))
+    aln = H.Oracle(d).pairs(b, 100.0, 10.0, 512); rmq = np.ascontiguousarray(aln["read_mapq"], np.float64)
+    lib = C.CDLL(os.path.join(H.REPO, "tests", "native", "build", "libtyping_host.so")); lib.typing_host_last_error.restype = C.c_char_p
+    calls = [0]
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_longlong)
+    def allreduce(ptr, count):
+        t = torch.from_numpy(np.ctypeslib.as_array(ptr, shape=(count,)))
+        dist.all_reduce(t); calls[0] += 1
+        return 0
+    out = os.path.join(out_root, "hla") if rank == 0 else ""
+    if out:
+        os.makedirs(out, exist_ok=True)
+    q = np.zeros(34, np.float64); ps = np.zeros(17, np.float64)
+    n = lib.typing_host_run_ranked(d.encode(), C.c_longlong(len(b["read_off"]) - 1), H.p(b["read_off"]), H.p(b["bases"]), H.p(b["quals"]), C.c_int(512), H.p(aln["n_cols"]), H.p(aln["level"]),
+                                   H.p(aln["gchar"]), H.p(aln["schar"]), H.p(aln["mapq"]), H.p(aln["read_reverse"]), H.p(rmq), C.c_double(100.0), C.c_double(10.0), out.encode(), C.c_int(1),
+                                   C.c_int(rank), C.c_int(world), allreduce, H.p(q), H.p(ps))
+    assert n == 17, lib.typing_host_last_error().decode()
+    assert calls[0] == 17
+    if rank == 0:
+        np.save(os.path.join(out_root, "q.npy"), np.concatenate([q, ps]))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_two_rank_typing_allreduce_matches_single_process(dataset, tmp_path):
+    import ctypes as C
+    d, b, mu, sd = dataset("typing")
+    aln = H.Oracle(d).pairs(b, mu, sd, 512); rmq = np.ascontiguousarray(aln["read_mapq"], np.float64)
+    lib = C.CDLL(os.path.join(H.REPO, "tests", "native", "build", "libtyping_host.so")); lib.typing_host_last_error.restype = C.c_char_p
+    single = str(tmp_path / "single" / "hla"); os.makedirs(single)
+    q1 = np.zeros(34, np.float64); ps1 = np.zeros(17, np.float64)
+    n = lib.typing_host_run_ranked(d.encode(), C.c_longlong(len(b["read_off"]) - 1), H.p(b["read_off"]), H.p(b["bases"]), H.p(b["quals"]), C.c_int(512), H.p(aln["n_cols"]), H.p(aln["level"]),
+                                   H.p(aln["gchar"]), H.p(aln["schar"]), H.p(aln["mapq"]), H.p(aln["read_reverse"]), H.p(rmq), C.c_double(mu), C.c_double(sd), single.encode(), C.c_int(0),
+                                   C.c_int(0), C.c_int(1), None, H.p(q1), H.p(ps1))
+    assert n == 17, lib.typing_host_last_error().decode()
+    multi = str(tmp_path / "multi"); os.makedirs(multi)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_typing_worker, args=(2, d, port, multi), nprocs=2, join=True)
+    got = np.load(os.path.join(multi, "q.npy"))
+    assert np.allclose(got[34:], ps1, rtol=1e-12, atol=1e-9), "allele-pair log-likelihood sums after the all-reduce"
+    assert np.allclose(got[:34], q1, rtol=1e-9, atol=1e-12)
+    assert open(os.path.join(multi, "hla", "R1_bestguess.txt")).read() == open(os.path.join(single, "R1_bestguess.txt")).read()
+    assert sorted(os.listdir(os.path.join(multi, "hla"))) == sorted(os.listdir(single))
