@@ -44,6 +44,22 @@ def rewrite_contigs(d, G, rng):
                 o.write(">%s\n" % k + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
 
 
+def check_loader(d, R):
+    """the product's flat graph (canonical order, gap-edge paths, jump lists in the reference's iteration order, gap stretches) against the
+    reference's pointer graph on this shuffled, gap-dense graph"""
+    rg = R.graph(); P = H.Product(d)
+    node_ord = P.array("node_ord"); eo = P.array("edge_ord"); ef = P.array("edge_from"); et = P.array("edge_to")
+    assert np.array_equal(rg["node_level"][node_ord], P.array("node_level"))
+    assert np.array_equal(rg["edge_from"][eo], node_ord[ef]) and np.array_equal(rg["edge_to"][eo], node_ord[et]) and np.array_equal(rg["edge_emis"][eo], P.array("edge_emis"))
+    assert np.array_equal(P.array("path_off"), rg["path_off"]) and np.array_equal(eo[P.array("path_edges")], rg["path_edges"]), "gap-edge paths"
+    assert np.array_equal(P.array("gap_stretch"), rg["gap_stretch"]), "gap stretches"
+    for name, key, src, dst in (("jump_fwd", "jumps_fwd", "path_from", "path_to"), ("jump_bwd", "jumps_bwd", "path_to", "path_from")):
+        off = P.array(name + "_off"); lst = P.array(name + "_path"); a, b_, c = rg[key]
+        mine = [(int(node_ord[n]), int(node_ord[P.array(dst)[p]]), int(p)) for n in np.argsort(node_ord) for p in lst[off[n]:off[n + 1]]]
+        assert mine == list(zip(a.tolist(), b_.tolist(), c.tolist())), name
+    P.close()
+
+
 def add_secondary_chains(b, rng, contig_len):
     """about half of the reads get extra secondary records: the primary's CIGAR at a random place of a random contig (same or other strand,
     lower score), and sometimes an exact duplicate of the primary's coordinates — the pair stage then has several combinations to rank,
@@ -92,6 +108,7 @@ def main():
     b = H.synth_reads(d, os.path.join(d, "seeds.bin"), pairs=120, len=60, seed=seed, clip_frac=0.5, indel_rate=0.01, gap_mean=30, gap_sd=6)
     b = add_secondary_chains(b, rng, P_dims)
     R = H.quiet(H.Ref, d); O = H.Oracle(d)
+    check_loader(d, R)
     rc = H.quiet(R.chains, b, 512); oc = O.chains(b, 512)
     for k in ("chain_order", "status", "n_cols", "seed_begin", "seed_end", "ll"):
         assert np.array_equal(rc[k], oc[k]), "seed %d: chains %s: oracle != reference" % (seed, k)
