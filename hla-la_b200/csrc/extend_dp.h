@@ -79,6 +79,11 @@ struct DpResult { int32_t n_cols; int32_t n_lvl; int32_t far_y; };   // far_y: r
 #ifdef HLALA_DP_STATS   // host-only instrumentation (tools/dp_stats.py): work per extension
 struct DpStats { long long ext, diags, touched, m1, m2, cells, diags_all_at_end, cand, max_td, max_m1; };
 inline DpStats& dp_stats() { static DpStats s = {}; return s; }
+// one record per extension: clip length, diagonals, cells, largest touched set / wavefront, widest level reached (z + 1), widest spread of
+// read positions inside one touched set, first diagonal with a gap-path jump over more than one level (0: none), longest such jump, revisits
+struct DpExtStat { int clip, diags, cells, max_td, max_m1, max_w, max_vspread, first_long_jump, max_jump_len, revisits, max_deg; };
+#include <vector>
+inline std::vector<DpExtStat>& dp_ext_stats() { static std::vector<DpExtStat> v; return v; }
 #endif
 
 __host__ __device__ inline uint32_t dp_hash3(int x, int y, int z) { uint32_t h = (uint32_t)x * 0x9E3779B1u ^ (uint32_t)y * 0x85EBCA77u ^ (uint32_t)z * 0xC2B2AE3Du; h ^= h >> 15; return h; }
@@ -143,6 +148,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     auto addneg = [](int a, int b) { return a <= DP_NEG ? DP_NEG : a + b; };
 
     int status = 0;
+#ifdef HLALA_DP_STATS
+    DpExtStat xs = {}; xs.clip = pos ? seq_len - start_seq : start_seq;
+#endif
     for (int diag = 1; ; diag++) {
         if (diag - last_inc > 40) break;
         if (n_m1 == 0 && n_m2 == 0) break;      // nothing can be produced any more; the reference idles until the patience test fires
@@ -203,12 +211,18 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
                   int tgt = pos ? G.path_to[p] : G.path_from[p];
                   int jz = tgt - G.level_node_off[jx];
                   int ti = touch(jx, jy, jz); if (ti < 0) { status = -4; break; }
+#ifdef HLALA_DP_STATS
+                  if (len > 1) { if (!xs.first_long_jump) xs.first_long_jump = diag; if (len > xs.max_jump_len) xs.max_jump_len = len; }
+#endif
                   candD(ti, pc.D + 0, dp_bt(m1[i], -2 - p, 0));
               } }
         }
         if (status) break;
 #ifdef HLALA_DP_STATS
         dp_stats().touched += n_td; if (n_td > dp_stats().max_td) dp_stats().max_td = n_td;
+        { xs.diags = diag; if (n_td > xs.max_td) xs.max_td = n_td; if (n_m1 > xs.max_m1) xs.max_m1 = n_m1; int ylo = 1 << 30, yhi = -1;
+          for (int i = 0; i < n_td; i++) { const DpTouch& t = S.td[i]; if (t.z + 1 > xs.max_w) xs.max_w = t.z + 1; if (t.y < ylo) ylo = t.y; if (t.y > yhi) yhi = t.y; }
+          if (n_td && yhi - ylo + 1 > xs.max_vspread) xs.max_vspread = yhi - ylo + 1; }
 #endif
         // ---- finalise touched cells in (x, y, z) order
         for (int i = 0; i < n_td; i++) {
@@ -230,6 +244,9 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
             int selD = t.vD;
             if (selD < -16) continue;
             bool isNew = (ci < 0);
+#ifdef HLALA_DP_STATS
+            if (!isNew) xs.revisits++;
+#endif
             if (isNew) { ci = add_cell(t.x, t.y, t.z); if (ci < 0) { status = -4; break; } }
             DpCell& c = S.cells[ci];
             bool overwritten = false;
@@ -263,7 +280,7 @@ __host__ __device__ inline int dp_extend(const DpGraph& G, const uint8_t* seq, i
     }
     S.gens[1] = tgen;
 #ifdef HLALA_DP_STATS
-    dp_stats().ext++; dp_stats().cells += n_cells;
+    dp_stats().ext++; dp_stats().cells += n_cells; xs.cells = n_cells; dp_ext_stats().push_back(xs);
 #endif
     if (status) return status;
 

@@ -28,7 +28,10 @@ typedef WdCfg<48, 64, 128, 4> WdTiny;        // ~8 KB per warp: most extensions,
 typedef WdCfg<128, 128, 256, 4> WdSmall;
 typedef WdCfg<512, 1024, 2048, 2> WdLarge;
 constexpr int WD_SUB = 64;         // edges + jumps per node
+#ifndef DP_DEFER_DEFINED
+#define DP_DEFER_DEFINED
 constexpr int DP_DEFER = -100;
+#endif
 
 struct WdEntry { int32_t cell; int32_t node; int32_t x; int16_t y; int16_t z; int16_t D, GG, SG; uint16_t deg; int32_t k0; int32_t j0; uint16_t jdeg; uint16_t pad; };
 

@@ -13,7 +13,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import harness as H  # noqa: E402
 import kmer_fuzz  # noqa: E402
-from test_dp_host import check_dp_host  # noqa: E402
+from test_dp_host import check_dp_host, check_lean_host  # noqa: E402
 
 
 def rewrite_contigs(d, G, rng):
@@ -123,6 +123,7 @@ def main():
         for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
             assert np.array_equal(rp[k][r, :m[r]], op[k][r, :m[r]]), "seed %d read %d %s" % (seed, r, k)
     tested = check_dp_host(d, b, rc)
+    lean_ok, lean_deferred = check_lean_host(d, b, rc)      # the first GPU tier (extend_lean.h) against extend_dp.h
     if "--gpu" in sys.argv:
         Pg = H.Product(d); Pg.to_gpu(0)
         gc = Pg.chains(b, 512)
@@ -137,7 +138,7 @@ def main():
             for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
                 assert np.array_equal(gp[k][r, :m[r]], rp[k][r, :m[r]]), "seed %d GPU read %d %s" % (seed, r, k)
         print("seed %d: GPU kernels ok" % seed)
-    print("seed %d: %d chains, %d extended by extend_dp.h, %d pairs ok" % (seed, int((rc["status"] == 0).sum()), tested, len(m) // 2))
+    print("seed %d: %d chains, %d extended by extend_dp.h, lean tier %d equal / %d deferred, %d pairs ok" % (seed, int((rc["status"] == 0).sum()), tested, lean_ok, lean_deferred, len(m) // 2))
 
 
 if __name__ == "__main__":

@@ -2,6 +2,8 @@
 // can compare the extension DP with the compiled reference without a GPU.
 #include "../../hla-la_b200/host/prg_graph.h"
 #include "../../hla-la_b200/csrc/extend_dp.h"
+#include "../../hla-la_b200/csrc/extend_lean.h"
+#include "../../hla-la_b200/host/dp_pack.h"
 #include <memory>
 #include <string>
 #include <vector>
@@ -9,7 +11,9 @@
 
 using namespace hlala;
 
-struct DpHost { FlatGraph g; std::vector<uint32_t> pack; DpGraph view; std::vector<unsigned char> scratch; };
+struct DpHost { FlatGraph g; std::vector<uint32_t> pack; DpGraph view; std::vector<unsigned char> scratch;
+                std::vector<uint32_t> dp_pack; std::vector<int32_t> leo; LnGraph ln; std::vector<LnRec> rec; std::vector<uint32_t> ahead; long long ln_steps = 0; };
+template <int WORDS> struct HostWords { uint32_t w[WORDS]; uint32_t& operator()(int i) { return w[i]; } };
 
 extern "C" {
 void* dp_host_open(const char* dir) {
@@ -23,6 +27,11 @@ void* dp_host_open(const char* dir) {
         v.path_off = g.path_off.data(); v.path_edges = g.path_edges.data(); v.path_from = g.path_from.data(); v.path_to = g.path_to.data();
         v.jump_fwd_off = g.jump_fwd_off.data(); v.jump_fwd_path = g.jump_fwd_path.data(); v.jump_bwd_off = g.jump_bwd_off.data(); v.jump_bwd_path = g.jump_bwd_path.data();
         h->scratch.resize(dp_scratch_bytes());
+        h->dp_pack = make_dp_pack(g); h->leo = g.level_edge_off; h->leo.resize((size_t)g.n_levels + 1, g.n_edges);
+        LnGraph& l = h->ln; l.n_levels = g.n_levels; l.level_node_off = g.level_node_off.data(); l.level_edge_off = h->leo.data(); l.dp_pack = h->dp_pack.data();
+        l.path_off = g.path_off.data(); l.path_edges = g.path_edges.data(); l.path_from = g.path_from.data(); l.path_to = g.path_to.data();
+        l.jump_fwd_off = g.jump_fwd_off.data(); l.jump_fwd_path = g.jump_fwd_path.data(); l.jump_bwd_off = g.jump_bwd_off.data(); l.jump_bwd_path = g.jump_bwd_path.data();
+        h->rec.resize(LN_CELLS + 1); h->ahead.assign(LN_AHEAD, 0xDEADBEEFu);   // the tier clears its table itself
         return h.release();
     } catch (...) { return nullptr; }
 }
@@ -43,6 +52,30 @@ int dp_host_extend(void* hv, const uint8_t* seq, int seq_len, int start_seq, int
     return 0;
 }
 }
+// the first GPU tier (extend_lean.h) on the host; returns 0, DP_DEFER (-100) or a negative code
+extern "C" int dp_host_extend_lean(void* hv, const uint8_t* seq, int seq_len, int start_seq, int seed_edge_ord, int pos, int32_t* out_edge_ord, uint8_t* out_s, int32_t* n_cols, int32_t* far_y, int32_t* applicable) {
+    DpHost* h = (DpHost*)hv; const FlatGraph& g = h->g;
+    int e = g.ord_to_edge[seed_edge_ord];
+    int node = pos ? g.edge_to[e] : g.edge_from[e]; int level = g.node_level[node]; int z = node - g.level_node_off[level];
+    *applicable = pos ? (level < g.n_levels - 1) : (level > 0);
+    *n_cols = 0; *far_y = start_seq;
+    if (!*applicable) return 0;
+    typedef HostWords<LnStd::WORDS> SM; typedef LnDp<LnStd, SM> DP;
+    SM S; LnState st;
+    int rc = DP::init(h->ln, S, st, h->rec.data(), seq, seq_len, start_seq, level, z, pos != 0);
+    if (rc) return rc;
+    for (;;) { rc = DP::step(h->ln, S, st, h->rec.data(), h->ahead.data()); h->ln_steps++; if (rc) break; }
+    if (rc != 1) return rc;
+    for (int i = 0; i < LnStd::TD; i++) if (S(LnStd::TK + i) != LN_EMPTY) return -77;   // the touch table must be left empty
+    std::vector<int32_t> oe(DP_EXT_CAP); DpResult r;
+    rc = DP::finish(h->ln, st, h->rec.data(), oe.data(), out_s, r);
+    if (rc) return rc;
+    for (int i = 0; i < r.n_cols; i++) out_edge_ord[i] = oe[i] >= 0 ? g.edge_ord[oe[i]] : -1;
+    *n_cols = r.n_cols; *far_y = r.far_y;
+    return 0;
+}
+extern "C" int dp_host_key_less_check(int x1, int z1, int x2, int z2) { return (int)dp_key_less(x1, z1, x2, z2) == (int)ln_key_less(x1, z1, x2, z2); }
 #ifdef HLALA_DP_STATS
 extern "C" void dp_host_stats(long long* out) { DpStats& s = dp_stats(); out[0] = s.ext; out[1] = s.diags; out[2] = s.touched; out[3] = s.m1; out[4] = s.m2; out[5] = s.cells; out[6] = s.diags_all_at_end; out[7] = s.max_td; out[8] = s.max_m1; s = DpStats(); }
+extern "C" long long dp_host_ext_stats(int* out, long long cap) { auto& v = dp_ext_stats(); long long n = (long long)v.size() < cap ? (long long)v.size() : cap; memcpy(out, v.data(), (size_t)n * sizeof(DpExtStat)); v.clear(); return n; }
 #endif
