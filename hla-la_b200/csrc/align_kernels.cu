@@ -3,6 +3,7 @@
 #include "extend_dp.h"
 #include "extend_warp.cuh"
 #include "extend_group.cuh"
+#include "extend_lean_kernel.cuh"
 #include "pair_kernel.cuh"
 #include "align_kernels.h"
 
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
             if (lane == 0) {
                 P.n_cols[slot] = n; P.first_level[slot] = l_first; P.last_level[slot] = l_last; P.status[slot] = CH_PENDING_EXT;
                 int idx = atomicAdd(P.pending_count, 1); P.pending_slots[idx] = slot;
+                if (need_left) { const int i = atomicAdd(P.dp_task_count, 1); const int bin = 255 - min(start_raw, 255); P.dp_tasks[i] = 2 * idx; P.dp_task_bin[i] = (uint8_t)bin; atomicAdd(P.dp_task_hist + bin, 1); }
+                if (need_right) { const int i = atomicAdd(P.dp_task_count, 1); const int bin = 255 - min(rdlen - 1 - stop_raw, 255); P.dp_tasks[i] = 2 * idx + 1; P.dp_task_bin[i] = (uint8_t)bin; atomicAdd(P.dp_task_hist + bin, 1); }
             }
             __syncwarp();
             continue;
@@ -431,6 +434,31 @@ cudaError_t launch_extend_group(const ExtParams& E0, int n_sm, cudaStream_t stre
     E.n_gd_groups = grid * per_cta;
     k_extend_group<CFG><<<grid, CFG::WARPS * 32, gd_slab_bytes<CFG>() * per_cta, stream>>>(E);
     return cudaGetLastError();
+}
+
+// Extension tasks ordered by clipped length, longest first (one CTA; counting sort over the 256 bins filled by k_chain_seed): the threads of a
+// warp then run extensions of similar length, and the longest extensions of a wave start first instead of forming its tail.
+__global__ void __launch_bounds__(1024) k_sort_dp_tasks(const int32_t* tasks, const uint8_t* bin, const int32_t* hist, const int32_t* count, int32_t* sorted) {
+    __shared__ int32_t cursor[256];
+    if (threadIdx.x < 256) cursor[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int b = 0; b < 256; b++) { const int c = cursor[b]; cursor[b] = acc; acc += c; } }
+    __syncthreads();
+    const int n = *count;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[atomicAdd(&cursor[bin[i]], 1)] = tasks[i];
+}
+cudaError_t launch_sort_dp_tasks(const ChainParams& P, int32_t* sorted, cudaStream_t stream) {
+    k_sort_dp_tasks<<<1, 1024, 0, stream>>>(P.dp_tasks, P.dp_task_bin, P.dp_task_hist, P.dp_task_count, sorted);
+    return cudaGetLastError();
+}
+
+// thread-per-extension tier (extend_lean.h): cfg 0 = LnStd over the task list, cfg 1 = LnBig over what LnStd deferred
+int ln_threads_for_any(int n_sm) { return std::max(ln_threads_for<LnStd>(n_sm), ln_threads_for<LnBig>(n_sm)); }
+size_t ln_thread_rec_bytes() { return sizeof(LnRec) * (size_t)(LN_CELLS + 1); }
+size_t ln_thread_ahead_bytes() { return 4 * (size_t)LN_AHEAD; }
+cudaError_t launch_extend_lean(const ExtParams& E, int n_sm, int cfg, cudaStream_t stream) {
+    if (E.n_pending <= 0) return cudaSuccess;
+    return cfg == 0 ? launch_ln<LnStd>(E, n_sm, stream) : launch_ln<LnBig>(E, n_sm, stream);
 }
 
 // Algorithmic HBM bytes of the extension tasks of one wave (extension DP): per task that runs, per clipped read base: the base

@@ -12,6 +12,11 @@ cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t strea
 cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream);
 cudaError_t launch_extend_warp(const ExtParams& E, int n_sm, int cfg, bool only_deferred, cudaStream_t stream);
 cudaError_t launch_extend_group(const ExtParams& E, int n_sm, cudaStream_t stream);
+cudaError_t launch_extend_lean(const ExtParams& E, int n_sm, int cfg, cudaStream_t stream);
+cudaError_t launch_sort_dp_tasks(const ChainParams& P, int32_t* sorted, cudaStream_t stream);
+int ln_threads_for_any(int n_sm);
+size_t ln_thread_rec_bytes();
+size_t ln_thread_ahead_bytes();
 int gd_groups_for(int n_sm);
 size_t gd_group_scratch_bytes();
 int wd_warps_for(int n_sm);

@@ -1,6 +1,8 @@
 // extern "C" boundary of libhlala_b200.so (include/hlala_b200.h). Host logic in C++, compute in CUDA; no CPU fallback.
 #include "../../include/hlala_b200.h"
 #include "../host/prg_graph.h"
+#include "../host/dp_pack.h"
+#include "extend_lean.h"
 #include "chain_params.h"
 #include "align_kernels.h"
 #include "typing_kernels.h"
@@ -160,18 +162,20 @@ struct ChainScratch {   // per-chain results of the whole batch
 // One in-flight wave: its column scratch, work lists, extension buffers, DP working memory and stream. Waves alternate between the
 // lanes, so the low-occupancy tail of one wave's extension cascade overlaps the next wave's chain kernel and first DP tier.
 struct Lane {
-    DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count;
+    DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count, dp_tasks, dp_task_count, dp_task_bin, dp_task_hist, dp_sorted;
+    DevBuf ln_rec, ln_ahead;   // thread-per-extension tier: 16-byte cell records and the ahead table of every resident thread
     DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch, gd_scratch; int32_t ext_cap = 0;
     DevBuf q_ctr, q_a, q_b;   // task queues of the extension cascade (counters, two ping-pong lists of deferred tasks)
     int32_t* n_pending_host = nullptr; cudaStream_t stream = nullptr; cudaEvent_t front_done = nullptr, done = nullptr;
     Lane() {}
     Lane(const Lane&) = delete; Lane& operator=(const Lane&) = delete;
     ~Lane() { if (n_pending_host) cudaFreeHost(n_pending_host); if (stream) cudaStreamDestroy(stream); if (front_done) cudaEventDestroy(front_done); if (done) cudaEventDestroy(done); }
-    void alloc(int32_t wave_chains, int32_t maxcol, size_t dp_bytes, size_t wd_bytes, size_t gd_bytes) {
+    void alloc(int32_t wave_chains, int32_t maxcol, size_t dp_bytes, size_t wd_bytes, size_t gd_bytes, size_t ln_rec_bytes, size_t ln_ahead_bytes) {
         size_t wc = (size_t)std::max(wave_chains, 1);
         c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol);
         pending_slots.alloc(wc * 4); pending_count.alloc(4); todo_slots.alloc(wc * 4); todo_count.alloc(4); defer_slots.alloc(wc * 4); defer_count.alloc(4);
-        dp_scratch.alloc(dp_bytes); wd_scratch.alloc(wd_bytes); gd_scratch.alloc(gd_bytes); q_ctr.alloc(64);
+        dp_scratch.alloc(dp_bytes); wd_scratch.alloc(wd_bytes); gd_scratch.alloc(gd_bytes); q_ctr.alloc(128);
+        dp_tasks.alloc(wc * 8); dp_task_count.alloc(4); dp_task_bin.alloc(wc * 2); dp_task_hist.alloc(1024); dp_sorted.alloc(wc * 8); ln_rec.alloc(ln_rec_bytes); ln_ahead.alloc(ln_ahead_bytes);
         if (!n_pending_host) { CUDA_OK(cudaMallocHost((void**)&n_pending_host, 4)); *n_pending_host = 0; }
         if (!stream) CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (!front_done) { CUDA_OK(cudaEventCreateWithFlags(&front_done, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); }
@@ -181,6 +185,7 @@ struct Lane {
         P.pending_slots = pending_slots.as<int32_t>(); P.pending_count = pending_count.as<int32_t>();
         P.todo_slots = todo_slots.as<int32_t>(); P.todo_count = todo_count.as<int32_t>();
         P.defer_slots = defer_slots.as<int32_t>(); P.defer_count = defer_count.as<int32_t>();
+        P.dp_tasks = dp_tasks.as<int32_t>(); P.dp_task_count = dp_task_count.as<int32_t>(); P.dp_task_bin = dp_task_bin.as<uint8_t>(); P.dp_task_hist = dp_task_hist.as<int32_t>();
     }
 };
 
@@ -235,6 +240,8 @@ struct Pipeline {
     ~Pipeline() { if (fork_ev) cudaEventDestroy(fork_ev); }
     bool scalar_dp_only = false;   // test hook: run every extension through the scalar kernel
     int32_t n_gd_groups = 0; bool group_dp = true; bool dp_trace = false;
+    bool lean_big = false;
+    int32_t n_ln_threads = 0; bool lean_dp = true;   // first DP tier: one thread per extension (extend_lean.h); false: the 8-lane group kernel (A/B runs)
     DevBuf bpl_ws; std::vector<int32_t> bpl_host;   // per-level coverage of a host-buffer call
     DevBuf is_table, phred_thr; double is_mean = -1, is_sd = -1, is_pen = 0; int32_t is_dmin = 0, is_n = 0;
     DevBuf pair_mapq, read_mapq, read_reverse, chosen_slot, pair_ll, pair_status, digest;
@@ -278,13 +285,17 @@ struct Pipeline {
         n_dp_threads = g->n_sm * (scalar_dp_only ? 64 : 8);     // otherwise the scalar kernel is the last resort of the cascade (a handful of tasks per wave)
         n_wd_warps = wd_warps_for(g->n_sm);
         n_gd_groups = gd_groups_for(g->n_sm);
+        n_ln_threads = ln_threads_for_any(g->n_sm);
+        lean_big = getenv("HLALA_LEAN_BIG") != nullptr;                  // experiment: a second thread-per-extension pass with doubled capacities before the warp tiers
+        if (getenv("HLALA_NO_LEAN_DP")) lean_dp = false;                 // test hook: the round-1 cascade (8-lane groups first)
         if (const char* e = allow_env_budget ? getenv("HLALA_LANES") : nullptr) n_lanes_max = std::max(1, atoi(e));   // test hook
         const int n_lanes = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_lanes_max, wave_pair.size() - 1));
         while ((int)lanes.size() > n_lanes) lanes.pop_back();
         for (int i = 0; i < n_lanes; i++) {
             if ((int)lanes.size() <= i) lanes.emplace_back(new Lane());
             Lane& L = *lanes[(size_t)i];
-            L.alloc(max_wave_chains, mc, (size_t)n_dp_threads * dp_thread_scratch_bytes(), (size_t)n_wd_warps * wd_warp_scratch_bytes(), (size_t)n_gd_groups * gd_group_scratch_bytes());
+            L.alloc(max_wave_chains, mc, (size_t)n_dp_threads * dp_thread_scratch_bytes(), (size_t)n_wd_warps * wd_warp_scratch_bytes(), (size_t)n_gd_groups * gd_group_scratch_bytes(),
+                    (size_t)n_ln_threads * ln_thread_rec_bytes(), (size_t)n_ln_threads * ln_thread_ahead_bytes());
             // DP working memory is zeroed once; its hashes are generation-stamped and reused without clearing afterwards
             if (L.dp_scratch.fresh) CUDA_OK(cudaMemsetAsync(L.dp_scratch.p, 0, L.dp_scratch.bytes, st));
             if (L.wd_scratch.fresh) CUDA_OK(cudaMemsetAsync(L.wd_scratch.p, 0, L.wd_scratch.bytes, st));
@@ -308,7 +319,7 @@ struct Pipeline {
           chain_kernel_bytes = 24ll * pb.n_chains + 4 * ncg + 2 * rb + cols * (4 + 1 + 6 + 8 + 1 + 6) + 44ll * pb.n_chains; }
     }
     // defaults of everything the test hooks (environment variables read in prepare) can change; a workspace kept across calls starts from them
-    void reset_config() { scratch_budget = (size_t)6 << 30; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; dp_trace = false; }
+    void reset_config() { scratch_budget = (size_t)6 << 30; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
     void ensure_columns() {
         if (have_columns) return;
         size_t n = (size_t)std::max<int64_t>(pb.n_reads, 2) * maxcol;
@@ -332,7 +343,7 @@ struct Pipeline {
             q->slot_base = db_chain_off(2 * wave_pair[w]); q->slot_end = db_chain_off(2 * wave_pair[w + 1]);
             q->read_begin = (int32_t)(2 * wave_pair[w]); q->read_end = (int32_t)(2 * wave_pair[w + 1]); q->dedup = dedup ? 1 : 0;
         }
-        CUDA_OK(cudaMemsetAsync(L.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.todo_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.defer_count.p, 0, 4, st));
+        CUDA_OK(cudaMemsetAsync(L.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.todo_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.defer_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.dp_task_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.dp_task_hist.p, 0, 1024, st));
         if (P.slot_end > P.slot_base) {
             CUDA_OK(launch_prepare(P0, st));
             tic(0, st); CUDA_OK(launch_chain_seed(P0, g->n_sm, st)); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches += 3;
@@ -355,6 +366,7 @@ struct Pipeline {
             ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = L.ext_edge.as<int32_t>(); E.ext_s = L.ext_s.as<uint8_t>(); E.ext_n = L.ext_n.as<int32_t>();
             E.ext_nlvl = L.ext_nlvl.as<int32_t>(); E.ext_rc = L.ext_rc.as<int32_t>(); E.dp_scratch = L.dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
             E.wd_scratch = L.wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps; E.gd_scratch = L.gd_scratch.as<unsigned char>(); E.n_gd_groups = n_gd_groups;
+            E.ln_rec = L.ln_rec.as<LnRec>(); E.ln_ahead = L.ln_ahead.as<uint32_t>(); E.n_ln_threads = n_ln_threads;
             if (timing) { if (!dp_bytes.p) { dp_bytes.alloc(8); CUDA_OK(cudaMemsetAsync(dp_bytes.p, 0, 8, st)); } CUDA_OK(launch_dp_task_bytes(E, dp_bytes.as<unsigned long long>(), st)); }
             tic(1, st);
             if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
@@ -368,7 +380,37 @@ struct Pipeline {
                     fprintf(stderr, "[dp-trace] %-12s %8.2f ms, tasks %d, still deferred %lld\n", what, ms, 2 * n_pending, nd); cudaEventDestroy(b); CUDA_OK(cudaEventRecord(a, st)); };
                 cudaEvent_t tr0 = nullptr; if (dp_trace) { CUDA_OK(cudaEventCreate(&tr0)); CUDA_OK(cudaEventRecord(tr0, st)); }
                 int32_t* ctr = L.q_ctr.as<int32_t>(); int32_t* qa = L.q_a.as<int32_t>(); int32_t* qb = L.q_b.as<int32_t>();
-                CUDA_OK(cudaMemsetAsync(ctr, 0, 64, st));
+                CUDA_OK(cudaMemsetAsync(ctr, 0, 128, st));
+                if (lean_dp) {
+                    // thread-per-extension tiers over the list of tasks that run; the other sides of the pending chains have no extension
+                    const size_t nt = (size_t)2 * n_pending;
+                    CUDA_OK(cudaMemsetAsync(E.ext_rc, 0, nt * 4, st)); CUDA_OK(cudaMemsetAsync(E.ext_n, 0, nt * 4, st)); CUDA_OK(cudaMemsetAsync(E.ext_nlvl, 0, nt * 4, st));
+                    CUDA_OK(launch_sort_dp_tasks(P, L.dp_sorted.as<int32_t>(), st));
+                    E.in_list = L.dp_sorted.as<int32_t>(); E.in_count = L.dp_task_count.as<int32_t>(); E.pop = ctr + 8; E.out_list = qa; E.out_count = ctr + 9;
+                    CUDA_OK(launch_extend_lean(E, g->n_sm, 0, st)); if (dp_trace) trace("lean std", tr0);
+                    launches += 1;
+                    if (lean_big) {
+                        E.in_list = qa; E.in_count = ctr + 9; E.pop = ctr + 10; E.out_list = qb; E.out_count = ctr + 11;
+                        CUDA_OK(launch_extend_lean(E, g->n_sm, 1, st)); launches += 1; if (dp_trace) trace("lean big", tr0);
+                    }
+                    toc(st);
+                    tic(4, st);
+                    E.in_list = lean_big ? qb : qa; E.in_count = lean_big ? ctr + 11 : ctr + 9; E.pop = ctr + 12; E.out_list = lean_big ? qa : qb; E.out_count = ctr + 13;
+                    if (!lean_big) { CUDA_OK(launch_extend_warp(E, g->n_sm, 0, true, st)); if (dp_trace) trace("warp tiny", tr0);
+                        E.in_list = qb; E.in_count = ctr + 13; E.pop = ctr + 14; E.out_list = qa; E.out_count = ctr + 15;
+                        CUDA_OK(launch_extend_warp(E, g->n_sm, 1, true, st)); if (dp_trace) trace("warp small", tr0);
+                        E.in_list = qa; E.in_count = ctr + 15; E.pop = ctr + 16; E.out_list = qb; E.out_count = ctr + 17;
+                        CUDA_OK(launch_extend_warp(E, g->n_sm, 2, true, st)); if (dp_trace) trace("warp large", tr0); toc(st);
+                        tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4; if (dp_trace) { trace("scalar", tr0); cudaEventDestroy(tr0); }
+                    } else {
+                    CUDA_OK(launch_extend_warp(E, g->n_sm, 0, true, st)); if (dp_trace) trace("warp tiny", tr0);
+                    E.in_list = qa; E.in_count = ctr + 13; E.pop = ctr + 14; E.out_list = qb; E.out_count = ctr + 15;
+                    CUDA_OK(launch_extend_warp(E, g->n_sm, 1, true, st)); if (dp_trace) trace("warp small", tr0);
+                    E.in_list = qb; E.in_count = ctr + 15; E.pop = ctr + 16; E.out_list = qa; E.out_count = ctr + 17;
+                    CUDA_OK(launch_extend_warp(E, g->n_sm, 2, true, st)); if (dp_trace) trace("warp large", tr0); toc(st);
+                    tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4; if (dp_trace) { trace("scalar", tr0); cudaEventDestroy(tr0); }
+                    }
+                } else {
                 if (group_dp) { E.in_list = nullptr; E.in_count = nullptr; E.pop = ctr + 0; E.out_list = qa; E.out_count = ctr + 1; CUDA_OK(launch_extend_group(E, g->n_sm, st)); launches += 1; if (dp_trace) trace("group8", tr0); }
                 toc(st);
                 tic(4, st);
@@ -379,6 +421,7 @@ struct Pipeline {
                 E.in_list = qa; E.in_count = ctr + 5; E.pop = ctr + 6; E.out_list = qb; E.out_count = ctr + 7;
                 CUDA_OK(launch_extend_warp(E, g->n_sm, 2, true, st)); if (dp_trace) trace("warp large", tr0); toc(st);
                 tic(5, st); E.only_deferred = 1; CUDA_OK(launch_extend(E, st)); launches += 4; if (dp_trace) { trace("scalar", tr0); cudaEventDestroy(tr0); }
+                }
             }
             toc(st);
             tic(2, st); CUDA_OK(launch_chain_finish(E, g->n_sm, st)); toc(st); launches += 1;
@@ -495,7 +538,7 @@ int hlala_graph_to_gpu(hlala_graph_t* g, int device) {
         g->bufs.clear(); g->kbufs.clear(); g->kix_on_gpu = false;
         DevGraph& d = g->d;
         d.n_levels = h.n_levels; d.n_nodes = h.n_nodes; d.n_edges = h.n_edges; d.n_contigs = h.n_contigs;
-        d.level_node_off = g->up(h.level_node_off); d.level_edge_off = g->up(leo); d.edge_pack = g->up(pack); d.edge_ord = g->up(h.edge_ord); d.edge_from = g->up(h.edge_from); d.edge_to = g->up(h.edge_to);
+        d.level_node_off = g->up(h.level_node_off); d.level_edge_off = g->up(leo); d.edge_pack = g->up(pack); d.dp_pack = g->up(make_dp_pack(h)); d.edge_ord = g->up(h.edge_ord); d.edge_from = g->up(h.edge_from); d.edge_to = g->up(h.edge_to);
         d.node_out_off = g->up(h.node_out_off); d.node_out = g->up(h.node_out); d.node_in_off = g->up(h.node_in_off); d.node_in = g->up(h.node_in);
         d.path_off = g->up(h.path_off); d.path_edges = g->up(h.path_edges); d.path_from = g->up(h.path_from); d.path_to = g->up(h.path_to);
         d.jump_fwd_off = g->up(h.jump_fwd_off); d.jump_fwd_path = g->up(h.jump_fwd_path); d.jump_bwd_off = g->up(h.jump_bwd_off); d.jump_bwd_path = g->up(h.jump_bwd_path);

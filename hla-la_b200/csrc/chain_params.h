@@ -34,6 +34,8 @@ struct ChainParams {
     int32_t* error_count;  // global counter of chains that ended with status < 0
     int32_t* id_first; int32_t* id_last;   // PRG levels of the BAM record's first/last reference base (processBAM.cpp:3840): de-dup key
     int32_t* pending_slots; int32_t* pending_count;   // chains whose seed needs the extension DP
+    int32_t* dp_tasks; int32_t* dp_task_count;        // the extension tasks that run: 2 * (index in pending_slots) + side, in no particular order
+    uint8_t* dp_task_bin; int32_t* dp_task_hist;      // per task: 255 - min(clipped bases, 255); histogram of the bins (k_sort_dp_tasks: longest first)
     int32_t* todo_slots; int32_t* todo_count;         // chains the chain kernel has to align (written by k_prepare)
     int32_t* defer_slots; int32_t* defer_count;       // chains that did not fit the tier-0 slab
     int32_t read_begin, read_end;                     // reads of this wave
@@ -47,6 +49,7 @@ constexpr int32_t CH_DUPLICATE = 3;   // same PRG start/stop as an earlier (bett
 constexpr int32_t CH_PENDING_EXT = 2;
 
 // extension stage (one thread per (pending chain, side))
+struct LnRec;
 struct ExtParams {
     ChainParams C;
     int32_t n_pending;
@@ -55,6 +58,7 @@ struct ExtParams {
     unsigned char* dp_scratch; int32_t n_dp_threads;   // scalar kernel: one slice per thread
     unsigned char* wd_scratch; int32_t n_wd_warps;     // warp kernel: one slice per warp
     unsigned char* gd_scratch; int32_t n_gd_groups;    // group kernel: one slice per 8-lane group
+    LnRec* ln_rec; uint32_t* ln_ahead; int32_t n_ln_threads;   // thread-per-extension tier: cell records and ahead table, one slice per thread
     int32_t only_deferred;                              // scalar kernel: run only the tasks the warp kernel deferred
     // dynamic task queues of the cascade: a tier pops task indices from `pop`; its tasks are in_list[0 .. *in_count) (in_list == nullptr: all
     // 2 * n_pending tasks) and the tasks it defers for capacity are appended to out_list

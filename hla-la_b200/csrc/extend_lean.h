@@ -30,16 +30,25 @@ namespace hlala {
 constexpr int DP_DEFER = -100;
 #endif
 
+#ifdef HLALA_LN_REASONS   // host-only instrumentation (tools/dp_stats.py): why the tier deferred
+inline long long* ln_reasons() { static long long r[16] = {}; return r; }
+#define LN_WHY(i) (ln_reasons()[i]++)
+#else
+#define LN_WHY(i) ((void)0)
+#endif
+
 template <int LIST_, int TD_> struct LnCfg {
     static constexpr int LIST = LIST_, TD = TD_;                       // TD: slots of the touch table (power of two), at most TD - 4 in use
     static constexpr int M_A = 0, M_B = 2 * LIST_, TK = 4 * LIST_, TV = TK + TD_, TB = TV + TD_, PERM = TB + TD_;
     static constexpr int WORDS = PERM + TD_ / 4;
 };
-typedef LnCfg<24, 32> LnStd;
+typedef LnCfg<24, 32> LnStd;      // 800 B per thread
+typedef LnCfg<48, 64> LnBig;      // 1600 B per thread: re-runs what LnStd deferred for its list / table capacities
+static_assert(LnBig::LIST <= 64, "list positions are 6-bit fields");
 
 constexpr int LN_CELLS = 2047;          // 11-bit cell index
-constexpr int LN_AHEAD = 512;           // slots of the ahead table (power of two)
-constexpr int LN_AHEAD_FILL = 320;
+constexpr int LN_AHEAD = 4096;          // slots of the ahead table (power of two)
+constexpr int LN_AHEAD_FILL = 1400;
 constexpr int LN_MAXLEAD = 62;
 constexpr int LN_UMAX = 510, LN_VMAX = 255, LN_ZMAX = 15, LN_EMAX = 31;
 constexpr uint32_t LN_KMASK = 0x1FFFFFu, LN_EMPTY = 0xFFFFFFFFu;
@@ -87,7 +96,7 @@ template <class CFG, class SM> struct LnDp {
     __host__ __device__ static int init(const LnGraph& G, SM& S, LnState& st, LnRec* rec, const uint8_t* seq, int seq_len, int start_seq, int start_level, int start_z, bool pos) {
         st.seq = seq; st.max_seq = seq_len; st.max_level = G.n_levels - 1; st.dir = pos ? 1 : -1; st.start_seq = start_seq;
         const int clip = pos ? seq_len - start_seq : start_seq;
-        if (clip > LN_VMAX || start_z > LN_ZMAX) return DP_DEFER;
+        if (clip > LN_VMAX || start_z > LN_ZMAX) { LN_WHY(9); return DP_DEFER; }
         st.xbase = pos ? start_level : start_level - LN_UMAX; st.ybase = pos ? start_seq : start_seq - LN_VMAX;
         st.kv_end = (pos ? seq_len : 0) - st.ybase;
         st.n_m1 = 1; st.n_m2 = 0; st.rot = 0; st.diag = 0; st.last_inc = 0; st.run_max = 32; st.first_max_cell = 0; st.n_cells = 1; st.n_ahead = 0;
@@ -127,11 +136,11 @@ template <class CFG, class SM> struct LnDp {
         };
         auto candGG = [&](int slot, uint32_t f, uint32_t pos_in_m1, uint32_t from_gg) {
             const uint32_t tv = S(CFG::TV + slot);
-            if (f > ((tv >> 10) & 1023u)) { S(CFG::TV + slot) = (tv & ~(1023u << 10)) | (f << 10); S(CFG::TB + slot) = (S(CFG::TB + slot) & ~(63u << 8)) | (pos_in_m1 << 8) | (from_gg << 13); }
+            if (f > ((tv >> 10) & 1023u)) { S(CFG::TV + slot) = (tv & ~(1023u << 10)) | (f << 10); S(CFG::TB + slot) = (S(CFG::TB + slot) & ~(127u << 8)) | (pos_in_m1 << 8) | (from_gg << 14); }
         };
         auto candSG = [&](int slot, uint32_t f, uint32_t pos_in_m1, uint32_t from_sg, uint32_t rank, uint32_t gap) {
             const uint32_t tv = S(CFG::TV + slot);
-            if (f > (tv >> 20)) { S(CFG::TV + slot) = (tv & ~(1023u << 20)) | (f << 20); S(CFG::TB + slot) = (S(CFG::TB + slot) & ~(4095u << 14)) | (pos_in_m1 << 14) | (from_sg << 19) | (rank << 20) | (gap << 25); }
+            if (f > (tv >> 20)) { S(CFG::TV + slot) = (tv & ~(1023u << 20)) | (f << 20); S(CFG::TB + slot) = (S(CFG::TB + slot) & ~(8191u << 15)) | (pos_in_m1 << 15) | (from_sg << 21) | (rank << 22) | (gap << 27); }
         };
         // ---- candidates from the m-2 list: diagonal steps (extensionAligner.cpp:565-607)
         for (int i = 0; i < st.n_m2 && !bad; i++) {
@@ -141,15 +150,15 @@ template <class CFG, class SM> struct LnDp {
             live |= (kv != st.kv_end);
             const int x = st.xbase + ku, y = st.ybase + kv, nx = x + dir, ny = y + dir;
             if (nx > st.max_level || ny > st.max_seq || nx < 0 || ny < 0) continue;
-            if (ku + dir < 0 || ku + dir > LN_UMAX) { bad = true; break; }
+            if (ku + dir < 0 || ku + dir > LN_UMAX) { LN_WHY(0); bad = true; break; }
             const uint8_t sc = dir > 0 ? st.seq[y] : st.seq[y - 1];
             const int lvl = dir > 0 ? x : x - 1; const int ea = G.level_edge_off[lvl], eb = G.level_edge_off[lvl + 1];
-            if (eb - ea > LN_EMAX + 1) { bad = true; break; }
+            if (eb - ea > LN_EMAX + 1) { LN_WHY(1); bad = true; break; }
             for (int e = ea; e < eb; e++) {
                 const uint32_t pk = G.dp_pack[e]; const int zf = (int)(pk & 255u), zt = (int)((pk >> 8) & 255u);
                 if ((dir > 0 ? zf : zt) != z) continue;
-                const int nz = dir > 0 ? zt : zf; if (nz > LN_ZMAX) { bad = true; break; }
-                const int slot = touch(((uint32_t)(ku + dir) << 12) | ((uint32_t)(kv + dir) << 4) | (uint32_t)nz); if (slot < 0) { bad = true; break; }
+                const int nz = dir > 0 ? zt : zf; if (nz > LN_ZMAX) { LN_WHY(2); bad = true; break; }
+                const int slot = touch(((uint32_t)(ku + dir) << 12) | ((uint32_t)(kv + dir) << 4) | (uint32_t)nz); if (slot < 0) { LN_WHY(3); bad = true; break; }
                 candD(slot, fD + (((pk >> 16) & 255u) == sc ? 2 : -5), idx, LN_DIAG, (uint32_t)(e - ea));
             }
         }
@@ -163,23 +172,23 @@ template <class CFG, class SM> struct LnDp {
             {   // gap in graph: consume a read base, stay on the node
                 const int gy = y + dir;
                 if (dir > 0 ? gy <= st.max_seq : gy >= 0) {
-                    const int slot = touch(((uint32_t)ku << 12) | ((uint32_t)(kv + dir) << 4) | (uint32_t)z); if (slot < 0) { bad = true; break; }
+                    const int slot = touch(((uint32_t)ku << 12) | ((uint32_t)(kv + dir) << 4) | (uint32_t)z); if (slot < 0) { LN_WHY(3); bad = true; break; }
                     candGG(slot, fD - 6, (uint32_t)i, 0); if (fGG) candGG(slot, fGG - 2, (uint32_t)i, 1);
                 }
             }
             const int sx = x + dir;
             if (!(dir > 0 ? sx <= st.max_level : sx >= 0)) continue;
-            if (ku + dir < 0 || ku + dir > LN_UMAX) { bad = true; break; }
+            if (ku + dir < 0 || ku + dir > LN_UMAX) { LN_WHY(0); bad = true; break; }
             const int lvl = dir > 0 ? x : x - 1; const int ea = G.level_edge_off[lvl], eb = G.level_edge_off[lvl + 1];
-            if (eb - ea > LN_EMAX + 1) { bad = true; break; }
+            if (eb - ea > LN_EMAX + 1) { LN_WHY(1); bad = true; break; }
             bool longjump = false;
             for (int e = ea; e < eb; e++) {   // gap in sequence along every edge; the non-affine '_' step
                 const uint32_t pk = G.dp_pack[e]; const int zf = (int)(pk & 255u), zt = (int)((pk >> 8) & 255u);
                 if ((dir > 0 ? zf : zt) != z) continue;
-                const int nz = dir > 0 ? zt : zf; if (nz > LN_ZMAX) { bad = true; break; }
+                const int nz = dir > 0 ? zt : zf; if (nz > LN_ZMAX) { LN_WHY(2); bad = true; break; }
                 const bool gap = ((pk >> 16) & 255u) == (uint32_t)'_';
                 if (pk & (dir > 0 ? (1u << 24) : (1u << 25))) longjump = true;
-                const int slot = touch(((uint32_t)(ku + dir) << 12) | ((uint32_t)kv << 4) | (uint32_t)nz); if (slot < 0) { bad = true; break; }
+                const int slot = touch(((uint32_t)(ku + dir) << 12) | ((uint32_t)kv << 4) | (uint32_t)nz); if (slot < 0) { LN_WHY(3); bad = true; break; }
                 if (!gap) candSG(slot, fD - 6, (uint32_t)i, 0, (uint32_t)(e - ea), 0);
                 if (fSG) candSG(slot, gap ? fSG : fSG - 2, (uint32_t)i, 1, (uint32_t)(e - ea), gap ? 1u : 0u);
                 if (gap) { live = true; candD(slot, fD, idx, LN_GAPEDGE, (uint32_t)(e - ea)); }
@@ -195,9 +204,9 @@ template <class CFG, class SM> struct LnDp {
                     if (len < 2) continue;
                     const int jx = x + dir * len;
                     if (!(dir > 0 ? jx <= st.max_level : jx >= 0)) continue;
-                    const int nku = ku + dir * len; if (nku < 0 || nku > LN_UMAX || k - k0 > LN_EMAX) { bad = true; break; }
-                    const int jz = (dir > 0 ? G.path_to[p] : G.path_from[p]) - G.level_node_off[jx]; if (jz > LN_ZMAX) { bad = true; break; }
-                    const int slot = touch(((uint32_t)nku << 12) | ((uint32_t)kv << 4) | (uint32_t)jz); if (slot < 0) { bad = true; break; }
+                    const int nku = ku + dir * len; if (nku < 0 || nku > LN_UMAX || k - k0 > LN_EMAX) { LN_WHY(4); bad = true; break; }
+                    const int jz = (dir > 0 ? G.path_to[p] : G.path_from[p]) - G.level_node_off[jx]; if (jz > LN_ZMAX) { LN_WHY(2); bad = true; break; }
+                    const int slot = touch(((uint32_t)nku << 12) | ((uint32_t)kv << 4) | (uint32_t)jz); if (slot < 0) { LN_WHY(3); bad = true; break; }
                     candD(slot, fD, idx, LN_JUMP, (uint32_t)(k - k0));
                 }
             }
@@ -241,18 +250,18 @@ template <class CFG, class SM> struct LnDp {
             const bool isNew = ci < 0;
             uint32_t b0n = 0, b1n = 0;     // backtrace steps offered by this diagonal
             {
-                const uint32_t ggsrc = fGG ? (S(m1o + 2 * ((tb >> 8) & 31u)) >> 21) : 0u, sgsrc = fSG ? (S(m1o + 2 * ((tb >> 14) & 31u)) >> 21) : 0u;
-                b0n = (kind >= LN_SELF_GG ? 0u : (tk >> 21)) | (kind << 11) | (((tb >> 3) & 31u) << 14) | (ggsrc << 19) | (((tb >> 13) & 1u) << 30);
-                b1n = sgsrc | (((tb >> 19) & 1u) << 11) | (((tb >> 20) & 31u) << 12) | (((tb >> 25) & 1u) << 17);
+                const uint32_t ggsrc = fGG ? (S(m1o + 2 * ((tb >> 8) & 63u)) >> 21) : 0u, sgsrc = fSG ? (S(m1o + 2 * ((tb >> 15) & 63u)) >> 21) : 0u;
+                b0n = (kind >= LN_SELF_GG ? 0u : (tk >> 21)) | (kind << 11) | (((tb >> 3) & 31u) << 14) | (ggsrc << 19) | (((tb >> 14) & 1u) << 30);
+                b1n = sgsrc | (((tb >> 21) & 1u) << 11) | (((tb >> 22) & 31u) << 12) | (((tb >> 27) & 1u) << 17);
             }
             LnRec r; bool overwritten = false;
             if (isNew) {
-                if (st.n_cells >= LN_CELLS) { rc = DP_DEFER; continue; }
+                if (st.n_cells >= LN_CELLS) { LN_WHY(5); rc = DP_DEFER; continue; }
                 ci = st.n_cells++;
                 r.k = K; r.v = fD | (fGG << 10) | (fSG << 20); r.b0 = b0n; r.b1 = b1n; rec[ci] = r;
                 if (lead > 0) {
-                    if (lead > LN_MAXLEAD || st.n_ahead >= LN_AHEAD_FILL) { rc = DP_DEFER; continue; }
-                    if (!st.ahead_ready) { for (int i = 0; i < LN_AHEAD; i++) ahead[i] = 0; st.ahead_ready = 1; }
+                    if (lead > LN_MAXLEAD || st.n_ahead >= LN_AHEAD_FILL) { LN_WHY(lead > LN_MAXLEAD ? 6 : 7); rc = DP_DEFER; continue; }
+                    if (!st.ahead_ready) { LnRec zero; zero.k = zero.v = zero.b0 = zero.b1 = 0; for (int i = 0; i < LN_AHEAD / 4; i++) reinterpret_cast<LnRec*>(ahead)[i] = zero; st.ahead_ready = 1; }
                     uint32_t h = ahead_hash(K); while (ahead[h] != 0) h = (h + 1) & (LN_AHEAD - 1);
                     ahead[h] = K | ((uint32_t)ci << 21); st.n_ahead++; st.aheadmask |= 1ull << (g & 63);
                 }
@@ -274,12 +283,12 @@ template <class CFG, class SM> struct LnDp {
                 const int x = st.xbase + ku;
                 if (st.end_idx < 0 || (int)stD > st.end_f || ((int)stD == st.end_f && ci != st.end_idx && ln_key_less(x, z, st.end_x, st.end_z))) { st.end_idx = ci; st.end_f = (int)stD; st.end_x = x; st.end_z = z; }
             }
-            if (n_mt >= CFG::LIST) { rc = DP_DEFER; continue; }
+            if (n_mt >= CFG::LIST) { LN_WHY(8); rc = DP_DEFER; continue; }
             S(m2o + 2 * n_mt) = K | ((uint32_t)ci << 21); S(m2o + 2 * n_mt + 1) = r.v; n_mt++;
             // running maximum / patience (:1007-1062); the step score is 0 exactly for '_' steps, jumps and a sequence gap extended along '_'
             if ((int)fD == st.run_max) {
                 bool tie;
-                if (isNew && !dirty) tie = !(kind == LN_GAPEDGE || kind == LN_JUMP || (kind == LN_SELF_SG && ((tb >> 19) & 1u) && ((tb >> 25) & 1u)));
+                if (isNew && !dirty) tie = !(kind == LN_GAPEDGE || kind == LN_JUMP || (kind == LN_SELF_SG && ((tb >> 21) & 1u) && ((tb >> 27) & 1u)));
                 else {   // through the STORED backtrace and the scores stored now
                     const uint32_t sk = (r.b0 >> 11) & 7u; uint32_t src, f;
                     if (sk == LN_SELF_GG) { src = (r.b0 >> 19) & 2047u; const uint32_t v = rec[src].v; f = ((r.b0 >> 30) & 1u) ? ((v >> 10) & 1023u) : (v & 1023u); }
@@ -300,6 +309,17 @@ template <class CFG, class SM> struct LnDp {
             st.n_m2 = st.n_m1; st.n_m1 = w; st.rot ^= 1;
         }
         st.aheadmask &= ~(1ull << (diag & 63));     // cells of this anti-diagonal can no longer be touched
+        // Exact early exit by bound. No stored cell can be touched again (no ahead cell is pending), so the cells and backtrace steps written so
+        // far are final; a cell still to come descends from a live entry and scores at most that entry's D + 2 per read base left (every
+        // other move adds <= 0, and GG, SG <= D). If that stays strictly below the best sequence-complete D, no later cell can take over or tie
+        // the end cell: what the reference computes during its remaining (up to 40) diagonals does not reach the result.
+        if (st.end_idx >= 0 && st.aheadmask == 0ull) {
+            int best = 0;
+            const int a1 = st.rot ? CFG::M_B : CFG::M_A, a2 = st.rot ? CFG::M_A : CFG::M_B;
+            for (int i = 0; i < st.n_m1; i++) { const int kv = (int)((S(a1 + 2 * i) >> 4) & 255u); const int rem = kv > st.kv_end ? kv - st.kv_end : st.kv_end - kv; const int v = (int)(S(a1 + 2 * i + 1) & 1023u) + 2 * rem; if (v > best) best = v; }
+            for (int i = 0; i < st.n_m2; i++) { const int kv = (int)((S(a2 + 2 * i) >> 4) & 255u); const int rem = kv > st.kv_end ? kv - st.kv_end : st.kv_end - kv; const int v = (int)(S(a2 + 2 * i + 1) & 1023u) + 2 * rem; if (v > best) best = v; }
+            if (best < st.end_f) return 1;
+        }
         return 0;
     }
 
@@ -342,7 +362,7 @@ template <class CFG, class SM> struct LnDp {
         return 0;
     }
 
-    __host__ __device__ static uint32_t ahead_hash(uint32_t K) { uint32_t h = K * 0x9E3779B1u; return (h >> 20) & (LN_AHEAD - 1); }
+    __host__ __device__ static uint32_t ahead_hash(uint32_t K) { uint32_t h = K * 0x9E3779B1u; return (h >> 19) & (LN_AHEAD - 1); }
     __host__ __device__ static int getb(SM& S, int i) { return (int)((S(CFG::PERM + (i >> 2)) >> ((i & 3) * 8)) & 255u); }
     __host__ __device__ static void setb(SM& S, int i, int v) { const int sh = (i & 3) * 8; uint32_t w = S(CFG::PERM + (i >> 2)); w = (w & ~(255u << sh)) | ((uint32_t)v << sh); S(CFG::PERM + (i >> 2)) = w; }
     __host__ __device__ static void clear_touch(SM& S) { for (int i = 0; i < CFG::TD; i++) S(CFG::TK + i) = LN_EMPTY; }

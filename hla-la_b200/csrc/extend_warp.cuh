@@ -129,6 +129,7 @@ template <class CFG> __device__ int wd_extend(const WdCtx& C, const WdSlab& S, i
     __syncwarp();
     WdEntry* m1 = S.l0; WdEntry* m2 = S.l1; WdEntry* mt = S.l2; int n_m1 = 1, n_m2 = 0;
     int cur_max = 0, first_max_cell = 0, last_inc = 0;
+    int best_end = DP_NEG;      // best stored D of a sequence-complete cell so far (exit by bound, below)
     int status = 0;
     for (int diag = 1; ; diag++) {
         if (diag - last_inc > 40) break;
@@ -263,6 +264,7 @@ template <class CFG> __device__ int wd_extend(const WdCtx& C, const WdSlab& S, i
                 int deg, jdeg; wd_adj(C, tn, ne.k0, deg, ne.j0, jdeg); ne.deg = (uint16_t)min(deg, 65535); ne.jdeg = (uint16_t)min(jdeg, 65535);
             }
             if (__any_sync(0xffffffffu, keep && (selD > running || tie_counts || overwritten))) any_inc = true;
+            best_end = max(best_end, __reduce_max_sync(0xffffffffu, (keep && ty == end_seq) ? stD : DP_NEG));
             // the cell that first reaches the largest value becomes maxima[0]
             const int chunk_max = __shfl_sync(0xffffffffu, incl, 31);
             if (chunk_max > run_max) {
@@ -300,6 +302,14 @@ template <class CFG> __device__ int wd_extend(const WdCtx& C, const WdSlab& S, i
         }
         WdEntry* t2 = m2; m2 = m1; n_m2 = n_m1; m1 = mt; n_m1 = n_mt; mt = t2;
         __syncwarp();
+        // Exact exit by bound (extend_lean.h has the argument): while no jump over >= 2 levels has been taken no stored cell can be touched again,
+        // and a cell still to come scores at most its live ancestor's D + 2 per read base left; below the best sequence-complete D nothing changes.
+        if (!hashed && best_end > DP_NEG) {
+            int bound = -1000000;
+            for (int i = lane; i < n_m1; i += 32) { const int rem = C.pos ? max_seq - m1[i].y : m1[i].y; bound = max(bound, (int)m1[i].D + 2 * rem); }
+            for (int i = lane; i < n_m2; i += 32) { const int rem = C.pos ? max_seq - m2[i].y : m2[i].y; bound = max(bound, (int)m2[i].D + 2 * rem); }
+            if (__reduce_max_sync(0xffffffffu, bound) < best_end) break;
+        }
     }
     if (status) return status;
     // ---- end cell: best sequence-complete cell (ties: lexicographically first "level/state" key), else the first cell of the maximum

@@ -53,20 +53,20 @@ int dp_host_extend(void* hv, const uint8_t* seq, int seq_len, int start_seq, int
 }
 }
 // the first GPU tier (extend_lean.h) on the host; returns 0, DP_DEFER (-100) or a negative code
-extern "C" int dp_host_extend_lean(void* hv, const uint8_t* seq, int seq_len, int start_seq, int seed_edge_ord, int pos, int32_t* out_edge_ord, uint8_t* out_s, int32_t* n_cols, int32_t* far_y, int32_t* applicable) {
+template <class CFG> static int run_lean(void* hv, const uint8_t* seq, int seq_len, int start_seq, int seed_edge_ord, int pos, int32_t* out_edge_ord, uint8_t* out_s, int32_t* n_cols, int32_t* far_y, int32_t* applicable) {
     DpHost* h = (DpHost*)hv; const FlatGraph& g = h->g;
     int e = g.ord_to_edge[seed_edge_ord];
     int node = pos ? g.edge_to[e] : g.edge_from[e]; int level = g.node_level[node]; int z = node - g.level_node_off[level];
     *applicable = pos ? (level < g.n_levels - 1) : (level > 0);
     *n_cols = 0; *far_y = start_seq;
     if (!*applicable) return 0;
-    typedef HostWords<LnStd::WORDS> SM; typedef LnDp<LnStd, SM> DP;
+    typedef HostWords<CFG::WORDS> SM; typedef LnDp<CFG, SM> DP;
     SM S; LnState st;
     int rc = DP::init(h->ln, S, st, h->rec.data(), seq, seq_len, start_seq, level, z, pos != 0);
     if (rc) return rc;
     for (;;) { rc = DP::step(h->ln, S, st, h->rec.data(), h->ahead.data()); h->ln_steps++; if (rc) break; }
+    for (int i = 0; i < CFG::TD; i++) if (S(CFG::TK + i) != LN_EMPTY) return -77;   // the touch table must be left empty
     if (rc != 1) return rc;
-    for (int i = 0; i < LnStd::TD; i++) if (S(LnStd::TK + i) != LN_EMPTY) return -77;   // the touch table must be left empty
     std::vector<int32_t> oe(DP_EXT_CAP); DpResult r;
     rc = DP::finish(h->ln, st, h->rec.data(), oe.data(), out_s, r);
     if (rc) return rc;
@@ -74,6 +74,16 @@ extern "C" int dp_host_extend_lean(void* hv, const uint8_t* seq, int seq_len, in
     *n_cols = r.n_cols; *far_y = r.far_y;
     return 0;
 }
+extern "C" int dp_host_extend_lean(void* hv, const uint8_t* seq, int seq_len, int start_seq, int seed_edge_ord, int pos, int32_t* out_edge_ord, uint8_t* out_s, int32_t* n_cols, int32_t* far_y, int32_t* applicable) {
+    return run_lean<LnStd>(hv, seq, seq_len, start_seq, seed_edge_ord, pos, out_edge_ord, out_s, n_cols, far_y, applicable);
+}
+extern "C" int dp_host_extend_lean_big(void* hv, const uint8_t* seq, int seq_len, int start_seq, int seed_edge_ord, int pos, int32_t* out_edge_ord, uint8_t* out_s, int32_t* n_cols, int32_t* far_y, int32_t* applicable) {
+    return run_lean<LnBig>(hv, seq, seq_len, start_seq, seed_edge_ord, pos, out_edge_ord, out_s, n_cols, far_y, applicable);
+}
+#ifdef HLALA_LN_REASONS
+extern "C" void dp_host_ln_reasons(long long* out) { for (int i = 0; i < 16; i++) { out[i] = ln_reasons()[i]; ln_reasons()[i] = 0; } }
+#endif
+extern "C" long long dp_host_ln_steps(void* hv) { DpHost* h = (DpHost*)hv; long long n = h->ln_steps; h->ln_steps = 0; return n; }
 extern "C" int dp_host_key_less_check(int x1, int z1, int x2, int z2) { return (int)dp_key_less(x1, z1, x2, z2) == (int)ln_key_less(x1, z1, x2, z2); }
 #ifdef HLALA_DP_STATS
 extern "C" void dp_host_stats(long long* out) { DpStats& s = dp_stats(); out[0] = s.ext; out[1] = s.diags; out[2] = s.touched; out[3] = s.m1; out[4] = s.m2; out[5] = s.cells; out[6] = s.diags_all_at_end; out[7] = s.max_td; out[8] = s.max_m1; s = DpStats(); }

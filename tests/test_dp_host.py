@@ -38,7 +38,7 @@ def check_dp_host(d, b, oc):
     return tested
 
 
-def check_lean_host(d, b, oc, lib_path=None):
+def check_lean_host(d, b, oc, lib_path=None, big=False):
     """every extension of the chains in `oc`: the first GPU tier (extend_lean.h, host build) against the scalar DP (extend_dp.h);
     returns (extensions compared, extensions the tier deferred)"""
     lib = C.CDLL(lib_path or LIB); lib.dp_host_open.restype = C.c_void_p
@@ -55,7 +55,7 @@ def check_lean_host(d, b, oc, lib_path=None):
             if not need:
                 continue
             res = []
-            for fn in (lib.dp_host_extend, lib.dp_host_extend_lean):
+            for fn in (lib.dp_host_extend, lib.dp_host_extend_lean_big if big else lib.dp_host_extend_lean):
                 oe = np.zeros(512, np.int32); os_ = np.zeros(512, np.uint8); nc = C.c_int32(); fy = C.c_int32(); app = C.c_int32()
                 rc = fn(h, H.p(seq), len(seq), int(start_seq), int(eord), pos, H.p(oe), H.p(os_), C.byref(nc), C.byref(fy), C.byref(app))
                 res.append((rc, oe[:nc.value].copy(), os_[:nc.value].copy(), fy.value, app.value))
@@ -75,6 +75,8 @@ def test_lean_tier_matches_scalar_dp(dataset, name):
     oc = H.Oracle(d).chains(b, 1024)
     tested, deferred = check_lean_host(d, b, oc)
     assert tested > 50 and deferred < tested
+    tested_big, deferred_big = check_lean_host(d, b, oc, big=True)
+    assert tested_big >= tested and deferred_big <= deferred
 
 
 def test_lean_key_order_matches_string_order():

@@ -52,13 +52,13 @@ def main():
         print("kernel not found in", so); return 1
     print("kernel:", name[:110]); print("SASS instructions: report %d, disassembly %d" % (len(data), len(lines)))
     n = min(len(data), len(lines))
-    agg = collections.defaultdict(lambda: [0.0, 0.0, collections.Counter()])
+    agg = collections.defaultdict(lambda: [0.0, 0.0, collections.Counter(), 0.0])
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot_s = tot_i = 0.0
     for k in range(n):
         r = data[k]
         s = float(r[ci["# Samples"]] or 0); ins = float(r[ci["Instructions Executed"]] or 0)
-        a = agg[lines[k]]; a[0] += s; a[1] += ins
+        a = agg[lines[k]]; a[0] += s; a[1] += ins; a[3] += float(r[ci["Thread Instructions Executed"]] or 0) if "Thread Instructions Executed" in ci else 0.0
         for h in stall_cols:
             v = float(r[ci[h]] or 0)
             if v:
@@ -79,10 +79,10 @@ def main():
         L = src_cache[f]
         return L[l - 1].strip()[:110] if 0 < l <= len(L) else ""
     print("total samples %.0f, total warp instructions %.3g" % (tot_s, tot_i))
-    print("%6s %6s  %-26s %-40s %s" % ("smp%", "ins%", "location", "top stalls", "source"))
+    print("%6s %6s %5s  %-26s %-40s %s" % ("smp%", "ins%", "lanes", "location", "top stalls", "source"))
     for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         st = ", ".join("%s %.0f%%" % (h.replace("stall_", ""), 100 * v / max(a[0], 1)) for h, v in a[2].most_common(3))
-        print("%6.2f %6.2f  %-26s %-40s %s" % (100 * a[0] / max(tot_s, 1), 100 * a[1] / max(tot_i, 1), "%s:%d" % loc if loc else "?", st, src(loc)))
+        print("%6.2f %6.2f %5.1f  %-26s %-40s %s" % (100 * a[0] / max(tot_s, 1), 100 * a[1] / max(tot_i, 1), a[3] / max(a[1], 1), "%s:%d" % loc if loc else "?", st, src(loc)))
     return 0
 
 
