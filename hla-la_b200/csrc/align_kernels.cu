@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
     WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    if (lane == 0) { mbar_init(S.mbar, 1); *S.mbar_phase = 0; }
+    __syncwarp();
     const DevBatch& B = P.b;
     const int nw = gridDim.x * K1_WARPS;
     const int n_todo = P.tier == 0 ? *P.todo_count : *P.defer_count;
@@ -455,7 +457,7 @@ cudaError_t launch_sort_dp_tasks(const ChainParams& P, int32_t* sorted, cudaStre
 // thread-per-extension tier (extend_lean.h): cfg 0 = LnStd over the task list, cfg 1 = LnBig over what LnStd deferred
 int ln_threads_for_any(int n_sm) { return std::max(ln_threads_for<LnStd>(n_sm), ln_threads_for<LnBig>(n_sm)); }
 size_t ln_thread_rec_bytes() { return sizeof(LnRec) * (size_t)(LN_CELLS + 1); }
-size_t ln_thread_ahead_bytes() { return 4 * (size_t)LN_AHEAD; }
+size_t ln_thread_ahead_bytes() { return sizeof(LnAhead) * (size_t)LN_AHEAD; }
 cudaError_t launch_extend_lean(const ExtParams& E, int n_sm, int cfg, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
     return cfg == 0 ? launch_ln<LnStd>(E, n_sm, stream) : launch_ln<LnBig>(E, n_sm, stream);

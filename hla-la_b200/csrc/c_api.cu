@@ -202,7 +202,7 @@ void chain_caps(int32_t maxcol, bool bt16, int tier, ChainParams& P) {
     P.slab_cols = maxcol; P.wcap = K1_WCAP;
     long long pool_entries = std::max<long long>(4LL * maxcol, 2560);       // entries needed
     P.pool_cap = (int32_t)(bt16 ? (pool_entries + 1) / 2 : pool_entries);    // in 32-bit words when 16-bit entries are used
-    P.win_cap = (int32_t)std::max<long long>(2LL * maxcol, 512);
+    P.win_cap = (int32_t)((std::max<long long>(2LL * maxcol, 512) + 3) & ~3LL);     // a multiple of 4 words (bulk copies are 16-byte granular)
     while (k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap) * K1_WARPS > 220000 && P.win_cap > 256) P.win_cap /= 2;
     while (k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap) * K1_WARPS > 220000 && P.pool_cap > 512) P.pool_cap /= 2;
 }
@@ -534,11 +534,12 @@ int hlala_graph_to_gpu(hlala_graph_t* g, int device) {
             int32_t f = h.edge_from[e], t = h.edge_to[e];
             pack[e] = (uint32_t)(f - h.level_node_off[h.node_level[f]]) | ((uint32_t)(t - h.level_node_off[h.node_level[t]]) << 8) | ((uint32_t)h.edge_emis[e] << 16);
         }
+        pack.resize(pack.size() + 4, 0u);      // slack: the chain kernel's bulk copies read the 16-byte aligned superset of an edge range
         std::vector<int32_t> leo(h.level_edge_off); leo.resize((size_t)h.n_levels + 1, h.n_edges);
         g->bufs.clear(); g->kbufs.clear(); g->kix_on_gpu = false;
         DevGraph& d = g->d;
         d.n_levels = h.n_levels; d.n_nodes = h.n_nodes; d.n_edges = h.n_edges; d.n_contigs = h.n_contigs;
-        d.level_node_off = g->up(h.level_node_off); d.level_edge_off = g->up(leo); d.edge_pack = g->up(pack); d.dp_pack = g->up(make_dp_pack(h)); d.edge_ord = g->up(h.edge_ord); d.edge_from = g->up(h.edge_from); d.edge_to = g->up(h.edge_to);
+        d.level_node_off = g->up(h.level_node_off); d.level_edge_off = g->up(leo); d.edge_pack = g->up(pack); { std::vector<uint32_t> dpp = make_dp_pack(h); d.lvl4 = g->up(make_lvl4(h, dpp)); d.dp_pack = g->up(dpp); } d.edge_ord = g->up(h.edge_ord); d.edge_from = g->up(h.edge_from); d.edge_to = g->up(h.edge_to);
         d.node_out_off = g->up(h.node_out_off); d.node_out = g->up(h.node_out); d.node_in_off = g->up(h.node_in_off); d.node_in = g->up(h.node_in);
         d.path_off = g->up(h.path_off); d.path_edges = g->up(h.path_edges); d.path_from = g->up(h.path_from); d.path_to = g->up(h.path_to);
         d.jump_fwd_off = g->up(h.jump_fwd_off); d.jump_fwd_path = g->up(h.jump_fwd_path); d.jump_bwd_off = g->up(h.jump_bwd_off); d.jump_bwd_path = g->up(h.jump_bwd_path);

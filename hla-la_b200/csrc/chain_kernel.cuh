@@ -9,8 +9,9 @@
 //   extensionAligner::extendSeedChain                  mapper/aligner/extensionAligner.cpp:186-333 (extension hook + padding)
 //   verboseSeedChain::extendToFullSequenceLength       mapper/reads/verboseSeedChain.cpp:82-144
 //   extensionAligner::scoreOneAlignment                mapper/aligner/extensionAligner.cpp:52-182
-// as a B200 design: columns live in shared memory (one slab per warp), the edges of the chain's level window are
-// staged once from HBM into shared memory with coalesced loads, the per-column Viterbi step is a shared-memory
+// as a B200 design: columns live in shared memory (one slab per warp), the edges of the chain's level window (a contiguous range of the
+// flat edge array) are brought into shared memory by ONE bulk copy of the TMA engine (cp.async.bulk + mbarrier, issued by lane 0 and
+// overlapped with the computation of the per-level offsets), the per-column Viterbi step is a shared-memory
 // atomicMax over packed (score, canonical edge rank) keys so that "keep all arg-max incoming edges, take the first in
 // set<Edge*> order" becomes a single integer max, and the backtrace never leaves shared memory.
 #pragma once
@@ -24,14 +25,34 @@ __constant__ ScoreTables c_tables;
 struct WarpSlab {
     int32_t* lvlA; int32_t* lvlB; uint8_t* gA; uint8_t* sA; uint8_t* gB; uint8_t* sB;
     uint32_t* bt; uint32_t* win; uint16_t* weoff; uint16_t* wwid; uint16_t* coloff; uint32_t* cur; uint32_t* nxt;
+    unsigned long long* mbar; uint32_t* mbar_phase;     // transaction barrier of the window's bulk copy and its phase bit
 };
+
+// ---- TMA bulk copy (1-D, global -> shared, completion on an mbarrier): the PTX the SASS shows as UBLKCP / SYNCS
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// src and dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses to dst are ordered before the async-proxy writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_addr(bar)), "r"(phase) : "memory");
+}
 
 __device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_cap, int win_cap, int wcap) {
     WarpSlab s; unsigned char* p = base;
+    s.win = (uint32_t*)p; p += (size_t)(win_cap + 4) * 4;      // first: the slab is 16-byte aligned, which the bulk copy needs; 3 words of slack for the aligned start, win_cap % 4 == 0
+    s.mbar = (unsigned long long*)p; p += 8; s.mbar_phase = (uint32_t*)p; p += 8;
     s.lvlA = (int32_t*)p; p += (size_t)maxcol * 4;
     s.lvlB = (int32_t*)p; p += (size_t)maxcol * 4;
     s.bt = (uint32_t*)p; p += (size_t)pool_cap * 4;
-    s.win = (uint32_t*)p; p += (size_t)win_cap * 4;
     s.weoff = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2; s.wwid = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2;
     s.cur = (uint32_t*)p; p += (size_t)wcap * 4;
     s.nxt = (uint32_t*)p; p += (size_t)wcap * 4;
@@ -230,18 +251,22 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     const int nlev = l_last - l_first + 1;
     if (l_last + 1 >= G.n_levels) return HLALA_E_INVARIANT_DEV;
     if (nlev > P.slab_cols) return HLALA_E_CAPACITY_DEV;
-    // stage the window: per level the edge offset (relative) and the node count, then the packed edges in between
+    // stage the window: the packed edges of levels [l_first, l_first + nlev) are one contiguous range of edge_pack. Lane 0 hands the 16-byte
+    // aligned superset of that range to the TMA engine; the per-level edge offsets (relative) and node counts are computed while it is in flight.
     const int e_base = G.level_edge_off[l_first];
+    const int n_win = G.level_edge_off[l_first + nlev] - e_base;
+    const int woff = e_base & 3;
+    const bool staged = n_win + woff <= P.win_cap;
+    const uint32_t* win = S.win + woff;
+    __syncwarp();
+    if (staged && lane == 0) bulk_copy_g2s(S.win, G.edge_pack + (e_base - woff), (uint32_t)(((n_win + woff) * 4 + 15) & ~15), S.mbar);
     int bad = 0;
     for (int i = lane; i <= nlev + 1; i += 32) {
         if (i <= nlev) { int rel = G.level_edge_off[l_first + i] - e_base; if (rel > 65535) bad = 1; S.weoff[i] = (uint16_t)rel; }
         int w = G.level_node_off[l_first + i + 1] - G.level_node_off[l_first + i]; if (w > P.wcap) bad = 1; S.wwid[i] = (uint16_t)w;
     }
+    if (staged) { const uint32_t ph = *S.mbar_phase; mbar_wait(S.mbar, ph); __syncwarp(); if (lane == 0) *S.mbar_phase = ph ^ 1u; }
     if (__any_sync(0xffffffffu, bad)) return HLALA_E_CAPACITY_DEV;
-    __syncwarp();
-    const int n_win = S.weoff[nlev];
-    const bool staged = n_win <= P.win_cap;
-    if (staged) for (int i = lane; i < n_win; i += 32) S.win[i] = G.edge_pack[e_base + i];
     __syncwarp();
     // init: every node of the first level, score 0 (processBAM.cpp:2696-2701)
     const int w0 = S.wwid[0];
@@ -263,7 +288,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
             // one node on either side (the common case outside variant sites): the step is a single warp reduction
             uint32_t key = 0; uint32_t pk = 0; const int e = e0 + lane;
             if (e < e1) {
-                pk = staged ? S.win[e] : G.edge_pack[e_base + e];
+                pk = staged ? win[e] : G.edge_pack[e_base + e];
                 const uint32_t kf = cur[0]; const uint8_t em = (uint8_t)(pk >> 16);
                 if (kf != 0 && !(isMatch && em != sc)) key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
             }
@@ -282,7 +307,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
         for (int z = lane; z < wn; z += 32) nxt[z] = 0;
         __syncwarp();
         for (int e = e0 + lane; e < e1; e += 32) {
-            uint32_t pk = staged ? S.win[e] : G.edge_pack[e_base + e];
+            uint32_t pk = staged ? win[e] : G.edge_pack[e_base + e];
             uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);
             if (kf != 0 && !(isMatch && em != sc)) {
                 uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
@@ -291,7 +316,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
         }
         __syncwarp();
         for (int e = e0 + lane; e < e1; e += 32) {
-            uint32_t pk = staged ? S.win[e] : G.edge_pack[e_base + e];
+            uint32_t pk = staged ? win[e] : G.edge_pack[e_base + e];
             uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);
             if (kf != 0 && !(isMatch && em != sc)) {
                 uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
@@ -322,7 +347,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
             if (BT16) { uint16_t ent = bt16[S.coloff[col] + z]; rank = ent & 255; fz = ent >> 8; }
             else { uint32_t ent = S.bt[S.coloff[col] + z]; rank = (int)(ent & KEY_RANK_MASK); fz = (int)(ent >> 20); }
             int erel = S.weoff[l - l_first] + rank;
-            uint32_t pk = staged ? S.win[erel] : G.edge_pack[e_base + erel];
+            uint32_t pk = staged ? win[erel] : G.edge_pack[e_base + erel];
             edge_out[col] = e_base + erel; c.g[col] = (uint8_t)(pk >> 16);
             z = fz; l--;
         }

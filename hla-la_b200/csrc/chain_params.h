@@ -101,7 +101,7 @@ __host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int wi
     b += (size_t)maxcol * 4 * 2;          // lvlA, lvlB
     b += (size_t)maxcol * 4;              // gA,sA,gB,sB
     b += (size_t)pool_cap * 4;            // bt (half of it used when entries are 16 bit: pool_cap then counts 16-bit entries * 2)
-    b += (size_t)win_cap * 4;             // win
+    b += (size_t)(win_cap + 4) * 4 + 16;  // win (+ slack for the 16-byte aligned bulk copy), mbarrier + phase
     b += (size_t)(maxcol + 4) * 2 * 2;    // weoff, wwid (u16)
     b += (size_t)((maxcol + 1) / 2 * 2) * 2;   // coloff (u16)
     b += (size_t)wcap * 4 * 2;            // cur, nxt

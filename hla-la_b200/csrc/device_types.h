@@ -12,6 +12,7 @@ struct DevGraph {
     const int32_t* level_edge_off;   // [n_levels+1]  (last real entry at n_levels-1; [n_levels] == n_edges)
     const uint32_t* edge_pack;       // from_z | to_z << 8 | emission << 16   (z = rank of the node inside its level)
     const uint32_t* dp_pack;         // edge_pack | long-jump flags of the edge's end nodes (host/dp_pack.h): what the first DP tier scans
+    const uint32_t* lvl4;            // [n_levels * 4] per-level record of the first DP tier (extend_lean.h LnLvl): first edge | count << 26, first three dp_pack words
     const int32_t* edge_ord;         // flat edge -> canonical ordinal
     const int32_t* edge_from; const int32_t* edge_to;   // flat edge -> flat nodes (k-mer seeding)
     const int32_t* node_out_off; const int32_t* node_out;

@@ -12,7 +12,7 @@
 //   * finished cells go to HBM as one 16-byte record (key, scores, the three backtrace steps as cell index + step kind + edge rank inside
 //     its level) written once; they are read again only by the backtrace, by revisits and by the previous-score rule on revisits;
 //   * a cell can be touched on two diagonals only if a gap-path jump over >= 2 levels created it AHEAD of its anti-diagonal
-//     (lead = anti-diagonal - diagonal > 0). Only such cells enter a small per-thread (x, y, z) -> cell table in HBM, and a 64-bit mask of
+//     (lead = anti-diagonal - diagonal > 0). Only such cells enter a small per-thread (x, y, z) -> cell table in HBM, and a 256-bit mask of
 //     the anti-diagonals that hold ahead cells keeps every other touched cell away from it.
 //   * jumps over ONE level are not replayed: their candidate equals the '_' edge's D candidate of the same source (pushed earlier, same
 //     target, same score), so it never is the first maximum and never creates a cell of its own.
@@ -40,16 +40,17 @@ inline long long* ln_reasons() { static long long r[16] = {}; return r; }
 template <int LIST_, int TD_> struct LnCfg {
     static constexpr int LIST = LIST_, TD = TD_;                       // TD: slots of the touch table (power of two), at most TD - 4 in use
     static constexpr int M_A = 0, M_B = 2 * LIST_, TK = 4 * LIST_, TV = TK + TD_, TB = TV + TD_, PERM = TB + TD_;
-    static constexpr int WORDS = PERM + TD_ / 4;
+    static constexpr int AM = PERM + TD_ / 4;                          // 256-bit mask of the anti-diagonals (mod 256) that hold ahead cells
+    static constexpr int WORDS = AM + 8;
 };
 typedef LnCfg<24, 32> LnStd;      // 800 B per thread
 typedef LnCfg<48, 64> LnBig;      // 1600 B per thread: re-runs what LnStd deferred for its list / table capacities
 static_assert(LnBig::LIST <= 64, "list positions are 6-bit fields");
 
 constexpr int LN_CELLS = 2047;          // 11-bit cell index
-constexpr int LN_AHEAD = 4096;          // slots of the ahead table (power of two)
+constexpr int LN_AHEAD = 2048;          // slots of the ahead table (power of two)
 constexpr int LN_AHEAD_FILL = 1400;
-constexpr int LN_MAXLEAD = 62;
+constexpr int LN_MAXLEAD = 250;
 constexpr int LN_UMAX = 510, LN_VMAX = 255, LN_ZMAX = 15, LN_EMAX = 31;
 constexpr uint32_t LN_KMASK = 0x1FFFFFu, LN_EMPTY = 0xFFFFFFFFu;
 constexpr int HLALA_DP_E_CAPACITY = -4, HLALA_DP_E_INVARIANT = -5;
@@ -59,8 +60,18 @@ struct LnRec { uint32_t k, v, b0, b1; };
 // b0: D source cell (11) | D kind (3) << 11 | D edge rank / jump rank (5) << 14 | GG source (11) << 19 | GG from GG (1) << 30
 // b1: SG source (11) | SG from SG (1) << 11 | SG edge rank (5) << 12 | SG edge is '_' (1) << 17
 
+// one 16-byte record per level: first edge (26 bits) | edge count (6 bits; 63 = more than the tier takes) and the dp_pack words of its first three edges, so
+// that a cell's edges cost one load (94 % of the levels of a PRG have <= 3 edges); records are prefetched when a cell enters the next wavefront
+struct LnLvl { uint32_t ec, pk0, pk1, pk2; };
+#if defined(__CUDA_ARCH__)
+#define LN_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#else
+#define LN_PREFETCH(p) ((void)0)
+#endif
+struct LnAhead { uint32_t k, v; };   // ahead table entry: key | cell index << 21 (0 = empty), stored scores
+
 struct LnGraph {   // what the tier reads of the graph; dp_pack = edge_pack | (from node has a forward jump over >= 2 levels) << 24 | (to node has a backward one) << 25
-    int32_t n_levels; const int32_t* level_node_off; const int32_t* level_edge_off; const uint32_t* dp_pack;
+    int32_t n_levels; const int32_t* level_node_off; const int32_t* level_edge_off; const uint32_t* dp_pack; const LnLvl* lvl4;
     const int32_t* path_off; const int32_t* path_edges; const int32_t* path_from; const int32_t* path_to;
     const int32_t* jump_fwd_off; const int32_t* jump_fwd_path; const int32_t* jump_bwd_off; const int32_t* jump_bwd_path;
 };
@@ -69,7 +80,7 @@ struct LnState {
     const uint8_t* seq; int max_seq, max_level, dir, xbase, ybase, kv_end, start_seq;
     int n_m1, n_m2, rot, diag, last_inc, run_max, first_max_cell, n_cells, n_ahead;
     int end_idx, end_f, end_x, end_z;
-    unsigned long long aheadmask; int ahead_ready;
+    int ahead_hi; int ahead_ready;      // ahead_hi: largest anti-diagonal that holds an ahead cell (none pending once the diagonal has passed it)
 };
 
 __host__ __device__ inline int ln_dec(uint32_t f) { return f == 0 ? DP_NEG : (int)f - 32; }
@@ -100,7 +111,8 @@ template <class CFG, class SM> struct LnDp {
         st.xbase = pos ? start_level : start_level - LN_UMAX; st.ybase = pos ? start_seq : start_seq - LN_VMAX;
         st.kv_end = (pos ? seq_len : 0) - st.ybase;
         st.n_m1 = 1; st.n_m2 = 0; st.rot = 0; st.diag = 0; st.last_inc = 0; st.run_max = 32; st.first_max_cell = 0; st.n_cells = 1; st.n_ahead = 0;
-        st.end_idx = -1; st.end_f = 0; st.end_x = 0; st.end_z = 0; st.aheadmask = 0ull; st.ahead_ready = 0;
+        st.end_idx = -1; st.end_f = 0; st.end_x = 0; st.end_z = 0; st.ahead_hi = 0; st.ahead_ready = 0;
+        for (int i = 0; i < 8; i++) S(CFG::AM + i) = 0u;
         const uint32_t K = ((uint32_t)(start_level - st.xbase) << 12) | ((uint32_t)(start_seq - st.ybase) << 4) | (uint32_t)start_z;
         S(CFG::M_A) = K; S(CFG::M_A + 1) = 32u;       // cell 0: D = 0, GG = SG = -infinity
         for (int i = 0; i < CFG::TD; i++) S(CFG::TK + i) = LN_EMPTY;
@@ -109,7 +121,7 @@ template <class CFG, class SM> struct LnDp {
     }
 
     // ---- one diagonal; returns 0 to continue, 1 when the extension has ended, DP_DEFER on capacity
-    __host__ __device__ static int step(const LnGraph& G, SM& S, LnState& st, LnRec* rec, uint32_t* ahead) {
+    __host__ __device__ static int step(const LnGraph& G, SM& S, LnState& st, LnRec* rec, LnAhead* ahead) {
         const int dir = st.dir; const int diag = ++st.diag;
         if (diag - st.last_inc > 40 || (st.n_m1 == 0 && st.n_m2 == 0)) return 1;
         const int m1o = st.rot ? CFG::M_B : CFG::M_A, m2o = st.rot ? CFG::M_A : CFG::M_B;
@@ -152,14 +164,14 @@ template <class CFG, class SM> struct LnDp {
             if (nx > st.max_level || ny > st.max_seq || nx < 0 || ny < 0) continue;
             if (ku + dir < 0 || ku + dir > LN_UMAX) { LN_WHY(0); bad = true; break; }
             const uint8_t sc = dir > 0 ? st.seq[y] : st.seq[y - 1];
-            const int lvl = dir > 0 ? x : x - 1; const int ea = G.level_edge_off[lvl], eb = G.level_edge_off[lvl + 1];
-            if (eb - ea > LN_EMAX + 1) { LN_WHY(1); bad = true; break; }
-            for (int e = ea; e < eb; e++) {
-                const uint32_t pk = G.dp_pack[e]; const int zf = (int)(pk & 255u), zt = (int)((pk >> 8) & 255u);
+            const LnLvl lv = G.lvl4[dir > 0 ? x : x - 1]; const int ea = (int)(lv.ec & 0x3FFFFFFu), ne = (int)(lv.ec >> 26);
+            if (ne > LN_EMAX + 1) { LN_WHY(1); bad = true; break; }
+            for (int k = 0; k < ne; k++) {
+                const uint32_t pk = k == 0 ? lv.pk0 : (k == 1 ? lv.pk1 : (k == 2 ? lv.pk2 : G.dp_pack[ea + k])); const int zf = (int)(pk & 255u), zt = (int)((pk >> 8) & 255u);
                 if ((dir > 0 ? zf : zt) != z) continue;
                 const int nz = dir > 0 ? zt : zf; if (nz > LN_ZMAX) { LN_WHY(2); bad = true; break; }
                 const int slot = touch(((uint32_t)(ku + dir) << 12) | ((uint32_t)(kv + dir) << 4) | (uint32_t)nz); if (slot < 0) { LN_WHY(3); bad = true; break; }
-                candD(slot, fD + (((pk >> 16) & 255u) == sc ? 2 : -5), idx, LN_DIAG, (uint32_t)(e - ea));
+                candD(slot, fD + (((pk >> 16) & 255u) == sc ? 2 : -5), idx, LN_DIAG, (uint32_t)k);
             }
         }
         // ---- candidates from the m-1 list (:621-786)
@@ -179,19 +191,19 @@ template <class CFG, class SM> struct LnDp {
             const int sx = x + dir;
             if (!(dir > 0 ? sx <= st.max_level : sx >= 0)) continue;
             if (ku + dir < 0 || ku + dir > LN_UMAX) { LN_WHY(0); bad = true; break; }
-            const int lvl = dir > 0 ? x : x - 1; const int ea = G.level_edge_off[lvl], eb = G.level_edge_off[lvl + 1];
-            if (eb - ea > LN_EMAX + 1) { LN_WHY(1); bad = true; break; }
+            const LnLvl lv = G.lvl4[dir > 0 ? x : x - 1]; const int ea = (int)(lv.ec & 0x3FFFFFFu), ne = (int)(lv.ec >> 26);
+            if (ne > LN_EMAX + 1) { LN_WHY(1); bad = true; break; }
             bool longjump = false;
-            for (int e = ea; e < eb; e++) {   // gap in sequence along every edge; the non-affine '_' step
-                const uint32_t pk = G.dp_pack[e]; const int zf = (int)(pk & 255u), zt = (int)((pk >> 8) & 255u);
+            for (int k = 0; k < ne; k++) {   // gap in sequence along every edge; the non-affine '_' step
+                const uint32_t pk = k == 0 ? lv.pk0 : (k == 1 ? lv.pk1 : (k == 2 ? lv.pk2 : G.dp_pack[ea + k])); const int zf = (int)(pk & 255u), zt = (int)((pk >> 8) & 255u);
                 if ((dir > 0 ? zf : zt) != z) continue;
                 const int nz = dir > 0 ? zt : zf; if (nz > LN_ZMAX) { LN_WHY(2); bad = true; break; }
                 const bool gap = ((pk >> 16) & 255u) == (uint32_t)'_';
                 if (pk & (dir > 0 ? (1u << 24) : (1u << 25))) longjump = true;
                 const int slot = touch(((uint32_t)(ku + dir) << 12) | ((uint32_t)kv << 4) | (uint32_t)nz); if (slot < 0) { LN_WHY(3); bad = true; break; }
-                if (!gap) candSG(slot, fD - 6, (uint32_t)i, 0, (uint32_t)(e - ea), 0);
-                if (fSG) candSG(slot, gap ? fSG : fSG - 2, (uint32_t)i, 1, (uint32_t)(e - ea), gap ? 1u : 0u);
-                if (gap) { live = true; candD(slot, fD, idx, LN_GAPEDGE, (uint32_t)(e - ea)); }
+                if (!gap) candSG(slot, fD - 6, (uint32_t)i, 0, (uint32_t)k, 0);
+                if (fSG) candSG(slot, gap ? fSG : fSG - 2, (uint32_t)i, 1, (uint32_t)k, gap ? 1u : 0u);
+                if (gap) { live = true; candD(slot, fD, idx, LN_GAPEDGE, (uint32_t)k); }
             }
             if (bad) break;
             if (longjump) {   // gap-path jumps over >= 2 levels: D + 0 into (jump level, same y, jump node)
@@ -227,6 +239,12 @@ template <class CFG, class SM> struct LnDp {
                 slot = (slot + 1) & (CFG::TD - 1);
             }
         }
+        if (st.ahead_hi >= diag) {   // ahead cells are pending: start the table look-ups of this diagonal's cells now, they are consumed one by one below
+            for (int oi = 0; oi < n_td; oi++) {
+                const uint32_t K = S(CFG::TK + getb(S, oi)) & LN_KMASK; const int s = (int)(K >> 12) + (int)((K >> 4) & 255u); const int g = dir > 0 ? s : (LN_UMAX + LN_VMAX) - s;
+                if (g <= st.ahead_hi && ((S(CFG::AM + ((g >> 5) & 7)) >> (g & 31)) & 1u)) LN_PREFETCH(ahead + ahead_hash(K));
+            }
+        }
         // ---- finalise in that order (:794-1071); the next wavefront is written over the m-2 list
         int n_mt = 0; bool dirty = false; int rc = 0;
         for (int oi = 0; oi < n_td; oi++) {
@@ -242,10 +260,10 @@ template <class CFG, class SM> struct LnDp {
             if (fD < 16) continue;                                        // keep only D >= -16
             const int ku = (int)(K >> 12), kv = (int)((K >> 4) & 255u), z = (int)(K & 15u);
             const int s = ku + kv; const int g = dir > 0 ? s : (LN_UMAX + LN_VMAX) - s; const int lead = g - diag;
-            int ci = -1;
-            if ((st.aheadmask >> (g & 63)) & 1ull) {
-                uint32_t h = ahead_hash(K);
-                for (;;) { const uint32_t a = ahead[h]; if (a == 0) break; if ((a & LN_KMASK) == K) { ci = (int)(a >> 21); break; } h = (h + 1) & (LN_AHEAD - 1); }
+            int ci = -1; uint32_t ah = 0, stv = 0;     // ahead slot and stored scores of a revisited cell
+            if (g <= st.ahead_hi && ((S(CFG::AM + ((g >> 5) & 7)) >> (g & 31)) & 1u)) {
+                ah = ahead_hash(K);
+                for (;;) { const LnAhead a = ahead[ah]; if (a.k == 0) break; if ((a.k & LN_KMASK) == K) { ci = (int)(a.k >> 21); stv = a.v; break; } ah = (ah + 1) & (LN_AHEAD - 1); }
             }
             const bool isNew = ci < 0;
             uint32_t b0n = 0, b1n = 0;     // backtrace steps offered by this diagonal
@@ -258,38 +276,43 @@ template <class CFG, class SM> struct LnDp {
             if (isNew) {
                 if (st.n_cells >= LN_CELLS) { LN_WHY(5); rc = DP_DEFER; continue; }
                 ci = st.n_cells++;
-                r.k = K; r.v = fD | (fGG << 10) | (fSG << 20); r.b0 = b0n; r.b1 = b1n; rec[ci] = r;
+                stv = fD | (fGG << 10) | (fSG << 20);
+                r.k = K; r.v = stv; r.b0 = b0n; r.b1 = b1n; rec[ci] = r;
                 if (lead > 0) {
                     if (lead > LN_MAXLEAD || st.n_ahead >= LN_AHEAD_FILL) { LN_WHY(lead > LN_MAXLEAD ? 6 : 7); rc = DP_DEFER; continue; }
-                    if (!st.ahead_ready) { LnRec zero; zero.k = zero.v = zero.b0 = zero.b1 = 0; for (int i = 0; i < LN_AHEAD / 4; i++) reinterpret_cast<LnRec*>(ahead)[i] = zero; st.ahead_ready = 1; }
-                    uint32_t h = ahead_hash(K); while (ahead[h] != 0) h = (h + 1) & (LN_AHEAD - 1);
-                    ahead[h] = K | ((uint32_t)ci << 21); st.n_ahead++; st.aheadmask |= 1ull << (g & 63);
+                    if (!st.ahead_ready) { LnRec zero; zero.k = zero.v = zero.b0 = zero.b1 = 0; for (int i = 0; i < LN_AHEAD / 2; i++) reinterpret_cast<LnRec*>(ahead)[i] = zero; st.ahead_ready = 1; }
+                    uint32_t h = ahead_hash(K); while (ahead[h].k != 0) h = (h + 1) & (LN_AHEAD - 1);
+                    LnAhead a; a.k = K | ((uint32_t)ci << 21); a.v = stv; ahead[h] = a; st.n_ahead++; S(CFG::AM + ((g >> 5) & 7)) |= 1u << (g & 31); if (g > st.ahead_hi) st.ahead_hi = g;
                 }
-            } else {
-                r = rec[ci];
-                uint32_t sD = r.v & 1023u, sGG = (r.v >> 10) & 1023u, sSG = r.v >> 20;
-                if (sD < fD) { overwritten = true; sD = fD; r.b0 = (r.b0 & ~0x7FFFFu) | (b0n & 0x7FFFFu); }
-                if (sGG < fGG) { overwritten = true; sGG = fGG; r.b0 = (r.b0 & 0x7FFFFu) | (b0n & ~0x7FFFFu); }
-                if (sSG < fSG) { overwritten = true; sSG = fSG; r.b1 = b1n; }
+            } else {     // revisit: the scores come with the table entry; the record is read only if a matrix improves (or for the tie rule below)
+                uint32_t sD = stv & 1023u, sGG = (stv >> 10) & 1023u, sSG = stv >> 20;
+                overwritten = sD < fD || sGG < fGG || sSG < fSG;
                 if (overwritten) {
-                    r.v = sD | (sGG << 10) | (sSG << 20); rec[ci] = r; dirty = true;
+                    r = rec[ci];
+                    if (sD < fD) { sD = fD; r.b0 = (r.b0 & ~0x7FFFFu) | (b0n & 0x7FFFFu); }
+                    if (sGG < fGG) { sGG = fGG; r.b0 = (r.b0 & 0x7FFFFu) | (b0n & ~0x7FFFFu); }
+                    if (sSG < fSG) { sSG = fSG; r.b1 = b1n; }
+                    stv = sD | (sGG << 10) | (sSG << 20);
+                    r.v = stv; rec[ci] = r; dirty = true; ahead[ah].v = stv;
                     // the reference's lists hold coordinates and read the score table when used: a cell improved while it still sits in the
                     // m-1 list must show its new scores when that list is consumed as the m-2 list of the next diagonal
-                    for (int i = 0; i < st.n_m1; i++) if ((S(m1o + 2 * i) >> 21) == (uint32_t)ci) S(m1o + 2 * i + 1) = r.v;
+                    for (int i = 0; i < st.n_m1; i++) if ((S(m1o + 2 * i) >> 21) == (uint32_t)ci) S(m1o + 2 * i + 1) = stv;
                 }
             }
-            const uint32_t stD = r.v & 1023u;
+            const uint32_t stD = stv & 1023u;
             if (kv == st.kv_end) {   // sequence-complete: best end cell so far (max stored D, ties -> lexicographically first "level/state" key, :1391-1478)
                 const int x = st.xbase + ku;
                 if (st.end_idx < 0 || (int)stD > st.end_f || ((int)stD == st.end_f && ci != st.end_idx && ln_key_less(x, z, st.end_x, st.end_z))) { st.end_idx = ci; st.end_f = (int)stD; st.end_x = x; st.end_z = z; }
             }
             if (n_mt >= CFG::LIST) { LN_WHY(8); rc = DP_DEFER; continue; }
-            S(m2o + 2 * n_mt) = K | ((uint32_t)ci << 21); S(m2o + 2 * n_mt + 1) = r.v; n_mt++;
+            S(m2o + 2 * n_mt) = K | ((uint32_t)ci << 21); S(m2o + 2 * n_mt + 1) = stv; n_mt++;
+            { const int pl = st.xbase + ku - (dir > 0 ? 0 : 1); if (pl >= 0 && pl < G.n_levels) LN_PREFETCH(G.lvl4 + pl); }     // the level record this cell reads on the next two diagonals
             // running maximum / patience (:1007-1062); the step score is 0 exactly for '_' steps, jumps and a sequence gap extended along '_'
             if ((int)fD == st.run_max) {
                 bool tie;
                 if (isNew && !dirty) tie = !(kind == LN_GAPEDGE || kind == LN_JUMP || (kind == LN_SELF_SG && ((tb >> 21) & 1u) && ((tb >> 27) & 1u)));
                 else {   // through the STORED backtrace and the scores stored now
+                    if (!isNew && !overwritten) r = rec[ci];
                     const uint32_t sk = (r.b0 >> 11) & 7u; uint32_t src, f;
                     if (sk == LN_SELF_GG) { src = (r.b0 >> 19) & 2047u; const uint32_t v = rec[src].v; f = ((r.b0 >> 30) & 1u) ? ((v >> 10) & 1023u) : (v & 1023u); }
                     else if (sk == LN_SELF_SG) { src = r.b1 & 2047u; const uint32_t v = rec[src].v; f = ((r.b1 >> 11) & 1u) ? (v >> 20) : (v & 1023u); }
@@ -308,12 +331,12 @@ template <class CFG, class SM> struct LnDp {
             for (int i = 0; i < n_mt; i++) { const uint32_t a = S(m2o + 2 * i), b = S(m2o + 2 * i + 1); if (mx - (b & 1023u) <= 15u) { S(m2o + 2 * w) = a; S(m2o + 2 * w + 1) = b; w++; } }
             st.n_m2 = st.n_m1; st.n_m1 = w; st.rot ^= 1;
         }
-        st.aheadmask &= ~(1ull << (diag & 63));     // cells of this anti-diagonal can no longer be touched
+        if (st.ahead_hi >= diag) S(CFG::AM + ((diag >> 5) & 7)) &= ~(1u << (diag & 31));     // cells of this anti-diagonal can no longer be touched
         // Exact early exit by bound. No stored cell can be touched again (no ahead cell is pending), so the cells and backtrace steps written so
         // far are final; a cell still to come descends from a live entry and scores at most that entry's D + 2 per read base left (every
         // other move adds <= 0, and GG, SG <= D). If that stays strictly below the best sequence-complete D, no later cell can take over or tie
         // the end cell: what the reference computes during its remaining (up to 40) diagonals does not reach the result.
-        if (st.end_idx >= 0 && st.aheadmask == 0ull) {
+        if (st.end_idx >= 0 && st.ahead_hi <= diag) {
             int best = 0;
             const int a1 = st.rot ? CFG::M_B : CFG::M_A, a2 = st.rot ? CFG::M_A : CFG::M_B;
             for (int i = 0; i < st.n_m1; i++) { const int kv = (int)((S(a1 + 2 * i) >> 4) & 255u); const int rem = kv > st.kv_end ? kv - st.kv_end : st.kv_end - kv; const int v = (int)(S(a1 + 2 * i + 1) & 1023u) + 2 * rem; if (v > best) best = v; }
@@ -351,9 +374,9 @@ template <class CFG, class SM> struct LnDp {
                     if (dir > 0) { for (int q = b - 1; q >= a; q--) { out_edge[n] = G.path_edges[q]; out_s[n] = '_'; n++; n_lvl++; } }
                     else { for (int q = a; q < b; q++) { out_edge[n] = G.path_edges[q]; out_s[n] = '_'; n++; n_lvl++; } }
                     emit1 = false;
-                } else { e = G.level_edge_off[lvl] + (int)((c.b0 >> 14) & 31u); s = kind == LN_DIAG ? sc : (uint8_t)'_'; }
+                } else { e = (int)(G.lvl4[lvl].ec & 0x3FFFFFFu) + (int)((c.b0 >> 14) & 31u); s = kind == LN_DIAG ? sc : (uint8_t)'_'; }
             } else if (mat == 1) { src = (int)((c.b0 >> 19) & 2047u); nmat = (int)((c.b0 >> 30) & 1u) ? 1 : 0; e = -1; s = sc; }
-            else { src = (int)(c.b1 & 2047u); nmat = (int)((c.b1 >> 11) & 1u) ? 2 : 0; e = G.level_edge_off[lvl] + (int)((c.b1 >> 12) & 31u); s = '_'; }
+            else { src = (int)(c.b1 & 2047u); nmat = (int)((c.b1 >> 11) & 1u) ? 2 : 0; e = (int)(G.lvl4[lvl].ec & 0x3FFFFFFu) + (int)((c.b1 >> 12) & 31u); s = '_'; }
             if (emit1) { if (n >= DP_EXT_CAP) return HLALA_DP_E_CAPACITY; out_edge[n] = e; out_s[n] = s; n++; if (e >= 0) n_lvl++; }
             cur = src; mat = nmat; c = rec[cur];
         }
@@ -363,8 +386,8 @@ template <class CFG, class SM> struct LnDp {
     }
 
     __host__ __device__ static uint32_t ahead_hash(uint32_t K) { uint32_t h = K * 0x9E3779B1u; return (h >> 19) & (LN_AHEAD - 1); }
-    __host__ __device__ static int getb(SM& S, int i) { return (int)((S(CFG::PERM + (i >> 2)) >> ((i & 3) * 8)) & 255u); }
-    __host__ __device__ static void setb(SM& S, int i, int v) { const int sh = (i & 3) * 8; uint32_t w = S(CFG::PERM + (i >> 2)); w = (w & ~(255u << sh)) | ((uint32_t)v << sh); S(CFG::PERM + (i >> 2)) = w; }
+    __host__ __device__ static int getb(SM& S, int i) { return (int)S.b(CFG::PERM + (i >> 2), i & 3); }
+    __host__ __device__ static void setb(SM& S, int i, int v) { S.b(CFG::PERM + (i >> 2), i & 3) = (uint8_t)v; }
     __host__ __device__ static void clear_touch(SM& S) { for (int i = 0; i < CFG::TD; i++) S(CFG::TK + i) = LN_EMPTY; }
 };
 

@@ -17,7 +17,11 @@ namespace hlala {
 constexpr int LN_BLOCK = 32;       // threads per CTA: one warp, so that the resident warps per SM follow the shared-memory budget in steps of one
 constexpr int LN_BATCH = 6;        // waiting threads of a warp that trigger the backtrace / fetch phase
 
-struct LnSmem { uint32_t* base; __device__ __forceinline__ uint32_t& operator()(int i) const { return base[i * 32]; } };
+struct LnSmem {
+    uint32_t* base;
+    __device__ __forceinline__ uint32_t& operator()(int i) const { return base[i * 32]; }
+    __device__ __forceinline__ uint8_t& b(int word, int byte) const { return reinterpret_cast<uint8_t*>(base + word * 32)[byte]; }
+};
 
 template <class CFG> __global__ void __launch_bounds__(LN_BLOCK) k_extend_lean(ExtParams E) {
     extern __shared__ __align__(16) uint32_t ln_smem[];
@@ -26,8 +30,8 @@ template <class CFG> __global__ void __launch_bounds__(LN_BLOCK) k_extend_lean(E
     LnSmem S; S.base = ln_smem + (size_t)warp * CFG::WORDS * 32 + lane;
     const int gt = blockIdx.x * LN_BLOCK + threadIdx.x;
     LnRec* rec = E.ln_rec + (size_t)gt * (LN_CELLS + 1);
-    uint32_t* ahead = E.ln_ahead + (size_t)gt * LN_AHEAD;
-    LnGraph G; G.n_levels = DG.n_levels; G.level_node_off = DG.level_node_off; G.level_edge_off = DG.level_edge_off; G.dp_pack = DG.dp_pack;
+    LnAhead* ahead = reinterpret_cast<LnAhead*>(E.ln_ahead) + (size_t)gt * LN_AHEAD;
+    LnGraph G; G.n_levels = DG.n_levels; G.level_node_off = DG.level_node_off; G.level_edge_off = DG.level_edge_off; G.dp_pack = DG.dp_pack; G.lvl4 = reinterpret_cast<const LnLvl*>(DG.lvl4);
     G.path_off = DG.path_off; G.path_edges = DG.path_edges; G.path_from = DG.path_from; G.path_to = DG.path_to;
     G.jump_fwd_off = DG.jump_fwd_off; G.jump_fwd_path = DG.jump_fwd_path; G.jump_bwd_off = DG.jump_bwd_off; G.jump_bwd_path = DG.jump_bwd_path;
     typedef LnDp<CFG, LnSmem> DP;

@@ -3,6 +3,7 @@
 //   bit 24: the edge's FROM node has such a forward jump, bit 25: the edge's TO node has such a backward jump.
 #pragma once
 #include "prg_graph.h"
+#include <stdexcept>
 #include <vector>
 
 namespace hlala {
@@ -17,6 +18,20 @@ inline std::vector<uint32_t> make_dp_pack(const FlatGraph& g) {
                   | ((uint32_t)fwd[f] << 24) | ((uint32_t)bwd[t] << 25);
     }
     return pack;
+}
+
+// extend_lean.h LnLvl, as four words per level: first edge | min(edge count, 63) << 26, dp_pack of the first three edges; levels [0, n_levels)
+inline std::vector<uint32_t> make_lvl4(const FlatGraph& g, const std::vector<uint32_t>& dp_pack) {
+    std::vector<uint32_t> r((size_t)g.n_levels * 4, 0u);
+    for (int32_t l = 0; l < g.n_levels; l++) {
+        const int32_t ea = l < (int32_t)g.level_edge_off.size() ? g.level_edge_off[l] : g.n_edges;
+        const int32_t eb = l + 1 < (int32_t)g.level_edge_off.size() ? g.level_edge_off[l + 1] : g.n_edges;
+        const int32_t n = eb - ea;
+        if (ea >= (1 << 26)) throw std::runtime_error("graph has more than 2^26 edges: the level records of the extension DP hold 26-bit edge offsets");
+        r[(size_t)l * 4] = (uint32_t)ea | ((uint32_t)(n > 63 ? 63 : n) << 26);
+        for (int k = 0; k < 3 && k < n; k++) r[(size_t)l * 4 + 1 + k] = dp_pack[(size_t)ea + k];
+    }
+    return r;
 }
 
 } // namespace hlala

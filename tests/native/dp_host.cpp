@@ -12,8 +12,8 @@
 using namespace hlala;
 
 struct DpHost { FlatGraph g; std::vector<uint32_t> pack; DpGraph view; std::vector<unsigned char> scratch;
-                std::vector<uint32_t> dp_pack; std::vector<int32_t> leo; LnGraph ln; std::vector<LnRec> rec; std::vector<uint32_t> ahead; long long ln_steps = 0; };
-template <int WORDS> struct HostWords { uint32_t w[WORDS]; uint32_t& operator()(int i) { return w[i]; } };
+                std::vector<uint32_t> dp_pack; std::vector<int32_t> leo; LnGraph ln; std::vector<LnRec> rec; std::vector<LnAhead> ahead; std::vector<uint32_t> lvl4; long long ln_steps = 0; };
+template <int WORDS> struct HostWords { uint32_t w[WORDS]; uint32_t& operator()(int i) { return w[i]; } uint8_t& b(int word, int byte) { return ((uint8_t*)&w[word])[byte]; } };
 
 extern "C" {
 void* dp_host_open(const char* dir) {
@@ -31,7 +31,8 @@ void* dp_host_open(const char* dir) {
         LnGraph& l = h->ln; l.n_levels = g.n_levels; l.level_node_off = g.level_node_off.data(); l.level_edge_off = h->leo.data(); l.dp_pack = h->dp_pack.data();
         l.path_off = g.path_off.data(); l.path_edges = g.path_edges.data(); l.path_from = g.path_from.data(); l.path_to = g.path_to.data();
         l.jump_fwd_off = g.jump_fwd_off.data(); l.jump_fwd_path = g.jump_fwd_path.data(); l.jump_bwd_off = g.jump_bwd_off.data(); l.jump_bwd_path = g.jump_bwd_path.data();
-        h->rec.resize(LN_CELLS + 1); h->ahead.assign(LN_AHEAD, 0xDEADBEEFu);   // the tier clears its table itself
+        h->lvl4 = make_lvl4(g, h->dp_pack); l.lvl4 = (const LnLvl*)h->lvl4.data();
+        h->rec.resize(LN_CELLS + 1); h->ahead.assign(LN_AHEAD, LnAhead{0xDEADBEEFu, 0xDEADBEEFu});   // the tier clears its table itself
         return h.release();
     } catch (...) { return nullptr; }
 }
