@@ -361,9 +361,11 @@ static void load_contigs(const std::string& dir, FlatGraph& g) {
         if (f.size() != header.size()) throw std::runtime_error("sequences.txt: field count mismatch");
         int32_t id = atoi(f[c_id].c_str());
         std::string bam = f[c_chr].empty() ? ("PRG_" + f[c_id]) : f[c_chr];
+        // processBAM.cpp:86-88: the PRG-only FASTA must NOT hold PRG_5 (assert) and the reference injects "N" for it
         auto it = fa.find(bam);
-        if (it == fa.end()) throw std::runtime_error(bam + " cannot be found in the PRG-only reference genome " + dir + "/mapping_PRGonly/referenceGenome.fa");
-        const std::string seq = (bam == "PRG_5") ? std::string("N") : it->second;   // processBAM.cpp:87-88
+        if (bam == "PRG_5") { if (it != fa.end()) throw std::runtime_error("PRG_5 must not be part of " + dir + "/mapping_PRGonly/referenceGenome.fa (the reference asserts this and uses \"N\")"); }
+        else if (it == fa.end()) throw std::runtime_error(bam + " cannot be found in the PRG-only reference genome " + dir + "/mapping_PRGonly/referenceGenome.fa");
+        const std::string seq = (bam == "PRG_5") ? std::string("N") : it->second;
         // translation file with the reference's getline loop semantics (processBAM.cpp:4409-4414): every line is parsed with
         // StrtoI, and a file ending in a newline yields one more (empty) line that parses as 0
         std::string tp = dir + "/translation/" + f[c_id] + ".txt";

@@ -69,3 +69,32 @@ def test_missing_directory_reports_error(tmp_path):
     g = C.c_void_p()
     rc = lib.hlala_graph_load(str(tmp_path / "nope").encode(), C.byref(g))
     assert rc == -2 and b"graph" in lib.hlala_last_error()
+
+
+def test_prg5_is_injected_not_looked_up(dataset, tmp_path):
+    """sequences.txt lists contig 5 but the PRG-only FASTA does not hold PRG_5: the reference asserts exactly that and injects "N" (processBAM.cpp:86-88)"""
+    d, b, mu, sd = dataset("small")
+    d2 = str(tmp_path / "prg"); shutil.copytree(d, d2)
+    for f in ("PRG/graph.hlala_b200.cache",):
+        if os.path.exists(os.path.join(d2, f)):
+            os.remove(os.path.join(d2, f))
+    with open(os.path.join(d2, "sequences.txt"), "a") as f:
+        f.write("5\tpgf\tPRG_5\t\t1\t1\n")
+    with open(os.path.join(d2, "translation", "5.txt"), "w") as f:
+        f.write("7\n")
+    os.environ["HLALA_NO_GRAPH_CACHE"] = "1"
+    try:
+        A = H.Product(d); Bp = H.Product(d2)
+        off = Bp.array("contig_off"); seq = Bp.array("contig_seq")
+        assert len(off) == len(A.array("contig_off")) + 1
+        assert bytes(seq[off[-2]:off[-1]]) == b"N" and int(Bp.array("contig_prg_id")[-1]) == 5
+        assert int(Bp.array("contig_level")[off[-2]]) == 7
+        A.close(); Bp.close()
+        # a FASTA that does hold PRG_5 is refused like the reference's assert
+        with open(os.path.join(d2, "mapping_PRGonly", "referenceGenome.fa"), "a") as f:
+            f.write(">PRG_5\nACGT\n")
+        lib = C.CDLL(H.LIB_PRODUCT); lib.hlala_last_error.restype = C.c_char_p
+        g = C.c_void_p()
+        assert lib.hlala_graph_load(d2.encode(), C.byref(g)) != 0 and b"PRG_5" in lib.hlala_last_error()
+    finally:
+        os.environ.pop("HLALA_NO_GRAPH_CACHE", None)
