@@ -258,12 +258,20 @@ struct Pipeline {
         timed.clear();
     }
     std::vector<int64_t> wave_pair;    // wave w covers pairs [wave_pair[w], wave_pair[w+1])
-    size_t scratch_budget = (size_t)6 << 30;   // bytes of per-chain column scratch per wave
+    size_t scratch_budget = 0;   // bytes of per-chain column scratch per wave; 0 = from the device's memory (see prepare)
     bool allow_env_budget = true;
     bool dedup = true;    // false: align every same-strand chain (parity tests of the chain kernels)
 
     void prepare(hlala_graph* graph, const hlala_seed_batch_t& b, int32_t mc, cudaStream_t st) {
         g = graph; maxcol = mc; have_columns = false;
+        if (scratch_budget == 0) {
+            // The extension tiers are persistent grids that pop tasks from a queue: the more tasks a launch holds, the smaller the share of its
+            // tail (measured on B200, 1 M pairs: one wave 445 ms, ten waves on three lanes 507 ms). So: one wave if the column scratch of the
+            // whole batch fits 40 % of the device memory, else three lanes sharing that much.
+            size_t free_b = 0, total_b = 0; CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t avail = total_b / 5 * 2, need = (size_t)std::max(b.chain_off[b.n_reads], 1) * (size_t)mc * 6;
+            scratch_budget = need <= avail ? need : avail / 3;
+        }
         if (const char* e = allow_env_budget ? getenv("HLALA_WAVE_BYTES") : nullptr) scratch_budget = (size_t)strtoull(e, nullptr, 10);   // test hook: force several waves
         pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1); host_read_off.assign(b.read_off, b.read_off + b.n_reads + 1);
         // waves: consecutive pairs whose chains fit the column-scratch budget
@@ -319,7 +327,7 @@ struct Pipeline {
           chain_kernel_bytes = 24ll * pb.n_chains + 4 * ncg + 2 * rb + cols * (4 + 1 + 6 + 8 + 1 + 6) + 44ll * pb.n_chains; }
     }
     // defaults of everything the test hooks (environment variables read in prepare) can change; a workspace kept across calls starts from them
-    void reset_config() { scratch_budget = (size_t)6 << 30; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
+    void reset_config() { scratch_budget = 0; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
     void ensure_columns() {
         if (have_columns) return;
         size_t n = (size_t)std::max<int64_t>(pb.n_reads, 2) * maxcol;

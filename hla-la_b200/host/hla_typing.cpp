@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <exception>
+#include <memory>
 #include <thread>
 #include <mutex>
 #include <condition_variable>
@@ -19,6 +20,7 @@
 #include <stdexcept>
 #include <sys/stat.h>
 #include <unordered_set>
+#include <chrono>
 
 namespace hlala {
 
@@ -295,6 +297,16 @@ struct KmerSet {
     }
 };
 
+// HLALA_TYPING_PROFILE=1: wall time per phase of run_typing, summed over loci / threads, on stderr
+struct PhaseClock {
+    static constexpr int N = 10; std::atomic<long long> ns[N]; bool on;
+    PhaseClock() : on(getenv("HLALA_TYPING_PROFILE") != nullptr) { for (auto& v : ns) v = 0; }
+    struct Scope { PhaseClock& c; int i; std::chrono::steady_clock::time_point t0; Scope(PhaseClock& c_, int i_) : c(c_), i(i_), t0(std::chrono::steady_clock::now()) {}
+                   ~Scope() { if (c.on) c.ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } };
+    void report() { if (!on) return; const char* nm[N] = {"mates+kmers", "projection", "first20", "counts", "pileup+files", "device input", "device", "rank+PP file", "QC+calls", "-"};
+        for (int i = 0; i < N; i++) if (ns[i]) fprintf(stderr, "[typing-profile] %-14s %9.3f ms\n", nm[i], ns[i] / 1e6); }
+};
+
 double chi2_1_pvalue(double statistic) { return 1 - (statistic <= 0 ? 0 : erf(sqrt(statistic / 2.0))); }   // boost::math::cdf(chi_squared(1), x) == erf(sqrt(x/2))
 
 } // namespace
@@ -302,6 +314,7 @@ double chi2_1_pvalue(double statistic) { return 1 - (statistic <= 0 ? 0 : erf(sq
 void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double is_sd, const std::string& out_dir, const std::string& g_dir,
                 TypingDevice& dev, const TypingOptions& opt, std::vector<LocusCall>& calls) {
     calls.clear();
+    PhaseClock clk; std::unique_ptr<PhaseClock::Scope> ph0(new PhaseClock::Scope(clk, 0));
     const size_t NP = in.n_pairs(); TY_REQUIRE(NP > 0, "rawPairedReads.size() > 0");
     std::vector<Mate> mates(2 * NP);
     for (size_t r = 0; r < 2 * NP; r++) {
@@ -319,6 +332,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         KmerSet::scan(mates[r].bases, (size_t)mates[r].len, [&](uint64_t k) { read_kmers.insert(k); }, []() {});
     }
 
+    ph0.reset();
     // out_dir empty: compute only (ranks other than 0 of a multi-GPU run); every stream then goes to /dev/null
     auto target = [&](const std::string& name) { return out_dir.empty() ? std::string("/dev/null") : out_dir + "/" + name; };
     if (!out_dir.empty()) mkdir(out_dir.c_str(), 0777);
@@ -365,6 +379,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         std::ostringstream hist, best, bestG;   // this locus' lines of histogram_matchesPerRead.txt / R1_bestguess.txt / R1_bestguess_G.txt
         call.locus = L.name; const int32_t C = L.C(), P = L.P(); call.C = C;
         // ---- exon observations per read pair
+        std::unique_ptr<PhaseClock::Scope> ph(new PhaseClock::Scope(clk, 1));
         std::vector<std::vector<ExonObs>> reads;
         for (size_t p = 0; p < NP; p++) {
             const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1];
@@ -375,6 +390,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         }
         const size_t R = reads.size(); call.R = (int32_t)R;
         // ---- "first 20" filter (HLATyper.cpp:1551-1640)
+        ph.reset(new PhaseClock::Scope(clk, 2));
         std::set<std::string> ignored_reads; std::map<uint32_t, std::set<std::string>> ignored_alleles;
         {
             std::map<uint32_t, std::vector<std::string>> al; std::map<uint32_t, std::vector<double>> wq; std::map<uint32_t, std::vector<uint32_t>> rd; std::map<uint32_t, int> robust;
@@ -399,6 +415,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             return ignored_reads.count(*e.self->name) == 0;
         };
         // ---- allele counts per position, by strand / by mate (HLATyper.cpp:1663-1875); the frequency filters are off in short-read mode
+        ph.reset(new PhaseClock::Scope(clk, 3));
         std::map<uint32_t, std::map<std::string, double>> min_strand_freq, read1_freq; std::map<uint32_t, std::map<std::string, int>> counts_high_cov;
         {
             struct Cnt { int n = 0, fwd = 0, rev = 0, first = 0; }; std::map<uint32_t, std::map<std::string, Cnt>> cnt;
@@ -407,6 +424,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
                 for (auto& a : pk.second) { if (tot >= high_cov) counts_high_cov[pk.first][a.first] = a.second.n; int t = a.second.fwd + a.second.rev; min_strand_freq[pk.first][a.first] = (double)std::min(a.second.fwd, a.second.rev) / (double)t; read1_freq[pk.first][a.first] = (double)a.second.first / (double)t; } }
         }
         // ---- pile-up (HLATyper.cpp:1877-2037)
+        ph.reset(new PhaseClock::Scope(clk, 4));
         std::map<int, std::map<int, std::vector<const ExonObs*>>> pile; std::set<std::string> utilized;
         for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; pile[L.col_exon[e.pos]][L.col_exonpos[e.pos]].push_back(&e); hist << L.name << "\t" << "base" << e.self->weighted_ok << "\n"; }
         {
@@ -428,6 +446,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         { std::ofstream rs(target("R1_readIDs_" + L.name + ".txt")); for (const std::string& id : utilized) rs << id << "\n"; }
 
         // ---- the two GPU stages: per-read x cluster log-likelihoods, allele-pair sums
+        ph.reset(new PhaseClock::Scope(clk, 5));
         LocusDeviceInput di; di.C = C; di.P = P; di.R = (int32_t)R; di.cluster_seq = &L.cluster_seq; di.rec_off.assign(1, 0); long long bases_used = 0;
         for (uint32_t r = 0; r < R; r++) {
             for (const ExonObs& e : reads[r]) { if (!used(e)) continue;
@@ -435,7 +454,9 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
                 di.rec_pos.push_back((int16_t)e.pos); di.rec_c0.push_back(gap ? (uint8_t)'_' : (uint8_t)e.genotype[0]); di.rec_q0.push_back(gap ? 0 : (uint8_t)e.qualities[0]); di.rec_glen.push_back((uint16_t)std::min<size_t>(e.genotype.size(), 65535)); bases_used++; }
             di.rec_off.push_back((int32_t)di.rec_pos.size());
         }
+        ph.reset(new PhaseClock::Scope(clk, 6));
         take_turn(li); try { dev.run_locus(di, opt.keep_read_ll, call.dev); } catch (...) { pass_turn(li); throw; } pass_turn(li);
+        ph.reset(new PhaseClock::Scope(clk, 7));
         const std::vector<double>& LLs = call.dev.pair_ll; const std::vector<double>& Mavg = call.dev.pair_mavg; const std::vector<double>& Mmin = call.dev.pair_mmin;
         const size_t NPAIR = (size_t)C * ((size_t)C + 1) / 2; TY_REQUIRE(LLs.size() == NPAIR && Mavg.size() == NPAIR && Mmin.size() == NPAIR, "pair arrays complete");
         std::vector<std::pair<uint32_t, uint32_t>> ids; ids.reserve(NPAIR); for (uint32_t c1 = 0; c1 < (uint32_t)C; c1++) for (uint32_t c2 = c1; c2 < (uint32_t)C; c2++) ids.push_back({c1, c2});
@@ -458,6 +479,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         const std::pair<double, int> b2 = first_max(tie_break);
         call.call1 = members((uint32_t)b1.second); call.call2 = members((uint32_t)b2.second); call.q1 = b1.first; call.q2 = p2.first;
         // ---- QC (HLATyper.cpp:2543-2759, 4258-4320)
+        ph.reset(new PhaseClock::Scope(clk, 8));
         int total_columns = 0; for (int l : L.exon_len) total_columns += l;
         const double locus_cov = (double)bases_used / (double)total_columns;
         std::vector<double> pos_cov; for (int32_t i = 0; i < P; i++) pos_cov.push_back((double)pile[L.col_exon[i]][L.col_exonpos[i]].size());
@@ -500,6 +522,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         }
         if (!opt.keep_read_ll) { call.dev.LL.clear(); call.dev.LL.shrink_to_fit(); call.dev.mism.clear(); call.dev.mism.shrink_to_fit(); }
         outs[li].hist = hist.str(); outs[li].best = best.str(); outs[li].bestG = bestG.str();
+        ph.reset();
     };
     {
         std::atomic<size_t> next(0);
@@ -519,6 +542,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         calls.push_back(std::move(outs[li].call));
     }
     best << std::flush; bestG << std::flush;
+    clk.report();
     { std::ofstream ps(target("R1_parameters.txt")); ps << "Loci = " << join_with(locus_names, ",") << "\n" << "veryConservativeReadLikelihoods = " << true << "\n"; }
 }
 
