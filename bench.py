@@ -130,14 +130,28 @@ def cpu_reference_run(args, prg_dir_small, n_pairs, threads):
     return n_pairs / out["seconds"], out["seconds"]
 
 
+def sample_dims(args):
+    """The reference arm's PRG: a slice of the bench PRG with the same generator parameters — the same gene-block density (one block per
+    levels/genes levels) and the same number of alleles per block — small enough for the reference's pointer graph to load in seconds."""
+    genes = max(1, int(round(args.genes * args.cpu_levels / float(args.levels))))
+    return args.cpu_levels, genes, args.alleles
+
+
 def small_prg(args, root):
     import harness as H
-    d = os.path.join(root, "prg_cpu_sample_l%d" % args.cpu_levels)
+    levels, genes, alleles = sample_dims(args)
+    d = os.path.join(root, "prg_cpu_sample_l%d_g%d_a%d" % (levels, genes, alleles))
     if not os.path.exists(os.path.join(d, ".complete")):
         os.makedirs(d, exist_ok=True)
-        H.synth_prg(d, levels=args.cpu_levels, haps=args.haps, genes=min(args.genes, 4), alleles=min(args.alleles, 200), allele_contigs=4, seed=0xB200)
+        H.synth_prg(d, levels=levels, haps=args.haps, genes=genes, alleles=alleles, allele_contigs=4, seed=0xB200)
         open(os.path.join(d, ".complete"), "w").write("ok\n")
     return d
+
+
+def sample_text(args):
+    levels, genes, alleles = sample_dims(args)
+    return ("%d pairs 2x%d per step, same read generator, on a %d-level slice of the PRG generator's output with identical parameters (%d haplotypes, %d gene block(s) x %d alleles: "
+            "the bench PRG's block density and allele count)" % (args.cpu_pairs, args.read_len, levels, args.haps, genes, alleles))
 
 
 def ncu_traffic_bytes(kernel_file):
@@ -204,10 +218,10 @@ def stage_typing(args, root, H):
     """§8 a20-a28 on this box: alignment session with columns kept -> gene filter/extract -> hlala_typer_infer (per-read x cluster kernel,
     allele-pair kernel) on a PRG with 17 gene blocks x 200 alleles and reads concentrated in the gene blocks."""
     import tempfile
-    d = os.path.join(root, "prg_typing_stage")
+    d = os.path.join(root, "prg_typing_stage_a%d" % args.alleles)
     if not os.path.exists(os.path.join(d, ".complete")):
         os.makedirs(d, exist_ok=True)
-        H.synth_prg(d, levels=200000, haps=4, genes=17, alleles=200, seed=11)
+        H.synth_prg(d, levels=200000, haps=4, genes=17, alleles=args.alleles, seed=11)
         open(os.path.join(d, ".complete"), "w").write("ok\n")
     b = H.synth_reads(d, os.path.join(d, "seeds_stage.bin"), pairs=60000, len=args.read_len, seed=11, gene_frac=0.8)
     P = H.Product(d); P.to_gpu(int(os.environ.get("LOCAL_RANK", "0")))
@@ -218,11 +232,25 @@ def stage_typing(args, root, H):
     t = time.time(); T.infer([blob], args.is_mean, args.is_sd, out_dir, device=int(os.environ.get("LOCAL_RANK", "0")), keep_read_ll=False); t_infer = time.time() - t
     tm = T.timing()
     P.lib.hlala_session_free(sess)
-    res = dict(workload="60000 pairs 2x%d (80%% inside gene blocks), PRG of 200000 levels / 17 gene blocks x 200 alleles" % args.read_len, pairs_selected=n_sel,
+    res = dict(workload="60000 pairs 2x%d (80%% inside gene blocks), PRG of 200000 levels / 17 gene blocks x %d alleles (the bench PRG's allele count)" % (args.read_len, args.alleles), pairs_selected=n_sel,
                extract_s=t_extract, infer_call_s=t_infer, read_x_cluster_kernel_ms=tm["ms"][0], allele_pair_kernel_ms=tm["ms"][1], kernel_launches=tm["launches"],
                read_cluster_observation_steps=tm["work"][0], log_avg_evaluations=tm["work"][1],
                log_avg_evaluations_per_s=(tm["work"][1] / (tm["ms"][1] / 1e3)) if tm["ms"][1] > 0 else None, files_written=len(os.listdir(os.path.join(out_dir, "hla"))) if os.path.isdir(os.path.join(out_dir, "hla")) else 0)
     T.close(); P.close()
+    # the allele-pair kernels alone at the cluster count of the real class-I loci (SURVEY config C2: C = 4000), R = 10000 reads
+    try:
+        rng = np.random.default_rng(1); Cn, R = 4000, 10000
+        ll = np.ascontiguousarray(-rng.gamma(2.0, 15.0, size=(Cn, R))); mm = rng.integers(0, 6, size=(Cn, R)).astype(np.int32); npair = Cn * (Cn + 1) // 2
+        probe = {}
+        lib = C.CDLL(H.LIB_PRODUCT); lib.hlala_typing_pair_probe.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        for termwise in (0, 1):
+            pl = np.zeros(npair); ms = C.c_double(0)
+            rc = lib.hlala_typing_pair_probe(int(os.environ.get("LOCAL_RANK", "0")), Cn, R, H.p(ll), H.p(mm), termwise, H.p(pl), None, None, C.byref(ms))
+            probe["termwise" if termwise else "max_shifted"] = {"kernel_ms": ms.value, "log_avg_terms_per_s": npair * R / (ms.value / 1e3) if rc == 0 and ms.value > 0 else None, "rc": rc, "checksum": float(pl.sum())}
+        probe["relative_difference_of_sums"] = abs(probe["max_shifted"]["checksum"] - probe["termwise"]["checksum"]) / abs(probe["termwise"]["checksum"])
+        res["allele_pair_kernel_at_C4000_R10000"] = probe
+    except Exception as e:
+        res["allele_pair_kernel_at_C4000_R10000"] = {"error": str(e)[:200]}
     return res
 
 
@@ -242,7 +270,7 @@ def main():
     ap.add_argument("--is-sd", type=float, default=10.0)
     ap.add_argument("--max-columns", type=int, default=640)
     ap.add_argument("--cpu-pairs", type=int, default=6000)
-    ap.add_argument("--cpu-levels", type=int, default=250000)
+    ap.add_argument("--cpu-levels", type=int, default=294118, help="levels of the reference arm's PRG slice (default: levels / genes = one gene block, the bench PRG's density)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--stages", type=int, default=1, help="also time the k-mer seeding and typing stages (rank 0, N=1 only)")
     args = ap.parse_args()
@@ -256,7 +284,8 @@ def main():
     config = {"workload": "%d synthetic 2x%dbp pairs per GPU, bwa-style seed chains (15%% soft-clipped), synthetic PRG of %d levels / %d haplotypes / %d gene blocks x %d alleles; "
                           "full seed projection + graph-DP extension + pair likelihood/mapQ + per-level coverage" % (args.pairs, args.read_len, args.levels, args.haps, args.genes, args.alleles),
               "pairs_per_gpu": args.pairs, "read_len": args.read_len, "levels": args.levels, "sharding": "pairs sharded across ranks (weak scaling)",
-              "cache": "batch (>1 GB) and per-wave scratch exceed the 126 MB L2, so every step streams its inputs from HBM"}
+              "cache": "batch (>1 GB) and per-wave scratch exceed the 126 MB L2, so every step streams its inputs from HBM",
+              "reference_arm_sample": "the reference's CPU implementation cannot load or finish the full workload in minutes; `--impl reference` and cpu_baseline run " + sample_text(args)}
 
     # ------------------------------------------------------------------ reference arm: the reference's own CPU implementation
     if args.impl == "reference":
@@ -275,7 +304,7 @@ def main():
                 vals.append((v, sec))
         tot_pairs = n * len(vals); tot_sec = sum(s for _, s in vals)
         value = tot_pairs / tot_sec
-        sample = "%d pairs 2x%d per step on a %d-level PRG built with the same generator parameters; reference TUs unmodified, outer OpenMP loop over pairs (%d threads)" % (n, args.read_len, args.cpu_levels, threads)
+        sample = sample_text(args) + "; reference TUs unmodified, outer OpenMP loop over pairs (%d threads)" % threads
         line = {"metric": "paired reads/sec aligned to the PRG (seed projection + extension + pair scoring)", "value": value, "unit": "pairs/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * tot_sec / max(len(vals), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
                 "config": config, "impl": "reference", "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "reference", "sample": sample},
@@ -350,7 +379,7 @@ def main():
     if rank == 0:
         sys.stderr.write("[bench] resident: %.1f ms/step, %.0f pairs/s; kernel ms/step: seed %.1f extend %.1f finish %.1f pair %.1f; launches %d; errors %d\n" % (
             ms_total / args.steps, value, kms[0] / args.steps, (kms[1] + kms[4] + kms[5]) / args.steps, kms[2] / args.steps, kms[3] / args.steps, launches, dig[3]))
-        sys.stderr.write("[bench] extension ms/step: warp-small %.1f warp-large %.1f scalar %.1f\n" % (kms[1] / args.steps, kms[4] / args.steps, kms[5] / args.steps))
+        sys.stderr.write("[bench] extension ms/step: lean %.1f warp tiers %.1f scalar %.1f\n" % (kms[1] / args.steps, kms[4] / args.steps, kms[5] / args.steps))
 
     # ---- end to end through the host-buffer C-ABI call (pinned host inputs, H2D + kernels + D2H inside the timed region)
     pinned = {k: torch.from_numpy(b[k]).pin_memory() for k in H.BATCH_KEYS}
@@ -409,20 +438,34 @@ def main():
             dist.destroy_process_group()
         return 0
     peak, peak_src = measured_peak()
-    names = ["k_chain_seed", "k_extend_group", "k_chain_finish", "k_pair", "k_extend_warp(tiny+small+large)", "k_extend(scalar)"]
+    names = ["k_chain_seed", "k_extend_lean", "k_chain_finish", "k_pair", "k_extend_warp(tiny+small+large)", "k_extend(scalar)"]
+    ab = (C.c_int64 * 3)(); aligned = None
+    try:
+        s2 = C.c_void_p(); P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(s2)))
+        P._chk(L.hlala_session_run(s2, C.c_double(args.is_mean), C.c_double(args.is_sd), C.c_uint64(0), C.c_void_p(stream.cuda_stream)))
+        torch.cuda.synchronize(); P._chk(L.hlala_session_aligned_bytes(s2, ab)); L.hlala_session_free(s2)
+        aligned = {"chains_aligned": int(ab[0]), "chains_in_batch": int(len(b["chain_contig"])), "chain_kernel_bytes_per_step": int(ab[1]), "whole_path_bytes_per_step": int(ab[2])}
+    except Exception as e:
+        aligned = {"error": str(e)[:200]}
     per_kernel = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kl[i] / args.steps} for i in range(6)}
     dom = max(range(6), key=lambda i: kms[i])
     # dominant kernel: the first tier of the extension DP. Algorithmic bytes of all extension tasks (it attempts every task) over the summed
     # CUDA-event durations of its launches; the launches of different waves overlap on several streams, so this is a per-launch average.
     dp_ach = dp_bytes_total / (kms[1] / 1000.0) / 1e9 if kms[1] > 0 and dp_bytes_total > 0 else None
     chain_ach = chain_bytes * args.steps / (kms[0] / 1000.0) / 1e9 if kms[0] > 0 else None
-    traffic = ncu_traffic_bytes("r01_ncu_k_extend_group.txt")
-    roofline = {"bound": "hbm", "kernel": "k_extend_group", "achieved": dp_ach, "peak": peak, "unit": "GB/s", "frac": (dp_ach / peak) if dp_ach else None, "traffic": traffic,
-                "traffic_source": "profiles/r01_ncu_k_extend_group.txt (ncu --set full, one launch = one wave of the same size as here)", "peak_source": peak_src,
+    traffic = ncu_traffic_bytes("r02_ncu_k_extend_lean.txt")
+    roofline = {"bound": "hbm", "kernel": "k_extend_lean", "achieved": dp_ach, "peak": peak, "unit": "GB/s", "frac": (dp_ach / peak) if dp_ach else None, "traffic": traffic,
+                "traffic_source": "profiles/r02_ncu_k_extend_lean.txt (ncu --set full of one launch over a 100 k-pair wave; the default run launches it once over the whole batch, 10x the tasks)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dp_bytes_total / max(kl[1], 1), "launch_ms_avg": kms[1] / max(kl[1], 1),
-                "note": "integer DP over a sparse cell set: bounded by dependent-load latency and issue slots (ncu: 16 % issue-active, long-scoreboard stalls), not by HBM bandwidth; the fraction is reported as measured",
-                "chain_kernel": {"kernel": "k_chain_seed", "achieved": chain_ach, "frac": (chain_ach / peak) if chain_ach else None, "algorithmic_bytes_per_step": chain_bytes},
-                "whole_path_algorithmic_bytes_per_step": total_bytes, "whole_path_achieved": total_bytes * args.steps / (ms_total / 1000.0) / 1e9,
+                "note": "integer DP over a sparse cell set, one thread per extension: bounded by SIMT divergence, dependent shared-memory accesses and issue slots (ncu: 7 of 32 lanes active, 22 % issue-active), not by HBM bandwidth; the fraction is reported as measured",
+                "chain_kernel": {"kernel": "k_chain_seed", "achieved_counting_all_chains": chain_ach, "frac_counting_all_chains": (chain_ach / peak) if chain_ach else None, "algorithmic_bytes_per_step_all_chains": chain_bytes,
+                                 "achieved": (aligned["chain_kernel_bytes_per_step"] * args.steps / (kms[0] / 1000.0) / 1e9) if aligned and "error" not in aligned and kms[0] > 0 else None,
+                                 "frac": (aligned["chain_kernel_bytes_per_step"] * args.steps / (kms[0] / 1000.0) / 1e9 / peak) if aligned and "error" not in aligned and kms[0] > 0 else None,
+                                 "note": "achieved / frac count only the chains the kernels read (k_prepare skips chains that the pair stage would discard as duplicates: 86 % of this workload's chains)"},
+                "aligned_chains": aligned,
+                "whole_path_algorithmic_bytes_per_step_all_chains": total_bytes, "whole_path_achieved_counting_all_chains": total_bytes * args.steps / (ms_total / 1000.0) / 1e9,
+                "whole_path_algorithmic_bytes_per_step": aligned["whole_path_bytes_per_step"] if aligned and "error" not in aligned else None,
+                "whole_path_achieved": (aligned["whole_path_bytes_per_step"] * args.steps / (ms_total / 1000.0) / 1e9) if aligned and "error" not in aligned else None,
                 "dominant_kernel_by_time": names[dom], "per_kernel": per_kernel,
                 "per_kernel_note": "durations of launches on different streams overlap (and slow each other down); their sum exceeds ms_per_step"}
     if serial and "kernel_ms" in serial:
@@ -441,8 +484,20 @@ def main():
         vN, sN = cpu_reference_run(args, d, args.cpu_pairs, threads)
         cpu = {"value": vN, "unit": "pairs/s", "cores": threads, "kind": "reference",
                "single_thread_value": v1,
-               "sample": "%d pairs 2x%d on a %d-level PRG built with the same generator parameters; unmodified reference TUs; the reference itself runs this loop on 1 thread (%.0f pairs/s), "
-                         "the value is the courtesy all-cores OpenMP loop over pairs" % (args.cpu_pairs, args.read_len, args.cpu_levels, v1)}
+               "sample": sample_text(args) + "; unmodified reference TUs; the reference itself runs this loop on 1 thread (%.0f pairs/s), the value is the courtesy all-cores OpenMP loop over pairs" % v1}
+        # the GPU path on EXACTLY the reference arm's sample (same PRG slice, same reads), end to end through the host-buffer call
+        try:
+            bs = make_reads(args, d, 0, args.cpu_pairs, tag="cpu")
+            Ps = H.Product(d); Ps.to_gpu(local_rank)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); Ps.pairs(bs, args.is_mean, args.is_sd, cap=args.max_columns); ts.append(time.perf_counter() - t0)
+            Ps.close()
+            gv = args.cpu_pairs / min(ts[1:])
+            cpu["same_workload"] = {"gpu_e2e_pairs_per_s": gv, "reference_pairs_per_s_all_cores": vN, "reference_pairs_per_s_1_thread": v1, "ratio_vs_all_cores": gv / vN, "ratio_vs_1_thread": gv / v1,
+                                    "note": "hlala_align_pairs on the reference arm's own sample (host buffers in, per-pair results out); the batch is far too small to fill the GPU, so this is a lower bound of the same-workload ratio"}
+        except Exception as e:
+            cpu["same_workload"] = {"error": str(e)[:200]}
     stages = None
     if args.stages and n_gpus == 1:
         stages = {}

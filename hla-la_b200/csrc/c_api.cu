@@ -325,6 +325,23 @@ struct Pipeline {
         // translation 4 + contig base 1 + graph window (edge_pack 4*1.5 + level offsets 8 + gap flag 1) + output (edge 4 + read char 1 + seed flag 1), 44 B scalars
         { int64_t rb = 0; for (int64_t r = 0; r < b.n_reads; r++) rb += (b.read_off[r + 1] - b.read_off[r]) * (int64_t)(b.chain_off[r + 1] - b.chain_off[r]);
           chain_kernel_bytes = 24ll * pb.n_chains + 4 * ncg + 2 * rb + cols * (4 + 1 + 6 + 8 + 1 + 6) + 44ll * pb.n_chains; }
+        // per input chain, for aligned_bytes(): columns, CIGAR operations, read length
+        cb_cols.assign((size_t)pb.n_chains, 0); cb_ops.assign((size_t)pb.n_chains, 0); cb_len.assign((size_t)pb.n_chains, 0);
+        for (int64_t r = 0; r < b.n_reads; r++) for (int32_t c = b.chain_off[r]; c < b.chain_off[r + 1]; c++) {
+            int32_t cc = 0; for (int32_t k = b.cigar_off[c]; k < b.cigar_off[c + 1]; k++) { int op = b.cigar[k] & 15; if (op == 0 || op == 1 || op == 2 || op == 7 || op == 8) cc += (int32_t)(b.cigar[k] >> 4); }
+            cb_cols[(size_t)c] = cc; cb_ops[(size_t)c] = b.cigar_off[c + 1] - b.cigar_off[c]; cb_len[(size_t)c] = (int32_t)(b.read_off[r + 1] - b.read_off[r]); }
+        algo_fixed = 2 * nb + 2 * nb * 12 / 2 + 40ll * (b.n_reads / 2) + 4 * nb;
+    }
+    std::vector<int32_t> cb_cols, cb_ops, cb_len; int64_t algo_fixed = 0;
+    // The same two figures counted over the chains the run ALIGNED (status 0) only: k_prepare marks chains the pair stage would discard as duplicates
+    // and chains on the other strand, and no kernel touches their CIGARs, columns or graph windows. out: {chains aligned, chain kernel bytes, whole path bytes}
+    void aligned_bytes(int64_t out[3]) {
+        std::vector<int32_t> st((size_t)std::max(pb.n_chains, 1)); cs.status.download(st.data(), (size_t)pb.n_chains, 0); CUDA_OK(cudaStreamSynchronize(0));
+        int64_t n = 0, ck = 0, chains_part = 0;
+        for (int32_t s = 0; s < pb.n_chains; s++) { if (st[(size_t)s] != CH_OK) continue; const size_t c = (size_t)pb.chain_order[(size_t)s]; n++;
+            ck += 24 + 4ll * cb_ops[c] + 2ll * cb_len[c] + (int64_t)cb_cols[c] * (4 + 1 + 6 + 8 + 1 + 6) + 44;
+            chains_part += 24 + 4ll * cb_ops[c] + (int64_t)cb_cols[c] * (4 + 7); }
+        out[0] = n; out[1] = ck; out[2] = algo_fixed + chains_part;
     }
     // defaults of everything the test hooks (environment variables read in prepare) can change; a workspace kept across calls starts from them
     void reset_config() { scratch_budget = 0; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
@@ -707,6 +724,10 @@ int hlala_session_timing(hlala_session_t* s, double ms[6], int launches[6]) {
 }
 int64_t hlala_session_chain_kernel_bytes(const hlala_session_t* s) { return s ? s->pl.chain_kernel_bytes : -1; }
 int64_t hlala_session_algorithmic_bytes(const hlala_session_t* s) { return s ? s->pl.algo_bytes : -1; }
+int hlala_session_aligned_bytes(hlala_session_t* s, int64_t out[3]) {
+    if (!s || !out) return fail(HLALA_E_ARG, "hlala_session_aligned_bytes: null argument");
+    return guarded([&]() { CUDA_OK(cudaSetDevice(s->pl.g->device)); if (s->pl.cb_cols.empty()) return fail(HLALA_E_ARG, "hlala_session_aligned_bytes: session created without byte accounting"); s->pl.aligned_bytes(out); return 0; });
+}
 int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out) {
     if (!s || !out) return fail(HLALA_E_ARG, "hlala_session_fetch: null argument");
     return guarded([&]() { CUDA_OK(cudaSetDevice(s->pl.g->device)); s->pl.fetch(out, 0); return 0; });
@@ -772,7 +793,12 @@ struct GpuTypingDevice : TypingDevice {
         CUDA_OK(launch_read_cluster_ll(d_ct.as<uint8_t>(), C, Cpad, r0, r1, max_rec, d_off.as<int32_t>(), d_pos.as<int16_t>(), d_c0.as<uint8_t>(), d_q0.as<uint8_t>(), d_glen.as<uint16_t>(), d_ll.as<double>(), d_mm.as<int32_t>(), st));
         CUDA_OK(cudaEventRecord(e1, st));
         double* pl = d_pair.as<double>();
-        CUDA_OK(launch_allele_pair_ll(d_ll.as<double>(), d_mm.as<int32_t>(), C, Cpad, r0, r1, pl, pl + npair, pl + 2 * npair, st));
+        if (getenv("HLALA_TYPING_TERMWISE")) CUDA_OK(launch_allele_pair_ll(d_ll.as<double>(), d_mm.as<int32_t>(), C, Cpad, r0, r1, pl, pl + npair, pl + 2 * npair, st));     // A/B hook: one exp + one log per (pair, read)
+        else {
+            DevBuf d_e, d_rm, d_cs, d_ms; d_e.alloc((size_t)std::max(R, 1) * Cpad * 8); d_rm.alloc((size_t)std::max(R, 1) * 8); d_cs.alloc((size_t)std::max(C, 1) * 8); d_ms.alloc(8);
+            CUDA_OK(launch_allele_pair_prod(d_ll.as<double>(), d_mm.as<int32_t>(), C, Cpad, r0, r1, d_e.as<double>(), d_rm.as<double>(), d_cs.as<double>(), d_ms.as<double>(), pl, pl + npair, pl + 2 * npair, st));
+            CUDA_OK(cudaStreamSynchronize(st));     // the scratch buffers above are freed at the end of this scope
+        }
         CUDA_OK(cudaEventRecord(e2, st));
         if (world > 1) {
             if (!allreduce) throw std::runtime_error("hlala_typer_infer: world > 1 needs an all-reduce callback");
@@ -895,6 +921,33 @@ int hlala_typer_result_call(const hlala_typer_t* t, int l, const char** a1, cons
     const LocusCall& c = t->calls[(size_t)l];
     if (a1) *a1 = c.call1.c_str(); if (a2) *a2 = c.call2.c_str(); if (q1) *q1 = c.q1; if (q2) *q2 = c.q2; return 0;
 }
+int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll /* [C*R], index c*R + r */, const int32_t* mism /* [C*R] */, int termwise,
+                            double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms) {
+    if (C <= 0 || R < 0 || !ll || !mism || !pair_ll) return fail(HLALA_E_ARG, "hlala_typing_pair_probe: bad argument");
+    return guarded([&]() {
+        int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(HLALA_E_CUDA, "no CUDA device available: the typing kernels have no CPU fallback");
+        CUDA_OK(cudaSetDevice(device));
+        TypingScoreTables t = make_typing_tables(); CUDA_OK(upload_typing_tables(t));
+        const int32_t Cpad = (C + 31) / 32 * 32; const size_t npair = (size_t)C * ((size_t)C + 1) / 2;
+        std::vector<double> llt((size_t)std::max(R, 1) * Cpad, 0.0); std::vector<int32_t> mmt((size_t)std::max(R, 1) * Cpad, 0);
+        for (int32_t c = 0; c < C; c++) for (int32_t r = 0; r < R; r++) { llt[(size_t)r * Cpad + c] = ll[(size_t)c * R + r]; mmt[(size_t)r * Cpad + c] = mism[(size_t)c * R + r]; }
+        cudaStream_t st = 0; DevBuf d_ll, d_mm, d_pair, d_e, d_rm, d_cs, d_ms;
+        d_ll.upload(llt, st); d_mm.upload(mmt, st); d_pair.alloc(3 * npair * 8); d_e.alloc(llt.size() * 8); d_rm.alloc((size_t)std::max(R, 1) * 8); d_cs.alloc((size_t)C * 8); d_ms.alloc(8);
+        double* pl = d_pair.as<double>(); cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+        for (int rep = 0; rep < 2; rep++) {     // the second run is the timed one
+            CUDA_OK(cudaEventRecord(e0, st));
+            if (termwise) CUDA_OK(launch_allele_pair_ll(d_ll.as<double>(), d_mm.as<int32_t>(), C, Cpad, 0, R, pl, pl + npair, pl + 2 * npair, st));
+            else CUDA_OK(launch_allele_pair_prod(d_ll.as<double>(), d_mm.as<int32_t>(), C, Cpad, 0, R, d_e.as<double>(), d_rm.as<double>(), d_cs.as<double>(), d_ms.as<double>(), pl, pl + npair, pl + 2 * npair, st));
+            CUDA_OK(cudaEventRecord(e1, st)); CUDA_OK(cudaStreamSynchronize(st));
+        }
+        float f = 0; CUDA_OK(cudaEventElapsedTime(&f, e0, e1)); if (kernel_ms) *kernel_ms = f; cudaEventDestroy(e0); cudaEventDestroy(e1);
+        CUDA_OK(cudaMemcpy(pair_ll, pl, npair * 8, cudaMemcpyDeviceToHost));
+        if (pair_mavg) CUDA_OK(cudaMemcpy(pair_mavg, pl + npair, npair * 8, cudaMemcpyDeviceToHost));
+        if (pair_mmin) CUDA_OK(cudaMemcpy(pair_mmin, pl + 2 * npair, npair * 8, cudaMemcpyDeviceToHost));
+        return 0;
+    });
+}
+
 int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], double work[2]) {
     if (!t) return fail(HLALA_E_ARG, "null typer");
     for (int k = 0; k < 2; k++) { if (ms) ms[k] = t->ms[k]; if (launches) launches[k] = t->launches[k]; if (work) work[k] = t->work[k]; }

@@ -33,5 +33,8 @@ cudaError_t launch_read_cluster_ll(const uint8_t* clusterT, int32_t C, int32_t C
                                    const uint8_t* rec_c0, const uint8_t* rec_q0, const uint16_t* rec_glen, double* LLt, int32_t* mmT, cudaStream_t st);
 // a26: for every cluster pair c1 <= c2 (reference loop order), sums over reads r in [r0, r1) in ascending r
 cudaError_t launch_allele_pair_ll(const double* LLt, const int32_t* mmT, int32_t C, int32_t Cpad, int32_t r0, int32_t r1, double* pair_ll, double* pair_mavg, double* pair_mmin, cudaStream_t st);
+// the same sums, max-shifted (one exp per (cluster, read)); Et [R * Cpad], rowmax [R], colsum [C], msum [1] are scratch
+cudaError_t launch_allele_pair_prod(const double* LLt, const int32_t* mmT, int32_t C, int32_t Cpad, int32_t r0, int32_t r1, double* Et, double* rowmax, double* colsum, double* msum,
+                                    double* pair_ll, double* pair_mavg, double* pair_mmin, cudaStream_t st);
 
 } // namespace hlala

@@ -5,6 +5,7 @@
 #include "hla_typing.h"
 
 #include <algorithm>
+#include <array>
 #include <exception>
 #include <memory>
 #include <thread>
@@ -21,6 +22,7 @@
 #include <sys/stat.h>
 #include <unordered_set>
 #include <chrono>
+#include <charconv>
 
 namespace hlala {
 
@@ -40,7 +42,10 @@ std::string join_with(const std::vector<std::string>& v, const char* d) { std::s
 void chomp(std::string& s) { while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); }
 // default ostream formatting == Utilities::ItoStr / DtoStr; spelled with snprintf / to_string because constructing a stream per number dominated
 // the host time of the typing stage ("%g" is what operator<<(double) prints at the default precision of 6)
-template <class T> std::string str(T v) { if constexpr (std::is_floating_point<T>::value) { char b[40]; snprintf(b, sizeof b, "%g", (double)v); return b; } else if constexpr (std::is_integral<T>::value) return std::to_string(v); else { std::ostringstream o; o << v; return o.str(); } }
+// std::to_chars(general, 6) is specified to produce what printf("%.6g") produces
+template <class T> std::string str(T v) { if constexpr (std::is_floating_point<T>::value) { char b[48]; auto r = std::to_chars(b, b + sizeof b, (double)v, std::chars_format::general, 6); return std::string(b, r.ptr); } else if constexpr (std::is_integral<T>::value) return std::to_string(v); else { std::ostringstream o; o << v; return o.str(); } }
+inline void put_num(std::string& o, double v) { char b[48]; auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, 6); o.append(b, r.ptr); }
+inline void put_num(std::string& o, long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); o.append(b, r.ptr); }
 
 std::vector<std::string> read_lines(const std::string& path, bool keep_trailing_empty) {
     std::ifstream f(path); if (!f.is_open()) throw std::runtime_error("Cannot open file " + path);
@@ -192,6 +197,10 @@ struct Mate {     // one read's chosen alignment
     int n = 0; const int32_t* level = nullptr; const uint8_t* g = nullptr; const uint8_t* s = nullptr; const uint8_t* mq = nullptr;
     int len = 0; const uint8_t* bases = nullptr; const uint8_t* quals = nullptr; bool reverse = false; double mapQ = 0;
     int first_level = -1, last_level = -1, nongap_cols = 0; double weighted_ok = 0, fraction_ok = 0; const std::string* name = nullptr;
+    // text of this read's observations in R1_pileup_<L>.txt / histogram_matchesPerRead.txt, formatted once (the same pieces repeat for every exon column)
+    std::string pile_mid;    // ") [pairsDistance <d> | alignmentLength <n> | "
+    std::string pile_tail;   // " | <mapQ> <mapQ> | <weighted self> <weighted mate> | <name> <mate name>]"
+    std::string hist_base;   // "base<weighted>\n"
 };
 
 void mate_stats(Mate& m) {
@@ -221,7 +230,7 @@ int level_distance(const Mate& a, const Mate& b) { return a.first_level < b.firs
 
 struct ExonObs {    // hla::oneExonPosition (hla/oneExonPosition.h:15-46), fields that are read anywhere in short-read mode
     uint32_t pos = 0; int32_t level = -1; std::string genotype, qualities; const Mate* self = nullptr; const Mate* mate = nullptr;
-    double dist = 0, mapq_pos = 0;
+    double dist = 0, mapq_pos = 0; unsigned char mq_char = 0;    // mq_char: the per-column quality character mapq_pos was derived from
 };
 
 // oneReadAlignment_2_exonPositions_paired (HLATyper.cpp:3192-3565)
@@ -239,7 +248,7 @@ void project_read(const Mate& A, const Mate& M, const TypingLocus& L, std::vecto
             if (!all.empty()) { ExonObs& b = all.back(); if (b.genotype == "_") { TY_REQUIRE(b.qualities.empty(), "gap has no quality"); b.genotype.clear(); } b.genotype.push_back((char)A.s[c]); b.qualities.push_back((char)A.quals[idx]); }
             continue;
         }
-        ExonObs e; e.level = A.level[c]; e.self = &A; e.mate = &M; e.dist = dist; e.mapq_pos = pcorrect_of(A.mq[c]);
+        ExonObs e; e.level = A.level[c]; e.self = &A; e.mate = &M; e.dist = dist; e.mapq_pos = pcorrect_of(A.mq[c]); e.mq_char = A.mq[c];
         if (A.s[c] != '_') { idx++; TY_REQUIRE(idx < A.len, "read index inside the read"); e.genotype.assign(1, (char)A.s[c]); e.qualities.assign(1, (char)A.quals[idx]); }
         else e.genotype = "_";
         all.push_back(std::move(e));
@@ -365,6 +374,18 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     for (size_t p = 0; p < NP; p++) { const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1]; TY_REQUIRE(a.mapQ >= 0 && a.mapQ <= 1, "mapQ in [0,1]");
         gate[p] = strands_ok(a, b) && fabs(level_distance(a, b) - is_mean) <= 5 * is_sd && a.mapQ >= min_mapq && a.weighted_ok >= min_weighted && b.weighted_ok >= min_weighted; }
 
+    std::vector<std::array<std::string, 3>> hist_pair(NP);     // the three lines a gated pair contributes to every locus' histogram (without the locus name)
+    std::string mapq_pos_str[256], qual_int_str[256];
+    for (int q = 0; q < 256; q++) { qual_int_str[q] = str((int)(char)q); if (q == 0 || q >= 33) mapq_pos_str[q] = str(pcorrect_of((unsigned char)q)); }
+    for (size_t p = 0; p < NP; p++) {
+        Mate& a = mates[2 * p]; Mate& b = mates[2 * p + 1];
+        for (int m = 0; m < 2; m++) { Mate& x = m ? b : a; const Mate& y = m ? a : b;
+            x.hist_base = "base" + str(x.weighted_ok) + "\n";
+            x.pile_mid = ") [pairsDistance " + str((double)level_distance(x, y)) + " | alignmentLength " + str(x.nongap_cols) + " | ";
+            x.pile_tail = " | " + str(x.mapQ) + " " + str(x.mapQ) + " | " + str(x.weighted_ok) + " " + str(y.weighted_ok) + " | " + *x.name + " " + *y.name + "]"; }
+        if (gate[p]) hist_pair[p] = {"\tread" + str(a.weighted_ok) + "\n", "\tread" + str(b.weighted_ok) + "\n", "\treadPair" + str((a.weighted_ok + b.weighted_ok) / 2.0) + "\n"};
+    }
+
     // The loci are independent up to the order of their lines in the shared files and the order of the device stage (with several ranks
     // the per-locus all-reduce must be issued in the same order everywhere): host work of different loci runs on a thread pool, the device
     // stage is entered in locus order, and the shared files are assembled in locus order afterwards.
@@ -376,7 +397,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     auto pass_turn = [&](size_t li) { { std::lock_guard<std::mutex> lk(dev_mu); if (dev_turn == li) dev_turn = li + 1; } dev_cv.notify_all(); };
     auto process = [&](size_t li) {
         TypingLocus& L = T.loci[li]; LocusCall& call = outs[li].call;
-        std::ostringstream hist, best, bestG;   // this locus' lines of histogram_matchesPerRead.txt / R1_bestguess.txt / R1_bestguess_G.txt
+        std::string hist; std::ostringstream best, bestG;   // this locus' lines of histogram_matchesPerRead.txt / R1_bestguess.txt / R1_bestguess_G.txt
         call.locus = L.name; const int32_t C = L.C(), P = L.P(); call.C = C;
         // ---- exon observations per read pair
         std::unique_ptr<PhaseClock::Scope> ph(new PhaseClock::Scope(clk, 1));
@@ -386,7 +407,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             std::vector<ExonObs> obs; project_read(a, b, L, obs); project_read(b, a, L, obs);    // both are validated even if the pair is gated out
             if (!gate[p]) continue;
             if (!obs.empty()) reads.push_back(one_per_level(obs));
-            hist << L.name << "\t" << "read" << a.weighted_ok << "\n" << L.name << "\t" << "read" << b.weighted_ok << "\n" << L.name << "\t" << "readPair" << (a.weighted_ok + b.weighted_ok) / 2.0 << "\n";
+            for (const std::string& piece : hist_pair[p]) { hist += L.name; hist += piece; }
         }
         const size_t R = reads.size(); call.R = (int32_t)R;
         // ---- "first 20" filter (HLATyper.cpp:1551-1640)
@@ -426,22 +447,33 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         // ---- pile-up (HLATyper.cpp:1877-2037)
         ph.reset(new PhaseClock::Scope(clk, 4));
         std::map<int, std::map<int, std::vector<const ExonObs*>>> pile; std::set<std::string> utilized;
-        for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; pile[L.col_exon[e.pos]][L.col_exonpos[e.pos]].push_back(&e); hist << L.name << "\t" << "base" << e.self->weighted_ok << "\n"; }
+        for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; pile[L.col_exon[e.pos]][L.col_exonpos[e.pos]].push_back(&e); hist += L.name; hist += '\t'; hist += e.self->hist_base; }
         {
-            std::ofstream ps(target("R1_pileup_" + L.name + ".txt"));
+            // every observation is "<genotype> (<qualities>) [pairsDistance d | alignmentLength n | mapQ_position | mapQ mapQ | w w | name name]"; all but
+            // the genotype, the qualities and the per-column mapQ are per-read text prepared once (Mate::pile_mid / pile_tail)
+            std::string text; text.reserve((size_t)1 << 22);
+            std::unordered_set<const Mate*> utilized_mates;
             for (auto& ex : pile) { const int exon = ex.first, len = L.exon_len.at((size_t)exon);
                 for (int ep = 0; ep < len; ep++) {
                     auto it = ex.second.find(ep);
-                    if (it == ex.second.end()) { ps << exon << "\t" << ep << "\t" << 0 << "\n"; continue; }
-                    const std::vector<const ExonObs*>& pu = it->second; std::vector<std::string> parts; std::map<std::string, std::vector<int>> per_allele; uint32_t this_pos = pu[0]->pos;
-                    for (const ExonObs* e : pu) { std::vector<std::string> qs; for (char q : e->qualities) qs.push_back(str((int)q)); TY_REQUIRE(e->pos == this_pos, "pile-up column holds one exon position");
-                        parts.push_back(e->genotype + " (" + join_with(qs, ", ") + ") [pairsDistance " + str(e->dist) + " | alignmentLength " + str(e->self->nongap_cols) + " | " + str(e->mapq_pos) + " | " + str(e->self->mapQ) + " " + str(e->self->mapQ) + " | " +
-                                        str(e->self->weighted_ok) + " " + str(e->mate->weighted_ok) + " | " + *e->self->name + " " + *e->mate->name + "]");
-                        utilized.insert(*e->self->name); per_allele[e->genotype].push_back(e->self->nongap_cols); }
-                    std::string summary;
-                    for (auto& a : per_allele) { long long tot = 0; for (int l : a.second) tot += l; summary += a.first + "x" + str(a.second.size()) + "[" + str((double)tot / (double)a.second.size()) + ";" + str(min_strand_freq.at(this_pos).at(a.first)) + ";" + str(read1_freq.at(this_pos).at(a.first)) + "]"; }
-                    ps << exon << "\t" << ep << "\t" << pu.size() << "\t" << join_with(parts, ", ") << "\t" << summary << "\n";
+                    put_num(text, (long long)exon); text += '\t'; put_num(text, (long long)ep); text += '\t';
+                    if (it == ex.second.end()) { text += "0\n"; continue; }
+                    const std::vector<const ExonObs*>& pu = it->second; std::map<std::string, std::pair<long long, long long>> per_allele; uint32_t this_pos = pu[0]->pos;
+                    put_num(text, (long long)pu.size()); text += '\t';
+                    bool first_part = true;
+                    for (const ExonObs* e : pu) { TY_REQUIRE(e->pos == this_pos, "pile-up column holds one exon position");
+                        if (!first_part) text += ", "; first_part = false;
+                        text += e->genotype; text += " (";
+                        for (size_t qi = 0; qi < e->qualities.size(); qi++) { if (qi) text += ", "; text += qual_int_str[(unsigned char)e->qualities[qi]]; }
+                        text += e->self->pile_mid; text += mapq_pos_str[e->mq_char]; text += e->self->pile_tail;
+                        utilized_mates.insert(e->self); auto& pa = per_allele[e->genotype]; pa.first += e->self->nongap_cols; pa.second++; }
+                    text += '\t';
+                    for (auto& a : per_allele) { text += a.first; text += 'x'; put_num(text, a.second.second); text += '['; put_num(text, (double)a.second.first / (double)a.second.second); text += ';';
+                        put_num(text, min_strand_freq.at(this_pos).at(a.first)); text += ';'; put_num(text, read1_freq.at(this_pos).at(a.first)); text += ']'; }
+                    text += '\n';
                 } }
+            for (const Mate* m : utilized_mates) utilized.insert(*m->name);
+            std::ofstream ps(target("R1_pileup_" + L.name + ".txt")); ps.write(text.data(), (std::streamsize)text.size());
         }
         { std::ofstream rs(target("R1_readIDs_" + L.name + ".txt")); for (const std::string& id : utilized) rs << id << "\n"; }
 
@@ -462,15 +494,22 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         std::vector<std::pair<uint32_t, uint32_t>> ids; ids.reserve(NPAIR); for (uint32_t c1 = 0; c1 < (uint32_t)C; c1++) for (uint32_t c2 = c1; c2 < (uint32_t)C; c2++) ids.push_back({c1, c2});
         // ---- normalise, rank, call (HLATyper.cpp:2366-2538)
         std::vector<size_t> order(NPAIR); for (size_t i = 0; i < NPAIR; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { if (LLs.at(a) == LLs.at(b)) return Mavg.at(b) < Mavg.at(a); return LLs.at(a) < LLs.at(b); }); std::reverse(order.begin(), order.end());
+        { const double* ll = LLs.data(); const double* ma = Mavg.data();      // same comparator, same std::sort: the order of exact ties is the reference's
+          std::sort(order.begin(), order.end(), [ll, ma](unsigned a, unsigned b) { if (ll[a] == ll[b]) return ma[b] < ma[a]; return ll[a] < ll[b]; }); std::reverse(order.begin(), order.end()); }
         size_t imax = 0; for (size_t i = 1; i < NPAIR; i++) if (LLs[i] > LLs[imax]) imax = i; const double ll_max = LLs[imax];
         double psum = 0; for (double v : LLs) psum += exp(v - ll_max);
         std::vector<double> Pn(NPAIR); for (size_t i = 0; i < NPAIR; i++) { if (psum > 0) { Pn[i] = exp(LLs[i] - ll_max) / psum; TY_REQUIRE(Pn[i] >= 0 && Pn[i] <= 1, "P_normalized in [0,1]"); } else Pn[i] = 1.0 / (double)NPAIR; }
-        auto members = [&](uint32_t c) { return join_with(L.cluster_members[c], ";"); };
+        std::vector<std::string> member_str((size_t)C); for (int32_t c = 0; c < C; c++) member_str[(size_t)c] = join_with(L.cluster_members[(size_t)c], ";");
+        auto members = [&](uint32_t c) -> const std::string& { return member_str[c]; };
         std::map<int, double> marginal;
         { std::ofstream ap(target("R1_PP_" + L.name + "_pairs.txt")); ap << "ClusterID\tP\tLL\tMismatches_avg\n";
-          for (size_t k = 0; k < NPAIR; k++) { const size_t i = order[k]; ap << members(ids[i].first) << "/" << members(ids[i].second) << "\t" << Pn[i] << "\t" << LLs[i] << "\t" << Mavg[i] << "\n";
-              marginal[(int)ids[i].first] += Pn[i]; if (ids[i].second != ids[i].first) marginal[(int)ids[i].second] += Pn[i]; } }
+          std::vector<double> marg((size_t)C, 0.0); std::string text; text.reserve((size_t)1 << 22);
+          for (size_t k = 0; k < NPAIR; k++) { const size_t i = order[k];
+              text += members(ids[i].first); text += '/'; text += members(ids[i].second); text += '\t'; put_num(text, Pn[i]); text += '\t'; put_num(text, LLs[i]); text += '\t'; put_num(text, Mavg[i]); text += '\n';
+              if (text.size() > ((size_t)1 << 22) - 4096) { ap.write(text.data(), (std::streamsize)text.size()); text.clear(); }
+              marg[ids[i].first] += Pn[i]; if (ids[i].second != ids[i].first) marg[ids[i].second] += Pn[i]; }
+          ap.write(text.data(), (std::streamsize)text.size());
+          for (int32_t c = 0; c < C; c++) marginal[c] = marg[(size_t)c]; }      // every cluster is part of a pair: the keys the reference's map holds
         auto first_max = [](const std::map<int, double>& m) { double mx = 0; int at = 0; bool first = true; for (auto& kv : m) if (first || kv.second > mx) { mx = kv.second; at = kv.first; first = false; } return std::make_pair(mx, at); };   // Utilities::findIntMapMaxP_nonCritical
         const std::pair<double, int> b1 = first_max(marginal);
         std::map<int, double> partner_p, partner_mm;
@@ -521,7 +560,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             row(bestG, 1, g1, b1.first); bestG << "\t" << p1 << "\n"; row(bestG, 2, g2, p2.first); bestG << "\t" << p2g << "\n" << std::flush;
         }
         if (!opt.keep_read_ll) { call.dev.LL.clear(); call.dev.LL.shrink_to_fit(); call.dev.mism.clear(); call.dev.mism.shrink_to_fit(); }
-        outs[li].hist = hist.str(); outs[li].best = best.str(); outs[li].bestG = bestG.str();
+        outs[li].hist = std::move(hist); outs[li].best = best.str(); outs[li].bestG = bestG.str();
         ph.reset();
     };
     {

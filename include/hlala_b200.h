@@ -143,6 +143,10 @@ int64_t hlala_session_dp_kernel_bytes(hlala_session_t* s);
 int64_t hlala_session_chain_kernel_bytes(const hlala_session_t* s);
 /* Algorithmic HBM bytes of one run (SURVEY.md §8d formula evaluated on this batch). */
 int64_t hlala_session_algorithmic_bytes(const hlala_session_t* s);
+/* The two figures above counted over the chains the last run aligned only (chains skipped as duplicates of a better chain of the
+ * same read, processBAM.cpp:3234, or for their strand, :3216, are never read by a kernel): out = {chains aligned, chain-kernel bytes,
+ * whole-path bytes}. The reference projects every chain and discards the duplicates afterwards; the skip does not change any output. */
+int hlala_session_aligned_bytes(hlala_session_t* s, int64_t out[3]);
 /* Copy per-pair results of the last run to host buffers (any pointer may be NULL). */
 int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out);
 /* Small digest of the last run for checks at sizes where fetching everything is pointless:
@@ -191,6 +195,13 @@ int hlala_typer_result_call(const hlala_typer_t* t, int locus, const char** alle
 /* Device time of the last hlala_typer_infer: ms[0] per-read x cluster kernel, ms[1] allele-pair kernel (CUDA events); launches of each;
  * work[0] = sum over loci of C*R*observations (select+add steps), work[1] = sum over loci of C(C+1)/2 * R (logAvg evaluations). */
 int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], double work[2]);
+
+/* The allele-pair stage alone on caller-supplied per-read x cluster values (HLATyper.cpp:2280-2364: sum_r logAvg(LL[c1][r], LL[c2][r]),
+ * average and minimum mismatch sums for all c1 <= c2 in loop order): measurement and parity hook for cluster counts a test PRG does
+ * not reach (C = 4000). termwise = 1 runs the kernel with one exp + one log per (pair, read), 0 the max-shifted product kernel that
+ * hlala_typer_infer uses. ll / mism: [C*R], index c*R + r; outputs [C(C+1)/2]; kernel_ms: CUDA-event time of the second of two runs. */
+int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll, const int32_t* mism, int termwise,
+                            double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * k-mer seeding. Reference seam B5 of SURVEY.md §8b (no live caller in the reference: HLA-LA.cpp:230,1439 are commented out):

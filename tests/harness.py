@@ -66,7 +66,12 @@ def batch_args(b):
 class Ref:
     """oracle/_ref/libhlala_ref.so: the unmodified reference TUs behind ref_driver.cpp."""
 
-    def __init__(self, prg_dir, arena_bytes=1 << 30):
+    def __init__(self, prg_dir, arena_bytes=0):
+        if arena_bytes <= 0:   # the pointer graph takes ~30x the size of graph.txt (1000-allele gene blocks); the arena is malloc'ed and committed lazily
+            try:
+                arena_bytes = max(1 << 30, 48 * os.path.getsize(os.path.join(prg_dir, "PRG", "graph.txt")))
+            except OSError:
+                arena_bytes = 1 << 30
         self.lib = C.CDLL(LIB_REF)
         self.lib.hlala_ref_open.restype = C.c_void_p
         self.lib.hlala_ref_last_error.restype = C.c_char_p
@@ -358,9 +363,39 @@ def checker(prg_dir):
     return Oracle(prg_dir), "restatement (oracle/hlala_oracle.cpp)"
 
 
+def _ref_subprocess(prg_dir, b, is_mean, is_sd, cap, what):
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory(prefix="hlala_refw_") as t:
+        fin = os.path.join(t, "in.npz"); fout = os.path.join(t, "out.npz")
+        np.savez(fin, **{k: b[k] for k in BATCH_KEYS})
+        r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "ref_worker.py"), prg_dir, fin, fout, repr(float(is_mean)), repr(float(is_sd)), str(int(cap)), what],
+                           cwd=os.path.join(REPO, "tests"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference worker failed: " + r.stderr[-2000:])
+        out = dict(np.load(fout))
+    out["oracle"] = "compiled reference (oracle/_ref, own process)"
+    return out
+
+
 def oracle_pairs(prg_dir, b, is_mean, is_sd, cap=1024):
+    """pairs of `b` from the strongest checker: the compiled reference, in this process for the first PRG and in a process of its own
+    (tests/ref_worker.py) for every further one; the restatement only where oracle/_ref is not built"""
+    if have_ref() and _REF_CACHE and prg_dir not in _REF_CACHE:
+        return _ref_subprocess(prg_dir, b, is_mean, is_sd, cap, "pairs")
     o, kind = checker(prg_dir)
     r = quiet(o.pairs, b, is_mean, is_sd, cap)
+    r["oracle"] = kind
+    return r
+
+
+def oracle_chains(prg_dir, b, cap=1024):
+    """per-chain records of `b` from the strongest checker (see oracle_pairs)"""
+    if have_ref() and _REF_CACHE and prg_dir not in _REF_CACHE:
+        return _ref_subprocess(prg_dir, b, 0.0, 1.0, cap, "chains")
+    o, kind = checker(prg_dir)
+    r = quiet(o.chains, b, cap)
     r["oracle"] = kind
     return r
 

@@ -98,3 +98,31 @@ def test_typing_two_rank_split_gives_same_calls(dataset, tmp_path):
         assert np.allclose(tot[:n], single[i]["pair_ll"], rtol=1e-12, atol=1e-9)
         assert np.array_equal(tot[n:2 * n], single[i]["pair_mavg"]) and np.array_equal(tot[2 * n:], single[i]["pair_mmin"])
     T.close(); P.close(); T2.close(); P2.close()
+
+
+@pytest.mark.gpu
+def test_allele_pair_product_kernel_matches_termwise_and_numpy():
+    """the max-shifted allele-pair kernel (one exp per (cluster, read)) against the term-by-term kernel and a numpy statement of
+    HLATyper.cpp:2280-2364 / Utilities::logAvg, including reads on which some clusters are > 700 nats below the best one"""
+    import ctypes as C
+    lib = C.CDLL(H.LIB_PRODUCT); lib.hlala_last_error.restype = C.c_char_p
+    rng = np.random.default_rng(3)
+    Cn, R = 157, 211
+    ll = -rng.gamma(2.0, 20.0, size=(Cn, R)); ll[rng.random((Cn, R)) < 0.05] -= 1500.0; ll[:, 7] -= 900.0; ll[3, 7] += 900.0     # read 7: every cluster but one vanishes
+    ll[5] = ll[4]                                                                                                              # two identical clusters (d == 0 branch of logAvg)
+    mm = rng.integers(0, 9, size=(Cn, R)).astype(np.int32)
+    ll = np.ascontiguousarray(ll); npair = Cn * (Cn + 1) // 2
+    out = {}
+    for termwise in (1, 0):
+        pl = np.zeros(npair); pa = np.zeros(npair); pm = np.zeros(npair); ms = C.c_double(0)
+        rc = lib.hlala_typing_pair_probe(0, Cn, R, H.p(ll), H.p(mm), termwise, H.p(pl), H.p(pa), H.p(pm), C.byref(ms))
+        assert rc == 0, lib.hlala_last_error().decode()
+        out[termwise] = (pl, pa, pm)
+    iu = np.triu_indices(Cn)
+    want_ll = np.array([np.sum(np.log(0.5) + np.logaddexp(ll[a], ll[b])) for a, b in zip(*iu)])
+    want_avg = np.array([np.sum((mm[a] + mm[b]) / 2.0) for a, b in zip(*iu)]); want_min = np.array([np.sum(np.minimum(mm[a], mm[b])) for a, b in zip(*iu)], np.float64)
+    for termwise in (1, 0):
+        pl, pa, pm = out[termwise]
+        assert np.max(np.abs(pl - want_ll) / np.abs(want_ll)) < 1e-12, termwise
+        assert np.array_equal(pa, want_avg) and np.array_equal(pm, want_min), termwise
+    assert np.max(np.abs(out[0][0] - out[1][0]) / np.abs(out[1][0])) < 1e-12
