@@ -235,7 +235,7 @@ def stage_typing(args, root, H):
     res = dict(workload="60000 pairs 2x%d (80%% inside gene blocks), PRG of 200000 levels / 17 gene blocks x %d alleles (the bench PRG's allele count)" % (args.read_len, args.alleles), pairs_selected=n_sel,
                extract_s=t_extract, infer_call_s=t_infer, read_x_cluster_kernel_ms=tm["ms"][0], allele_pair_kernel_ms=tm["ms"][1], kernel_launches=tm["launches"],
                read_cluster_observation_steps=tm["work"][0], log_avg_evaluations=tm["work"][1],
-               log_avg_evaluations_per_s=(tm["work"][1] / (tm["ms"][1] / 1e3)) if tm["ms"][1] > 0 else None, files_written=len(os.listdir(os.path.join(out_dir, "hla"))) if os.path.isdir(os.path.join(out_dir, "hla")) else 0)
+               log_avg_evaluations_per_s=(tm["work"][1] / (tm["ms"][1] / 1e3)) if tm["ms"][1] > 0 else None, files_written=len(os.listdir(out_dir)), megabytes_written=sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)) / 1e6)
     T.close(); P.close()
     # the allele-pair kernels alone at the cluster count of the real class-I loci (SURVEY config C2: C = 4000), R = 10000 reads
     try:

@@ -500,18 +500,23 @@ cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t strea
     return cudaGetLastError();
 }
 
+template <class CFG, bool FROM_LIST> static cudaError_t launch_pair_tier(const PairParams& P, int n_sm, long long want_warps, cudaStream_t stream) {
+    const size_t smem = pair_slab_bytes<CFG>(P.maxcol) * K3_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(k_pair<CFG, FROM_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
+    int per_sm = 1; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair<CFG, FROM_LIST>, K3_WARPS * 32, smem);
+    if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
+    long long want = (want_warps + K3_WARPS - 1) / K3_WARPS;
+    int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm); if (grid < 1) grid = 1;
+    k_pair<CFG, FROM_LIST><<<grid, K3_WARPS * 32, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+// tier 0 over all pairs of the wave, then tier 1 (64 chains per read, 4096 combinations) over the pairs tier 0 queued; P.defer_count must be zero on entry
 cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream) {
     long long n_pairs = P.pair_end - P.pair_begin;
     if (n_pairs <= 0) return cudaSuccess;
-    size_t smem = k3_slab_bytes(P.maxcol) * K3_WARPS;
-    static size_t configured = 0;
-    if (smem > configured) { cudaError_t e = cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; configured = smem; }
-    int per_sm = 1; cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair, K3_WARPS * 32, smem);
-    if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
-    long long want = (n_pairs + K3_WARPS - 1) / K3_WARPS;
-    int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm); if (grid < 1) grid = 1;
-    k_pair<<<grid, K3_WARPS * 32, smem, stream>>>(P);
-    return cudaGetLastError();
+    cudaError_t e = launch_pair_tier<PairTier0, false>(P, n_sm, n_pairs, stream); if (e != cudaSuccess) return e;
+    if (!P.defer_list) return cudaSuccess;
+    return launch_pair_tier<PairTier1, true>(P, n_sm, (long long)n_sm * K3_WARPS, stream);     // a handful of pairs at most: one CTA per SM pops them
 }
 
 size_t dp_thread_scratch_bytes() { return dp_scratch_bytes(); }

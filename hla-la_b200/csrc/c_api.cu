@@ -163,6 +163,7 @@ struct ChainScratch {   // per-chain results of the whole batch
 // lanes, so the low-occupancy tail of one wave's extension cascade overlaps the next wave's chain kernel and first DP tier.
 struct Lane {
     DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count, dp_tasks, dp_task_count, dp_task_bin, dp_task_hist, dp_sorted;
+    DevBuf pair_defer, pair_defer_count;   // pairs queued for the large tier of the pair kernel
     DevBuf ln_rec, ln_ahead;   // thread-per-extension tier: 16-byte cell records and the ahead table of every resident thread
     DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch, gd_scratch; int32_t ext_cap = 0;
     DevBuf q_ctr, q_a, q_b;   // task queues of the extension cascade (counters, two ping-pong lists of deferred tasks)
@@ -175,6 +176,7 @@ struct Lane {
         c_edge.alloc(wc * maxcol * 4); c_schar.alloc(wc * maxcol); c_fromseed.alloc(wc * maxcol);
         pending_slots.alloc(wc * 4); pending_count.alloc(4); todo_slots.alloc(wc * 4); todo_count.alloc(4); defer_slots.alloc(wc * 4); defer_count.alloc(4);
         dp_scratch.alloc(dp_bytes); wd_scratch.alloc(wd_bytes); gd_scratch.alloc(gd_bytes); q_ctr.alloc(128);
+        pair_defer.alloc(wc * 2 + 64); pair_defer_count.alloc(4);     // at most one entry per pair; a pair has >= 2 chains
         dp_tasks.alloc(wc * 8); dp_task_count.alloc(4); dp_task_bin.alloc(wc * 2); dp_task_hist.alloc(1024); dp_sorted.alloc(wc * 8); ln_rec.alloc(ln_rec_bytes); ln_ahead.alloc(ln_ahead_bytes);
         if (!n_pending_host) { CUDA_OK(cudaMallocHost((void**)&n_pending_host, 4)); *n_pending_host = 0; }
         if (!stream) CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -481,7 +483,8 @@ struct Pipeline {
         Q.pair_ll = pair_ll.as<double>(); Q.pair_status = pair_status.as<int32_t>();
         if (want_columns) { Q.out_n_cols = o_n_cols.as<int32_t>(); Q.out_level = o_level.as<int32_t>(); Q.out_edge = o_edge.as<int32_t>(); Q.out_gchar = o_gchar.as<uint8_t>(); Q.out_schar = o_schar.as<uint8_t>(); Q.out_fromseed = o_fromseed.as<uint8_t>(); Q.out_mapq = o_mapq.as<uint8_t>(); }
         Q.bases_per_level = bases_per_level_dev; Q.error_count = cs.error_count.as<int32_t>(); Q.digest = digest.as<unsigned long long>();
-        if (Q.pair_end > Q.pair_begin) { tic(3, st); CUDA_OK(launch_pair(Q, g->n_sm, st)); toc(st); launches++; }
+        Q.defer_list = L.pair_defer.as<int32_t>(); Q.defer_count = L.pair_defer_count.as<int32_t>();
+        if (Q.pair_end > Q.pair_begin) { CUDA_OK(cudaMemsetAsync(Q.defer_count, 0, 4, st)); tic(3, st); CUDA_OK(launch_pair(Q, g->n_sm, st)); toc(st); launches += 2; }
     }
     // lanes start after everything queued on the caller's stream and the caller's stream continues after the lanes
     void fork_lanes(cudaStream_t st) { CUDA_OK(cudaEventRecord(fork_ev, st)); for (auto& L : lanes) CUDA_OK(cudaStreamWaitEvent(L->stream, fork_ev, 0)); }

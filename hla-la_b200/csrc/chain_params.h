@@ -84,17 +84,8 @@ struct PairParams {
     int32_t* bases_per_level;      // [n_levels-1] += , may be null
     int32_t* error_count;
     unsigned long long* digest;    // [4]: sum n_cols, sum (edge ordinal + 1), pairs with mapQ < 1, -
+    int32_t* defer_list; int32_t* defer_count;   // pairs beyond the small tier's capacities (kept chains per read, combinations), re-run by the large tier
 };
-
-__host__ __device__ inline size_t k3_slab_bytes(int maxcol) {
-    size_t b = 0;
-    b += (size_t)K3_COMBO_CAP * 8;      // LL / PP
-    b += (size_t)maxcol * 8;            // Q
-    b += (size_t)maxcol * 4 * 2;        // member masks, base->level table
-    b += (size_t)maxcol * 2;            // base->gchar, level info
-    b += (size_t)K3_KCAP * 4 * 2;       // kept slots
-    return (b + 15) & ~size_t(15);
-}
 
 __host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int win_cap, int wcap) {
     size_t b = 0;

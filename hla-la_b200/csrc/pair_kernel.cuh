@@ -17,15 +17,25 @@
 
 namespace hlala {
 
-struct PairSlab { double* ll; double* Q; uint32_t* mask; int32_t* blevel; uint8_t* bg; uint8_t* linfo; int32_t* kept1; int32_t* kept2; };
+// Two capacity tiers (the reference has no limit): tier 0 holds 32 kept chains per read and 512 combinations per pair in 8.6 KB of shared memory per
+// warp and serves practically every pair; pairs beyond it (reads with tens of distinct-coordinate chains inside HLA paralogs) are queued and re-run
+// by tier 1 with 64 chains per read (64-bit membership masks) and 4096 combinations. Beyond tier 1 a pair is an error (HLALA_E_CAPACITY).
+template <int KCAP_, int COMBO_, class MASK_> struct PairCfg { static constexpr int KCAP = KCAP_, COMBO = COMBO_; typedef MASK_ Mask; };
+typedef PairCfg<K3_KCAP, K3_COMBO_CAP, uint32_t> PairTier0;
+typedef PairCfg<64, 4096, unsigned long long> PairTier1;
 
-__device__ inline PairSlab carve_pair_slab(unsigned char* p, int maxcol) {
-    PairSlab s;
-    s.ll = (double*)p; p += (size_t)K3_COMBO_CAP * 8;
+template <class CFG> struct PairSlab { double* ll; double* Q; typename CFG::Mask* mask; int32_t* blevel; uint8_t* bg; uint8_t* linfo; int32_t* kept1; int32_t* kept2; };
+template <class CFG> __host__ __device__ inline size_t pair_slab_bytes(int maxcol) {
+    size_t b = (size_t)CFG::COMBO * 8 + (size_t)maxcol * 8 + (size_t)maxcol * sizeof(typename CFG::Mask) + (size_t)maxcol * 4 + (size_t)CFG::KCAP * 4 * 2 + (size_t)maxcol * 2;
+    return (b + 15) & ~size_t(15);
+}
+template <class CFG> __device__ inline PairSlab<CFG> carve_pair_slab(unsigned char* p, int maxcol) {
+    PairSlab<CFG> s;
+    s.ll = (double*)p; p += (size_t)CFG::COMBO * 8;
     s.Q = (double*)p; p += (size_t)maxcol * 8;
-    s.mask = (uint32_t*)p; p += (size_t)maxcol * 4;
+    s.mask = (typename CFG::Mask*)p; p += (size_t)maxcol * sizeof(typename CFG::Mask);
     s.blevel = (int32_t*)p; p += (size_t)maxcol * 4;
-    s.kept1 = (int32_t*)p; p += K3_KCAP * 4; s.kept2 = (int32_t*)p; p += K3_KCAP * 4;
+    s.kept1 = (int32_t*)p; p += CFG::KCAP * 4; s.kept2 = (int32_t*)p; p += CFG::KCAP * 4;
     s.bg = p; p += maxcol; s.linfo = p; p += maxcol;
     return s;
 }
@@ -65,7 +75,7 @@ __device__ __forceinline__ uint8_t phred_char(const PairParams& P, double q) {
 }
 
 // per-read helper: kept chains after the strand and identical-coordinates rules (processBAM.cpp:3216, 3234)
-__device__ int gather_kept(const PairParams& P, int r, int32_t* kept, int& err) {
+template <int KCAP> __device__ int gather_kept(const PairParams& P, int r, int32_t* kept, int& err) {
     int n = 0;
     for (int s = P.b.chain_off[r]; s < P.b.chain_off[r + 1]; s++) {
         int st = P.status[s];
@@ -74,14 +84,14 @@ __device__ int gather_kept(const PairParams& P, int r, int32_t* kept, int& err) 
         bool dup = false;
         for (int k = 0; k < n; k++) if (P.id_first[kept[k]] == P.id_first[s] && P.id_last[kept[k]] == P.id_last[s]) { dup = true; break; }
         if (dup) continue;        // chains are AS-sorted, so the registered score of an equal id is always >= this one
-        if (n >= K3_KCAP) { err = HLALA_E_CAPACITY_DEV; return n; }
+        if (n >= KCAP) { err = HLALA_E_CAPACITY_DEV; return n; }
         kept[n++] = s;
     }
     return n;
 }
 
 // membership bit `bit` for every column of the chosen chain `cs` against chain `as` (both of the same read)
-__device__ void mark_members(const PairParams& P, const PairSlab& S, int cs, int as, int bit, int lane) {
+template <class CFG> __device__ void mark_members(const PairParams& P, const PairSlab<CFG>& S, int cs, int as, int bit, int lane) {
     const int mc = P.maxcol;
     const int na = P.n_cols[as], fa = P.first_level[as], nlev_a = P.last_level[as] - fa + 1;
     const int32_t* ae = P.c_edge + (size_t)(as - P.slot_base) * mc; const uint8_t* asq = P.c_schar + (size_t)(as - P.slot_base) * mc;
@@ -114,25 +124,32 @@ __device__ void mark_members(const PairParams& P, const PairSlab& S, int cs, int
             bool mem;
             if (sc != '_') { int bi = cb + __popc(mb & ((1u << lane) - 1)); mem = (S.blevel[bi] == lvl && S.bg[bi] == g); }
             else { int kk = lvl - fa; mem = (e >= 0 && kk >= 0 && kk < nlev_a && S.linfo[kk] == (uint8_t)(g | 0x80)); }
-            if (mem) S.mask[k] |= (1u << bit);
+            if (mem) S.mask[k] |= ((typename CFG::Mask)1 << bit);
         }
         cl += __popc(ml); cb += __popc(mb);
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
+template <class CFG, bool FROM_LIST> __global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
+    typedef typename CFG::Mask Mask;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    PairSlab S = carve_pair_slab(smem + (size_t)warp * k3_slab_bytes(P.maxcol), P.maxcol);
+    PairSlab<CFG> S = carve_pair_slab<CFG>(smem + (size_t)warp * pair_slab_bytes<CFG>(P.maxcol), P.maxcol);
     const DevBatch& B = P.b; const int mc = P.maxcol;
     const int nw = gridDim.x * K3_WARPS;
-    for (long long p = P.pair_begin + (long long)blockIdx.x * K3_WARPS + warp; p < P.pair_end; p += nw) {
+    const long long n_work = FROM_LIST ? (long long)*P.defer_count : P.pair_end - P.pair_begin;
+    for (long long wi = (long long)blockIdx.x * K3_WARPS + warp; wi < n_work; wi += nw) {
+        const long long p = FROM_LIST ? (long long)P.defer_list[wi] : P.pair_begin + wi;
         const int r1 = (int)(2 * p), r2 = r1 + 1;
         int n1 = 0, n2 = 0, err = 0;
-        if (lane == 0) { n1 = gather_kept(P, r1, S.kept1, err); if (!err) n2 = gather_kept(P, r2, S.kept2, err); if (!err && (n1 == 0 || n2 == 0)) err = HLALA_E_INVARIANT_DEV; if (!err && n1 * n2 > K3_COMBO_CAP) err = HLALA_E_CAPACITY_DEV; }
+        if (lane == 0) { n1 = gather_kept<CFG::KCAP>(P, r1, S.kept1, err); if (!err) n2 = gather_kept<CFG::KCAP>(P, r2, S.kept2, err); if (!err && (n1 == 0 || n2 == 0)) err = HLALA_E_INVARIANT_DEV; if (!err && n1 * n2 > CFG::COMBO) err = HLALA_E_CAPACITY_DEV; }
         n1 = __shfl_sync(0xffffffffu, n1, 0); n2 = __shfl_sync(0xffffffffu, n2, 0); err = __shfl_sync(0xffffffffu, err, 0);
         __syncwarp();
+        if (!FROM_LIST && err == HLALA_E_CAPACITY_DEV && P.defer_list) {     // re-run by the large tier
+            if (lane == 0) P.defer_list[atomicAdd(P.defer_count, 1)] = (int32_t)p;
+            continue;
+        }
         if (err) {
             if (lane == 0) { P.pair_status[p] = err; P.pair_mapq[p] = -1; P.chosen_slot[r1] = -1; P.chosen_slot[r2] = -1; if (P.out_n_cols) { P.out_n_cols[r1] = 0; P.out_n_cols[r2] = 0; } atomicAdd(P.error_count, 1); }
             continue;
@@ -191,11 +208,11 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
                 for (int k = lane; k < ncol; k += 32) S.mask[k] = 0;
                 __syncwarp();
                 const int nk = which == 0 ? n1 : n2; const int32_t* kept = which == 0 ? S.kept1 : S.kept2;
-                for (int t = 0; t < nk; t++) mark_members(P, S, cs, kept[t], t, lane);
+                for (int t = 0; t < nk; t++) mark_members<CFG>(P, S, cs, kept[t], t, lane);
                 for (int k = lane; k < ncol; k += 32) {
-                    const uint32_t m = S.mask[k]; double q = 0;
-                    if (which == 0) { for (int a = 0; a < n1; a++) if ((m >> a) & 1u) for (int b = 0; b < n2; b++) q += S.ll[a * n2 + b]; }
-                    else { for (int a = 0; a < n1; a++) for (int b = 0; b < n2; b++) if ((m >> b) & 1u) q += S.ll[a * n2 + b]; }
+                    const Mask m = S.mask[k]; double q = 0;
+                    if (which == 0) { for (int a = 0; a < n1; a++) if ((m >> a) & 1) for (int b = 0; b < n2; b++) q += S.ll[a * n2 + b]; }
+                    else { for (int a = 0; a < n1; a++) for (int b = 0; b < n2; b++) if ((m >> b) & 1) q += S.ll[a * n2 + b]; }
                     if (q > 1) q = 1;
                     S.Q[k] = q;
                 }

@@ -29,6 +29,7 @@ DATASETS = {
     "small": (dict(levels=6000, haps=4, genes=1, alleles=16, seed=7), dict(pairs=150, len=100, seed=7), 100.0, 10.0),
     "S": (dict(levels=25000, haps=4, genes=2, alleles=64), dict(pairs=1200, len=100, clip_frac=0.15), 100.0, 10.0),
     "typing": (dict(levels=40000, haps=4, genes=17, alleles=24, seed=11), dict(pairs=1500, len=100, seed=11, gene_frac=0.8), 100.0, 10.0),
+    "typing1k": (dict(levels=60000, haps=4, genes=17, alleles=1000, seed=31), dict(pairs=700, len=150, seed=31, gene_frac=0.85), 100.0, 10.0),   # 1000 alleles per locus like the bench PRG
     "typing250": (dict(levels=35000, haps=4, genes=17, alleles=24, seed=24), dict(pairs=800, len=250, seed=24, gene_frac=0.8, clip_frac=0.2, gap_mean=300, gap_sd=40), 300.0, 40.0),
     "genes": (dict(levels=30000, haps=8, genes=8, alleles=300), dict(pairs=250, len=150, clip_frac=0.15, gene_frac=1.0), 100.0, 10.0),
     "L250": (dict(levels=20000, haps=6, genes=2, alleles=32, seed=21), dict(pairs=400, len=250, clip_frac=0.3, indel_rate=0.002, seed=21), 250.0, 35.0),

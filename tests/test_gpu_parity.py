@@ -171,3 +171,42 @@ def test_empty_and_single_pair_batches(dataset):
     assert np.array_equal(one["n_cols"], full["n_cols"][-2:]) and np.array_equal(one["pair_mapq"], full["pair_mapq"][-1:])
     for k in ("level", "edge", "schar", "mapq"):
         assert np.array_equal(one[k], full[k][-2:]), k
+
+
+def _with_many_chains(b, contig_len, n_extra, pairs, seed=1):
+    """first `pairs` pairs: every read gets n_extra extra secondary records (the primary's CIGAR at other places of its contig, same strand,
+    lower score): more kept chains per read and more combinations per pair than the pair kernel's small tier holds"""
+    rng = np.random.RandomState(seed); nr = len(b["read_off"]) - 1
+    out = {k: [] for k in ("chain_contig", "chain_pos", "chain_flag", "chain_as")}; cig = []; cig_off = [0]; chain_off = [0]
+    for r in range(nr):
+        c0, c1 = int(b["chain_off"][r]), int(b["chain_off"][r + 1])
+        recs = [(int(b["chain_contig"][c]), int(b["chain_pos"][c]), int(b["chain_flag"][c]), int(b["chain_as"][c]), list(b["cigar"][b["cigar_off"][c]:b["cigar_off"][c + 1]])) for c in range(c0, c1)]
+        if recs and r < 2 * pairs:
+            prim = [x for x in recs if not (x[2] & 0x100)][0]; ctg, pos, flag, as_, cg = prim
+            reflen = sum(int(x) >> 4 for x in cg if (int(x) & 15) in (0, 2, 3, 7, 8))
+            for k in range(n_extra):
+                p2 = int(rng.randint(0, contig_len[ctg] - reflen - 1))
+                recs.append((ctg, p2, flag | 0x100, as_ - 1 - k, cg))
+        for ctg, pos, flag, as_, cg in recs:
+            out["chain_contig"].append(ctg); out["chain_pos"].append(pos); out["chain_flag"].append(flag); out["chain_as"].append(as_)
+            cig += [int(x) for x in cg]; cig_off.append(len(cig))
+        chain_off.append(len(out["chain_contig"]))
+    nb = dict(b)
+    nb["chain_off"] = np.array(chain_off, b["chain_off"].dtype); nb["cigar_off"] = np.array(cig_off, b["cigar_off"].dtype); nb["cigar"] = np.array(cig, b["cigar"].dtype)
+    for k in out:
+        nb[k] = np.array(out[k], b[k].dtype)
+    return nb
+
+
+def test_pairs_beyond_the_small_pair_tier(dataset):
+    """reads with 44 kept chains (> 32) and pairs with > 512 combinations: served by the pair kernel's large tier, equal to the oracle (which, like the reference, has no limit)"""
+    d, b, mu, sd = dataset("small")
+    P = product(d); contig_len = np.diff(P.array("contig_off"))
+    nb = _with_many_chains(b, contig_len, 43, 6)
+    sub = {k: v for k, v in nb.items()}
+    want = H.oracle_pairs(d, nb, mu, sd, 1024); got = P.pairs(nb, mu, sd, 1024)
+    assert_pairs_equal(got, want)
+    # beyond the large tier (> 64 kept chains) the pair is reported, not silently dropped
+    nb2 = _with_many_chains(b, contig_len, 70, 1)
+    with pytest.raises(RuntimeError, match="capacity|invariant"):
+        P.pairs(nb2, mu, sd, 1024)

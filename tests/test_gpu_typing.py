@@ -36,8 +36,9 @@ def run_product(d, b, mu, sd, out_dir, world=1):
     return P, T, blobs
 
 
-def test_typing_matches_oracle(dataset, tmp_path):
-    d, b, mu, sd = dataset("typing")
+@pytest.mark.parametrize("name", ["typing", "typing1k"])
+def test_typing_matches_oracle(dataset, tmp_path, name):
+    d, b, mu, sd = dataset(name)
     P, T, blobs = run_product(d, b, mu, sd, None)
     out = str(tmp_path / "gpu" / "hla")
     T.infer(blobs, mu, sd, out)
@@ -63,6 +64,8 @@ def test_typing_matches_oracle(dataset, tmp_path):
     # the pair tables print 6 significant digits of sums that may differ in the last bits: compare them field by field
     for f in fo:
         if not f.startswith("R1_PP_"):
+            continue
+        if filecmp.cmp(os.path.join(or_dir, f), os.path.join(out, f), shallow=False):
             continue
         a = open(os.path.join(or_dir, f)).read().split("\n"); g_ = open(os.path.join(out, f)).read().split("\n")
         assert len(a) == len(g_)
