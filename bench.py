@@ -254,6 +254,63 @@ def stage_typing(args, root, H):
     return res
 
 
+def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels):
+    """BASELINE.json configs[2] on N GPUs: --strong-pairs pairs in total, sharded by pair across the ranks (graph replicated). Timed per rank, max over ranks:
+    alignment of the shard (columns kept) -> all-reduce of the per-level coverage -> extraction of the gene-overlapping pairs -> all-gather of those (small)
+    alignment blobs -> typing with the reads split across ranks and ONE NCCL all-reduce of the allele-pair sums per locus -> rank 0 writes the hla/* files."""
+    import tempfile
+    n_shard = args.strong_pairs // world
+    b = make_reads(args, prg_dir, 1000 + rank, n_shard, tag="strong%d" % world)
+    T = H.ProductTyping(P, prg_dir)
+    L = P.lib; sb = H.make_batch_struct(b); sess = C.c_void_p()
+    P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(sess))); P._chk(L.hlala_session_set_keep_columns(sess, 1))
+    cov = torch.zeros(n_levels - 1, dtype=torch.int32, device="cuda"); stream = torch.cuda.current_stream()
+    n_calls = [0]
+
+    def allreduce(ctx, ptr, count, st):
+        t = H.dev_f64_tensor(ptr, count, local_rank)
+        torch.cuda.current_stream().synchronize(); dist.all_reduce(t); torch.cuda.synchronize(); n_calls[0] += 1
+        return 0
+
+    class _Solo:      # N = 1: the same leg without collectives (the strong-scaling baseline)
+        class ReduceOp:
+            MAX = None
+
+        @staticmethod
+        def barrier():
+            pass
+
+        @staticmethod
+        def all_reduce(t, op=None):
+            return t
+
+        @staticmethod
+        def all_gather_object(lst, obj):
+            lst[0] = obj
+    if dist is None:
+        dist = _Solo
+    out = tempfile.mkdtemp(prefix="hlala_strong_") if rank == 0 else None
+    res = None
+    for it in range(2):     # the second pass is the timed one
+        cov.zero_(); n_calls[0] = 0
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        P._chk(L.hlala_session_run(sess, C.c_double(args.is_mean), C.c_double(args.is_sd), C.c_uint64(cov.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        dist.all_reduce(cov); torch.cuda.synchronize(); t_align = time.perf_counter() - t0
+        blob, nsel = T.extract(sess, base=rank * n_shard)
+        blobs = [None] * world; dist.all_gather_object(blobs, blob); t_gather = time.perf_counter() - t0
+        T.infer(blobs, args.is_mean, args.is_sd, os.path.join(out, "hla%d" % it) if out else None, device=local_rank, rank=rank, world=world, allreduce=allreduce if world > 1 else None, keep_read_ll=False)
+        torch.cuda.synchronize(); t_all = time.perf_counter() - t0
+        tt = torch.tensor([t_align, t_gather, t_all, float(nsel)], dtype=torch.float64, device="cuda")
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); tsum = tt.clone(); dist.all_reduce(tsum)
+        res = {"total_pairs": n_shard * world, "pairs_per_rank": n_shard, "seconds": float(tmax[2]), "pairs_per_s": n_shard * world / float(tmax[2]),
+               "seconds_alignment_plus_coverage_allreduce": float(tmax[0]), "seconds_until_blobs_gathered": float(tmax[1]), "pairs_selected_for_typing": int(tsum[3]),
+               "allele_pair_allreduces_per_rank": n_calls[0], "gathered_blob_bytes": int(sum(len(x) for x in blobs)),
+               "files_written_by_rank0": len(os.listdir(os.path.join(out, "hla%d" % it))) if out else None,
+               "note": "strong scaling: the total is fixed, every rank aligns total/N pairs; wall clock, max over ranks, second of two passes; inputs resident in HBM, typing outputs written by rank 0"}
+    L.hlala_session_free(sess); T.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,6 +330,8 @@ def main():
     ap.add_argument("--cpu-levels", type=int, default=294118, help="levels of the reference arm's PRG slice (default: levels / genes = one gene block, the bench PRG's density)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--stages", type=int, default=1, help="also time the k-mer seeding and typing stages (rank 0, N=1 only)")
+    ap.add_argument("--strong-single", type=int, default=0, help="run the strong-scaling leg at N = 1 too (its baseline; off by default to keep the default run short)")
+    ap.add_argument("--strong-pairs", type=int, default=4000000, help="N > 1: total pairs of the strong-scaling leg (BASELINE.json configs[2]: ~4M pairs sharded over the GPUs, typing with one NCCL all-reduce per locus); 0 = skip")
     args = ap.parse_args()
     rank, local_rank, world = rank_info()
     n_gpus = max(world, 1)
@@ -317,6 +376,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:   # every rank keeps to its own slice of the host cores (chain sorting and the typing host stage are threaded): the e2e numbers of N ranks then do not fight over the same cores
+        try:
+            cores = sorted(os.sched_getaffinity(0)); lw = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))); per = max(1, len(cores) // lw)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores))
+            os.environ["HLALA_HOST_THREADS"] = str(per)
+        except Exception:
+            pass
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -433,6 +499,9 @@ def main():
     if rank == 0:
         sys.stderr.write("[bench] e2e: %s pairs/s (%s s per call)\n" % (e2e_value, [round(x, 3) for x in e2e_times]))
 
+    strong = None
+    if args.strong_pairs > 0 and (dist or args.strong_single):
+        strong = strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -511,7 +580,7 @@ def main():
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
-            "stages": stages, "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
+            "stages": stages, "strong_scaling_config3": strong, "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

@@ -114,6 +114,7 @@ struct PreparedBatch {
             }
         };
         unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("HLALA_HOST_THREADS")) nt = (unsigned)std::max(1, std::min(64, atoi(e)));     // several ranks on one node: each keeps to its share of the cores
         if (n_reads < 20000) nt = 1;
         std::vector<std::thread> th; int64_t per = (n_reads + nt - 1) / nt;
         for (unsigned t = 0; t < nt; t++) { int64_t r0 = t * per, r1 = std::min<int64_t>(n_reads, r0 + per); if (r0 < r1) th.emplace_back(work, r0, r1); }

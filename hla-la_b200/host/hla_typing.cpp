@@ -570,6 +570,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             { std::unique_lock<std::mutex> lk(dev_mu); dev_cv.wait(lk, [&]() { return dev_turn >= li; }); if (dev_turn == li) dev_turn = li + 1; }   // a locus that failed before its device stage still hands the turn on
             dev_cv.notify_all(); } };
         unsigned nt = opt.threads > 0 ? (unsigned)opt.threads : std::max(1u, std::min<unsigned>((unsigned)NL, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("HLALA_HOST_THREADS")) nt = std::min<unsigned>(nt, (unsigned)std::max(1, atoi(e)));     // several ranks on one node
         if (const char* e = getenv("HLALA_TYPING_THREADS")) nt = (unsigned)std::max(1, atoi(e));
         std::vector<std::thread> th; for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
         worker(); for (auto& t : th) t.join();

@@ -644,7 +644,10 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def dev_f64_tensor(ptr, count):
-    """torch view (no copy) of `count` doubles at device address `ptr` (what the typing all-reduce callback receives)."""
+def dev_f64_tensor(ptr, count, device=None):
+    """torch view (no copy) of `count` doubles at device address `ptr` (what the typing all-reduce callback receives). The callback runs on a
+    host thread of the typing stage: torch's current device is per thread, so pass the rank's device."""
     import torch
-    return torch.as_tensor(_DevArray(ptr, count), device="cuda")
+    if device is not None:
+        torch.cuda.set_device(device)
+    return torch.as_tensor(_DevArray(ptr, count), device="cuda" if device is None else "cuda:%d" % device)

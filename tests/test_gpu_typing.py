@@ -68,12 +68,18 @@ def test_typing_matches_oracle(dataset, tmp_path, name):
         if filecmp.cmp(os.path.join(or_dir, f), os.path.join(out, f), shallow=False):
             continue
         a = open(os.path.join(or_dir, f)).read().split("\n"); g_ = open(os.path.join(out, f)).read().split("\n")
-        assert len(a) == len(g_)
-        for la, lg in zip(a[1:], g_[1:]):
-            if la == lg:
-                continue
-            fa, fg = la.split("\t"), lg.split("\t")
-            assert fa[0] == fg[0] and np.allclose([float(x) for x in fa[1:]], [float(x) for x in fg[1:]], rtol=1e-5, atol=0), (f, la, lg)
+        assert len(a) == len(g_) and a[0] == g_[0]
+        # Same rows; the order may differ only among rows whose LL agree to the printed precision: the reference sorts by the exact doubles, and sums
+        # that differ in the last bits (device exp/log, max-shifted products) order near-ties differently
+        ra = {l.split("\t")[0]: [float(x) for x in l.split("\t")[1:]] for l in a[1:] if l}; rg = {l.split("\t")[0]: [float(x) for x in l.split("\t")[1:]] for l in g_[1:] if l}
+        assert ra.keys() == rg.keys()
+        ka = [l.split("\t")[0] for l in a[1:] if l]; kg = [l.split("\t")[0] for l in g_[1:] if l]
+        va = np.array([ra[k] for k in ka]); vg = np.array([rg[k] for k in ka])
+        assert np.allclose(va, vg, rtol=1e-5, atol=0), f
+        lg = np.array([rg[k][1] for k in kg]); assert np.all(np.diff(lg) <= 1e-6 * np.abs(lg[1:])), f     # our file is sorted by LL as well
+        moved = [i for i, (x, y) in enumerate(zip(ka, kg)) if x != y]
+        for i in moved:
+            assert abs(ra[ka[i]][1] - ra[kg[i]][1]) <= 1e-5 * abs(ra[ka[i]][1]), (f, ka[i], kg[i])
     O.close(); T.close(); P.close()
 
 

@@ -52,7 +52,7 @@ def main():
     n_calls = [0]
 
     def allreduce(ctx, ptr, count, stream):                # exchange 3: one sum all-reduce of the allele-pair vectors per locus
-        t = H.dev_f64_tensor(ptr, count)
+        t = H.dev_f64_tensor(ptr, count, local)
         torch.cuda.current_stream().synchronize(); dist.all_reduce(t); torch.cuda.synchronize(); n_calls[0] += 1
         return 0
     out = tempfile.mkdtemp(prefix="hlala_nccl_") if rank == 0 else None
