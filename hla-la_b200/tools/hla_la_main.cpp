@@ -6,7 +6,17 @@
 //   <outputDirectory>/reads_per_level.txt         processBAM.cpp:1907-1913
 //   <outputDirectory>/hla/*                        hla::HLATyper::HLATypeInference, hla/HLATyper.cpp:933-2810
 // Everything goes through the C ABI (include/hlala_b200.h); there is no CPU fallback.
+//
+// --gpus N (N > 1): the read pairs are sharded in contiguous blocks over N GPUs of this node (one host thread, one replica of the flat graph and
+// one NCCL communicator per GPU). The exchanges are the ones of SURVEY.md §8e: one ncclAllReduce(int32, sum) of the per-level coverage, the
+// gene-overlapping alignment blobs of all shards handed to every rank (host memory of this process), and ONE ncclAllReduce(double, sum) of
+// the allele-pair vectors per locus behind the callback of hlala_typer_infer. Rank 0 writes the files.
 #include "../../include/hlala_b200.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <atomic>
+#include <thread>
 
 #include <chrono>
 #include <cstdio>
@@ -16,12 +26,107 @@
 #include <string>
 #include <sys/stat.h>
 #include <vector>
+#include <algorithm>
 
 static std::chrono::steady_clock::time_point g_t0;
 static void phase(const char* what) {   // wall time of every phase, on stdout
     const auto t1 = std::chrono::steady_clock::now(); fprintf(stdout, "hlala-b200: [%8.2f s] %s\n", std::chrono::duration<double>(t1 - g_t0).count(), what); g_t0 = t1;
 }
 static int die(const char* what) { fprintf(stderr, "hlala-b200: %s: %s\n", what, hlala_last_error()); return 1; }
+
+// ---- multi-GPU -------------------------------------------------------------------------------------------------------------
+namespace {
+struct Shard {     // contiguous block of pairs of the BAM batch, offsets rebased to zero
+    std::vector<int64_t> read_off; std::vector<int32_t> chain_off, cigar_off; hlala_seed_batch_t view; int64_t pair0 = 0;
+    void cut(const hlala_seed_batch_t& b, int64_t p0, int64_t p1) {
+        pair0 = p0; const int64_t r0 = 2 * p0, r1 = 2 * p1; const int32_t c0 = b.chain_off[r0], c1 = b.chain_off[r1]; const int32_t g0 = b.cigar_off[c0]; const int64_t q0 = b.read_off[r0];
+        read_off.resize((size_t)(r1 - r0 + 1)); for (int64_t r = r0; r <= r1; r++) read_off[(size_t)(r - r0)] = b.read_off[r] - q0;
+        chain_off.resize((size_t)(r1 - r0 + 1)); for (int64_t r = r0; r <= r1; r++) chain_off[(size_t)(r - r0)] = b.chain_off[r] - c0;
+        cigar_off.resize((size_t)(c1 - c0 + 1)); for (int32_t c = c0; c <= c1; c++) cigar_off[(size_t)(c - c0)] = b.cigar_off[c] - g0;
+        view = b; view.n_reads = r1 - r0; view.read_off = read_off.data(); view.bases = b.bases + q0; view.quals = b.quals + q0; view.chain_off = chain_off.data();
+        view.chain_contig = b.chain_contig + c0; view.chain_pos = b.chain_pos + c0; view.chain_flag = b.chain_flag + c0; view.chain_as = b.chain_as + c0;
+        view.cigar_off = cigar_off.data(); view.cigar = b.cigar + g0;
+    }
+};
+struct Barrier {   // all ranks of this process meet here (C++17 has no std::barrier)
+    std::atomic<int> count{0}; std::atomic<int> gen{0}; int n = 1;
+    void wait() { const int g = gen.load(); if (count.fetch_add(1) + 1 == n) { count.store(0); gen.fetch_add(1); } else while (gen.load() == g) std::this_thread::yield(); }
+};
+struct RankCtx { ncclComm_t comm; int device; };
+int nccl_sum_f64(void* ctx, uint64_t dev_ptr, int64_t count, void* stream) {     // hlala_allreduce_f64_fn: the one collective of the typing stage
+    RankCtx* c = (RankCtx*)ctx; cudaSetDevice(c->device); cudaStream_t st = (cudaStream_t)stream;
+    if (ncclAllReduce((const void*)dev_ptr, (void*)dev_ptr, (size_t)count, ncclDouble, ncclSum, c->comm, st) != ncclSuccess) return 1;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
+}
+
+static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
+    const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
+    int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus) { fprintf(stderr, "hlala-b200: --gpus %d but %d CUDA devices are visible\n", n_gpus, ndev); return 1; }
+    { const unsigned hc = std::max(1u, std::thread::hardware_concurrency()); setenv("HLALA_HOST_THREADS", std::to_string(std::max(1u, hc / (unsigned)n_gpus)).c_str(), 0); }
+    std::vector<int> devs((size_t)n_gpus); for (int i = 0; i < n_gpus; i++) devs[(size_t)i] = i;
+    std::vector<ncclComm_t> comms((size_t)n_gpus);
+    if (ncclCommInitAll(comms.data(), n_gpus, devs.data()) != ncclSuccess) { fprintf(stderr, "hlala-b200: ncclCommInitAll failed\n"); return 1; }
+    g_t0 = std::chrono::steady_clock::now();
+    // rank 0's graph handle also serves the BAM ingest (contig names); every rank loads its own replica (the flat cache makes that seconds)
+    std::vector<hlala_graph_t*> graphs((size_t)n_gpus, nullptr); std::atomic<int> failed{0}; std::vector<std::string> err((size_t)n_gpus);
+    { std::vector<std::thread> th; for (int r = 0; r < n_gpus; r++) th.emplace_back([&, r]() { if (hlala_graph_load(prg.c_str(), &graphs[(size_t)r]) || hlala_graph_to_gpu(graphs[(size_t)r], r)) { err[(size_t)r] = hlala_last_error(); failed++; } }); for (auto& t : th) t.join(); }
+    if (failed) { for (auto& e : err) if (!e.empty()) fprintf(stderr, "hlala-b200: loading the PRG: %s\n", e.c_str()); return 1; }
+    phase("PRG loaded and replicated on the GPUs");
+    hlala_bam_batch_t* bam = nullptr;
+    if (hlala_bam_read(graphs[0], a["BAM"].c_str(), a.count("threads") ? atoi(a["threads"].c_str()) : 0, &bam)) return die("reading the BAM");
+    phase("BAM read, records selected and grouped");
+    hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
+    hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
+    if (a.count("insertSizeMean")) is_mean = atof(a["insertSizeMean"].c_str());
+    if (a.count("insertSizeSD")) is_sd = atof(a["insertSizeSD"].c_str());
+    const int64_t n_pairs = batch.n_reads / 2;
+    fprintf(stdout, "hlala-b200: %lld records, %lld used, %lld pairs to align on %d GPUs; insert size %g +- %g\n", (long long)counts[0], (long long)counts[1], (long long)n_pairs, n_gpus, is_mean, is_sd);
+    if (n_pairs < n_gpus) { fprintf(stderr, "hlala-b200: fewer read pairs than GPUs\n"); return 1; }
+    if (!(is_sd > 0)) { fprintf(stderr, "hlala-b200: cannot estimate the insert size; pass --insertSizeMean / --insertSizeSD\n"); return 1; }
+    mkdir(out_dir.c_str(), 0777);
+    const int64_t nl = hlala_graph_n_levels(graphs[0]);
+    std::vector<const uint8_t*> blobs((size_t)n_gpus, nullptr); std::vector<int64_t> blob_bytes((size_t)n_gpus, 0), n_sel((size_t)n_gpus, 0);
+    std::vector<hlala_typer_t*> typers((size_t)n_gpus, nullptr); Barrier bar; bar.n = n_gpus;
+    const std::string hla_dir = out_dir + "/hla";
+    struct stat sbuf; const std::string gdir = a.count("hla_nom_g_dir") ? a["hla_nom_g_dir"] : (stat((prg + "/hla_nom_g.txt").c_str(), &sbuf) == 0 ? prg : std::string("."));
+    auto rank_main = [&](int r) {
+        auto fail = [&](const std::string& what) { err[(size_t)r] = what + ": " + hlala_last_error(); failed++; };
+        cudaSetDevice(r);
+        Shard sh; { const int64_t base = n_pairs / n_gpus, rem = n_pairs % n_gpus; const int64_t p0 = r * base + std::min<int64_t>(r, rem); sh.cut(batch, p0, p0 + base + (r < rem ? 1 : 0)); }
+        hlala_session_t* s = nullptr; int32_t* cov = nullptr; cudaStream_t st = nullptr; cudaStreamCreate(&st);
+        bool ok = cudaMalloc((void**)&cov, (size_t)std::max<int64_t>(nl - 1, 1) * 4) == cudaSuccess && cudaMemsetAsync(cov, 0, (size_t)std::max<int64_t>(nl - 1, 1) * 4, st) == cudaSuccess;
+        if (!ok) fail("allocating the coverage histogram");
+        if (ok && (hlala_session_create(graphs[(size_t)r], &sh.view, maxcol, &s) || hlala_session_set_keep_columns(s, 1) || hlala_session_run(s, is_mean, is_sd, (uint64_t)(uintptr_t)cov, st))) { ok = false; fail("aligning"); }
+        if (ok) { int64_t dig[4]; double sll = 0; if (hlala_session_digest(s, dig, &sll) || dig[3] != 0) { ok = false; fail("chains/pairs violated a reference invariant or a kernel capacity"); } }
+        bar.wait();                                              // nobody enters a collective unless every rank got here in good shape
+        if (failed) return;
+        ncclAllReduce(cov, cov, (size_t)(nl - 1), ncclInt32, ncclSum, comms[(size_t)r], st); cudaStreamSynchronize(st);      // exchange 1: per-level coverage
+        if (r == 0) {
+            std::vector<int32_t> h((size_t)(nl - 1)); cudaMemcpy(h.data(), cov, h.size() * 4, cudaMemcpyDeviceToHost);
+            const std::string path = out_dir + "/reads_per_level.txt"; FILE* f = fopen(path.c_str(), "w");
+            if (f) { for (int64_t l = 0; l + 1 < nl; l++) fprintf(f, "%lld\t%s\t%d\n", (long long)l, hlala_graph_level_name(graphs[0], l), h[(size_t)l]); fclose(f); } else fail("cannot write " + path);
+        }
+        if (hlala_typer_create(prg.c_str(), &typers[(size_t)r]) || hlala_session_typing_extract(s, typers[(size_t)r], names + sh.pair0, sh.pair0, &blobs[(size_t)r], &blob_bytes[(size_t)r], &n_sel[(size_t)r])) fail("selecting the gene-overlapping pairs");
+        bar.wait();                                              // exchange 2: every rank now sees every shard's blob (one address space)
+        if (failed) return;
+        RankCtx ctx{comms[(size_t)r], r};
+        if (hlala_typer_infer(typers[(size_t)r], r, blobs.data(), blob_bytes.data(), n_gpus, is_mean, is_sd, r == 0 ? hla_dir.c_str() : nullptr, gdir.c_str(), r, n_gpus, nccl_sum_f64, &ctx, 0)) fail("HLA type inference");
+        bar.wait();
+        hlala_session_free(s); cudaFree(cov); cudaStreamDestroy(st);
+    };
+    { std::vector<std::thread> th; for (int r = 0; r < n_gpus; r++) th.emplace_back(rank_main, r); for (auto& t : th) t.join(); }
+    if (failed) { for (auto& e : err) if (!e.empty()) fprintf(stderr, "hlala-b200: %s\n", e.c_str()); return 1; }
+    phase("read pairs aligned on all GPUs, coverage all-reduced, HLA types inferred (one NCCL all-reduce per locus), files written");
+    long long sel = 0; for (int64_t v : n_sel) sel += v; fprintf(stdout, "hlala-b200: %lld read pairs overlap the typed genes\n", sel);
+    for (int l = 0; l < hlala_typer_n_loci(typers[0]); l++) {
+        const char* a1 = nullptr; const char* a2 = nullptr; double q1 = 0, q2 = 0;
+        if (hlala_typer_result_call(typers[0], l, &a1, &a2, &q1, &q2) == 0) fprintf(stdout, "%s\t%s\t%s\t%g\t%g\n", hlala_typer_locus_name(typers[0], l), a1, a2, q1, q2);
+    }
+    for (int r = 0; r < n_gpus; r++) { hlala_typer_free(typers[(size_t)r]); ncclCommDestroy(comms[(size_t)r]); hlala_graph_free(graphs[(size_t)r]); }
+    hlala_bam_batch_free(bam);
+    return 0;
+}
 
 int main(int argc, char** argv) {
     std::map<std::string, std::string> a;
@@ -42,9 +147,10 @@ int main(int argc, char** argv) {
     if (a["action"] != "HLA" || !a.count("BAM") || !a.count("outputDirectory") || !a.count("PRG_graph_dir")) {
         fprintf(stderr, "usage: hlala-b200 --action HLA --sampleID <id> --BAM <remapped.bam> --outputDirectory <dir> --PRG_graph_dir <dir>\n"
                         "       hlala-b200 --action prepareGraph --PRG_graph_dir <dir>\n"
-                        "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n>] [--maxColumns <n>] [--threads <n>]\n");
+                        "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n> | --gpus <N>] [--maxColumns <n>] [--threads <n>]\n");
         return 2;
     }
+    if (a.count("gpus") && atoi(a["gpus"].c_str()) > 1) return run_multi_gpu(a, atoi(a["gpus"].c_str()));
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"];
     const int device = a.count("device") ? atoi(a["device"].c_str()) : 0; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
     g_t0 = std::chrono::steady_clock::now();
