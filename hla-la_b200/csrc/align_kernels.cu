@@ -361,11 +361,9 @@ cudaError_t upload_score_tables(const ScoreTables& t) { return cudaMemcpyToSymbo
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream) {
     size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
     size_t smem = slab * K1_WARPS;
-    static size_t configured = 0;
-    if (smem > configured) {
+    {   // a function attribute belongs to the current device: set it on every launch (several GPUs may be driven from one process)
         cudaError_t e = cudaFuncSetAttribute(k_chain_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     int per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_seed, K1_WARPS * 32, smem);
@@ -490,8 +488,7 @@ cudaError_t launch_dp_task_bytes(const ExtParams& E, unsigned long long* out, cu
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
     size_t smem = k1_slab_bytes(E.C.slab_cols, E.C.pool_cap, E.C.win_cap, E.C.wcap) * K1_WARPS;
-    static size_t configured = 0;
-    if (smem > configured) { cudaError_t e = cudaFuncSetAttribute(k_chain_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; configured = smem; }
+    { cudaError_t e = cudaFuncSetAttribute(k_chain_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     int per_sm = 1; cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_finish, K1_WARPS * 32, smem);
     if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
     long long want = ((long long)E.n_pending + K1_WARPS - 1) / K1_WARPS;

@@ -780,6 +780,8 @@ struct GpuTypingDevice : TypingDevice {
     double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0};
     void run_locus(const LocusDeviceInput& in, bool want_read_ll, LocusDeviceOutput& out) override {
         CUDA_OK(cudaSetDevice(device));   // entered from the host thread pool of run_typing (one locus at a time, in locus order)
+        static const bool prof = getenv("HLALA_TYPING_PROFILE") != nullptr; auto tp0 = std::chrono::steady_clock::now();
+        auto lapp = [&](const char* what) { if (!prof) return; auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[typing-device] C=%d R=%d %-12s %8.3f ms\n", in.C, in.R, what, std::chrono::duration<double, std::milli>(t1 - tp0).count()); tp0 = t1; };
         const int32_t C = in.C, P = in.P, R = in.R; const int32_t Cpad = (C + 31) / 32 * 32;
         const size_t npair = (size_t)C * ((size_t)C + 1) / 2;
         std::vector<uint8_t> ct((size_t)P * Cpad, (uint8_t)'_');
@@ -792,6 +794,7 @@ struct GpuTypingDevice : TypingDevice {
         if (want_read_ll) { CUDA_OK(cudaMemsetAsync(d_ll.p, 0, d_ll.bytes, st)); CUDA_OK(cudaMemsetAsync(d_mm.p, 0, d_mm.bytes, st)); }
         int32_t max_rec = 0; double steps = 0;
         for (int32_t r = 0; r < R; r++) { max_rec = std::max(max_rec, in.rec_off[r + 1] - in.rec_off[r]); if (r >= r0 && r < r1) steps += (double)(in.rec_off[r + 1] - in.rec_off[r]); }
+        lapp("alloc+upload");
         cudaEvent_t e0, e1, e2; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaEventCreate(&e2));
         CUDA_OK(cudaEventRecord(e0, st));
         CUDA_OK(launch_read_cluster_ll(d_ct.as<uint8_t>(), C, Cpad, r0, r1, max_rec, d_off.as<int32_t>(), d_pos.as<int16_t>(), d_c0.as<uint8_t>(), d_q0.as<uint8_t>(), d_glen.as<uint16_t>(), d_ll.as<double>(), d_mm.as<int32_t>(), st));
@@ -804,10 +807,12 @@ struct GpuTypingDevice : TypingDevice {
             CUDA_OK(cudaStreamSynchronize(st));     // the scratch buffers above are freed at the end of this scope
         }
         CUDA_OK(cudaEventRecord(e2, st));
+        if (prof) { CUDA_OK(cudaStreamSynchronize(st)); lapp("kernels"); }
         if (world > 1) {
             if (!allreduce) throw std::runtime_error("hlala_typer_infer: world > 1 needs an all-reduce callback");
             if (allreduce(ctx, (uint64_t)(uintptr_t)d_pair.p, (int64_t)(3 * npair), (void*)st) != 0) throw std::runtime_error("hlala_typer_infer: all-reduce callback failed");
         }
+        lapp("all-reduce");
         out.pair_ll.resize(npair); out.pair_mavg.resize(npair); out.pair_mmin.resize(npair);
         CUDA_OK(cudaMemcpyAsync(out.pair_ll.data(), pl, npair * 8, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaMemcpyAsync(out.pair_mavg.data(), pl + npair, npair * 8, cudaMemcpyDeviceToHost, st));
@@ -815,6 +820,7 @@ struct GpuTypingDevice : TypingDevice {
         std::vector<double> llt; std::vector<int32_t> mmt;
         if (want_read_ll && R > 0) { llt.resize((size_t)R * Cpad); mmt.resize((size_t)R * Cpad); d_ll.download(llt.data(), llt.size(), st); d_mm.download(mmt.data(), mmt.size(), st); }
         CUDA_OK(cudaStreamSynchronize(st));
+        lapp("download");
         float f = 0; CUDA_OK(cudaEventElapsedTime(&f, e0, e1)); ms[0] += f; CUDA_OK(cudaEventElapsedTime(&f, e1, e2)); ms[1] += f; launches[0] += (r1 > r0); launches[1]++;
         work[0] += steps * C; work[1] += (double)npair * (r1 - r0);
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);

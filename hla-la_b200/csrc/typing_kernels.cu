@@ -93,8 +93,7 @@ cudaError_t launch_read_cluster_ll(const uint8_t* clusterT, int32_t C, int32_t C
                                    const uint8_t* rec_c0, const uint8_t* rec_q0, const uint16_t* rec_glen, double* LLt, int32_t* mmT, cudaStream_t st) {
     if (r1 <= r0 || C <= 0) return cudaSuccess;
     const size_t smem = (size_t)std::max(max_rec, 1) * (sizeof(K4Rec) + 2 + 1 + 1) + 16;
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k_read_cluster_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; configured = smem; }
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(k_read_cluster_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     dim3 grid((unsigned)((Cpad + K4_THREADS - 1) / K4_THREADS), (unsigned)(r1 - r0));
     k_read_cluster_ll<<<grid, K4_THREADS, smem, st>>>(clusterT, C, Cpad, r0, rec_off, rec_pos, rec_c0, rec_q0, rec_glen, LLt, mmT);
     return cudaGetLastError();
@@ -152,7 +151,8 @@ cudaError_t launch_allele_pair_ll(const double* LLt, const int32_t* mmT, int32_t
 //   sum_r logAvg(a_r, b_r) = sum_r m_r + n log(1/2) + log prod_r (e^{a_r - m_r} + e^{b_r - m_r}),   m_r = max_c LL[c][r]
 // The product is carried as a mantissa in [1, 2) and an integer exponent (one multiply, one add and a few integer operations per
 // term), so it can neither overflow nor underflow; a term whose two exponentials both vanish (both clusters > 690 nats below the
-// read's best cluster) falls back to the term-by-term form for that pair. Deviation from the term-by-term sums: ~1e-15 relative.
+// read's best cluster: two alleles with a deletion where the read has bases) is computed term-wise from the log-likelihoods themselves
+// and added to a side sum. Deviation from the term-by-term sums: ~1e-15 relative.
 // The mismatch sums are integers: the average is (S[c1] + S[c2]) / 2 with S the per-cluster totals, the minimum an integer sum.
 __global__ void k_read_exp_shift(const double* __restrict__ LLt, int32_t C, int32_t Cpad, int32_t r0, int32_t r1, double* __restrict__ Et, double* __restrict__ rowmax) {
     const int r = r0 + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); const int lane = threadIdx.x & 31;
@@ -170,14 +170,14 @@ __global__ void k_typing_col_sums(const int32_t* __restrict__ mmT, const double*
     if (c == 0) { double t = 0.0; for (int r = r0; r < r1; r++) t = __dadd_rn(t, rowmax[r]); *msum = t; }     // one thread, ascending reads: a fixed order
 }
 __global__ void __launch_bounds__(K5_T * K5_T) k_allele_pair_prod(const double* __restrict__ LLt, const double* __restrict__ Et, const int32_t* __restrict__ mmT, const double* __restrict__ colsum,
-                                                                  const double* __restrict__ msum, int32_t C, int32_t Cpad, int32_t r0, int32_t r1,
+                                                                  const double* __restrict__ msum, const double* __restrict__ rowmax, int32_t C, int32_t Cpad, int32_t r0, int32_t r1,
                                                                   double* __restrict__ pair_ll, double* __restrict__ pair_mavg, double* __restrict__ pair_mmin) {
     if (blockIdx.x < blockIdx.y) return;
     __shared__ double sA[K5_R][K5_T], sB[K5_R][K5_T]; __shared__ int32_t mA[K5_R][K5_T], mB[K5_R][K5_T];
     const int tx = threadIdx.x & (K5_T - 1), ty = threadIdx.x / K5_T;
     const int c1 = blockIdx.y * K5_T + ty, c2 = blockIdx.x * K5_T + tx;
     const bool mine = c1 < C && c2 < C && c2 >= c1;
-    double acc = 1.0; long long esum = 0; long long sm = 0; bool bad = false;
+    double acc = 1.0, extra = 0.0; long long esum = 0; long long sm = 0;
     for (int rb = r0; rb < r1; rb += K5_R) {
         const int nr = min(K5_R, r1 - rb);
         for (int i = threadIdx.x; i < K5_R * K5_T; i += K5_T * K5_T) {
@@ -189,23 +189,22 @@ __global__ void __launch_bounds__(K5_T * K5_T) k_allele_pair_prod(const double* 
         if (mine) {
             for (int rr = 0; rr < nr; rr++) {
                 const double t = __dadd_rn(sA[rr][ty], sB[rr][tx]);
-                bad |= !(t > 1.0e-300);
-                acc = __dmul_rn(acc, t);
-                const int hi = __double2hiint(acc);
-                esum += ((hi >> 20) & 0x7ff) - 1023;
-                acc = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(acc));
+                if (t > 1.0e-300) {
+                    acc = __dmul_rn(acc, t);
+                    const int hi = __double2hiint(acc);
+                    esum += ((hi >> 20) & 0x7ff) - 1023;
+                    acc = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(acc));
+                } else {      // both exponentials vanished: this term from the log-likelihoods, relative to what the closing formula adds per read
+                    const size_t row = (size_t)(rb + rr) * Cpad;
+                    extra = __dadd_rn(extra, __dadd_rn(log_avg_dev(LLt[row + c1], LLt[row + c2]), -__dadd_rn(rowmax[rb + rr], c_ty.log_half)));
+                }
                 sm += min(mA[rr][ty], mB[rr][tx]);
             }
         }
         __syncthreads();
     }
     if (mine) {
-        double pl;
-        if (!bad) pl = __dadd_rn(__dadd_rn(*msum, __dmul_rn((double)(r1 - r0), c_ty.log_half)), __dadd_rn(__dmul_rn((double)esum, c_ty.log_two), log(acc)));
-        else {   // a vanished term: this pair term by term, as the reference computes it
-            pl = 0.0;
-            for (int r = r0; r < r1; r++) pl = __dadd_rn(pl, log_avg_dev(LLt[(size_t)r * Cpad + c1], LLt[(size_t)r * Cpad + c2]));
-        }
+        const double pl = __dadd_rn(__dadd_rn(__dadd_rn(*msum, __dmul_rn((double)(r1 - r0), c_ty.log_half)), __dadd_rn(__dmul_rn((double)esum, c_ty.log_two), log(acc))), extra);
         const size_t idx = (size_t)c1 * C - (size_t)c1 * (c1 - 1) / 2 + (size_t)(c2 - c1);
         pair_ll[idx] = pl; pair_mavg[idx] = (colsum[c1] + colsum[c2]) / 2.0; pair_mmin[idx] = (double)sm;
     }
@@ -216,7 +215,7 @@ cudaError_t launch_allele_pair_prod(const double* LLt, const int32_t* mmT, int32
     if (r1 > r0) k_read_exp_shift<<<(unsigned)(((size_t)(r1 - r0) * 32 + 127) / 128), 128, 0, st>>>(LLt, C, Cpad, r0, r1, Et, rowmax);
     k_typing_col_sums<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(mmT, rowmax, C, Cpad, r0, r1, colsum, msum);
     const unsigned nt = (unsigned)((C + K5_T - 1) / K5_T);
-    k_allele_pair_prod<<<dim3(nt, nt), K5_T * K5_T, 0, st>>>(LLt, Et, mmT, colsum, msum, C, Cpad, r0, r1, pair_ll, pair_mavg, pair_mmin);
+    k_allele_pair_prod<<<dim3(nt, nt), K5_T * K5_T, 0, st>>>(LLt, Et, mmT, colsum, msum, rowmax, C, Cpad, r0, r1, pair_ll, pair_mavg, pair_mmin);
     return cudaGetLastError();
 }
 
