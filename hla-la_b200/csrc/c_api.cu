@@ -2,6 +2,7 @@
 #include "../../include/hlala_b200.h"
 #include "../host/prg_graph.h"
 #include "../host/dp_pack.h"
+#include "../host/insert_size.h"
 #include "extend_lean.h"
 #include "chain_params.h"
 #include "align_kernels.h"
@@ -1142,6 +1143,50 @@ int hlala_bam_batch_stats(const hlala_bam_batch_t* B, int64_t counts[4], double*
     return 0;
 }
 void hlala_bam_batch_free(hlala_bam_batch_t* B) { delete B; }
+
+// ---- the reference's insert-size estimate (processBAM::estimateInsertSize, processBAM.cpp:1071-1181)
+int hlala_bam_insert_size_sample(const hlala_bam_batch_t* B, hlala_seed_batch_t* view, const int32_t** loaded_contigs, int32_t* n_loaded) {
+    if (!B || !view) return fail(HLALA_E_ARG, "hlala_bam_insert_size_sample: null argument");
+    const BamBatch::Sample& S = B->b.is_sample;
+    memset(view, 0, sizeof *view);
+    view->n_reads = (int64_t)S.read_off.size() - 1; if (view->n_reads < 0) view->n_reads = 0;
+    view->read_off = S.read_off.data(); view->bases = S.bases.data(); view->quals = S.quals.data(); view->chain_off = S.chain_off.data();
+    view->chain_contig = S.chain_contig.data(); view->chain_pos = S.chain_pos.data(); view->chain_flag = S.chain_flag.data(); view->chain_as = S.chain_as.data();
+    view->cigar_off = S.cigar_off.data(); view->cigar = S.cigar.data();
+    if (loaded_contigs) *loaded_contigs = S.loaded_contigs.data(); if (n_loaded) *n_loaded = (int32_t)S.loaded_contigs.size();
+    return 0;
+}
+int hlala_insert_size_from_levels(const hlala_graph_t* g, int64_t n_pairs, const int32_t* first_level, const int32_t* last_level, const uint8_t* reverse,
+                                  const int32_t* loaded_contigs, int32_t n_loaded, double* mean, double* sd, int64_t* used, int64_t* skipped) {
+    if (!g || !first_level || !last_level || !reverse || !mean || !sd) return fail(HLALA_E_ARG, "hlala_insert_size_from_levels: null argument");
+    return guarded([&]() { InsertSizeEstimate e = estimate_insert_size(g->h, n_pairs, first_level, last_level, reverse, loaded_contigs, n_loaded);
+        *mean = e.mean; *sd = e.sd; if (used) *used = e.used; if (skipped) *skipped = e.skipped; return 0; });
+}
+int hlala_bam_insert_size(hlala_graph_t* g, const hlala_bam_batch_t* B, int32_t max_columns, double* mean, double* sd, int64_t* used, int64_t* skipped) {
+    if (!g || !B || !mean || !sd) return fail(HLALA_E_ARG, "hlala_bam_insert_size: null argument");
+    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
+    if (max_columns < 32 || max_columns > 2040) return fail(HLALA_E_ARG, "max_columns must be in [32, 2040]");
+    hlala_seed_batch_t v; const int32_t* loaded = nullptr; int32_t n_loaded = 0;
+    if (int rc = hlala_bam_insert_size_sample(B, &v, &loaded, &n_loaded)) return rc;
+    if (v.n_reads < 2) return fail(HLALA_E_INVARIANT, "insert size: the BAM holds no complete read pair in its first 4000 read names");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(g->device)); cudaStream_t st = 0;
+        // the primary records of the sample through the chain kernels and the extension DP, every chain aligned (one chain per read)
+        Pipeline pl; pl.scratch_budget = (size_t)1 << 62; pl.allow_env_budget = false; pl.dedup = false; pl.prepare(g, v, max_columns, st);
+        pl.begin_run(st); pl.fork_lanes(st);
+        if (pl.wave_pair.size() > 1) pl.run_chains_wave(0, *pl.lanes[0]);
+        pl.join_lanes(st);
+        const int32_t nc = pl.pb.n_chains; std::vector<int32_t> status((size_t)nc), fl((size_t)nc), ll((size_t)nc);
+        pl.cs.status.download(status.data(), (size_t)nc, st); pl.cs.first_level.download(fl.data(), (size_t)nc, st); pl.cs.last_level.download(ll.data(), (size_t)nc, st);
+        CUDA_OK(cudaStreamSynchronize(st));
+        std::vector<uint8_t> rev((size_t)nc);
+        for (int32_t c = 0; c < nc; c++) { if (status[(size_t)c] != CH_OK) return fail(status[(size_t)c] < 0 ? status[(size_t)c] : HLALA_E_INVARIANT, "insert size: a primary record of the sample could not be aligned (status " + std::to_string(status[(size_t)c]) + ")");
+            rev[(size_t)c] = (v.chain_flag[c] & 0x10) ? 1 : 0; }     // slot == chain: one chain per read
+        InsertSizeEstimate e = estimate_insert_size(g->h, v.n_reads / 2, fl.data(), ll.data(), rev.data(), loaded, n_loaded);
+        *mean = e.mean; *sd = e.sd; if (used) *used = e.used; if (skipped) *skipped = e.skipped;
+        return 0;
+    });
+}
 
 void hlala_graph_release_workspace(hlala_graph_t* g) { if (!g) return; std::lock_guard<std::mutex> lock(g->ws_mu); g->ws.reset(); }
 

@@ -154,6 +154,48 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
         if (it == gid.end()) { g = (int32_t)gname.size(); gid.emplace(nm, g); gname.push_back(nm); gcount.push_back(0); } else g = it->second;
         rec_gid[i] = g; gcount[(size_t)g]++; out.records_used++;
     }
+    // ---- the insert-size sample (see bam_reader.h): replay of extractSeeds(4000) over the kept records
+    {
+        std::vector<uint32_t> scan; scan.reserve((size_t)out.records_used); for (size_t i = 0; i < NR; i++) if (keep[i]) scan.push_back((uint32_t)i);
+        std::vector<int32_t> contig_rank(contig_names.size());      // byte order of the contig names = iteration order of the reference's interval map
+        { std::vector<int32_t> o(contig_names.size()); for (size_t i = 0; i < o.size(); i++) o[i] = (int32_t)i; std::sort(o.begin(), o.end(), [&](int32_t x, int32_t y) { return contig_names[(size_t)x] < contig_names[(size_t)y]; }); for (size_t k = 0; k < o.size(); k++) contig_rank[(size_t)o[k]] = (int32_t)k; }
+        std::stable_sort(scan.begin(), scan.end(), [&](uint32_t x, uint32_t y) { return contig_rank[(size_t)recs[x].ref] < contig_rank[(size_t)recs[y].ref]; });   // stable: file order inside a contig
+        struct St { int32_t first1 = -1, first2 = -1; bool prim1 = false, prim2 = false; };   // first primary record of either mate, in scan order
+        std::vector<St> state(gname.size()); std::vector<uint8_t> seen(gname.size(), 0); std::vector<uint8_t> loaded(contig_names.size(), 0);
+        // The reference leaves the record loop of the CURRENT interval when both thresholds are met (processBAM.cpp:672-676) but then moves on to the next
+        // interval (:691-693 set tryAgain again): once the thresholds hold, every later contig still contributes its first record (and gets its translation
+        // loaded) before the test fires again. Reproduced, because those records can complete a pair and those translations anchor the distances.
+        long long included = 0, included_complete = 0; const long long want = 4000; int32_t skip_contig = -1;
+        for (uint32_t i : scan) {
+            const Rec& r = recs[i];
+            if (r.ref == skip_contig) continue;
+            const int32_t g = rec_gid[i]; St& s = state[(size_t)g];
+            const bool first_mate = (r.flag & 0x40) != 0, primary = !(r.flag & 0x100);
+            if (first_mate) { if (primary && s.first1 < 0) s.first1 = (int32_t)i; s.prim1 = s.prim1 || primary; } else { if (primary && s.first2 < 0) s.first2 = (int32_t)i; s.prim2 = s.prim2 || primary; }
+            loaded[(size_t)r.ref] = 1;
+            if (!seen[(size_t)g]) { seen[(size_t)g] = 1; included++; }
+            if (s.prim1 && s.prim2) included_complete++;
+            if (included >= want && included_complete >= want / 2) skip_contig = r.ref;     // the rest of this contig is not read
+        }
+        BamBatch::Sample& S = out.is_sample; S = BamBatch::Sample();
+        for (size_t c = 0; c < loaded.size(); c++) if (loaded[c]) S.loaded_contigs.push_back((int32_t)c);
+        std::vector<int32_t> order; for (size_t g = 0; g < gname.size(); g++) if (seen[g]) { S.names_seen++; if (state[g].prim1 && state[g].prim2) order.push_back((int32_t)g); else S.incomplete++; }
+        std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { const NameRef& a = gname[(size_t)x]; const NameRef& b = gname[(size_t)y]; const int c = memcmp(a.p, b.p, std::min(a.n, b.n)); return c < 0 || (c == 0 && a.n < b.n); });
+        static const char SEQ16s[] = "=ACMGRSVTWYHKDBN";
+        S.read_off.assign(1, 0); S.chain_off.assign(1, 0); S.cigar_off.assign(1, 0);
+        for (int32_t g : order) {
+            S.pair_name.emplace_back(gname[(size_t)g].p, gname[(size_t)g].n);
+            for (int m = 0; m < 2; m++) {
+                const Rec& c = recs[(size_t)(m ? state[(size_t)g].first2 : state[(size_t)g].first1)];
+                for (int32_t k = 0; k < c.l_seq; k++) { const uint8_t b = d[c.seq_at + (size_t)k / 2]; S.bases.push_back((uint8_t)SEQ16s[(k & 1) ? (b & 15) : (b >> 4)]); }
+                const uint8_t* q = &d[c.seq_at + (size_t)(c.l_seq + 1) / 2]; for (int32_t k = 0; k < c.l_seq; k++) S.quals.push_back((uint8_t)(q[k] + 33));
+                S.read_off.push_back((int64_t)S.bases.size());
+                S.chain_contig.push_back(c.ref); S.chain_pos.push_back(c.pos); S.chain_flag.push_back(c.flag); S.chain_as.push_back(c.as);
+                for (uint32_t k = 0; k < c.n_cigar; k++) S.cigar.push_back(le32(&d[c.seq_at] - 4ull * c.n_cigar + 4ull * k));
+                S.cigar_off.push_back((int32_t)S.cigar.size()); S.chain_off.push_back((int32_t)S.chain_contig.size());
+            }
+        }
+    }
     const size_t NG = gname.size(); out.names_seen = (int64_t)NG;
     std::vector<int64_t> goff(NG + 1, 0); for (size_t g = 0; g < NG; g++) goff[g + 1] = goff[g] + gcount[g];
     std::vector<uint32_t> grec((size_t)goff[NG]); { std::vector<int64_t> at(goff.begin(), goff.end() - 1); for (size_t i = 0; i < NR; i++) if (keep[i]) grec[(size_t)at[(size_t)rec_gid[i]]++] = (uint32_t)i; }   // file order inside a group

@@ -27,7 +27,19 @@ struct BamBatch {
     std::vector<int32_t> cigar_off; std::vector<uint32_t> cigar;
     // bookkeeping the reference prints (processBAM.cpp:858-859, 2386)
     int64_t records = 0, records_used = 0, names_seen = 0, pairs_incomplete = 0;
-    double tlen_mean = 0, tlen_sd = 0; int64_t tlen_n = 0;   // gap between the mates of properly oriented primary pairs (insert-size estimate)
+    double tlen_mean = 0, tlen_sd = 0; int64_t tlen_n = 0;   // gap between the mates of properly oriented primary pairs (a plain statistic of the BAM; NOT the reference's estimate)
+    // The sample processBAM::estimateInsertSize aligns (processBAM.cpp:1071-1181 over extractSeeds(4000), :521-700): records are scanned contig by contig
+    // in byte order of the contig NAMES (std::map of intervals), file order inside a contig, until 4000 read names have been seen and 2000 records
+    // arrived at a then-complete pair (plus the first record of every later contig: the reference only leaves the current interval); of the pairs complete at that point, in name order, the first primary record of either mate (each with its
+    // own SEQ/QUAL). One chain per read. is_loaded_contigs: contigs whose translation the reference has loaded by then (their anchors are the only
+    // ones its distance computation sees, :836, :4441-4456).
+    struct Sample {
+        std::vector<std::string> pair_name;
+        std::vector<int64_t> read_off; std::vector<uint8_t> bases, quals;
+        std::vector<int32_t> chain_off, chain_contig, chain_pos, chain_as; std::vector<uint16_t> chain_flag;
+        std::vector<int32_t> cigar_off; std::vector<uint32_t> cigar;
+        std::vector<int32_t> loaded_contigs; int64_t names_seen = 0, incomplete = 0;
+    } is_sample;
 };
 
 // contig_names: BAM reference name of every PRG contig in sequences.txt order (FlatGraph::contig_bam_name); contig_len: their lengths.

@@ -78,8 +78,8 @@ static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     phase("BAM read, records selected and grouped");
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
-    if (a.count("insertSizeMean")) is_mean = atof(a["insertSizeMean"].c_str());
-    if (a.count("insertSizeSD")) is_sd = atof(a["insertSizeSD"].c_str());
+    if (a.count("insertSizeMean") && a.count("insertSizeSD")) { is_mean = atof(a["insertSizeMean"].c_str()); is_sd = atof(a["insertSizeSD"].c_str()); }
+    else { int64_t used = 0, skipped = 0; if (hlala_bam_insert_size(graphs[0], bam, maxcol, &is_mean, &is_sd, &used, &skipped)) return die("estimating the insert size"); }
     const int64_t n_pairs = batch.n_reads / 2;
     fprintf(stdout, "hlala-b200: %lld records, %lld used, %lld pairs to align on %d GPUs; insert size %g +- %g\n", (long long)counts[0], (long long)counts[1], (long long)n_pairs, n_gpus, is_mean, is_sd);
     if (n_pairs < n_gpus) { fprintf(stderr, "hlala-b200: fewer read pairs than GPUs\n"); return 1; }
@@ -164,8 +164,12 @@ int main(int argc, char** argv) {
     phase("BAM read, records selected and grouped");
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
-    if (a.count("insertSizeMean")) is_mean = atof(a["insertSizeMean"].c_str());
-    if (a.count("insertSizeSD")) is_sd = atof(a["insertSizeSD"].c_str());
+    if (a.count("insertSizeMean") && a.count("insertSizeSD")) { is_mean = atof(a["insertSizeMean"].c_str()); is_sd = atof(a["insertSizeSD"].c_str()); }
+    else {   // what HLA-LA.cpp:788 does: processBAM::estimateInsertSize on the first ~4000 read names
+        int64_t used = 0, skipped = 0;
+        if (hlala_bam_insert_size(g, bam, maxcol, &is_mean, &is_sd, &used, &skipped)) return die("estimating the insert size");
+        is_n = used - skipped; phase("insert size estimated (primary records of the first 4000 read names aligned)");
+    }
     fprintf(stdout, "hlala-b200: %lld records, %lld used, %lld read names, %lld incomplete pairs, %lld pairs to align; insert size %g +- %g (from %lld pairs)\n",
             (long long)counts[0], (long long)counts[1], (long long)counts[2], (long long)counts[3], (long long)(batch.n_reads / 2), is_mean, is_sd, (long long)is_n);
     if (batch.n_reads == 0) { fprintf(stderr, "hlala-b200: no complete read pair on the PRG contigs\n"); return 1; }

@@ -247,6 +247,19 @@ int hlala_bam_batch_view(const hlala_bam_batch_t* b, hlala_seed_batch_t* view, c
 int hlala_bam_batch_stats(const hlala_bam_batch_t* b, int64_t counts[4], double* is_mean, double* is_sd, int64_t* is_n);
 void hlala_bam_batch_free(hlala_bam_batch_t* b);
 
+/* processBAM::estimateInsertSize (mapper/processBAM.cpp:1071-1181; histogram statistics :991-1069): the insert-size mean / sd the reference
+ * passes to alignReads_and_inferHLA (HLA-LA.cpp:788-799). hlala_bam_read selects the sample the way extractSeeds(4000) does (contigs in
+ * byte order of their names, file order inside; 4000 read names and 2000 records at complete pairs); hlala_bam_insert_size aligns the first
+ * primary record of either mate of every complete pair of it on the GPU (seed projection + extension) and applies the reference's strand
+ * rule, underlying-sequence distances (only contigs whose translation the reference has loaded by then) and weighted histogram.
+ * used / skipped: pairs examined / pairs whose strands are not valid. */
+int hlala_bam_insert_size(hlala_graph_t* g, const hlala_bam_batch_t* b, int32_t max_columns, double* mean, double* sd, int64_t* used, int64_t* skipped);
+/* The two halves of the above for callers (and tests) that hold the alignments already: the sample as a seed batch (one chain per read,
+ * pairs in name order) with the loaded contigs, and the host arithmetic on per-read first / last levels and strands. */
+int hlala_bam_insert_size_sample(const hlala_bam_batch_t* b, hlala_seed_batch_t* view, const int32_t** loaded_contigs, int32_t* n_loaded);
+int hlala_insert_size_from_levels(const hlala_graph_t* g, int64_t n_pairs, const int32_t* first_level, const int32_t* last_level, const uint8_t* reverse,
+                                  const int32_t* loaded_contigs, int32_t n_loaded, double* mean, double* sd, int64_t* used, int64_t* skipped);
+
 /* Let the session own the per-level coverage histogram (processBAM.cpp:2411-2426): zeroed at every hlala_session_run that is given no
  * bases_per_level_dev, copied out as int32[n_levels-1]. */
 int hlala_session_set_coverage(hlala_session_t* s, int on);

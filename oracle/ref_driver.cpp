@@ -69,6 +69,10 @@ public:
     std::unordered_map<const Edge*, int> edge_ord;
     std::vector<std::string> contig_names;   // batch contig index -> BAM reference name
 
+    std::vector<int> all_ids;
+    void forget_mappings() { extendedReferenceGenome_levelTranslation.clear(); for (auto& m : graphLevel_2_underlyingSequencePositions) m.clear(); }
+    void reload_mappings() { forget_mappings(); for (int id : all_ids) _loadMapping(id); }
+    std::string current_bam() const { return _currentBAM; }
     void finish_open(const std::string& dir) {
         // contigs in sequences.txt order = RefID order of the synthetic "BAM"
         std::ifstream s(dir + "/sequences.txt"); std::string line; std::getline(s, line);
@@ -82,6 +86,7 @@ public:
             BamTools::BamReader::shim_refs().push_back(BamTools::RefData(name, (int)PRGonlyReferenceGenomeSequences.at(name).length()));
         }
         initBAM(dir + "/sequences.txt", false, false);
+        all_ids = ids;
         for (int id : ids) _loadMapping(id);   // all contigs up-front (lazy loading is order-dependent state)
         nodes.assign(g->Nodes.begin(), g->Nodes.end());
         edges.assign(g->Edges.begin(), g->Edges.end());
@@ -428,6 +433,28 @@ int hlala_ref_extract_seeds(void* h, long long n_rec, const char* names_blob /* 
         }
         R.clear(); if (extra_ref) BamTools::BamReader::shim_refs().pop_back();
         *n_seeds = (long long)g_seeds.names.size(); *n_out_recs = (long long)g_seeds.recs.size();
+        return 0; });
+}
+// ---- the reference's own estimateInsertSize (processBAM.cpp:1071-1181) over in-memory records (coordinate-sorted, like the indexed BAM it requires).
+// The translation tables are loaded lazily by the scan itself, as in a fresh run (the distances only see contigs loaded by then); all are reloaded afterwards.
+int hlala_ref_estimate_insert_size(void* h, long long n_rec, const char* names_blob, const int32_t* ref, const int32_t* pos, const uint16_t* flag, const int32_t* as,
+                                   const int32_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off, const uint8_t* seq, const uint8_t* qual, double* mean, double* sd) {
+    Driver* d = (Driver*)h;
+    return guarded([&]() {
+        std::vector<BamTools::BamAlignment>& R = BamTools::BamReader::shim_records(); R.clear();
+        const char* nm = names_blob;
+        for (long long i = 0; i < n_rec; i++) {
+            BamTools::BamAlignment a; a.Name = nm; nm += a.Name.size() + 1;
+            a.RefID = ref[i]; a.Position = pos[i]; a.AlignmentFlag = flag[i]; a.shim_int_tags["AS"] = as[i];
+            for (int32_t k = cigar_off[i]; k < cigar_off[i + 1]; k++) a.CigarData.push_back(BamTools::CigarOp("MIDNSHP=X"[cigar[k] & 15], (uint32_t)(cigar[k] >> 4)));
+            a.QueryBases.assign((const char*)seq + seq_off[i], (size_t)(seq_off[i + 1] - seq_off[i])); a.Qualities.assign((const char*)qual + seq_off[i], (size_t)(seq_off[i + 1] - seq_off[i])); a.Length = (int32_t)a.QueryBases.size();
+            R.push_back(a);
+        }
+        d->forget_mappings();
+        std::pair<double, double> e = d->estimateInsertSize(d->current_bam(), false);
+        d->reload_mappings();
+        R.clear();
+        *mean = e.first; *sd = e.second;
         return 0; });
 }
 // names: caller buffer of name_bytes, zero-terminated names back to back

@@ -151,6 +151,12 @@ class Ref:
         out_names = buf.raw.split(b"\0")[:ns.value]
         return [x.decode() for x in out_names], comp[:ns.value], n1[:ns.value], n2[:ns.value], recs[:nr.value]
 
+    def estimate_insert_size(self, names, ref, pos, flag, as_, cigar_off, cigar, seq_off, seq, qual):
+        """the unmodified processBAM::estimateInsertSize over coordinate-sorted in-memory records (SEQ / QUAL+33 per record, may be empty for secondaries)"""
+        blob = b"".join(n.encode() + b"\0" for n in names); m = C.c_double(); s = C.c_double()
+        self._chk(self.lib.hlala_ref_estimate_insert_size(self.h, C.c_longlong(len(names)), blob, p(ref), p(pos), p(flag), p(as_), p(cigar_off), p(cigar), p(seq_off), p(seq), p(qual), C.byref(m), C.byref(s)))
+        return m.value, s.value
+
     # ---- k-mer seeding (GraphAndEdgeIndex)
     def kmer_index(self, k):
         L = self.lib; L.hlala_ref_kmer_index.restype = C.c_void_p
@@ -530,6 +536,41 @@ class Product:
             return b, [names[i].decode() for i in range(nr // 2)], dict(records=cnt[0], used=cnt[1], names=cnt[2], incomplete=cnt[3], is_mean=m.value, is_sd=sd.value, is_n=n.value)
         finally:
             L.hlala_bam_batch_free(h)
+
+    def bam_insert_size(self, path, cap=640, gpu=False, threads=0):
+        """the reference's insert-size sample of a BAM (hlala_bam_insert_size_sample) as a batch dict + loaded contig indices; with gpu=True also
+        (mean, sd, used, skipped) of hlala_bam_insert_size"""
+        L = self.lib; h = C.c_void_p()
+        self._chk(L.hlala_bam_read(self.g, path.encode(), C.c_int(threads), C.byref(h)))
+        try:
+            v = SeedBatch(); lc = C.POINTER(C.c_int32)(); nlc = C.c_int32()
+            self._chk(L.hlala_bam_insert_size_sample(h, C.byref(v), C.byref(lc), C.byref(nlc)))
+            nr = v.n_reads; dts = dict(read_off=np.int64, bases=np.uint8, quals=np.uint8, chain_off=np.int32, chain_contig=np.int32, chain_pos=np.int32, chain_flag=np.uint16, chain_as=np.int32, cigar_off=np.int32, cigar=np.uint32)
+
+            def arr(key, n):
+                ptr = getattr(v, key)
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dts[key]))), shape=(n,)).copy() if n and ptr else np.zeros(n, dts[key])
+            b = {"read_off": arr("read_off", nr + 1)}
+            nb = int(b["read_off"][-1]); b["bases"] = arr("bases", nb); b["quals"] = arr("quals", nb)
+            b["chain_off"] = arr("chain_off", nr + 1); nc = int(b["chain_off"][-1])
+            for k in ("chain_contig", "chain_pos", "chain_flag", "chain_as"):
+                b[k] = arr(k, nc)
+            b["cigar_off"] = arr("cigar_off", nc + 1); b["cigar"] = arr("cigar", int(b["cigar_off"][-1]))
+            loaded = np.array([lc[i] for i in range(nlc.value)], np.int32)
+            est = None
+            if gpu:
+                m = C.c_double(); sd = C.c_double(); used = C.c_int64(); sk = C.c_int64()
+                self._chk(L.hlala_bam_insert_size(self.g, h, C.c_int32(cap), C.byref(m), C.byref(sd), C.byref(used), C.byref(sk)))
+                est = (m.value, sd.value, used.value, sk.value)
+            return b, loaded, est
+        finally:
+            L.hlala_bam_batch_free(h)
+
+    def insert_size_from_levels(self, first_level, last_level, reverse, loaded):
+        m = C.c_double(); sd = C.c_double(); used = C.c_int64(); sk = C.c_int64()
+        fl = np.ascontiguousarray(first_level, np.int32); ll = np.ascontiguousarray(last_level, np.int32); rv = np.ascontiguousarray(reverse, np.uint8); lc = np.ascontiguousarray(loaded, np.int32)
+        self._chk(self.lib.hlala_insert_size_from_levels(self.g, C.c_int64(len(fl) // 2), p(fl), p(ll), p(rv), p(lc), C.c_int32(len(lc)), C.byref(m), C.byref(sd), C.byref(used), C.byref(sk)))
+        return m.value, sd.value, used.value, sk.value
 
     # ---- k-mer seeding
     def kmer_index(self, k):

@@ -84,6 +84,25 @@ def test_ingest_matches_the_references_extractSeeds2():
     assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not built on this box")
+def test_insert_size_estimate_matches_the_references_estimateInsertSize():
+    """sample selection (incl. the reference's habit of reading on after its thresholds are met), lazily loaded translations, strand rule, underlying-sequence
+    distances and histogram statistics against the unmodified processBAM::estimateInsertSize (own process); alignments from the oracle restatement"""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "insert_size_ref_compare.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not built on this box")
+def test_insert_size_estimate_on_the_gpu_matches_the_reference():
+    """hlala_bam_insert_size (what the command line uses when no --insertSizeMean/--insertSizeSD is given): the sample's primary records through the CUDA chain
+    kernels and the extension DP, equal to the unmodified processBAM::estimateInsertSize"""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "insert_size_ref_compare.py"), "--gpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "GPU estimate identical" in r.stdout, r.stdout[-3000:]
+
+
 def test_cli_prepare_graph(dataset):
     """--action prepareGraph (HLA-LA.cpp:1341): needs no GPU; builds the flat-array cache next to graph.txt"""
     d, _b, _mu, _sd = dataset("small")
