@@ -254,6 +254,45 @@ def stage_typing(args, root, H):
     return res
 
 
+def stage_long_reads(args, root, H):
+    """BASELINE.json configs[3]: long-read mode, 50 k synthetic 8 kb reads on one B200 through hlala_align_long_reads (host buffers in, per-read results and
+    per-level coverage out); the unmodified processBAM::alignOneLongRead on the first reads of the same batch, same PRG, one thread (what the reference does).
+    The reference has no DP in this mode (the seed is padded to the read, processBAM.cpp:3728-3731), so neither has the GPU path."""
+    d = small_prg(args, root)
+    n, L, cap = args.long_reads, 8000, 10240
+    b = H.synth_reads(d, os.path.join(d, "long_stage.bin"), pairs=n, len=L, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=400, gene_frac=0.2, seed=0xB200)
+    P = H.Product(d); P.to_gpu(int(os.environ.get("LOCAL_RANK", "0")))
+    nr = len(b["read_off"]) - 1
+    o = dict(pair_mapq=np.zeros(nr), read_mapq=np.zeros(nr), read_reverse=np.zeros(nr, np.uint8), chosen_slot=np.zeros(nr, np.int32), pair_ll=np.zeros(nr), n_cols=np.zeros(nr, np.int32))
+    po = H.PairOut(); po.max_columns = cap
+    for k in o:
+        setattr(po, k, o[k].ctypes.data)
+    sb = H.make_batch_struct(b); bpl = np.zeros(P.dims()["n_levels"], np.int32); ts = []
+    for _ in range(3):
+        t = time.perf_counter(); P._chk(P.lib.hlala_align_long_reads(P.g, C.byref(sb), C.byref(po), H.p(bpl))); ts.append(time.perf_counter() - t)
+    levels, genes, alleles = sample_dims(args)
+    out = dict(workload="%d single reads x %d bases (3 %% indels, half clipped by up to 400 bases, %.1f BAM records per read), PRG of %d levels / %d haplotypes / %d gene block(s) x %d alleles, max_columns %d"
+               % (nr, L, len(b["chain_contig"]) / float(nr), levels, args.haps, genes, alleles, cap), call_s=min(ts[1:]), reads_per_s_e2e=nr / min(ts[1:]), bases_per_s_e2e=nr * L / min(ts[1:]),
+               reads_with_mapq_lt_1=int((o["pair_mapq"] < 1).sum()), sum_columns=int(o["n_cols"].sum()), sum_ll=float(o["pair_ll"].sum()))
+    P.close()
+    if os.path.exists(H.LIB_REF):
+        try:
+            k = min(args.long_ref_reads, nr); nch = int(b["chain_off"][k]); ncg = int(b["cigar_off"][nch]); nb = int(b["read_off"][k])
+            sbt = dict(read_off=b["read_off"][:k + 1].copy(), bases=b["bases"][:nb].copy(), quals=b["quals"][:nb].copy(), chain_off=b["chain_off"][:k + 1].copy(),
+                       chain_contig=b["chain_contig"][:nch].copy(), chain_pos=b["chain_pos"][:nch].copy(), chain_flag=b["chain_flag"][:nch].copy(), chain_as=b["chain_as"][:nch].copy(),
+                       cigar_off=b["cigar_off"][:nch + 1].copy(), cigar=b["cigar"][:ncg].copy())
+            if d in _REF:
+                want = H.quiet(_REF[d].long_reads, sbt, cap, 1, False)
+            else:
+                want = H._ref_subprocess(d, sbt, 0.0, 1.0, cap, "long_reads")
+            sec = float(want["seconds"]) if "seconds" in want else None
+            same = bool(np.array_equal(want["n_cols"], o["n_cols"][:k]) and np.array_equal(want["read_ll"], o["pair_ll"][:k]) and np.allclose(want["read_mapq"], o["pair_mapq"][:k], rtol=0, atol=1e-12))
+            out.update(reference_reads=k, reference_seconds_1_thread=sec, reference_reads_per_s_1_thread=(k / sec) if sec else None, sample_identical_to_reference=same)
+        except Exception as e:
+            out["reference_error"] = str(e)[:200]
+    return out
+
+
 def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels):
     """BASELINE.json configs[2] on N GPUs: --strong-pairs pairs in total, sharded by pair across the ranks (graph replicated). Timed per rank, max over ranks:
     alignment of the shard (columns kept) -> all-reduce of the per-level coverage -> extraction of the gene-overlapping pairs -> all-gather of those (small)
@@ -330,6 +369,8 @@ def main():
     ap.add_argument("--cpu-levels", type=int, default=294118, help="levels of the reference arm's PRG slice (default: levels / genes = one gene block, the bench PRG's density)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--stages", type=int, default=1, help="also time the k-mer seeding and typing stages (rank 0, N=1 only)")
+    ap.add_argument("--long-reads", type=int, default=50000, help="reads of the long-read stage (BASELINE.json configs[3]: 50 k x 8 kb)")
+    ap.add_argument("--long-ref-reads", type=int, default=100, help="reads of that batch the reference's alignOneLongRead is timed on (1 thread)")
     ap.add_argument("--strong-single", type=int, default=0, help="run the strong-scaling leg at N = 1 too (its baseline; off by default to keep the default run short)")
     ap.add_argument("--strong-pairs", type=int, default=4000000, help="N > 1: total pairs of the strong-scaling leg (BASELINE.json configs[2]: ~4M pairs sharded over the GPUs, typing with one NCCL all-reduce per locus); 0 = skip")
     args = ap.parse_args()
@@ -570,7 +611,7 @@ def main():
     stages = None
     if args.stages and n_gpus == 1:
         stages = {}
-        for nm, fn in (("kmer_seeding", stage_kmer_seeding), ("typing", stage_typing)):
+        for nm, fn in (("kmer_seeding", stage_kmer_seeding), ("typing", stage_typing), ("long_reads", stage_long_reads)):
             try:
                 stages[nm] = fn(args, root, H)
             except Exception as e:   # a stage measurement must not cost the headline line

@@ -70,13 +70,14 @@ __device__ void finalize_chain(const ChainParams& P, const WarpSlab& S, int slot
     }
     __syncwarp();
     if (lane == 0) {
+        const ScoreTables& T = P.long_mode ? c_tables_long : c_tables;
         double ll = 0;
         for (int k = 0; k < n_total; k++) {
             switch (kind[k]) {
-            case 1: ll += c_tables.ins_term; break;                                                     // insertion (extensionAligner.cpp:119)
-            case 2: ll += c_tables.rate_deletion; break;                                                // deletion  (:163)
-            case 3: ll += c_tables.rate_match_mismatch; ll += c_tables.log_match[qv[k]]; break;         // (:125,139)
-            case 4: ll += c_tables.rate_match_mismatch; ll += c_tables.log_mismatch[qv[k]]; break;      // (:125,146)
+            case 1: ll += T.ins_term; break;                                                     // insertion (extensionAligner.cpp:119)
+            case 2: ll += T.rate_deletion; break;                                                // deletion  (:163)
+            case 3: ll += T.rate_match_mismatch; ll += T.log_match[qv[k]]; break;         // (:125,139)
+            case 4: ll += T.rate_match_mismatch; ll += T.log_mismatch[qv[k]]; break;      // (:125,146)
             default: break;                                                                             // gap against gap
             }
         }
@@ -126,8 +127,7 @@ __global__ void k_prepare(ChainParams P) {
 __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
-    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    WarpSlab S = slab_of(P, smem, warp, K1_WARPS);
     if (lane == 0) { mbar_init(S.mbar, 1); *S.mbar_phase = 0; }
     __syncwarp();
     const DevBatch& B = P.b;
@@ -315,8 +315,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_finish(ExtParams E) {
     extern __shared__ __align__(16) unsigned char smem[];
     const ChainParams& P = E.C; const DevGraph& G = P.g; const DevBatch& B = P.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
-    WarpSlab S = carve_slab(smem + (size_t)warp * slab, P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    WarpSlab S = slab_of(P, smem, warp, K1_WARPS);
     const int nw = gridDim.x * K1_WARPS;
     for (int pi = blockIdx.x * K1_WARPS + warp; pi < E.n_pending; pi += nw) {
         const int slot = P.pending_slots[pi];
@@ -356,10 +355,13 @@ __global__ void k_export_chain_columns(DevGraph G, int n_chains, int maxcol, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-cudaError_t upload_score_tables(const ScoreTables& t) { return cudaMemcpyToSymbol(c_tables, &t, sizeof(ScoreTables)); }
+cudaError_t upload_score_tables(const ScoreTables& t, const ScoreTables& t_long) {
+    cudaError_t e = cudaMemcpyToSymbol(c_tables, &t, sizeof(ScoreTables)); if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_tables_long, &t_long, sizeof(ScoreTables));
+}
 
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream) {
-    size_t slab = k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    size_t slab = P.gslab ? k1_gslab_smem_bytes(P.win_cap, P.wcap) : k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
     size_t smem = slab * K1_WARPS;
     {   // a function attribute belongs to the current device: set it on every launch (several GPUs may be driven from one process)
         cudaError_t e = cudaFuncSetAttribute(k_chain_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -374,6 +376,14 @@ cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t strea
     if (grid < 1) grid = 1;
     k_chain_seed<<<grid, K1_WARPS * 32, smem, stream>>>(P);
     return cudaGetLastError();
+}
+
+// warps a launch of the chain kernel can have resident with these capacities (ChainParams::gslab: one HBM slice per such warp)
+int chain_seed_max_warps(const ChainParams& P, int n_sm) {
+    size_t smem = (P.gslab ? k1_gslab_smem_bytes(P.win_cap, P.wcap) : k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap)) * K1_WARPS;
+    if (cudaFuncSetAttribute(k_chain_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int per_sm = 1; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_seed, K1_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return n_sm * per_sm * K1_WARPS;
 }
 
 cudaError_t launch_prepare(const ChainParams& P, cudaStream_t stream) {
@@ -487,7 +497,7 @@ cudaError_t launch_dp_task_bytes(const ExtParams& E, unsigned long long* out, cu
 
 cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
-    size_t smem = k1_slab_bytes(E.C.slab_cols, E.C.pool_cap, E.C.win_cap, E.C.wcap) * K1_WARPS;
+    size_t smem = (E.C.gslab ? k1_gslab_smem_bytes(E.C.win_cap, E.C.wcap) : k1_slab_bytes(E.C.slab_cols, E.C.pool_cap, E.C.win_cap, E.C.wcap)) * K1_WARPS;
     { cudaError_t e = cudaFuncSetAttribute(k_chain_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     int per_sm = 1; cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_finish, K1_WARPS * 32, smem);
     if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
@@ -497,23 +507,35 @@ cudaError_t launch_chain_finish(const ExtParams& E, int n_sm, cudaStream_t strea
     return cudaGetLastError();
 }
 
-template <class CFG, bool FROM_LIST> static cudaError_t launch_pair_tier(const PairParams& P, int n_sm, long long want_warps, cudaStream_t stream) {
-    const size_t smem = pair_slab_bytes<CFG>(P.maxcol) * K3_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(k_pair<CFG, FROM_LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
-    int per_sm = 1; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair<CFG, FROM_LIST>, K3_WARPS * 32, smem);
+// shared memory of a warp's pair slab; beyond PAIR_SMEM_SLAB_MAX per warp the slabs live in HBM (PairParams::gslab, long-read mode with thousands of columns)
+constexpr size_t PAIR_SMEM_SLAB_MAX = 100 * 1024;
+size_t pair_gslab_bytes(int maxcol, int tier) { size_t b = tier == 0 ? pair_slab_bytes<PairTier0>(maxcol) : pair_slab_bytes<PairTier1>(maxcol); return b > PAIR_SMEM_SLAB_MAX ? b : 0; }
+template <class CFG, bool FROM_LIST, bool UNPAIRED> static cudaError_t launch_pair_tier(const PairParams& P, int n_sm, long long want_warps, cudaStream_t stream) {
+    // the slab of a warp grows with max_columns: as many warps per CTA (<= K3_WARPS) as fit the shared memory of an SM
+    const bool in_hbm = P.gslab[FROM_LIST ? 1 : 0] != nullptr;
+    int warps = K3_WARPS; while (!in_hbm && warps > 1 && pair_slab_bytes<CFG>(P.maxcol) * (size_t)warps > 200 * 1024) warps /= 2;
+    const size_t smem = in_hbm ? 0 : pair_slab_bytes<CFG>(P.maxcol) * (size_t)warps;
+    cudaError_t e = cudaFuncSetAttribute(k_pair<CFG, FROM_LIST, UNPAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
+    int per_sm = 1; e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair<CFG, FROM_LIST, UNPAIRED>, warps * 32, smem);
     if (e != cudaSuccess) return e; if (per_sm < 1) per_sm = 1;
-    long long want = (want_warps + K3_WARPS - 1) / K3_WARPS;
-    int grid = (int)std::min<long long>(want, (long long)n_sm * per_sm); if (grid < 1) grid = 1;
-    k_pair<CFG, FROM_LIST><<<grid, K3_WARPS * 32, smem, stream>>>(P);
+    long long want = (want_warps + warps - 1) / warps;
+    long long cap = (long long)n_sm * per_sm; if (in_hbm) cap = std::min<long long>(cap, (long long)(P.gslab_warps / (unsigned long long)warps));
+    int grid = (int)std::min<long long>(want, cap); if (grid < 1) grid = 1;
+    k_pair<CFG, FROM_LIST, UNPAIRED><<<grid, warps * 32, smem, stream>>>(P);
     return cudaGetLastError();
 }
 // tier 0 over all pairs of the wave, then tier 1 (64 chains per read, 4096 combinations) over the pairs tier 0 queued; P.defer_count must be zero on entry
 cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream) {
     long long n_pairs = P.pair_end - P.pair_begin;
     if (n_pairs <= 0) return cudaSuccess;
-    cudaError_t e = launch_pair_tier<PairTier0, false>(P, n_sm, n_pairs, stream); if (e != cudaSuccess) return e;
+    if (P.unpaired) {
+        cudaError_t e = launch_pair_tier<PairTier0, false, true>(P, n_sm, n_pairs, stream); if (e != cudaSuccess) return e;
+        if (!P.defer_list) return cudaSuccess;
+        return launch_pair_tier<PairTier1, true, true>(P, n_sm, (long long)n_sm * K3_WARPS, stream);
+    }
+    cudaError_t e = launch_pair_tier<PairTier0, false, false>(P, n_sm, n_pairs, stream); if (e != cudaSuccess) return e;
     if (!P.defer_list) return cudaSuccess;
-    return launch_pair_tier<PairTier1, true>(P, n_sm, (long long)n_sm * K3_WARPS, stream);     // a handful of pairs at most: one CTA per SM pops them
+    return launch_pair_tier<PairTier1, true, false>(P, n_sm, (long long)n_sm * K3_WARPS, stream);     // a handful of pairs at most: one CTA per SM pops them
 }
 
 size_t dp_thread_scratch_bytes() { return dp_scratch_bytes(); }

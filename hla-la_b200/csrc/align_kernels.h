@@ -6,9 +6,11 @@
 namespace hlala {
 
 struct ChainParams; struct ExtParams; struct PairParams;
-cudaError_t upload_score_tables(const ScoreTables& t);
+cudaError_t upload_score_tables(const ScoreTables& t, const ScoreTables& t_long);
 cudaError_t launch_prepare(const ChainParams& P, cudaStream_t stream);
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream);
+int chain_seed_max_warps(const ChainParams& P, int n_sm);
+size_t pair_gslab_bytes(int maxcol, int tier);      // per-warp bytes of the pair kernel's HBM slab for this max_columns (0: the slab fits shared memory)
 cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream);
 cudaError_t launch_extend_warp(const ExtParams& E, int n_sm, int cfg, bool only_deferred, cudaStream_t stream);
 cudaError_t launch_extend_group(const ExtParams& E, int n_sm, cudaStream_t stream);

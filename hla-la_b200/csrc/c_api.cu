@@ -55,9 +55,10 @@ struct DevBuf {
 
 // Score tables with the reference's own arithmetic (Utilities::PhredToPCorrect Utilities.cpp:357-377,
 // extensionAligner::scoreOneAlignment extensionAligner.cpp:58-66,127-146), evaluated by the host libm once.
-ScoreTables make_score_tables() {
+ScoreTables make_score_tables(bool long_reads = false) {
     ScoreTables t;
     double rate_deletions = log(0.001), rate_insertions = log(0.001);
+    if (long_reads) { rate_deletions = log(0.075); rate_insertions = log(0.075); }      // extensionAligner.cpp:60-64
     t.rate_match_mismatch = log(1 - exp(rate_deletions) - exp(rate_insertions));
     t.rate_deletion = rate_deletions;
     t.ins_term = rate_insertions + log(1.0 / 4.0);
@@ -165,6 +166,7 @@ struct ChainScratch {   // per-chain results of the whole batch
 // lanes, so the low-occupancy tail of one wave's extension cascade overlaps the next wave's chain kernel and first DP tier.
 struct Lane {
     DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count, dp_tasks, dp_task_count, dp_task_bin, dp_task_hist, dp_sorted;
+    DevBuf pair_gslab[2];
     DevBuf pair_defer, pair_defer_count;   // pairs queued for the large tier of the pair kernel
     DevBuf ln_rec, ln_ahead;   // thread-per-extension tier: 16-byte cell records and the ahead table of every resident thread
     DevBuf ext_edge, ext_s, ext_n, ext_nlvl, ext_rc, dp_scratch, wd_scratch, gd_scratch; int32_t ext_cap = 0;
@@ -207,6 +209,7 @@ void chain_caps(int32_t maxcol, bool bt16, int tier, ChainParams& P) {
     long long pool_entries = std::max<long long>(4LL * maxcol, 2560);       // entries needed
     P.pool_cap = (int32_t)(bt16 ? (pool_entries + 1) / 2 : pool_entries);    // in 32-bit words when 16-bit entries are used
     P.win_cap = (int32_t)((std::max<long long>(2LL * maxcol, 512) + 3) & ~3LL);     // a multiple of 4 words (bulk copies are 16-byte granular)
+    if (maxcol > 2040) return;       // the slab of such chains lives in HBM (Pipeline::chain_params)
     while (k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap) * K1_WARPS > 220000 && P.win_cap > 256) P.win_cap /= 2;
     while (k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap) * K1_WARPS > 220000 && P.pool_cap > 512) P.pool_cap /= 2;
 }
@@ -245,6 +248,7 @@ struct Pipeline {
     bool scalar_dp_only = false;   // test hook: run every extension through the scalar kernel
     int32_t n_gd_groups = 0; bool group_dp = true; bool dp_trace = false;
     bool lean_big = false;
+    bool long_mode = false; DevBuf gslab; size_t gslab_bytes = 0;     // long-read mode (alignOneLongRead): one read per unit, no extension DP, chain buffers in HBM
     int32_t n_ln_threads = 0; bool lean_dp = true;   // first DP tier: one thread per extension (extend_lean.h); false: the 8-lane group kernel (A/B runs)
     DevBuf bpl_ws; std::vector<int32_t> bpl_host;   // per-level coverage of a host-buffer call
     DevBuf is_table, phred_thr; double is_mean = -1, is_sd = -1, is_pen = 0; int32_t is_dmin = 0, is_n = 0;
@@ -348,14 +352,21 @@ struct Pipeline {
         out[0] = n; out[1] = ck; out[2] = algo_fixed + chains_part;
     }
     // defaults of everything the test hooks (environment variables read in prepare) can change; a workspace kept across calls starts from them
-    void reset_config() { scratch_budget = 0; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
+    void reset_config() { long_mode = false; scratch_budget = 0; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
     void ensure_columns() {
         if (have_columns) return;
         size_t n = (size_t)std::max<int64_t>(pb.n_reads, 2) * maxcol;
         o_n_cols.alloc((size_t)std::max<int64_t>(pb.n_reads, 2) * 4); o_level.alloc(n * 4); o_edge.alloc(n * 4); o_gchar.alloc(n); o_schar.alloc(n); o_fromseed.alloc(n); o_mapq.alloc(n);
         have_columns = true;
     }
-    ChainParams chain_params(int tier, Lane& L) { ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, tier, P); P.do_extension = 1; cs.fill(P); L.fill(P); return P; }
+    ChainParams chain_params(int tier, Lane& L) {
+        ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, tier, P); P.do_extension = long_mode ? 0 : 1; P.long_mode = long_mode ? 1 : 0; cs.fill(P); L.fill(P);
+        if (tier == 1 && maxcol > 2040) {     // chains of thousands of columns: slab in HBM, one slice per resident warp
+            P.gslab = 1; P.win_cap = 4096; P.gslab_bytes = k1_gslab_bytes(P.slab_cols, P.pool_cap);
+            const int warps = chain_seed_max_warps(P, g->n_sm); gslab.alloc((size_t)std::max(warps, 1) * P.gslab_bytes); P.gslab_base = gslab.as<unsigned char>();
+        }
+        return P;
+    }
 
     void begin_run(cudaStream_t st) {
         launches = 0;
@@ -485,7 +496,11 @@ struct Pipeline {
         Q.pair_ll = pair_ll.as<double>(); Q.pair_status = pair_status.as<int32_t>();
         if (want_columns) { Q.out_n_cols = o_n_cols.as<int32_t>(); Q.out_level = o_level.as<int32_t>(); Q.out_edge = o_edge.as<int32_t>(); Q.out_gchar = o_gchar.as<uint8_t>(); Q.out_schar = o_schar.as<uint8_t>(); Q.out_fromseed = o_fromseed.as<uint8_t>(); Q.out_mapq = o_mapq.as<uint8_t>(); }
         Q.bases_per_level = bases_per_level_dev; Q.error_count = cs.error_count.as<int32_t>(); Q.digest = digest.as<unsigned long long>();
-        Q.defer_list = L.pair_defer.as<int32_t>(); Q.defer_count = L.pair_defer_count.as<int32_t>();
+        Q.defer_list = L.pair_defer.as<int32_t>(); Q.defer_count = L.pair_defer_count.as<int32_t>(); Q.unpaired = long_mode ? 1 : 0;
+        for (int t = 0; t < 2; t++) {     // thousands of columns per read: the per-warp pair slabs do not fit shared memory
+            const size_t per_warp = pair_gslab_bytes(maxcol, t); Q.gslab[t] = nullptr;
+            if (per_warp) { const size_t warps = (size_t)g->n_sm * 2 * K3_WARPS; L.pair_gslab[t].alloc(warps * per_warp); Q.gslab[t] = L.pair_gslab[t].as<unsigned char>(); Q.gslab_warps = warps; }
+        }
         if (Q.pair_end > Q.pair_begin) { CUDA_OK(cudaMemsetAsync(Q.defer_count, 0, 4, st)); tic(3, st); CUDA_OK(launch_pair(Q, g->n_sm, st)); toc(st); launches += 2; }
     }
     // lanes start after everything queued on the caller's stream and the caller's stream continues after the lanes
@@ -588,8 +603,8 @@ int hlala_graph_to_gpu(hlala_graph_t* g, int device) {
         }
         d.gap_stretch = g->up(h.gap_stretch); d.contig_off = g->up(h.contig_off); d.contig_seq = g->up(h.contig_seq); d.contig_level = g->up(h.contig_level);
         d.contig_prg_id = g->up(h.contig_prg_id); d.anchor_off = g->up(h.anchor_off); d.anchor_prg_id = g->up(h.anchor_prg_id); d.anchor_pos = g->up(h.anchor_pos);
-        ScoreTables t = make_score_tables();
-        CUDA_OK(upload_score_tables(t));
+        ScoreTables t = make_score_tables(), tl = make_score_tables(true);
+        CUDA_OK(upload_score_tables(t, tl));
         CUDA_OK(cudaDeviceSynchronize());
         g->on_gpu = true; g->device = device;
         return 0;
@@ -678,6 +693,46 @@ int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double 
         }
         lap("fetch");
         if (pl.n_errors > 0) return fail(HLALA_E_INVARIANT, std::to_string(pl.n_errors) + " chains/pairs violated a reference invariant (-5) or a kernel capacity (-4):" + pl.error_breakdown());
+        return 0;
+    });
+}
+
+// processBAM::alignReadsUnpaired_postSeedExtraction_andStoreInto / alignOneLongRead (processBAM.cpp:2224-2340, 3618-3838): every read on its own.
+int hlala_align_long_reads(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_pair_out_t* out, int32_t* bases_per_level) {
+    if (!g || !out || !batch) return fail(HLALA_E_ARG, "hlala_align_long_reads: null argument");
+    if (batch->n_reads < 0 || !batch->read_off || !batch->chain_off || !batch->cigar_off) return fail(HLALA_E_ARG, "seed batch: null offset arrays");
+    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
+    if (out->max_columns < 32 || out->max_columns > 16384) return fail(HLALA_E_ARG, "max_columns must be in [32, 16384] in long-read mode");
+    return guarded([&]() {
+        CUDA_OK(cudaSetDevice(g->device)); cudaStream_t st = 0;
+        // internally a read is a pair whose second mate is empty (no bases, no chains): the wave / slot / output indexing of the paired path is kept
+        const int64_t n = batch->n_reads; std::vector<int64_t> ro((size_t)(2 * n + 1)); std::vector<int32_t> co((size_t)(2 * n + 1));
+        for (int64_t r = 0; r < n; r++) { ro[(size_t)(2 * r)] = batch->read_off[r]; ro[(size_t)(2 * r + 1)] = batch->read_off[r + 1]; co[(size_t)(2 * r)] = batch->chain_off[r]; co[(size_t)(2 * r + 1)] = batch->chain_off[r + 1]; }
+        ro[(size_t)(2 * n)] = batch->read_off[n]; co[(size_t)(2 * n)] = batch->chain_off[n];
+        hlala_seed_batch_t b2 = *batch; b2.n_reads = 2 * n; b2.read_off = ro.data(); b2.chain_off = co.data();
+        Pipeline pl; pl.long_mode = true; pl.prepare(g, b2, out->max_columns, st);
+        DevBuf bpl; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
+        if (bases_per_level) { bpl.alloc(nl * 4); CUDA_OK(cudaMemsetAsync(bpl.p, 0, nl * 4, st)); }
+        const bool want_cols = out->level || out->edge || out->gchar || out->schar || out->from_seed || out->mapq || out->n_cols;
+        pl.run(100.0, 10.0, bases_per_level ? bpl.as<int32_t>() : nullptr, want_cols, st);       // the insert-size model is not used for single reads
+        // fetch in the internal layout, hand the even rows (the reads) to the caller
+        const size_t mc = (size_t)out->max_columns; const size_t nr2 = (size_t)(2 * n);
+        std::vector<double> pm((size_t)n), rm(nr2), pll((size_t)n); std::vector<uint8_t> rr(nr2); std::vector<int32_t> cslot(nr2), ncol(nr2);
+        hlala_pair_out_t tmp{}; tmp.max_columns = out->max_columns; tmp.pair_mapq = pm.data(); tmp.read_mapq = rm.data(); tmp.read_reverse = rr.data(); tmp.chosen_slot = cslot.data(); tmp.pair_ll = pll.data(); tmp.n_cols = ncol.data();
+        std::vector<int32_t> lv, ed; std::vector<uint8_t> gc, sc, fs, mq;
+        if (want_cols) { if (out->level) { lv.resize(nr2 * mc); tmp.level = lv.data(); } if (out->edge) { ed.resize(nr2 * mc); tmp.edge = ed.data(); } if (out->gchar) { gc.resize(nr2 * mc); tmp.gchar = gc.data(); }
+            if (out->schar) { sc.resize(nr2 * mc); tmp.schar = sc.data(); } if (out->from_seed) { fs.resize(nr2 * mc); tmp.from_seed = fs.data(); } if (out->mapq) { mq.resize(nr2 * mc); tmp.mapq = mq.data(); } }
+        pl.fetch(&tmp, st);
+        for (int64_t r = 0; r < n; r++) {
+            if (out->pair_mapq) out->pair_mapq[r] = pm[(size_t)r]; if (out->read_mapq) out->read_mapq[r] = rm[(size_t)(2 * r)]; if (out->read_reverse) out->read_reverse[r] = rr[(size_t)(2 * r)];
+            if (out->chosen_slot) out->chosen_slot[r] = cslot[(size_t)(2 * r)]; if (out->pair_ll) out->pair_ll[r] = pll[(size_t)r]; if (out->n_cols) out->n_cols[r] = ncol[(size_t)(2 * r)];
+            const size_t src = (size_t)(2 * r) * mc, dst = (size_t)r * mc;
+            if (out->level) memcpy(out->level + dst, lv.data() + src, mc * 4); if (out->edge) memcpy(out->edge + dst, ed.data() + src, mc * 4);
+            if (out->gchar) memcpy(out->gchar + dst, gc.data() + src, mc); if (out->schar) memcpy(out->schar + dst, sc.data() + src, mc);
+            if (out->from_seed) memcpy(out->from_seed + dst, fs.data() + src, mc); if (out->mapq) memcpy(out->mapq + dst, mq.data() + src, mc);
+        }
+        if (bases_per_level) { std::vector<int32_t> h(nl); bpl.download(h.data(), nl, st); CUDA_OK(cudaStreamSynchronize(st)); for (size_t i = 0; i + 1 < (size_t)g->h.n_levels; i++) bases_per_level[i] += h[i]; }
+        if (pl.n_errors > 0) return fail(HLALA_E_INVARIANT, std::to_string(pl.n_errors) + " chains/reads violated a reference invariant (-5) or a kernel capacity (-4):" + pl.error_breakdown());
         return 0;
     });
 }

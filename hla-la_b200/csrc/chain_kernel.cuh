@@ -21,6 +21,7 @@
 namespace hlala {
 
 __constant__ ScoreTables c_tables;
+__constant__ ScoreTables c_tables_long;     // long-read mode: indel rates 0.075 (extensionAligner.cpp:58-64)
 
 struct WarpSlab {
     int32_t* lvlA; int32_t* lvlB; uint8_t* gA; uint8_t* sA; uint8_t* gB; uint8_t* sB;
@@ -59,6 +60,29 @@ __device__ inline WarpSlab carve_slab(unsigned char* base, int maxcol, int pool_
     s.coloff = (uint16_t*)p; p += (size_t)((maxcol + 1) / 2 * 2) * 2;
     s.gA = p; p += maxcol; s.sA = p; p += maxcol; s.gB = p; p += maxcol; s.sB = p; p += maxcol;
     return s;
+}
+
+// long chains: window, node-score rows and barrier in shared memory, everything else in this warp's slice of HBM
+__device__ inline WarpSlab carve_slab_split(unsigned char* sm, unsigned char* gm, int maxcol, int pool_cap, int win_cap, int wcap) {
+    WarpSlab s; unsigned char* p = sm;
+    s.win = (uint32_t*)p; p += (size_t)(win_cap + 4) * 4;
+    s.mbar = (unsigned long long*)p; p += 8; s.mbar_phase = (uint32_t*)p; p += 8;
+    s.cur = (uint32_t*)p; p += (size_t)wcap * 4; s.nxt = (uint32_t*)p; p += (size_t)wcap * 4;
+    p = gm;
+    s.lvlA = (int32_t*)p; p += (size_t)maxcol * 4;
+    s.lvlB = (int32_t*)p; p += (size_t)maxcol * 4;
+    s.bt = (uint32_t*)p; p += (size_t)pool_cap * 4;
+    s.weoff = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2; s.wwid = (uint16_t*)p; p += (size_t)(maxcol + 4) * 2;
+    s.coloff = (uint16_t*)p; p += (size_t)((maxcol + 1) / 2 * 2) * 2;
+    s.gA = p; p += maxcol; s.sA = p; p += maxcol; s.gB = p; p += maxcol; s.sB = p; p += maxcol;
+    return s;
+}
+__device__ inline WarpSlab slab_of(const ChainParams& P, unsigned char* smem, int warp, int warps_per_cta) {
+    if (P.gslab) {
+        const size_t gw = (size_t)blockIdx.x * warps_per_cta + warp;
+        return carve_slab_split(smem + (size_t)warp * k1_gslab_smem_bytes(P.win_cap, P.wcap), P.gslab_base + gw * P.gslab_bytes, P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
+    }
+    return carve_slab(smem + (size_t)warp * k1_slab_bytes(P.slab_cols, P.pool_cap, P.win_cap, P.wcap), P.slab_cols, P.pool_cap, P.win_cap, P.wcap);
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {

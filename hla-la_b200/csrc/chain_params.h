@@ -40,6 +40,11 @@ struct ChainParams {
     int32_t* defer_slots; int32_t* defer_count;       // chains that did not fit the tier-0 slab
     int32_t read_begin, read_end;                     // reads of this wave
     int32_t dedup;                                    // 1: chains that the pair stage would discard as duplicates are not aligned at all
+    // long-read mode (processBAM::alignOneLongRead, processBAM.cpp:3618-3838): no extension DP (the seed is padded to the read), indel rates 0.075
+    // (extensionAligner.cpp:58-64). Chains of thousands of columns do not fit a shared-memory slab: with gslab the per-warp column buffers,
+    // backtrack pool and level tables live in a per-warp slice of HBM (gslab_base, gslab_bytes each) and only the staged edge window, the two
+    // node-score rows and the copy barrier stay in shared memory.
+    int32_t long_mode, gslab; unsigned char* gslab_base; unsigned long long gslab_bytes;
 };
 
 constexpr int32_t CH_TODO = -100;
@@ -85,7 +90,16 @@ struct PairParams {
     int32_t* error_count;
     unsigned long long* digest;    // [4]: sum n_cols, sum (edge ordinal + 1), pairs with mapQ < 1, -
     int32_t* defer_list; int32_t* defer_count;   // pairs beyond the small tier's capacities (kept chains per read, combinations), re-run by the large tier
+    int32_t unpaired;                            // long-read mode: every "pair" is one read followed by an empty mate (see k_pair)
+    unsigned char* gslab[2]; unsigned long long gslab_warps;   // max_columns beyond what shared memory holds: per-warp slabs of tier 0 / tier 1 in HBM (gslab_warps each)
 };
+
+// the shared-memory part of a slab whose large arrays live in HBM (ChainParams::gslab)
+__host__ __device__ inline size_t k1_gslab_bytes(int maxcol, int pool_cap) {
+    size_t b = (size_t)maxcol * 4 * 2 + (size_t)pool_cap * 4 + (size_t)(maxcol + 4) * 2 * 2 + (size_t)((maxcol + 1) / 2 * 2) * 2 + (size_t)maxcol * 4;
+    return (b + 255) & ~size_t(255);
+}
+__host__ __device__ inline size_t k1_gslab_smem_bytes(int win_cap, int wcap) { return ((size_t)(win_cap + 4) * 4 + 16 + (size_t)wcap * 4 * 2 + 15) & ~size_t(15); }
 
 __host__ __device__ inline size_t k1_slab_bytes(int maxcol, int pool_cap, int win_cap, int wcap) {
     size_t b = 0;

@@ -131,19 +131,25 @@ template <class CFG> __device__ void mark_members(const PairParams& P, const Pai
     __syncwarp();
 }
 
-template <class CFG, bool FROM_LIST> __global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
+// UNPAIRED (long-read mode): the unit is one read (stored as a pair whose second mate is empty): processBAM::alignOneLongRead's first-maximum chain and
+// assignMappingQualities_unpaired (processBAM.cpp:3752-3758, 3900-4059) — the posterior over the read's kept chains, no insert-size term, the same per-column
+// confidences. It is the paired arithmetic with one (virtual) chain of log-likelihood 0 on the other side.
+template <class CFG, bool FROM_LIST, bool UNPAIRED> __global__ void __launch_bounds__(K3_WARPS * 32) k_pair(PairParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     typedef typename CFG::Mask Mask;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    PairSlab<CFG> S = carve_pair_slab<CFG>(smem + (size_t)warp * pair_slab_bytes<CFG>(P.maxcol), P.maxcol);
+    const int warps_per_cta = blockDim.x >> 5;
+    unsigned char* const gs = P.gslab[FROM_LIST ? 1 : 0];
+    if (gs && (unsigned long long)gridDim.x * warps_per_cta > P.gslab_warps) return;     // cannot happen: the launcher sizes the grid to the slabs
+    PairSlab<CFG> S = carve_pair_slab<CFG>(gs ? gs + ((size_t)blockIdx.x * warps_per_cta + warp) * pair_slab_bytes<CFG>(P.maxcol) : smem + (size_t)warp * pair_slab_bytes<CFG>(P.maxcol), P.maxcol);
     const DevBatch& B = P.b; const int mc = P.maxcol;
-    const int nw = gridDim.x * K3_WARPS;
+    const int nw = gridDim.x * warps_per_cta;
     const long long n_work = FROM_LIST ? (long long)*P.defer_count : P.pair_end - P.pair_begin;
-    for (long long wi = (long long)blockIdx.x * K3_WARPS + warp; wi < n_work; wi += nw) {
+    for (long long wi = (long long)blockIdx.x * warps_per_cta + warp; wi < n_work; wi += nw) {
         const long long p = FROM_LIST ? (long long)P.defer_list[wi] : P.pair_begin + wi;
         const int r1 = (int)(2 * p), r2 = r1 + 1;
         int n1 = 0, n2 = 0, err = 0;
-        if (lane == 0) { n1 = gather_kept<CFG::KCAP>(P, r1, S.kept1, err); if (!err) n2 = gather_kept<CFG::KCAP>(P, r2, S.kept2, err); if (!err && (n1 == 0 || n2 == 0)) err = HLALA_E_INVARIANT_DEV; if (!err && n1 * n2 > CFG::COMBO) err = HLALA_E_CAPACITY_DEV; }
+        if (lane == 0) { n1 = gather_kept<CFG::KCAP>(P, r1, S.kept1, err); if (UNPAIRED) n2 = 1; else if (!err) n2 = gather_kept<CFG::KCAP>(P, r2, S.kept2, err); if (!err && (n1 == 0 || n2 == 0)) err = HLALA_E_INVARIANT_DEV; if (!err && n1 * n2 > CFG::COMBO) err = HLALA_E_CAPACITY_DEV; }
         n1 = __shfl_sync(0xffffffffu, n1, 0); n2 = __shfl_sync(0xffffffffu, n2, 0); err = __shfl_sync(0xffffffffu, err, 0);
         __syncwarp();
         if (!FROM_LIST && err == HLALA_E_CAPACITY_DEV && P.defer_list) {     // re-run by the large tier
@@ -154,10 +160,11 @@ template <class CFG, bool FROM_LIST> __global__ void __launch_bounds__(K3_WARPS 
             if (lane == 0) { P.pair_status[p] = err; P.pair_mapq[p] = -1; P.chosen_slot[r1] = -1; P.chosen_slot[r2] = -1; if (P.out_n_cols) { P.out_n_cols[r1] = 0; P.out_n_cols[r2] = 0; } atomicAdd(P.error_count, 1); }
             continue;
         }
-        const bool rev1 = (B.chain_flag[B.chain_order[S.kept1[0]]] & 0x10) != 0, rev2 = (B.chain_flag[B.chain_order[S.kept2[0]]] & 0x10) != 0;
+        const bool rev1 = (B.chain_flag[B.chain_order[S.kept1[0]]] & 0x10) != 0, rev2 = UNPAIRED ? false : (B.chain_flag[B.chain_order[S.kept2[0]]] & 0x10) != 0;
         const int nc = n1 * n2;
         // ---- combination likelihoods (processBAM.cpp:3408-3506)
         for (int i = lane; i < nc; i += 32) {
+            if (UNPAIRED) { S.ll[i] = P.ll[S.kept1[i]]; continue; }
             const int a = S.kept1[i / n2], b = S.kept2[i % n2];
             double ll = P.ll[a] + P.ll[b];
             const int f1 = P.first_level[a], l1 = P.last_level[a], f2 = P.first_level[b], l2 = P.last_level[b];
@@ -177,7 +184,7 @@ template <class CFG, bool FROM_LIST> __global__ void __launch_bounds__(K3_WARPS 
             if (oi >= 0 && (besti < 0 || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
         }
         const int ia = besti / n2, ib = besti % n2;
-        const int sa = S.kept1[ia], sb = S.kept2[ib];
+        const int sa = S.kept1[ia], sb = UNPAIRED ? -1 : S.kept2[ib];
         double mapq = 1, mq1 = 1, mq2 = 1;
         if (nc > 1) {
             // ---- posteriors (processBAM.cpp:4070-4123)
@@ -196,12 +203,13 @@ template <class CFG, bool FROM_LIST> __global__ void __launch_bounds__(K3_WARPS 
             mapq = __shfl_sync(0xffffffffu, mapq, 0); mq1 = __shfl_sync(0xffffffffu, mq1, 0); mq2 = __shfl_sync(0xffffffffu, mq2, 0);
         }
         if (lane == 0) {
-            P.pair_status[p] = 0; P.pair_mapq[p] = mapq; P.pair_ll[p] = best; P.read_mapq[r1] = mq1; P.read_mapq[r2] = mq2;
+            P.pair_status[p] = 0; P.pair_mapq[p] = mapq; P.pair_ll[p] = best; P.read_mapq[r1] = mq1; P.read_mapq[r2] = UNPAIRED ? 0.0 : mq2;
             P.read_reverse[r1] = rev1; P.read_reverse[r2] = rev2; P.chosen_slot[r1] = sa; P.chosen_slot[r2] = sb;
+            if (UNPAIRED && P.out_n_cols) P.out_n_cols[r2] = 0;
             if (mapq < 1) atomicAdd(P.digest + 2, 1ull);
         }
         // ---- per read: per-column confidences, outputs, coverage
-        for (int which = 0; which < 2; which++) {
+        for (int which = 0; which < (UNPAIRED ? 1 : 2); which++) {
             const int cs = which == 0 ? sa : sb; const int r = which == 0 ? r1 : r2;
             const int ncol = P.n_cols[cs]; const int fl = P.first_level[cs];
             if (nc > 1) {

@@ -467,6 +467,9 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
     const int max_chains = arg<int>(a, "max-chains", 12);
     const double decoy_frac = arg<double>(a, "decoy-frac", 0.02);
     const uint64_t seed = arg<uint64_t>(a, "seed", 0xB200);
+    // --single 1: long-read mode input (HLA-LA.pl --longReads): one unpaired read per unit (flags without the pairing bits), clips up to --clip-max bases
+    const bool single = arg<int>(a, "single", 0) != 0;
+    const int clip_max = arg<int>(a, "clip-max", 40);
     std::vector<Contig> cs = load_contigs(prg);
     std::vector<int> haps; for (size_t i = 0; i < cs.size(); i++) if (cs[i].is_hap) haps.push_back((int)i);
     if (haps.empty()) throw std::runtime_error("no haplotype contigs");
@@ -501,8 +504,8 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
         for (;;) {
             src = &cs[haps[R.below(haps.size())]];
             gap = (int)std::lround(R.normal(gap_mean, gap_sd));
-            int64_t frag = 2 * (int64_t)L + gap + 16;
-            if ((int64_t)src->seq.size() < frag + 64 || gap < -L / 2) continue;
+            int64_t frag = single ? (int64_t)L + L / 8 + 16 : 2 * (int64_t)L + gap + 16;
+            if ((int64_t)src->seq.size() < frag + 64 || (!single && gap < -L / 2)) continue;
             if (!gene_ranges.empty() && R.bern(gene_frac)) {
                 auto gr = gene_ranges[R.below(gene_ranges.size())];
                 int64_t c0 = std::lower_bound(src->lv.begin(), src->lv.end(), gr.first) - src->lv.begin();
@@ -513,9 +516,9 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
             break;
         }
         bool first_is_fwd = R.bern(0.5);
-        for (int mate = 0; mate < 2; mate++) {
+        for (int mate = 0; mate < (single ? 1 : 2); mate++) {
             bool upstream = (mate == 0) == first_is_fwd;   // the forward-strand mate is the upstream one
-            int64_t s0 = upstream ? start : start + L + gap;
+            int64_t s0 = (upstream || single) ? start : start + L + gap;
             // build the read with sequencing errors, all in reference orientation (BAM SEQ convention)
             std::vector<ReadItem> rd; int64_t ci = s0;
             while ((int)rd.size() < L) {
@@ -529,7 +532,7 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
             // an inserted first/last base would make truth ambiguous; force them onto levels
             if (rd.front().lv < 0) { rd.front().lv = src->lv[s0 > 0 ? s0 - 1 : 0]; rd.front().b = src->seq[s0 > 0 ? s0 - 1 : 0]; }
             int clipL = 0, clipR = 0;
-            if (R.bern(clip_frac)) { int c = 5 + (int)R.below(36); if (R.bern(0.5)) clipL = c; else clipR = c; }
+            if (R.bern(clip_frac)) { int c = 5 + (int)R.below((uint64_t)std::max(1, clip_max - 4)); if (R.bern(0.5)) clipL = c; else clipR = c; }
             std::vector<Chain> chains;
             for (size_t c = 0; c < cs.size(); c++) {
                 Chain ch;
@@ -547,7 +550,7 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
                 if (better) prim = k;
             }
             bool rev = !upstream;
-            uint16_t base_flag = 0x1 | (mate == 0 ? 0x40 : 0x80) | (rev ? 0x10 : 0x20);
+            uint16_t base_flag = single ? (uint16_t)(rev ? 0x10 : 0) : (uint16_t)(0x1 | (mate == 0 ? 0x40 : 0x80) | (rev ? 0x10 : 0x20));
             if (R.bern(decoy_frac)) { Chain d = chains[R.below(chains.size())]; d.as = std::max(30, d.as - 7); d.flag = 0xFFFF; chains.push_back(d); }
             for (size_t k = 0; k < chains.size(); k++) {
                 bool decoy = chains[k].flag == 0xFFFF;
@@ -608,7 +611,7 @@ int cmd_reads(const std::map<std::string, std::string>& a) {
     f.put("cigar_off", DT_I32, cigar_off); f.put("cigar", DT_U32, cigar);
     f.put("truth_first", DT_I32, truth_first); f.put("truth_last", DT_I32, truth_last); f.put("truth_src", DT_I32, truth_src);
     f.write(out);
-    fprintf(stderr, "hlala-synth: %lld pairs, %zu chains (%.2f per read)\n", (long long)n_pairs, chain_contig.size(), (double)chain_contig.size() / (2.0 * n_pairs));
+    fprintf(stderr, "hlala-synth: %lld %s, %zu chains (%.2f per read)\n", (long long)n_pairs, single ? "single reads" : "pairs", chain_contig.size(), (double)chain_contig.size() / ((single ? 1.0 : 2.0) * n_pairs));
     return 0;
 }
 

@@ -124,6 +124,14 @@ void hlala_graph_release_workspace(hlala_graph_t* g);
 
 /* Device-resident variant used by bench.py: upload once, run many times, read back small results.
  * The session owns device copies of the batch and all scratch. */
+/* Long-read mode (HLA-LA.pl --longReads ont2d|pacbio): processBAM::alignReadsUnpaired_postSeedExtraction_andStoreInto (mapper/processBAM.cpp:2224-2340) with
+ * processBAM::alignOneLongRead (:3618-3838) and assignMappingQualities_unpaired (:3900-4059). The batch holds single reads (n_reads of any parity;
+ * every read needs a primary record); each same-strand, non-duplicate chain is projected to the graph (the same seed projection as the paired path),
+ * padded to the full read (no extension DP: verboseSeedChain::extendToFullSequenceLength), scored with indel rates 0.075 (extensionAligner.cpp:58-64); the
+ * first maximum is the read's alignment, its mapping quality the posterior over the read's chains. Outputs as in hlala_align_pairs, per READ:
+ * pair_mapq[r] == read_mapq[r], pair_ll[r] = log-likelihood of the chosen chain, columns [n_reads * max_columns]; max_columns up to 16384. */
+int hlala_align_long_reads(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_pair_out_t* out, int32_t* bases_per_level);
+
 typedef struct hlala_session hlala_session_t;
 int hlala_session_create(hlala_graph_t* g, const hlala_seed_batch_t* batch, int32_t max_columns, hlala_session_t** out);
 void hlala_session_free(hlala_session_t* s);

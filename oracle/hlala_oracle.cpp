@@ -426,17 +426,17 @@ struct Oracle {
     }
 
     // extendSeedChain (extensionAligner.cpp:186-333) + extendToFullSequenceLength (verboseSeedChain.cpp:82-144)
-    Chain extend_chain(const std::string& seq, const Chain& seed) const {
+    Chain extend_chain(const std::string& seq, const Chain& seed, bool dp = true) const {
         Chain r = seed;
         auto splice = [&](const Chain& e, bool left) {
             if (left) { r.level.insert(r.level.begin(), e.level.begin(), e.level.end()); r.edge.insert(r.edge.begin(), e.edge.begin(), e.edge.end()); r.gchar = e.gchar + r.gchar; r.schar = e.schar + r.schar; r.from_seed.insert(r.from_seed.begin(), e.from_seed.begin(), e.from_seed.end()); r.seq_begin = e.seq_begin; }
             else { r.level.insert(r.level.end(), e.level.begin(), e.level.end()); r.edge.insert(r.edge.end(), e.edge.begin(), e.edge.end()); r.gchar += e.gchar; r.schar += e.schar; r.from_seed.insert(r.from_seed.end(), e.from_seed.begin(), e.from_seed.end()); r.seq_end = e.seq_end; }
         };
-        if (seed.seq_begin != 0) {
+        if (dp && seed.seq_begin != 0) {
             int node = g.edges[seed.edge.front()].from;
             if (g.node_level[node] > 0) { Chain e; if (extend(seq, seed.seq_begin, g.node_level[node], g.node_z[node], false, e)) splice(e, true); }
         }
-        if (seed.seq_end != (int)seq.size() - 1) {
+        if (dp && seed.seq_end != (int)seq.size() - 1) {
             int node = g.edges[seed.edge.back()].to;
             if (g.node_level[node] < g.n_levels - 1) { Chain e; if (extend(seq, seed.seq_end + 1, g.node_level[node], g.node_z[node], true, e)) splice(e, false); }
         }
@@ -447,8 +447,10 @@ struct Oracle {
     }
 
     // scoreOneAlignment (extensionAligner.cpp:52-182); qualities are consumed in alignment orientation
-    static double score(const Chain& ch, const std::string& qual) {
-        double rate_del = log(0.001), rate_ins = log(0.001), rate_mm = log(1 - exp(rate_del) - exp(rate_ins)), ll = 0; int idx = ch.seq_begin - 1;
+    static double score(const Chain& ch, const std::string& qual, bool long_reads = false) {
+        double rate_del = log(0.001), rate_ins = log(0.001);
+        if (long_reads) { rate_del = log(0.075); rate_ins = log(0.075); }      // extensionAligner.cpp:60-64
+        double rate_mm = log(1 - exp(rate_del) - exp(rate_ins)), ll = 0; int idx = ch.seq_begin - 1;
         for (size_t i = 0; i < ch.schar.size(); i++) {
             if (ch.schar[i] != '_') {
                 idx++;
@@ -544,6 +546,37 @@ struct Oracle {
         auto assign = [&](Chain& c, const char* tag) { c.mapq.clear(); for (const std::string& k : keys(c, tag)) { double q = conf.at(k); if (q > 1) q = 1; c.mapq.push_back((char)to_phred(q)); } };
         assign(out1, "r1"); assign(out2, "r2");
     }
+
+    // alignOneLongRead (processBAM.cpp:3618-3838: the seed is only padded to the read, verboseSeedChain.cpp:82-144; indel rates 0.075) +
+    // assignMappingQualities_unpaired (:3900-4059)
+    void long_read(const Batch& b, long long r, Chain& out, double& best_ll) const {
+        std::vector<Chain> ch; std::vector<double> ll;
+        ReadChains rc = prepare_read(b, r); std::map<std::pair<int, int>, int> seen;
+        for (size_t i = 0; i < rc.order.size(); i++) {
+            int c = rc.order[i];
+            if (((b.chain_flag[c] & 0x10) != 0) != rc.reverse) continue;
+            std::pair<int, int> id = prg_span(b, c);
+            Chain seed = project(b, c, rc.seq, rc.reverse);
+            if (seen.count(id) && seen[id] >= b.chain_as[c]) continue;
+            Chain full = extend_chain(rc.seq, seed, false);
+            ch.push_back(full); ll.push_back(score(full, rc.qual, true));
+            if (!seen.count(id) || seen[id] < b.chain_as[c]) seen[id] = b.chain_as[c];
+        }
+        REQUIRE(!ch.empty(), "at least one chain per read");
+        size_t bi = 0; for (size_t i = 1; i < ll.size(); i++) if (ll[i] > ll[bi]) bi = i;
+        out = ch[bi]; best_ll = ll[bi];
+        if (ll.size() == 1) { out.chain_mapq = 1; out.mapq.assign(out.gchar.size(), (char)to_phred(1)); return; }
+        std::vector<double> pp(ll.size()); double sum = 0;
+        for (size_t i = 0; i < ll.size(); i++) pp[i] = exp(ll[i] - ll[bi]);
+        for (double v : pp) sum += v; for (double& v : pp) v = v / sum;
+        out.chain_mapq = pp[bi];
+        auto keys = [](const Chain& c) { std::vector<std::string> k; int nb = 0, tot = 0; for (char x : c.schar) if (x != '_') tot++;
+            for (size_t j = 0; j < c.gchar.size(); j++) { int si = -1; if (c.schar[j] != '_') { si = c.reverse ? tot - nb - 1 : nb; nb++; }
+                k.push_back(std::string(1, c.gchar[j]) + ":" + std::to_string(c.level[j]) + ":r1:" + (c.reverse ? "minus" : "plus") + ":" + std::to_string(si)); } return k; };
+        std::map<std::string, double> conf;
+        for (size_t i = 0; i < pp.size(); i++) for (const std::string& k : keys(ch[i])) conf[k] += pp[i];
+        out.mapq.clear(); for (const std::string& k : keys(out)) { double q = conf.at(k); if (q > 1) q = 1; out.mapq.push_back((char)to_phred(q)); }
+    }
 };
 
 std::string g_err;
@@ -612,6 +645,24 @@ int hlala_oracle_pairs(void* h, long long n_reads, const int64_t* read_off, cons
             pair_mapq[p] = mq; read_mapq[2 * p] = a.chain_mapq; read_mapq[2 * p + 1] = c.chain_mapq; read_reverse[2 * p] = a.reverse; read_reverse[2 * p + 1] = c.reverse;
             if (level) { size_t oa = (size_t)(2 * p) * cap, ob = oa + cap; export_chain(a, cap, n_cols + 2 * p, level + oa, edge + oa, gchar + oa, schar + oa, from_seed + oa, mapq + oa); export_chain(c, cap, n_cols + 2 * p + 1, level + ob, edge + ob, gchar + ob, schar + ob, from_seed + ob, mapq + ob); }
             else { n_cols[2 * p] = (int)a.level.size(); n_cols[2 * p + 1] = (int)c.level.size(); }
+        }
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return 0;
+    });
+}
+
+// one read per unit (long-read mode): read_mapq[r] = posterior of the chosen chain, read_ll[r] its log-likelihood
+int hlala_oracle_long_reads(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, const int32_t* chain_off, const int32_t* chain_contig,
+                            const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as, const int32_t* cigar_off, const uint32_t* cigar, int cap,
+                            double* read_mapq, double* read_ll, uint8_t* read_reverse, int32_t* n_cols, int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) {
+    Oracle* o = (Oracle*)h; Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() {
+        auto t0 = std::chrono::steady_clock::now();
+        for (long long r = 0; r < n_reads; r++) {
+            Chain a; double ll; o->long_read(b, r, a, ll);
+            read_mapq[r] = a.chain_mapq; read_ll[r] = ll; read_reverse[r] = a.reverse;
+            if (level) { size_t oa = (size_t)r * cap; export_chain(a, cap, n_cols + r, level + oa, edge + oa, gchar + oa, schar + oa, from_seed + oa, mapq + oa); }
+            else n_cols[r] = (int)a.level.size();
         }
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return 0;

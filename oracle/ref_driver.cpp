@@ -195,6 +195,32 @@ public:
         return 0;
     }
 
+    // long-read mode: the unmodified processBAM::alignOneLongRead per read (what alignReadsUnpaired_postSeedExtraction_andStoreInto calls, processBAM.cpp:2288)
+    int run_long_reads(const Batch& b, int cap, int threads, double* read_mapq, double* read_ll, uint8_t* read_reverse, int32_t* n_cols,
+                       int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) const {
+        if (threads < 1) threads = 1;
+        omp_set_num_threads(threads); eA->init_for_threads(threads);
+        auto t0 = std::chrono::steady_clock::now();
+        #pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+        for (int64_t r = 0; r < b.n_reads; r++) {
+            mapper::reads::protoSeeds ps; std::vector<int32_t> o1;
+            build_read(b, r, "r" + std::to_string(r), ps.read1_alignments, o1);
+            mapper::reads::verboseSeedChain res = alignOneLongRead(ps, nullptr, nullptr, "ont2d");
+            read_mapq[r] = res.mapQ; read_reverse[r] = res.reverse;
+            if (read_ll) {   // the chosen chain's likelihood is not a member of the result: score it again with the reference's own function
+                size_t prim = ps.read1_getPrimaryAlignmentI(); const BamTools::BamAlignment& P = std::get<2>(ps.read1_alignments.at(prim));
+                mapper::reads::oneRead rd(P.Name, P.QueryBases, P.Qualities); if (P.IsReverseStrand()) rd.invert();
+                read_ll[r] = eA->scoreOneAlignment(res, rd, "ont2d");
+            }
+            size_t oa = (size_t)r * cap;
+            if (level) export_chain(res, cap, n_cols + r, level + oa, edge + oa, gchar + oa, schar + oa, from_seed + oa, mapq + oa);
+            else n_cols[r] = (int)res.graph_aligned_levels.size();
+        }
+        omp_set_num_threads(1); eA->init_for_threads(1);
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return 0;
+    }
+
     // processBAM.cpp:2410-2481 (serial loop, gene filter, raw read construction) followed by the one HLATypeInference call at :1920.
     // HLATypeInference reads hla_nom_g.txt from the current directory, so the call runs with cwd = g_dir.
     hla::HLATyper* typer = nullptr;
@@ -333,6 +359,16 @@ int hlala_ref_pairs(void* h, long long n_reads, const int64_t* read_off, const u
     Driver* d = (Driver*)h;
     Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
     return guarded([&]() { return d->run_pairs(b, is_mean, is_sd, cap, threads, pair_mapq, read_mapq, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
+}
+
+int hlala_ref_long_reads(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
+                         const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
+                         const int32_t* cigar_off, const uint32_t* cigar, int cap, int threads,
+                         double* read_mapq, double* read_ll, uint8_t* read_reverse, int32_t* n_cols,
+                         int32_t* level, int32_t* edge, uint8_t* gchar, uint8_t* schar, uint8_t* from_seed, uint8_t* mapq, double* seconds) {
+    Driver* d = (Driver*)h;
+    Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() { return d->run_long_reads(b, cap, threads, read_mapq, read_ll, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
 }
 
 // Gene filter + HLATyper::HLATypeInference on the pairs of the batch; writes the reference's files into out_dir.

@@ -32,6 +32,9 @@ DATASETS = {
     "typing1k": (dict(levels=60000, haps=4, genes=17, alleles=1000, seed=31), dict(pairs=700, len=150, seed=31, gene_frac=0.85), 100.0, 10.0),   # 1000 alleles per locus like the bench PRG
     "typing250": (dict(levels=35000, haps=4, genes=17, alleles=24, seed=24), dict(pairs=800, len=250, seed=24, gene_frac=0.8, clip_frac=0.2, gap_mean=300, gap_sd=40), 300.0, 40.0),
     "genes": (dict(levels=30000, haps=8, genes=8, alleles=300), dict(pairs=250, len=150, clip_frac=0.15, gene_frac=1.0), 100.0, 10.0),
+    # long-read mode (HLA-LA.pl --longReads): single reads of 3-6 kb, 3 % indels, half of them clipped by up to 400 bases, half starting in gene blocks
+    "long": (dict(levels=40000, haps=6, genes=3, alleles=32, seed=41), dict(pairs=160, len=4000, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=400, gene_frac=0.5, seed=41), 0.0, 1.0),
+    "long_small": (dict(levels=12000, haps=4, genes=1, alleles=16, seed=43), dict(pairs=40, len=1500, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=200, gene_frac=0.5, seed=43), 0.0, 1.0),
     "L250": (dict(levels=20000, haps=6, genes=2, alleles=32, seed=21), dict(pairs=400, len=250, clip_frac=0.3, indel_rate=0.002, seed=21), 250.0, 35.0),
 }
 

@@ -132,6 +132,23 @@ class Ref:
         return o
 
 
+    def long_reads(self, b, cap=16384, threads=1, columns=True):
+        """long-read mode: alignOneLongRead per read of `b` (single reads)"""
+        nr = len(b["read_off"]) - 1
+        o = dict(read_mapq=np.zeros(nr, np.float64), read_ll=np.zeros(nr, np.float64), read_reverse=np.zeros(nr, np.uint8), n_cols=np.zeros(nr, np.int32))
+        cols = ("level", "edge", "gchar", "schar", "from_seed", "mapq")
+        if columns:
+            o.update(level=np.zeros((nr, cap), np.int32), edge=np.zeros((nr, cap), np.int32), gchar=np.zeros((nr, cap), np.uint8), schar=np.zeros((nr, cap), np.uint8),
+                     from_seed=np.zeros((nr, cap), np.uint8), mapq=np.zeros((nr, cap), np.uint8))
+        sec = C.c_double(0)
+        args = [self.h, *batch_args(b), C.c_int(cap)] + ([C.c_int(threads)] if self.LONG_HAS_THREADS else [])
+        self._chk(self.lib.hlala_ref_long_reads(*args, p(o["read_mapq"]), p(o["read_ll"]), p(o["read_reverse"]), p(o["n_cols"]),
+                                                *[(p(o[k]) if columns else None) for k in cols], C.byref(sec)))
+        o["seconds"] = sec.value
+        return o
+
+    LONG_HAS_THREADS = True
+
     def type(self, prg_dir, b, is_mean, is_sd, out_dir, threads=1):
         """gene filter + unmodified HLATyper::HLATypeInference; writes the reference's files into out_dir."""
         os.makedirs(out_dir, exist_ok=True)
@@ -191,7 +208,7 @@ class Oracle(Ref):
         self.lib = C.CDLL(LIB_ORACLE)
         L = self.lib
         # expose the oracle's entry points under the names Ref's methods call
-        for name in ("open", "last_error", "n_levels", "n_nodes", "n_edges", "graph_export", "gap_paths_total", "gap_paths_export", "gap_stretch", "chains", "pairs"):
+        for name in ("open", "last_error", "n_levels", "n_nodes", "n_edges", "graph_export", "gap_paths_total", "gap_paths_export", "gap_stretch", "chains", "pairs", "long_reads"):
             setattr(L, "hlala_ref_" + name, getattr(L, "hlala_oracle_" + name))
         L.hlala_ref_open.restype = C.c_void_p
         L.hlala_ref_last_error.restype = C.c_char_p
@@ -200,6 +217,8 @@ class Oracle(Ref):
         self.h = C.c_void_p(L.hlala_ref_open(prg_dir.encode()))
         if not self.h:
             raise RuntimeError(L.hlala_ref_last_error().decode())
+
+    LONG_HAS_THREADS = False
 
     def graph(self):
         nl = self.lib.hlala_ref_n_levels(self.h); nn = self.lib.hlala_ref_n_nodes(self.h); ne = self.lib.hlala_ref_n_edges(self.h)
@@ -396,6 +415,16 @@ def oracle_pairs(prg_dir, b, is_mean, is_sd, cap=1024):
     return r
 
 
+def oracle_long_reads(prg_dir, b, cap=16384):
+    """long-read alignments of `b` (single reads) from the strongest checker (see oracle_pairs)"""
+    if have_ref() and _REF_CACHE and prg_dir not in _REF_CACHE:
+        return _ref_subprocess(prg_dir, b, 0.0, 1.0, cap, "long_reads")
+    o, kind = checker(prg_dir)
+    r = quiet(o.long_reads, b, cap)
+    r["oracle"] = kind
+    return r
+
+
 def oracle_chains(prg_dir, b, cap=1024):
     """per-chain records of `b` from the strongest checker (see oracle_pairs)"""
     if have_ref() and _REF_CACHE and prg_dir not in _REF_CACHE:
@@ -511,6 +540,21 @@ class Product:
         o["bases_per_level"] = bpl
         return o
 
+    def long_reads(self, b, cap=16384, want_levels=True):
+        """hlala_align_long_reads: one unit per read of `b`"""
+        nr = len(b["read_off"]) - 1
+        o = dict(pair_mapq=np.zeros(nr, np.float64), read_mapq=np.zeros(nr, np.float64), read_reverse=np.zeros(nr, np.uint8), chosen_slot=np.zeros(nr, np.int32),
+                 pair_ll=np.zeros(nr, np.float64), n_cols=np.zeros(nr, np.int32), level=np.zeros((nr, cap), np.int32), edge=np.zeros((nr, cap), np.int32),
+                 gchar=np.zeros((nr, cap), np.uint8), schar=np.zeros((nr, cap), np.uint8), from_seed=np.zeros((nr, cap), np.uint8), mapq=np.zeros((nr, cap), np.uint8))
+        po = PairOut(); po.max_columns = cap
+        for k in o:
+            setattr(po, k, o[k].ctypes.data)
+        sb = make_batch_struct(b)
+        nl = self.dims()["n_levels"]
+        bpl = np.zeros(max(nl - 1, 1), np.int32) if want_levels else None
+        self._chk(self.lib.hlala_align_long_reads(self.g, C.byref(sb), C.byref(po), p(bpl) if want_levels else None))
+        o["bases_per_level"] = bpl
+        return o
 
 
     # ---- BAM ingest

@@ -1,5 +1,5 @@
 """Runs the compiled reference (oracle/_ref) on one batch in a process of its own: the reference's graph arena holds one PRG per process, so
-harness.oracle_pairs() sends every further dataset of a test session here.   usage: ref_worker.py <prg_dir> <in.npz> <out.npz> <mean> <sd> <cap> [pairs|chains]"""
+harness.oracle_pairs() sends every further dataset of a test session here.   usage: ref_worker.py <prg_dir> <in.npz> <out.npz> <mean> <sd> <cap> [pairs|chains|long_reads]"""
 import sys
 
 import numpy as np
@@ -12,8 +12,8 @@ def main():
     b = dict(np.load(fin))
     what = sys.argv[7] if len(sys.argv) > 7 else "pairs"
     R = H.quiet(H.Ref, prg)
-    r = H.quiet(R.chains, b, cap) if what == "chains" else H.quiet(R.pairs, b, mu, sd, cap)
-    np.savez(fout, **{k: v for k, v in r.items() if isinstance(v, np.ndarray)})
+    r = H.quiet(R.chains, b, cap) if what == "chains" else H.quiet(R.long_reads, b, cap) if what == "long_reads" else H.quiet(R.pairs, b, mu, sd, cap)
+    np.savez(fout, **{k: np.asarray(v) for k, v in r.items() if isinstance(v, (np.ndarray, float))})
 
 
 if __name__ == "__main__":
