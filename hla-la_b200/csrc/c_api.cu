@@ -11,6 +11,7 @@
 #include "../host/kmer_index.h"
 #include "../host/bam_reader.h"
 #include "../host/hla_typing.h"
+#include "../host/hla_eval.h"
 
 #include <algorithm>
 #include <cmath>
@@ -361,6 +362,11 @@ struct Pipeline {
     }
     ChainParams chain_params(int tier, Lane& L) {
         ChainParams P{}; P.g = g->d; P.b = db.view; chain_caps(maxcol, g->h.max_edges_per_level <= 255 && g->h.max_nodes_per_level <= 256, tier, P); P.do_extension = long_mode ? 0 : 1; P.long_mode = long_mode ? 1 : 0; cs.fill(P); L.fill(P);
+        {   // score field of the packed Viterbi keys: 12 bits (key_shift 20) cover max_columns <= 2040; longer chains take bits from the rank field, which must still hold the widest level's edges
+            int ks = 20; while (ks > 12 && (long long)maxcol + 2 >= (1LL << (32 - ks))) ks--;
+            if ((long long)maxcol + 2 >= (1LL << (32 - ks)) || (long long)g->h.max_edges_per_level >= (1LL << ks)) throw std::runtime_error("max_columns " + std::to_string(maxcol) + " with levels of " + std::to_string(g->h.max_edges_per_level) + " edges exceeds the packed Viterbi key of the chain kernel");
+            P.key_shift = ks;
+        }
         if (tier == 1 && maxcol > 2040) {     // chains of thousands of columns: slab in HBM, one slice per resident warp
             P.gslab = 1; P.win_cap = 4096; P.gslab_bytes = k1_gslab_bytes(P.slab_cols, P.pool_cap);
             const int warps = chain_seed_max_warps(P, g->n_sm); gslab.alloc((size_t)std::max(warps, 1) * P.gslab_bytes); P.gslab_base = gslab.as<unsigned char>();
@@ -641,6 +647,9 @@ int hlala_align_chains(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_
         cudaStream_t st = 0;
         Pipeline pl; pl.scratch_budget = (size_t)1 << 62; pl.allow_env_budget = false; pl.dedup = false; pl.prepare(g, *batch, out->max_columns, st);   // one wave: the chain records are exported whole
         pl.begin_run(st);
+        {   // records of chains that are skipped (strand rule) never get a seed span: defined zeros in the exported arrays
+            const size_t nb = (size_t)std::max(pl.pb.n_chains, 1) * 4; CUDA_OK(cudaMemsetAsync(pl.cs.seed_begin.p, 0, nb, st)); CUDA_OK(cudaMemsetAsync(pl.cs.seed_end.p, 0, nb, st));
+        }
         Lane& L0 = *pl.lanes[0];
         pl.fork_lanes(st);
         if (pl.wave_pair.size() > 1) pl.run_chains_wave(0, L0);
@@ -834,6 +843,12 @@ TypingScoreTables make_typing_tables() {   // HLATyper.cpp:2060-2066, 2189-2216;
 struct GpuTypingDevice : TypingDevice {
     int device = 0, rank = 0, world = 1; hlala_allreduce_f64_fn allreduce = nullptr; void* ctx = nullptr; cudaStream_t st = 0;
     double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0};
+    void abort_locus(int32_t C) override {     // see TypingDevice::abort_locus: NaNs into this locus' all-reduce
+        if (world <= 1 || !allreduce) return;
+        CUDA_OK(cudaSetDevice(device));
+        const size_t npair = (size_t)C * ((size_t)C + 1) / 2; DevBuf d; d.alloc(3 * npair * 8); CUDA_OK(cudaMemsetAsync(d.p, 0xFF, 3 * npair * 8, st));
+        allreduce(ctx, (uint64_t)(uintptr_t)d.p, (int64_t)(3 * npair), (void*)st); CUDA_OK(cudaStreamSynchronize(st));
+    }
     void run_locus(const LocusDeviceInput& in, bool want_read_ll, LocusDeviceOutput& out) override {
         CUDA_OK(cudaSetDevice(device));   // entered from the host thread pool of run_typing (one locus at a time, in locus order)
         static const bool prof = getenv("HLALA_TYPING_PROFILE") != nullptr; auto tp0 = std::chrono::steady_clock::now();
@@ -869,6 +884,7 @@ struct GpuTypingDevice : TypingDevice {
             if (allreduce(ctx, (uint64_t)(uintptr_t)d_pair.p, (int64_t)(3 * npair), (void*)st) != 0) throw std::runtime_error("hlala_typer_infer: all-reduce callback failed");
         }
         lapp("all-reduce");
+        if (world > 1) { double first = 0; CUDA_OK(cudaMemcpyAsync(&first, pl, 8, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); if (first != first) throw std::runtime_error("hlala_typer_infer: this locus failed on another rank (poisoned all-reduce)"); }
         out.pair_ll.resize(npair); out.pair_mavg.resize(npair); out.pair_mmin.resize(npair);
         CUDA_OK(cudaMemcpyAsync(out.pair_ll.data(), pl, npair * 8, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaMemcpyAsync(out.pair_mavg.data(), pl + npair, npair * 8, cudaMemcpyDeviceToHost, st));
@@ -987,6 +1003,22 @@ int hlala_typer_result_call(const hlala_typer_t* t, int l, const char** a1, cons
     const LocusCall& c = t->calls[(size_t)l];
     if (a1) *a1 = c.call1.c_str(); if (a2) *a2 = c.call2.c_str(); if (q1) *q1 = c.q1; if (q2) *q2 = c.q2; return 0;
 }
+int hlala_evaluate_types(const char* sample_id, const char* bestguess_file, const char* true_types_file, char* loci_out, int64_t loci_cap,
+                         int32_t* counts_out, int32_t max_loci, char* summary_out, int64_t summary_cap) {
+    if (!sample_id || !bestguess_file || !true_types_file) return fail(HLALA_E_ARG, "hlala_evaluate_types: null argument");
+    int n = 0;
+    int rc = guarded([&]() {
+        InferredTypes inf; TrueTypes tru; read_inferred_types(sample_id, inf, bestguess_file); read_true_types(tru, true_types_file);
+        std::string text; const std::map<std::string, std::pair<int, int>> r = evaluate_types(tru, inf, &text);
+        std::string loci; int i = 0;
+        for (const auto& kv : r) { if (i) loci += ';'; loci += kv.first; if (counts_out && i < max_loci) { counts_out[2 * i] = kv.second.first; counts_out[2 * i + 1] = kv.second.second; } i++; }
+        if (loci_out && loci_cap > 0) { snprintf(loci_out, (size_t)loci_cap, "%s", loci.c_str()); }
+        if (summary_out && summary_cap > 0) { snprintf(summary_out, (size_t)summary_cap, "%s", text.c_str()); }
+        n = i; return 0;
+    });
+    return rc == 0 ? n : rc;
+}
+
 int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll /* [C*R], index c*R + r */, const int32_t* mism /* [C*R] */, int termwise,
                             double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms) {
     if (C <= 0 || R < 0 || !ll || !mism || !pair_ll) return fail(HLALA_E_ARG, "hlala_typing_pair_probe: bad argument");

@@ -275,6 +275,10 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     const int nlev = l_last - l_first + 1;
     if (l_last + 1 >= G.n_levels) return HLALA_E_INVARIANT_DEV;
     if (nlev > P.slab_cols) return HLALA_E_CAPACITY_DEV;
+    // packed Viterbi keys: (score + 1) << KS | (rank mask - edge rank inside its level); KS = P.key_shift (20 for short reads: scores up to 4094; smaller for
+    // chains of thousands of columns, chosen from the graph's widest level). A chain whose score could leave the field is a capacity error, never a wrap-around.
+    const int KS = P.key_shift; const uint32_t RM = (1u << KS) - 1u;
+    if ((uint32_t)n + 2u >= (1u << (32 - KS))) return HLALA_E_CAPACITY_DEV;
     // stage the window: the packed edges of levels [l_first, l_first + nlev) are one contiguous range of edge_pack. Lane 0 hands the 16-byte
     // aligned superset of that range to the TMA engine; the per-level edge offsets (relative) and node counts are computed while it is in flight.
     const int e_base = G.level_edge_off[l_first];
@@ -296,7 +300,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     const int w0 = S.wwid[0];
     uint32_t* cur = S.cur; uint32_t* nxt = S.nxt;
     uint16_t* bt16 = (uint16_t*)S.bt; const int pool_cap = BT16 ? P.pool_cap * 2 : P.pool_cap;
-    for (int z = lane; z < w0; z += 32) cur[z] = (1u << 20) | KEY_RANK_MASK;
+    for (int z = lane; z < w0; z += 32) cur[z] = (1u << KS) | RM;
     __syncwarp();
     int pool = 0; int lev = l_first; int status = 0;
     for (int col = 0; col < n; col++) {
@@ -305,7 +309,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
         const int li = lev - l_first;
         const int e0 = S.weoff[li], e1 = S.weoff[li + 1];
         const int wn = S.wwid[li + 1];
-        if (BT16 && (e1 - e0) > 255) { status = HLALA_E_CAPACITY_DEV; break; }
+        if ((BT16 && (e1 - e0) > 255) || (uint32_t)(e1 - e0) > RM) { status = HLALA_E_CAPACITY_DEV; break; }
         if (pool + wn > pool_cap || pool > 65535) { status = HLALA_E_CAPACITY_DEV; break; }
         const uint8_t sc = c.s[col], gc = c.g[col]; const bool isMatch = (sc == gc);
         if (wn == 1 && S.wwid[li] == 1 && (e1 - e0) <= 32) {
@@ -314,12 +318,12 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
             if (e < e1) {
                 pk = staged ? win[e] : G.edge_pack[e_base + e];
                 const uint32_t kf = cur[0]; const uint8_t em = (uint8_t)(pk >> 16);
-                if (kf != 0 && !(isMatch && em != sc)) key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
+                if (kf != 0 && !(isMatch && em != sc)) key = (((kf >> KS) + (em == sc ? 1u : 0u)) << KS) | (RM - (uint32_t)(e - e0));
             }
             const uint32_t best = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) {
                 nxt[0] = best;
-                const uint32_t rank = KEY_RANK_MASK - (best & KEY_RANK_MASK);
+                const uint32_t rank = RM - (best & RM);
                 if (BT16) bt16[pool] = (uint16_t)rank; else S.bt[pool] = rank;       // from node is node 0
                 S.coloff[col] = (uint16_t)pool;
             }
@@ -334,7 +338,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
             uint32_t pk = staged ? win[e] : G.edge_pack[e_base + e];
             uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);
             if (kf != 0 && !(isMatch && em != sc)) {
-                uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
+                uint32_t key = (((kf >> KS) + (em == sc ? 1u : 0u)) << KS) | (RM - (uint32_t)(e - e0));
                 atomicMax(&nxt[(pk >> 8) & 255u], key);
             }
         }
@@ -343,7 +347,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
             uint32_t pk = staged ? win[e] : G.edge_pack[e_base + e];
             uint32_t kf = cur[pk & 255u]; uint8_t em = (uint8_t)(pk >> 16);
             if (kf != 0 && !(isMatch && em != sc)) {
-                uint32_t key = (((kf >> 20) + (em == sc ? 1u : 0u)) << 20) | (KEY_RANK_MASK - (uint32_t)(e - e0));
+                uint32_t key = (((kf >> KS) + (em == sc ? 1u : 0u)) << KS) | (RM - (uint32_t)(e - e0));
                 uint32_t tz = (pk >> 8) & 255u;
                 if (nxt[tz] == key) {                                    // the unique winner records (edge rank, from node)
                     if (BT16) bt16[pool + tz] = (uint16_t)((e - e0) | ((pk & 255u) << 8));
@@ -360,7 +364,7 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     // end nodes with maximal score; the first of them in canonical node order (processBAM.cpp:2856-2867)
     const int wl = S.wwid[nlev];
     uint32_t best = 0;
-    for (int z = lane; z < wl; z += 32) { uint32_t k = cur[z]; if (k) { uint32_t v = ((k >> 20) << 12) | (uint32_t)(4095 - min(z, 4095)); best = max(best, v); } }
+    for (int z = lane; z < wl; z += 32) { uint32_t k = cur[z]; if (k) { uint32_t v = ((k >> KS) << 12) | (uint32_t)(4095 - min(z, 4095)); best = max(best, v); } }
     for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
     if (best == 0) return HLALA_E_INVARIANT_DEV;                    // the reference asserts a non-empty column map
     if (lane == 0) {

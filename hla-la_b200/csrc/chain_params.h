@@ -12,7 +12,7 @@ namespace hlala {
 
 constexpr int K1_WARPS = 4;           // warps per CTA
 constexpr int K1_WCAP = 256;          // max nodes per level (edge_pack holds z in 8 bits)
-constexpr uint32_t KEY_RANK_MASK = 0xFFFFFu;   // 20 bits of edge rank inside a level, 11 bits of score+1 above
+constexpr uint32_t KEY_RANK_MASK = 0xFFFFFu;   // backtrack pool entries: 20 bits of edge rank inside a level, the from node above
 
 struct ChainParams {
     DevGraph g; DevBatch b;
@@ -45,6 +45,7 @@ struct ChainParams {
     // backtrack pool and level tables live in a per-warp slice of HBM (gslab_base, gslab_bytes each) and only the staged edge window, the two
     // node-score rows and the copy barrier stay in shared memory.
     int32_t long_mode, gslab; unsigned char* gslab_base; unsigned long long gslab_bytes;
+    int32_t key_shift;       // bit position of the score in the packed Viterbi keys (chain_kernel.cuh): 20 unless max_columns needs more score bits
 };
 
 constexpr int32_t CH_TODO = -100;

@@ -395,10 +395,12 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     std::mutex dev_mu; std::condition_variable dev_cv; size_t dev_turn = 0;
     auto take_turn = [&](size_t li) { std::unique_lock<std::mutex> lk(dev_mu); dev_cv.wait(lk, [&]() { return dev_turn == li; }); };
     auto pass_turn = [&](size_t li) { { std::lock_guard<std::mutex> lk(dev_mu); if (dev_turn == li) dev_turn = li + 1; } dev_cv.notify_all(); };
-    auto process = [&](size_t li) {
+    std::vector<uint8_t> entered_device(NL, 0);
+    auto process_locus = [&](size_t li) {
         TypingLocus& L = T.loci[li]; LocusCall& call = outs[li].call;
         std::string hist; std::ostringstream best, bestG;   // this locus' lines of histogram_matchesPerRead.txt / R1_bestguess.txt / R1_bestguess_G.txt
         call.locus = L.name; const int32_t C = L.C(), P = L.P(); call.C = C;
+        if (const char* e = getenv("HLALA_TEST_FAIL_LOCUS")) if ((size_t)atoi(e) == li) throw std::runtime_error("typing: locus " + L.name + " failed (HLALA_TEST_FAIL_LOCUS test hook)");
         // ---- exon observations per read pair
         std::unique_ptr<PhaseClock::Scope> ph(new PhaseClock::Scope(clk, 1));
         std::vector<std::vector<ExonObs>> reads;
@@ -487,7 +489,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             di.rec_off.push_back((int32_t)di.rec_pos.size());
         }
         ph.reset(new PhaseClock::Scope(clk, 6));
-        take_turn(li); try { dev.run_locus(di, opt.keep_read_ll, call.dev); } catch (...) { pass_turn(li); throw; } pass_turn(li);
+        take_turn(li); entered_device[li] = 1; try { dev.run_locus(di, opt.keep_read_ll, call.dev); } catch (...) { pass_turn(li); throw; } pass_turn(li);
         ph.reset(new PhaseClock::Scope(clk, 7));
         const std::vector<double>& LLs = call.dev.pair_ll; const std::vector<double>& Mavg = call.dev.pair_mavg; const std::vector<double>& Mmin = call.dev.pair_mmin;
         const size_t NPAIR = (size_t)C * ((size_t)C + 1) / 2; TY_REQUIRE(LLs.size() == NPAIR && Mavg.size() == NPAIR && Mmin.size() == NPAIR, "pair arrays complete");
@@ -562,6 +564,12 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         if (!opt.keep_read_ll) { call.dev.LL.clear(); call.dev.LL.shrink_to_fit(); call.dev.mism.clear(); call.dev.mism.shrink_to_fit(); }
         outs[li].hist = std::move(hist); outs[li].best = best.str(); outs[li].bestG = bestG.str();
         ph.reset();
+    };
+    // a locus that fails on this rank before its device stage still enters the per-locus collective (poisoned), so that all ranks fail together instead of
+    // the others waiting in the all-reduce for ever
+    auto process = [&](size_t li) {
+        try { process_locus(li); }
+        catch (...) { if (!entered_device[li]) { take_turn(li); try { dev.abort_locus(T.loci[li].C()); } catch (...) {} pass_turn(li); } throw; }
     };
     {
         std::atomic<size_t> next(0);

@@ -68,6 +68,9 @@ public:
     virtual ~TypingDevice() {}
     // want_read_ll: also return LL / mism (parity tests); the pair sums are always returned
     virtual void run_locus(const LocusDeviceInput& in, bool want_read_ll, LocusDeviceOutput& out) = 0;
+    // A locus failed on this rank before its device stage: with several ranks the per-locus collective must still be entered (the other ranks are
+    // waiting in it) and must tell them — the implementation contributes NaNs, which run_locus reports as an error on every rank.
+    virtual void abort_locus(int32_t /*C*/) {}
 };
 
 struct LocusCall { std::string locus; int32_t C = 0, R = 0; std::string call1, call2; double q1 = 0, q2 = 0; LocusDeviceOutput dev; };

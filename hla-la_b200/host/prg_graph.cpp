@@ -1,6 +1,8 @@
 #include "prg_graph.h"
 #include "arrayfile.h"
 #include <sys/stat.h>
+#include <dirent.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -62,7 +64,7 @@ static void load_contigs(const std::string& dir, FlatGraph& g);
 
 // Binary cache of the flat arrays next to graph.txt, reused when newer than its inputs — the role serializedGRAPH plays for the
 // reference (processBAM.cpp:37-53); its Boost text archive cannot be read without Boost and holds nothing graph.txt lacks.
-static const int64_t CACHE_VERSION = 3;
+static const int64_t CACHE_VERSION = 4;
 static time_t mtime_of(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 ? st.st_mtime : 0; }
 
 #define FG_I32(X) X(level_node_off) X(node_ord) X(node_level) X(level_edge_off) X(edge_from) X(edge_to) X(edge_ord) X(ord_to_edge) X(node_out_off) X(node_out) \
@@ -70,9 +72,24 @@ static time_t mtime_of(const std::string& p) { struct stat st; return stat(p.c_s
     X(contig_prg_id) X(contig_level) X(contig_tr_len) X(anchor_off) X(anchor_prg_id) X(anchor_pos)
 #define FG_U8(X) X(edge_emis) X(gap_stretch) X(contig_seq)
 
-static void save_cache(const std::string& path, const FlatGraph& g) {
+// Everything the cache is derived from: size and mtime of graph.txt, sequences.txt, the PRG-only FASTA and every translation/*.txt (contig_level and the
+// anchors are baked into the cache), folded into one 64-bit value that is stored with the arrays and compared on load.
+static int64_t inputs_signature(const std::string& dir) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&](uint64_t v) { for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 255u; h *= 0x100000001b3ull; } };
+    auto add = [&](const std::string& p) { struct stat st; if (stat(p.c_str(), &st) != 0) { mix(0); return; } mix((uint64_t)st.st_size); mix((uint64_t)st.st_mtime); for (char c : p) mix((unsigned char)c); };
+    add(dir + "/PRG/graph.txt"); add(dir + "/sequences.txt"); add(dir + "/mapping_PRGonly/referenceGenome.fa");
+    std::vector<std::string> tr;
+    if (DIR* dp = opendir((dir + "/translation").c_str())) { while (dirent* e = readdir(dp)) { std::string n = e->d_name; if (n != "." && n != "..") tr.push_back(n); } closedir(dp); }
+    std::sort(tr.begin(), tr.end());
+    for (const std::string& n : tr) add(dir + "/translation/" + n);
+    return (int64_t)(h & 0x7fffffffffffffffull);
+}
+
+static void save_cache(const std::string& path, const FlatGraph& g, int64_t sig) {
     try {
         ArrayFile f;
+        std::vector<int64_t> sigv{sig}; f.put("inputs_signature", DT_I64, sigv);
         std::vector<int64_t> meta{CACHE_VERSION, g.n_levels, g.n_nodes, g.n_edges, g.max_nodes_per_level, g.max_edges_per_level, g.n_paths, g.n_contigs};
         f.put("meta", DT_I64, meta);
 #define X(n) f.put(#n, DT_I32, g.n);
@@ -84,14 +101,17 @@ static void save_cache(const std::string& path, const FlatGraph& g) {
         f.put("contig_off", DT_I64, g.contig_off);
         auto blob = [](const std::vector<std::string>& v) { std::vector<uint8_t> b; for (const std::string& s : v) { b.insert(b.end(), s.begin(), s.end()); b.push_back('\n'); } return b; };
         f.put("level_names", DT_U8, blob(g.level_names)); f.put("contig_bam_name", DT_U8, blob(g.contig_bam_name));
-        f.write(path + ".tmp");
-        rename((path + ".tmp").c_str(), path.c_str());
+        const std::string tmp = path + ".tmp." + std::to_string((long long)getpid());      // two processes preparing the same PRG must not interleave their writes
+        f.write(tmp);
+        if (rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
     } catch (...) { /* a read-only PRG directory just means no cache */ }
 }
-static bool load_cache(const std::string& path, FlatGraph& g) {
+static bool load_cache(const std::string& path, FlatGraph& g, int64_t sig) {
     try {
         ArrayFile f; f.read(path);
-        uint64_t n = 0; const int64_t* meta = f.get<int64_t>("meta", &n);
+        uint64_t n = 0;
+        { const int64_t* s = f.get<int64_t>("inputs_signature", &n); if (n != 1 || s[0] != sig) return false; }
+        const int64_t* meta = f.get<int64_t>("meta", &n);
         if (n != 8 || meta[0] != CACHE_VERSION) return false;
         g.n_levels = (int32_t)meta[1]; g.n_nodes = (int32_t)meta[2]; g.n_edges = (int32_t)meta[3]; g.max_nodes_per_level = (int32_t)meta[4]; g.max_edges_per_level = (int32_t)meta[5];
         g.n_paths = (int32_t)meta[6]; g.n_contigs = (int32_t)meta[7];
@@ -112,9 +132,8 @@ void load_prg_dir(const std::string& dir, FlatGraph& g) {
     const std::string graph_path = dir + "/PRG/graph.txt";
     const std::string cache_path = dir + "/PRG/graph.hlala_b200.cache";
     {
-        time_t tc = mtime_of(cache_path);
-        if (tc && tc > mtime_of(graph_path) && tc > mtime_of(dir + "/sequences.txt") && tc > mtime_of(dir + "/mapping_PRGonly/referenceGenome.fa") && !getenv("HLALA_NO_GRAPH_CACHE")) {
-            if (load_cache(cache_path, g)) return;
+        if (mtime_of(cache_path) && !getenv("HLALA_NO_GRAPH_CACHE")) {
+            if (load_cache(cache_path, g, inputs_signature(dir))) return;
             g = FlatGraph();
         }
     }
@@ -252,7 +271,7 @@ void load_prg_dir(const std::string& dir, FlatGraph& g) {
     compute_gap_paths(g);
     compute_gap_stretches(g);
     load_contigs(dir, g);
-    if (!getenv("HLALA_NO_GRAPH_CACHE")) save_cache(cache_path, g);
+    if (!getenv("HLALA_NO_GRAPH_CACHE")) save_cache(cache_path, g, inputs_signature(dir));
 }
 
 // Graph::computeGapEdgePaths (Graph.cpp:347-476), containers keyed by canonical ordinals instead of pointers.

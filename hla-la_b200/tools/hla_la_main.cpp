@@ -60,6 +60,7 @@ int nccl_sum_f64(void* ctx, uint64_t dev_ptr, int64_t count, void* stream) {    
 }
 }
 
+static int evaluate_calls(std::map<std::string, std::string>& a, const std::string& out_dir);
 static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus) { fprintf(stderr, "hlala-b200: --gpus %d but %d CUDA devices are visible\n", n_gpus, ndev); return 1; }
@@ -128,9 +129,42 @@ static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     return 0;
 }
 
+// --trueHLA <file> (HLA-LA.cpp:801-810): hla/R1_bestguess.txt against known types, the reference's summary on stdout
+static int evaluate_calls(std::map<std::string, std::string>& a, const std::string& out_dir) {
+    if (!a.count("trueHLA") || a["trueHLA"].empty()) return 0;
+    std::vector<char> loci(4096), text(1 << 16); std::vector<int32_t> counts(2 * 64);
+    const std::string sample = a.count("sampleID") ? a["sampleID"] : std::string("sample");
+    const int n = hlala_evaluate_types(sample.c_str(), (out_dir + "/hla/R1_bestguess.txt").c_str(), a["trueHLA"].c_str(), loci.data(), (int64_t)loci.size(), counts.data(), 64, text.data(), (int64_t)text.size());
+    if (n < 0) return die("evaluating the inferred types");
+    fputs(text.data(), stdout);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     std::map<std::string, std::string> a;
-    for (int i = 1; i + 1 < argc; i += 2) { if (strncmp(argv[i], "--", 2) != 0) { fprintf(stderr, "hlala-b200: bad argument %s\n", argv[i]); return 2; } a[argv[i] + 2] = argv[i + 1]; }
+    // the argument surface of the reference binary (HLA-LA.cpp:60-92 collects --key value pairs; HLA-LA.pl:563 passes the keys below) plus this program's own
+    static const char* const known[] = {"action", "sampleID", "BAM", "outputDirectory", "PRG_graph_dir", "trueHLA", "maxThreads", "threads", "insertSizeMean", "insertSizeSD", "device", "gpus", "maxColumns",
+                                        "hla_nom_g_dir", "bwa_bin", "samtools_bin", "FASTQ1", "FASTQ2", "FASTQU", "longReads", "mapAgainstCompleteGenome", "remap_with_a", "workingDir", "graph"};
+    if ((argc - 1) % 2 != 0) { fprintf(stderr, "hlala-b200: arguments come as --key value pairs; '%s' has no value\n", argv[argc - 1]); return 2; }
+    for (int i = 1; i + 1 < argc; i += 2) {
+        if (strncmp(argv[i], "--", 2) != 0) { fprintf(stderr, "hlala-b200: bad argument %s\n", argv[i]); return 2; }
+        bool ok = false; for (const char* k : known) ok = ok || strcmp(k, argv[i] + 2) == 0;
+        if (!ok) { fprintf(stderr, "hlala-b200: unknown argument %s\n", argv[i]); return 2; }
+        a[argv[i] + 2] = argv[i + 1];
+    }
+    if (a.count("maxThreads") && !a.count("threads")) a["threads"] = a["maxThreads"];     // HLA-LA.pl passes --maxThreads
+    if (!a.count("action")) { fprintf(stderr, "\n\nMissing --action parameter. Please don't try calling me directly; use HLA-LA.pl instead (see documentation on GitHub).\n\n"); return 2; }     // HLA-LA.cpp:104-108
+    if (a["action"] == "testBinary") { fprintf(stdout, "\nHLA*LA binary functional!\n\n"); return 0; }                                                                                          // HLA-LA.cpp:129-132
+    if (a["action"] == "HLA" && !a.count("BAM") && (a.count("FASTQ1") || a.count("FASTQU"))) {
+        // HLA-LA.cpp:745-790: the reference maps the extracted FASTQ with `bwa mem -a -M` (BWAmapper::map / mapLong) and continues with the remapped BAM.
+        // bwa / samtools belong to the control plane that stays outside this program: run that step and pass its output as --BAM.
+        fprintf(stderr, "hlala-b200: --FASTQ1/--FASTQ2/--FASTQU: map the reads first (bwa mem -a -M <PRG_graph_dir>/mapping_PRGonly/referenceGenome.fa ... | samtools sort) and pass the result as --BAM\n");
+        return 2;
+    }
+    if (a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "") {
+        fprintf(stderr, "hlala-b200: --longReads %s: long reads are aligned through the C ABI (hlala_align_long_reads); HLA typing from unpaired reads (HLATyper.cpp:1467-1495, 3568) is not part of this program yet\n", a["longReads"].c_str());
+        return 2;
+    }
     if (a["action"] == "prepareGraph" && a.count("PRG_graph_dir")) {
         // HLA-LA.cpp:1341-1385 reads graph.txt, computes the gap-edge paths and serialises the pointer graph (hours and ~40 GB for the real
         // PRG). Here the flat arrays (gap paths included) are built in seconds and cached next to graph.txt (PRG/graph.hlala_b200.cache); the
@@ -147,7 +181,8 @@ int main(int argc, char** argv) {
     if (a["action"] != "HLA" || !a.count("BAM") || !a.count("outputDirectory") || !a.count("PRG_graph_dir")) {
         fprintf(stderr, "usage: hlala-b200 --action HLA --sampleID <id> --BAM <remapped.bam> --outputDirectory <dir> --PRG_graph_dir <dir>\n"
                         "       hlala-b200 --action prepareGraph --PRG_graph_dir <dir>\n"
-                        "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n> | --gpus <N>] [--maxColumns <n>] [--threads <n>]\n");
+                        "       hlala-b200 --action testBinary\n"
+                        "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n> | --gpus <N>] [--maxColumns <n>] [--maxThreads <n>] [--trueHLA <file>]\n");
         return 2;
     }
     if (a.count("gpus") && atoi(a["gpus"].c_str()) > 1) return run_multi_gpu(a, atoi(a["gpus"].c_str()));
@@ -206,5 +241,5 @@ int main(int argc, char** argv) {
         if (hlala_typer_result_call(t, l, &a1, &a2, &q1, &q2) == 0) fprintf(stdout, "%s\t%s\t%s\t%g\t%g\n", hlala_typer_locus_name(t, l), a1, a2, q1, q2);
     }
     hlala_typer_free(t); hlala_session_free(s); hlala_bam_batch_free(bam); hlala_graph_free(g);
-    return 0;
+    return evaluate_calls(a, out_dir);
 }

@@ -211,6 +211,15 @@ int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], do
 int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll, const int32_t* mism, int termwise,
                             double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms);
 
+/* Evaluation of the inferred types against known ones: what `--action HLA ... --trueHLA <file>` runs after the inference (HLA-LA.cpp:801-810):
+ *   hla::HLATyper::read_inferred_types(sampleID, inferred, R1_bestguess.txt)   hla/HLATyper.cpp:580-626
+ *   hla::HLATyper::read_true_types(truth, file)                                 hla/HLATyper.cpp:628-688
+ *   hla::HLATyper::evaluate_HLA_types(truth, inferred)                          hla/HLATyper.cpp:407-529 (alleles_compatible :530-578)
+ * Host only. loci_out: the evaluated loci, ';'-joined in the reference's map order; counts_out[2*i], [2*i+1] = alleles compared / correct of
+ * locus i (at most max_loci); summary_out: the text the reference prints. Returns the number of evaluated loci or a negative HLALA_E_* code. */
+int hlala_evaluate_types(const char* sample_id, const char* bestguess_file, const char* true_types_file, char* loci_out, int64_t loci_cap,
+                         int32_t* counts_out, int32_t max_loci, char* summary_out, int64_t summary_cap);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * k-mer seeding. Reference seam B5 of SURVEY.md §8b (no live caller in the reference: HLA-LA.cpp:230,1439 are commented out):
  *   hlala_kmer_index_build    GraphAndEdgeIndex::GraphAndEdgeIndex(Graph*, int k) -> Index()   Graph/GraphAndEdgeIndex.cpp:18-26, 428-959

@@ -382,6 +382,23 @@ int hlala_ref_type(void* h, const char* prg_dir, long long n_reads, const int64_
     return guarded([&]() { return d->run_type(b, prg_dir, is_mean, is_sd, out_dir, g_dir, threads, n_used, seconds); });
 }
 
+// The unmodified static evaluation functions (what --trueHLA runs, HLA-LA.cpp:801-810). loci ';'-joined in map order, counts [2 * n]: compared, correct.
+int hlala_ref_evaluate_types(const char* sample_id, const char* bestguess_file, const char* true_types_file, char* loci_out, long long loci_cap, int32_t* counts_out, int max_loci) {
+    int n = 0;
+    int rc = guarded([&]() {
+        std::map<std::string, std::map<std::string, std::pair<std::set<std::string>, std::set<std::string>>>> inferred;
+        std::map<std::string, std::map<std::string, std::pair<std::string, std::string>>> truth;
+        hla::HLATyper::read_inferred_types(sample_id, inferred, bestguess_file);
+        hla::HLATyper::read_true_types(truth, true_types_file);
+        std::map<std::string, std::pair<int, int>> r = hla::HLATyper::evaluate_HLA_types(truth, inferred);
+        std::string loci; int i = 0;
+        for (auto& kv : r) { if (i) loci += ';'; loci += kv.first; if (i < max_loci) { counts_out[2 * i] = kv.second.first; counts_out[2 * i + 1] = kv.second.second; } i++; }
+        snprintf(loci_out, (size_t)loci_cap, "%s", loci.c_str());
+        n = i; return 0;
+    });
+    return rc == 0 ? n : rc;
+}
+
 // ---- k-mer seeding (GraphAndEdgeIndex; dormant in the reference's own main(), HLA-LA.cpp:230,1439)
 struct KmerRef {
     GraphAndEdgeIndex* gi = nullptr; int k = 0;

@@ -34,6 +34,7 @@ DATASETS = {
     "genes": (dict(levels=30000, haps=8, genes=8, alleles=300), dict(pairs=250, len=150, clip_frac=0.15, gene_frac=1.0), 100.0, 10.0),
     # long-read mode (HLA-LA.pl --longReads): single reads of 3-6 kb, 3 % indels, half of them clipped by up to 400 bases, half starting in gene blocks
     "long": (dict(levels=40000, haps=6, genes=3, alleles=32, seed=41), dict(pairs=160, len=4000, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=400, gene_frac=0.5, seed=41), 0.0, 1.0),
+    "long8k": (dict(levels=60000, haps=6, genes=2, alleles=200, seed=45), dict(pairs=70, len=8000, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=400, gene_frac=0.5, seed=45), 0.0, 1.0),   # Viterbi scores beyond 4095: found a wrap-around of the packed keys
     "long_small": (dict(levels=12000, haps=4, genes=1, alleles=16, seed=43), dict(pairs=40, len=1500, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=200, gene_frac=0.5, seed=43), 0.0, 1.0),
     "L250": (dict(levels=20000, haps=6, genes=2, alleles=32, seed=21), dict(pairs=400, len=250, clip_frac=0.3, indel_rate=0.002, seed=21), 250.0, 35.0),
 }

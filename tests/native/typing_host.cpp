@@ -13,6 +13,10 @@ namespace {
 typedef int (*host_allreduce_fn)(double* data, long long count);   // sum over ranks, in place (the gloo test passes torch.distributed.all_reduce)
 struct LoopDevice : TypingDevice {   // HLATyper.cpp:2049-2364 restated as loops over the device input layout
     int rank = 0, world = 1; host_allreduce_fn allreduce = nullptr;   // reads split across ranks like the GPU device does (c_api.cu: r0 = R*rank/world)
+    void abort_locus(int32_t C) override {     // poisoned contribution, as the GPU device does (c_api.cu)
+        if (world <= 1 || !allreduce) return;
+        std::vector<double> v((size_t)3 * ((size_t)C * ((size_t)C + 1) / 2), NAN); allreduce(v.data(), (long long)v.size());
+    }
     void run_locus(const LocusDeviceInput& in, bool, LocusDeviceOutput& out) override {
         const int C = in.C, R = in.R; const int r0 = (int)((long long)R * rank / world), r1 = (int)((long long)R * (rank + 1) / world); const double ll_ins_actual = log(0.001) + log(1.0 / 4.0), ll_del = log(0.001), ll_mm = log(1 - 0.001 - 0.001);
         out.LL.assign((size_t)C * R, 0); out.mism.assign((size_t)C * R, 0);
@@ -32,6 +36,7 @@ struct LoopDevice : TypingDevice {   // HLATyper.cpp:2049-2364 restated as loops
             if (!allreduce) throw std::runtime_error("world > 1 needs an all-reduce callback");
             std::vector<double> v; v.insert(v.end(), out.pair_ll.begin(), out.pair_ll.end()); v.insert(v.end(), out.pair_mavg.begin(), out.pair_mavg.end()); v.insert(v.end(), out.pair_mmin.begin(), out.pair_mmin.end());
             if (allreduce(v.data(), (long long)v.size()) != 0) throw std::runtime_error("all-reduce callback failed");
+            if (!v.empty() && v[0] != v[0]) throw std::runtime_error("this locus failed on another rank (poisoned all-reduce)");
             const size_t n = out.pair_ll.size(); for (size_t i = 0; i < n; i++) { out.pair_ll[i] = v[i]; out.pair_mavg[i] = v[n + i]; out.pair_mmin[i] = v[2 * n + i]; }
         }
     }

@@ -62,6 +62,14 @@ def test_cache_round_trip(dataset, tmp_path):
     for k in H.Product.INT32 + H.Product.UINT8 + ["contig_off"]:
         assert np.array_equal(A.array(k), Bp.array(k)), k
     A.close(); Bp.close()
+    # an edited translation file (same mtime, other size) invalidates the cache: contig_level and the anchors are baked into it.
+    # The edit repeats a level, which the loader refuses — so a load that succeeds would have come from the stale cache.
+    tr = os.path.join(d2, "translation", sorted(os.listdir(os.path.join(d2, "translation")))[0])
+    st = os.stat(tr); lines = open(tr).read().split("\n"); lines[1] = lines[0]
+    open(tr, "w").write("\n".join(lines) + "\n\n"); os.utime(tr, (st.st_atime, st.st_mtime))
+    with pytest.raises(RuntimeError, match="translation"):
+        H.Product(d2)
+    assert not [f for f in os.listdir(os.path.join(d2, "PRG")) if ".tmp" in f]
 
 
 def test_missing_directory_reports_error(tmp_path):

@@ -57,9 +57,11 @@ def test_gpu_golden(dataset):
 
 
 @pytest.mark.gpu
-def test_gpu_long_reads_match_oracle(dataset):
-    d, b, mu, sd = dataset("long")
-    want = H.oracle_long_reads(d, b, 8192); got = product(d).long_reads(b, 8192)
+@pytest.mark.parametrize("name,cap", [("long", 8192), ("long8k", 10240)])
+def test_gpu_long_reads_match_oracle(dataset, name, cap):
+    d, b, mu, sd = dataset(name)
+    want = H.oracle_long_reads(d, b, cap); got = product(d).long_reads(b, cap)
+    assert name != "long8k" or want["n_cols"].max() > 8200
     n = want["n_cols"]
     assert np.array_equal(got["n_cols"], n) and np.array_equal(got["read_reverse"], want["read_reverse"])
     for r in range(len(n)):

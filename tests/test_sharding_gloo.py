@@ -62,7 +62,7 @@ def test_shard_bounds_cover_everything():
 
 
 # ---------------------------------------------------------------------------------------------------------------- typing exchange
-def _typing_worker(rank, world, d, port, out_root):
+def _typing_worker(rank, world, d, port, out_root, fail_rank=-1):
     """each rank runs the product's typing HOST logic (hla_typing.cpp) with the test-only loop stand-in for the kernels on its slice of the reads;
     the allele-pair vectors are combined with ONE gloo all-reduce per locus through the callback, as hlala_typer_infer does with NCCL"""
     import ctypes as C
@@ -82,9 +82,18 @@ def _typing_worker(rank, world, d, port, out_root):
     if out:
         os.makedirs(out, exist_ok=True)
     q = np.zeros(34, np.float64); ps = np.zeros(17, np.float64)
+    if rank == fail_rank:
+        os.environ["HLALA_TEST_FAIL_LOCUS"] = "3"
     n = lib.typing_host_run_ranked(d.encode(), C.c_longlong(len(b["read_off"]) - 1), H.p(b["read_off"]), H.p(b["bases"]), H.p(b["quals"]), C.c_int(512), H.p(aln["n_cols"]), H.p(aln["level"]),
                                    H.p(aln["gchar"]), H.p(aln["schar"]), H.p(aln["mapq"]), H.p(aln["read_reverse"]), H.p(rmq), C.c_double(100.0), C.c_double(10.0), out.encode(), C.c_int(1),
                                    C.c_int(rank), C.c_int(world), allreduce, H.p(q), H.p(ps))
+    if fail_rank >= 0:   # a locus that fails on one rank before its device stage: every rank returns an error, none is left waiting in the collective
+        msg = lib.typing_host_last_error().decode()
+        assert n != 17 and calls[0] == 17, (n, calls[0], msg)
+        assert ("test hook" in msg) if rank == fail_rank else ("another rank" in msg), msg
+        open(os.path.join(out_root, "failed_%d" % rank), "w").write(msg)
+        dist.barrier(); dist.destroy_process_group()
+        return
     assert n == 17, lib.typing_host_last_error().decode()
     assert calls[0] == 17
     if rank == 0:
@@ -111,3 +120,11 @@ def test_two_rank_typing_allreduce_matches_single_process(dataset, tmp_path):
     assert np.allclose(got[:34], q1, rtol=1e-9, atol=1e-12)
     assert open(os.path.join(multi, "hla", "R1_bestguess.txt")).read() == open(os.path.join(single, "R1_bestguess.txt")).read()
     assert sorted(os.listdir(os.path.join(multi, "hla"))) == sorted(os.listdir(single))
+
+
+def test_two_rank_typing_fails_together(dataset, tmp_path):
+    d, b, mu, sd = dataset("typing")
+    out = str(tmp_path / "multi"); os.makedirs(out)
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_typing_worker, args=(2, d, port, out, 1), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(out, "failed_0")) and os.path.exists(os.path.join(out, "failed_1"))
