@@ -193,9 +193,10 @@ def stage_kmer_seeding(args, root, H):
         ms = (C.c_double * 2)(); P._chk(P.lib.hlala_kmer_chains_timing(res, ms))
         nr = C.c_int64(); nc = C.c_int64(); ne = C.c_int64(); nf = C.c_int64()
         P._chk(P.lib.hlala_kmer_chains_dims(res, C.byref(nr), C.byref(nc), C.byref(ne), C.byref(nf)))
+        n2 = C.c_int64(); P._chk(P.lib.hlala_kmer_chains_second_tier_reads(res, C.byref(n2)))
         P.lib.hlala_kmer_chains_free(res)
         if best is None or ms[0] < best["kernel_ms"]:
-            best = dict(kernel_ms=ms[0], order_gather_ms=ms[1], call_s=dt, chains=nc.value, chain_edges=ne.value, reads_over_capacity=nf.value)
+            best = dict(kernel_ms=ms[0], order_gather_ms=ms[1], call_s=dt, chains=nc.value, chain_edges=ne.value, reads_second_tier=n2.value, reads_over_capacity=nf.value)
     n = len(off) - 1
     out = dict(workload="%d reads x %d bp, k=25, PRG of 1000000 levels / %d haplotypes / %d gene blocks x 8 alleles" % (n, args.read_len, args.haps, args.genes),
                index_build_host_s=t_index, reads_per_s_kernel=n / (best["kernel_ms"] / 1e3), reads_per_s_call_device_resident_output=n / best["call_s"], **best)

@@ -1057,7 +1057,7 @@ int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], do
 // ---------------------------------------------------------------------------------------------------------------------
 // k-mer seeding (reference seam B5 of SURVEY.md §8b)
 struct hlala_kmer_chains {
-    int64_t n_reads = 0, n_chains = 0, n_edges = 0, n_failed = 0;
+    int64_t n_reads = 0, n_chains = 0, n_edges = 0, n_failed = 0, n_second_tier = 0;
     DevBuf chain_off, read_status, begin, end, edge_off, edges;
     double ms[3] = {0, 0, 0};
 };
@@ -1119,7 +1119,7 @@ int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_km
         const int64_t nr = reads->n_reads; R->n_reads = nr;
         const int64_t nb = nr ? reads->read_off[nr] : 0; int64_t maxL = 0;
         for (int64_t r = 0; r < nr; r++) maxL = std::max<int64_t>(maxL, reads->read_off[r + 1] - reads->read_off[r]);
-        DevBuf d_off, d_bases, n_chains, recs, pool, counts, counters, chain_scratch, scan_scratch, ordered, ord_ne, temp;
+        DevBuf d_off, d_bases, n_chains, recs, pool, counts, counters, chain_scratch, scan_scratch, ordered, ord_ne, temp, defer_list, defer_count, read_tier, big_chain_scratch, big_scan_scratch;
         std::vector<int64_t> off0(1, 0);
         d_off.upload(nr ? reads->read_off : off0.data(), (size_t)nr + 1, st); d_bases.upload(reads->bases, (size_t)nb, st);
         n_chains.alloc((size_t)std::max<int64_t>(nr, 1) * 4); R->read_status.alloc((size_t)std::max<int64_t>(nr, 1) * 4);
@@ -1129,7 +1129,8 @@ int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_km
         chain_scratch.alloc((size_t)warps * SEED_RC * (size_t)P.ecap * 4); scan_scratch.alloc((size_t)warps * seed_scan_scratch_ints() * 4);
         P.chain_scratch = chain_scratch.as<int32_t>(); P.scan_scratch = scan_scratch.as<int32_t>();
         P.read_n_chains = n_chains.as<int32_t>(); P.read_status = R->read_status.as<int32_t>();
-        counts.alloc(16); counters.alloc(16);
+        counts.alloc(16); counters.alloc(16); defer_list.alloc((size_t)std::max<int64_t>(nr, 1) * 4); defer_count.alloc(4); read_tier.alloc((size_t)std::max<int64_t>(nr, 1));
+        P.defer_list = getenv("HLALA_SEED_NO_BIG_TIER") ? nullptr : defer_list.as<int32_t>(); P.defer_count = defer_count.as<int32_t>(); P.read_tier = read_tier.as<uint8_t>();     // (the variable is an A/B and test hook)
         P.rec_count = counts.as<unsigned long long>(); P.edge_count = counts.as<unsigned long long>() + 1; P.counters = counters.as<int32_t>();
         int64_t rec_cap = nr * 3 + 1024, edge_cap = nb * 3 + 65536;
         cudaEvent_t e0, e1, e2; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaEventCreate(&e2));
@@ -1137,9 +1138,17 @@ int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_km
         for (int attempt = 0; ; attempt++) {
             recs.alloc((size_t)rec_cap * sizeof(SeedChainRec)); pool.alloc((size_t)edge_cap * 4);
             P.recs = recs.as<SeedChainRec>(); P.rec_cap = rec_cap; P.edge_pool = pool.as<int32_t>(); P.edge_cap = edge_cap;
-            CUDA_OK(cudaMemsetAsync(counts.p, 0, 16, st)); CUDA_OK(cudaMemsetAsync(counters.p, 0, 16, st));
+            CUDA_OK(cudaMemsetAsync(counts.p, 0, 16, st)); CUDA_OK(cudaMemsetAsync(counters.p, 0, 16, st)); CUDA_OK(cudaMemsetAsync(defer_count.p, 0, 4, st));
             CUDA_OK(cudaEventRecord(e0, st));
             CUDA_OK(launch_seed_chains(P, g->n_sm, st));
+            int32_t n_def = 0; defer_count.download(&n_def, 1, st); CUDA_OK(cudaStreamSynchronize(st));
+            if (n_def > 0) {     // second tier: 1024 running chains per read, for the reads the first tier queued
+                SeedParams Q = P; const int bw = seed_big_warps_for(g->n_sm);
+                big_chain_scratch.alloc((size_t)bw * SEED_RC_BIG * (size_t)P.ecap * 4); big_scan_scratch.alloc((size_t)bw * seed_scan_scratch_ints() * 4);
+                Q.chain_scratch = big_chain_scratch.as<int32_t>(); Q.scan_scratch = big_scan_scratch.as<int32_t>();
+                CUDA_OK(launch_seed_chains_big(Q, g->n_sm, st));
+            }
+            R->n_second_tier = n_def;
             CUDA_OK(cudaEventRecord(e1, st));
             counts.download(cnt, 2, st); counters.download(ctr, 4, st);
             CUDA_OK(cudaStreamSynchronize(st));
@@ -1156,7 +1165,7 @@ int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_km
         long long total_chains = 0; CUDA_OK(cudaMemcpyAsync(&total_chains, R->chain_off.as<long long>() + nr, 8, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
         R->n_chains = total_chains;
         ordered.alloc((size_t)std::max<long long>(total_chains, 1) * sizeof(SeedChainRec)); ord_ne.alloc((size_t)std::max<long long>(total_chains, 1) * 4);
-        CUDA_OK(launch_seed_order(recs.as<SeedChainRec>(), (long long)cnt[0], R->chain_off.as<long long>(), R->read_status.as<int32_t>(), ordered.as<SeedChainRec>(), ord_ne.as<int32_t>(), st));
+        CUDA_OK(launch_seed_order(recs.as<SeedChainRec>(), (long long)cnt[0], R->chain_off.as<long long>(), R->read_status.as<int32_t>(), read_tier.as<uint8_t>(), ordered.as<SeedChainRec>(), ord_ne.as<int32_t>(), st));
         R->edge_off.alloc((size_t)(total_chains + 1) * 8);
         size_t need2 = 0; CUDA_OK(seed_exclusive_scan_i32_to_i64(ord_ne.as<int32_t>(), total_chains, R->edge_off.as<long long>(), nullptr, 0, &need2, st));
         if (need2 > need) { temp.alloc(need2 + 16); }
@@ -1173,6 +1182,7 @@ int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_km
         return 0;
     });
 }
+int hlala_kmer_chains_second_tier_reads(const hlala_kmer_chains_t* c, int64_t* n) { if (!c || !n) return fail(HLALA_E_ARG, "hlala_kmer_chains_second_tier_reads: null argument"); *n = c->n_second_tier; return 0; }
 int hlala_kmer_chains_dims(const hlala_kmer_chains_t* c, int64_t* n_reads, int64_t* n_chains, int64_t* n_edges, int64_t* n_failed_reads) {
     if (!c) return fail(HLALA_E_ARG, "hlala_kmer_chains_dims: null result");
     if (n_reads) *n_reads = c->n_reads; if (n_chains) *n_chains = c->n_chains; if (n_edges) *n_edges = c->n_edges; if (n_failed_reads) *n_failed_reads = c->n_failed;

@@ -24,7 +24,7 @@ namespace hlala {
 namespace {
 
 struct RunEnt { int32_t begin, n, target, slot; };
-struct SeedWarp { RunEnt run[SEED_RC]; uint16_t free_slots[SEED_RC]; int32_t n_run, n_free; };
+template <int RC> struct SeedWarpT { RunEnt run[RC]; uint16_t free_slots[RC]; int32_t n_run, n_free; };
 
 __device__ __forceinline__ I4 ldI4(const I4* p) { const int4 v = __ldg(reinterpret_cast<const int4*>(p)); I4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
 
@@ -84,17 +84,21 @@ __device__ int scan_slow(const DevGraph& G, int target, uint8_t c, int32_t* ss) 
 
 } // namespace
 
-__global__ void __launch_bounds__(SEED_WARPS * 32) k_seed_chains(SeedParams P) {
-    __shared__ SeedWarp sw[SEED_WARPS];
+// RC running chains per read; BIG: second tier over the reads the first one queued
+template <int RC, bool BIG> __global__ void __launch_bounds__(SEED_WARPS * 32) k_seed_chains(SeedParams P) {
+    extern __shared__ __align__(16) unsigned char seed_smem[];
+    typedef SeedWarpT<RC> SeedWarp;
+    constexpr int SEED_RC = RC;     // (shadows the first tier's constant inside this kernel)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SeedWarp& W = sw[warp];
+    SeedWarp& W = reinterpret_cast<SeedWarp*>(seed_smem)[warp];
     const DevGraph& G = P.g; const DevKmerIndex& ix = P.ix; const int k = ix.k; const int ecap = P.ecap;
     const size_t gw = (size_t)blockIdx.x * SEED_WARPS + warp;
     int32_t* cs = P.chain_scratch + gw * (size_t)SEED_RC * ecap;
     int32_t* ss = P.scan_scratch + gw * (size_t)(SEED_SCAN_NB + SEED_SCAN_CB) * SEED_SCAN_PLEN;
     for (;;) {
-        long long r = 0; if (lane == 0) r = atomicAdd(P.counters, 1); r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= P.n_reads) break;
+        long long r = 0;
+        if (BIG) { int qi = 0; if (lane == 0) qi = atomicAdd(P.counters + 3, 1); qi = __shfl_sync(0xffffffffu, qi, 0); if (qi >= *P.defer_count) break; r = P.defer_list[qi]; }
+        else { if (lane == 0) r = atomicAdd(P.counters, 1); r = __shfl_sync(0xffffffffu, r, 0); if (r >= P.n_reads) break; }
         const int64_t rd0 = P.read_off[r]; const int L = (int)(P.read_off[r + 1] - rd0); const uint8_t* seq = P.bases + rd0;
         int status = 0, ord = 0;
         for (int i = lane; i < SEED_RC; i += 32) W.free_slots[i] = (uint16_t)(SEED_RC - 1 - i);
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_seed_chains(SeedParams P) {
             if ((long long)ri < P.rec_cap && (long long)(eo + e.n) <= P.edge_cap) {
                 const int32_t* src = cs + (size_t)e.slot * ecap;
                 for (int j = lane; j < e.n; j += 32) P.edge_pool[eo + j] = src[j];
-                if (lane == 0) { SeedChainRec rec; rec.read = (int32_t)r; rec.ord = ord; rec.begin = e.begin; rec.end = end; rec.edge_off = (long long)eo; rec.n_edges = e.n; rec.pad = 0; P.recs[ri] = rec; }
+                if (lane == 0) { SeedChainRec rec; rec.read = (int32_t)r; rec.ord = ord; rec.begin = e.begin; rec.end = end; rec.edge_off = (long long)eo; rec.n_edges = e.n; rec.pad = BIG ? 1 : 0; P.recs[ri] = rec; }
             } else if (lane == 0) P.counters[2] = 1;
             ord++;
         };
@@ -227,16 +231,20 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) k_seed_chains(SeedParams P) {
             // ---- remaining chains in list order (:344-348)
             if (!status) { const int n1 = W.n_run; for (int i = 0; i < n1; i++) archive(i, L - 1); }
         }
-        if (lane == 0) { P.read_n_chains[r] = status ? 0 : ord; P.read_status[r] = status; if (status) atomicAdd(P.counters + 1, 1); }
+        if (lane == 0) {
+            P.read_n_chains[r] = status ? 0 : ord; P.read_status[r] = status;
+            if (!BIG && status == HLALA_E_CAPACITY_DEV && P.defer_list) { P.read_tier[r] = 1; P.defer_list[atomicAdd(P.defer_count, 1)] = (int32_t)r; }     // the records archived so far are void: the second tier starts over
+            else { P.read_tier[r] = BIG ? 1 : 0; if (status) atomicAdd(P.counters + 1, 1); }
+        }
         __syncwarp();
     }
 }
 
-__global__ void k_seed_order(const SeedChainRec* recs, long long n, const long long* chain_off, const int32_t* read_status, SeedChainRec* out, int32_t* out_n_edges) {
+__global__ void k_seed_order(const SeedChainRec* recs, long long n, const long long* chain_off, const int32_t* read_status, const uint8_t* read_tier, SeedChainRec* out, int32_t* out_n_edges) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const SeedChainRec r = recs[i];
-    if (read_status[r.read] != 0) return;   // chains archived before the read hit a capacity error are dropped with it
+    if (read_status[r.read] != 0 || (int)read_tier[r.read] != r.pad) return;   // chains archived before the read hit a capacity error are dropped with it (and replaced by the next tier's)
     const long long o = chain_off[r.read] + r.ord;
     out[o] = r; out_n_edges[o] = r.n_edges;
 }
@@ -250,11 +258,13 @@ __global__ void k_seed_gather(DevGraph G, const SeedChainRec* ordered, long long
     for (int j = lane; j < r.n_edges; j += 32) out_edges[o + j] = G.edge_ord[pool[r.edge_off + j]];
 }
 
+static size_t seed_smem_bytes(bool big) { return (big ? sizeof(SeedWarpT<SEED_RC_BIG>) : sizeof(SeedWarpT<SEED_RC>)) * SEED_WARPS; }
 int seed_warps_for(int n_sm) {
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_chains, SEED_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_chains<SEED_RC, false>, SEED_WARPS * 32, seed_smem_bytes(false)) != cudaSuccess || per_sm < 1) per_sm = 1;
     return n_sm * per_sm * SEED_WARPS;
 }
+int seed_big_warps_for(int n_sm) { return std::max(1, n_sm / 2) * SEED_WARPS; }     // a handful of reads: half a wave of CTAs keeps the chain scratch (1024 chains per warp) small
 size_t seed_scan_scratch_ints() { return (size_t)(SEED_SCAN_NB + SEED_SCAN_CB) * SEED_SCAN_PLEN; }
 
 cudaError_t launch_seed_chains(const SeedParams& P, int n_sm, cudaStream_t st) {
@@ -262,13 +272,18 @@ cudaError_t launch_seed_chains(const SeedParams& P, int n_sm, cudaStream_t st) {
     const int warps = seed_warps_for(n_sm);
     long long want = (P.n_reads + SEED_WARPS - 1) / SEED_WARPS;
     int grid = (int)std::min<long long>(want, warps / SEED_WARPS); if (grid < 1) grid = 1;
-    k_seed_chains<<<grid, SEED_WARPS * 32, 0, st>>>(P);
+    k_seed_chains<SEED_RC, false><<<grid, SEED_WARPS * 32, seed_smem_bytes(false), st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_seed_chains_big(const SeedParams& P, int n_sm, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_seed_chains<SEED_RC_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(true)); if (e != cudaSuccess) return e;
+    k_seed_chains<SEED_RC_BIG, true><<<seed_big_warps_for(n_sm) / SEED_WARPS, SEED_WARPS * 32, seed_smem_bytes(true), st>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_seed_order(const SeedChainRec* recs, long long n_recs, const long long* chain_off, const int32_t* read_status, SeedChainRec* out, int32_t* out_n_edges, cudaStream_t st) {
+cudaError_t launch_seed_order(const SeedChainRec* recs, long long n_recs, const long long* chain_off, const int32_t* read_status, const uint8_t* read_tier, SeedChainRec* out, int32_t* out_n_edges, cudaStream_t st) {
     if (n_recs <= 0) return cudaSuccess;
-    k_seed_order<<<(unsigned)((n_recs + 255) / 256), 256, 0, st>>>(recs, n_recs, chain_off, read_status, out, out_n_edges);
+    k_seed_order<<<(unsigned)((n_recs + 255) / 256), 256, 0, st>>>(recs, n_recs, chain_off, read_status, read_tier, out, out_n_edges);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <exception>
+#include <functional>
 #include <memory>
 #include <thread>
 #include <mutex>
@@ -306,6 +307,13 @@ struct KmerSet {
     }
 };
 
+struct KmerShards {     // a KmerSet split by hash, one shard per builder thread
+    std::vector<KmerSet> shard;
+    explicit KmerShards(unsigned n) : shard(n ? n : 1) {}
+    unsigned owner(uint64_t k) const { return (unsigned)((KmerSet::mix(k) >> 40) % shard.size()); }
+    bool has(uint64_t k) const { return shard[owner(k)].has(k); }
+};
+
 // HLALA_TYPING_PROFILE=1: wall time per phase of run_typing, summed over loci / threads, on stderr
 struct PhaseClock {
     static constexpr int N = 10; std::atomic<long long> ns[N]; bool on;
@@ -326,20 +334,35 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     PhaseClock clk; std::unique_ptr<PhaseClock::Scope> ph0(new PhaseClock::Scope(clk, 0));
     const size_t NP = in.n_pairs(); TY_REQUIRE(NP > 0, "rawPairedReads.size() > 0");
     std::vector<Mate> mates(2 * NP);
-    for (size_t r = 0; r < 2 * NP; r++) {
-        Mate& m = mates[r]; const int64_t c0 = in.col_off[r], b0 = in.base_off[r];
-        m.n = (int)(in.col_off[r + 1] - c0); m.level = in.level.data() + c0; m.g = in.g.data() + c0; m.s = in.s.data() + c0; m.mq = in.mq.data() + c0;
-        m.len = (int)(in.base_off[r + 1] - b0); m.bases = in.bases.data() + b0; m.quals = in.quals.data() + b0; m.reverse = in.reverse[r] != 0; m.mapQ = in.mapq[r]; m.name = &in.name[r / 2];
-        mate_stats(m);
-    }
+    // per-read statistics and the 31-mer set of the reads, on the host thread pool: reads are dealt in blocks; the k-mer set is sharded by hash so that every
+    // thread owns one shard (each scans all reads and keeps the k-mers of its shard: scanning is cheap, inserting is what costs)
+    unsigned pro_threads = opt.threads > 0 ? (unsigned)opt.threads : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("HLALA_HOST_THREADS")) pro_threads = std::min<unsigned>(pro_threads, (unsigned)std::max(1, atoi(e)));
+    if (2 * NP < 4096) pro_threads = 1;
+    auto on_pool = [&](const std::function<void(unsigned)>& f) {
+        std::vector<std::exception_ptr> errs(pro_threads); std::vector<std::thread> th;
+        auto body = [&](unsigned t) { try { f(t); } catch (...) { errs[t] = std::current_exception(); } };
+        for (unsigned t = 1; t < pro_threads; t++) th.emplace_back(body, t);
+        body(0); for (auto& x : th) x.join();
+        for (auto& e : errs) if (e) std::rethrow_exception(e);
+    };
+    on_pool([&](unsigned t) {
+        for (size_t r = (size_t)t * 2 * NP / pro_threads; r < (size_t)(t + 1) * 2 * NP / pro_threads; r++) {
+            Mate& m = mates[r]; const int64_t c0 = in.col_off[r], b0 = in.base_off[r];
+            m.n = (int)(in.col_off[r + 1] - c0); m.level = in.level.data() + c0; m.g = in.g.data() + c0; m.s = in.s.data() + c0; m.mq = in.mq.data() + c0;
+            m.len = (int)(in.base_off[r + 1] - b0); m.bases = in.bases.data() + b0; m.quals = in.quals.data() + b0; m.reverse = in.reverse[r] != 0; m.mapQ = in.mapq[r]; m.name = &in.name[r / 2];
+            mate_stats(m);
+            for (int i = 0; i < m.len; i++) { unsigned char c = m.bases[i]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N' || c == 'a' || c == 'c' || c == 'g' || c == 't' || c == 'n' || c == '_' || c == '*')) throw std::runtime_error("typing: reverse complement of unknown character"); }
+        }
+    });
     // constants of HLATypeInference (HLATyper.cpp:944-946, 1032, 1551-1640)
     const double min_mapq = 0.0, min_pos_mapq = 0.7, min_weighted = 0.0, f20_min_prop = 0.1, unacc_min_frac = 0.2; const int F20N = 20, f20_limit = 2, high_cov = 100, unacc_min_cov = 30;
 
-    KmerSet read_kmers;
-    for (size_t r = 0; r < 2 * NP; r++) {   // k-mers of the raw read == k-mers of the BAM-orientation read after canonicalisation
-        for (int i = 0; i < mates[r].len; i++) { unsigned char c = mates[r].bases[i]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N' || c == 'a' || c == 'c' || c == 'g' || c == 't' || c == 'n' || c == '_' || c == '*')) throw std::runtime_error("typing: reverse complement of unknown character"); }
-        KmerSet::scan(mates[r].bases, (size_t)mates[r].len, [&](uint64_t k) { read_kmers.insert(k); }, []() {});
-    }
+    KmerShards read_kmers(pro_threads);     // k-mers of the raw read == k-mers of the BAM-orientation read after canonicalisation
+    on_pool([&](unsigned t) {
+        KmerSet& mine = read_kmers.shard[t];
+        for (size_t r = 0; r < 2 * NP; r++) KmerSet::scan(mates[r].bases, (size_t)mates[r].len, [&](uint64_t k) { if (read_kmers.owner(k) == t) mine.insert(k); }, []() {});
+    });
 
     ph0.reset();
     // out_dir empty: compute only (ranks other than 0 of a multi-GPU run); every stream then goes to /dev/null

@@ -226,7 +226,7 @@ int hlala_evaluate_types(const char* sample_id, const char* bestguess_file, cons
  *   hlala_kmer_index_export   getIndexedkMers() + queryIndex() over the whole index            Graph/GraphAndEdgeIndex.cpp:28-38, 986-997
  *   hlala_seed_kmers          std::vector<kMerEdgeChain*> findChains(std::string sequence)     Graph/GraphAndEdgeIndex.cpp:39-356
  * The index is built on the host from the flat graph and uploaded; hlala_seed_kmers runs on the GPU only. A read whose working set
- * exceeds the kernel's capacities (128 running chains, chains of 3 x the longest read) gets read_status HLALA_E_CAPACITY and no chains. */
+ * exceeds the kernel's capacities (1024 running chains in the second tier, chains of 3 x the longest read) gets read_status HLALA_E_CAPACITY and no chains. */
 int hlala_kmer_index_build(hlala_graph_t* g, int k);
 int hlala_kmer_index_dims(const hlala_graph_t* g, int32_t* k, int64_t* n_kmers, int64_t* n_positions, int64_t* n_edges);
 /* k-mers ascending ([n_kmers * k] bytes, std::map<std::string> order), pos_off [n_kmers+1], edge_off [n_positions+1], edges as canonical
@@ -241,6 +241,8 @@ typedef struct {
 typedef struct hlala_kmer_chains hlala_kmer_chains_t;   /* result, device resident, owned by the library */
 int hlala_seed_kmers(hlala_graph_t* g, const hlala_read_batch_t* reads, hlala_kmer_chains_t** out);
 int hlala_kmer_chains_dims(const hlala_kmer_chains_t* c, int64_t* n_reads, int64_t* n_chains, int64_t* n_edges, int64_t* n_failed_reads);
+/* reads that exceeded the first tier's 128 running chains and were re-run by the second tier (1024 running chains); a read beyond that is a failed read */
+int hlala_kmer_chains_second_tier_reads(const hlala_kmer_chains_t* c, int64_t* n);
 /* chains of read r: [chain_off[r], chain_off[r+1]) in the order findChains returns them; per chain sequence_begin / sequence_end and
  * traversedEdges = edges[edge_off[c] .. edge_off[c+1]) as canonical edge ordinals. Caller-allocated host arrays, any may be NULL. */
 int hlala_kmer_chains_fetch(const hlala_kmer_chains_t* c, int64_t* chain_off, int32_t* read_status, int32_t* seq_begin, int32_t* seq_end,

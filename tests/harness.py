@@ -642,6 +642,7 @@ class Product:
                      edge_off=np.zeros(nc.value + 1, np.int64), edges=np.zeros(max(ne.value, 1), np.int32), n_failed=nf.value)
             self._chk(self.lib.hlala_kmer_chains_fetch(res, p(o["chain_off"]), p(o["status"]), p(o["begin"]), p(o["end"]), p(o["edge_off"]), p(o["edges"])))
             ms = (C.c_double * 2)(); self._chk(self.lib.hlala_kmer_chains_timing(res, ms)); o["ms"] = list(ms)
+            n2 = C.c_int64(); self._chk(self.lib.hlala_kmer_chains_second_tier_reads(res, C.byref(n2))); o["n_second_tier"] = n2.value
             o["begin"] = o["begin"][:nc.value]; o["end"] = o["end"][:nc.value]; o["edges"] = o["edges"][:ne.value]; o["status"] = o["status"][:nr.value]
             return o
         finally:

@@ -140,9 +140,10 @@ def test_gpu_chains_match_oracle(dataset, name, k, n, length):
 
 
 @pytest.mark.gpu
-def test_gpu_chains_capacity_is_reported(dataset):
-    """a short k in a 14-node-wide gene region keeps hundreds of chains alive: reads beyond the kernel's 128 running chains are flagged
-    HLALA_E_CAPACITY and carry no chains, every other read is exact"""
+def test_gpu_chains_second_tier_and_capacity(dataset):
+    """a short k in a 14-node-wide gene region keeps hundreds of chains alive. Reads beyond the first tier's 128 running chains are re-run by the second
+    tier (1024 running chains) and are exact; what exceeds that as well is flagged HLALA_E_CAPACITY and carries no chains, never a silent truncation"""
+    import os
     d, _b, _mu, _sd = dataset("genes")
     G = H.Oracle(d).graph()
     P = gpu_product(d)
@@ -151,9 +152,18 @@ def test_gpu_chains_capacity_is_reported(dataset):
         off, bases = H.walk_reads(G, 300, 150, seed)
         want = O.find_chains(off, bases)
         P.kmer_index(k)
+        os.environ["HLALA_SEED_NO_BIG_TIER"] = "1"
+        try:
+            one = P.find_chains(off, bases)
+        finally:
+            os.environ.pop("HLALA_SEED_NO_BIG_TIER")
+        n_failed_one_tier = assert_reads_equal(one, want, allow_capacity=True)
         got = P.find_chains(off, bases)
         n_failed = assert_reads_equal(got, want, allow_capacity=True)
-        assert 0 < n_failed < 300 if k == 9 else n_failed < 100
+        assert one["n_second_tier"] == 0 and got["n_second_tier"] == n_failed_one_tier
+        assert 0 < n_failed_one_tier < (300 if k == 9 else 100) and n_failed < n_failed_one_tier
+        if k == 12:
+            assert n_failed == 0
         O.close()
 
 
