@@ -6,6 +6,7 @@
 #include "extend_lean_kernel.cuh"
 #include "pair_kernel.cuh"
 #include "align_kernels.h"
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
 
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_chain_seed(ChainParams P) {
             if (lane == 0) {
                 P.n_cols[slot] = n; P.first_level[slot] = l_first; P.last_level[slot] = l_last; P.status[slot] = CH_PENDING_EXT;
                 int idx = atomicAdd(P.pending_count, 1); P.pending_slots[idx] = slot;
-                if (need_left) { const int i = atomicAdd(P.dp_task_count, 1); const int bin = 255 - min(start_raw, 255); P.dp_tasks[i] = 2 * idx; P.dp_task_bin[i] = (uint8_t)bin; atomicAdd(P.dp_task_hist + bin, 1); }
-                if (need_right) { const int i = atomicAdd(P.dp_task_count, 1); const int bin = 255 - min(rdlen - 1 - stop_raw, 255); P.dp_tasks[i] = 2 * idx + 1; P.dp_task_bin[i] = (uint8_t)bin; atomicAdd(P.dp_task_hist + bin, 1); }
+                if (need_left) { const int i = atomicAdd(P.dp_task_count, 1); const int bin = 255 - min(start_raw, 255); P.dp_tasks[i] = 2 * idx; P.dp_task_bin[i] = (uint8_t)bin; P.dp_task_key[i] = l_first; atomicAdd(P.dp_task_hist + bin, 1); }
+                if (need_right) { const int i = atomicAdd(P.dp_task_count, 1); const int bin = 255 - min(rdlen - 1 - stop_raw, 255); P.dp_tasks[i] = 2 * idx + 1; P.dp_task_bin[i] = (uint8_t)bin; P.dp_task_key[i] = l_last + 1; atomicAdd(P.dp_task_hist + bin, 1); }
             }
             __syncwarp();
             continue;
@@ -460,6 +461,13 @@ __global__ void __launch_bounds__(1024) k_sort_dp_tasks(const int32_t* tasks, co
 cudaError_t launch_sort_dp_tasks(const ChainParams& P, int32_t* sorted, cudaStream_t stream) {
     k_sort_dp_tasks<<<1, 1024, 0, stream>>>(P.dp_tasks, P.dp_task_bin, P.dp_task_hist, P.dp_task_count, sorted);
     return cudaGetLastError();
+}
+
+// Extension tasks ordered by the level they start from (radix sort of (level, task) pairs; n covers the unused slots, whose keys are large): the threads of a
+// warp then walk neighbouring windows of the graph - the same level records, the same bubbles and jumps - instead of 32 unrelated ones.
+cudaError_t sort_dp_tasks_by_level(const int32_t* keys_in, int32_t* keys_out, const int32_t* tasks_in, int32_t* tasks_out, int n, void* temp, size_t temp_bytes, size_t* need_bytes, cudaStream_t stream) {
+    if (!temp) { size_t need = 0; cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, tasks_in, tasks_out, n, 0, 31, stream); *need_bytes = need; return e; }
+    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, tasks_in, tasks_out, n, 0, 31, stream);
 }
 
 // thread-per-extension tier (extend_lean.h): cfg 0 = LnStd over the task list, cfg 1 = LnBig over what LnStd deferred

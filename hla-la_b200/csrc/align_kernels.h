@@ -10,6 +10,7 @@ cudaError_t upload_score_tables(const ScoreTables& t, const ScoreTables& t_long)
 cudaError_t launch_prepare(const ChainParams& P, cudaStream_t stream);
 cudaError_t launch_chain_seed(const ChainParams& P, int n_sm, cudaStream_t stream);
 int chain_seed_max_warps(const ChainParams& P, int n_sm);
+cudaError_t sort_dp_tasks_by_level(const int32_t* keys_in, int32_t* keys_out, const int32_t* tasks_in, int32_t* tasks_out, int n, void* temp, size_t temp_bytes, size_t* need_bytes, cudaStream_t stream);
 size_t pair_gslab_bytes(int maxcol, int tier);      // per-warp bytes of the pair kernel's HBM slab for this max_columns (0: the slab fits shared memory)
 cudaError_t launch_extend(const ExtParams& E, cudaStream_t stream);
 cudaError_t launch_extend_warp(const ExtParams& E, int n_sm, int cfg, bool only_deferred, cudaStream_t stream);

@@ -166,7 +166,7 @@ struct ChainScratch {   // per-chain results of the whole batch
 // One in-flight wave: its column scratch, work lists, extension buffers, DP working memory and stream. Waves alternate between the
 // lanes, so the low-occupancy tail of one wave's extension cascade overlaps the next wave's chain kernel and first DP tier.
 struct Lane {
-    DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count, dp_tasks, dp_task_count, dp_task_bin, dp_task_hist, dp_sorted;
+    DevBuf c_edge, c_schar, c_fromseed, pending_slots, pending_count, todo_slots, todo_count, defer_slots, defer_count, dp_tasks, dp_task_count, dp_task_bin, dp_task_hist, dp_sorted, dp_task_key, dp_key_sorted, dp_sort_temp;
     DevBuf pair_gslab[2];
     DevBuf pair_defer, pair_defer_count;   // pairs queued for the large tier of the pair kernel
     DevBuf ln_rec, ln_ahead;   // thread-per-extension tier: 16-byte cell records and the ahead table of every resident thread
@@ -182,7 +182,7 @@ struct Lane {
         pending_slots.alloc(wc * 4); pending_count.alloc(4); todo_slots.alloc(wc * 4); todo_count.alloc(4); defer_slots.alloc(wc * 4); defer_count.alloc(4);
         dp_scratch.alloc(dp_bytes); wd_scratch.alloc(wd_bytes); gd_scratch.alloc(gd_bytes); q_ctr.alloc(128);
         pair_defer.alloc(wc * 2 + 64); pair_defer_count.alloc(4);     // at most one entry per pair; a pair has >= 2 chains
-        dp_tasks.alloc(wc * 8); dp_task_count.alloc(4); dp_task_bin.alloc(wc * 2); dp_task_hist.alloc(1024); dp_sorted.alloc(wc * 8); ln_rec.alloc(ln_rec_bytes); ln_ahead.alloc(ln_ahead_bytes);
+        dp_tasks.alloc(wc * 8); dp_task_key.alloc(wc * 8); dp_key_sorted.alloc(wc * 8); dp_task_count.alloc(4); dp_task_bin.alloc(wc * 2); dp_task_hist.alloc(1024); dp_sorted.alloc(wc * 8); ln_rec.alloc(ln_rec_bytes); ln_ahead.alloc(ln_ahead_bytes);
         if (!n_pending_host) { CUDA_OK(cudaMallocHost((void**)&n_pending_host, 4)); *n_pending_host = 0; }
         if (!stream) CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (!front_done) { CUDA_OK(cudaEventCreateWithFlags(&front_done, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); }
@@ -192,7 +192,7 @@ struct Lane {
         P.pending_slots = pending_slots.as<int32_t>(); P.pending_count = pending_count.as<int32_t>();
         P.todo_slots = todo_slots.as<int32_t>(); P.todo_count = todo_count.as<int32_t>();
         P.defer_slots = defer_slots.as<int32_t>(); P.defer_count = defer_count.as<int32_t>();
-        P.dp_tasks = dp_tasks.as<int32_t>(); P.dp_task_count = dp_task_count.as<int32_t>(); P.dp_task_bin = dp_task_bin.as<uint8_t>(); P.dp_task_hist = dp_task_hist.as<int32_t>();
+        P.dp_tasks = dp_tasks.as<int32_t>(); P.dp_task_count = dp_task_count.as<int32_t>(); P.dp_task_bin = dp_task_bin.as<uint8_t>(); P.dp_task_hist = dp_task_hist.as<int32_t>(); P.dp_task_key = dp_task_key.as<int32_t>();
     }
 };
 
@@ -248,7 +248,7 @@ struct Pipeline {
     ~Pipeline() { if (fork_ev) cudaEventDestroy(fork_ev); }
     bool scalar_dp_only = false;   // test hook: run every extension through the scalar kernel
     int32_t n_gd_groups = 0; bool group_dp = true; bool dp_trace = false;
-    bool lean_big = false;
+    int32_t ln_batch = 16; bool lean_big = false; bool sort_by_level = true;      // extension tasks in level order (HLALA_DP_SORT=clip: by clipped length, longest first)
     bool long_mode = false; DevBuf gslab; size_t gslab_bytes = 0;     // long-read mode (alignOneLongRead): one read per unit, no extension DP, chain buffers in HBM
     int32_t n_ln_threads = 0; bool lean_dp = true;   // first DP tier: one thread per extension (extend_lean.h); false: the 8-lane group kernel (A/B runs)
     DevBuf bpl_ws; std::vector<int32_t> bpl_host;   // per-level coverage of a host-buffer call
@@ -321,6 +321,8 @@ struct Pipeline {
         if (!fork_ev) CUDA_OK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
         CUDA_OK(cudaStreamSynchronize(st));   // the lanes' own streams start from initialised scratch
         if (getenv("HLALA_DP_TRACE")) dp_trace = true;
+        if (const char* e = getenv("HLALA_DP_SORT")) sort_by_level = strcmp(e, "clip") != 0;
+        if (const char* e = getenv("HLALA_LN_BATCH")) ln_batch = std::max(1, std::min(32, atoi(e)));
         if (getenv("HLALA_NO_GROUP_DP")) group_dp = false;               // test hook: first tier = warp kernel, tiny configuration
         if (allow_env_budget && getenv("HLALA_ALIGN_DUPLICATES")) dedup = false;   // align the chains k_prepare would skip
     }
@@ -353,7 +355,7 @@ struct Pipeline {
         out[0] = n; out[1] = ck; out[2] = algo_fixed + chains_part;
     }
     // defaults of everything the test hooks (environment variables read in prepare) can change; a workspace kept across calls starts from them
-    void reset_config() { long_mode = false; scratch_budget = 0; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
+    void reset_config() { ln_batch = 16; sort_by_level = true; long_mode = false; scratch_budget = 0; allow_env_budget = true; dedup = true; n_lanes_max = 3; scalar_dp_only = false; group_dp = true; lean_dp = true; dp_trace = false; }
     void ensure_columns() {
         if (have_columns) return;
         size_t n = (size_t)std::max<int64_t>(pb.n_reads, 2) * maxcol;
@@ -390,6 +392,7 @@ struct Pipeline {
             q->read_begin = (int32_t)(2 * wave_pair[w]); q->read_end = (int32_t)(2 * wave_pair[w + 1]); q->dedup = dedup ? 1 : 0;
         }
         CUDA_OK(cudaMemsetAsync(L.pending_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.todo_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.defer_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.dp_task_count.p, 0, 4, st)); CUDA_OK(cudaMemsetAsync(L.dp_task_hist.p, 0, 1024, st));
+        if (sort_by_level) CUDA_OK(cudaMemsetAsync(L.dp_task_key.p, 0x7f, L.dp_task_key.bytes, st));
         if (P.slot_end > P.slot_base) {
             CUDA_OK(launch_prepare(P0, st));
             tic(0, st); CUDA_OK(launch_chain_seed(P0, g->n_sm, st)); CUDA_OK(launch_chain_seed(P, g->n_sm, st)); toc(st); launches += 3;
@@ -412,7 +415,7 @@ struct Pipeline {
             ExtParams E{}; E.C = P; E.n_pending = n_pending; E.ext_edge = L.ext_edge.as<int32_t>(); E.ext_s = L.ext_s.as<uint8_t>(); E.ext_n = L.ext_n.as<int32_t>();
             E.ext_nlvl = L.ext_nlvl.as<int32_t>(); E.ext_rc = L.ext_rc.as<int32_t>(); E.dp_scratch = L.dp_scratch.as<unsigned char>(); E.n_dp_threads = n_dp_threads;
             E.wd_scratch = L.wd_scratch.as<unsigned char>(); E.n_wd_warps = n_wd_warps; E.gd_scratch = L.gd_scratch.as<unsigned char>(); E.n_gd_groups = n_gd_groups;
-            E.ln_rec = L.ln_rec.as<LnRec>(); E.ln_ahead = L.ln_ahead.as<uint32_t>(); E.n_ln_threads = n_ln_threads;
+            E.ln_rec = L.ln_rec.as<LnRec>(); E.ln_ahead = L.ln_ahead.as<uint32_t>(); E.n_ln_threads = n_ln_threads; E.ln_batch = ln_batch;
             if (timing) { if (!dp_bytes.p) { dp_bytes.alloc(8); CUDA_OK(cudaMemsetAsync(dp_bytes.p, 0, 8, st)); } CUDA_OK(launch_dp_task_bytes(E, dp_bytes.as<unsigned long long>(), st)); }
             tic(1, st);
             if (scalar_dp_only) { E.only_deferred = 0; CUDA_OK(launch_extend(E, st)); launches += 1; }
@@ -431,7 +434,12 @@ struct Pipeline {
                     // thread-per-extension tiers over the list of tasks that run; the other sides of the pending chains have no extension
                     const size_t nt = (size_t)2 * n_pending;
                     CUDA_OK(cudaMemsetAsync(E.ext_rc, 0, nt * 4, st)); CUDA_OK(cudaMemsetAsync(E.ext_n, 0, nt * 4, st)); CUDA_OK(cudaMemsetAsync(E.ext_nlvl, 0, nt * 4, st));
-                    CUDA_OK(launch_sort_dp_tasks(P, L.dp_sorted.as<int32_t>(), st));
+                    if (sort_by_level) {
+                        const int n_sort = (int)std::min<size_t>(nt, L.dp_task_key.bytes / 4); size_t need = 0;
+                        CUDA_OK(sort_dp_tasks_by_level(L.dp_task_key.as<int32_t>(), L.dp_key_sorted.as<int32_t>(), P.dp_tasks, L.dp_sorted.as<int32_t>(), n_sort, nullptr, 0, &need, st));
+                        if (need > L.dp_sort_temp.bytes) { CUDA_OK(cudaStreamSynchronize(st)); L.dp_sort_temp.alloc(need + 256); }
+                        CUDA_OK(sort_dp_tasks_by_level(L.dp_task_key.as<int32_t>(), L.dp_key_sorted.as<int32_t>(), P.dp_tasks, L.dp_sorted.as<int32_t>(), n_sort, L.dp_sort_temp.p, L.dp_sort_temp.bytes, &need, st));
+                    } else CUDA_OK(launch_sort_dp_tasks(P, L.dp_sorted.as<int32_t>(), st));
                     E.in_list = L.dp_sorted.as<int32_t>(); E.in_count = L.dp_task_count.as<int32_t>(); E.pop = ctr + 8; E.out_list = qa; E.out_count = ctr + 9;
                     CUDA_OK(launch_extend_lean(E, g->n_sm, 0, st)); if (dp_trace) trace("lean std", tr0);
                     launches += 1;

@@ -304,6 +304,48 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     __syncwarp();
     int pool = 0; int lev = l_first; int status = 0;
     for (int col = 0; col < n; col++) {
+        {   // ---- a run of columns whose levels have ONE node on either side (everything outside bubbles and gene blocks): one column per lane.
+            // With a single node per level the step has no choice of node: the edge is the first one that emits the read's character (+1), else - if the
+            // linear alignment has a mismatch here - the first edge (+0); the scores are a prefix sum. Anything else (several nodes, a level without a usable
+            // edge, a capacity limit) ends the run and is taken by the general step below, which also reports the errors.
+            const unsigned full = 0xffffffffu;
+            const int j = col + lane; const bool in = j < n;
+            const int lv = in ? c.lvl[j] : -2;
+            const bool isl = in && lv != -1;
+            const unsigned lm = __ballot_sync(full, isl);
+            const int pre = __popc(lm & ((1u << lane) - 1u));
+            bool ok = in; int rank = 0, inc = 0;
+            if (isl) {
+                const int li = lev - l_first + pre;
+                ok = (lv == lev + pre) && S.wwid[li] == 1 && S.wwid[li + 1] == 1;
+                if (ok) {
+                    const int e0 = S.weoff[li], ne = (int)S.weoff[li + 1] - e0;
+                    ok = ne >= 1 && ne <= 8;
+                    if (ok) {
+                        const uint8_t sc = c.s[j], gc = c.g[j]; int hit = -1;
+                        for (int k = 0; k < ne; k++) { const uint32_t pk = staged ? win[e0 + k] : G.edge_pack[e_base + e0 + k]; if ((uint8_t)(pk >> 16) == sc) { hit = k; break; } }
+                        if (hit >= 0) { rank = hit; inc = 1; } else if (sc != gc) { rank = 0; inc = 0; } else ok = false;
+                    }
+                }
+            }
+            const unsigned okm = __ballot_sync(full, ok);
+            const int m = okm == full ? 32 : __ffs(~okm) - 1;      // leading run of columns this path can take
+            const unsigned mm = m >= 32 ? full : ((1u << m) - 1u);
+            const int cnt = __popc(lm & mm);
+            if (m >= 4 && cnt == 0) { col += m - 1; continue; }     // insertion columns only
+            const uint32_t k0 = cur[0];
+            if (m >= 4 && k0 != 0 && pool + cnt <= pool_cap && pool + cnt - 1 <= 65535) {
+                int sinc = (lane < m && isl) ? inc : 0;
+                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(full, sinc, d); if (lane >= d) sinc += t; }
+                if (lane < m && isl) { const int pj = pool + pre; if (BT16) bt16[pj] = (uint16_t)rank; else S.bt[pj] = (uint32_t)rank; S.coloff[j] = (uint16_t)pj; }
+                const int lastl = 31 - __clz(lm & mm);
+                __syncwarp();
+                if (lane == lastl) cur[0] = (((k0 >> KS) + (uint32_t)sinc) << KS) | (RM - (uint32_t)rank);
+                pool += cnt; lev += cnt; col += m - 1;
+                __syncwarp();
+                continue;
+            }
+        }
         if (c.lvl[col] == -1) continue;
         if (c.lvl[col] != lev) { status = HLALA_E_INVARIANT_DEV; break; }     // level contiguity (processBAM.cpp:2649-2665)
         const int li = lev - l_first;

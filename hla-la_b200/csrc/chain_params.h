@@ -36,6 +36,7 @@ struct ChainParams {
     int32_t* pending_slots; int32_t* pending_count;   // chains whose seed needs the extension DP
     int32_t* dp_tasks; int32_t* dp_task_count;        // the extension tasks that run: 2 * (index in pending_slots) + side, in no particular order
     uint8_t* dp_task_bin; int32_t* dp_task_hist;      // per task: 255 - min(clipped bases, 255); histogram of the bins (k_sort_dp_tasks: longest first)
+    int32_t* dp_task_key;                             // per task: the level the extension starts from (tasks sorted by it run neighbouring graph windows in one warp); unused slots keep a large key
     int32_t* todo_slots; int32_t* todo_count;         // chains the chain kernel has to align (written by k_prepare)
     int32_t* defer_slots; int32_t* defer_count;       // chains that did not fit the tier-0 slab
     int32_t read_begin, read_end;                     // reads of this wave
@@ -65,6 +66,7 @@ struct ExtParams {
     unsigned char* wd_scratch; int32_t n_wd_warps;     // warp kernel: one slice per warp
     unsigned char* gd_scratch; int32_t n_gd_groups;    // group kernel: one slice per 8-lane group
     LnRec* ln_rec; uint32_t* ln_ahead; int32_t n_ln_threads;   // thread-per-extension tier: cell records and ahead table, one slice per thread
+    int32_t ln_batch;                                   // thread-per-extension tier: waiting threads of a warp that trigger the backtrace / fetch phase
     int32_t only_deferred;                              // scalar kernel: run only the tasks the warp kernel deferred
     // dynamic task queues of the cascade: a tier pops task indices from `pop`; its tasks are in_list[0 .. *in_count) (in_list == nullptr: all
     // 2 * n_pending tasks) and the tasks it defers for capacity are appended to out_list

@@ -15,7 +15,7 @@
 namespace hlala {
 
 constexpr int LN_BLOCK = 32;       // threads per CTA: one warp, so that the resident warps per SM follow the shared-memory budget in steps of one
-constexpr int LN_BATCH = 6;        // waiting threads of a warp that trigger the backtrace / fetch phase
+constexpr int LN_BATCH = 16;       // default of ExtParams::ln_batch: waiting threads of a warp that trigger the backtrace / fetch phase
 
 struct LnSmem {
     uint32_t* base;
@@ -42,7 +42,7 @@ template <class CFG> __global__ void __launch_bounds__(LN_BLOCK) k_extend_lean(E
         const unsigned waiting = __ballot_sync(0xffffffffu, phase == 0 || phase == 2);
         const unsigned running = __ballot_sync(0xffffffffu, phase == 1);
         if (waiting == 0u && running == 0u) break;
-        if (waiting != 0u && (__popc(waiting) >= LN_BATCH || running == 0u)) {
+        if (waiting != 0u && (__popc(waiting) >= E.ln_batch || running == 0u)) {
             if (phase == 2) {
                 DpResult res; const int rc = DP::finish(G, st, rec, E.ext_edge + (size_t)t * DP_EXT_CAP, E.ext_s + (size_t)t * DP_EXT_CAP, res);
                 E.ext_rc[t] = rc; E.ext_n[t] = rc == 0 ? res.n_cols : 0; E.ext_nlvl[t] = rc == 0 ? res.n_lvl : 0;
