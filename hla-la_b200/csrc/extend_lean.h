@@ -38,7 +38,7 @@ inline long long* ln_reasons() { static long long r[16] = {}; return r; }
 #endif
 
 template <int LIST_, int TD_> struct LnCfg {
-    static constexpr int LIST = LIST_, TD = TD_;                       // TD: slots of the touch table (power of two), at most TD - 4 in use
+    static constexpr int LIST = LIST_, TD = TD_;                       // TD: slots of the touch table (power of two), at most TD - 1 in use (one empty slot ends the probe of a key that is not in the table)
     static constexpr int M_A = 0, M_B = 2 * LIST_, TK = 4 * LIST_, TV = TK + TD_, TB = TV + TD_, PERM = TB + TD_;
     static constexpr int AM = PERM + TD_ / 4;                          // 256-bit mask of the anti-diagonals (mod 256) that hold ahead cells
     static constexpr int WORDS = AM + 8;
@@ -132,7 +132,7 @@ template <class CFG, class SM> struct LnDp {
             for (int probe = 0; probe < CFG::TD; probe++) {
                 const uint32_t k = S(CFG::TK + slot);
                 if (k == LN_EMPTY) {
-                    if (n_td >= CFG::TD - 4) return -1;
+                    if (n_td >= CFG::TD - 1) return -1;
                     S(CFG::TK + slot) = K; S(CFG::TV + slot) = 0; S(CFG::TB + slot) = 0; n_td++;
                     if (kv > kv_hi) kv_hi = kv; if (s < s_lo) s_lo = s;
                     return slot;
@@ -245,6 +245,10 @@ template <class CFG, class SM> struct LnDp {
                 if (g <= st.ahead_hi && ((S(CFG::AM + ((g >> 5) & 7)) >> (g & 31)) & 1u)) LN_PREFETCH(ahead + ahead_hash(K));
             }
         }
+        // A lower bound of the best D this diagonal will store (a cell stores at least its D candidate): cells more than 15 below it are dropped by the
+        // pruning at the end of the step (:1076-1105) whatever the exact maximum turns out to be, so they need no place in the next wavefront list.
+        uint32_t mx_lo = 0;
+        for (int oi = 0; oi < n_td; oi++) { const uint32_t f = S(CFG::TV + getb(S, oi)) & 1023u; if (f > mx_lo) mx_lo = f; }
         // ---- finalise in that order (:794-1071); the next wavefront is written over the m-2 list
         int n_mt = 0; bool dirty = false; int rc = 0;
         for (int oi = 0; oi < n_td; oi++) {
@@ -304,9 +308,11 @@ template <class CFG, class SM> struct LnDp {
                 const int x = st.xbase + ku;
                 if (st.end_idx < 0 || (int)stD > st.end_f || ((int)stD == st.end_f && ci != st.end_idx && ln_key_less(x, z, st.end_x, st.end_z))) { st.end_idx = ci; st.end_f = (int)stD; st.end_x = x; st.end_z = z; }
             }
-            if (n_mt >= CFG::LIST) { LN_WHY(8); rc = DP_DEFER; continue; }
-            S(m2o + 2 * n_mt) = K | ((uint32_t)ci << 21); S(m2o + 2 * n_mt + 1) = stv; n_mt++;
-            { const int pl = st.xbase + ku - (dir > 0 ? 0 : 1); if (pl >= 0 && pl < G.n_levels) LN_PREFETCH(G.lvl4 + pl); }     // the level record this cell reads on the next two diagonals
+            if (mx_lo <= 15u + stD) {     // else: pruned below in any case
+                if (n_mt >= CFG::LIST) { LN_WHY(8); rc = DP_DEFER; continue; }
+                S(m2o + 2 * n_mt) = K | ((uint32_t)ci << 21); S(m2o + 2 * n_mt + 1) = stv; n_mt++;
+                { const int pl = st.xbase + ku - (dir > 0 ? 0 : 1); if (pl >= 0 && pl < G.n_levels) LN_PREFETCH(G.lvl4 + pl); }     // the level record this cell reads on the next two diagonals
+            }
             // running maximum / patience (:1007-1062); the step score is 0 exactly for '_' steps, jumps and a sequence gap extended along '_'
             if ((int)fD == st.run_max) {
                 bool tie;
