@@ -43,7 +43,7 @@ template <int LIST_, int TD_> struct LnCfg {
     static constexpr int AM = PERM + TD_ / 4;                          // 256-bit mask of the anti-diagonals (mod 256) that hold ahead cells
     static constexpr int WORDS = AM + 8;
 };
-typedef LnCfg<24, 32> LnStd;      // 800 B per thread
+typedef LnCfg<26, 32> LnStd;      // 864 B per thread
 typedef LnCfg<48, 64> LnBig;      // 1600 B per thread: re-runs what LnStd deferred for its list / table capacities
 static_assert(LnBig::LIST <= 64, "list positions are 6-bit fields");
 

@@ -14,7 +14,7 @@
 
 namespace hlala {
 
-constexpr int LN_BLOCK = 32;       // threads per CTA: one warp, so that the resident warps per SM follow the shared-memory budget in steps of one
+constexpr int LN_BLOCK = 64;       // threads per CTA: one warp, so that the resident warps per SM follow the shared-memory budget in steps of one
 constexpr int LN_BATCH = 16;       // default of ExtParams::ln_batch: waiting threads of a warp that trigger the backtrace / fetch phase
 
 struct LnSmem {
