@@ -294,13 +294,13 @@ def stage_long_reads(args, root, H):
     return out
 
 
-def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels):
+def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels, batch=None):
     """BASELINE.json configs[2] on N GPUs: --strong-pairs pairs in total, sharded by pair across the ranks (graph replicated). Timed per rank, max over ranks:
     alignment of the shard (columns kept) -> all-reduce of the per-level coverage -> extraction of the gene-overlapping pairs -> all-gather of those (small)
     alignment blobs -> typing with the reads split across ranks and ONE NCCL all-reduce of the allele-pair sums per locus -> rank 0 writes the hla/* files."""
     import tempfile
-    n_shard = args.strong_pairs // world
-    b = make_reads(args, prg_dir, 1000 + rank, n_shard, tag="strong%d" % world)
+    n_shard = args.strong_pairs // world if batch is None else (len(batch["read_off"]) - 1) // 2
+    b = make_reads(args, prg_dir, 1000 + rank, n_shard, tag="strong%d" % world) if batch is None else batch
     T = H.ProductTyping(P, prg_dir)
     L = P.lib; sb = H.make_batch_struct(b); sess = C.c_void_p()
     P._chk(L.hlala_session_create(P.g, C.byref(sb), C.c_int32(args.max_columns), C.byref(sess))); P._chk(L.hlala_session_set_keep_columns(sess, 1))
@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--stages", type=int, default=1, help="also time the k-mer seeding and typing stages (rank 0, N=1 only)")
     ap.add_argument("--long-reads", type=int, default=50000, help="reads of the long-read stage (BASELINE.json configs[3]: 50 k x 8 kb)")
     ap.add_argument("--long-ref-reads", type=int, default=100, help="reads of that batch the reference's alignOneLongRead is timed on (1 thread)")
+    ap.add_argument("--pipeline", type=int, default=1, help="N = 1: also time the headline batch through alignment + typing + files (BASELINE.json configs[1] end to end)")
     ap.add_argument("--strong-single", type=int, default=0, help="run the strong-scaling leg at N = 1 too (its baseline; off by default to keep the default run short)")
     ap.add_argument("--strong-pairs", type=int, default=4000000, help="N > 1: total pairs of the strong-scaling leg (BASELINE.json configs[2]: ~4M pairs sharded over the GPUs, typing with one NCCL all-reduce per locus); 0 = skip")
     args = ap.parse_args()
@@ -544,6 +545,17 @@ def main():
     strong = None
     if args.strong_pairs > 0 and (dist or args.strong_single):
         strong = strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels)
+    pipeline = None
+    if args.pipeline and not dist:
+        # BASELINE.json configs[1] end to end on the bench batch itself: alignment (columns kept) -> coverage -> gene filter -> typing kernels -> the 73 hla/* files,
+        # batch resident in HBM when the clock starts (the strong-scaling leg at N = 1, on the headline workload)
+        try:
+            pipeline = strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, None, torch, n_levels, batch=b)
+            pipeline["note"] = "the headline batch through the whole path of BASELINE config 2: alignment with columns kept, per-level coverage, gene filter + extraction, typing (two kernels per locus) and all hla/* files; wall clock, second of two passes, batch resident in HBM"
+            for k in ("allele_pair_allreduces_per_rank", "pairs_per_rank", "gathered_blob_bytes"):
+                pipeline.pop(k, None)
+        except Exception as e:
+            pipeline = {"error": str(e)[:300]}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -622,7 +634,7 @@ def main():
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
-            "stages": stages, "strong_scaling_config3": strong, "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
+            "stages": stages, "pipeline_config2": pipeline, "strong_scaling_config3": strong, "check": {"sum_columns": int(dig[0]), "edge_checksum": int(dig[1]), "pairs_mapq_lt_1": int(dig[2]), "errors": int(dig[3]), "sum_pair_ll": sll.value}}
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

@@ -173,7 +173,7 @@ template <class T> void put_vec(std::vector<uint8_t>& b, const std::vector<T>& v
 template <class T> void get_vec(const uint8_t*& p, const uint8_t* end, std::vector<T>& v) { if (p + 8 > end) throw std::runtime_error("typing blob truncated"); uint64_t n; memcpy(&n, p, 8); p += 8; if (p + n * sizeof(T) > end) throw std::runtime_error("typing blob truncated"); v.resize(n); if (n) memcpy(v.data(), p, n * sizeof(T)); p += n * sizeof(T); while ((uintptr_t)(p - (const uint8_t*)nullptr) % 8 && p < end) p++; }
 }
 std::vector<uint8_t> TypingReads::serialize() const {
-    std::vector<uint8_t> b; std::vector<uint64_t> magic = {0x484C415459503031ull};   // "HLATYP01"
+    std::vector<uint8_t> b; std::vector<uint64_t> magic = {long_reads ? 0x484C415459503032ull : 0x484C415459503031ull};   // "HLATYP01" paired, "HLATYP02" long reads
     put_vec(b, magic); put_vec(b, pair_id);
     std::vector<int64_t> noff(1, 0); std::vector<uint8_t> nch; for (const std::string& n : name) { nch.insert(nch.end(), n.begin(), n.end()); noff.push_back((int64_t)nch.size()); }
     put_vec(b, noff); put_vec(b, nch); put_vec(b, col_off); put_vec(b, level); put_vec(b, g); put_vec(b, s); put_vec(b, mq); put_vec(b, base_off); put_vec(b, bases); put_vec(b, quals); put_vec(b, reverse); put_vec(b, mapq);
@@ -183,12 +183,33 @@ void TypingReads::deserialize_append(const uint8_t* p, size_t n) {
     // blobs are 8-byte aligned internally relative to their start; copy to an aligned buffer to keep get_vec's padding rule simple
     std::vector<uint64_t> aligned((n + 7) / 8); memcpy(aligned.data(), p, n);
     const uint8_t* q = (const uint8_t*)aligned.data(); const uint8_t* end = q + n;
-    TypingReads o; std::vector<uint64_t> magic; get_vec(q, end, magic); if (magic.size() != 1 || magic[0] != 0x484C415459503031ull) throw std::runtime_error("typing blob: bad magic");
+    TypingReads o; std::vector<uint64_t> magic; get_vec(q, end, magic); if (magic.size() != 1 || (magic[0] != 0x484C415459503031ull && magic[0] != 0x484C415459503032ull)) throw std::runtime_error("typing blob: bad magic");
+    o.long_reads = magic[0] == 0x484C415459503032ull;
+    if (!pair_id.empty() && o.long_reads != long_reads) throw std::runtime_error("typing blob: paired and long-read blobs cannot be mixed");
+    long_reads = o.long_reads;
     get_vec(q, end, o.pair_id); std::vector<int64_t> noff; std::vector<uint8_t> nch; get_vec(q, end, noff); get_vec(q, end, nch);
     for (size_t i = 0; i + 1 < noff.size(); i++) o.name.emplace_back((const char*)nch.data() + noff[i], (size_t)(noff[i + 1] - noff[i]));
     get_vec(q, end, o.col_off); get_vec(q, end, o.level); get_vec(q, end, o.g); get_vec(q, end, o.s); get_vec(q, end, o.mq); get_vec(q, end, o.base_off); get_vec(q, end, o.bases); get_vec(q, end, o.quals); get_vec(q, end, o.reverse); get_vec(q, end, o.mapq);
     if (o.name.size() != o.pair_id.size() || o.col_off.size() != 2 * o.pair_id.size() + 1 || o.base_off.size() != o.col_off.size()) throw std::runtime_error("typing blob: inconsistent sizes");
     append(o);
+}
+
+TypingReads long_read_typing_input(const TypingTables& T, int64_t n_reads, const char* const* names, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int32_t cap,
+                                   const int32_t* n_cols, const int32_t* level, const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* mapq) {
+    TypingReads tr; tr.long_reads = true; tr.col_off.push_back(0); tr.base_off.push_back(0);
+    for (int64_t r = 0; r < n_reads; r++) {
+        const size_t o = (size_t)r * (size_t)cap; const int n = n_cols[r];
+        if (n > cap) throw std::runtime_error("typing: a long-read alignment has more columns than max_columns");
+        int f = -1, l = -1; for (int c = 0; c < n; c++) { const int lv = level[o + c]; if (lv != -1) { if (f == -1) f = lv; l = lv; } }
+        if (!pair_overlaps_genes(T, f, l, -1, -1)) continue;
+        tr.pair_id.push_back(r); tr.name.push_back(names && names[r] ? std::string(names[r]) : "r" + std::to_string(r));
+        tr.level.insert(tr.level.end(), level + o, level + o + n); tr.g.insert(tr.g.end(), g + o, g + o + n); tr.s.insert(tr.s.end(), s + o, s + o + n); tr.mq.insert(tr.mq.end(), mq + o, mq + o + n);
+        tr.col_off.push_back((int64_t)tr.level.size()); tr.col_off.push_back((int64_t)tr.level.size());
+        tr.bases.insert(tr.bases.end(), bases + read_off[r], bases + read_off[r + 1]); tr.quals.insert(tr.quals.end(), quals + read_off[r], quals + read_off[r + 1]);
+        tr.base_off.push_back((int64_t)tr.bases.size()); tr.base_off.push_back((int64_t)tr.bases.size());
+        tr.reverse.push_back(reverse[r]); tr.reverse.push_back(0); tr.mapq.push_back(mapq[r]); tr.mapq.push_back(0);
+    }
+    return tr;
 }
 
 // ------------------------------------------------------------------------------------------------------------ inference
@@ -232,15 +253,24 @@ int level_distance(const Mate& a, const Mate& b) { return a.first_level < b.firs
 struct ExonObs {    // hla::oneExonPosition (hla/oneExonPosition.h:15-46), fields that are read anywhere in short-read mode
     uint32_t pos = 0; int32_t level = -1; std::string genotype, qualities; const Mate* self = nullptr; const Mate* mate = nullptr;
     double dist = 0, mapq_pos = 0; unsigned char mq_char = 0;    // mq_char: the per-column quality character mapq_pos was derived from
+    int novel_gap = 0;                                           // runningNovelGapEitherDirection (HLATyper.cpp:3616-3662): only read in long-read mode
 };
 
 // oneReadAlignment_2_exonPositions_paired (HLATyper.cpp:3192-3565)
-void project_read(const Mate& A, const Mate& M, const TypingLocus& L, std::vector<ExonObs>& out) {
+// and oneReadAlignment_2_exonPositions_unpaired (:3568-3930) with unpaired = true: no mate (distance -1), running novel gaps recorded
+void project_read(const Mate& A, const Mate& M, const TypingLocus& L, std::vector<ExonObs>& out, bool unpaired = false) {
     TY_REQUIRE(A.first_level <= A.last_level, "alignment_firstLevel <= alignment_lastLevel");
     const int fl = A.first_level, ll = A.last_level;
     if (!((fl >= L.lmin && fl <= L.lmax) || (ll >= L.lmin && ll <= L.lmax) || (L.lmin >= fl && L.lmin <= ll) || (L.lmax >= fl && L.lmax <= ll))) return;
-    const double dist = level_distance(A, M);
+    const double dist = unpaired ? -1.0 : level_distance(A, M);
     std::vector<ExonObs> all; all.reserve((size_t)A.n);
+    std::vector<int> novel;
+    if (unpaired) {   // longest run of columns with exactly one gap character that reaches the column, from either side
+        novel.assign((size_t)A.n, 0); int run = 0;
+        for (int c = 0; c < A.n; c++) { if (A.g[c] != '_' && A.s[c] != '_') run = 0; else if (!(A.g[c] == '_' && A.s[c] == '_')) run++; if (run > novel[(size_t)c]) novel[(size_t)c] = run; }
+        run = 0;
+        for (int c = A.n - 1; c >= 0; c--) { if (A.g[c] != '_' && A.s[c] != '_') run = 0; else if (!(A.g[c] == '_' && A.s[c] == '_')) run++; if (run > novel[(size_t)c]) novel[(size_t)c] = run; }
+    }
     int idx = -1;
     for (int c = 0; c < A.n; c++) {
         if (A.level[c] == -1) {       // inserted base: joins the previous position's genotype; a leading "_" is dropped (:3328-3334)
@@ -249,7 +279,7 @@ void project_read(const Mate& A, const Mate& M, const TypingLocus& L, std::vecto
             if (!all.empty()) { ExonObs& b = all.back(); if (b.genotype == "_") { TY_REQUIRE(b.qualities.empty(), "gap has no quality"); b.genotype.clear(); } b.genotype.push_back((char)A.s[c]); b.qualities.push_back((char)A.quals[idx]); }
             continue;
         }
-        ExonObs e; e.level = A.level[c]; e.self = &A; e.mate = &M; e.dist = dist; e.mapq_pos = pcorrect_of(A.mq[c]); e.mq_char = A.mq[c];
+        ExonObs e; e.level = A.level[c]; e.self = &A; e.mate = &M; e.dist = dist; e.mapq_pos = pcorrect_of(A.mq[c]); e.mq_char = A.mq[c]; if (unpaired) e.novel_gap = novel[(size_t)c];
         if (A.s[c] != '_') { idx++; TY_REQUIRE(idx < A.len, "read index inside the read"); e.genotype.assign(1, (char)A.s[c]); e.qualities.assign(1, (char)A.quals[idx]); }
         else e.genotype = "_";
         all.push_back(std::move(e));
@@ -332,7 +362,9 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
                 TypingDevice& dev, const TypingOptions& opt, std::vector<LocusCall>& calls) {
     calls.clear();
     PhaseClock clk; std::unique_ptr<PhaseClock::Scope> ph0(new PhaseClock::Scope(clk, 0));
-    const size_t NP = in.n_pairs(); TY_REQUIRE(NP > 0, "rawPairedReads.size() > 0");
+    const size_t NP = in.n_pairs(); TY_REQUIRE(NP > 0, "rawPairedReads.size() > 0 || rawUnpairedReads.size() > 0");
+    const bool LR = in.long_reads;       // long-read mode: entry p is the single read 2p; its "mate" 2p+1 is empty and stands for "no paired read" (-1 / "" in the reference's records)
+    static const std::string no_name;
     std::vector<Mate> mates(2 * NP);
     // per-read statistics and the 31-mer set of the reads, on the host thread pool: reads are dealt in blocks; the k-mer set is sharded by hash so that every
     // thread owns one shard (each scans all reads and keeps the k-mers of its shard: scanning is cheap, inserting is what costs)
@@ -351,6 +383,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
             Mate& m = mates[r]; const int64_t c0 = in.col_off[r], b0 = in.base_off[r];
             m.n = (int)(in.col_off[r + 1] - c0); m.level = in.level.data() + c0; m.g = in.g.data() + c0; m.s = in.s.data() + c0; m.mq = in.mq.data() + c0;
             m.len = (int)(in.base_off[r + 1] - b0); m.bases = in.bases.data() + b0; m.quals = in.quals.data() + b0; m.reverse = in.reverse[r] != 0; m.mapQ = in.mapq[r]; m.name = &in.name[r / 2];
+            if (LR && (r & 1)) { TY_REQUIRE(m.n == 0 && m.len == 0, "long-read entries have no second read"); m.name = &no_name; m.weighted_ok = -1; m.fraction_ok = -1; continue; }   // pairedRead_* = -1, pairedRead_ID = "" (HLATyper.cpp:3574-3581)
             mate_stats(m);
             for (int i = 0; i < m.len; i++) { unsigned char c = m.bases[i]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N' || c == 'a' || c == 'c' || c == 'g' || c == 't' || c == 'n' || c == '_' || c == '*')) throw std::runtime_error("typing: reverse complement of unknown character"); }
         }
@@ -370,20 +403,23 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     if (!out_dir.empty()) mkdir(out_dir.c_str(), 0777);
     {   // summaryStatistics.txt (HLATyper.cpp:1026-1125)
         int valid = 0, valid_dist = 0, perfect = 0, one_perfect = 0; std::vector<double> dists; double fsum = 0;
-        for (size_t p = 0; p < NP; p++) { const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1];
+        const size_t NPP = LR ? 0 : NP, NU = LR ? NP : 0;      // paired / unpaired alignments
+        int u_perfect = 0, u_long = 0; double u_fsum = 0;
+        for (size_t p = 0; p < NU; p++) { const Mate& a = mates[2 * p]; if (a.n >= 1000) u_long++; if (a.fraction_ok == 1) u_perfect++; u_fsum += a.fraction_ok; }
+        for (size_t p = 0; p < NPP; p++) { const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1];
             if (strands_ok(a, b)) { valid++; double d = level_distance(a, b); dists.push_back(d); if (fabs(d - is_mean) <= 5 * is_sd) valid_dist++; }
             perfect += (a.fraction_ok == 1) + (b.fraction_ok == 1); one_perfect += (a.fraction_ok == 1 || b.fraction_ok == 1); fsum += a.fraction_ok; fsum += b.fraction_ok; }
         std::sort(dists.begin(), dists.end()); double dsum = 0; for (double d : dists) dsum += d;
         double dmean = 0, dmed = 0; if (!dists.empty()) { dmean = dsum / (double)dists.size(); dmed = dists[dists.size() / 2]; }
-        auto pct = [](double a, double b) { return str((a / b) * 100); };
+        auto pct = [](double a, double b) { volatile double q = a / b; std::ostringstream o; o << (q * 100); return o.str(); };      // printPerc: 0 / 0 prints as the stream prints that NaN
         std::ofstream s(target("summaryStatistics.txt")); if (!s.is_open()) throw std::runtime_error("Cannot open " + target("summaryStatistics.txt") + " for writing");
-        s << "\nRead alignment statistics:\n" << "\t - Total number (paired) alignments:                 " << NP << "\n"
-          << "\t\t - Alignment pairs with strands OK:                  " << valid << " (" << pct(valid, NP) << "%)\n"
-          << "\t\t - Alignment pairs with strands OK && distance OK:   " << valid_dist << " (" << pct(valid_dist, NP) << "%)\n"
+        s << "\nRead alignment statistics:\n" << "\t - Total number (paired) alignments:                 " << NPP << "\n"
+          << "\t\t - Alignment pairs with strands OK:                  " << valid << " (" << pct(valid, NPP) << "%)\n"
+          << "\t\t - Alignment pairs with strands OK && distance OK:   " << valid_dist << " (" << pct(valid_dist, NPP) << "%)\n"
           << "\t\t - Alignment pairs with strands OK, mean distance:   " << dmean << "\n" << "\t\t - Alignment pairs with strands OK, median distance: " << dmed << "\n"
-          << "\t\t - Alignment pairs, average fraction alignment OK:   " << (fsum / (2.0 * (double)NP)) << "\n" << "\t\t - Alignment pairs, at least one alignment perfect:   " << one_perfect << "\n"
-          << "\t\t - Single alignments, perfect (total):   " << perfect << " (" << NP * 2 << ")\n" << "\t - Total number (unpaired) alignments:                 " << 0 << "\n"
-          << "\t\t - Alignment pairs, average fraction alignment OK:   " << 0.0 << "\n" << "\t\t - Single alignments, perfect (total):   " << 0 << " (" << 0 << ")\n" << "\t\t - Alignments with length >= " << 1000 << ":   " << 0 << "\n";
+          << "\t\t - Alignment pairs, average fraction alignment OK:   " << (NPP > 0 ? fsum / (2.0 * (double)NPP) : 0.0) << "\n" << "\t\t - Alignment pairs, at least one alignment perfect:   " << one_perfect << "\n"
+          << "\t\t - Single alignments, perfect (total):   " << perfect << " (" << NPP * 2 << ")\n" << "\t - Total number (unpaired) alignments:                 " << NU << "\n"
+          << "\t\t - Alignment pairs, average fraction alignment OK:   " << (NU > 0 ? u_fsum / (double)NU : 0.0) << "\n" << "\t\t - Single alignments, perfect (total):   " << u_perfect << " (" << NU * 2 << ")\n" << "\t\t - Alignments with length >= " << 1000 << ":   " << u_long << "\n";
     }
     std::ofstream best(target("R1_bestguess.txt")), bestG(target("R1_bestguess_G.txt")), hist(target("histogram_matchesPerRead.txt"));
     if (!best.is_open() || !bestG.is_open() || !hist.is_open()) throw std::runtime_error("Cannot open output files in " + out_dir);
@@ -395,7 +431,8 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
     // which pairs pass the read-pair gates (HLATyper.cpp:1405-1410) does not depend on the locus
     std::vector<uint8_t> gate(NP, 0);
     for (size_t p = 0; p < NP; p++) { const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1]; TY_REQUIRE(a.mapQ >= 0 && a.mapQ <= 1, "mapQ in [0,1]");
-        gate[p] = strands_ok(a, b) && fabs(level_distance(a, b) - is_mean) <= 5 * is_sd && a.mapQ >= min_mapq && a.weighted_ok >= min_weighted && b.weighted_ok >= min_weighted; }
+        if (LR) gate[p] = a.mapQ >= min_mapq && a.n >= 1000;       // HLATyper.cpp:1475-1476 (minAlignmentLength_unpaired)
+        else gate[p] = strands_ok(a, b) && fabs(level_distance(a, b) - is_mean) <= 5 * is_sd && a.mapQ >= min_mapq && a.weighted_ok >= min_weighted && b.weighted_ok >= min_weighted; }
 
     std::vector<std::array<std::string, 3>> hist_pair(NP);     // the three lines a gated pair contributes to every locus' histogram (without the locus name)
     std::string mapq_pos_str[256], qual_int_str[256];
@@ -404,9 +441,10 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         Mate& a = mates[2 * p]; Mate& b = mates[2 * p + 1];
         for (int m = 0; m < 2; m++) { Mate& x = m ? b : a; const Mate& y = m ? a : b;
             x.hist_base = "base" + str(x.weighted_ok) + "\n";
-            x.pile_mid = ") [pairsDistance " + str((double)level_distance(x, y)) + " | alignmentLength " + str(x.nongap_cols) + " | ";
+            if (LR && m == 1) continue;
+            x.pile_mid = ") [pairsDistance " + (LR ? std::string("-1") : str((double)level_distance(x, y))) + " | alignmentLength " + str(x.nongap_cols) + " | ";
             x.pile_tail = " | " + str(x.mapQ) + " " + str(x.mapQ) + " | " + str(x.weighted_ok) + " " + str(y.weighted_ok) + " | " + *x.name + " " + *y.name + "]"; }
-        if (gate[p]) hist_pair[p] = {"\tread" + str(a.weighted_ok) + "\n", "\tread" + str(b.weighted_ok) + "\n", "\treadPair" + str((a.weighted_ok + b.weighted_ok) / 2.0) + "\n"};
+        if (gate[p] && !LR) hist_pair[p] = {"\tread" + str(a.weighted_ok) + "\n", "\tread" + str(b.weighted_ok) + "\n", "\treadPair" + str((a.weighted_ok + b.weighted_ok) / 2.0) + "\n"};
     }
 
     // The loci are independent up to the order of their lines in the shared files and the order of the device stage (with several ranks
@@ -429,7 +467,9 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         std::vector<std::vector<ExonObs>> reads;
         for (size_t p = 0; p < NP; p++) {
             const Mate& a = mates[2 * p]; const Mate& b = mates[2 * p + 1];
-            std::vector<ExonObs> obs; project_read(a, b, L, obs); project_read(b, a, L, obs);    // both are validated even if the pair is gated out
+            std::vector<ExonObs> obs;
+            if (LR) { project_read(a, b, L, obs, true); if (!gate[p]) continue; if (!obs.empty()) reads.push_back(std::move(obs)); continue; }     // HLATyper.cpp:1467-1495: no double positions inside one read
+            project_read(a, b, L, obs); project_read(b, a, L, obs);    // both are validated even if the pair is gated out
             if (!gate[p]) continue;
             if (!obs.empty()) reads.push_back(one_per_level(obs));
             for (const std::string& piece : hist_pair[p]) { hist += L.name; hist += piece; }
@@ -438,7 +478,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         // ---- "first 20" filter (HLATyper.cpp:1551-1640)
         ph.reset(new PhaseClock::Scope(clk, 2));
         std::set<std::string> ignored_reads; std::map<uint32_t, std::set<std::string>> ignored_alleles;
-        {
+        if (!LR) {     // filterFirst20 && longReadsMode.length() == 0 (HLATyper.cpp:1509)
             std::map<uint32_t, std::vector<std::string>> al; std::map<uint32_t, std::vector<double>> wq; std::map<uint32_t, std::vector<uint32_t>> rd; std::map<uint32_t, int> robust;
             for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { TY_REQUIRE(e.mapq_pos >= 0 && e.mapq_pos <= 1, "mapQ_position in [0,1]"); if (e.mapq_pos < min_pos_mapq) continue;
                 al[e.pos].push_back(e.genotype); wq[e.pos].push_back((e.self->weighted_ok + e.mate->weighted_ok) / 2.0); rd[e.pos].push_back(r); }
@@ -465,14 +505,22 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         std::map<uint32_t, std::map<std::string, double>> min_strand_freq, read1_freq; std::map<uint32_t, std::map<std::string, int>> counts_high_cov;
         {
             struct Cnt { int n = 0, fwd = 0, rev = 0, first = 0; }; std::map<uint32_t, std::map<std::string, Cnt>> cnt;
-            for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; Cnt& c = cnt[e.pos][e.genotype]; c.n++; if (e.self->reverse) c.rev++; else c.fwd++; /* fromFirstRead is false for both mates: processBAM.cpp:3545-3548 overwrites the flag */ }
+            for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; Cnt& c = cnt[e.pos][e.genotype]; c.n++; if (e.self->reverse) c.rev++; else c.fwd++;
+                if (LR) c.first++; /* paired mode: fromFirstRead is false for both mates (processBAM.cpp:3545-3548 overwrites the flag); alignOneLongRead sets it (:3756) */ }
+            // long-read mode: highCoverage_filter_alleles with minCoverage 1 and minAlleleFreq 0.15 (HLATyper.cpp:944-946, 1806-1828), strand filter for alleles seen >= 100 times (:1847-1856)
+            const int cov_min = LR ? 1 : high_cov; const double min_af = 0.15, min_strand = 0.1; const int strand_min_cov = 100;
             for (auto& pk : cnt) { int tot = 0; for (auto& a : pk.second) tot += a.second.n;
-                for (auto& a : pk.second) { if (tot >= high_cov) counts_high_cov[pk.first][a.first] = a.second.n; int t = a.second.fwd + a.second.rev; min_strand_freq[pk.first][a.first] = (double)std::min(a.second.fwd, a.second.rev) / (double)t; read1_freq[pk.first][a.first] = (double)a.second.first / (double)t; } }
+                for (auto& a : pk.second) {
+                    if (tot >= cov_min) { if (LR && (double)a.second.n / (double)tot < min_af) ignored_alleles[pk.first].insert(a.first); else counts_high_cov[pk.first][a.first] = a.second.n; }
+                }
+                for (auto& a : pk.second) { int t = a.second.fwd + a.second.rev; const double msf = (double)std::min(a.second.fwd, a.second.rev) / (double)t; min_strand_freq[pk.first][a.first] = msf; read1_freq[pk.first][a.first] = (double)a.second.first / (double)t;
+                    if (LR && t >= strand_min_cov && msf < min_strand) ignored_alleles[pk.first].insert(a.first); } }
         }
         // ---- pile-up (HLATyper.cpp:1877-2037)
         ph.reset(new PhaseClock::Scope(clk, 4));
         std::map<int, std::map<int, std::vector<const ExonObs*>>> pile; std::set<std::string> utilized;
-        for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; pile[L.col_exon[e.pos]][L.col_exonpos[e.pos]].push_back(&e); hist += L.name; hist += '\t'; hist += e.self->hist_base; }
+        for (uint32_t r = 0; r < R; r++) for (const ExonObs& e : reads[r]) { if (!used(e)) continue; if (LR && e.novel_gap >= 2) continue;     // HLATyper.cpp:1918
+            pile[L.col_exon[e.pos]][L.col_exonpos[e.pos]].push_back(&e); hist += L.name; hist += '\t'; hist += e.self->hist_base; }
         {
             // every observation is "<genotype> (<qualities>) [pairsDistance d | alignmentLength n | mapQ_position | mapQ mapQ | w w | name name]"; all but
             // the genotype, the qualities and the per-column mapQ are per-read text prepared once (Mate::pile_mid / pile_tail)
@@ -504,7 +552,7 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
 
         // ---- the two GPU stages: per-read x cluster log-likelihoods, allele-pair sums
         ph.reset(new PhaseClock::Scope(clk, 5));
-        LocusDeviceInput di; di.C = C; di.P = P; di.R = (int32_t)R; di.cluster_seq = &L.cluster_seq; di.rec_off.assign(1, 0); long long bases_used = 0;
+        LocusDeviceInput di; di.C = C; di.P = P; di.R = (int32_t)R; di.long_reads = LR; di.cluster_seq = &L.cluster_seq; di.rec_off.assign(1, 0); long long bases_used = 0;
         for (uint32_t r = 0; r < R; r++) {
             for (const ExonObs& e : reads[r]) { if (!used(e)) continue;
                 const bool gap = e.genotype == "_"; if (!gap) { TY_REQUIRE(e.genotype.find('_') == std::string::npos, "no gap inside an insertion"); TY_REQUIRE(!e.qualities.empty(), "quality present"); double pc = pcorrect_of((unsigned char)e.qualities[0]); TY_REQUIRE(pc >= 0 && pc <= 1, "pCorrect in [0,1]"); }

@@ -2,7 +2,8 @@
 // stage — per-read x allele-cluster log-likelihoods and allele-pair log-likelihood sums — run on the GPU (csrc/typing_kernels.cu)
 // behind the TypingDevice interface; this file never computes them (there is no CPU fallback).
 //
-// Reference (paths relative to the reference tree), short-read paired mode:
+// Reference (paths relative to the reference tree); short-read paired mode and long-read unpaired mode (HLATyper.cpp:935-946, 1079-1097, 1467-1495,
+// 1797-1880, 1918, 3568-3930):
 //   gene filter                                   mapper/processBAM.cpp:2427-2446, hla/HLATyper.cpp:259
 //   HLATyper::HLATyper (segments, gene bounds)     hla/HLATyper.cpp:36-256, Graph::readGraphLoci Graph/Graph.cpp:2563
 //   HLATyper::HLATypeInference                     hla/HLATyper.cpp:933-2810
@@ -44,6 +45,7 @@ struct TypingReads {
     std::vector<int64_t> base_off;       // [2n+1] into bases / quals (BAM orientation)
     std::vector<uint8_t> bases, quals;
     std::vector<uint8_t> reverse; std::vector<double> mapq;   // per read
+    bool long_reads = false;             // long-read mode: every entry is ONE read (reads 2i) followed by an empty mate (no columns, no bases)
     size_t n_pairs() const { return pair_id.size(); }
     void clear();
     void append(const TypingReads& o);
@@ -53,6 +55,7 @@ struct TypingReads {
 
 struct LocusDeviceInput {     // what the GPU needs for one locus
     int32_t C = 0, P = 0, R = 0;
+    bool long_reads = false;             // indel probabilities 0.075 instead of 0.001 (HLATyper.cpp:935-946)
     const std::vector<std::string>* cluster_seq = nullptr;
     std::vector<int32_t> rec_off;        // [R+1]
     std::vector<int16_t> rec_pos;        // exon column
@@ -75,10 +78,15 @@ public:
 
 struct LocusCall { std::string locus; int32_t C = 0, R = 0; std::string call1, call2; double q1 = 0, q2 = 0; LocusDeviceOutput dev; };
 
-struct TypingOptions { bool keep_read_ll = false; int threads = 0; };   // threads: host threads over loci; 0 = one per locus up to the core count, 1 = everything on the calling thread
+struct TypingOptions { bool keep_read_ll = false; int threads = 0; };     // (long-read mode travels with the reads: TypingReads::long_reads)   // threads: host threads over loci; 0 = one per locus up to the core count, 1 = everything on the calling thread
 
 // Gene filter predicate (processBAM.cpp:2427-2446): either mate's [first,last] level interval overlaps a gene.
 bool pair_overlaps_genes(const TypingTables& T, int32_t f1, int32_t l1, int32_t f2, int32_t l2);
+
+// Long-read mode: the reads whose chosen alignment overlaps a gene (processBAM.cpp:2297-2309), packed as TypingReads entries (read + empty mate). Alignment arrays
+// are [n_reads, cap] as hlala_align_long_reads returns them; names: one per read or nullptr ("r<index>").
+TypingReads long_read_typing_input(const TypingTables& T, int64_t n_reads, const char* const* names, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int32_t cap,
+                                   const int32_t* n_cols, const int32_t* level, const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* mapq);
 
 // HLATypeInference on the included pairs; writes out_dir/{R1_bestguess.txt, R1_bestguess_G.txt, R1_PP_<L>_pairs.txt, R1_pileup_<L>.txt,
 // R1_readIDs_<L>.txt, R1_columnIncompatibilities_<L>.txt, summaryStatistics.txt, histogram_matchesPerRead.txt, R1_parameters.txt}.

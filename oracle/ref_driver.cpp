@@ -263,6 +263,37 @@ public:
         if (chdir(cwd) != 0) rc = -5;
         return rc;
     }
+    // long-read mode of the same: alignReadsUnpaired_postSeedExtraction_andStoreInto (processBAM.cpp:2267-2335: alignOneLongRead, gene filter, raw read) followed by
+    // HLATypeInference(no paired reads, unpaired reads, ..., longReadsMode) as called at processBAM.cpp:1920
+    int run_type_long(const Batch& b, const std::string& prg_dir, const std::string& out_dir, const std::string& g_dir, int threads, long long* n_used, double* seconds) {
+        if (!typer) typer = new hla::HLATyper(g, prg_dir, "");
+        omp_set_num_threads(1); eA->init_for_threads(1);
+        std::vector<mapper::reads::oneRead> raw; std::vector<mapper::reads::verboseSeedChain> aligned;
+        for (int64_t r = 0; r < b.n_reads; r++) {
+            mapper::reads::protoSeeds ps; std::vector<int32_t> o1;
+            build_read(b, r, "r" + std::to_string(r), ps.read1_alignments, o1);
+            mapper::reads::verboseSeedChain alignment = alignOneLongRead(ps, nullptr, nullptr, "ont2d");
+            std::pair<int, int> l1 = std::make_pair(alignment.alignment_firstLevel(), alignment.alignment_lastLevel());
+            if (!(l1.first != -1 && typer->intervalOverlapsWithGenes(l1.first, l1.second))) continue;
+            size_t p1 = ps.read1_getPrimaryAlignmentI(); const BamTools::BamAlignment& A1 = std::get<2>(ps.read1_alignments.at(p1));
+            mapper::reads::oneRead r1(A1.Name, A1.QueryBases, A1.Qualities);
+            if (A1.IsReverseStrand()) r1.invert();
+            raw.push_back(r1); aligned.push_back(alignment);
+        }
+        if (n_used) *n_used = (long long)raw.size();
+        char cwd[4096]; if (!getcwd(cwd, sizeof cwd)) return -3;
+        if (chdir(g_dir.c_str()) != 0) return -4;
+        int rc = 0;
+        auto t0 = std::chrono::steady_clock::now();
+        try {
+            omp_set_num_threads(threads < 1 ? 1 : threads);
+            typer->HLATypeInference(std::vector<mapper::reads::oneReadPair>(), std::vector<mapper::reads::verboseSeedChainPair>(), raw, aligned, 0, 1, out_dir, "ont2d");
+        } catch (...) { omp_set_num_threads(1); if (chdir(cwd) != 0) {} throw; }
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        omp_set_num_threads(1);
+        if (chdir(cwd) != 0) rc = -5;
+        return rc;
+    }
 };
 
 std::string g_err;
@@ -380,6 +411,14 @@ int hlala_ref_type(void* h, const char* prg_dir, long long n_reads, const int64_
     Driver* d = (Driver*)h;
     Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
     return guarded([&]() { return d->run_type(b, prg_dir, is_mean, is_sd, out_dir, g_dir, threads, n_used, seconds); });
+}
+
+int hlala_ref_type_long(void* h, const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
+                        const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
+                        const int32_t* cigar_off, const uint32_t* cigar, const char* out_dir, const char* g_dir, int threads, long long* n_used, double* seconds) {
+    Driver* d = (Driver*)h;
+    Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() { return d->run_type_long(b, prg_dir, out_dir, g_dir, threads, n_used, seconds); });
 }
 
 // The unmodified static evaluation functions (what --trueHLA runs, HLA-LA.cpp:801-810). loci ';'-joined in map order, counts [2 * n]: compared, correct.

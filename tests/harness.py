@@ -159,6 +159,13 @@ class Ref:
 
 
 
+    def type_long(self, prg_dir, b, out_dir, threads=1):
+        """long-read mode: alignOneLongRead per read, gene filter, unmodified HLATypeInference(unpaired reads, "ont2d"); writes the reference's files into out_dir."""
+        os.makedirs(out_dir, exist_ok=True)
+        n_used = C.c_longlong(0); sec = C.c_double(0)
+        self._chk(self.lib.hlala_ref_type_long(self.h, prg_dir.encode(), *batch_args(b), out_dir.encode(), prg_dir.encode(), C.c_int(threads), C.byref(n_used), C.byref(sec)))
+        return dict(n_used=n_used.value, seconds=sec.value)
+
     # ---- seed collection (processBAM::extractSeeds2 over in-memory records)
     def extract_seeds(self, names, ref, pos, flag, as_, cigar_off, cigar):
         blob = b"".join(n.encode() + b"\0" for n in names); ns = C.c_longlong(); nr = C.c_longlong()

@@ -18,7 +18,7 @@ struct LoopDevice : TypingDevice {   // HLATyper.cpp:2049-2364 restated as loops
         std::vector<double> v((size_t)3 * ((size_t)C * ((size_t)C + 1) / 2), NAN); allreduce(v.data(), (long long)v.size());
     }
     void run_locus(const LocusDeviceInput& in, bool, LocusDeviceOutput& out) override {
-        const int C = in.C, R = in.R; const int r0 = (int)((long long)R * rank / world), r1 = (int)((long long)R * (rank + 1) / world); const double ll_ins_actual = log(0.001) + log(1.0 / 4.0), ll_del = log(0.001), ll_mm = log(1 - 0.001 - 0.001);
+        const int C = in.C, R = in.R; const int r0 = (int)((long long)R * rank / world), r1 = (int)((long long)R * (rank + 1) / world); const double ip = in.long_reads ? 0.075 : 0.001, dp = in.long_reads ? 0.075 : 0.001; const double ll_ins_actual = log(ip) + log(1.0 / 4.0), ll_del = log(dp), ll_mm = log(1 - ip - dp);
         out.LL.assign((size_t)C * R, 0); out.mism.assign((size_t)C * R, 0);
         for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) { double ll = 0; int mm = 0; const std::string& cs = (*in.cluster_seq)[c];
             for (int k = in.rec_off[r]; k < in.rec_off[r + 1]; k++) { char e = cs[in.rec_pos[k]]; char c0 = (char)in.rec_c0[k]; unsigned glen = in.rec_glen[k]; double lp = 0;
@@ -50,6 +50,18 @@ const char* typing_host_last_error() { return g_err.c_str(); }
 int typing_host_run_ranked(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
                            const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, double is_mean, double is_sd, const char* out_dir, int roundtrip_blob,
                            int rank, int world, host_allreduce_fn allreduce, double* call_q /* [n_loci * 2] */, double* pair_ll_sum /* [n_loci] */);
+// long-read mode: alignment arrays [n_reads, cap] of single reads (any implementation's long_reads output), reads named "r<index>"
+int typing_host_run_long(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
+                         const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, const char* out_dir, int roundtrip_blob) {
+    try {
+        TypingTables T; T.load(prg_dir);
+        TypingReads tr = long_read_typing_input(T, n_reads, nullptr, read_off, bases, quals, cap, n_cols, level, g, s, mq, reverse, read_mapq), use;
+        if (roundtrip_blob) { std::vector<uint8_t> b = tr.serialize(); use.deserialize_append(b.data(), b.size()); } else use = tr;
+        LoopDevice dev; TypingOptions opt; std::vector<LocusCall> calls;
+        run_typing(T, use, 0, 1, out_dir, prg_dir, dev, opt, calls);
+        return (int)calls.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 int typing_host_run(const char* prg_dir, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals, int cap, const int32_t* n_cols, const int32_t* level,
                     const uint8_t* g, const uint8_t* s, const uint8_t* mq, const uint8_t* reverse, const double* read_mapq, double is_mean, double is_sd, const char* out_dir, int roundtrip_blob) {
     return typing_host_run_ranked(prg_dir, n_reads, read_off, bases, quals, cap, n_cols, level, g, s, mq, reverse, read_mapq, is_mean, is_sd, out_dir, roundtrip_blob, 0, 1, nullptr, nullptr, nullptr);
