@@ -830,9 +830,9 @@ int hlala_session_digest(hlala_session_t* s, int64_t out[4], double* sum_pair_ll
 // HLA typing stage
 namespace {
 
-TypingScoreTables make_typing_tables() {   // HLATyper.cpp:2060-2066, 2189-2216; Utilities.cpp:357-377, 1368-1379
+TypingScoreTables make_typing_tables(bool long_reads = false) {   // HLATyper.cpp:935-958, 2189-2216; Utilities.cpp:357-377, 1368-1379
     TypingScoreTables t;
-    const double insertionP = 0.001, deletionP = 0.001;
+    const double insertionP = long_reads ? 0.075 : 0.001, deletionP = long_reads ? 0.075 : 0.001;
     const double ll_ins = log(insertionP);
     t.ll_ins_actual = ll_ins + log(1.0 / 4.0); t.ll_del = log(deletionP); t.ll_mm = log(1 - insertionP - deletionP);
     t.log_half = log(0.5); t.log_two = log(1 + exp(0.0));
@@ -912,7 +912,8 @@ struct GpuTypingDevice : TypingDevice {
 
 } // namespace
 
-struct hlala_typer { TypingTables T; std::vector<LocusCall> calls; double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0}; bool tables_on_device = false; int device = -1; };
+struct hlala_typer { TypingTables T; std::vector<LocusCall> calls; double ms[2] = {0, 0}; int launches[2] = {0, 0}; double work[2] = {0, 0}; bool tables_on_device = false, tables_long = false; int device = -1;
+                     std::vector<uint8_t> long_blob; };
 
 extern "C" {
 
@@ -968,6 +969,21 @@ int hlala_session_typing_extract(hlala_session_t* s, const hlala_typer_t* t, con
     });
 }
 
+// Long-read mode: gene filter of alignReadsUnpaired_postSeedExtraction_andStoreInto (processBAM.cpp:2297-2331) over the host arrays hlala_align_long_reads returned.
+int hlala_typing_blob_from_long_reads(hlala_typer_t* t, const hlala_seed_batch_t* batch, const char* const* read_names, const hlala_pair_out_t* aligned,
+                                      const uint8_t** blob, int64_t* blob_bytes, int64_t* n_selected) {
+    if (!t || !batch || !aligned || !blob || !blob_bytes) return fail(HLALA_E_ARG, "hlala_typing_blob_from_long_reads: null argument");
+    if (!aligned->n_cols || !aligned->level || !aligned->gchar || !aligned->schar || !aligned->mapq || !aligned->read_reverse || !aligned->pair_mapq)
+        return fail(HLALA_E_ARG, "hlala_typing_blob_from_long_reads: the typing stage needs n_cols, level, gchar, schar, mapq, read_reverse and pair_mapq of hlala_align_long_reads");
+    return guarded([&]() {
+        TypingReads tr = long_read_typing_input(t->T, batch->n_reads, read_names, batch->read_off, batch->bases, batch->quals, aligned->max_columns, aligned->n_cols, aligned->level,
+                                                aligned->gchar, aligned->schar, aligned->mapq, aligned->read_reverse, aligned->pair_mapq);
+        t->long_blob = tr.serialize();
+        *blob = t->long_blob.data(); *blob_bytes = (int64_t)t->long_blob.size(); if (n_selected) *n_selected = (int64_t)tr.n_pairs();
+        return 0;
+    });
+}
+
 int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs, const int64_t* blob_bytes, int n_blobs, double is_mean, double is_sd,
                       const char* out_dir, const char* g_nom_dir, int rank, int world, hlala_allreduce_f64_fn allreduce, void* allreduce_ctx, int keep_read_ll) {
     if (!t || !blobs || !blob_bytes || n_blobs < 1 || !g_nom_dir) return fail(HLALA_E_ARG, "hlala_typer_infer: null argument");
@@ -976,8 +992,8 @@ int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs,
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(HLALA_E_CUDA, "no CUDA device available: the typing kernels have no CPU fallback");
         CUDA_OK(cudaSetDevice(device));
-        if (!t->tables_on_device || t->device != device) { CUDA_OK(upload_typing_tables(make_typing_tables())); t->tables_on_device = true; t->device = device; }
         TypingReads all; for (int i = 0; i < n_blobs; i++) all.deserialize_append(blobs[i], (size_t)blob_bytes[i]);
+        if (!t->tables_on_device || t->device != device || t->tables_long != all.long_reads) { CUDA_OK(upload_typing_tables(make_typing_tables(all.long_reads))); t->tables_on_device = true; t->device = device; t->tables_long = all.long_reads; }
         GpuTypingDevice dev; dev.device = device; dev.rank = rank; dev.world = world; dev.allreduce = allreduce; dev.ctx = allreduce_ctx;
         TypingOptions opt; opt.keep_read_ll = keep_read_ll != 0;
         if (allreduce) opt.threads = 1;   // the caller's all-reduce callback (NCCL, Python) is only ever entered from the calling thread
@@ -1220,18 +1236,26 @@ struct hlala_bam_batch { BamBatch b; std::vector<const char*> names; };
 
 extern "C" {
 
-int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out) {
+static int bam_read_impl(const hlala_graph_t* g, const char* bam_path, int threads, bool long_reads, hlala_bam_batch_t** out) {
     if (!g || !bam_path || !out) return fail(HLALA_E_ARG, "hlala_bam_read: null argument");
     *out = nullptr;
     return guarded([&]() {
         std::unique_ptr<hlala_bam_batch> B(new hlala_bam_batch());
         std::vector<int64_t> len; for (int32_t c = 0; c < g->h.n_contigs; c++) len.push_back(g->h.contig_off[(size_t)c + 1] - g->h.contig_off[(size_t)c]);
-        read_bam_seeds(bam_path, g->h.contig_bam_name, len, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency()), B->b);
+        read_bam_seeds(bam_path, g->h.contig_bam_name, len, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency()), B->b, long_reads);
+        if (long_reads) {     // hand the batch out in the single-read form hlala_align_long_reads takes: the empty second reads carry no bases and no chains
+            BamBatch& b = B->b; const size_t n = b.pair_name.size();
+            std::vector<int64_t> ro(n + 1); std::vector<int32_t> co(n + 1);
+            for (size_t r = 0; r <= n; r++) { ro[r] = b.read_off[2 * r]; co[r] = b.chain_off[2 * r]; }
+            b.read_off.swap(ro); b.chain_off.swap(co);
+        }
         for (const std::string& n : B->b.pair_name) B->names.push_back(n.c_str());
         *out = B.release();
         return 0;
     });
 }
+int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out) { return bam_read_impl(g, bam_path, threads, false, out); }
+int hlala_bam_read_long(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out) { return bam_read_impl(g, bam_path, threads, true, out); }
 int hlala_bam_batch_view(const hlala_bam_batch_t* B, hlala_seed_batch_t* view, const char* const** pair_names) {
     if (!B || !view) return fail(HLALA_E_ARG, "hlala_bam_batch_view: null argument");
     const BamBatch& b = B->b;

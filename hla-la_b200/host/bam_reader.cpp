@@ -70,7 +70,11 @@ struct Rec { int32_t ref, pos, as; uint16_t flag; uint32_t cigar_at, n_cigar; si
 
 } // namespace
 
-void read_bam_seeds(const std::string& path, const std::vector<std::string>& contig_names, const std::vector<int64_t>& contig_len, int threads, BamBatch& out) {
+void read_bam_seeds(const std::string& path, const std::vector<std::string>& contig_names, const std::vector<int64_t>& contig_len, int threads, BamBatch& out, bool long_reads) {
+    // long_reads (extractSeeds2 with a longReadMode, processBAM.cpp:732-738, 781-784, 816-819): only primary records are kept, records need not be paired, and every record
+    // counts as "mate 1" of its read name; a read is complete when it holds a primary record (protoSeeds::isComplete_unpaired). The batch keeps its pair layout:
+    // read 2p is the long read, read 2p+1 an empty mate (no bases, no chains).
+    auto mate_of = [long_reads](uint16_t flag) { return long_reads ? 0 : ((flag & 0x40) ? 0 : 1); };
     out = BamBatch();
     const bool trace = getenv("HLALA_BAM_TRACE") != nullptr; auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (!trace) return; auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[bam] %-10s %6.2f s\n", what, std::chrono::duration<double>(t1 - t0).count()); t0 = t1; };
@@ -104,12 +108,13 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
                 const size_t at_name = 32, at_cigar = at_name + l_read_name, at_seq = at_cigar + 4ull * n_cigar, at_qual = at_seq + (size_t)(l_seq + 1) / 2, at_aux = at_qual + (size_t)l_seq;
                 if (l_seq < 0 || at_aux > bs) { err_kind = 1; continue; }
                 if (flag & 0x4) continue;                                   // IsMapped (processBAM.cpp:727)
+                if (long_reads && (flag & 0x100)) continue;                 // long-read mode: primary records only (:732-738)
                 if (ref < 0 || ref >= (int32_t)n_ref || ref2contig[ref] < 0) continue;   // not an interesting contig (:739)
                 if (n_cigar == 0) continue;                                 // :755
                 int64_t reflen = 0; for (uint32_t k = 0; k < n_cigar; k++) { const uint32_t c = le32(r + at_cigar + 4 * k); const int op = c & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += c >> 4; }
                 const int contig = ref2contig[ref]; const int64_t stop = (int64_t)pos + reflen - 1;
                 if (!(pos >= 0 && pos <= contig_len[contig] - 1 && stop >= 0 && stop <= contig_len[contig] - 1)) continue;   // inside the interval = the whole contig (:764-766)
-                if (!(flag & 0x1)) { err_kind = 2; continue; }
+                if (!long_reads && !(flag & 0x1)) { err_kind = 2; continue; }
                 int32_t as = 0; bool have_as = false; bool bad = false;
                 for (size_t a = at_aux; a + 3 <= bs && !bad;) {   // aux fields: tag[2] type value
                     const char t0 = (char)r[a], t1 = (char)r[a + 1], ty = (char)r[a + 2]; a += 3; size_t len = 0; int64_t v = 0; bool is_int = true;
@@ -155,7 +160,7 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
         rec_gid[i] = g; gcount[(size_t)g]++; out.records_used++;
     }
     // ---- the insert-size sample (see bam_reader.h): replay of extractSeeds(4000) over the kept records
-    {
+    if (!long_reads) {     // the insert-size sample (paired reads only)
         std::vector<uint32_t> scan; scan.reserve((size_t)out.records_used); for (size_t i = 0; i < NR; i++) if (keep[i]) scan.push_back((uint32_t)i);
         std::vector<int32_t> contig_rank(contig_names.size());      // byte order of the contig names = iteration order of the reference's interval map
         { std::vector<int32_t> o(contig_names.size()); for (size_t i = 0; i < o.size(); i++) o[i] = (int32_t)i; std::sort(o.begin(), o.end(), [&](int32_t x, int32_t y) { return contig_names[(size_t)x] < contig_names[(size_t)y]; }); for (size_t k = 0; k < o.size(); k++) contig_rank[(size_t)o[k]] = (int32_t)k; }
@@ -215,7 +220,7 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
         for (;;) { const size_t g0 = nextg.fetch_add(1) * blk; if (g0 >= NG) break; const size_t g1 = std::min(NG, g0 + blk);
             for (size_t g = g0; g < g1; g++) {
                 GInfo& I = ginfo[g]; int64_t w = goff[g];
-                for (int m = 0; m < 2; m++) { for (int64_t j = goff[g]; j < goff[g + 1]; j++) { const uint32_t i = grec[(size_t)j]; if (((recs[i].flag & 0x40) ? 0 : 1) == m) gm[(size_t)w++] = i; } if (m == 0) I.n0 = (int32_t)(w - goff[g]); }
+                for (int m = 0; m < 2; m++) { for (int64_t j = goff[g]; j < goff[g + 1]; j++) { const uint32_t i = grec[(size_t)j]; if (mate_of(recs[i].flag) == m) gm[(size_t)w++] = i; } if (m == 0) I.n0 = (int32_t)(w - goff[g]); }
                 for (int m = 0; m < 2; m++) {
                     // the record whose SEQ/QUAL stand for the read: the first primary record after sortChainsInSeeds (processBAM.cpp:1945: std::sort ascending by AS, then std::reverse)
                     const uint32_t* mr = gm.data() + goff[g] + (m ? I.n0 : 0); const int nm = m ? (int)(goff[g + 1] - goff[g]) - I.n0 : I.n0;
@@ -224,7 +229,7 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
                     int prim = -1; for (int i : idx) if (!(recs[mr[i]].flag & 0x100)) { prim = i; break; }
                     (m ? I.prim1 : I.prim0) = prim;
                 }
-                I.complete = (I.prim0 >= 0 && I.prim1 >= 0) ? 1 : 0;   // protoSeeds::isComplete
+                I.complete = long_reads ? (I.prim0 >= 0 ? 1 : 0) : ((I.prim0 >= 0 && I.prim1 >= 0) ? 1 : 0);   // protoSeeds::isComplete / isComplete_unpaired
             } } });
     std::vector<int32_t> pair_group; pair_group.reserve(NG);
     out.read_off.assign(1, 0); out.chain_off.assign(1, 0);
@@ -236,7 +241,7 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
         int64_t ncig = 0;
         for (int m = 0; m < 2; m++) {
             const uint32_t* mr = gm.data() + goff[g] + (m ? I.n0 : 0); const int nm = m ? (int)(goff[g + 1] - goff[g]) - I.n0 : I.n0;
-            out.read_off.push_back(out.read_off.back() + recs[mr[m ? I.prim1 : I.prim0]].l_seq);
+            out.read_off.push_back(out.read_off.back() + ((long_reads && m) ? 0 : recs[mr[m ? I.prim1 : I.prim0]].l_seq));
             out.chain_off.push_back(out.chain_off.back() + nm);
             for (int i = 0; i < nm; i++) ncig += recs[mr[i]].n_cigar;
         }
@@ -255,6 +260,7 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
                 int64_t cg = pair_cigar_at[pi];
                 for (int m = 0; m < 2; m++) {
                     const uint32_t* mr = gm.data() + goff[g] + (m ? I.n0 : 0); const int nm = m ? (int)(goff[g + 1] - goff[g]) - I.n0 : I.n0;
+                    if (long_reads && m) continue;     // the empty mate
                     const Rec& P = recs[mr[m ? I.prim1 : I.prim0]]; const int64_t b0 = out.read_off[2 * pi + (size_t)m];
                     for (int32_t i = 0; i < P.l_seq; i++) { const uint8_t b = d[P.seq_at + (size_t)i / 2]; out.bases[(size_t)b0 + (size_t)i] = (uint8_t)SEQ16[(i & 1) ? (b & 15) : (b >> 4)]; }
                     const uint8_t* q = &d[P.seq_at + (size_t)(P.l_seq + 1) / 2];
@@ -266,6 +272,7 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
                         out.cigar_off[ci + 1] = (int32_t)cg; }
                 }
                 // insert-size sample: both primaries on one contig, opposite strands, forward mate upstream; gap = start of the downstream mate - end of the upstream mate - 1
+                if (long_reads) continue;
                 const Rec& A = recs[gm[(size_t)goff[g] + (size_t)I.prim0]]; const Rec& B = recs[gm[(size_t)goff[g] + (size_t)I.n0 + (size_t)I.prim1]];
                 if (A.ref == B.ref && ((A.flag ^ B.flag) & 0x10)) {
                     auto end_of = [&](const Rec& c) { int64_t rl = 0; for (uint32_t k = 0; k < c.n_cigar; k++) { const uint32_t cgv = cigar_of(c, k); const int op = cgv & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += cgv >> 4; } return (int64_t)c.pos + rl - 1; };

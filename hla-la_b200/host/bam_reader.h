@@ -44,6 +44,7 @@ struct BamBatch {
 
 // contig_names: BAM reference name of every PRG contig in sequences.txt order (FlatGraph::contig_bam_name); contig_len: their lengths.
 // Throws std::runtime_error on malformed input.
-void read_bam_seeds(const std::string& path, const std::vector<std::string>& contig_names, const std::vector<int64_t>& contig_len, int threads, BamBatch& out);
+// long_reads: the selection of extractSeeds2 in long-read mode (primary records only, unpaired); the batch keeps the pair layout with an empty second read per name.
+void read_bam_seeds(const std::string& path, const std::vector<std::string>& contig_names, const std::vector<int64_t>& contig_len, int threads, BamBatch& out, bool long_reads = false);
 
 } // namespace hlala

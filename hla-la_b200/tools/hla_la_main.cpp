@@ -61,6 +61,7 @@ int nccl_sum_f64(void* ctx, uint64_t dev_ptr, int64_t count, void* stream) {    
 }
 
 static int evaluate_calls(std::map<std::string, std::string>& a, const std::string& out_dir);
+static int run_long_reads(std::map<std::string, std::string>& a);
 static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus) { fprintf(stderr, "hlala-b200: --gpus %d but %d CUDA devices are visible\n", n_gpus, ndev); return 1; }
@@ -129,6 +130,68 @@ static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     return 0;
 }
 
+// --longReads ont2d|pacbio (HLA-LA.cpp:756-799 with a long-read mode): the remapped BAM of single long reads -> reads_per_level.txt + hla/*. Seam:
+//   processBAM::alignReads_and_inferHLA(BAM, 0, 0, 0, outputDirectory, false, &HLAtyper, 1, longReads)  ->  alignReadsUnpaired_postSeedExtraction_andStoreInto
+// (processBAM.cpp:1855, 2224-2337) + HLATypeInference(no paired reads, unpaired reads, ..., longReads) (:1920). Reads are aligned in chunks (the column arrays of
+// thousands of columns per read are large); the gene-overlapping reads of every chunk are packed, and one typing call sees them all.
+static int run_long_reads(std::map<std::string, std::string>& a) {
+    const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; const int device = a.count("device") ? atoi(a["device"].c_str()) : 0;
+    g_t0 = std::chrono::steady_clock::now();
+    hlala_graph_t* g = nullptr;
+    if (hlala_graph_load(prg.c_str(), &g)) return die("loading the PRG");
+    if (hlala_graph_to_gpu(g, device)) return die("uploading the PRG");
+    phase("PRG loaded and on the GPU");
+    hlala_bam_batch_t* bam = nullptr;
+    if (hlala_bam_read_long(g, a["BAM"].c_str(), a.count("threads") ? atoi(a["threads"].c_str()) : 0, &bam)) return die("reading the BAM");
+    hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double m0 = 0, s0 = 0; int64_t n0 = 0;
+    hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &m0, &s0, &n0);
+    phase("BAM read, primary records selected and grouped");
+    const int64_t n = batch.n_reads; int64_t longest = 0; for (int64_t r = 0; r < n; r++) longest = std::max<int64_t>(longest, batch.read_off[r + 1] - batch.read_off[r]);
+    fprintf(stdout, "hlala-b200: %lld records, %lld used, %lld read names, %lld without a primary record, %lld long reads to align (longest %lld bases)\n",
+            (long long)counts[0], (long long)counts[1], (long long)counts[2], (long long)counts[3], (long long)n, (long long)longest);
+    if (n == 0) { fprintf(stderr, "hlala-b200: no long read with a primary record on the PRG contigs\n"); return 1; }
+    const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : (int)std::min<int64_t>(16384, longest + longest / 4 + 64);
+    mkdir(out_dir.c_str(), 0777);
+    const int64_t nl = hlala_graph_n_levels(g); std::vector<int32_t> cov((size_t)std::max<int64_t>(nl - 1, 1), 0);
+    hlala_typer_t* t = nullptr; if (hlala_typer_create(prg.c_str(), &t)) return die("loading the typing tables");
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)1 << 30) / ((int64_t)maxcol * 12)));      // about 1 GB of column arrays per chunk
+    std::vector<std::vector<uint8_t>> blobs; int64_t n_sel = 0;
+    std::vector<double> mapq((size_t)chunk), ll((size_t)chunk); std::vector<uint8_t> rev((size_t)chunk), gc((size_t)chunk * maxcol), sc((size_t)chunk * maxcol), mq((size_t)chunk * maxcol);
+    std::vector<int32_t> ncol((size_t)chunk), lv((size_t)chunk * maxcol);
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t r1 = std::min(n, r0 + chunk), m = r1 - r0;
+        std::vector<int64_t> ro((size_t)m + 1); std::vector<int32_t> co((size_t)m + 1), go;
+        const int32_t c0 = batch.chain_off[r0], c1 = batch.chain_off[r1]; const int32_t g0 = batch.cigar_off[c0];
+        for (int64_t r = r0; r <= r1; r++) { ro[(size_t)(r - r0)] = batch.read_off[r] - batch.read_off[r0]; co[(size_t)(r - r0)] = batch.chain_off[r] - c0; }
+        go.resize((size_t)(c1 - c0) + 1); for (int32_t c = c0; c <= c1; c++) go[(size_t)(c - c0)] = batch.cigar_off[c] - g0;
+        hlala_seed_batch_t v = batch; v.n_reads = m; v.read_off = ro.data(); v.bases = batch.bases + batch.read_off[r0]; v.quals = batch.quals + batch.read_off[r0]; v.chain_off = co.data();
+        v.chain_contig = batch.chain_contig + c0; v.chain_pos = batch.chain_pos + c0; v.chain_flag = batch.chain_flag + c0; v.chain_as = batch.chain_as + c0; v.cigar_off = go.data(); v.cigar = batch.cigar + g0;
+        hlala_pair_out_t o{}; o.max_columns = maxcol; o.pair_mapq = mapq.data(); o.pair_ll = ll.data(); o.read_reverse = rev.data(); o.n_cols = ncol.data(); o.level = lv.data(); o.gchar = gc.data(); o.schar = sc.data(); o.mapq = mq.data();
+        if (hlala_align_long_reads(g, &v, &o, cov.data())) return die("aligning the long reads");
+        const uint8_t* blob = nullptr; int64_t nb = 0, ns = 0;
+        if (hlala_typing_blob_from_long_reads(t, &v, names + r0, &o, &blob, &nb, &ns)) return die("selecting the gene-overlapping reads");
+        blobs.emplace_back(blob, blob + nb); n_sel += ns;
+    }
+    phase("long reads aligned (seed projection, padding, likelihoods, mapping qualities)");
+    {   const std::string path = out_dir + "/reads_per_level.txt"; FILE* f = fopen(path.c_str(), "w");
+        if (!f) { fprintf(stderr, "hlala-b200: cannot write %s\n", path.c_str()); return 1; }
+        for (int64_t l = 0; l + 1 < nl; l++) fprintf(f, "%lld\t%s\t%d\n", (long long)l, hlala_graph_level_name(g, l), cov[(size_t)l]);
+        fclose(f); }
+    fprintf(stdout, "hlala-b200: %lld long reads overlap the typed genes\n", (long long)n_sel);
+    if (n_sel == 0) { fprintf(stderr, "hlala-b200: no long read overlaps a typed gene\n"); return 1; }
+    std::vector<const uint8_t*> bp; std::vector<int64_t> bb; for (auto& b : blobs) { bp.push_back(b.data()); bb.push_back((int64_t)b.size()); }
+    const std::string hla_dir = out_dir + "/hla";
+    struct stat sb; const std::string gdir = a.count("hla_nom_g_dir") ? a["hla_nom_g_dir"] : (stat((prg + "/hla_nom_g.txt").c_str(), &sb) == 0 ? prg : std::string("."));
+    if (hlala_typer_infer(t, device, bp.data(), bb.data(), (int)bp.size(), 0, 1, hla_dir.c_str(), gdir.c_str(), 0, 1, nullptr, nullptr, 0)) return die("HLA type inference");
+    phase("HLA types inferred, hla/* written");
+    for (int l = 0; l < hlala_typer_n_loci(t); l++) {
+        const char* a1 = nullptr; const char* a2 = nullptr; double q1 = 0, q2 = 0;
+        if (hlala_typer_result_call(t, l, &a1, &a2, &q1, &q2) == 0) fprintf(stdout, "%s\t%s\t%s\t%g\t%g\n", hlala_typer_locus_name(t, l), a1, a2, q1, q2);
+    }
+    hlala_typer_free(t); hlala_bam_batch_free(bam); hlala_graph_free(g);
+    return evaluate_calls(a, out_dir);
+}
+
 // --trueHLA <file> (HLA-LA.cpp:801-810): hla/R1_bestguess.txt against known types, the reference's summary on stdout
 static int evaluate_calls(std::map<std::string, std::string>& a, const std::string& out_dir) {
     if (!a.count("trueHLA") || a["trueHLA"].empty()) return 0;
@@ -161,10 +224,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, "hlala-b200: --FASTQ1/--FASTQ2/--FASTQU: map the reads first (bwa mem -a -M <PRG_graph_dir>/mapping_PRGonly/referenceGenome.fa ... | samtools sort) and pass the result as --BAM\n");
         return 2;
     }
-    if (a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "") {
-        fprintf(stderr, "hlala-b200: --longReads %s: long reads are aligned through the C ABI (hlala_align_long_reads); HLA typing from unpaired reads (HLATyper.cpp:1467-1495, 3568) is not part of this program yet\n", a["longReads"].c_str());
-        return 2;
-    }
+    const bool long_reads = a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "";
+    if (long_reads && a["longReads"] != "ont2d" && a["longReads"] != "pacbio") { fprintf(stderr, "hlala-b200: --longReads must be 0, ont2d or pacbio\n"); return 2; }     // HLA-LA.cpp:759
     if (a["action"] == "prepareGraph" && a.count("PRG_graph_dir")) {
         // HLA-LA.cpp:1341-1385 reads graph.txt, computes the gap-edge paths and serialises the pointer graph (hours and ~40 GB for the real
         // PRG). Here the flat arrays (gap paths included) are built in seconds and cached next to graph.txt (PRG/graph.hlala_b200.cache); the
@@ -182,9 +243,11 @@ int main(int argc, char** argv) {
         fprintf(stderr, "usage: hlala-b200 --action HLA --sampleID <id> --BAM <remapped.bam> --outputDirectory <dir> --PRG_graph_dir <dir>\n"
                         "       hlala-b200 --action prepareGraph --PRG_graph_dir <dir>\n"
                         "       hlala-b200 --action testBinary\n"
+                        "       [--longReads ont2d|pacbio]  (the BAM then holds single long reads: bwa mem -x ont2d|pacbio)\n"
                         "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n> | --gpus <N>] [--maxColumns <n>] [--maxThreads <n>] [--trueHLA <file>]\n");
         return 2;
     }
+    if (long_reads) return run_long_reads(a);
     if (a.count("gpus") && atoi(a["gpus"].c_str()) > 1) return run_multi_gpu(a, atoi(a["gpus"].c_str()));
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"];
     const int device = a.count("device") ? atoi(a["device"].c_str()) : 0; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;

@@ -646,17 +646,18 @@ int cmd_bam(const std::map<std::string, std::string>& a) {
     const uint8_t* bases = f.get<uint8_t>("bases"); const uint8_t* quals = f.get<uint8_t>("quals");
     const int32_t* chain_off = f.get<int32_t>("chain_off"); const int32_t* chain_contig = f.get<int32_t>("chain_contig"); const int32_t* chain_pos = f.get<int32_t>("chain_pos");
     const uint16_t* chain_flag = f.get<uint16_t>("chain_flag"); const int32_t* chain_as = f.get<int32_t>("chain_as"); const int32_t* cigar_off = f.get<int32_t>("cigar_off"); const uint32_t* cigar = f.get<uint32_t>("cigar");
+    const bool single = arg<int>(a, "single", 0) != 0;     // long-read batch: one read per name, flags without the pairing bits (bwa mem -x ont2d writes secondary records too: they are kept here and must be dropped by the reader)
     Bgzf z(out);
     std::string text = "@HD\tVN:1.6\tSO:unsorted\n"; for (const Contig& c : cs) text += "@SQ\tSN:PRG_" + std::to_string(c.id) + "\tLN:" + std::to_string(c.seq.size()) + "\n";
     z.write("BAM\1", 4); z.put<int32_t>((int32_t)text.size()); z.write(text.data(), text.size()); z.put<int32_t>((int32_t)cs.size());
     for (const Contig& c : cs) { const std::string n = "PRG_" + std::to_string(c.id); z.put<int32_t>((int32_t)n.size() + 1); z.write(n.c_str(), n.size() + 1); z.put<int32_t>((int32_t)c.seq.size()); }
     auto code = [](uint8_t b) -> uint8_t { const char* t = "=ACMGRSVTWYHKDBN"; const char* q = strchr(t, (char)b); return q ? (uint8_t)(q - t) : 15; };
     for (int64_t r = 0; r < n_reads; r++) {
-        char name[32]; snprintf(name, sizeof name, "r%09lld", (long long)(r / 2));
+        char name[32]; snprintf(name, sizeof name, "r%09lld", (long long)(single ? r : r / 2));
         const int64_t b0 = read_off[r]; const int32_t L = (int32_t)(read_off[r + 1] - b0);
         for (int32_t c = chain_off[r]; c < chain_off[r + 1]; c++) {
             const bool secondary = (chain_flag[c] & 0x100) != 0; const int32_t l_seq = secondary ? 0 : L; const int32_t n_cig = cigar_off[c + 1] - cigar_off[c];
-            const uint16_t flag = (uint16_t)((chain_flag[c] & 0x110) | 0x1 | ((r & 1) ? 0x80 : 0x40));
+            const uint16_t flag = single ? (uint16_t)(chain_flag[c] & 0x110) : (uint16_t)((chain_flag[c] & 0x110) | 0x1 | ((r & 1) ? 0x80 : 0x40));
             std::vector<uint8_t> rec;
             auto put32 = [&](int32_t v) { const uint8_t* q = (const uint8_t*)&v; rec.insert(rec.end(), q, q + 4); }; auto put16 = [&](uint16_t v) { rec.push_back((uint8_t)(v & 255)); rec.push_back((uint8_t)(v >> 8)); };
             put32(chain_contig[c]); put32(chain_pos[c]); rec.push_back((uint8_t)(strlen(name) + 1)); rec.push_back(60); put16(4680); put16((uint16_t)n_cig); put16(flag); put32(l_seq); put32(-1); put32(-1); put32(0);

@@ -162,7 +162,7 @@ int hlala_session_fetch(hlala_session_t* s, hlala_pair_out_t* out);
 int hlala_session_digest(hlala_session_t* s, int64_t out[4], double* sum_pair_ll);
 
 /* ---------------------------------------------------------------------------------------------------------------------
- * HLA typing stage (short-read paired mode). Reference seam B4 of SURVEY.md §8b:
+ * HLA typing stage (short-read paired mode; long-read unpaired mode through hlala_typing_blob_from_long_reads). Reference seam B4 of SURVEY.md §8b:
  *   hlala_typer_create             hla::HLATyper::HLATyper (segments, gene boundaries)  hla/HLATyper.cpp:36-256
  *                                  + exon tables / allele clustering of HLATypeInference  hla/HLATyper.cpp:1177-1372
  *   hlala_session_set_keep_columns (no counterpart: keep the chosen alignments' columns in HBM for the typing stage)
@@ -184,6 +184,14 @@ const char* hlala_typer_locus_name(const hlala_typer_t* t, int locus);
 int hlala_typer_locus_dims(const hlala_typer_t* t, int locus, int32_t* n_clusters, int32_t* n_exon_columns);
 
 int hlala_session_set_keep_columns(hlala_session_t* s, int on);
+/* Long-read mode (HLA-LA.pl --longReads): the reads whose alignment overlaps a typed gene (processBAM::alignReadsUnpaired_postSeedExtraction_andStoreInto,
+ * mapper/processBAM.cpp:2297-2331), packed for hlala_typer_infer from the HOST arrays hlala_align_long_reads filled (n_cols, level, gchar, schar, mapq,
+ * read_reverse, pair_mapq are required). hlala_typer_infer recognises such a blob and runs HLATypeInference's long-read branch (hla/HLATyper.cpp:935-946 rates
+ * 0.075, :1079-1097, :1467-1495 unpaired projection and the >= 1000-column gate, oneReadAlignment_2_exonPositions_unpaired :3568-3930, no first-20 filter :1509,
+ * allele-frequency and strand filters :1797-1880, novel-gap rule :1918); is_mean / is_sd are not used in that mode. read_names: [n_reads] or NULL ("r<read>").
+ * *blob stays valid until the next call with this typer or hlala_typer_free. */
+int hlala_typing_blob_from_long_reads(hlala_typer_t* t, const hlala_seed_batch_t* batch, const char* const* read_names, const hlala_pair_out_t* aligned,
+                                      const uint8_t** blob, int64_t* blob_bytes, int64_t* n_selected);
 /* After hlala_session_run with keep_columns on. pair_names: [n_pairs] BAM QNAMEs or NULL ("r<pair_index_base + pair>").
  * *blob stays valid until the next call on this session or hlala_session_free. */
 int hlala_session_typing_extract(hlala_session_t* s, const hlala_typer_t* t, const char* const* pair_names, int64_t pair_index_base,
@@ -262,6 +270,9 @@ void hlala_kmer_chains_free(hlala_kmer_chains_t* c);
  * estimateInsertSize processBAM.cpp:1071-1181; ours is the whole-file statistic on contig coordinates and can be overridden by the caller). */
 typedef struct hlala_bam_batch hlala_bam_batch_t;
 int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads /* <=0: all cores */, hlala_bam_batch_t** out);
+/* Long-read mode of the same (extractSeeds2 with a longReadMode, mapper/processBAM.cpp:732-738, 781-784, 816-819; protoSeeds::isComplete_unpaired): primary records
+ * only, unpaired; hlala_bam_batch_view then shows ONE read per name (the form hlala_align_long_reads takes), n_reads = number of names, pair_names = read names. */
+int hlala_bam_read_long(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out);
 int hlala_bam_batch_view(const hlala_bam_batch_t* b, hlala_seed_batch_t* view, const char* const** pair_names);
 int hlala_bam_batch_stats(const hlala_bam_batch_t* b, int64_t counts[4], double* is_mean, double* is_sd, int64_t* is_n);
 void hlala_bam_batch_free(hlala_bam_batch_t* b);

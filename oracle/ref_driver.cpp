@@ -497,7 +497,8 @@ int hlala_ref_find_chains_fetch(void* idx, int64_t* chain_off, int32_t* begin, i
 
 // ---- seed collection: the reference's own extractSeeds2 over in-memory records (record i carries the tag XI = i)
 struct SeedsRef { std::vector<std::string> names; std::vector<int32_t> complete, n1, n2, recs; };
-static SeedsRef g_seeds;
+static SeedsRef g_seeds; static bool g_seeds_long_mode = false;
+void hlala_ref_extract_seeds_long_mode(int on) { g_seeds_long_mode = on != 0; }     // extractSeeds2(..., longReadMode) / isComplete_unpaired
 int hlala_ref_extract_seeds(void* h, long long n_rec, const char* names_blob /* n_rec zero-terminated names */, const int32_t* ref, const int32_t* pos, const uint16_t* flag, const int32_t* as,
                             const int32_t* cigar_off, const uint32_t* cigar, long long* n_seeds, long long* n_out_recs) {
     Driver* d = (Driver*)h;
@@ -515,10 +516,10 @@ int hlala_ref_extract_seeds(void* h, long long n_rec, const char* names_blob /* 
             a.QueryBases.assign((size_t)qlen, 'A'); a.Qualities.assign((size_t)qlen, 'I'); a.Length = qlen;
             R.push_back(a);
         }
-        std::map<std::string, mapper::reads::protoSeeds> seeds = d->extractSeeds2();
+        std::map<std::string, mapper::reads::protoSeeds> seeds = d->extractSeeds2(std::set<std::string>(), g_seeds_long_mode ? "ont2d" : "");
         g_seeds = SeedsRef();
         for (auto& kv : seeds) {
-            g_seeds.names.push_back(kv.first); g_seeds.complete.push_back(kv.second.isComplete() ? 1 : 0);
+            g_seeds.names.push_back(kv.first); g_seeds.complete.push_back((g_seeds_long_mode ? kv.second.isComplete_unpaired() : kv.second.isComplete()) ? 1 : 0);
             g_seeds.n1.push_back((int32_t)kv.second.read1_alignments.size()); g_seeds.n2.push_back((int32_t)kv.second.read2_alignments.size());
             for (auto& al : kv.second.read1_alignments) { int32_t xi = -1; std::get<2>(al).GetTag("XI", xi); g_seeds.recs.push_back(xi); }
             for (auto& al : kv.second.read2_alignments) { int32_t xi = -1; std::get<2>(al).GetTag("XI", xi); g_seeds.recs.push_back(xi); }

@@ -34,6 +34,9 @@ DATASETS = {
     "genes": (dict(levels=30000, haps=8, genes=8, alleles=300), dict(pairs=250, len=150, clip_frac=0.15, gene_frac=1.0), 100.0, 10.0),
     # long-read mode (HLA-LA.pl --longReads): single reads of 3-6 kb, 3 % indels, half of them clipped by up to 400 bases, half starting in gene blocks
     "long": (dict(levels=40000, haps=6, genes=3, alleles=32, seed=41), dict(pairs=160, len=4000, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=400, gene_frac=0.5, seed=41), 0.0, 1.0),
+    # long-read typing: 17 typed loci, reads concentrated in the gene blocks; the deep one reaches >= 100 observations per allele (strand filter, HLATyper.cpp:1847)
+    "long_typing": (dict(levels=40000, haps=4, genes=17, alleles=24, seed=11), dict(pairs=400, len=3000, single=1, indel_rate=0.02, clip_frac=0.3, clip_max=200, gene_frac=0.8, seed=13), 0.0, 1.0),
+    "long_typing_deep": (dict(levels=30000, haps=4, genes=17, alleles=16, seed=17), dict(pairs=2600, len=2500, single=1, indel_rate=0.02, clip_frac=0.3, clip_max=200, gene_frac=0.95, seed=19), 0.0, 1.0),
     "long8k": (dict(levels=60000, haps=6, genes=2, alleles=200, seed=45), dict(pairs=70, len=8000, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=400, gene_frac=0.5, seed=45), 0.0, 1.0),   # Viterbi scores beyond 4095: found a wrap-around of the packed keys
     "long_small": (dict(levels=12000, haps=4, genes=1, alleles=16, seed=43), dict(pairs=40, len=1500, single=1, indel_rate=0.03, clip_frac=0.5, clip_max=200, gene_frac=0.5, seed=43), 0.0, 1.0),
     "L250": (dict(levels=20000, haps=6, genes=2, alleles=32, seed=21), dict(pairs=400, len=250, clip_frac=0.3, indel_rate=0.002, seed=21), 250.0, 35.0),

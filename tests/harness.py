@@ -565,9 +565,9 @@ class Product:
 
 
     # ---- BAM ingest
-    def bam_read(self, path, threads=0):
+    def bam_read(self, path, threads=0, long_reads=False):
         L = self.lib; h = C.c_void_p()
-        self._chk(L.hlala_bam_read(self.g, path.encode(), C.c_int(threads), C.byref(h)))
+        self._chk((L.hlala_bam_read_long if long_reads else L.hlala_bam_read)(self.g, path.encode(), C.c_int(threads), C.byref(h)))
         try:
             v = SeedBatch(); names = C.POINTER(C.c_char_p)()
             self._chk(L.hlala_bam_batch_view(h, C.byref(v), C.byref(names)))
@@ -584,7 +584,7 @@ class Product:
             b["cigar_off"] = arr("cigar_off", nc + 1); b["cigar"] = arr("cigar", int(b["cigar_off"][-1]))
             cnt = (C.c_int64 * 4)(); m = C.c_double(); sd = C.c_double(); n = C.c_int64()
             self._chk(L.hlala_bam_batch_stats(h, cnt, C.byref(m), C.byref(sd), C.byref(n)))
-            return b, [names[i].decode() for i in range(nr // 2)], dict(records=cnt[0], used=cnt[1], names=cnt[2], incomplete=cnt[3], is_mean=m.value, is_sd=sd.value, is_n=n.value)
+            return b, [names[i].decode() for i in range(nr if long_reads else nr // 2)], dict(records=cnt[0], used=cnt[1], names=cnt[2], incomplete=cnt[3], is_mean=m.value, is_sd=sd.value, is_n=n.value)
         finally:
             L.hlala_bam_batch_free(h)
 
@@ -690,6 +690,15 @@ class ProductTyping:
             arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         self.P._chk(self.lib.hlala_session_typing_extract(sess, self.t, arr, C.c_int64(base), C.byref(blob), C.byref(nb), C.byref(ns)))
         return C.string_at(blob, nb.value), ns.value
+
+    def long_read_blob(self, b, aln, cap):
+        """gene filter + packing of the host arrays Product.long_reads returned -> bytes, number of reads selected"""
+        po = PairOut(); po.max_columns = cap
+        for k in ("pair_mapq", "read_mapq", "read_reverse", "chosen_slot", "pair_ll", "n_cols", "level", "edge", "gchar", "schar", "from_seed", "mapq"):
+            setattr(po, k, aln[k].ctypes.data)
+        sb = make_batch_struct(b); blob = C.POINTER(C.c_uint8)(); nb = C.c_int64(0); ns = C.c_int64(0)
+        self.P._chk(self.lib.hlala_typing_blob_from_long_reads(self.t, C.byref(sb), None, C.byref(po), C.byref(blob), C.byref(nb), C.byref(ns)))
+        return bytes(C.cast(blob, C.POINTER(C.c_uint8 * nb.value)).contents), ns.value
 
     def infer(self, blobs, is_mean, is_sd, out_dir, device=0, rank=0, world=1, allreduce=None, keep_read_ll=True):
         if out_dir:

@@ -85,6 +85,14 @@ def test_ingest_matches_the_references_extractSeeds2():
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not built on this box")
+def test_long_read_ingest_matches_the_references_extractSeeds2():
+    """long-read mode (primary records only, unpaired, supplementary records count as primary, one read per name) against extractSeeds2(.., longReadMode) + isComplete_unpaired"""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "bam_long_ref_compare.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not built on this box")
 def test_insert_size_estimate_matches_the_references_estimateInsertSize():
     """sample selection (incl. the reference's habit of reading on after its thresholds are met), lazily loaded translations, strand rule, underlying-sequence
     distances and histogram statistics against the unmodified processBAM::estimateInsertSize (own process); alignments from the oracle restatement"""
