@@ -16,7 +16,7 @@ import harness as H
 def main():
     d, seeds, out, mode = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
     cap = int(sys.argv[5]) if len(sys.argv) > 5 else 4096
-    b = H.read_arrayfile(seeds)
+    b = dict(np.load(seeds)) if seeds.endswith(".npz") else H.read_arrayfile(seeds)
     R = H.quiet(H.Ref, d)
     ref_dir = os.path.join(out, "ref", "hla"); my_dir = os.path.join(out, mode, "hla"); os.makedirs(my_dir)
     r = H.quiet(R.type_long, d, b, ref_dir)
@@ -35,6 +35,24 @@ def main():
         T.close(); P.close()
     fr = sorted(os.listdir(ref_dir)); fm = sorted(os.listdir(my_dir))
     bad = [f for f in fr if f not in fm or not filecmp.cmp(os.path.join(ref_dir, f), os.path.join(my_dir, f), shallow=False)]
+    near = []
+    if mode == "gpu":
+        # the allele-pair tables print 6 significant digits of sums that differ in the last bits on the device (max-shifted products instead of one exp + log per term):
+        # same rows, values within 1e-5, the order may differ only among rows whose LL agree to that precision (as tests/test_gpu_typing.py does for paired reads)
+        for f in list(bad):
+            if not (f.startswith("R1_PP_") and f in fm):
+                continue
+            a = open(os.path.join(ref_dir, f)).read().split("\n"); g_ = open(os.path.join(my_dir, f)).read().split("\n")
+            if len(a) != len(g_) or a[0] != g_[0]:
+                continue
+            ra = {l.split("\t")[0]: [float(x) for x in l.split("\t")[1:]] for l in a[1:] if l}; rg = {l.split("\t")[0]: [float(x) for x in l.split("\t")[1:]] for l in g_[1:] if l}
+            if ra.keys() != rg.keys():
+                continue
+            ka = [l.split("\t")[0] for l in a[1:] if l]; kg = [l.split("\t")[0] for l in g_[1:] if l]
+            va = np.array([ra[k] for k in ka]); vg = np.array([rg[k] for k in ka])
+            ok = np.allclose(va, vg, rtol=1e-5, atol=0) and all(abs(ra[x][1] - ra[y][1]) <= 1e-5 * abs(ra[x][1]) for x, y in zip(ka, kg) if x != y)
+            if ok:
+                bad.remove(f); near.append(f)
     # how much of the long-read branch the dataset exercises, read off the reference's own pile-up: deepest column, columns where an allele was seen on one strand only >= 100 times
     deepest = 0; one_strand_100 = 0
     for f in fr:
@@ -43,7 +61,7 @@ def main():
                 x = line.rstrip("\n").split("\t")
                 if len(x) >= 3:
                     deepest = max(deepest, int(x[2]))
-    print(json.dumps({"n_used": r["n_used"], "n_selected": int(n_sel), "files_ref": len(fr), "files_mine": len(fm), "differing": bad, "deepest_pileup_column": deepest}))
+    print(json.dumps({"n_used": r["n_used"], "n_selected": int(n_sel), "files_ref": len(fr), "files_mine": len(fm), "differing": bad, "pair_tables_equal_to_1e-5": near, "deepest_pileup_column": deepest}))
 
 
 if __name__ == "__main__":
