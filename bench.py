@@ -307,9 +307,10 @@ def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch
     cov = torch.zeros(n_levels - 1, dtype=torch.int32, device="cuda"); stream = torch.cuda.current_stream()
     n_calls = [0]
 
-    def allreduce(ctx, ptr, count, st):
+    def allreduce(ctx, ptr, count, st):     # entered from a worker thread of the library (one locus at a time, in locus order): a new thread starts on device 0
+        torch.cuda.set_device(local_rank)
         t = H.dev_f64_tensor(ptr, count, local_rank)
-        torch.cuda.current_stream().synchronize(); dist.all_reduce(t); torch.cuda.synchronize(); n_calls[0] += 1
+        torch.cuda.synchronize(); dist.all_reduce(t); torch.cuda.synchronize(); n_calls[0] += 1
         return 0
 
     class _Solo:      # N = 1: the same leg without collectives (the strong-scaling baseline)
@@ -338,7 +339,7 @@ def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch
         dist.all_reduce(cov); torch.cuda.synchronize(); t_align = time.perf_counter() - t0
         blob, nsel = T.extract(sess, base=rank * n_shard)
         blobs = [None] * world; dist.all_gather_object(blobs, blob); t_gather = time.perf_counter() - t0
-        T.infer(blobs, args.is_mean, args.is_sd, os.path.join(out, "hla%d" % it) if out else None, device=local_rank, rank=rank, world=world, allreduce=allreduce if world > 1 else None, keep_read_ll=False)
+        T.infer(blobs, args.is_mean, args.is_sd, os.path.join(out, "hla%d" % it) if out else None, device=local_rank, rank=rank, world=world, allreduce=allreduce if world > 1 else None, keep_read_ll=False, callback_any_thread=True)
         torch.cuda.synchronize(); t_all = time.perf_counter() - t0
         tt = torch.tensor([t_align, t_gather, t_all, float(nsel)], dtype=torch.float64, device="cuda")
         tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); tsum = tt.clone(); dist.all_reduce(tsum)
@@ -542,6 +543,7 @@ def main():
     if rank == 0:
         sys.stderr.write("[bench] e2e: %s pairs/s (%s s per call)\n" % (e2e_value, [round(x, 3) for x in e2e_times]))
 
+    L.hlala_graph_release_workspace(P.g)     # the device workspace hlala_align_pairs keeps in the graph handle (about the size of a session): the legs below bring their own
     strong = None
     if args.strong_pairs > 0 and (dist or args.strong_single):
         strong = strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels)

@@ -278,7 +278,7 @@ struct Pipeline {
             // tail (measured on B200, 1 M pairs: one wave 445 ms, ten waves on three lanes 507 ms). So: one wave if the column scratch of the
             // whole batch fits 40 % of the device memory, else three lanes sharing that much.
             size_t free_b = 0, total_b = 0; CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-            const size_t avail = total_b / 5 * 2, need = (size_t)std::max(b.chain_off[b.n_reads], 1) * (size_t)mc * 6;
+            const size_t avail = std::min(total_b / 5 * 2, free_b / 5 * 3), need = (size_t)std::max(b.chain_off[b.n_reads], 1) * (size_t)mc * 6;     // never more than 60 % of what is free right now
             scratch_budget = need <= avail ? need : avail / 3;
         }
         if (const char* e = allow_env_budget ? getenv("HLALA_WAVE_BYTES") : nullptr) scratch_budget = (size_t)strtoull(e, nullptr, 10);   // test hook: force several waves
@@ -995,8 +995,8 @@ int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs,
         TypingReads all; for (int i = 0; i < n_blobs; i++) all.deserialize_append(blobs[i], (size_t)blob_bytes[i]);
         if (!t->tables_on_device || t->device != device || t->tables_long != all.long_reads) { CUDA_OK(upload_typing_tables(make_typing_tables(all.long_reads))); t->tables_on_device = true; t->device = device; t->tables_long = all.long_reads; }
         GpuTypingDevice dev; dev.device = device; dev.rank = rank; dev.world = world; dev.allreduce = allreduce; dev.ctx = allreduce_ctx;
-        TypingOptions opt; opt.keep_read_ll = keep_read_ll != 0;
-        if (allreduce) opt.threads = 1;   // the caller's all-reduce callback (NCCL, Python) is only ever entered from the calling thread
+        TypingOptions opt; opt.keep_read_ll = (keep_read_ll & HLALA_TYPER_KEEP_READ_LL) != 0;
+        if (allreduce && !(keep_read_ll & HLALA_TYPER_CALLBACK_ANY_THREAD)) opt.threads = 1;   // the caller's all-reduce callback (NCCL, Python) is then only ever entered from the calling thread
         t->calls.clear();
         run_typing(t->T, all, is_mean, is_sd, out_dir ? std::string(out_dir) : std::string(), g_nom_dir, dev, opt, t->calls);
         for (int k = 0; k < 2; k++) { t->ms[k] = dev.ms[k]; t->launches[k] = dev.launches[k]; t->work[k] = dev.work[k]; }

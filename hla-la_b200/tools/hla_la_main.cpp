@@ -113,7 +113,7 @@ static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
         bar.wait();                                              // exchange 2: every rank now sees every shard's blob (one address space)
         if (failed) return;
         RankCtx ctx{comms[(size_t)r], r};
-        if (hlala_typer_infer(typers[(size_t)r], r, blobs.data(), blob_bytes.data(), n_gpus, is_mean, is_sd, r == 0 ? hla_dir.c_str() : nullptr, gdir.c_str(), r, n_gpus, nccl_sum_f64, &ctx, 0)) fail("HLA type inference");
+        if (hlala_typer_infer(typers[(size_t)r], r, blobs.data(), blob_bytes.data(), n_gpus, is_mean, is_sd, r == 0 ? hla_dir.c_str() : nullptr, gdir.c_str(), r, n_gpus, nccl_sum_f64, &ctx, HLALA_TYPER_CALLBACK_ANY_THREAD)) fail("HLA type inference");
         bar.wait();
         hlala_session_free(s); cudaFree(cov); cudaStreamDestroy(st);
     };

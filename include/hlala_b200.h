@@ -201,7 +201,12 @@ int hlala_session_typing_extract(hlala_session_t* s, const hlala_typer_t* t, con
 typedef int (*hlala_allreduce_f64_fn)(void* ctx, uint64_t dev_ptr, int64_t count, void* cuda_stream);
 int hlala_typer_infer(hlala_typer_t* t, int device, const uint8_t* const* blobs, const int64_t* blob_bytes, int n_blobs,
                       double is_mean, double is_sd, const char* out_dir /* NULL: compute only */, const char* g_nom_dir /* holds hla_nom_g.txt */,
-                      int rank, int world, hlala_allreduce_f64_fn allreduce, void* allreduce_ctx, int keep_read_ll);
+                      int rank, int world, hlala_allreduce_f64_fn allreduce, void* allreduce_ctx, int keep_read_ll /* flags, see below */);
+/* Last argument: bit 0 = keep the per-read x cluster values for hlala_typer_result_read_ll; bit 1 (HLALA_TYPER_CALLBACK_ANY_THREAD) = the all-reduce callback may
+ * be entered from a worker thread of the library (always one locus at a time, in locus order on every rank). Without bit 1 a call with a callback runs the loci one
+ * after the other on the calling thread; with it the host work of the loci runs on the thread pool as in a single-rank call. */
+#define HLALA_TYPER_KEEP_READ_LL 1
+#define HLALA_TYPER_CALLBACK_ANY_THREAD 2
 /* Results of the last hlala_typer_infer (arrays caller-allocated). LL / mism: [C*R], index c*R + r (needs keep_read_ll; with
  * world > 1 only this rank's reads are filled). Pair arrays: [C(C+1)/2] in the reference's c1 <= c2 loop order. */
 int hlala_typer_result_dims(const hlala_typer_t* t, int locus, int32_t* n_clusters, int32_t* n_reads);

@@ -700,7 +700,7 @@ class ProductTyping:
         self.P._chk(self.lib.hlala_typing_blob_from_long_reads(self.t, C.byref(sb), None, C.byref(po), C.byref(blob), C.byref(nb), C.byref(ns)))
         return bytes(C.cast(blob, C.POINTER(C.c_uint8 * nb.value)).contents), ns.value
 
-    def infer(self, blobs, is_mean, is_sd, out_dir, device=0, rank=0, world=1, allreduce=None, keep_read_ll=True):
+    def infer(self, blobs, is_mean, is_sd, out_dir, device=0, rank=0, world=1, allreduce=None, keep_read_ll=True, callback_any_thread=False):
         if out_dir:
             os.makedirs(out_dir, exist_ok=True)
         bufs = [C.create_string_buffer(b, len(b)) for b in blobs]
@@ -708,7 +708,7 @@ class ProductTyping:
         sizes = (C.c_int64 * len(bufs))(*[len(b) for b in blobs])
         cb = ALLREDUCE_FN(allreduce) if allreduce else C.cast(None, ALLREDUCE_FN)
         self.P._chk(self.lib.hlala_typer_infer(self.t, C.c_int(device), ptrs, sizes, C.c_int(len(bufs)), C.c_double(is_mean), C.c_double(is_sd),
-                                               out_dir.encode() if out_dir else None, self.prg_dir.encode(), C.c_int(rank), C.c_int(world), cb, None, C.c_int(1 if keep_read_ll else 0)))
+                                               out_dir.encode() if out_dir else None, self.prg_dir.encode(), C.c_int(rank), C.c_int(world), cb, None, C.c_int((1 if keep_read_ll else 0) | (2 if callback_any_thread else 0))))
 
     def locus(self, i, read_ll=True):
         c = C.c_int32(0); r = C.c_int32(0)
