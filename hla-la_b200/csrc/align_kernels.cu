@@ -473,7 +473,7 @@ cudaError_t sort_dp_tasks_by_level(const int32_t* keys_in, int32_t* keys_out, co
 // thread-per-extension tier (extend_lean.h): cfg 0 = LnStd over the task list, cfg 1 = LnBig over what LnStd deferred
 int ln_threads_for_any(int n_sm) { return std::max(ln_threads_for<LnStd>(n_sm), ln_threads_for<LnBig>(n_sm)); }
 size_t ln_thread_rec_bytes() { return sizeof(LnRec) * (size_t)(LN_CELLS + 1); }
-size_t ln_thread_ahead_bytes() { return sizeof(LnAhead) * (size_t)LN_AHEAD; }
+size_t ln_thread_ahead_bytes() { return sizeof(LnAhead) * (size_t)LN_AHEAD + (size_t)LN_RING; }     // ring entries + per-anti-diagonal counts
 cudaError_t launch_extend_lean(const ExtParams& E, int n_sm, int cfg, cudaStream_t stream) {
     if (E.n_pending <= 0) return cudaSuccess;
     return cfg == 0 ? launch_ln<LnStd>(E, n_sm, stream) : launch_ln<LnBig>(E, n_sm, stream);

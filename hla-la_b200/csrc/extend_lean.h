@@ -12,8 +12,9 @@
 //   * finished cells go to HBM as one 16-byte record (key, scores, the three backtrace steps as cell index + step kind + edge rank inside
 //     its level) written once; they are read again only by the backtrace, by revisits and by the previous-score rule on revisits;
 //   * a cell can be touched on two diagonals only if a gap-path jump over >= 2 levels created it AHEAD of its anti-diagonal
-//     (lead = anti-diagonal - diagonal > 0). Only such cells enter a small per-thread (x, y, z) -> cell table in HBM, and a 256-bit mask of
-//     the anti-diagonals that hold ahead cells keeps every other touched cell away from it.
+//     (lead = anti-diagonal - diagonal > 0). Only such cells are remembered, in a per-thread ring in HBM indexed by their anti-diagonal (mod 256, at most
+//     16 per anti-diagonal): what a diagonal has to look up is one contiguous 128-byte line, and a 256-bit mask of the anti-diagonals that hold ahead cells
+//     keeps every other touched cell away from it. A slot of the ring is recycled when the diagonal has passed its anti-diagonal.
 //   * jumps over ONE level are not replayed: their candidate equals the '_' edge's D candidate of the same source (pushed earlier, same
 //     target, same score), so it never is the first maximum and never creates a cell of its own.
 // Anything beyond the small capacities (wide gene blocks, long clips, very long jumps) returns DP_DEFER and is re-run by the next tiers.
@@ -48,8 +49,8 @@ typedef LnCfg<48, 64> LnBig;      // 1600 B per thread: re-runs what LnStd defer
 static_assert(LnBig::LIST <= 64, "list positions are 6-bit fields");
 
 constexpr int LN_CELLS = 2047;          // 11-bit cell index
-constexpr int LN_AHEAD = 2048;          // slots of the ahead table (power of two)
-constexpr int LN_AHEAD_FILL = 1400;
+constexpr int LN_RING = 256, LN_RSLOT = 16;     // ahead cells: a ring over the anti-diagonals (mod 256) of LN_RSLOT entries each
+constexpr int LN_AHEAD = LN_RING * LN_RSLOT;    // entries per thread; the per-diagonal counts (LN_RING bytes) follow them
 constexpr int LN_MAXLEAD = 250;
 constexpr int LN_UMAX = 510, LN_VMAX = 255, LN_ZMAX = 15, LN_EMAX = 31;
 constexpr uint32_t LN_KMASK = 0x1FFFFFu, LN_EMPTY = 0xFFFFFFFFu;
@@ -68,7 +69,7 @@ struct LnLvl { uint32_t ec, pk0, pk1, pk2; };
 #else
 #define LN_PREFETCH(p) ((void)0)
 #endif
-struct LnAhead { uint32_t k, v; };   // ahead table entry: key | cell index << 21 (0 = empty), stored scores
+struct LnAhead { uint32_t k, v; };   // ahead ring entry: key | cell index << 21, stored scores
 
 struct LnGraph {   // what the tier reads of the graph; dp_pack = edge_pack | (from node has a forward jump over >= 2 levels) << 24 | (to node has a backward one) << 25
     int32_t n_levels; const int32_t* level_node_off; const int32_t* level_edge_off; const uint32_t* dp_pack; const LnLvl* lvl4;
@@ -242,7 +243,7 @@ template <class CFG, class SM> struct LnDp {
         if (st.ahead_hi >= diag) {   // ahead cells are pending: start the table look-ups of this diagonal's cells now, they are consumed one by one below
             for (int oi = 0; oi < n_td; oi++) {
                 const uint32_t K = S(CFG::TK + getb(S, oi)) & LN_KMASK; const int s = (int)(K >> 12) + (int)((K >> 4) & 255u); const int g = dir > 0 ? s : (LN_UMAX + LN_VMAX) - s;
-                if (g <= st.ahead_hi && ((S(CFG::AM + ((g >> 5) & 7)) >> (g & 31)) & 1u)) LN_PREFETCH(ahead + ahead_hash(K));
+                if (g <= st.ahead_hi && ((S(CFG::AM + ((g >> 5) & 7)) >> (g & 31)) & 1u)) LN_PREFETCH(ahead + (g & (LN_RING - 1)) * LN_RSLOT);
             }
         }
         // A lower bound of the best D this diagonal will store (a cell stores at least its D candidate): cells more than 15 below it are dropped by the
@@ -266,8 +267,8 @@ template <class CFG, class SM> struct LnDp {
             const int s = ku + kv; const int g = dir > 0 ? s : (LN_UMAX + LN_VMAX) - s; const int lead = g - diag;
             int ci = -1; uint32_t ah = 0, stv = 0;     // ahead slot and stored scores of a revisited cell
             if (g <= st.ahead_hi && ((S(CFG::AM + ((g >> 5) & 7)) >> (g & 31)) & 1u)) {
-                ah = ahead_hash(K);
-                for (;;) { const LnAhead a = ahead[ah]; if (a.k == 0) break; if ((a.k & LN_KMASK) == K) { ci = (int)(a.k >> 21); stv = a.v; break; } ah = (ah + 1) & (LN_AHEAD - 1); }
+                const int rg = g & (LN_RING - 1); const int cnt = (int)ring_count(ahead)[rg];
+                for (int q = 0; q < cnt; q++) { const LnAhead a = ahead[rg * LN_RSLOT + q]; if ((a.k & LN_KMASK) == K) { ci = (int)(a.k >> 21); stv = a.v; ah = (uint32_t)(rg * LN_RSLOT + q); break; } }
             }
             const bool isNew = ci < 0;
             uint32_t b0n = 0, b1n = 0;     // backtrace steps offered by this diagonal
@@ -283,10 +284,11 @@ template <class CFG, class SM> struct LnDp {
                 stv = fD | (fGG << 10) | (fSG << 20);
                 r.k = K; r.v = stv; r.b0 = b0n; r.b1 = b1n; rec[ci] = r;
                 if (lead > 0) {
-                    if (lead > LN_MAXLEAD || st.n_ahead >= LN_AHEAD_FILL) { LN_WHY(lead > LN_MAXLEAD ? 6 : 7); rc = DP_DEFER; continue; }
-                    if (!st.ahead_ready) { LnRec zero; zero.k = zero.v = zero.b0 = zero.b1 = 0; for (int i = 0; i < LN_AHEAD / 2; i++) reinterpret_cast<LnRec*>(ahead)[i] = zero; st.ahead_ready = 1; }
-                    uint32_t h = ahead_hash(K); while (ahead[h].k != 0) h = (h + 1) & (LN_AHEAD - 1);
-                    LnAhead a; a.k = K | ((uint32_t)ci << 21); a.v = stv; ahead[h] = a; st.n_ahead++; S(CFG::AM + ((g >> 5) & 7)) |= 1u << (g & 31); if (g > st.ahead_hi) st.ahead_hi = g;
+                    if (lead > LN_MAXLEAD) { LN_WHY(6); rc = DP_DEFER; continue; }
+                    if (!st.ahead_ready) { LnRec zero; zero.k = zero.v = zero.b0 = zero.b1 = 0; for (int i = 0; i < LN_RING / 16; i++) reinterpret_cast<LnRec*>(ring_count(ahead))[i] = zero; st.ahead_ready = 1; }
+                    const int rg = g & (LN_RING - 1); const int cnt = (int)ring_count(ahead)[rg];
+                    if (cnt >= LN_RSLOT) { LN_WHY(7); rc = DP_DEFER; continue; }
+                    LnAhead a; a.k = K | ((uint32_t)ci << 21); a.v = stv; ahead[rg * LN_RSLOT + cnt] = a; ring_count(ahead)[rg] = (uint8_t)(cnt + 1); st.n_ahead++; S(CFG::AM + ((g >> 5) & 7)) |= 1u << (g & 31); if (g > st.ahead_hi) st.ahead_hi = g;
                 }
             } else {     // revisit: the scores come with the table entry; the record is read only if a matrix improves (or for the tie rule below)
                 uint32_t sD = stv & 1023u, sGG = (stv >> 10) & 1023u, sSG = stv >> 20;
@@ -337,7 +339,9 @@ template <class CFG, class SM> struct LnDp {
             for (int i = 0; i < n_mt; i++) { const uint32_t a = S(m2o + 2 * i), b = S(m2o + 2 * i + 1); if (mx - (b & 1023u) <= 15u) { S(m2o + 2 * w) = a; S(m2o + 2 * w + 1) = b; w++; } }
             st.n_m2 = st.n_m1; st.n_m1 = w; st.rot ^= 1;
         }
-        if (st.ahead_hi >= diag) S(CFG::AM + ((diag >> 5) & 7)) &= ~(1u << (diag & 31));     // cells of this anti-diagonal can no longer be touched
+        if (st.ahead_hi >= diag && ((S(CFG::AM + ((diag >> 5) & 7)) >> (diag & 31)) & 1u)) {     // cells of this anti-diagonal can no longer be touched: its ring slot is free again
+            S(CFG::AM + ((diag >> 5) & 7)) &= ~(1u << (diag & 31)); ring_count(ahead)[diag & (LN_RING - 1)] = 0;
+        }
         // Exact early exit by bound. No stored cell can be touched again (no ahead cell is pending), so the cells and backtrace steps written so
         // far are final; a cell still to come descends from a live entry and scores at most that entry's D + 2 per read base left (every
         // other move adds <= 0, and GG, SG <= D). If that stays strictly below the best sequence-complete D, no later cell can take over or tie
@@ -391,7 +395,7 @@ template <class CFG, class SM> struct LnDp {
         return 0;
     }
 
-    __host__ __device__ static uint32_t ahead_hash(uint32_t K) { uint32_t h = K * 0x9E3779B1u; return (h >> 19) & (LN_AHEAD - 1); }
+    __host__ __device__ static uint8_t* ring_count(LnAhead* ahead) { return reinterpret_cast<uint8_t*>(ahead + LN_AHEAD); }
     __host__ __device__ static int getb(SM& S, int i) { return (int)S.b(CFG::PERM + (i >> 2), i & 3); }
     __host__ __device__ static void setb(SM& S, int i, int v) { S.b(CFG::PERM + (i >> 2), i & 3) = (uint8_t)v; }
     __host__ __device__ static void clear_touch(SM& S) { for (int i = 0; i < CFG::TD; i++) S(CFG::TK + i) = LN_EMPTY; }

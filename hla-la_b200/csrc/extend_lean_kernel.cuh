@@ -30,7 +30,7 @@ template <class CFG> __global__ void __launch_bounds__(LN_BLOCK) k_extend_lean(E
     LnSmem S; S.base = ln_smem + (size_t)warp * CFG::WORDS * 32 + lane;
     const int gt = blockIdx.x * LN_BLOCK + threadIdx.x;
     LnRec* rec = E.ln_rec + (size_t)gt * (LN_CELLS + 1);
-    LnAhead* ahead = reinterpret_cast<LnAhead*>(E.ln_ahead) + (size_t)gt * LN_AHEAD;
+    LnAhead* ahead = reinterpret_cast<LnAhead*>(reinterpret_cast<unsigned char*>(E.ln_ahead) + (size_t)gt * (sizeof(LnAhead) * (size_t)LN_AHEAD + (size_t)LN_RING));
     LnGraph G; G.n_levels = DG.n_levels; G.level_node_off = DG.level_node_off; G.level_edge_off = DG.level_edge_off; G.dp_pack = DG.dp_pack; G.lvl4 = reinterpret_cast<const LnLvl*>(DG.lvl4);
     G.path_off = DG.path_off; G.path_edges = DG.path_edges; G.path_from = DG.path_from; G.path_to = DG.path_to;
     G.jump_fwd_off = DG.jump_fwd_off; G.jump_fwd_path = DG.jump_fwd_path; G.jump_bwd_off = DG.jump_bwd_off; G.jump_bwd_path = DG.jump_bwd_path;

@@ -32,7 +32,7 @@ void* dp_host_open(const char* dir) {
         l.path_off = g.path_off.data(); l.path_edges = g.path_edges.data(); l.path_from = g.path_from.data(); l.path_to = g.path_to.data();
         l.jump_fwd_off = g.jump_fwd_off.data(); l.jump_fwd_path = g.jump_fwd_path.data(); l.jump_bwd_off = g.jump_bwd_off.data(); l.jump_bwd_path = g.jump_bwd_path.data();
         h->lvl4 = make_lvl4(g, h->dp_pack); l.lvl4 = (const LnLvl*)h->lvl4.data();
-        h->rec.resize(LN_CELLS + 1); h->ahead.assign(LN_AHEAD, LnAhead{0xDEADBEEFu, 0xDEADBEEFu});   // the tier clears its table itself
+        h->rec.resize(LN_CELLS + 1); h->ahead.assign(LN_AHEAD + LN_RING / 8, LnAhead{0xDEADBEEFu, 0xDEADBEEFu});   // the tier clears its table itself
         return h.release();
     } catch (...) { return nullptr; }
 }
