@@ -409,17 +409,45 @@ __device__ int viterbi_backtrace(const ChainParams& P, ColBuf c, int n, const Wa
     for (int z = lane; z < wl; z += 32) { uint32_t k = cur[z]; if (k) { uint32_t v = ((k >> KS) << 12) | (uint32_t)(4095 - min(z, 4095)); best = max(best, v); } }
     for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
     if (best == 0) return HLALA_E_INVARIANT_DEV;                    // the reference asserts a non-empty column map
-    if (lane == 0) {
-        int z = 4095 - (int)(best & 4095u); int l = l_last;
-        for (int col = n - 1; col >= 0; col--) {
-            if (c.lvl[col] == -1) { edge_out[col] = -1; c.g[col] = '_'; continue; }
-            int rank, fz;
-            if (BT16) { uint16_t ent = bt16[S.coloff[col] + z]; rank = ent & 255; fz = ent >> 8; }
-            else { uint32_t ent = S.bt[S.coloff[col] + z]; rank = (int)(ent & KEY_RANK_MASK); fz = (int)(ent >> 20); }
-            int erel = S.weoff[l - l_first] + rank;
-            uint32_t pk = staged ? win[erel] : G.edge_pack[e_base + erel];
-            edge_out[col] = e_base + erel; c.g[col] = (uint8_t)(pk >> 16);
-            z = fz; l--;
+    {   // ---- backtrace (processBAM.cpp:2869-2932), 32 columns at a time from the right. The entry a column reads is addressed by the node it arrives at in the NEXT
+        // level: wherever that level has one node the address is known at once, so those columns (80 % on a PRG) are independent; the others wait for the column to
+        // their right, a few rounds per block. Blocks with long runs of several-node levels (gene blocks) are walked by one lane as before.
+        const unsigned full = 0xffffffffu;
+        int carry = 4095 - (int)(best & 4095u);       // node the path arrives at in the level after the rightmost unresolved column
+        for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+            const int j = base + lane; const bool in = j < n;
+            const int lv = in ? c.lvl[j] : -1; const bool isl = in && lv != -1;
+            if (in && !isl) { edge_out[j] = -1; c.g[j] = '_'; }
+            const int li = isl ? lv - l_first : 0;
+            const bool known = isl && S.wwid[li + 1] == 1;
+            const unsigned lm = __ballot_sync(full, isl);
+            if (lm == 0u) continue;
+            const int n_unknown = __popc(lm & ~__ballot_sync(full, known));
+            auto take = [&](int col, int lcol, int z, int& fz_out) {
+                int rank, fz;
+                if (BT16) { const uint16_t ent = bt16[S.coloff[col] + z]; rank = ent & 255; fz = ent >> 8; }
+                else { const uint32_t ent = S.bt[S.coloff[col] + z]; rank = (int)(ent & KEY_RANK_MASK); fz = (int)(ent >> 20); }
+                const int erel = S.weoff[lcol] + rank;
+                const uint32_t pk = staged ? win[erel] : G.edge_pack[e_base + erel];
+                edge_out[col] = e_base + erel; c.g[col] = (uint8_t)(pk >> 16);
+                fz_out = fz;
+            };
+            if (n_unknown > 6) {      // one lane, right to left
+                if (lane == 0) { int z = carry; for (int col = min(base + 31, n - 1); col >= base; col--) { if (c.lvl[col] == -1) continue; int fz; take(col, c.lvl[col] - l_first, z, fz); z = fz; } carry = z; }
+                carry = __shfl_sync(full, carry, 0);
+                __syncwarp();
+                continue;
+            }
+            const unsigned higher = lane == 31 ? 0u : (lm & ~((2u << lane) - 1u));
+            const int nb = higher ? __ffs(higher) - 1 : -1;           // the level column to the right inside this block; -1: the carry
+            int z = known ? 0 : -1, fz = 0; bool done = !isl;
+            for (;;) {
+                if (isl && !done && z >= 0) { take(j, li, z, fz); done = true; }
+                if (__all_sync(full, done)) break;
+                const int nfz = __shfl_sync(full, fz, nb >= 0 ? nb : 0); const int ndone = __shfl_sync(full, (int)done, nb >= 0 ? nb : 0);
+                if (isl && !done && z < 0) { if (nb < 0) z = carry; else if (ndone) z = nfz; }
+            }
+            carry = __shfl_sync(full, fz, __ffs(lm) - 1);              // the leftmost level column of this block hands its node on
         }
     }
     __syncwarp();
