@@ -727,8 +727,12 @@ int hlala_align_long_reads(hlala_graph_t* g, const hlala_seed_batch_t* batch, hl
         for (int64_t r = 0; r < n; r++) { ro[(size_t)(2 * r)] = batch->read_off[r]; ro[(size_t)(2 * r + 1)] = batch->read_off[r + 1]; co[(size_t)(2 * r)] = batch->chain_off[r]; co[(size_t)(2 * r + 1)] = batch->chain_off[r + 1]; }
         ro[(size_t)(2 * n)] = batch->read_off[n]; co[(size_t)(2 * n)] = batch->chain_off[n];
         hlala_seed_batch_t b2 = *batch; b2.n_reads = 2 * n; b2.read_off = ro.data(); b2.chain_off = co.data();
-        Pipeline pl; pl.long_mode = true; pl.prepare(g, b2, out->max_columns, st);
-        DevBuf bpl; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
+        // the workspace kept in the graph handle across calls (device buffers are grow-only), as hlala_align_pairs does
+        std::lock_guard<std::mutex> lock(g->ws_mu);
+        if (!g->ws) g->ws = std::shared_ptr<void>(std::make_shared<Pipeline>());
+        Pipeline& pl = *static_cast<Pipeline*>(g->ws.get());
+        pl.reset_config(); pl.long_mode = true; pl.prepare(g, b2, out->max_columns, st);
+        DevBuf& bpl = pl.bpl_ws; size_t nl = (size_t)std::max(g->h.n_levels - 1, 1);
         if (bases_per_level) { bpl.alloc(nl * 4); CUDA_OK(cudaMemsetAsync(bpl.p, 0, nl * 4, st)); }
         const bool want_cols = out->level || out->edge || out->gchar || out->schar || out->from_seed || out->mapq || out->n_cols;
         pl.run(100.0, 10.0, bases_per_level ? bpl.as<int32_t>() : nullptr, want_cols, st);       // the insert-size model is not used for single reads
