@@ -128,12 +128,16 @@ struct PreparedBatch {
 struct DeviceBatch {
     DevBuf read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar, chain_order, read_primary, slot_read;
     DevBatch view{};
-    void upload(const hlala_seed_batch_t& b, const PreparedBatch& pb, cudaStream_t st) {
-        int64_t nb = b.read_off[b.n_reads]; int32_t nc = pb.n_chains; int32_t ncg = b.cigar_off[nc];
+    // the caller's arrays first (asynchronous from pinned memory: they travel while the host sorts the chains), then what the host prepared
+    void upload_raw(const hlala_seed_batch_t& b, cudaStream_t st) {
+        int64_t nb = b.read_off[b.n_reads]; int32_t nc = b.chain_off[b.n_reads]; int32_t ncg = b.cigar_off[nc];
         read_off.upload(b.read_off, (size_t)b.n_reads + 1, st); bases.upload(b.bases, (size_t)nb, st); quals.upload(b.quals, (size_t)nb, st);
         chain_off.upload(b.chain_off, (size_t)b.n_reads + 1, st);
         chain_contig.upload(b.chain_contig, (size_t)nc, st); chain_pos.upload(b.chain_pos, (size_t)nc, st); chain_flag.upload(b.chain_flag, (size_t)nc, st); chain_as.upload(b.chain_as, (size_t)nc, st);
         cigar_off.upload(b.cigar_off, (size_t)nc + 1, st); cigar.upload(b.cigar, (size_t)ncg, st);
+    }
+    void upload(const hlala_seed_batch_t& b, const PreparedBatch& pb, cudaStream_t st) {
+        int32_t nc = pb.n_chains;
         chain_order.upload(pb.chain_order, st); read_primary.upload(pb.read_primary, st); slot_read.upload(pb.slot_read, st);
         view.n_reads = b.n_reads; view.n_chains = nc;
         view.read_off = read_off.as<int64_t>(); view.bases = bases.as<uint8_t>(); view.quals = quals.as<uint8_t>();
@@ -282,7 +286,7 @@ struct Pipeline {
             scratch_budget = need <= avail ? need : avail / 3;
         }
         if (const char* e = allow_env_budget ? getenv("HLALA_WAVE_BYTES") : nullptr) scratch_budget = (size_t)strtoull(e, nullptr, 10);   // test hook: force several waves
-        pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1); host_read_off.assign(b.read_off, b.read_off + b.n_reads + 1);
+        db.upload_raw(b, st); pb.build(b); db.upload(b, pb, st); host_chain_off.assign(b.chain_off, b.chain_off + b.n_reads + 1); host_read_off.assign(b.read_off, b.read_off + b.n_reads + 1);
         // waves: consecutive pairs whose chains fit the column-scratch budget
         wave_pair.assign(1, 0); int32_t max_wave_chains = 0;
         { const int64_t np = b.n_reads / 2; const int64_t cap = std::max<int64_t>(1024, (int64_t)(scratch_budget / ((size_t)mc * 6)));
