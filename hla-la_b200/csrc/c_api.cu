@@ -722,8 +722,8 @@ int hlala_align_pairs(hlala_graph_t* g, const hlala_seed_batch_t* batch, double 
 int hlala_align_long_reads(hlala_graph_t* g, const hlala_seed_batch_t* batch, hlala_pair_out_t* out, int32_t* bases_per_level) {
     if (!g || !out || !batch) return fail(HLALA_E_ARG, "hlala_align_long_reads: null argument");
     if (batch->n_reads < 0 || !batch->read_off || !batch->chain_off || !batch->cigar_off) return fail(HLALA_E_ARG, "seed batch: null offset arrays");
-    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
     if (out->max_columns < 32 || out->max_columns > 16384) return fail(HLALA_E_ARG, "max_columns must be in [32, 16384] in long-read mode");
+    if (!g->on_gpu) return fail(HLALA_E_CUDA, "graph is not on a GPU: call hlala_graph_to_gpu first (there is no CPU fallback)");
     return guarded([&]() {
         CUDA_OK(cudaSetDevice(g->device)); cudaStream_t st = 0;
         // internally a read is a pair whose second mate is empty (no bases, no chains): the wave / slot / output indexing of the paired path is kept

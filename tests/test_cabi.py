@@ -41,6 +41,10 @@ def test_compute_without_gpu_fails_loudly(dataset):
         P.to_gpu(0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         P.chains(b, 512)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.pairs(b, mu, sd, 512)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.long_reads(b, 512)          # long-read entry: the same rule
     P.close()
 
 
@@ -50,4 +54,7 @@ def test_bad_arguments_are_rejected(dataset):
     sb = H.make_batch_struct(b); sb.n_reads = 3
     co = H.ChainOut(); co.max_columns = 512
     assert P.lib.hlala_align_chains(P.g, C.byref(sb), C.byref(co)) == -1
+    po = H.PairOut(); po.max_columns = 20000          # long reads: max_columns beyond 16384 is refused before anything runs
+    assert P.lib.hlala_align_long_reads(P.g, C.byref(H.make_batch_struct(b)), C.byref(po), None) == -1
+    assert P.lib.hlala_evaluate_types(None, None, None, None, 0, None, 0, None, 0) == -1
     P.close()
