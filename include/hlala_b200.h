@@ -18,6 +18,14 @@
  *                            assignMappingQualities :4062] + bases_per_level counting (:2411-2426)
  *   hlala_align_chains    the per-chain half of the above (alignment2Chain + extendSeedChain + scoreOneAlignment),
  *                         exposed for parity tests of the kernels (reference seams B2/B3 of SURVEY.md §8b)
+ *   hlala_align_long_reads  processBAM::alignReadsUnpaired_postSeedExtraction_andStoreInto  mapper/processBAM.cpp:2224
+ *                         = per read processBAM::alignOneLongRead (:3618) + assignMappingQualities_unpaired (:3900)
+ *   hlala_bam_read / hlala_bam_read_long / hlala_bam_insert_size
+ *                         processBAM::getReadIDs / extractSeeds2 (:169, :703), protoSeeds::takeAlignment, processBAM::estimateInsertSize (:1071)
+ *   hlala_typer_* / hlala_session_typing_extract / hlala_typing_blob_from_long_reads
+ *                         the gene filter (:2427-2446, :2297-2331) + hla::HLATyper::HLATypeInference  hla/HLATyper.cpp:933-2810
+ *   hlala_evaluate_types  hla::HLATyper::read_inferred_types / read_true_types / evaluate_HLA_types  hla/HLATyper.cpp:407-688
+ *   hlala_kmer_index_build / hlala_seed_kmers   GraphAndEdgeIndex::Index / findChains  Graph/GraphAndEdgeIndex.cpp:428, 39
  *
  * Conventions: plain pointers and sizes, no C++/torch types. All functions return 0 on success and a negative
  * HLALA_E_* code on failure; hlala_last_error() returns a message for the calling thread. Nothing throws across
