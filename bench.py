@@ -582,7 +582,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_extend_lean", "achieved": dp_ach, "peak": peak, "unit": "GB/s", "frac": (dp_ach / peak) if dp_ach else None, "traffic": traffic,
                 "traffic_source": "profiles/r02_ncu_k_extend_lean.txt (ncu --set full of the same launch: one launch over the whole 1 M-pair batch of the default workload)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dp_bytes_total / max(kl[1], 1), "launch_ms_avg": kms[1] / max(kl[1], 1),
-                "note": "integer DP over a sparse cell set, one thread per extension: bounded by SIMT divergence, dependent shared-memory accesses and issue slots (ncu: 7 of 32 lanes active, 22 % issue-active), not by HBM bandwidth; the fraction is reported as measured",
+                "note": "integer DP over a sparse cell set, one thread per extension: bounded by SIMT divergence, dependent shared-memory accesses and issue slots (ncu, profiles/r02_ncu_k_extend_lean.txt: 8.8 of 32 lanes active, issue slots 25 % busy, 8 warps per SM), not by HBM bandwidth; the fraction is reported as measured",
                 "chain_kernel": {"kernel": "k_chain_seed", "achieved_counting_all_chains": chain_ach, "frac_counting_all_chains": (chain_ach / peak) if chain_ach else None, "algorithmic_bytes_per_step_all_chains": chain_bytes,
                                  "achieved": (aligned["chain_kernel_bytes_per_step"] * args.steps / (kms[0] / 1000.0) / 1e9) if aligned and "error" not in aligned and kms[0] > 0 else None,
                                  "frac": (aligned["chain_kernel_bytes_per_step"] * args.steps / (kms[0] / 1000.0) / 1e9 / peak) if aligned and "error" not in aligned and kms[0] > 0 else None,
