@@ -576,12 +576,19 @@ void run_typing(TypingTables& T, const TypingReads& in, double is_mean, double i
         auto members = [&](uint32_t c) -> const std::string& { return member_str[c]; };
         std::map<int, double> marginal;
         { std::ofstream ap(target("R1_PP_" + L.name + "_pairs.txt")); ap << "ClusterID\tP\tLL\tMismatches_avg\n";
-          std::vector<double> marg((size_t)C, 0.0); std::string text; text.reserve((size_t)1 << 22);
-          for (size_t k = 0; k < NPAIR; k++) { const size_t i = order[k];
-              text += members(ids[i].first); text += '/'; text += members(ids[i].second); text += '\t'; put_num(text, Pn[i]); text += '\t'; put_num(text, LLs[i]); text += '\t'; put_num(text, Mavg[i]); text += '\n';
-              if (text.size() > ((size_t)1 << 22) - 4096) { ap.write(text.data(), (std::streamsize)text.size()); text.clear(); }
-              marg[ids[i].first] += Pn[i]; if (ids[i].second != ids[i].first) marg[ids[i].second] += Pn[i]; }
-          ap.write(text.data(), (std::streamsize)text.size());
+          std::vector<double> marg((size_t)C, 0.0);
+          // the lines are formatted in slices of the ranked list (helper threads when the table is large and cores are free: 500 k lines per locus at 1000 alleles),
+          // written in order; the marginals are summed in rank order by this thread (the order of the additions is part of the result)
+          const unsigned hw = std::max(1u, std::thread::hardware_concurrency()); unsigned helpers = NPAIR >= 100000 ? std::min(6u, std::max(1u, hw / (unsigned)std::max<size_t>(NL, 1))) : 1u;
+          if (const char* e = getenv("HLALA_HOST_THREADS")) helpers = std::min<unsigned>(helpers, std::max(1u, (unsigned)atoi(e) / (unsigned)std::max<size_t>(NL, 1)));
+          std::vector<std::string> part(helpers);
+          auto format = [&](unsigned h) { std::string& text = part[h]; const size_t k0 = NPAIR * h / helpers, k1 = NPAIR * (h + 1) / helpers; text.reserve((k1 - k0) * 72);
+              for (size_t k = k0; k < k1; k++) { const size_t i = order[k];
+                  text += members(ids[i].first); text += '/'; text += members(ids[i].second); text += '\t'; put_num(text, Pn[i]); text += '\t'; put_num(text, LLs[i]); text += '\t'; put_num(text, Mavg[i]); text += '\n'; } };
+          { std::vector<std::thread> th; for (unsigned h = 1; h < helpers; h++) th.emplace_back(format, h);
+            for (size_t k = 0; k < NPAIR; k++) { const size_t i = order[k]; marg[ids[i].first] += Pn[i]; if (ids[i].second != ids[i].first) marg[ids[i].second] += Pn[i]; }
+            format(0); for (auto& t : th) t.join(); }
+          for (const std::string& text : part) ap.write(text.data(), (std::streamsize)text.size());
           for (int32_t c = 0; c < C; c++) marginal[c] = marg[(size_t)c]; }      // every cluster is part of a pair: the keys the reference's map holds
         auto first_max = [](const std::map<int, double>& m) { double mx = 0; int at = 0; bool first = true; for (auto& kv : m) if (first || kv.second > mx) { mx = kv.second; at = kv.first; first = false; } return std::make_pair(mx, at); };   // Utilities::findIntMapMaxP_nonCritical
         const std::pair<double, int> b1 = first_max(marginal);
