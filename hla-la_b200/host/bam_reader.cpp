@@ -151,20 +151,36 @@ void read_bam_seeds(const std::string& path, const std::vector<std::string>& con
     struct NameRef { const char* p; uint32_t n; };
     struct NameHash { size_t operator()(const NameRef& x) const { uint64_t h = 1469598103934665603ull; for (uint32_t i = 0; i < x.n; i++) h = (h ^ (uint8_t)x.p[i]) * 1099511628211ull; return (size_t)h; } };
     struct NameEq { bool operator()(const NameRef& a, const NameRef& b) const { return a.n == b.n && memcmp(a.p, b.p, a.n) == 0; } };
-    std::unordered_map<NameRef, int32_t, NameHash, NameEq> gid; gid.reserve(NR / 4 + 16);
-    std::vector<NameRef> gname; std::vector<int32_t> rec_gid(NR, -1); std::vector<int32_t> gcount;
-    for (size_t i = 0; i < NR; i++) if (keep[i]) {
+    // open-addressing table of group ids (linear probing, load <= 0.5); the name hashes are computed on the thread pool first, the insertion itself runs in
+    // file order so that group ids follow the first appearance of a name
+    std::vector<uint64_t> name_hash(NR, 0);
+    { std::atomic<size_t> nb(0); auto hash_all = [&]() { const size_t blk = 65536; NameHash H;
+          for (;;) { const size_t i0 = nb.fetch_add(1) * blk; if (i0 >= NR) break; const size_t i1 = std::min(NR, i0 + blk);
+              for (size_t i = i0; i < i1; i++) if (keep[i]) { const uint8_t* r = &d[rec_at[i]]; const uint32_t ln = r[8]; name_hash[i] = (uint64_t)H(NameRef{(const char*)r + 32, ln ? ln - 1 : 0}); } } };
+      std::vector<std::thread> th; const int nt = std::max(1, std::min(threads, 16)); for (int t = 1; t < nt; t++) th.emplace_back(hash_all); hash_all(); for (auto& t : th) t.join(); }
+    size_t n_keep = 0; for (size_t i = 0; i < NR; i++) n_keep += keep[i] ? 1 : 0;
+    size_t tcap = 64; while (tcap < 2 * n_keep + 16) tcap <<= 1;
+    std::vector<int32_t> table(tcap, -1);
+    std::vector<NameRef> gname; std::vector<int32_t> rec_gid(NR, -1); std::vector<int32_t> gcount; gname.reserve(n_keep / 8 + 16); gcount.reserve(n_keep / 8 + 16);
+    { NameEq EQ;
+      for (size_t i = 0; i < NR; i++) if (keep[i]) {
         const uint8_t* r = &d[rec_at[i]]; const uint32_t ln = r[8]; NameRef nm{(const char*)r + 32, ln ? ln - 1 : 0};
-        auto it = gid.find(nm); int32_t g;
-        if (it == gid.end()) { g = (int32_t)gname.size(); gid.emplace(nm, g); gname.push_back(nm); gcount.push_back(0); } else g = it->second;
+        size_t h = (size_t)(name_hash[i] ^ (name_hash[i] >> 29)) & (tcap - 1); int32_t g = -1;
+        for (;;) { const int32_t v = table[h]; if (v < 0) break; if (EQ(gname[(size_t)v], nm)) { g = v; break; } h = (h + 1) & (tcap - 1); }
+        if (g < 0) { g = (int32_t)gname.size(); table[h] = g; gname.push_back(nm); gcount.push_back(0); }
         rec_gid[i] = g; gcount[(size_t)g]++; out.records_used++;
-    }
+      } }
     // ---- the insert-size sample (see bam_reader.h): replay of extractSeeds(4000) over the kept records
     if (!long_reads) {     // the insert-size sample (paired reads only)
         std::vector<uint32_t> scan; scan.reserve((size_t)out.records_used); for (size_t i = 0; i < NR; i++) if (keep[i]) scan.push_back((uint32_t)i);
         std::vector<int32_t> contig_rank(contig_names.size());      // byte order of the contig names = iteration order of the reference's interval map
         { std::vector<int32_t> o(contig_names.size()); for (size_t i = 0; i < o.size(); i++) o[i] = (int32_t)i; std::sort(o.begin(), o.end(), [&](int32_t x, int32_t y) { return contig_names[(size_t)x] < contig_names[(size_t)y]; }); for (size_t k = 0; k < o.size(); k++) contig_rank[(size_t)o[k]] = (int32_t)k; }
-        std::stable_sort(scan.begin(), scan.end(), [&](uint32_t x, uint32_t y) { return contig_rank[(size_t)recs[x].ref] < contig_rank[(size_t)recs[y].ref]; });   // stable: file order inside a contig
+        {   // stable counting sort by contig rank: file order inside a contig
+            std::vector<size_t> at(contig_names.size() + 1, 0); for (uint32_t i : scan) at[(size_t)contig_rank[(size_t)recs[i].ref] + 1]++;
+            for (size_t k = 1; k < at.size(); k++) at[k] += at[k - 1];
+            std::vector<uint32_t> sorted(scan.size()); for (uint32_t i : scan) sorted[at[(size_t)contig_rank[(size_t)recs[i].ref]]++] = i;
+            scan.swap(sorted);
+        }
         struct St { int32_t first1 = -1, first2 = -1; bool prim1 = false, prim2 = false; };   // first primary record of either mate, in scan order
         std::vector<St> state(gname.size()); std::vector<uint8_t> seen(gname.size(), 0); std::vector<uint8_t> loaded(contig_names.size(), 0);
         // The reference leaves the record loop of the CURRENT interval when both thresholds are met (processBAM.cpp:672-676) but then moves on to the next
