@@ -61,9 +61,15 @@ int nccl_sum_f64(void* ctx, uint64_t dev_ptr, int64_t count, void* stream) {    
 }
 
 static int evaluate_calls(std::map<std::string, std::string>& a, const std::string& out_dir);
+// An alignment has one column per read base plus one per graph level it spans without a base (deletions, gap stretches of hundreds of levels): 640 columns hold
+// 2 x 150 bp reads with room to spare; longer reads get 2.5 x their length (an alignment beyond max_columns is a reported capacity error, never a truncation).
+static int default_max_columns(const hlala_seed_batch_t& b) {
+    int64_t longest = 0; for (int64_t r = 0; r < b.n_reads; r++) longest = std::max<int64_t>(longest, b.read_off[r + 1] - b.read_off[r]);
+    return (int)std::min<int64_t>(2040, std::max<int64_t>(640, longest * 5 / 2 + 64));
+}
 static int run_long_reads(std::map<std::string, std::string>& a);
 static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
-    const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
+    const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
     int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus) { fprintf(stderr, "hlala-b200: --gpus %d but %d CUDA devices are visible\n", n_gpus, ndev); return 1; }
     { const unsigned hc = std::max(1u, std::thread::hardware_concurrency()); setenv("HLALA_HOST_THREADS", std::to_string(std::max(1u, hc / (unsigned)n_gpus)).c_str(), 0); }
     std::vector<int> devs((size_t)n_gpus); for (int i = 0; i < n_gpus; i++) devs[(size_t)i] = i;
@@ -80,6 +86,7 @@ static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     phase("BAM read, records selected and grouped");
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
+    if (!a.count("maxColumns") && batch.n_reads > 0) maxcol = default_max_columns(batch);
     if (a.count("insertSizeMean") && a.count("insertSizeSD")) { is_mean = atof(a["insertSizeMean"].c_str()); is_sd = atof(a["insertSizeSD"].c_str()); }
     else { int64_t used = 0, skipped = 0; if (hlala_bam_insert_size(graphs[0], bam, maxcol, &is_mean, &is_sd, &used, &skipped)) return die("estimating the insert size"); }
     const int64_t n_pairs = batch.n_reads / 2;
@@ -250,7 +257,7 @@ int main(int argc, char** argv) {
     if (long_reads) return run_long_reads(a);
     if (a.count("gpus") && atoi(a["gpus"].c_str()) > 1) return run_multi_gpu(a, atoi(a["gpus"].c_str()));
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"];
-    const int device = a.count("device") ? atoi(a["device"].c_str()) : 0; const int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
+    const int device = a.count("device") ? atoi(a["device"].c_str()) : 0; int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
     g_t0 = std::chrono::steady_clock::now();
     hlala_graph_t* g = nullptr;
     if (hlala_graph_load(prg.c_str(), &g)) return die("loading the PRG");
@@ -262,6 +269,7 @@ int main(int argc, char** argv) {
     phase("BAM read, records selected and grouped");
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
+    if (!a.count("maxColumns") && batch.n_reads > 0) maxcol = default_max_columns(batch);
     if (a.count("insertSizeMean") && a.count("insertSizeSD")) { is_mean = atof(a["insertSizeMean"].c_str()); is_sd = atof(a["insertSizeSD"].c_str()); }
     else {   // what HLA-LA.cpp:788 does: processBAM::estimateInsertSize on the first ~4000 read names
         int64_t used = 0, skipped = 0;
