@@ -366,7 +366,7 @@ def main():
     ap.add_argument("--alleles", type=int, default=1000)
     ap.add_argument("--is-mean", type=float, default=100.0)
     ap.add_argument("--is-sd", type=float, default=10.0)
-    ap.add_argument("--max-columns", type=int, default=640)
+    ap.add_argument("--max-columns", type=int, default=0, help="columns per alignment; 0 = 640 up to 150 bp reads (the headline), 4 x read length + 64 beyond (rare alignments span gap stretches of hundreds of levels)")
     ap.add_argument("--cpu-pairs", type=int, default=6000)
     ap.add_argument("--cpu-levels", type=int, default=294118, help="levels of the reference arm's PRG slice (default: levels / genes = one gene block, the bench PRG's density)")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -377,6 +377,8 @@ def main():
     ap.add_argument("--strong-single", type=int, default=0, help="run the strong-scaling leg at N = 1 too (its baseline; off by default to keep the default run short)")
     ap.add_argument("--strong-pairs", type=int, default=4000000, help="N > 1: total pairs of the strong-scaling leg (BASELINE.json configs[2]: ~4M pairs sharded over the GPUs, typing with one NCCL all-reduce per locus); 0 = skip")
     args = ap.parse_args()
+    if args.max_columns <= 0:
+        args.max_columns = 640 if args.read_len <= 150 else min(2040, 4 * args.read_len + 64)
     rank, local_rank, world = rank_info()
     n_gpus = max(world, 1)
 

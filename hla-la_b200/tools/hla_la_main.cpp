@@ -62,10 +62,11 @@ int nccl_sum_f64(void* ctx, uint64_t dev_ptr, int64_t count, void* stream) {    
 
 static int evaluate_calls(std::map<std::string, std::string>& a, const std::string& out_dir);
 // An alignment has one column per read base plus one per graph level it spans without a base (deletions, gap stretches of hundreds of levels): 640 columns hold
-// 2 x 150 bp reads with room to spare; longer reads get 2.5 x their length (an alignment beyond max_columns is a reported capacity error, never a truncation).
+// 2 x 150 bp reads with room to spare (1 M pairs on the bench PRG: none beyond); at 2 x 250 bp a handful of 1 M pairs passed 689, so longer reads get 4 x their
+// length (an alignment beyond max_columns is a reported capacity error, never a truncation).
 static int default_max_columns(const hlala_seed_batch_t& b) {
     int64_t longest = 0; for (int64_t r = 0; r < b.n_reads; r++) longest = std::max<int64_t>(longest, b.read_off[r + 1] - b.read_off[r]);
-    return (int)std::min<int64_t>(2040, std::max<int64_t>(640, longest * 5 / 2 + 64));
+    return longest <= 160 ? 640 : (int)std::min<int64_t>(2040, 4 * longest + 64);
 }
 static int run_long_reads(std::map<std::string, std::string>& a);
 static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
