@@ -12,6 +12,7 @@
 #include "../host/bam_reader.h"
 #include "../host/hla_typing.h"
 #include "../host/hla_eval.h"
+#include "../host/truth_levels.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1050,6 +1051,32 @@ int hlala_evaluate_types(const char* sample_id, const char* bestguess_file, cons
     });
     return rc == 0 ? n : rc;
 }
+
+struct hlala_truth { TruthLevels t; };
+int hlala_truth_load(const char* r1_levels, const char* r2_levels, hlala_truth_t** out) {
+    if (!r1_levels || !out) return fail(HLALA_E_ARG, "hlala_truth_load: null argument");
+    return guarded([&]() { std::unique_ptr<hlala_truth> h(new hlala_truth()); h->t.load(r1_levels, r2_levels ? r2_levels : ""); *out = h.release(); return 0; });
+}
+int64_t hlala_truth_n_reads(const hlala_truth_t* t) { return t ? (int64_t)t->t.reads.size() : (int64_t)fail(HLALA_E_ARG, "hlala_truth_n_reads: null handle"); }
+int hlala_truth_evaluate(hlala_truth_t* t, int64_t n_pairs, const char* const* pair_names, int64_t pair_index_base, const hlala_pair_out_t* a, int64_t* per_pair) {
+    if (!t || n_pairs < 0 || !a || !a->n_cols || !a->level || !a->schar || !a->read_reverse || a->max_columns <= 0) return fail(HLALA_E_ARG, "hlala_truth_evaluate: bad argument");
+    try {
+        const size_t cap = (size_t)a->max_columns;
+        for (int64_t p = 0; p < n_pairs; p++) {
+            const std::string id = pair_names ? std::string(pair_names[p]) : "r" + std::to_string(pair_index_base + p);
+            const int32_t* lv[2] = {a->level + (size_t)(2 * p) * cap, a->level + (size_t)(2 * p + 1) * cap};
+            const uint8_t* sc[2] = {a->schar + (size_t)(2 * p) * cap, a->schar + (size_t)(2 * p + 1) * cap};
+            const std::pair<int64_t, int64_t> r = t->t.evaluate(id, 2, lv, sc, a->n_cols + 2 * p, a->read_reverse + 2 * p);
+            if (per_pair) { per_pair[2 * p] = r.first; per_pair[2 * p + 1] = r.second; }
+        }
+    } catch (const std::exception& e) { return fail(HLALA_E_INVARIANT, e.what()); }
+    return 0;
+}
+int hlala_truth_totals(const hlala_truth_t* t, int64_t totals[3]) {
+    if (!t || !totals) return fail(HLALA_E_ARG, "hlala_truth_totals: null argument");
+    totals[0] = t->t.total; totals[1] = t->t.correct; totals[2] = t->t.reads_below_90; return 0;
+}
+void hlala_truth_free(hlala_truth_t* t) { delete t; }
 
 int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll /* [C*R], index c*R + r */, const int32_t* mism /* [C*R] */, int termwise,
                             double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms) {

@@ -37,6 +37,8 @@
 
 #include "mapper/processBAM.h"
 #include "hla/HLATyper.h"
+#include "simulator/trueReadLevels.h"
+#include <iostream>
 #include "Graph/Graph.h"
 #include "Graph/GraphAndEdgeIndex.h"
 #include "Utilities.h"
@@ -192,6 +194,32 @@ public:
         }
         omp_set_num_threads(1); eA->init_for_threads(1);
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return 0;
+    }
+
+    // The reference's accuracy harness: alignOneReadPair with a non-null simulator::trueReadLevels* (processBAM.cpp:3555-3560 calls the unmodified
+    // trueReadLevels::evaluateAlignment, simulator/trueReadLevels.cpp:18-196, on the selected pair; the `.levels` files are read by the unmodified
+    // constructor :203-320). Pairs with a read below 90 % must be left out by the caller: for those evaluateAlignment prints a re-scored "original alignment"
+    // through a verboseSeedChain whose sequence_begin is never set (trueReadLevels.cpp:117 -> extensionAligner.cpp:54), undefined behaviour that aborts here.
+    // per_pair: [2 * n_pairs] (bases, bases on their true level) from the differences of get_total_and_correct(); totals: [2].
+    int run_truth_pairs(const Batch& b, double is_mean, double is_sd, const char* r1_levels, const char* r2_levels, const long long* pair_id, long long* per_pair, long long* totals) const {
+        simulator::trueReadLevels truth(r1_levels, r2_levels);
+        boost::math::normal nd(is_mean, is_sd);
+        double pen = log(boost::math::pdf(nd, is_mean + 8 * is_sd));
+        omp_set_num_threads(1); eA->init_for_threads(1);
+        std::streambuf* keep = std::cout.rdbuf(nullptr);   // evaluateAlignment prints both alignments of every read below 90 %
+        for (int64_t p = 0; p < b.n_reads / 2; p++) {
+            mapper::reads::protoSeeds ps; std::vector<int32_t> o1, o2;
+            std::string name = "r" + std::to_string(pair_id ? pair_id[p] : (long long)p);   // the ID under which the `.levels` files know the pair
+            build_read(b, 2 * p, name, ps.read1_alignments, o1);
+            build_read(b, 2 * p + 1, name, ps.read2_alignments, o2);
+            std::pair<size_t, size_t> before = truth.get_total_and_correct();
+            alignOneReadPair(ps, nd, pen, &truth, nullptr);
+            std::pair<size_t, size_t> after = truth.get_total_and_correct();
+            if (per_pair) { per_pair[2 * p] = (long long)(after.first - before.first); per_pair[2 * p + 1] = (long long)(after.second - before.second); }
+        }
+        std::cout.rdbuf(keep); std::cout.clear();
+        totals[0] = (long long)truth.get_total_and_correct().first; totals[1] = (long long)truth.get_total_and_correct().second;
         return 0;
     }
 
@@ -390,6 +418,15 @@ int hlala_ref_pairs(void* h, long long n_reads, const int64_t* read_off, const u
     Driver* d = (Driver*)h;
     Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
     return guarded([&]() { return d->run_pairs(b, is_mean, is_sd, cap, threads, pair_mapq, read_mapq, read_reverse, n_cols, level, edge, gchar, schar, from_seed, mapq, seconds); });
+}
+
+int hlala_ref_truth_pairs(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
+                          const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
+                          const int32_t* cigar_off, const uint32_t* cigar, double is_mean, double is_sd, const char* r1_levels, const char* r2_levels,
+                          const long long* pair_id, long long* per_pair, long long* totals) {
+    Driver* d = (Driver*)h;
+    Driver::Batch b{n_reads, read_off, bases, quals, chain_off, chain_contig, chain_pos, chain_flag, chain_as, cigar_off, cigar};
+    return guarded([&]() { return d->run_truth_pairs(b, is_mean, is_sd, r1_levels, r2_levels, pair_id, per_pair, totals); });
 }
 
 int hlala_ref_long_reads(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,

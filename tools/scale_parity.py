@@ -18,24 +18,7 @@ import numpy as np  # noqa: E402
 import harness as H  # noqa: E402
 
 
-def subset(b, pairs):
-    """Sub-batch holding the given pairs (in the given order)."""
-    reads = np.stack([2 * pairs, 2 * pairs + 1], 1).reshape(-1)
-    ro = b["read_off"]; co = b["chain_off"]; go = b["cigar_off"]
-    out = {k: [] for k in ("bases", "quals", "chain_contig", "chain_pos", "chain_flag", "chain_as", "cigar")}
-    read_off = [0]; chain_off = [0]; cigar_off = [0]
-    for r in reads:
-        out["bases"].append(b["bases"][ro[r]:ro[r + 1]]); out["quals"].append(b["quals"][ro[r]:ro[r + 1]])
-        read_off.append(read_off[-1] + int(ro[r + 1] - ro[r]))
-        c0, c1 = int(co[r]), int(co[r + 1])
-        for k in ("chain_contig", "chain_pos", "chain_flag", "chain_as"):
-            out[k].append(b[k][c0:c1])
-        for c in range(c0, c1):
-            out["cigar"].append(b["cigar"][go[c]:go[c + 1]]); cigar_off.append(cigar_off[-1] + int(go[c + 1] - go[c]))
-        chain_off.append(chain_off[-1] + c1 - c0)
-    res = {k: np.ascontiguousarray(np.concatenate(v)).astype(b[k].dtype) for k, v in out.items()}
-    res["read_off"] = np.array(read_off, b["read_off"].dtype); res["chain_off"] = np.array(chain_off, b["chain_off"].dtype); res["cigar_off"] = np.array(cigar_off, b["cigar_off"].dtype)
-    return res
+subset = H.subset_pairs
 
 
 def session_results(P, b, maxcol, mu, sd):
