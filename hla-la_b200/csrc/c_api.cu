@@ -13,6 +13,7 @@
 #include "../host/hla_typing.h"
 #include "../host/hla_eval.h"
 #include "../host/truth_levels.h"
+#include "../host/read_simulator.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1077,6 +1078,21 @@ int hlala_truth_totals(const hlala_truth_t* t, int64_t totals[3]) {
     totals[0] = t->t.total; totals[1] = t->t.correct; totals[2] = t->t.reads_below_90; return 0;
 }
 void hlala_truth_free(hlala_truth_t* t) { delete t; }
+
+int64_t hlala_simulate_read_pairs(const char* matrix, int32_t read_length, int32_t interpolate, int32_t drop1, int32_t drop2, const uint8_t* path, int64_t n_levels, double coverage,
+                                  double diff_mean, double diff_sd, int32_t perfectly, int32_t include_deletions, const char* id_prefix, const char* out_prefix, int32_t append, double* error_rates) {
+    if (!matrix || read_length <= 0 || !path || n_levels <= 0 || !out_prefix) return fail(HLALA_E_ARG, "hlala_simulate_read_pairs: bad argument");
+    int64_t n = 0;
+    int rc = guarded([&]() {
+        ReadSimulator sim(matrix, (unsigned)read_length, interpolate != 0, drop1, drop2);
+        if (error_rates) { const std::pair<double, double> e = sim.average_error_rates(); error_rates[0] = e.first; error_rates[1] = e.second; }
+        const std::vector<SimulatedPair> pairs = sim.simulate_pairs_from_path(std::string((const char*)path, (size_t)n_levels), coverage, diff_mean, diff_sd, perfectly != 0,
+                                                                              id_prefix ? id_prefix : "", include_deletions != 0);
+        write_simulated_pairs(pairs, out_prefix, append != 0);
+        n = (int64_t)pairs.size(); return 0;
+    });
+    return rc == 0 ? n : rc;
+}
 
 int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll /* [C*R], index c*R + r */, const int32_t* mism /* [C*R] */, int termwise,
                             double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms) {
