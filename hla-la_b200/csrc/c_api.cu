@@ -1094,6 +1094,19 @@ int64_t hlala_simulate_read_pairs(const char* matrix, int32_t read_length, int32
     return rc == 0 ? n : rc;
 }
 
+int64_t hlala_simulate_individual(const char* prg_dir, const char* matrix, const char* out_dir, double is_mean, double is_sd, int32_t novel, int32_t with_error, uint32_t seed,
+                                  char* types_out, int64_t types_cap) {
+    if (!prg_dir || !matrix || !out_dir) return fail(HLALA_E_ARG, "hlala_simulate_individual: null argument");
+    int64_t n = 0;
+    int rc = guarded([&]() {
+        const SimulatedIndividual r = simulate_one_individual(prg_dir, matrix, out_dir, is_mean, is_sd, novel != 0, with_error != 0, seed);
+        std::string t; for (size_t i = 0; i < r.genes.size(); i++) { if (i) t += ';'; t += r.genes[i] + ":" + r.types[i].first + "/" + r.types[i].second; }
+        if (types_out && types_cap > 0) snprintf(types_out, (size_t)types_cap, "%s", t.c_str());
+        n = r.pairs; return 0;
+    });
+    return rc == 0 ? n : rc;
+}
+
 int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll /* [C*R], index c*R + r */, const int32_t* mism /* [C*R] */, int termwise,
                             double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms) {
     if (C <= 0 || R < 0 || !ll || !mism || !pair_ll) return fail(HLALA_E_ARG, "hlala_typing_pair_probe: bad argument");

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <random>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 
@@ -226,6 +227,127 @@ std::vector<SimulatedPair> ReadSimulator::simulate_pairs_from_path(const std::st
         }
     }
     return out;
+}
+
+namespace {
+
+std::vector<std::string> split_on(const std::string& s, char c) {   // Utilities::split(input, delimiter): an empty input has no fields, otherwise every delimiter separates
+    std::vector<std::string> out; if (s.empty()) return out;
+    size_t a = 0; for (;;) { size_t p = s.find(c, a); out.push_back(s.substr(a, p == std::string::npos ? std::string::npos : p - a)); if (p == std::string::npos) break; a = p + 1; }
+    return out;
+}
+std::string join_strings(const std::vector<std::string>& v, const std::string& d) { std::string s; for (size_t i = 0; i < v.size(); i++) { if (i) s += d; s += v[i]; } return s; }
+std::vector<std::string> file_lines(const std::string& path) {   // while(good) getline: a final newline leaves one empty line at the end, as in the reference
+    std::ifstream in(path.c_str()); if (!in.is_open()) throw std::runtime_error("cannot open " + path);
+    std::vector<std::string> out; std::string line; while (in.good()) { std::getline(in, line); chomp(line); out.push_back(line); } return out;
+}
+const std::string& uniform_choice(const std::vector<std::string>& v) { if (v.empty()) throw std::runtime_error("nothing to choose from"); return v.at((size_t)(rand() % (int)v.size())); }
+
+struct GeneTables {
+    std::vector<std::string> introns, exons, all;                                                      // segment IDs in segments.txt order
+    std::map<std::string, std::map<std::string, std::vector<std::string>>> seq;                        // segment -> type -> one string per level
+    std::map<std::string, std::vector<std::string>> level_names;                                       // segment -> level IDs
+};
+
+std::set<std::string> complete_genomic_types(const GeneTables& g) {   // HLATyper.cpp:353-404: the named (*) types of the first segment that holds any, introns first
+    std::set<std::string> r; bool first = true;
+    for (int ex = 0; ex <= 1; ex++) for (const std::string& id : (ex ? g.exons : g.introns)) {
+        if (first) for (const auto& kv : g.seq.at(id)) if (kv.first.find('*') != std::string::npos) r.insert(kv.first);
+        if (!g.seq.at(id).empty()) first = false;
+    }
+    for (const std::string& t : r) for (const auto& sg : g.seq) if (!sg.second.count(t)) throw std::runtime_error("type " + t + " is missing from segment " + sg.first);   // assert :398
+    return r;
+}
+std::set<std::string> complete_exonic_types(const GeneTables& g) {    // HLATyper.cpp:269-335: the named types present in every exon
+    if (g.exons.empty()) return complete_genomic_types(g);
+    std::map<std::string, int> n; for (const std::string& id : g.exons) for (const auto& kv : g.seq.at(id)) n[kv.first]++;
+    std::set<std::string> r; for (const auto& kv : n) if (kv.second == (int)g.exons.size() && kv.first.find('*') != std::string::npos) r.insert(kv.first);
+    return r;
+}
+
+} // namespace
+
+SimulatedIndividual simulate_one_individual(const std::string& prg_dir, const std::string& matrix, const std::string& out_dir, double is_mean, double is_sd, bool novel, bool with_error,
+                                            unsigned seed) {
+    if (matrix.empty()) throw std::runtime_error("simulate_one_individual: no quality matrix (assert(rS != 0), HLATyper.cpp:692)");
+    const unsigned read_length = 101; const double coverage = 15;   // HLATyper.cpp:98-99
+    ReadSimulator sim(matrix, read_length);
+    // tables of the constructor (:103-215)
+    std::map<std::string, GeneTables> genes;
+    for (const std::string& line : file_lines(prg_dir + "/PRG/segments.txt")) {
+        if (line.empty()) continue;
+        const std::vector<std::string> f = split_on(line, '_');
+        if (f.size() < 2) throw std::runtime_error("segments.txt: unexpected line " + line);
+        if (f[1] != "gene") continue;
+        if (f.size() < 5) throw std::runtime_error("segments.txt: unexpected line " + line);
+        GeneTables& g = genes[f[2]];
+        std::string id = f[4]; if (f.size() > 5) id += f[5];
+        const bool intron = id.find("intron") != std::string::npos;
+        if (!intron && id.find("exon") == std::string::npos) throw std::runtime_error("segments.txt: " + line + " is neither an exon nor an intron");
+        (intron ? g.introns : g.exons).push_back(id); g.all.push_back(id);
+        if (g.seq.count(id)) throw std::runtime_error("segments.txt: segment " + id + " of gene " + f[2] + " listed twice");
+        const std::vector<std::string> lines = file_lines(prg_dir + "/PRG/" + line);
+        const std::vector<std::string> head = split_on(lines.at(0), ' ');
+        if (head.empty() || head[0] != "IndividualID") throw std::runtime_error(line + ": first field is not IndividualID");
+        g.level_names[id] = std::vector<std::string>(head.begin() + 1, head.end());
+        g.seq[id];
+        for (size_t l = 1; l < lines.size(); l++) {
+            if (lines[l].empty()) continue;
+            const std::vector<std::string> fl = split_on(lines[l], ' ');
+            if (fl.size() != head.size()) throw std::runtime_error(line + ": a row with " + std::to_string(fl.size()) + " fields, header has " + std::to_string(head.size()));
+            g.seq[id][fl[0]] = std::vector<std::string>(fl.begin() + 1, fl.end());
+        }
+    }
+    {   // parameters.txt (:701-710)
+        std::ofstream ps((out_dir + "/parameters.txt").c_str());
+        if (!ps.is_open()) throw std::runtime_error("cannot write into " + out_dir);
+        const std::pair<double, double> er = sim.average_error_rates();
+        ps << "graphDir: " << prg_dir << "\n" << "simulations_read_length: " << read_length << "\n" << "insertSize_mean: " << is_mean << "\n" << "insertSize_sd: " << is_sd << "\n"
+           << "simulations_haploidCoverage: " << coverage << "\n" << "simulations_qualityMatrixFile: " << matrix << "\n" << "withError: " << with_error << "\n"
+           << "rS average error rates: " << er.first << "\t" << er.second << "\n";
+    }
+    srand(seed);
+    SimulatedIndividual res; std::vector<std::string> level_ids_out, haplotypes_out; bool first_write = true;
+    for (const auto& gk : genes) {   // std::set<std::string> graphGenes: name order
+        const std::string& gene = gk.first; const GeneTables& g = gk.second;
+        const std::set<std::string> from_set = novel ? complete_exonic_types(g) : complete_genomic_types(g);
+        const std::vector<std::string> from(from_set.begin(), from_set.end());
+        if (from.empty()) throw std::runtime_error("gene " + gene + ": no complete type to choose from");
+        std::vector<std::string> chosen; chosen.push_back(uniform_choice(from)); chosen.push_back(uniform_choice(from));
+        std::vector<std::vector<std::string>> hap(2); std::vector<std::string> level_ids;
+        for (const std::string& id : g.all) {
+            const bool exon = id.find("intron") == std::string::npos;
+            for (int h = 0; h < 2; h++) {
+                std::string type = chosen[(size_t)h];
+                if (!exon && novel) { std::vector<std::string> pool; for (const auto& kv : g.seq.at(id)) pool.push_back(kv.first); type = uniform_choice(pool); }
+                const std::vector<std::string>& a = g.seq.at(id).at(type);
+                hap[(size_t)h].insert(hap[(size_t)h].end(), a.begin(), a.end());
+                if (h == 0) level_ids.insert(level_ids.end(), g.level_names.at(id).begin(), g.level_names.at(id).end());
+            }
+        }
+        for (int h = 0; h < 2; h++) {
+            if (hap[(size_t)h].size() != level_ids.size()) throw std::runtime_error("gene " + gene + ": haplotype and level names differ in length");
+            for (const std::string& c : hap[(size_t)h]) if (c.size() != 1) throw std::runtime_error("gene " + gene + ": an allele of more than one character");
+            const std::vector<SimulatedPair> pairs = sim.simulate_pairs_from_path(join_strings(hap[(size_t)h], ""), coverage, is_mean, is_sd, !with_error, "PRG_" + gene + "_HAPLO_" + std::to_string(h));
+            write_simulated_pairs(pairs, out_dir + "/R", !first_write); first_write = false;
+            res.pairs += (int64_t)pairs.size();
+        }
+        res.genes.push_back(gene); res.types.push_back(std::make_pair(chosen[0], chosen[1]));
+        level_ids_out.push_back(join_strings(level_ids, ";")); haplotypes_out.push_back(join_strings(hap[0], ";") + "/" + join_strings(hap[1], ";"));
+    }
+    if (first_write) write_simulated_pairs(std::vector<SimulatedPair>(), out_dir + "/R", false);   // the four files exist even without a gene
+    {   // HLAtypes.txt, haplotypes.txt (:895-930)
+        std::ofstream ts((out_dir + "/HLAtypes.txt").c_str()), hs((out_dir + "/haplotypes.txt").c_str());
+        if (!ts.is_open() || !hs.is_open()) throw std::runtime_error("cannot write into " + out_dir);
+        std::vector<std::string> row{out_dir}, hhead, hrow{out_dir};
+        for (size_t i = 0; i < res.genes.size(); i++) {
+            row.push_back(res.types[i].first + "/" + res.types[i].second);
+            hhead.push_back("LevelIDs_" + res.genes[i]); hhead.push_back("Haplotype_" + res.genes[i]); hrow.push_back(level_ids_out[i]); hrow.push_back(haplotypes_out[i]);
+        }
+        ts << "IndividualID" << "\t" << join_strings(res.genes, "\t") << "\n" << join_strings(row, "\t") << "\n";
+        hs << "IndividualID" << "\t" << join_strings(hhead, "\t") << "\n" << join_strings(hrow, "\t") << "\n";
+    }
+    return res;
 }
 
 void write_simulated_pairs(const std::vector<SimulatedPair>& pairs, const std::string& prefix, bool append) {

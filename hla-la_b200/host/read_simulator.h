@@ -40,6 +40,17 @@ private:
     unsigned len_;
 };
 
+// One simulated individual from the allele tables of a PRG directory: hla::HLATyper::simulateOneIndividual (hla/HLATyper.cpp:690-930) with the tables
+// the HLATyper constructor loads (:103-215; PRG/segments.txt and the *_gene_* files it lists), the type lists of get_complete_genomic_types_per_gene
+// (:353-404) and get_complete_exonic_types_per_gene (:269-335), reads of 101 bases at 15 x per haplotype (:98-99) through
+// simulate_paired_reads_from_string (readSimulator.cpp:341-358). Two types per gene, in gene order, by Utilities::choose_uniformly_from_vector
+// (rand() % n, Utilities.cpp:1030-1037): the C library's generator, seeded here with `seed` (the reference leaves the seeding to whoever ran before).
+// Writes R_1.fq, R_2.fq, R_1.levels, R_2.levels, HLAtypes.txt, haplotypes.txt and parameters.txt into out_dir. The levels in the `.levels` files are
+// positions in the gene's haplotype string, as in the reference (its conversion to graph levels at :873-886 updates a field it does not print).
+struct SimulatedIndividual { std::vector<std::string> genes; std::vector<std::pair<std::string, std::string>> types; int64_t pairs = 0; };
+SimulatedIndividual simulate_one_individual(const std::string& prg_dir, const std::string& quality_matrix_file, const std::string& out_dir, double insert_mean, double insert_sd,
+                                            bool novel_intron_exon_recombinants, bool with_error, unsigned seed);
+
 // R_1.fq / R_2.fq / R_1.levels / R_2.levels under `prefix` + "_" (simulator.cpp:300-324), appended in the order of `pairs`
 void write_simulated_pairs(const std::vector<SimulatedPair>& pairs, const std::string& prefix, bool append);
 

@@ -277,6 +277,13 @@ int64_t hlala_simulate_read_pairs(const char* quality_matrix_file, int32_t read_
                                   int32_t additional_second_read_classes, const uint8_t* path_emission, int64_t n_levels, double haploid_coverage,
                                   double start_diff_mean, double start_diff_sd, int32_t perfectly, int32_t include_deletions, const char* id_prefix,
                                   const char* out_prefix, int32_t append, double* error_rates);
+/*   HLATyper::simulateOneIndividual(outputDirectory, insertSize_mean, insertSize_sd, novelIntronExonRecombinats, withError)   hla/HLATyper.cpp:690-930
+ * (the individual of the reference's TestHLATyping action, HLA-LA.cpp:1262-1340): two types per gene of PRG/segments.txt drawn with rand() % n after
+ * srand(seed), their gene haplotypes from the *_gene_* tables, reads of 101 bases at 15 x per haplotype; writes R_1.fq, R_2.fq, R_1.levels, R_2.levels,
+ * HLAtypes.txt (the truth file hlala_evaluate_types / --trueHLA reads), haplotypes.txt and parameters.txt into out_dir. types_out: "gene:type1/type2"
+ * entries joined by ';' (may be NULL). Returns the number of pairs or a negative HLALA_E_* code. */
+int64_t hlala_simulate_individual(const char* prg_graph_dir, const char* quality_matrix_file, const char* out_dir, double insert_mean, double insert_sd,
+                                  int32_t novel_intron_exon_recombinants, int32_t with_error, uint32_t seed, char* types_out, int64_t types_cap);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * k-mer seeding. Reference seam B5 of SURVEY.md §8b (no live caller in the reference: HLA-LA.cpp:230,1439 are commented out):

@@ -460,6 +460,18 @@ long long hlala_ref_simulate_pairs(const char* matrix, int read_length, int inte
     return rc == 0 ? n : -1;
 }
 
+// The unmodified hla::HLATyper::simulateOneIndividual (hla/HLATyper.cpp:690-930) of a typer constructed with a quality matrix (HLATyper.cpp:100-103),
+// after srand(seed): its type choices are rand() % n (Utilities.cpp:1030-1037).
+int hlala_ref_simulate_individual(void* h, const char* prg_dir, const char* matrix, const char* out_dir, double is_mean, double is_sd, int novel, int with_error, unsigned seed) {
+    Driver* d = (Driver*)h;
+    return guarded([&]() {
+        hla::HLATyper typer(d->graph(), prg_dir, matrix);
+        srand(seed);
+        typer.simulateOneIndividual(out_dir, is_mean, is_sd, novel != 0, with_error != 0);
+        return 0;
+    });
+}
+
 int hlala_ref_long_reads(void* h, long long n_reads, const int64_t* read_off, const uint8_t* bases, const uint8_t* quals,
                          const int32_t* chain_off, const int32_t* chain_contig, const int32_t* chain_pos, const uint16_t* chain_flag, const int32_t* chain_as,
                          const int32_t* cigar_off, const uint32_t* cigar, int cap, int threads,

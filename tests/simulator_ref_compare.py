@@ -41,6 +41,40 @@ def random_path(n, seed):
     return a
 
 
+FILES = ("R_1.fq", "R_2.fq", "R_1.levels", "R_2.levels", "HLAtypes.txt", "haplotypes.txt", "parameters.txt")
+
+
+def individual(R, P, d, matrix):
+    """hlala_simulate_individual against the unmodified HLATyper::simulateOneIndividual (hla/HLATyper.cpp:690-930) on a synthetic PRG with 3 genes x 12 alleles:
+    all seven files byte for byte, for several seeds, with and without novel intron / exon recombinants, with and without sequencing errors"""
+    prg = os.path.join(d, "prg"); H.synth_prg(prg, levels=14000, haps=4, genes=3, alleles=12, seed=3)
+    ref = H.quiet(H.Ref, prg)
+    R.hlala_ref_simulate_individual.restype = C.c_int; P.hlala_simulate_individual.restype = C.c_int64
+    out = os.path.join(d, "ind"); os.makedirs(out)
+    seen = set(); npairs = 0
+    for seed, novel, err in ((1, 0, 1), (2, 1, 1), (7, 0, 0), (11, 1, 1)):
+        rc = H.quiet(R.hlala_ref_simulate_individual, ref.h, prg.encode(), matrix.encode(), out.encode(), C.c_double(300.0), C.c_double(30.0), C.c_int(novel), C.c_int(err), C.c_uint(seed))
+        assert rc == 0, R.hlala_ref_last_error()
+        want = {f: open(os.path.join(out, f), "rb").read() for f in FILES}
+        for f in FILES:
+            os.remove(os.path.join(out, f))
+        types = C.create_string_buffer(4096)
+        n = P.hlala_simulate_individual(prg.encode(), matrix.encode(), out.encode(), C.c_double(300.0), C.c_double(30.0), C.c_int(novel), C.c_int(err), C.c_uint(seed), types, C.c_int64(4096))
+        assert n > 0, P.hlala_last_error()
+        for f in FILES:
+            got = open(os.path.join(out, f), "rb").read()
+            if got != want[f]:
+                la, lb = want[f].split(b"\n"), got.split(b"\n")
+                k = next((i for i in range(min(len(la), len(lb))) if la[i] != lb[i]), min(len(la), len(lb)))
+                raise AssertionError("individual seed %d: %s differs at line %d:\n  ref %r\n  got %r" % (seed, f, k + 1, la[k][:300] if k < len(la) else None, lb[k][:300] if k < len(lb) else None))
+        assert n == want["R_1.fq"].count(b"\n") // 4
+        row = want["HLAtypes.txt"].split(b"\n")[1].split(b"\t")[1:]
+        assert types.value.decode().split(";") == ["%s:%s" % (g, t.decode()) for g, t in zip("ABC", row)], (types.value, row)
+        seen.add(tuple(row)); npairs += n
+    assert len(seen) >= 3, "the seeds should lead to different individuals"
+    return dict(individuals=4, distinct_type_sets=len(seen), pairs=int(npairs))
+
+
 def main():
     R = C.CDLL(H.LIB_REF); R.hlala_ref_simulate_pairs.restype = C.c_longlong; R.hlala_ref_last_error.restype = C.c_char_p
     P = C.CDLL(H.LIB_PRODUCT); P.hlala_simulate_read_pairs.restype = C.c_int64; P.hlala_last_error.restype = C.c_char_p
@@ -93,6 +127,7 @@ def main():
     assert P.hlala_truth_load(os.path.join(d, "got0_1.levels").encode(), os.path.join(d, "got0_2.levels").encode(), C.byref(t)) == 0
     assert "pairs" in report[0] and P.hlala_truth_n_reads(t) == report[0]["pairs"] // 2   # the appended half repeats the first half's names
     P.hlala_truth_free(t)
+    report.append(individual(R, P, d, syn))
     print("ok: " + json.dumps(report))
 
 

@@ -18,7 +18,8 @@ import simulator_ref_compare as S  # noqa: E402
 def test_simulated_reads_match_the_references_readSimulator():
     """R_1.fq / R_2.fq / R_1.levels / R_2.levels byte for byte and the average error rates exactly, against the unmodified readSimulator (own process): exact and
     interpolated read lengths, removal of upper quality classes for either read, insertions / deletions from quality-0 rows, includeDeletions, perfect reads,
-    appending a second haplotype; on synthetic matrices and, where /root/reference is present, on the matrix the reference ships"""
+    appending a second haplotype; on synthetic matrices and, where /root/reference is present, on the matrix the reference ships. Also hlala_simulate_individual against
+    the unmodified HLATyper::simulateOneIndividual: all seven files of four individuals byte for byte"""
     r = subprocess.run([sys.executable, os.path.join(HERE, "simulator_ref_compare.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
 
@@ -83,3 +84,36 @@ def test_simulator_errors_are_reported(tmp_path):
     assert _run(L, mat, 101, path, out, d1=4)[0] < 0 and b"cannot remove 4 quality classes" in L.hlala_last_error()
     assert _run(L, mat, 101, path, out, d1=21)[0] < 0 and b"0..20" in L.hlala_last_error()
     assert _run(L, mat, 120, path, out, ip=1)[0] > 0
+
+
+def test_simulated_individual_closes_the_loop_with_the_type_evaluation(dataset, tmp_path):
+    """hlala_simulate_individual (HLATyper::simulateOneIndividual; pinned byte for byte in simulator_ref_compare.py): two types per gene, reads of 101 bases from the
+    gene haplotypes, and a truth file that hlala_evaluate_types (--trueHLA) reads back: calls equal to the truth score 2 of 2 at every locus, a wrong call 1 of 2"""
+    from test_evaluate_types import product_eval
+    L = _lib(); L.hlala_simulate_individual.restype = C.c_int64
+    d, _b, _mu, _sd = dataset("small")
+    mat = str(tmp_path / "m.txt"); S.synthetic_matrix(mat)
+    out = str(tmp_path / "ind"); os.makedirs(out)
+    types = C.create_string_buffer(4096)
+    n = L.hlala_simulate_individual(d.encode(), mat.encode(), out.encode(), C.c_double(250.0), C.c_double(25.0), C.c_int(0), C.c_int(1), C.c_uint(5), types, C.c_int64(4096))
+    assert n > 0, L.hlala_last_error()
+    chosen = dict(x.split(":", 1) for x in types.value.decode().split(";"))
+    assert list(chosen) == ["A"] and all(t.startswith("A*") for t in chosen["A"].split("/"))
+    for f in S.FILES:
+        assert os.path.getsize(os.path.join(out, f)) > 0
+    assert open(os.path.join(out, "R_1.fq")).read().count("\n") == 4 * n
+    assert open(os.path.join(out, "R_1.fq")).readline().startswith("@PRG_A_HAPLO_0r1|||")
+    t1, t2 = chosen["A"].split("/")
+    best = str(tmp_path / "best.txt")
+    open(best, "w").write("Locus\tChromosome\tAllele\tQ1\tQ2\nA\t1\t%s\t1\t1\nA\t2\t%s\t1\t1\n" % (t2, t1))
+    got, _ = product_eval(out, best, os.path.join(out, "HLAtypes.txt"))      # the individual's ID is the output directory (HLATyper.cpp:899)
+    assert got == {"A": (2, 2)}
+    open(best, "w").write("Locus\tChromosome\tAllele\tQ1\tQ2\nA\t1\t%s\t1\t1\nA\t2\tA*99:99\t1\t1\n" % t1)
+    got, _ = product_eval(out, best, os.path.join(out, "HLAtypes.txt"))
+    assert got == {"A": (2, 2 if t1 == t2 else 1)}
+    # same seed, same individual; no matrix, no simulation (assert(rS != 0) in the reference)
+    out2 = str(tmp_path / "ind2"); os.makedirs(out2)
+    assert L.hlala_simulate_individual(d.encode(), mat.encode(), out2.encode(), C.c_double(250.0), C.c_double(25.0), C.c_int(0), C.c_int(1), C.c_uint(5), None, C.c_int64(0)) == n
+    assert open(os.path.join(out2, "R_2.levels")).read() == open(os.path.join(out, "R_2.levels")).read()
+    assert L.hlala_simulate_individual(d.encode(), b"", out2.encode(), C.c_double(250.0), C.c_double(25.0), C.c_int(0), C.c_int(1), C.c_uint(5), None, C.c_int64(0)) < 0
+    assert L.hlala_simulate_individual((d + "_nowhere").encode(), mat.encode(), out2.encode(), C.c_double(250.0), C.c_double(25.0), C.c_int(0), C.c_int(1), C.c_uint(5), None, C.c_int64(0)) < 0
