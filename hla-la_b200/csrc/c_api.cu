@@ -1094,6 +1094,14 @@ int64_t hlala_simulate_read_pairs(const char* matrix, int32_t read_length, int32
     return rc == 0 ? n : rc;
 }
 
+int64_t hlala_simulate_from_graph(const hlala_graph_t* g, const char* graph_label, const char* matrix, int32_t read_length, double is_mean, double is_sd, int32_t n_genomes,
+                                  const char* out_dir, double coverage, int32_t with_error, uint32_t seed) {
+    if (!g || !matrix || !out_dir || read_length <= 0 || n_genomes < 0) return fail(HLALA_E_ARG, "hlala_simulate_from_graph: bad argument");
+    int64_t n = 0;
+    int rc = guarded([&]() { n = simulate_from_graph(g->h, graph_label ? graph_label : "", matrix, read_length, is_mean, is_sd, n_genomes, out_dir, coverage, with_error != 0, seed); return 0; });
+    return rc == 0 ? n : rc;
+}
+
 int64_t hlala_simulate_individual(const char* prg_dir, const char* matrix, const char* out_dir, double is_mean, double is_sd, int32_t novel, int32_t with_error, uint32_t seed,
                                   char* types_out, int64_t types_cap) {
     if (!prg_dir || !matrix || !out_dir) return fail(HLALA_E_ARG, "hlala_simulate_individual: null argument");

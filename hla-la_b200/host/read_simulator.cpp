@@ -1,5 +1,6 @@
 // See read_simulator.h. Written against the behaviour of simulator/readSimulator.cpp (constructor :58-334, simulate_paired_reads_from_edgePath :1194-1693).
 #include "read_simulator.h"
+#include "prg_graph.h"
 
 #include <algorithm>
 #include <cmath>
@@ -348,6 +349,41 @@ SimulatedIndividual simulate_one_individual(const std::string& prg_dir, const st
         hs << "IndividualID" << "\t" << join_strings(hhead, "\t") << "\n" << join_strings(hrow, "\t") << "\n";
     }
     return res;
+}
+
+int64_t simulate_from_graph(const FlatGraph& g, const std::string& graph_label, const std::string& matrix, int read_length, double is_mean, double is_sd, int n_genomes,
+                            const std::string& out_dir, double coverage, bool with_error, unsigned seed) {
+    if (g.n_levels < 2 || g.node_out_off.size() != (size_t)g.n_nodes + 1) throw std::runtime_error("simulate_from_graph: graph without edges");
+    ReadSimulator sim(matrix, (unsigned)read_length);
+    {   // simulator.cpp:263-276
+        std::ofstream ps((out_dir + "/parameters.txt").c_str());
+        if (!ps.is_open()) throw std::runtime_error("cannot write into " + out_dir);
+        const std::pair<double, double> er = sim.average_error_rates();
+        ps << "Graph: " << graph_label << "\n" << "simulatedGraphGenomes: " << n_genomes << "\n" << "qualityMatrixFile: " << matrix << "\n" << "read_length: " << read_length << "\n"
+           << "insertSize_mean: " << is_mean << "\n" << "insertSize_sd: " << is_sd << "\n" << "haploidCoverage: " << coverage << "\n" << "withError: " << with_error << "\n"
+           << "rS average error rates: " << er.first << "\t" << er.second << "\n";
+    }
+    write_simulated_pairs(std::vector<SimulatedPair>(), out_dir + "/R", false);
+    srand(seed);
+    int64_t total = 0;
+    for (int gi = 0; gi < n_genomes; gi++) {
+        std::string path[2];
+        for (int h = 0; h < 2; h++) {   // Graph.cpp:1485-1519
+            int32_t node = g.level_node_off[0];
+            while (g.node_out_off[(size_t)node + 1] > g.node_out_off[(size_t)node]) {
+                const int n = g.node_out_off[(size_t)node + 1] - g.node_out_off[(size_t)node];
+                int pick = (int)(((double)rand() / RAND_MAX) * n); if (pick == n) pick = n - 1;
+                const int32_t e = g.node_out[(size_t)g.node_out_off[(size_t)node] + (size_t)pick];
+                path[h].push_back((char)g.edge_emis[(size_t)e]); node = g.edge_to[(size_t)e];
+            }
+            if ((int32_t)path[h].size() != g.n_levels - 1) throw std::runtime_error("simulate_from_graph: a walk that ends before the last level");   // assert :1516
+        }
+        for (int h = 0; h < 2; h++) {   // both haplotypes are simulated before either is printed (simulator.cpp:333-343); the generators are per call, so the order is free
+            const std::vector<SimulatedPair> pairs = sim.simulate_pairs_from_path(path[h], coverage, is_mean, is_sd, !with_error, "PRG_" + std::to_string(gi) + "h" + std::to_string(h + 1) + "_");
+            write_simulated_pairs(pairs, out_dir + "/R", true); total += (int64_t)pairs.size();
+        }
+    }
+    return total;
 }
 
 void write_simulated_pairs(const std::vector<SimulatedPair>& pairs, const std::string& prefix, bool append) {

@@ -72,7 +72,32 @@ def individual(R, P, d, matrix):
         assert types.value.decode().split(";") == ["%s:%s" % (g, t.decode()) for g, t in zip("ABC", row)], (types.value, row)
         seen.add(tuple(row)); npairs += n
     assert len(seen) >= 3, "the seeds should lead to different individuals"
-    return dict(individuals=4, distinct_type_sets=len(seen), pairs=int(npairs))
+    # hlala_simulate_from_graph against the unmodified simulator::simulateFromGraph (random diploid walks through the same graph): five files byte for byte
+    G = H.Product(prg); R.hlala_ref_simulate_from_graph.restype = C.c_int; P.hlala_simulate_from_graph.restype = C.c_int64
+    gfiles = ("parameters.txt", "R_1.fq", "R_2.fq", "R_1.levels", "R_2.levels"); gpairs = 0
+    for seed, genomes, cov, err in ((3, 1, 5.0, 1), (4, 2, 2.0, 1), (9, 1, 3.0, 0)):
+        rc = H.quiet(R.hlala_ref_simulate_from_graph, ref.h, matrix.encode(), C.c_int(101), C.c_double(280.0), C.c_double(20.0), C.c_int(genomes), out.encode(), C.c_double(cov), C.c_int(err), C.c_uint(seed))
+        assert rc == 0, R.hlala_ref_last_error()
+        want = {f: open(os.path.join(out, f), "rb").read() for f in gfiles}
+        for f in gfiles:
+            os.remove(os.path.join(out, f))
+        n = G.lib.hlala_simulate_from_graph(G.g, (prg + "/PRG/graph.txt").encode(), matrix.encode(), C.c_int(101), C.c_double(280.0), C.c_double(20.0), C.c_int(genomes), out.encode(),
+                                            C.c_double(cov), C.c_int(err), C.c_uint(seed))
+        assert n > 0, G.lib.hlala_last_error()
+        for f in gfiles:
+            got = open(os.path.join(out, f), "rb").read()
+            if got != want[f]:
+                la, lb = want[f].split(b"\n"), got.split(b"\n")
+                k = next((i for i in range(min(len(la), len(lb))) if la[i] != lb[i]), min(len(la), len(lb)))
+                raise AssertionError("from graph, seed %d: %s differs at line %d:\n  ref %r\n  got %r" % (seed, f, k + 1, la[k][:300] if k < len(la) else None, lb[k][:300] if k < len(lb) else None))
+        assert n == want["R_1.fq"].count(b"\n") // 4
+        gpairs += n
+    # the levels in these files are graph levels: every simulated base names a level whose edges can emit it (perfect reads of the last run)
+    lv = H.read_levels_file(os.path.join(out, "R_1.levels")); lo = G.array("level_edge_off"); em = G.array("edge_emis")
+    for levels, labels, _a, _b, _c in list(lv.values())[:200]:
+        for l, ch in zip(levels, labels):
+            assert l == -1 or ord(ch) in em[lo[l]:lo[l + 1]]
+    return dict(individuals=4, distinct_type_sets=len(seen), pairs=int(npairs), graph_runs=3, graph_pairs=int(gpairs))
 
 
 def main():

@@ -19,7 +19,8 @@ def test_simulated_reads_match_the_references_readSimulator():
     """R_1.fq / R_2.fq / R_1.levels / R_2.levels byte for byte and the average error rates exactly, against the unmodified readSimulator (own process): exact and
     interpolated read lengths, removal of upper quality classes for either read, insertions / deletions from quality-0 rows, includeDeletions, perfect reads,
     appending a second haplotype; on synthetic matrices and, where /root/reference is present, on the matrix the reference ships. Also hlala_simulate_individual against
-    the unmodified HLATyper::simulateOneIndividual: all seven files of four individuals byte for byte"""
+    the unmodified HLATyper::simulateOneIndividual (all seven files of four individuals) and hlala_simulate_from_graph against simulator::simulateFromGraph with its random
+    diploid walks (five files of three runs), byte for byte"""
     r = subprocess.run([sys.executable, os.path.join(HERE, "simulator_ref_compare.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "ok:" in r.stdout, r.stdout[-3000:]
 
@@ -117,3 +118,38 @@ def test_simulated_individual_closes_the_loop_with_the_type_evaluation(dataset, 
     assert open(os.path.join(out2, "R_2.levels")).read() == open(os.path.join(out, "R_2.levels")).read()
     assert L.hlala_simulate_individual(d.encode(), b"", out2.encode(), C.c_double(250.0), C.c_double(25.0), C.c_int(0), C.c_int(1), C.c_uint(5), None, C.c_int64(0)) < 0
     assert L.hlala_simulate_individual((d + "_nowhere").encode(), mat.encode(), out2.encode(), C.c_double(250.0), C.c_double(25.0), C.c_int(0), C.c_int(1), C.c_uint(5), None, C.c_int64(0)) < 0
+
+
+def test_reads_simulated_from_the_graph_feed_the_truth_harness(dataset, tmp_path):
+    """hlala_simulate_from_graph (simulator::simulateFromGraph; pinned byte for byte in simulator_ref_compare.py): random diploid walks through the loaded graph, reads
+    with graph levels; hlala_truth_load takes the `.levels` files, and an alignment that puts every base on its simulated level scores 100 %"""
+    d, _b, _mu, _sd = dataset("small")
+    G = H.Product(d); L = G.lib; L.hlala_simulate_from_graph.restype = C.c_int64; L.hlala_truth_n_reads.restype = C.c_int64
+    mat = str(tmp_path / "m.txt"); S.synthetic_matrix(mat)
+    out = str(tmp_path / "g"); os.makedirs(out)
+    n = L.hlala_simulate_from_graph(G.g, b"label", mat.encode(), C.c_int(101), C.c_double(200.0), C.c_double(20.0), C.c_int(1), out.encode(), C.c_double(4.0), C.c_int(1), C.c_uint(2))
+    assert n > 50, L.hlala_last_error()
+    assert open(os.path.join(out, "parameters.txt")).read().startswith("Graph: label\nsimulatedGraphGenomes: 1\n")
+    r1, r2 = os.path.join(out, "R_1.levels"), os.path.join(out, "R_2.levels")
+    lv = [H.read_levels_file(r1), H.read_levels_file(r2)]
+    names = list(lv[0]); assert len(names) == n and names[0].startswith("PRG_0h1_r1|||") and any(x.startswith("PRG_0h2_") for x in names)
+    nl = G.dims()["n_levels"]
+    assert all(-1 <= l < nl - 1 for x in lv[0].values() for l in x[0])
+    # a "perfect aligner": columns = the simulated bases on their simulated levels, in graph direction
+    cap = 128; aln = dict(n_cols=np.zeros(2 * n, np.int32), level=np.zeros((2 * n, cap), np.int32), schar=np.zeros((2 * n, cap), np.uint8), read_reverse=np.zeros(2 * n, np.uint8))
+    for p_, nm in enumerate(names):
+        for m in (0, 1):
+            levels = lv[m][nm][0]; known = [l for l in levels if l != -1]; rev = known[0] > known[-1]
+            aln["read_reverse"][2 * p_ + m] = rev; aln["n_cols"][2 * p_ + m] = len(levels)
+            aln["level"][2 * p_ + m, :len(levels)] = levels[::-1] if rev else levels; aln["schar"][2 * p_ + m, :len(levels)] = ord("A")
+    per, tot, n_ids = H.truth_evaluate(aln, r1, r2, names=names)
+    assert n_ids == n and tot[0] == tot[1] == 2 * 101 * n and tot[2] == 0
+    aln["level"][0, 3] += 1
+    per, tot, _ = H.truth_evaluate(aln, r1, r2, names=names)
+    assert tot[0] - tot[1] == 1 and per[0].tolist() == [202, 201]
+    # a graph handle is needed, seeds differ, errors are reported
+    n2 = L.hlala_simulate_from_graph(G.g, b"label", mat.encode(), C.c_int(101), C.c_double(200.0), C.c_double(20.0), C.c_int(1), out.encode(), C.c_double(4.0), C.c_int(1), C.c_uint(3))
+    assert n2 > 0 and H.read_levels_file(r1) != lv[0]
+    assert L.hlala_simulate_from_graph(None, b"", mat.encode(), C.c_int(101), C.c_double(200.0), C.c_double(20.0), C.c_int(1), out.encode(), C.c_double(4.0), C.c_int(1), C.c_uint(3)) == -1
+    assert L.hlala_simulate_from_graph(G.g, b"", mat.encode(), C.c_int(101), C.c_double(200.0), C.c_double(20.0), C.c_int(1), (out + "/missing").encode(), C.c_double(4.0), C.c_int(1), C.c_uint(3)) < 0
+    G.close()
