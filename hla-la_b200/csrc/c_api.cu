@@ -14,6 +14,7 @@
 #include "../host/hla_eval.h"
 #include "../host/truth_levels.h"
 #include "../host/read_simulator.h"
+#include "../host/contig_mapper.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1327,6 +1328,16 @@ static int bam_read_impl(const hlala_graph_t* g, const char* bam_path, int threa
     });
 }
 int hlala_bam_read(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out) { return bam_read_impl(g, bam_path, threads, false, out); }
+int hlala_fastq_map_pairs(const hlala_graph_t* g, const char* fastq1, const char* fastq2, int threads, hlala_bam_batch_t** out) {
+    if (!g || !fastq1 || !fastq2 || !out) return fail(HLALA_E_ARG, "hlala_fastq_map_pairs: null argument");
+    *out = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<hlala_bam_batch> B(new hlala_bam_batch());
+        map_fastq_pairs(g->h, fastq1, fastq2, threads, MapperParams(), B->b);
+        B->names.reserve(B->b.pair_name.size()); for (const std::string& n : B->b.pair_name) B->names.push_back(n.c_str());
+        *out = B.release(); return 0;
+    });
+}
 int hlala_bam_read_long(const hlala_graph_t* g, const char* bam_path, int threads, hlala_bam_batch_t** out) { return bam_read_impl(g, bam_path, threads, true, out); }
 int hlala_bam_batch_view(const hlala_bam_batch_t* B, hlala_seed_batch_t* view, const char* const** pair_names) {
     if (!B || !view) return fail(HLALA_E_ARG, "hlala_bam_batch_view: null argument");

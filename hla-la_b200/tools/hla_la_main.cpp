@@ -68,6 +68,18 @@ static int default_max_columns(const hlala_seed_batch_t& b) {
     int64_t longest = 0; for (int64_t r = 0; r < b.n_reads; r++) longest = std::max<int64_t>(longest, b.read_off[r + 1] - b.read_off[r]);
     return longest <= 160 ? 640 : (int)std::min<int64_t>(2040, 4 * longest + 64);
 }
+// the seeds of the run: the remapped BAM (HLA-LA.cpp:775-779), or paired FASTQ files placed on the PRG contigs here (in place of BWAmapper::map, HLA-LA.cpp:742)
+static int read_seeds(std::map<std::string, std::string>& a, hlala_graph_t* g, hlala_bam_batch_t** bam) {
+    const int threads = a.count("threads") ? atoi(a["threads"].c_str()) : 0;
+    if (a.count("BAM")) {
+        if (hlala_bam_read(g, a["BAM"].c_str(), threads, bam)) return die("reading the BAM");
+        phase("BAM read, records selected and grouped");
+    } else {
+        if (hlala_fastq_map_pairs(g, a["FASTQ1"].c_str(), a["FASTQ2"].c_str(), threads, bam)) return die("mapping the FASTQ files");
+        phase("FASTQ read, reads placed on the PRG contigs (all placements, best one primary)");
+    }
+    return 0;
+}
 static int run_long_reads(std::map<std::string, std::string>& a);
 static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     const std::string out_dir = a["outputDirectory"], prg = a["PRG_graph_dir"]; int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
@@ -83,8 +95,7 @@ static int run_multi_gpu(std::map<std::string, std::string>& a, int n_gpus) {
     if (failed) { for (auto& e : err) if (!e.empty()) fprintf(stderr, "hlala-b200: loading the PRG: %s\n", e.c_str()); return 1; }
     phase("PRG loaded and replicated on the GPUs");
     hlala_bam_batch_t* bam = nullptr;
-    if (hlala_bam_read(graphs[0], a["BAM"].c_str(), a.count("threads") ? atoi(a["threads"].c_str()) : 0, &bam)) return die("reading the BAM");
-    phase("BAM read, records selected and grouped");
+    if (read_seeds(a, graphs[0], &bam)) return 1;
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
     if (!a.count("maxColumns") && batch.n_reads > 0) maxcol = default_max_columns(batch);
@@ -226,12 +237,14 @@ int main(int argc, char** argv) {
     if (a.count("maxThreads") && !a.count("threads")) a["threads"] = a["maxThreads"];     // HLA-LA.pl passes --maxThreads
     if (!a.count("action")) { fprintf(stderr, "\n\nMissing --action parameter. Please don't try calling me directly; use HLA-LA.pl instead (see documentation on GitHub).\n\n"); return 2; }     // HLA-LA.cpp:104-108
     if (a["action"] == "testBinary") { fprintf(stdout, "\nHLA*LA binary functional!\n\n"); return 0; }                                                                                          // HLA-LA.cpp:129-132
-    if (a["action"] == "HLA" && !a.count("BAM") && (a.count("FASTQ1") || a.count("FASTQU"))) {
-        // HLA-LA.cpp:745-790: the reference maps the extracted FASTQ with `bwa mem -a -M` (BWAmapper::map / mapLong) and continues with the remapped BAM.
-        // bwa / samtools belong to the control plane that stays outside this program: run that step and pass its output as --BAM.
-        fprintf(stderr, "hlala-b200: --FASTQ1/--FASTQ2/--FASTQU: map the reads first (bwa mem -a -M <PRG_graph_dir>/mapping_PRGonly/referenceGenome.fa ... | samtools sort) and pass the result as --BAM\n");
+    const bool from_fastq = a["action"] == "HLA" && !a.count("BAM") && a.count("FASTQ1") && a.count("FASTQ2");
+    if (a["action"] == "HLA" && !a.count("BAM") && !from_fastq && (a.count("FASTQ1") || a.count("FASTQ2") || a.count("FASTQU"))) {
+        // HLA-LA.cpp:745-790: the reference maps the extracted FASTQ with `bwa mem -a -M` (BWAmapper::map / mapLong / mapUnpaired) and continues with the remapped BAM.
+        // Paired files (--FASTQ1 + --FASTQ2, what HLA-LA.pl:563 passes for short reads) are mapped here (hlala_fastq_map_pairs); unpaired / long reads are not.
+        fprintf(stderr, "hlala-b200: --FASTQU / a single --FASTQ1: map the reads first (bwa mem -a -M <PRG_graph_dir>/mapping_PRGonly/referenceGenome.fa ... | samtools sort) and pass the result as --BAM\n");
         return 2;
     }
+    if (from_fastq && a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "") { fprintf(stderr, "hlala-b200: --longReads takes a --BAM (bwa mem -x ont2d|pacbio)\n"); return 2; }
     const bool long_reads = a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "";
     if (long_reads && a["longReads"] != "ont2d" && a["longReads"] != "pacbio") { fprintf(stderr, "hlala-b200: --longReads must be 0, ont2d or pacbio\n"); return 2; }     // HLA-LA.cpp:759
     if (a["action"] == "prepareGraph" && a.count("PRG_graph_dir")) {
@@ -247,8 +260,9 @@ int main(int argc, char** argv) {
         hlala_graph_free(g);
         return 0;
     }
-    if (a["action"] != "HLA" || !a.count("BAM") || !a.count("outputDirectory") || !a.count("PRG_graph_dir")) {
+    if (a["action"] != "HLA" || !(a.count("BAM") || from_fastq) || !a.count("outputDirectory") || !a.count("PRG_graph_dir")) {
         fprintf(stderr, "usage: hlala-b200 --action HLA --sampleID <id> --BAM <remapped.bam> --outputDirectory <dir> --PRG_graph_dir <dir>\n"
+                        "       hlala-b200 --action HLA --sampleID <id> --FASTQ1 <R1.fq[.gz]> --FASTQ2 <R2.fq[.gz]> --outputDirectory <dir> --PRG_graph_dir <dir>   (reads placed on the PRG contigs here, no bwa)\n"
                         "       hlala-b200 --action prepareGraph --PRG_graph_dir <dir>\n"
                         "       hlala-b200 --action testBinary\n"
                         "       [--longReads ont2d|pacbio]  (the BAM then holds single long reads: bwa mem -x ont2d|pacbio)\n"
@@ -266,8 +280,7 @@ int main(int argc, char** argv) {
     if (hlala_graph_to_gpu(g, device)) return die("uploading the PRG");
     phase("PRG on the GPU");
     hlala_bam_batch_t* bam = nullptr;
-    if (hlala_bam_read(g, a["BAM"].c_str(), a.count("threads") ? atoi(a["threads"].c_str()) : 0, &bam)) return die("reading the BAM");
-    phase("BAM read, records selected and grouped");
+    if (read_seeds(a, g, &bam)) return 1;
     hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4]; double is_mean = 0, is_sd = 0; int64_t is_n = 0;
     hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, &is_mean, &is_sd, &is_n);
     if (!a.count("maxColumns") && batch.n_reads > 0) maxcol = default_max_columns(batch);

@@ -635,9 +635,19 @@ class Product:
 
 
     # ---- BAM ingest
+    def fastq_map(self, fastq1, fastq2, threads=0):
+        """hlala_fastq_map_pairs: paired FASTQ -> (batch dict, pair names, counts) like bam_read"""
+        h = C.c_void_p()
+        self._chk(self.lib.hlala_fastq_map_pairs(self.g, fastq1.encode(), fastq2.encode(), C.c_int(threads), C.byref(h)))
+        return self._batch_of(h, False)
+
     def bam_read(self, path, threads=0, long_reads=False):
         L = self.lib; h = C.c_void_p()
         self._chk((L.hlala_bam_read_long if long_reads else L.hlala_bam_read)(self.g, path.encode(), C.c_int(threads), C.byref(h)))
+        return self._batch_of(h, long_reads)
+
+    def _batch_of(self, h, long_reads):
+        L = self.lib
         try:
             v = SeedBatch(); names = C.POINTER(C.c_char_p)()
             self._chk(L.hlala_bam_batch_view(h, C.byref(v), C.byref(names)))
@@ -658,11 +668,14 @@ class Product:
         finally:
             L.hlala_bam_batch_free(h)
 
-    def bam_insert_size(self, path, cap=640, gpu=False, threads=0):
+    def bam_insert_size(self, path, cap=640, gpu=False, threads=0, fastq2=None):
         """the reference's insert-size sample of a BAM (hlala_bam_insert_size_sample) as a batch dict + loaded contig indices; with gpu=True also
-        (mean, sd, used, skipped) of hlala_bam_insert_size"""
+        (mean, sd, used, skipped) of hlala_bam_insert_size. fastq2: `path` and fastq2 are paired FASTQ files mapped by hlala_fastq_map_pairs instead."""
         L = self.lib; h = C.c_void_p()
-        self._chk(L.hlala_bam_read(self.g, path.encode(), C.c_int(threads), C.byref(h)))
+        if fastq2 is not None:
+            self._chk(L.hlala_fastq_map_pairs(self.g, path.encode(), fastq2.encode(), C.c_int(threads), C.byref(h)))
+        else:
+            self._chk(L.hlala_bam_read(self.g, path.encode(), C.c_int(threads), C.byref(h)))
         try:
             v = SeedBatch(); lc = C.POINTER(C.c_int32)(); nlc = C.c_int32()
             self._chk(L.hlala_bam_insert_size_sample(h, C.byref(v), C.byref(lc), C.byref(nlc)))

@@ -1,5 +1,5 @@
 """Argument surface of hlala-b200 (no GPU needed): what the reference binary answers for --action testBinary (HLA-LA.cpp:129-132) and a missing --action (:104-108),
-and this program's own rules — unknown keys and odd argument counts are errors, FASTQ input is answered with the mapping step to run first, --longReads takes
+and this program's own rules — unknown keys and odd argument counts are errors, paired FASTQ input is mapped by the program itself while unpaired FASTQ input is answered with the mapping step to run first, --longReads takes
 0 / ont2d / pacbio (HLA-LA.cpp:759)."""
 import os
 import subprocess
@@ -30,8 +30,16 @@ def test_missing_action_and_bad_arguments():
 
 
 def test_fastq_and_long_read_arguments(tmp_path):
-    r = run("--action", "HLA", "--FASTQ1", "a.fq", "--FASTQ2", "b.fq", "--outputDirectory", str(tmp_path), "--PRG_graph_dir", str(tmp_path))
+    # paired FASTQ files (what HLA-LA.pl:563 passes) are accepted and mapped by the program itself: the run gets as far as the (missing) PRG
+    r = run("--action", "HLA", "--FASTQ1", "a.fq", "--FASTQ2", "b.fq", "--outputDirectory", str(tmp_path), "--PRG_graph_dir", str(tmp_path / "nope"))
+    assert r.returncode == 1 and "loading the PRG" in r.stderr
+    # unpaired / long-read FASTQ input still needs the external mapping step
+    r = run("--action", "HLA", "--FASTQU", "a.fq", "--outputDirectory", str(tmp_path), "--PRG_graph_dir", str(tmp_path))
     assert r.returncode == 2 and "bwa mem -a -M" in r.stderr
+    r = run("--action", "HLA", "--FASTQ1", "a.fq", "--outputDirectory", str(tmp_path), "--PRG_graph_dir", str(tmp_path))
+    assert r.returncode == 2 and "bwa mem -a -M" in r.stderr
+    r = run("--action", "HLA", "--FASTQ1", "a.fq", "--FASTQ2", "b.fq", "--longReads", "ont2d", "--outputDirectory", str(tmp_path), "--PRG_graph_dir", str(tmp_path))
+    assert r.returncode == 2 and "--longReads takes a --BAM" in r.stderr
     r = run("--action", "HLA", "--BAM", "x.bam", "--outputDirectory", str(tmp_path), "--PRG_graph_dir", str(tmp_path), "--longReads", "nanopore")
     assert r.returncode == 2 and "ont2d or pacbio" in r.stderr
     # --longReads 0 is the short-read path (HLA-LA.cpp:760-763); --maxThreads is HLA-LA.pl's name for the thread count: both are accepted, the run then fails at the missing PRG

@@ -1,0 +1,147 @@
+"""FASTQ input without bwa: hlala_fastq_map_pairs places paired reads on the PRG's linear contigs and returns the batch hlala_bam_read would return
+for their `bwa mem -a -M` BAM. There is no oracle for the mapper itself (bwa is an external program, absent here); what is measured is what the reference's own
+testPRGMapping actions measure (HLA-LA.cpp:1386-1621): the fraction of bases of simulated reads that the alignment path puts on their true level — against the
+same figure for the generator's own seeds (the chains a perfect mapper would report). The file sorts last on purpose: the mapper is the newest part."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness as H
+from conftest import DATASETS
+
+
+def _mapped(dataset, name, tmp_path):
+    d, _b, mu, sd = dataset(name)
+    pre = str(tmp_path / "R")
+    b = H.synth_reads(d, str(tmp_path / "seeds.bin"), levels_prefix=pre, **DATASETS[name][1])
+    P = H.Product(d)
+    mb, names, cnt = P.fastq_map(pre + "_1.fq", pre + "_2.fq", threads=4)
+    return d, b, mu, sd, pre, P, mb, names, cnt
+
+
+def _fraction(aln, pre, names):
+    _per, tot, _n = H.truth_evaluate(aln, pre + "_1.levels", pre + "_2.levels", names=names)
+    return tot[1] / tot[0]
+
+
+@pytest.mark.parametrize("name,floor", [("S", 0.985), ("genes", 0.99)])
+def test_mapped_fastq_reaches_the_accuracy_of_the_generators_seeds(dataset, tmp_path, name, floor):
+    d, b, mu, sd, pre, P, mb, names, cnt = _mapped(dataset, name, tmp_path)
+    npairs = DATASETS[name][1]["pairs"]
+    assert cnt["incomplete"] == 0 and len(names) == npairs and names == sorted(names) and cnt["records"] == cnt["used"] == len(mb["chain_contig"])
+    nr = len(mb["read_off"]) - 1
+    qlen = np.zeros(len(mb["chain_contig"]), np.int64)
+    for c in range(len(qlen)):
+        ops = mb["cigar"][mb["cigar_off"][c]:mb["cigar_off"][c + 1]]
+        qlen[c] = sum(int(x >> 4) for x in ops if (x & 15) in (0, 1, 4))
+        assert (ops[0] & 15) in (0, 4) and (ops[-1] & 15) in (0, 4) and all((x & 15) in (0, 1, 2, 4) for x in ops)
+        inner = [x & 15 for x in ops if (x & 15) != 4]
+        assert inner[0] == 0 and inner[-1] == 0                                   # an alignment starts and ends with matched bases
+    for r in range(nr):
+        c0, c1 = mb["chain_off"][r], mb["chain_off"][r + 1]
+        fl = mb["chain_flag"][c0:c1]; prim = np.nonzero((fl & 0x100) == 0)[0]
+        assert len(prim) == 1                                                     # exactly one primary record per mate (protoSeeds.cpp:252-314)
+        assert mb["chain_as"][c0:c1].max() == mb["chain_as"][c0 + prim[0]] >= 30  # ... the best-scoring one
+        assert ((fl & 0x40) != 0).all() == (r % 2 == 0) and ((fl & 0x80) != 0).all() == (r % 2 == 1)
+        key = list(zip(mb["chain_contig"][c0:c1], mb["chain_pos"][c0:c1])); assert key == sorted(key)   # coordinate order like a sorted BAM
+        assert (qlen[c0:c1] == mb["read_off"][r + 1] - mb["read_off"][r]).all()
+    # SEQ as in the FASTQ for a forward primary, reverse-complemented otherwise: either way the generator's BAM-orientation bases when the strand is right
+    same = sum(bytes(mb["bases"][mb["read_off"][2 * p]:mb["read_off"][2 * p + 1]]) == bytes(b["bases"][b["read_off"][2 * int(n[1:])]:b["read_off"][2 * int(n[1:]) + 1]]) for p, n in enumerate(names))
+    assert same >= 0.99 * npairs
+    O = H.Oracle(d)
+    got = _fraction(H.quiet(O.pairs, mb, mu, sd, 1024), pre, names)
+    want = _fraction(H.quiet(O.pairs, b, mu, sd, 1024), pre, None)
+    assert got >= floor and got >= want - 0.004, "bases on their true level: %.4f with the mapper's seeds, %.4f with the generator's" % (got, want)
+    # a gzip-compressed copy gives the same batch
+    for m in ("1", "2"):
+        with open(pre + "_%s.fq" % m, "rb") as f, gzip.open(pre + "_%s.fq.gz" % m, "wb") as z:
+            z.write(f.read())
+    mb2, names2, _ = P.fastq_map(pre + "_1.fq.gz", pre + "_2.fq.gz", threads=2)
+    assert names2 == names and all((mb2[k] == mb[k]).all() for k in H.BATCH_KEYS)
+    P.close()
+
+
+def test_unplaceable_reads_and_malformed_input(dataset, tmp_path):
+    d, _b, _mu, _sd = dataset("small")
+    P = H.Product(d)
+    rng = np.random.RandomState(1)
+    seq = P.array("contig_seq"); off = P.array("contig_off")
+    good = bytes(seq[off[0] + 500:off[0] + 600]).decode(); mate = bytes(seq[off[0] + 700:off[0] + 800]).decode()
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    mate_rc = "".join(comp[c] for c in reversed(mate)); junk = "".join("ACGT"[i] for i in rng.randint(0, 4, 100))
+    f1, f2 = str(tmp_path / "a_1.fq"), str(tmp_path / "a_2.fq")
+    open(f1, "w").write("@p2/1 extra\n%s\n+\n%s\n@p1/1\n%s\n+p1\n%s\n" % (good, "I" * 100, junk, "I" * 100))
+    open(f2, "w").write("@p2/2\n%s\n+\n%s\n@p1/2\n%s\n+\n%s\n" % (mate_rc, "5" * 100, mate_rc, "5" * 100))
+    mb, names, cnt = P.fastq_map(f1, f2)
+    assert names == ["p2"] and cnt["names"] == 2 and cnt["incomplete"] == 1          # the pair with a random mate has no placement for it and is dropped
+    c0 = mb["chain_off"][0]; prim = [c for c in range(c0, mb["chain_off"][1]) if not mb["chain_flag"][c] & 0x100][0]
+    assert mb["chain_contig"][prim] == 0 and mb["chain_pos"][prim] == 500 and mb["chain_as"][prim] == 100 and list(mb["cigar"][mb["cigar_off"][prim]:mb["cigar_off"][prim + 1]]) == [100 << 4]
+    prim2 = [c for c in range(mb["chain_off"][1], mb["chain_off"][2]) if not mb["chain_flag"][c] & 0x100][0]
+    assert mb["chain_flag"][prim2] & 0x10 and mb["chain_pos"][prim2] == 700 and bytes(mb["bases"][100:200]).decode() == mate and mb["chain_flag"][prim] & 0x20
+    open(f2, "w").write("@p2/2\n%s\n+\n%s\n" % (mate_rc, "5" * 100))
+    with pytest.raises(RuntimeError, match="different numbers of reads"):
+        P.fastq_map(f1, f2)
+    open(f2, "w").write("@p2/2\n%s\n+\n%s\n@px/2\n%s\n+\n%s\n" % (mate_rc, "5" * 100, mate_rc, "5" * 100))
+    with pytest.raises(RuntimeError, match="names differ"):
+        P.fastq_map(f1, f2)
+    open(f2, "w").write("@p2/2\n%s\n+\n%s\n" % (mate_rc, "5" * 99))
+    with pytest.raises(RuntimeError, match="malformed FASTQ"):
+        P.fastq_map(f1, f2)
+    with pytest.raises(RuntimeError, match="cannot open"):
+        P.fastq_map(f1, str(tmp_path / "none.fq"))
+    P.close()
+
+
+@pytest.mark.gpu
+def test_gpu_alignment_of_mapped_fastq_equals_the_oracle_and_keeps_the_accuracy(dataset, tmp_path):
+    """the batch from the mapper through hlala_align_pairs on the GPU: identical to the oracle on the same batch (columns, mapping qualities, coverage),
+    and the bases-on-true-level figure with it"""
+    d, b, mu, sd, pre, P, mb, names, cnt = _mapped(dataset, "S", tmp_path)
+    P.to_gpu(0)
+    got = P.pairs(mb, mu, sd, 1024)
+    want = H.oracle_pairs(d, mb, mu, sd, 1024)
+    from test_gpu_parity import assert_pairs_equal
+    assert_pairs_equal(got, want)
+    assert _fraction(got, pre, names) >= 0.985
+    P.close()
+
+
+@pytest.mark.gpu
+def test_cli_runs_from_fastq(dataset, tmp_path):
+    """hlala-b200 --action HLA --FASTQ1 --FASTQ2 (the arguments HLA-LA.pl:563 builds for short reads): reads placed here, then the usual path; the calls equal those
+    of the same run from the generator's BAM where the loci are covered"""
+    d, _b, _mu, _sd = dataset("typing")
+    pre = str(tmp_path / "R")
+    H.synth_reads(d, str(tmp_path / "seeds.bin"), levels_prefix=pre, **DATASETS["typing"][1])
+    out = str(tmp_path / "out")
+    r = subprocess.run([H.CLI, "--action", "HLA", "--sampleID", "S", "--FASTQ1", pre + "_1.fq", "--FASTQ2", pre + "_2.fq", "--outputDirectory", out, "--PRG_graph_dir", d,
+                        "--insertSizeMean", "100", "--insertSizeSD", "10"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "reads placed on the PRG contigs" in r.stdout
+    assert len(os.listdir(os.path.join(out, "hla"))) == 73 and os.path.getsize(os.path.join(out, "reads_per_level.txt")) > 0
+    calls = [l.split("\t") for l in r.stdout.splitlines() if l.count("\t") == 4]
+    assert len(calls) == 17 and calls[0][0] == "A"
+
+
+def test_insert_size_estimate_from_mapped_fastq(tmp_path):
+    """the default insert-size model of a FASTQ run: the mapper fills the sample estimateInsertSize works on (primary records of the first 2000 pairs in name order);
+    alignments from the oracle restatement here, the arithmetic is hlala_insert_size_from_levels (pinned to the reference in insert_size_ref_compare.py)"""
+    d = str(tmp_path / "prg"); H.synth_prg(d, levels=40000, haps=4, genes=2, alleles=48, seed=9)
+    pre = str(tmp_path / "R")
+    H.synth_reads(d, str(tmp_path / "seeds.bin"), pairs=2500, len=100, clip_frac=0.15, seed=9, gap_mean=180, gap_sd=25, levels_prefix=pre)
+    P = H.Product(d)
+    sample, loaded, _ = P.bam_insert_size(pre + "_1.fq", fastq2=pre + "_2.fq", threads=4)
+    assert len(sample["read_off"]) - 1 == 4000 and (np.diff(sample["chain_off"]) == 1).all() and not (sample["chain_flag"] & 0x100).any()
+    oc = H.Oracle(d).chains(sample, 640)
+    assert (oc["status"] == 0).all()
+    fl = np.full(len(oc["status"]), -1, np.int32); ll = np.full(len(oc["status"]), -1, np.int32)
+    for i, n in enumerate(oc["n_cols"]):
+        lv = oc["level"][i, :n]; lv = lv[lv != -1]
+        if len(lv):
+            fl[i], ll[i] = lv[0], lv[-1]
+    mean, sd, used, skipped = P.insert_size_from_levels(fl, ll, ((sample["chain_flag"] & 0x10) != 0).astype(np.uint8), loaded)
+    assert abs(mean - 180) <= 6 and 15 <= sd <= 35 and used >= 1900, (mean, sd, used, skipped)
+    P.close()
