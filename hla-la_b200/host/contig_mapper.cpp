@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -48,12 +51,38 @@ ContigMapper::ContigMapper(const FlatGraph& g, const MapperParams& p) : g_(g), p
 // Banded affine-gap alignment of read[0..len) around `diag` (contig position of read base 0) on `contig`: any start and end in the read, a clipped end costs p_.clip.
 bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t diag, Placement& out) const {
     const int64_t cb = g_.contig_off[(size_t)contig], clen = g_.contig_off[(size_t)contig + 1] - cb;
-    const int B = p_.band, Wd = 2 * B + 1;
     const uint8_t* ref = g_.contig_seq.data() + cb;
     const int go = p_.gap_open + p_.gap_extend, ge = p_.gap_extend;
-    // cell (i, b): read base i against contig position j = diag + i + b - B
-    std::vector<int32_t> M((size_t)2 * Wd, NEG), E((size_t)2 * Wd, NEG), F((size_t)2 * Wd, NEG);
-    std::vector<uint8_t> tb((size_t)len * Wd, 0);   // bits 0-1: M came from 0 start, 1 M, 2 E, 3 F; bit 2: E extended; bit 3: F extended
+    // Most placements have no gap at all: the best clipped stretch of the diagonal itself (one pass). It is taken as it stands when it holds at most two mismatches
+    // and the whole read lies on the contig: a gapped alignment would have to win back a gap (7 or more) from at most two mismatches (4 each) plus a clipped end.
+    if (diag >= 0 && diag + len <= clen) {
+        int run = NEG, run_start = 0, run_mm = 0, ub = NEG, ub_s = 0, ub_e = 0, ub_mm = 0;
+        for (int i = 0; i < len; i++) {
+            const int rc = code_of(ref[diag + i]); const bool eq = rd[i] < 4 && rd[i] == rc; const int sc = eq ? p_.match : -p_.mismatch;
+            const int fresh = (i == 0 ? 0 : -p_.clip);
+            if (eq && fresh >= run) { run = fresh; run_start = i; run_mm = 0; }   // a stretch begins on a matching base when that is at least as good as going on
+            if (run > NEG / 2) {
+                run += sc; run_mm += !eq;
+                const int fin = run + (i == len - 1 ? 0 : -p_.clip);
+                if (eq && (fin > ub || (fin == ub && i > ub_e))) { ub = fin; ub_s = run_start; ub_e = i; ub_mm = run_mm; }
+            }
+        }
+        if (ub > NEG / 2 && (ub_mm <= 2 || (ub_s == 0 && ub_e == len - 1 && ub_mm <= 6))) {   // ... or it spans the whole read with a few scattered mismatches (SNPs against another haplotype)
+            const int raw = ub + (ub_s > 0 ? p_.clip : 0) + (ub_e < len - 1 ? p_.clip : 0);
+            if (raw < p_.min_score) return false;
+            out.contig = contig; out.pos = (int32_t)(diag + ub_s); out.score = raw; out.cigar.clear();
+            if (ub_s > 0) out.cigar.push_back(((uint32_t)ub_s << 4) | OP_S);
+            out.cigar.push_back(((uint32_t)(ub_e - ub_s + 1) << 4) | OP_M);
+            if (ub_e < len - 1) out.cigar.push_back(((uint32_t)(len - 1 - ub_e) << 4) | OP_S);
+            return true;
+        }
+    }
+    // cell (i, b): read base i against contig position j = diag + i + b - B. A narrow band first; the full one only if the narrow alignment leans on the band's edge.
+    static thread_local std::vector<int32_t> M, E, F; static thread_local std::vector<uint8_t> tb;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const int B = attempt == 0 ? std::max(4, p_.band / 3) : p_.band, Wd = 2 * B + 1; bool edge = false;
+    M.assign((size_t)2 * Wd, NEG); E.assign((size_t)2 * Wd, NEG); F.assign((size_t)2 * Wd, NEG);
+    tb.assign((size_t)len * Wd, 0);   // bits 0-1: M came from 0 start, 1 M, 2 E, 3 F; bit 2: E extended; bit 3: F extended
     int best = NEG, best_i = -1, best_b = -1;
     for (int i = 0; i < len; i++) {
         int32_t* Mc = &M[(size_t)(i & 1) * Wd]; int32_t* Ec = &E[(size_t)(i & 1) * Wd]; int32_t* Fc = &F[(size_t)(i & 1) * Wd];
@@ -75,7 +104,7 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
             Mc[b] = m; Ec[b] = e < NEG / 2 ? NEG : e; Fc[b] = f < NEG / 2 ? NEG : f; tb[(size_t)i * Wd + b] = t;
         }
     }
-    if (best_i < 0) return false;
+    if (best_i < 0) { if (attempt == 0) continue; return false; }
     // trace back
     std::vector<uint8_t> ops; int i = best_i, b = best_b, state = 0;   // state 0 M, 1 E, 2 F
     int start_i = -1; int64_t start_j = -1;
@@ -87,8 +116,11 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
             i--; state = w - 1;   // diagonal predecessor keeps b
         } else if (state == 1) { ops.push_back(OP_D); const bool ext = t & 4; b--; state = ext ? 1 : 0; }
         else { ops.push_back(OP_I); const bool ext = t & 8; i--; b++; state = ext ? 2 : 0; }
-        if (i < 0 || b < 0 || b >= Wd) return false;
+        if (b <= 0 || b >= Wd - 1) edge = true;
+        if (i < 0 || b < 0 || b >= Wd) { edge = true; start_i = -1; break; }
     }
+    if (attempt == 0 && (edge || best_b <= 0 || best_b >= Wd - 1)) continue;
+    if (start_i < 0) return false;
     std::reverse(ops.begin(), ops.end());
     const int raw = best + (start_i > 0 ? p_.clip : 0) + (best_i < len - 1 ? p_.clip : 0);
     if (raw < p_.min_score) return false;
@@ -97,6 +129,8 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
     for (size_t k = 0; k < ops.size();) { size_t e2 = k; while (e2 < ops.size() && ops[e2] == ops[k]) e2++; out.cigar.push_back(((uint32_t)(e2 - k) << 4) | ops[k]); k = e2; }
     if (best_i < len - 1) out.cigar.push_back(((uint32_t)(len - 1 - best_i) << 4) | OP_S);
     return true;
+  }
+    return false;
 }
 
 std::vector<Placement> ContigMapper::map_read(const std::string& seq) const {
@@ -182,12 +216,17 @@ void map_fastq_pairs(const FlatGraph& g, const std::string& fastq1, const std::s
     if (r[0].size() != r[1].size()) throw std::runtime_error("the FASTQ files hold different numbers of reads (" + std::to_string(r[0].size()) + " / " + std::to_string(r[1].size()) + ")");
     const size_t n = r[0].size();
     for (size_t i = 0; i < n; i++) if (r[0][i].name != r[1][i].name) throw std::runtime_error("read " + std::to_string(i + 1) + " of the FASTQ files: names differ (" + r[0][i].name + " / " + r[1][i].name + ")");
+    const bool timing = getenv("HLALA_MAPPER_TIMING") != nullptr; auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (timing) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[mapper] %-28s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count()); t0 = t1; } };
+    lap("FASTQ files read");
     ContigMapper mapper(g, p);
+    lap("contig index built");
     std::vector<std::vector<Placement>> hits[2]; hits[0].resize(n); hits[1].resize(n);
     unsigned nt = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
     std::atomic<size_t> next(0);
     auto work = [&]() { for (;;) { const size_t a = next.fetch_add(64); if (a >= n) break; for (size_t i = a; i < std::min(n, a + 64); i++) for (int m = 0; m < 2; m++) hits[m][i] = mapper.map_read(r[m][i].seq); } };
     { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
+    lap("reads placed");
     std::vector<size_t> order(n); std::iota(order.begin(), order.end(), (size_t)0);
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return r[0][a].name != r[0][b].name ? r[0][a].name < r[0][b].name : a < b; });
     out = BamBatch(); out.read_off.push_back(0); out.chain_off.push_back(0); out.cigar_off.push_back(0);
@@ -221,6 +260,7 @@ void map_fastq_pairs(const FlatGraph& g, const std::string& fastq1, const std::s
             }
         }
     }
+    lap("batch assembled");
     S.names_seen = (int64_t)S.pair_name.size();
     S.loaded_contigs.resize((size_t)g.n_contigs); std::iota(S.loaded_contigs.begin(), S.loaded_contigs.end(), 0);   // every translation is at hand here
 }

@@ -22,6 +22,7 @@
  *                         = per read processBAM::alignOneLongRead (:3618) + assignMappingQualities_unpaired (:3900)
  *   hlala_bam_read / hlala_bam_read_long / hlala_bam_insert_size
  *                         processBAM::getReadIDs / extractSeeds2 (:169, :703), protoSeeds::takeAlignment, processBAM::estimateInsertSize (:1071)
+ *   hlala_fastq_map_pairs BWAmapper::map (bwa mem -a -M against the PRG contigs) + the read-back of its BAM  mapper/bwa/BWAmapper.cpp, HLA-LA.cpp:742-779
  *   hlala_typer_* / hlala_session_typing_extract / hlala_typing_blob_from_long_reads
  *                         the gene filter (:2427-2446, :2297-2331) + hla::HLATyper::HLATypeInference  hla/HLATyper.cpp:933-2810
  *   hlala_evaluate_types  hla::HLATyper::read_inferred_types / read_true_types / evaluate_HLA_types  hla/HLATyper.cpp:407-688
