@@ -75,9 +75,60 @@ static int read_seeds(std::map<std::string, std::string>& a, hlala_graph_t* g, h
         if (hlala_bam_read(g, a["BAM"].c_str(), threads, bam)) return die("reading the BAM");
         phase("BAM read, records selected and grouped");
     } else {
+        // HLA-LA.cpp:770: --mapAgainstCompleteGenome 1 maps against the whole genome plus the PRG; here the PRG contigs are all there is (extract the MHC reads first, as HLA-LA.pl does)
+        if (a.count("mapAgainstCompleteGenome") && a["mapAgainstCompleteGenome"] != "0") fprintf(stderr, "hlala-b200: note: --mapAgainstCompleteGenome is not available without bwa; the reads are placed on the PRG contigs only\n");
         if (hlala_fastq_map_pairs(g, a["FASTQ1"].c_str(), a["FASTQ2"].c_str(), threads, bam)) return die("mapping the FASTQ files");
         phase("FASTQ read, reads placed on the PRG contigs (all placements, best one primary)");
     }
+    return 0;
+}
+// --action testPRGMapping: the reference's synthetic integration test (HLA-LA.cpp:1386-1621, e.g. :1455-1527): reads with known levels from a random genome of the graph
+// (simulator::simulateFromGraph) -> mapped (there: bwa; here: hlala_fastq_map_pairs) -> alignReads with a trueReadLevels object -> "Graph: <bases> <fraction on their true level>".
+// The reference simulates its own small PRG first (Graph/graphSimulator); here the PRG is the one given by --PRG_graph_dir.
+static int run_test_prg_mapping(std::map<std::string, std::string>& a) {
+    if (!a.count("PRG_graph_dir") || !a.count("outputDirectory") || !a.count("qualityMatrixFile")) {
+        fprintf(stderr, "usage: hlala-b200 --action testPRGMapping --PRG_graph_dir <dir> --outputDirectory <dir> --qualityMatrixFile <file> [--haploidCoverage 5] [--seed 1]\n"
+                        "       [--insertSizeMean 100 --insertSizeSD 10] [--device <n>] [--maxColumns <n>] [--maxThreads <n>]\n");
+        return 2;
+    }
+    const std::string prg = a["PRG_graph_dir"], out = a["outputDirectory"], matrix = a["qualityMatrixFile"];
+    const double coverage = a.count("haploidCoverage") ? atof(a["haploidCoverage"].c_str()) : 5.0;                 // S.simulateFromGraph(&g, 1, dir, 5, true), HLA-LA.cpp:1456
+    const double is_mean = a.count("insertSizeMean") ? atof(a["insertSizeMean"].c_str()) : 100.0, is_sd = a.count("insertSizeSD") ? atof(a["insertSizeSD"].c_str()) : 10.0;   // simulator.h:20
+    const unsigned seed = a.count("seed") ? (unsigned)strtoul(a["seed"].c_str(), nullptr, 10) : 1u;
+    const int device = a.count("device") ? atoi(a["device"].c_str()) : 0; int maxcol = a.count("maxColumns") ? atoi(a["maxColumns"].c_str()) : 640;
+    mkdir(out.c_str(), 0777);
+    g_t0 = std::chrono::steady_clock::now();
+    hlala_graph_t* g = nullptr;
+    if (hlala_graph_load(prg.c_str(), &g)) return die("loading the PRG");
+    if (hlala_graph_to_gpu(g, device)) return die("uploading the PRG");
+    phase("PRG loaded and on the GPU");
+    const int64_t n_sim = hlala_simulate_from_graph(g, (prg + "/PRG/graph.txt").c_str(), matrix.c_str(), 101, is_mean, is_sd, 1, out.c_str(), coverage, 1, seed);
+    if (n_sim < 0) return die("simulating reads from the graph");
+    phase("read pairs simulated from one random diploid genome of the graph");
+    const std::string f1 = out + "/R_1.fq", f2 = out + "/R_2.fq", l1 = out + "/R_1.levels", l2 = out + "/R_2.levels";
+    hlala_bam_batch_t* bam = nullptr;
+    if (hlala_fastq_map_pairs(g, f1.c_str(), f2.c_str(), a.count("threads") ? atoi(a["threads"].c_str()) : 0, &bam)) return die("mapping the simulated reads");
+    phase("simulated reads placed on the PRG contigs");
+    hlala_seed_batch_t batch; const char* const* names = nullptr; int64_t counts[4];
+    hlala_bam_batch_view(bam, &batch, &names); hlala_bam_batch_stats(bam, counts, nullptr, nullptr, nullptr);
+    if (!a.count("maxColumns") && batch.n_reads > 0) maxcol = default_max_columns(batch);
+    const int64_t nr = batch.n_reads, np = nr / 2; const size_t cells = (size_t)nr * (size_t)maxcol;
+    if (np == 0) { fprintf(stderr, "hlala-b200: none of the %lld simulated pairs could be placed\n", (long long)n_sim); return 1; }
+    std::vector<double> pair_mapq((size_t)np), read_mapq((size_t)nr), pair_ll((size_t)np); std::vector<uint8_t> rev((size_t)nr), gch(cells), sch(cells), fs(cells), mq(cells);
+    std::vector<int32_t> slot((size_t)nr), ncols((size_t)nr), level(cells), edge(cells);
+    hlala_pair_out_t po; po.max_columns = maxcol; po.pair_mapq = pair_mapq.data(); po.read_mapq = read_mapq.data(); po.read_reverse = rev.data(); po.chosen_slot = slot.data(); po.pair_ll = pair_ll.data();
+    po.n_cols = ncols.data(); po.level = level.data(); po.edge = edge.data(); po.gchar = gch.data(); po.schar = sch.data(); po.from_seed = fs.data(); po.mapq = mq.data();
+    if (hlala_align_pairs(g, &batch, is_mean, is_sd, &po, nullptr)) return die("aligning the pairs");
+    phase("pairs aligned on the GPU");
+    hlala_truth_t* truth = nullptr;
+    if (hlala_truth_load(l1.c_str(), l2.c_str(), &truth)) return die("reading the true levels");
+    if (hlala_truth_evaluate(truth, np, names, 0, &po, nullptr)) return die("comparing with the true levels");
+    int64_t tot[3]; hlala_truth_totals(truth, tot);
+    phase("alignments compared with the true levels");
+    fprintf(stdout, "hlala-b200: %lld pairs simulated, %lld placed with both mates, %lld dropped\n", (long long)n_sim, (long long)np, (long long)counts[3]);
+    fprintf(stdout, "\tGraph: %lld %g\n", (long long)tot[0], tot[0] ? (double)tot[1] / (double)tot[0] : 0.0);     // the line of HLA-LA.cpp:1258
+    fprintf(stdout, "\tReads with less than 90 %% of their bases on the true level: %lld\n", (long long)tot[2]);
+    hlala_truth_free(truth); hlala_bam_batch_free(bam); hlala_graph_free(g);
     return 0;
 }
 static int run_long_reads(std::map<std::string, std::string>& a);
@@ -226,7 +277,8 @@ int main(int argc, char** argv) {
     std::map<std::string, std::string> a;
     // the argument surface of the reference binary (HLA-LA.cpp:60-92 collects --key value pairs; HLA-LA.pl:563 passes the keys below) plus this program's own
     static const char* const known[] = {"action", "sampleID", "BAM", "outputDirectory", "PRG_graph_dir", "trueHLA", "maxThreads", "threads", "insertSizeMean", "insertSizeSD", "device", "gpus", "maxColumns",
-                                        "hla_nom_g_dir", "bwa_bin", "samtools_bin", "FASTQ1", "FASTQ2", "FASTQU", "longReads", "mapAgainstCompleteGenome", "remap_with_a", "workingDir", "graph"};
+                                        "hla_nom_g_dir", "bwa_bin", "samtools_bin", "FASTQ1", "FASTQ2", "FASTQU", "longReads", "mapAgainstCompleteGenome", "remap_with_a", "workingDir", "graph",
+                                        "qualityMatrixFile", "haploidCoverage", "seed"};
     if ((argc - 1) % 2 != 0) { fprintf(stderr, "hlala-b200: arguments come as --key value pairs; '%s' has no value\n", argv[argc - 1]); return 2; }
     for (int i = 1; i + 1 < argc; i += 2) {
         if (strncmp(argv[i], "--", 2) != 0) { fprintf(stderr, "hlala-b200: bad argument %s\n", argv[i]); return 2; }
@@ -245,6 +297,7 @@ int main(int argc, char** argv) {
         return 2;
     }
     if (from_fastq && a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "") { fprintf(stderr, "hlala-b200: --longReads takes a --BAM (bwa mem -x ont2d|pacbio)\n"); return 2; }
+    if (a["action"] == "testPRGMapping") return run_test_prg_mapping(a);
     const bool long_reads = a.count("longReads") && a["longReads"] != "0" && a["longReads"] != "";
     if (long_reads && a["longReads"] != "ont2d" && a["longReads"] != "pacbio") { fprintf(stderr, "hlala-b200: --longReads must be 0, ont2d or pacbio\n"); return 2; }     // HLA-LA.cpp:759
     if (a["action"] == "prepareGraph" && a.count("PRG_graph_dir")) {
@@ -265,6 +318,7 @@ int main(int argc, char** argv) {
                         "       hlala-b200 --action HLA --sampleID <id> --FASTQ1 <R1.fq[.gz]> --FASTQ2 <R2.fq[.gz]> --outputDirectory <dir> --PRG_graph_dir <dir>   (reads placed on the PRG contigs here, no bwa)\n"
                         "       hlala-b200 --action prepareGraph --PRG_graph_dir <dir>\n"
                         "       hlala-b200 --action testBinary\n"
+                        "       hlala-b200 --action testPRGMapping --PRG_graph_dir <dir> --outputDirectory <dir> --qualityMatrixFile <file>   (simulated reads -> placed -> aligned -> bases on their true level)\n"
                         "       [--longReads ont2d|pacbio]  (the BAM then holds single long reads: bwa mem -x ont2d|pacbio)\n"
                         "       [--insertSizeMean <m> --insertSizeSD <s>] [--device <n> | --gpus <N>] [--maxColumns <n>] [--maxThreads <n>] [--trueHLA <file>]\n");
         return 2;

@@ -17,15 +17,16 @@ import harness as H  # noqa: E402
 REF_MATRIX = "/root/reference/simulator/predefinedQualityMatrices/I101_NA12878.txt"
 
 
-def synthetic_matrix(path, lengths=(101,), seed=3):
-    """quality classes with position-dependent counts and, unlike the file the reference ships, rows of quality character 0 (insertion / deletion counts)"""
+def synthetic_matrix(path, lengths=(101,), seed=3, accurate=False):
+    """quality classes with position-dependent counts and, unlike the file the reference ships, rows of quality character 0 (insertion / deletion counts);
+    accurate: mostly high qualities (about 1 % errors, like a sequencing run) instead of about 15 %"""
     rng = np.random.RandomState(seed)
     with open(path, "wb") as f:
         f.write(b"readLength\tqualityScore\tpositionInRead\tN\tExpectedCorrect\tEmpiricalCorrect\n")
         for L in lengths:
             for pos in range(L):
-                for q, acc in ((b"#", 0.55), (b"+", 0.9), (b"5", 0.99), (b"?", 0.999), (b"I", 0.9999)):
-                    n = int(rng.randint(0 if q == b"+" else 50, 5000))
+                for qi, (q, acc) in enumerate(((b"#", 0.55), (b"+", 0.9), (b"5", 0.99), (b"?", 0.999), (b"I", 0.9999))):
+                    n = int(rng.randint(0 if q == b"+" else 50, 5000)) * ((1, 2, 20, 200, 400)[qi] if accurate else 1)
                     f.write(b"%d\t%s\t%d\t%d\t%.6f\t%.9f\n" % (L, q, pos, n, acc, acc - rng.rand() * 0.01))
                 if pos % 3 != 1 and pos > 0:   # no counts at position 0: with includeDeletions a read starting in a deletion trips an assert of the reference (:1654)
                     f.write(b"%d\t\x00\t%d\t%d\t0\t0\n" % (L, pos, int(rng.randint(2, 40))))

@@ -145,3 +145,35 @@ def test_insert_size_estimate_from_mapped_fastq(tmp_path):
     mean, sd, used, skipped = P.insert_size_from_levels(fl, ll, ((sample["chain_flag"] & 0x10) != 0).astype(np.uint8), loaded)
     assert abs(mean - 180) <= 6 and 15 <= sd <= 35 and used >= 1900, (mean, sd, used, skipped)
     P.close()
+
+
+def test_test_prg_mapping_action_arguments(dataset, tmp_path):
+    """--action testPRGMapping (the reference's synthetic integration test, HLA-LA.cpp:1386-1621): argument check, and a loud failure where there is no GPU"""
+    r = subprocess.run([H.CLI, "--action", "testPRGMapping", "--PRG_graph_dir", "x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "usage: hlala-b200 --action testPRGMapping" in r.stderr
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    d, _b, _mu, _sd = dataset("small")
+    r = subprocess.run([H.CLI, "--action", "testPRGMapping", "--PRG_graph_dir", d, "--outputDirectory", str(tmp_path / "o"), "--qualityMatrixFile", "none.txt"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "uploading the PRG" in r.stderr
+
+
+@pytest.mark.gpu
+def test_test_prg_mapping_action_on_the_gpu(dataset, tmp_path):
+    """reads with known levels from a random genome of the graph -> placed on the contigs -> aligned on the GPU -> compared with their true levels: the figure the
+    reference prints as "Graph: <bases> <fraction>" (HLA-LA.cpp:1258). The same flow with the oracle's alignments on the CPU gives 0.994 on this PRG."""
+    import simulator_ref_compare as S
+    d, _b, _mu, _sd = dataset("S")
+    mat = str(tmp_path / "m.txt"); S.synthetic_matrix(mat, accurate=True)
+    r = subprocess.run([H.CLI, "--action", "testPRGMapping", "--PRG_graph_dir", d, "--outputDirectory", str(tmp_path / "o"), "--qualityMatrixFile", mat, "--seed", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("\tGraph: ")]
+    assert len(line) == 1, r.stdout[-2000:]
+    total, frac = line[0].split()[1:]
+    assert int(total) > 100000 and float(frac) >= 0.985, line
