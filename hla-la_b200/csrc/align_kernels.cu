@@ -549,6 +549,12 @@ cudaError_t launch_pair(const PairParams& P, int n_sm, cudaStream_t stream) {
 size_t dp_thread_scratch_bytes() { return dp_scratch_bytes(); }
 int dp_ext_cap() { return DP_EXT_CAP; }
 
+__global__ void k_exp_probe(const double* x, double* y, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = exp_like_host_libm(x[i]); }
+cudaError_t launch_exp_probe(const double* x, double* y, int n, cudaStream_t stream) {
+    if (n > 0) k_exp_probe<<<(n + 255) / 256, 256, 0, stream>>>(x, y, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_export_chain_columns(const DevGraph& G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
                                         const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar, cudaStream_t stream) {
     if (n_chains <= 0) return cudaSuccess;

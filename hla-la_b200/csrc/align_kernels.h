@@ -32,4 +32,7 @@ int dp_ext_cap();
 cudaError_t launch_export_chain_columns(const DevGraph& G, int n_chains, int maxcol, const int32_t* n_cols, const int32_t* first_level,
                                         const int32_t* c_edge, int32_t* out_level, int32_t* out_edge_ord, uint8_t* out_gchar, cudaStream_t stream);
 
+// parity hook: y[i] = exp_like_host_libm(x[i]) (exp_libm.cuh), the exp of the mapping-quality posteriors
+cudaError_t launch_exp_probe(const double* x, double* y, int n, cudaStream_t stream);
+
 } // namespace hlala

@@ -1095,6 +1095,18 @@ int64_t hlala_simulate_read_pairs(const char* matrix, int32_t read_length, int32
     return rc == 0 ? n : rc;
 }
 
+int hlala_exp_probe(int device, int64_t n, const double* x, double* y) {
+    if (n < 0 || n > (1 << 30) || (n && (!x || !y))) return fail(HLALA_E_ARG, "hlala_exp_probe: bad argument");
+    return guarded([&]() {
+        int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(HLALA_E_CUDA, "no CUDA device available");
+        CUDA_OK(cudaSetDevice(device));
+        DevBuf dx, dy; dx.upload(x, (size_t)n); dy.alloc((size_t)n * 8);
+        CUDA_OK(launch_exp_probe(dx.as<double>(), dy.as<double>(), (int)n, 0));
+        dy.download(y, (size_t)n); CUDA_OK(cudaStreamSynchronize(0));
+        return 0;
+    });
+}
+
 int64_t hlala_simulate_from_graph(const hlala_graph_t* g, const char* graph_label, const char* matrix, int32_t read_length, double is_mean, double is_sd, int32_t n_genomes,
                                   const char* out_dir, double coverage, int32_t with_error, uint32_t seed) {
     if (!g || !matrix || !out_dir || read_length <= 0 || n_genomes < 0) return fail(HLALA_E_ARG, "hlala_simulate_from_graph: bad argument");

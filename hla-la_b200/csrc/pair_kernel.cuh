@@ -13,6 +13,7 @@
 // sums run in the reference's order (combination index ascending) so that they round identically.
 #pragma once
 #include "chain_params.h"
+#include "exp_libm.cuh"
 #include <cuda_runtime.h>
 
 namespace hlala {
@@ -188,7 +189,7 @@ template <class CFG, bool FROM_LIST, bool UNPAIRED> __global__ void __launch_bou
         double mapq = 1, mq1 = 1, mq2 = 1;
         if (nc > 1) {
             // ---- posteriors (processBAM.cpp:4070-4123)
-            for (int i = lane; i < nc; i += 32) S.ll[i] = exp(S.ll[i] - best);
+            for (int i = lane; i < nc; i += 32) S.ll[i] = exp_like_host_libm(S.ll[i] - best);   // the host libm's exp bit for bit (exp_libm.cuh): these terms decide between phred 255 and 190
             __syncwarp();
             double sum = 0;
             if (lane == 0) { for (int i = 0; i < nc; i++) sum += S.ll[i]; }

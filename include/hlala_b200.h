@@ -237,6 +237,10 @@ int hlala_typer_timing(const hlala_typer_t* t, double ms[2], int launches[2], do
 int hlala_typing_pair_probe(int device, int32_t C, int32_t R, const double* ll, const int32_t* mism, int termwise,
                             double* pair_ll, double* pair_mavg, double* pair_mmin, double* kernel_ms);
 
+/* Parity hook for the one transcendental the alignment path evaluates on the device: the exp of the mapping-quality posteriors (processBAM.cpp:4074), computed as
+ * the host's libm computes it (glibc's table algorithm in the operation order of its x86-64 FMA build, hla-la_b200/csrc/exp_libm.cuh). y[i] = that exp(x[i]), on `device`. */
+int hlala_exp_probe(int device, int64_t n, const double* x, double* y);
+
 /* Evaluation of the inferred types against known ones: what `--action HLA ... --trueHLA <file>` runs after the inference (HLA-LA.cpp:801-810):
  *   hla::HLATyper::read_inferred_types(sampleID, inferred, R1_bestguess.txt)   hla/HLATyper.cpp:580-626
  *   hla::HLATyper::read_true_types(truth, file)                                 hla/HLATyper.cpp:628-688
