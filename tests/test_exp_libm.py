@@ -36,3 +36,38 @@ def test_device_exp_equals_the_hosts_libm():
     bad = np.nonzero(y[main].view(np.uint64) != want[main].view(np.uint64))[0]
     assert len(bad) == 0, "%d of %d differ, first at x = %r: device %r, libm %r" % (len(bad), main.sum(), x[main][bad[0]], y[main][bad[0]], want[main][bad[0]])
     assert np.allclose(y[~main], want[~main], rtol=1e-12, atol=0)
+
+
+def _fixture(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(H.REPO, "tests", "golden"))
+    from make_exp_lastbit import PRG_KW
+    gold = np.load(os.path.join(H.REPO, "tests", "golden", "exp_lastbit_pairs.npz"))
+    d = str(tmp_path / "prg"); H.synth_prg(d, **PRG_KW)
+    return d, gold, {k[3:]: gold[k] for k in gold.files if k.startswith("in_")}
+
+
+def _same_as_gold(got, gold):
+    pack = lambda cols, n: np.concatenate([cols[r, :n[r]] for r in range(len(n))])
+    assert np.array_equal(got["n_cols"], gold["n_cols"])
+    for k in ("level", "edge", "gchar", "schar", "from_seed", "mapq"):
+        assert np.array_equal(pack(got[k], got["n_cols"]), gold[k]), k
+    assert np.allclose(got["pair_mapq"], gold["pair_mapq"], rtol=0, atol=1e-12) and np.allclose(got["read_mapq"], gold["read_mapq"], rtol=0, atol=1e-12)
+
+
+def test_last_bit_fixture_on_the_oracle(tmp_path):
+    """the five pairs of tests/golden/exp_lastbit_pairs.npz (expected values from the compiled reference): the restatement agrees, and the read in question has the pattern
+    that makes the last bit visible: 110 columns of phred 255 (posteriors summing to exactly 1) next to 3 columns two of its four chains do not share"""
+    d, gold, b = _fixture(tmp_path)
+    _same_as_gold(H.quiet(H.Oracle(d).pairs, b, 100.0, 10.0, 640), gold)
+    n = gold["n_cols"]; q = gold["mapq"][int(n[:4].sum()):int(n[:5].sum())]
+    assert int((q == 255).sum()) == 110 and int((q == 38).sum()) == 3
+
+
+@pytest.mark.gpu
+def test_last_bit_fixture_on_the_gpu(tmp_path):
+    """with CUDA's own exp() the 110 columns came out as phred 190 (profiles/r02_gpu_tests_before_exp_fix.log)"""
+    d, gold, b = _fixture(tmp_path)
+    P = H.Product(d); P.to_gpu(0)
+    _same_as_gold(P.pairs(b, 100.0, 10.0, 640, want_levels=False), gold)
+    P.close()
