@@ -53,8 +53,8 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
     const int64_t cb = g_.contig_off[(size_t)contig], clen = g_.contig_off[(size_t)contig + 1] - cb;
     const uint8_t* ref = g_.contig_seq.data() + cb;
     const int go = p_.gap_open + p_.gap_extend, ge = p_.gap_extend;
-    // Most placements have no gap at all: the best clipped stretch of the diagonal itself (one pass). It is taken as it stands when it holds at most two mismatches
-    // and the whole read lies on the contig: a gapped alignment would have to win back a gap (7 or more) from at most two mismatches (4 each) plus a clipped end.
+    // Most placements have no gap at all: the best stretch of the diagonal itself (one pass). It is taken as it stands when it spans the whole read with at most six
+    // scattered mismatches (SNPs against another haplotype, sequencing errors): a gap (7 or more) cannot win that back. Everything else goes through the banded alignment.
     if (diag >= 0 && diag + len <= clen) {
         int run = NEG, run_start = 0, run_mm = 0, ub = NEG, ub_s = 0, ub_e = 0, ub_mm = 0;
         for (int i = 0; i < len; i++) {
@@ -67,7 +67,7 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
                 if (eq && (fin > ub || (fin == ub && i > ub_e))) { ub = fin; ub_s = run_start; ub_e = i; ub_mm = run_mm; }
             }
         }
-        if (ub > NEG / 2 && (ub_mm <= 2 || (ub_s == 0 && ub_e == len - 1 && ub_mm <= 6))) {   // ... or it spans the whole read with a few scattered mismatches (SNPs against another haplotype)
+        if (ub > NEG / 2 && ub_s == 0 && ub_e == len - 1 && ub_mm <= 6) {   // only when it spans the whole read: a clipped stretch may be one side of an insertion or deletion
             const int raw = ub + (ub_s > 0 ? p_.clip : 0) + (ub_e < len - 1 ? p_.clip : 0);
             if (raw < p_.min_score) return false;
             out.contig = contig; out.pos = (int32_t)(diag + ub_s); out.score = raw; out.cigar.clear();
@@ -203,6 +203,7 @@ std::vector<FqRead> read_fastq(const std::string& path) {
         if (h[0] != '@' || !line(s) || !line(p) || !line(q) || p.empty() || p[0] != '+' || s.size() != q.size()) { gzclose(f); throw std::runtime_error(path + ": malformed FASTQ record near " + h.substr(0, 60)); }
         FqRead r; size_t e = h.find_first_of(" \t"); r.name = h.substr(1, e == std::string::npos ? std::string::npos : e - 1);
         if (r.name.size() > 2 && r.name[r.name.size() - 2] == '/' && (r.name.back() == '1' || r.name.back() == '2')) r.name.resize(r.name.size() - 2);
+        for (char& c : s) if (c >= 'a' && c <= 'z') c = (char)(c - 32);   // soft-masked bases are bases
         r.seq = s; r.qual = q; out.push_back(std::move(r));
     }
     gzclose(f);

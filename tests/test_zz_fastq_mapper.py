@@ -177,3 +177,47 @@ def test_test_prg_mapping_action_on_the_gpu(dataset, tmp_path):
     assert len(line) == 1, r.stdout[-2000:]
     total, frac = line[0].split()[1:]
     assert int(total) > 100000 and float(frac) >= 0.985, line
+
+
+def test_placements_of_constructed_reads(dataset, tmp_path):
+    """reads cut from a contig with one known difference each: the placement, CIGAR and score (bwa mem's defaults: 1 / -4 / gap 6 + 1 per base / clipping 5) are the expected
+    ones, the oracle and the compiled reference take the batch and agree on it"""
+    d, _b, _mu, _sd = dataset("small")
+    P = H.Product(d); seq = P.array("contig_seq"); off = P.array("contig_off")
+    c0 = bytes(seq[off[0]:off[1]]).decode(); L0 = len(c0)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    rc = lambda s: "".join(comp[c] for c in reversed(s))
+    other = lambda ch: "ACGT"[("ACGT".index(ch) + 1) % 4] if ch in "ACGT" else ch
+    cases = [  # name, first read, second read (sequenced from the other strand), expected (pos, score, CIGAR) of the first read's primary, of the second read's
+        ("n_in_middle", c0[300:350] + "N" + c0[351:400], rc(c0[600:700]), (300, 95, "100M"), (600, 100, "100M")),
+        ("lowercase", c0[1000:1100].lower(), rc(c0[1300:1400]), (1000, 100, "100M"), (1300, 100, "100M")),
+        ("short_mate", c0[2000:2100], rc(c0[2300:2315]), None, None),                                       # 15 bases cannot be placed: the pair is dropped
+        ("unequal", c0[2500:2600], rc(c0[2800:2860]), (2500, 100, "100M"), (2800, 60, "60M")),
+        ("contig_start", "ACGTACGTAC" + c0[0:90], rc(c0[300:400]), (0, 90, "10S90M"), (300, 100, "100M")),
+        ("contig_end", c0[L0 - 400:L0 - 300], rc(c0[L0 - 90:L0] + "GATTACAGAT"), (L0 - 400, 100, "100M"), (L0 - 90, 90, "90M10S")),
+        ("deletion", c0[3000:3050] + c0[3056:3106], rc(c0[3400:3500]), (3000, 88, "50M6D50M"), (3400, 100, "100M")),
+        ("insertion", c0[3600:3650] + "GATTA" + c0[3650:3695], rc(c0[3900:4000]), (3600, 84, "50M5I45M"), (3900, 100, "100M")),
+        ("mismatches", "".join(other(ch) if i % 23 == 5 else ch for i, ch in enumerate(c0[4200:4300])), rc(c0[4500:4600]), (4200, 75, "100M"), (4500, 100, "100M")),
+    ]
+    f1, f2 = str(tmp_path / "a_1.fq"), str(tmp_path / "a_2.fq")
+    with open(f1, "w") as a, open(f2, "w") as b:
+        for n, x, y, _e1, _e2 in cases:
+            a.write("@%s/1\n%s\n+\n%s\n" % (n, x, "I" * len(x))); b.write("@%s/2\n%s\n+\n%s\n" % (n, y, "I" * len(y)))
+    mb, names, cnt = P.fastq_map(f1, f2)
+    assert names == sorted(n for n, *_ in cases if n != "short_mate") and cnt["incomplete"] == 1
+    for n, _x, _y, e1, e2 in cases:
+        if e1 is None:
+            continue
+        p_ = names.index(n)
+        for m, e in ((0, e1), (1, e2)):
+            r = 2 * p_ + m
+            prim = [c for c in range(mb["chain_off"][r], mb["chain_off"][r + 1]) if not mb["chain_flag"][c] & 0x100][0]
+            cig = "".join("%d%s" % (x >> 4, "MIDNSHP=X"[x & 15]) for x in mb["cigar"][mb["cigar_off"][prim]:mb["cigar_off"][prim + 1]])
+            assert (int(mb["chain_pos"][prim]), int(mb["chain_as"][prim]), cig) == e and mb["chain_contig"][prim] == 0, (n, m, mb["chain_pos"][prim], mb["chain_as"][prim], cig)
+            assert bool(mb["chain_flag"][prim] & 0x10) == (m == 1)
+    assert not (mb["bases"] >= ord("a")).any()
+    want = H.oracle_pairs(d, mb, 200.0, 50.0, 640)
+    rest = H.quiet(H.Oracle(d).pairs, mb, 200.0, 50.0, 640)
+    for k in ("n_cols", "level", "schar", "mapq"):
+        assert np.array_equal(want[k], rest[k]), k
+    P.close()
