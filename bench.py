@@ -294,6 +294,37 @@ def stage_long_reads(args, root, H):
     return out
 
 
+def stage_fastq_mapper(args, root, H):
+    """paired FASTQ files -> hlala_fastq_map_pairs (host code: k-mer votes per contig and diagonal, banded alignment with bwa mem's default scores, all
+    placements) -> hlala_align_pairs on the GPU -> bases on their true level (hlala_truth_evaluate), next to the same figure for the generator's own seeds. There is no
+    reference arm: the reference calls bwa here, which is an external program."""
+    d = small_prg(args, root)
+    n = args.fastq_pairs
+    pre = os.path.join(d, "fq_stage_R")
+    b = H.synth_reads(d, os.path.join(d, "fq_stage.bin"), pairs=n, len=args.read_len, clip_frac=0.15, seed=0xB200 + 7, levels_prefix=pre)
+    P = H.Product(d); ts = []
+    for _ in range(2):
+        t = time.perf_counter(); mb, names, cnt = P.fastq_map(pre + "_1.fq", pre + "_2.fq"); ts.append(time.perf_counter() - t)
+    levels, genes, alleles = sample_dims(args)
+    out = dict(workload="%d pairs of 2 x %d bp as FASTQ, PRG of %d levels / %d haplotypes / %d gene block(s) x %d alleles (%d contig bases)" % (n, args.read_len, levels, args.haps, genes, alleles, int(P.array("contig_off")[-1])),
+               host_threads=os.cpu_count(), map_call_s=min(ts), reads_per_s=2 * n / min(ts), pairs_placed=len(names), pairs_with_an_unplaced_mate=int(cnt["incomplete"]),
+               placements_per_read=len(mb["chain_contig"]) / float(max(1, len(mb["read_off"]) - 1)), generator_chains_per_read=len(b["chain_contig"]) / float(len(b["read_off"]) - 1))
+    try:
+        P.to_gpu(int(os.environ.get("LOCAL_RANK", "0")))
+        k = min(len(names), 8000)            # the accuracy figure on a slice: the columns of every read come back to the host for the comparison
+        sub = H.subset_pairs(mb, np.arange(k)); t = time.perf_counter(); aln = P.pairs(sub, args.is_mean, args.is_sd, cap=args.max_columns, want_levels=False); out["align_slice_s"] = time.perf_counter() - t
+        _per, tot, _n = H.truth_evaluate(aln, pre + "_1.levels", pre + "_2.levels", names=names[:k])
+        out.update(slice_pairs=k, bases_on_true_level_mapper_seeds=float(tot[1]) / float(tot[0]), reads_below_90_percent=int(tot[2]))
+        idx = np.array([int(x[1:]) for x in names[:k]])
+        aln = P.pairs(H.subset_pairs(b, idx), args.is_mean, args.is_sd, cap=args.max_columns, want_levels=False)
+        _per, tot, _n = H.truth_evaluate(aln, pre + "_1.levels", pre + "_2.levels", names=names[:k])
+        out["bases_on_true_level_generator_seeds"] = float(tot[1]) / float(tot[0])
+    except Exception as e:
+        out["gpu_error"] = str(e)[:300]
+    P.close()
+    return out
+
+
 def strong_scaling_leg(args, H, P, prg_dir, rank, local_rank, world, dist, torch, n_levels, batch=None):
     """BASELINE.json configs[2] on N GPUs: --strong-pairs pairs in total, sharded by pair across the ranks (graph replicated). Timed per rank, max over ranks:
     alignment of the shard (columns kept) -> all-reduce of the per-level coverage -> extraction of the gene-overlapping pairs -> all-gather of those (small)
@@ -369,6 +400,7 @@ def main():
     ap.add_argument("--max-columns", type=int, default=0, help="columns per alignment; 0 = 640 up to 150 bp reads (the headline), 4 x read length + 64 beyond (rare alignments span gap stretches of hundreds of levels)")
     ap.add_argument("--cpu-pairs", type=int, default=6000)
     ap.add_argument("--cpu-levels", type=int, default=294118, help="levels of the reference arm's PRG slice (default: levels / genes = one gene block, the bench PRG's density)")
+    ap.add_argument("--fastq-pairs", type=int, default=20000, help="pairs of the FASTQ mapper stage (host code in front of the GPU path)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--stages", type=int, default=1, help="also time the k-mer seeding and typing stages (rank 0, N=1 only)")
     ap.add_argument("--long-reads", type=int, default=50000, help="reads of the long-read stage (BASELINE.json configs[3]: 50 k x 8 kb)")
@@ -628,7 +660,7 @@ def main():
     stages = None
     if args.stages and n_gpus == 1:
         stages = {}
-        for nm, fn in (("kmer_seeding", stage_kmer_seeding), ("typing", stage_typing), ("long_reads", stage_long_reads)):
+        for nm, fn in (("kmer_seeding", stage_kmer_seeding), ("typing", stage_typing), ("long_reads", stage_long_reads), ("fastq_mapper", stage_fastq_mapper)):
             try:
                 stages[nm] = fn(args, root, H)
             except Exception as e:   # a stage measurement must not cost the headline line
