@@ -1345,7 +1345,11 @@ int hlala_fastq_map_pairs(const hlala_graph_t* g, const char* fastq1, const char
     *out = nullptr;
     return guarded([&]() {
         std::unique_ptr<hlala_bam_batch> B(new hlala_bam_batch());
-        map_fastq_pairs(g->h, fastq1, fastq2, threads, MapperParams(), B->b);
+        MapperParams mp;   // tuning hooks for experiments (defaults are what the tests and the profile describe)
+        if (const char* e = getenv("HLALA_MAPPER_READ_STEP")) mp.read_step = std::max(1, atoi(e));
+        if (const char* e = getenv("HLALA_MAPPER_REF_STEP")) mp.ref_step = std::max(1, atoi(e));
+        if (const char* e = getenv("HLALA_MAPPER_K")) mp.k = atoi(e);
+        map_fastq_pairs(g->h, fastq1, fastq2, threads, mp, B->b);
         B->names.reserve(B->b.pair_name.size()); for (const std::string& n : B->b.pair_name) B->names.push_back(n.c_str());
         *out = B.release(); return 0;
     });

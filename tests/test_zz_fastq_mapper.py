@@ -53,9 +53,10 @@ def test_mapped_fastq_reaches_the_accuracy_of_the_generators_seeds(dataset, tmp_
     assert same >= 0.99 * npairs
     O = H.Oracle(d)
     aln = H.quiet(O.pairs, mb, mu, sd, 1024)
-    ref = H.oracle_pairs(d, mb, mu, sd, 1024)      # the compiled reference where oracle/_ref is built: the mapper's batches are new ground for the restatement too
-    for k in ("n_cols", "level", "edge", "schar", "mapq", "read_reverse"):
-        assert np.array_equal(aln[k], ref[k]), "restatement and %s differ in %s" % (ref["oracle"], k)
+    if H.have_ref():      # the compiled reference (a process of its own: one graph per process): the mapper's batches are new ground for the restatement too
+        ref = H._ref_subprocess(d, mb, mu, sd, 1024, "pairs")
+        for k in ("n_cols", "level", "edge", "schar", "mapq", "read_reverse"):
+            assert np.array_equal(aln[k], ref[k]), "restatement and compiled reference differ in %s" % k
     got = _fraction(aln, pre, names)
     want = _fraction(H.quiet(O.pairs, b, mu, sd, 1024), pre, None)
     assert got >= floor and got >= want - 0.004, "bases on their true level: %.4f with the mapper's seeds, %.4f with the generator's" % (got, want)
@@ -106,7 +107,10 @@ def test_gpu_alignment_of_mapped_fastq_equals_the_oracle_and_keeps_the_accuracy(
     d, b, mu, sd, pre, P, mb, names, cnt = _mapped(dataset, "S", tmp_path)
     P.to_gpu(0)
     got = P.pairs(mb, mu, sd, 1024)
-    want = H.oracle_pairs(d, mb, mu, sd, 1024)
+    try:
+        want = H.oracle_pairs(d, mb, mu, sd, 1024)
+    except RuntimeError:      # a compiled-reference graph opened outside the harness cache earlier in this process: use a process of its own
+        want = H._ref_subprocess(d, mb, mu, sd, 1024, "pairs")
     from test_gpu_parity import assert_pairs_equal
     assert_pairs_equal(got, want)
     assert _fraction(got, pre, names) >= 0.985
@@ -220,8 +224,10 @@ def test_placements_of_constructed_reads(dataset, tmp_path):
             assert (int(mb["chain_pos"][prim]), int(mb["chain_as"][prim]), cig) == e and mb["chain_contig"][prim] == 0, (n, m, mb["chain_pos"][prim], mb["chain_as"][prim], cig)
             assert bool(mb["chain_flag"][prim] & 0x10) == (m == 1)
     assert not (mb["bases"] >= ord("a")).any()
-    want = H.oracle_pairs(d, mb, 200.0, 50.0, 640)
     rest = H.quiet(H.Oracle(d).pairs, mb, 200.0, 50.0, 640)
-    for k in ("n_cols", "level", "schar", "mapq"):
-        assert np.array_equal(want[k], rest[k]), k
+    assert (rest["n_cols"] >= np.diff(mb["read_off"])).all()
+    if H.have_ref():
+        want = H._ref_subprocess(d, mb, 200.0, 50.0, 640, "pairs")
+        for k in ("n_cols", "level", "schar", "mapq"):
+            assert np.array_equal(want[k], rest[k]), k
     P.close()
