@@ -1,12 +1,12 @@
 // FASTQ -> seed batch without bwa: stands where the reference runs `bwa mem -a -M <PRG>/mapping_PRGonly/referenceGenome.fa R1 R2`
 // (mapper/bwa/BWAmapper.cpp map(), called at HLA-LA.cpp:742-779) and reads the result back through extractSeeds2. Like bwa it maps every read against
-// the PRG's linear contigs (haplotypes and allele sequences of sequences.txt) and reports ALL placements (-a), the best one as the primary record, the
+// the PRG's linear contigs (haplotypes and allele sequences of sequences.txt) and reports all placements (-a; here the 64 best-scoring ones of a read at most), the best one as the primary record, the
 // others as secondary ones (protoSeeds.cpp:252-314 relies on exactly one primary per mate), each with a CIGAR and a bwa-style score
 // (match 1, mismatch 4, gap open 6 + extend 1, clipping 5, minimum score 30: bwa mem's defaults) that plays the part of the AS tag (processBAM.cpp:4314-4336).
 // Method: sampled k-mer index of the contigs, votes per (contig, strand, diagonal), banded affine-gap alignment of every candidate with free, penalised
 // clipping at either end. It is NOT bwa: there is no oracle for it (bwa is an external program and absent here), placements and scores of hard cases
 // may differ. What is measured instead is what the reference's own testPRGMapping measures: bases of simulated reads on their true level after the
-// full alignment path (tests/test_fastq_mapper.py). Host code (threads); a CUDA version of the voting + banded alignment is the natural next step.
+// full alignment path (tests/test_zz_fastq_mapper.py). Host code (threads); a CUDA version of the voting + banded alignment is the natural next step.
 #pragma once
 #include <cstdint>
 #include <string>
