@@ -78,30 +78,36 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
         }
     }
     // cell (i, b): read base i against contig position j = diag + i + b - B. A narrow band first; the full one only if the narrow alignment leans on the band's edge.
-    static thread_local std::vector<int32_t> M, E, F; static thread_local std::vector<uint8_t> tb;
+    static thread_local std::vector<int32_t> M, E, F; static thread_local std::vector<uint8_t> tb, rcode;
+    // contig codes of the widest window once (9 = beyond the contig: such cells stay unreachable)
+    const int BW = p_.band; rcode.resize((size_t)len + 2 * (size_t)BW);
+    for (int64_t q = 0; q < (int64_t)rcode.size(); q++) { const int64_t j = diag - BW + q; rcode[(size_t)q] = (j >= 0 && j < clen) ? (uint8_t)code_of(ref[j]) : (uint8_t)9; }
   for (int attempt = 0; attempt < 2; attempt++) {
-    const int B = attempt == 0 ? std::max(4, p_.band / 3) : p_.band, Wd = 2 * B + 1; bool edge = false;
-    M.assign((size_t)2 * Wd, NEG); E.assign((size_t)2 * Wd, NEG); F.assign((size_t)2 * Wd, NEG);
+    const int B = attempt == 0 ? std::max(4, p_.band / 3) : p_.band, Wd = 2 * B + 1, Ws = Wd + 2; bool edge = false;   // rows carry one unreachable cell at either end
+    M.assign((size_t)2 * Ws, NEG); E.assign((size_t)2 * Ws, NEG); F.assign((size_t)2 * Ws, NEG);
     tb.assign((size_t)len * Wd, 0);   // bits 0-1: M came from 0 start, 1 M, 2 E, 3 F; bit 2: E extended; bit 3: F extended
     int best = NEG, best_i = -1, best_b = -1;
+    const int mt = p_.match, mm = -p_.mismatch, clipc = p_.clip;
     for (int i = 0; i < len; i++) {
-        int32_t* Mc = &M[(size_t)(i & 1) * Wd]; int32_t* Ec = &E[(size_t)(i & 1) * Wd]; int32_t* Fc = &F[(size_t)(i & 1) * Wd];
-        const int32_t* Mp = &M[(size_t)((i & 1) ^ 1) * Wd]; const int32_t* Ep = &E[(size_t)((i & 1) ^ 1) * Wd]; const int32_t* Fp = &F[(size_t)((i & 1) ^ 1) * Wd];
-        const int start = i == 0 ? 0 : -p_.clip;
+        int32_t* Mc = &M[(size_t)(i & 1) * Ws] + 1; int32_t* Ec = &E[(size_t)(i & 1) * Ws] + 1; int32_t* Fc = &F[(size_t)(i & 1) * Ws] + 1;
+        const int32_t* Mp = &M[(size_t)((i & 1) ^ 1) * Ws] + 1; const int32_t* Ep = &E[(size_t)((i & 1) ^ 1) * Ws] + 1; const int32_t* Fp = &F[(size_t)((i & 1) ^ 1) * Ws] + 1;
+        const int start = i == 0 ? 0 : -clipc, endc = i == len - 1 ? 0 : -clipc;
+        const uint8_t* rc = rcode.data() + (BW - B) + i;   // rc[b] = code of contig position diag + i + b - B
+        const uint8_t ri = rd[i]; uint8_t* trow = tb.data() + (size_t)i * Wd;
         for (int b = 0; b < Wd; b++) {
-            const int64_t j = diag + i + b - B;
-            uint8_t t = 0; int m = NEG, e = NEG, f = NEG;
-            if (j >= 0 && j < clen) {
-                const int rc = code_of(ref[j]); const int s = (rd[i] < 4 && rd[i] == rc) ? p_.match : -p_.mismatch;
-                int from = start, which = 0;
-                if (i > 0) { if (Mp[b] > from) { from = Mp[b]; which = 1; } if (Ep[b] > from) { from = Ep[b]; which = 2; } if (Fp[b] > from) { from = Fp[b]; which = 3; } }
-                m = from + s; t = (uint8_t)which;
-                if (b > 0) { const int o = Mc[b - 1] - go, x = Ec[b - 1] - ge; if (x > o) { e = x; t |= 4; } else e = o; }                       // deletion: contig position j consumed after read base i
-                if (i > 0 && b + 1 < Wd) { const int o = Mp[b + 1] - go, x = Fp[b + 1] - ge; if (x > o) { f = x; t |= 8; } else f = o; }         // insertion: read base i without a contig position
-                const int fin = m + (i == len - 1 ? 0 : -p_.clip);
-                if (fin > best || (fin == best && i > best_i)) { best = fin; best_i = i; best_b = b; }
-            }
-            Mc[b] = m; Ec[b] = e < NEG / 2 ? NEG : e; Fc[b] = f < NEG / 2 ? NEG : f; tb[(size_t)i * Wd + b] = t;
+            const uint8_t c = rc[b];
+            if (c == 9) { Mc[b] = NEG; Ec[b] = NEG; Fc[b] = NEG; continue; }
+            int from = start, which = 0;
+            if (Mp[b] > from) { from = Mp[b]; which = 1; }      // the row before read base 0 is all unreachable: no special case for i == 0
+            if (Ep[b] > from) { from = Ep[b]; which = 2; }
+            if (Fp[b] > from) { from = Fp[b]; which = 3; }
+            const int m = from + ((ri < 4 && ri == c) ? mt : mm);
+            uint8_t t = (uint8_t)which;
+            const int eo = Mc[b - 1] - go, ex = Ec[b - 1] - ge; int e = eo; if (ex > eo) { e = ex; t |= 4; }       // deletion: contig position consumed after read base i
+            const int fo = Mp[b + 1] - go, fx = Fp[b + 1] - ge; int f = fo; if (fx > fo) { f = fx; t |= 8; }       // insertion: read base i without a contig position
+            const int fin = m + endc;
+            if (fin > best || (fin == best && i > best_i)) { best = fin; best_i = i; best_b = b; }
+            Mc[b] = m; Ec[b] = e < NEG ? NEG : e; Fc[b] = f < NEG ? NEG : f; trow[b] = t;
         }
     }
     if (best_i < 0) { if (attempt == 0) continue; return false; }
