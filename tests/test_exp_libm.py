@@ -62,12 +62,3 @@ def test_last_bit_fixture_on_the_oracle(tmp_path):
     _same_as_gold(H.quiet(H.Oracle(d).pairs, b, 100.0, 10.0, 640), gold)
     n = gold["n_cols"]; q = gold["mapq"][int(n[:4].sum()):int(n[:5].sum())]
     assert int((q == 255).sum()) == 110 and int((q == 38).sum()) == 3
-
-
-@pytest.mark.gpu
-def test_last_bit_fixture_on_the_gpu(tmp_path):
-    """with CUDA's own exp() the 110 columns came out as phred 190 (profiles/r02_gpu_tests_before_exp_fix.log)"""
-    d, gold, b = _fixture(tmp_path)
-    P = H.Product(d); P.to_gpu(0)
-    _same_as_gold(P.pairs(b, 100.0, 10.0, 640, want_levels=False), gold)
-    P.close()

@@ -231,3 +231,13 @@ def test_placements_of_constructed_reads(dataset, tmp_path):
         for k in ("n_cols", "level", "schar", "mapq"):
             assert np.array_equal(want[k], rest[k]), k
     P.close()
+
+
+@pytest.mark.gpu
+def test_last_bit_fixture_on_the_gpu(tmp_path):
+    """with CUDA's own exp() the 110 columns came out as phred 190 (profiles/r02_gpu_tests_before_exp_fix.log)"""
+    from test_exp_libm import _fixture, _same_as_gold
+    d, gold, b = _fixture(tmp_path)
+    P = H.Product(d); P.to_gpu(0)
+    _same_as_gold(P.pairs(b, 100.0, 10.0, 640, want_levels=False), gold)
+    P.close()
