@@ -30,7 +30,8 @@ struct Vote { int32_t contig; int32_t diag; };
 ContigMapper::ContigMapper(const FlatGraph& g, const MapperParams& p) : g_(g), p_(p) {
     if (p_.k < 11 || p_.k > 31 || p_.ref_step < 1 || p_.read_step < 1 || p_.band < 4) throw std::runtime_error("ContigMapper: k in 11..31, steps >= 1, band >= 4");
     const uint64_t mask = (p_.k == 32) ? ~0ull : ((1ull << (2 * p_.k)) - 1);
-    std::vector<std::pair<uint64_t, uint32_t>> e;
+    struct Entry { uint64_t key; uint32_t pos, ctg; bool operator<(const Entry& o) const { return key != o.key ? key < o.key : pos < o.pos; } };
+    std::vector<Entry> e;
     if (g.contig_seq.size() >= (1ull << 32)) throw std::runtime_error("ContigMapper: contigs beyond 4 G bases");
     for (int32_t c = 0; c < g.n_contigs; c++) {
         const int64_t b = g.contig_off[(size_t)c], n = g.contig_off[(size_t)c + 1] - b;
@@ -40,12 +41,15 @@ ContigMapper::ContigMapper(const FlatGraph& g, const MapperParams& p) : g_(g), p
             if (cd > 3) { run = 0; key = 0; continue; }
             key = ((key << 2) | (uint64_t)cd) & mask; run++;
             const int64_t start = i - p_.k + 1;
-            if (run >= p_.k && start % p_.ref_step == 0) e.emplace_back(key, (uint32_t)(b + start));
+            if (run >= p_.k && start % p_.ref_step == 0) e.push_back(Entry{key, (uint32_t)(b + start), (uint32_t)c});
         }
     }
     std::sort(e.begin(), e.end());
-    keys_.resize(e.size()); pos_.resize(e.size());
-    for (size_t i = 0; i < e.size(); i++) { keys_[i] = e[i].first; pos_[i] = e[i].second; }
+    keys_.resize(e.size()); pos_.resize(e.size()); ctg_.resize(e.size());
+    for (size_t i = 0; i < e.size(); i++) { keys_[i] = e[i].key; pos_[i] = e[i].pos; ctg_[i] = e[i].ctg; }
+    const int bits = std::min(22, 2 * p_.k); bucket_shift_ = 2 * p_.k - bits;
+    bucket_.assign(((size_t)1 << bits) + 1, (uint32_t)e.size());
+    { size_t i = 0; for (size_t v = 0; v < ((size_t)1 << bits); v++) { while (i < e.size() && (keys_[i] >> bucket_shift_) < v) i++; bucket_[v] = (uint32_t)i; } }
 }
 
 // Banded affine-gap alignment of read[0..len) around `diag` (contig position of read base 0) on `contig`: any start and end in the read, a clipped end costs p_.clip.
@@ -154,12 +158,13 @@ std::vector<Placement> ContigMapper::map_read(const std::string& seq) const {
                 key = ((key << 2) | rd[(size_t)i]) & mask; run++;
                 const int st = i - p_.k + 1;
                 if (run < p_.k || st % p_.read_step) continue;
-                auto lo = std::lower_bound(keys_.begin(), keys_.end(), key), hi = std::upper_bound(lo, keys_.end(), key);
+                const size_t bk = (size_t)(key >> bucket_shift_);
+                auto lo = std::lower_bound(keys_.begin() + bucket_[bk], keys_.begin() + bucket_[bk + 1], key), hi = lo;
+                while (hi != keys_.end() && *hi == key) ++hi;
                 if (pass == 0 && hi - lo > p_.max_occ) continue;
                 for (auto it = lo; it != hi; ++it) {
-                    const uint32_t gp = pos_[(size_t)(it - keys_.begin())];
-                    const int32_t c = (int32_t)(std::upper_bound(g_.contig_off.begin(), g_.contig_off.end(), (int64_t)gp) - g_.contig_off.begin()) - 1;
-                    votes.push_back(Vote{c, (int32_t)((int64_t)gp - g_.contig_off[(size_t)c] - st)});
+                    const size_t ix = (size_t)(it - keys_.begin()); const int32_t c = (int32_t)ctg_[ix];
+                    votes.push_back(Vote{c, (int32_t)((int64_t)pos_[ix] - g_.contig_off[(size_t)c] - st)});
                 }
             }
             if (!votes.empty()) break;

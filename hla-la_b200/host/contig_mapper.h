@@ -37,7 +37,8 @@ public:
 private:
     bool align(const uint8_t* read, int len, int32_t contig, int64_t diag, Placement& out) const;
     const FlatGraph& g_; MapperParams p_;
-    std::vector<uint64_t> keys_; std::vector<uint32_t> pos_;   // sorted by key; pos = offset into FlatGraph::contig_seq
+    std::vector<uint64_t> keys_; std::vector<uint32_t> pos_, ctg_;   // sorted by key; pos = offset into FlatGraph::contig_seq, ctg = its contig
+    std::vector<uint32_t> bucket_; int bucket_shift_ = 0;             // first index entry of every value of the key's top bits
 };
 
 // Paired FASTQ files (plain or gzip) -> the batch hlala_bam_read would return for their `bwa mem -a -M` BAM: pairs in byte order of their names, reads 2p / 2p+1
