@@ -1065,6 +1065,7 @@ int hlala_truth_evaluate(hlala_truth_t* t, int64_t n_pairs, const char* const* p
     try {
         const size_t cap = (size_t)a->max_columns;
         for (int64_t p = 0; p < n_pairs; p++) {
+            if (pair_names && !pair_names[p]) return fail(HLALA_E_ARG, "hlala_truth_evaluate: a null read name");
             const std::string id = pair_names ? std::string(pair_names[p]) : "r" + std::to_string(pair_index_base + p);
             const int32_t* lv[2] = {a->level + (size_t)(2 * p) * cap, a->level + (size_t)(2 * p + 1) * cap};
             const uint8_t* sc[2] = {a->schar + (size_t)(2 * p) * cap, a->schar + (size_t)(2 * p + 1) * cap};
