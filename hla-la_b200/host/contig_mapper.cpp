@@ -53,7 +53,7 @@ ContigMapper::ContigMapper(const FlatGraph& g, const MapperParams& p) : g_(g), p
 }
 
 // Banded affine-gap alignment of read[0..len) around `diag` (contig position of read base 0) on `contig`: any start and end in the read, a clipped end costs p_.clip.
-bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t diag, Placement& out) const {
+bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t diag, Placement& out, int force_band) const {
     const int64_t cb = g_.contig_off[(size_t)contig], clen = g_.contig_off[(size_t)contig + 1] - cb;
     const uint8_t* ref = g_.contig_seq.data() + cb;
     const int go = p_.gap_open + p_.gap_extend, ge = p_.gap_extend;
@@ -84,10 +84,10 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
     // cell (i, b): read base i against contig position j = diag + i + b - B. A narrow band first; the full one only if the narrow alignment leans on the band's edge.
     static thread_local std::vector<int32_t> M, E, F; static thread_local std::vector<uint8_t> tb, rcode;
     // contig codes of the widest window once (9 = beyond the contig: such cells stay unreachable)
-    const int BW = p_.band; rcode.resize((size_t)len + 2 * (size_t)BW);
+    const int BW = std::max(p_.band, force_band); rcode.resize((size_t)len + 2 * (size_t)BW);
     for (int64_t q = 0; q < (int64_t)rcode.size(); q++) { const int64_t j = diag - BW + q; rcode[(size_t)q] = (j >= 0 && j < clen) ? (uint8_t)code_of(ref[j]) : (uint8_t)9; }
-  for (int attempt = 0; attempt < 2; attempt++) {
-    const int B = attempt == 0 ? std::max(4, p_.band / 3) : p_.band, Wd = 2 * B + 1, Ws = Wd + 2; bool edge = false;   // rows carry one unreachable cell at either end
+  for (int attempt = force_band > 0 ? 1 : 0; attempt < 2; attempt++) {
+    const int B = force_band > 0 ? force_band : attempt == 0 ? std::max(4, p_.band / 3) : p_.band, Wd = 2 * B + 1, Ws = Wd + 2; bool edge = false;   // rows carry one unreachable cell at either end
     M.assign((size_t)2 * Ws, NEG); E.assign((size_t)2 * Ws, NEG); F.assign((size_t)2 * Ws, NEG);
     tb.assign((size_t)len * Wd, 0);   // bits 0-1: M came from 0 start, 1 M, 2 E, 3 F; bit 2: E extended; bit 3: F extended
     int best = NEG, best_i = -1, best_b = -1;
@@ -141,6 +141,15 @@ bool ContigMapper::align(const uint8_t* rd, int len, int32_t contig, int64_t dia
     return true;
   }
     return false;
+}
+
+bool ContigMapper::rescue(const std::string& seq, const Placement& mate, Placement& out) const {
+    const int len = (int)seq.size(); if (len < p_.min_score) return false;
+    const bool rev = !mate.reverse;                         // the mates of a pair lie on opposite strands
+    const std::string s = rev ? revcomp(seq) : seq;
+    std::vector<uint8_t> rd((size_t)len); for (int i = 0; i < len; i++) rd[(size_t)i] = (uint8_t)code_of((uint8_t)s[(size_t)i]);
+    out.reverse = rev;
+    return align(rd.data(), len, mate.contig, mate.pos, out, p_.rescue_window);
 }
 
 std::vector<Placement> ContigMapper::map_read(const std::string& seq) const {
@@ -239,9 +248,20 @@ void map_fastq_pairs(const FlatGraph& g, const std::string& fastq1, const std::s
     auto work = [&]() { for (;;) { const size_t a = next.fetch_add(64); if (a >= n) break; for (size_t i = a; i < std::min(n, a + 64); i++) for (int m = 0; m < 2; m++) hits[m][i] = mapper.map_read(r[m][i].seq); } };
     { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
     lap("reads placed");
+    std::atomic<int64_t> rescued(0);
+    {   // mate rescue for the pairs with exactly one placed mate
+        std::atomic<size_t> nx(0);
+        auto rw = [&]() { for (;;) { const size_t a = nx.fetch_add(256); if (a >= n) break; for (size_t i = a; i < std::min(n, a + 256); i++) {
+            const bool h0 = !hits[0][i].empty(), h1 = !hits[1][i].empty(); if (h0 == h1) continue;
+            const int m = h0 ? 1 : 0; Placement pl;
+            if (mapper.rescue(r[m][i].seq, hits[m ^ 1][i][0], pl)) { hits[m][i].push_back(std::move(pl)); rescued++; } } } };
+        std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(rw); for (auto& t : th) t.join();
+        lap("mates rescued");
+    }
     std::vector<size_t> order(n); std::iota(order.begin(), order.end(), (size_t)0);
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return r[0][a].name != r[0][b].name ? r[0][a].name < r[0][b].name : a < b; });
     out = BamBatch(); out.read_off.push_back(0); out.chain_off.push_back(0); out.cigar_off.push_back(0);
+    out.tlen_n = rescued.load();   // for FASTQ input hlala_bam_batch_stats' is_n reports the mates placed by rescue
     BamBatch::Sample& S = out.is_sample; S.read_off.push_back(0); S.chain_off.push_back(0); S.cigar_off.push_back(0);
     out.names_seen = (int64_t)n;
     for (size_t oi = 0; oi < n; oi++) {

@@ -22,6 +22,7 @@ struct MapperParams {
     int max_occ = 4000;                           // k-mers with more placements are skipped (used again only if nothing else votes)
     int min_votes = 2, max_candidates = 64, band = 24;
     int match = 1, mismatch = 4, gap_open = 6, gap_extend = 1, clip = 5, min_score = 30;
+    int rescue_window = 800;
 };
 
 struct Placement { int32_t contig = 0, pos = 0; bool reverse = false; int32_t score = 0; std::vector<uint32_t> cigar; };   // cigar: BAM packed ops, S for clipped bases
@@ -31,11 +32,14 @@ public:
     ContigMapper(const FlatGraph& g, const MapperParams& p = MapperParams());
     // all placements of one read (sequence as sequenced), best first; ties keep (strand, contig, position) order
     std::vector<Placement> map_read(const std::string& seq) const;
+    // bwa mem's mate rescue (mem_matesw): a read without a placement of its own is aligned, on the opposite strand, to the stretch of the contig within
+    // `rescue_window` bases of its mate's primary placement
+    bool rescue(const std::string& seq, const Placement& mate, Placement& out) const;
     const MapperParams& params() const { return p_; }
     int64_t index_entries() const { return (int64_t)keys_.size(); }
 
 private:
-    bool align(const uint8_t* read, int len, int32_t contig, int64_t diag, Placement& out) const;
+    bool align(const uint8_t* read, int len, int32_t contig, int64_t diag, Placement& out, int force_band = 0) const;
     const FlatGraph& g_; MapperParams p_;
     std::vector<uint64_t> keys_; std::vector<uint32_t> pos_, ctg_;   // sorted by key; pos = offset into FlatGraph::contig_seq, ctg = its contig
     std::vector<uint32_t> bucket_; int bucket_shift_ = 0;             // first index entry of every value of the key's top bits

@@ -354,7 +354,7 @@ void hlala_bam_batch_free(hlala_bam_batch_t* b);
 /* FASTQ input without bwa: stands where the reference runs BWAmapper::map (`bwa mem -a -M` against <PRG>/mapping_PRGonly/referenceGenome.fa,
  * mapper/bwa/BWAmapper.cpp; HLA-LA.cpp:742-779) and reads the BAM back. Every read is placed on the PRG's linear contigs (sampled k-mer votes per contig and
  * diagonal, banded affine-gap alignment with bwa mem's default scores: 1 / 4 / 6+1 / clip 5 / minimum 30); all placements are kept like `-a` (the 64 best-scoring ones of a read at most: what the pair stage's second tier holds), the best one as the
- * primary record (protoSeeds.cpp:252-314), its score in the place of the AS tag (processBAM.cpp:4314-4336). The result is the batch hlala_bam_read would return
+ * primary record (protoSeeds.cpp:252-314), its score in the place of the AS tag (processBAM.cpp:4314-4336); a mate without a placement of its own is looked for next to its mate's (mate rescue; hlala_bam_batch_stats reports their number as is_n). The result is the batch hlala_bam_read would return
  * (pairs in name order, SEQ / QUAL in the primary's orientation, pairs with an unplaced mate dropped and counted) and feeds hlala_align_pairs, hlala_bam_insert_size
  * and the typing calls unchanged. Host code. Not bwa: there is no oracle for it; its quality is measured the way the reference's testPRGMapping does (bases of
  * simulated reads on their true level after the alignment path, tests/test_zz_fastq_mapper.py). Files may be gzip-compressed. */

@@ -241,3 +241,30 @@ def test_last_bit_fixture_on_the_gpu(tmp_path):
     P = H.Product(d); P.to_gpu(0)
     _same_as_gold(P.pairs(b, 100.0, 10.0, 640, want_levels=False), gold)
     P.close()
+
+
+def test_mate_rescue(dataset, tmp_path):
+    """bwa mem's mate rescue: a mate without a 19-mer of its own (a mismatch every 15 bases) is aligned, on the opposite strand, within 800 bases of its mate's primary
+    placement; a mate that matches nothing there stays unplaced and the pair is dropped"""
+    d, _b, _mu, _sd = dataset("small")
+    P = H.Product(d); seq = P.array("contig_seq"); off = P.array("contig_off")
+    c0 = bytes(seq[off[0]:off[1]]).decode()
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    rc = lambda s: "".join(comp[c] for c in reversed(s))
+    other = lambda ch: "ACGT"[("ACGT".index(ch) + 2) % 4] if ch in "ACGT" else ch
+    noisy = "".join(other(ch) if i % 15 == 7 else ch for i, ch in enumerate(c0[1500:1600]))      # 7 mismatches: score 93 - 28 = 65
+    rng = np.random.RandomState(3); junk = "".join("ACGT"[i] for i in rng.randint(0, 4, 100))
+    f1, f2 = str(tmp_path / "a_1.fq"), str(tmp_path / "a_2.fq")
+    open(f1, "w").write("@down\n%s\n+\n%s\n@up\n%s\n+\n%s\n@none\n%s\n+\n%s\n" % (c0[1200:1300], "I" * 100, rc(noisy), "I" * 100, c0[3000:3100], "I" * 100))
+    open(f2, "w").write("@down\n%s\n+\n%s\n@up\n%s\n+\n%s\n@none\n%s\n+\n%s\n" % (rc(noisy), "I" * 100, c0[1200:1300], "I" * 100, junk, "I" * 100))
+    mb, names, cnt = P.fastq_map(f1, f2)
+    assert names == ["down", "up"] and cnt["incomplete"] == 1 and cnt["is_n"] == 2          # two mates placed by rescue
+    for p_, (r_noisy, r_clean) in enumerate(((1, 0), (0, 1))):
+        cn, cc = mb["chain_off"][2 * p_ + r_noisy], mb["chain_off"][2 * p_ + r_clean]
+        assert mb["chain_off"][2 * p_ + r_noisy + 1] - cn == 1
+        assert mb["chain_pos"][cn] == 1500 and mb["chain_as"][cn] == 65 and list(mb["cigar"][mb["cigar_off"][cn]:mb["cigar_off"][cn + 1]]) == [100 << 4]
+        assert mb["chain_flag"][cn] & 0x10 and not mb["chain_flag"][cn] & 0x100 and not mb["chain_flag"][cc] & 0x10 and mb["chain_pos"][cc] == 1200
+        s = mb["read_off"][2 * p_ + r_noisy]; assert bytes(mb["bases"][s:s + 100]).decode() == noisy       # stored in the orientation of its placement
+    aln = H.quiet(H.Oracle(d).pairs, mb, 200.0, 50.0, 640)
+    assert (aln["n_cols"] >= 100).all()
+    P.close()
